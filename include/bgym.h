@@ -1,0 +1,323 @@
+/* bgym.h — C-ABI of the B200-native batched Balatro environment step path.
+ *
+ * This is the drop-in boundary for the hot path of cassiusfive/balatro-gym:
+ *   BalatroEnv.reset            balatro_gym/balatro_env_2.py:505-558   -> bgym_reset
+ *   BalatroEnv.step             balatro_gym/balatro_env_2.py:616-1064  -> bgym_step
+ *   BalatroEnv._get_action_mask balatro_gym/balatro_env_2.py:1426-1471 -> bgym_action_mask
+ *   BalatroEnv._get_observation balatro_gym/balatro_env_2.py:1473-1541 -> BgymObs (written by reset/step)
+ *   _classify_hand + CardAdapter.to_scoring_format + UnifiedScorer.score_hand
+ *       balatro_gym/balatro_game.py:40-93, balatro_env_2.py:287-325,
+ *       balatro_gym/unified_scoring.py:111-299                         -> bgym_score_hands
+ *
+ * The reference has no FFI of its own (it is pure Python behind the Gymnasium
+ * Env protocol); INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - All pointers are plain borrowed pointers; the library never allocates or
+ *     frees caller memory.  Entry points named *_host take HOST pointers and do
+ *     their own staging through a BgymVec handle; all others take DEVICE pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     Device entry points are asynchronous and stream ordered.
+ *   - Return value: 0 on success, >0 a cudaError_t, <0 an argument error
+ *     (BGYM_E_*).  bgym_last_error() gives a thread-local message.
+ *   - Records are fixed-layout little-endian structs (below); arrays of records
+ *     are dense AoS: record i starts at base + i * sizeof(record).
+ */
+#ifndef BGYM_H
+#define BGYM_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGYM_ABI_VERSION 1
+
+/* ---- sizes ------------------------------------------------------------- */
+#define BGYM_STATE_BYTES 320
+#define BGYM_OBS_BYTES   240
+#define BGYM_INFO_BYTES  32
+#define BGYM_DRAWS_BYTES 256
+#define BGYM_NUM_ACTIONS 60
+#define BGYM_NUM_HAND_TYPES 12
+#define BGYM_MAX_HAND 8
+#define BGYM_DECK_SLOTS 52
+
+/* ---- enums (values follow the reference) -------------------------------- */
+/* constants.py:34-39 */
+enum { BGYM_PHASE_PLAY = 0, BGYM_PHASE_SHOP = 1, BGYM_PHASE_BLIND_SELECT = 2, BGYM_PHASE_PACK_OPEN = 3 };
+/* constants.py:43-88 */
+enum {
+  BGYM_A_PLAY_HAND = 0, BGYM_A_DISCARD = 1, BGYM_A_SELECT_BASE = 2, BGYM_A_USE_CONS_BASE = 10,
+  BGYM_A_SHOP_BUY_BASE = 20, BGYM_A_SHOP_REROLL = 30, BGYM_A_SHOP_END = 31,
+  BGYM_A_SELL_JOKER_BASE = 32, BGYM_A_SELL_CONS_BASE = 37, BGYM_A_SELECT_BLIND_BASE = 45,
+  BGYM_A_SKIP_BLIND = 48, BGYM_A_PACK_BASE = 50, BGYM_A_SKIP_PACK = 55
+};
+/* scoring_engine.py:12-24 */
+enum {
+  BGYM_HT_HIGH_CARD = 0, BGYM_HT_ONE_PAIR, BGYM_HT_TWO_PAIR, BGYM_HT_THREE_KIND, BGYM_HT_STRAIGHT,
+  BGYM_HT_FLUSH, BGYM_HT_FULL_HOUSE, BGYM_HT_FOUR_KIND, BGYM_HT_STRAIGHT_FLUSH,
+  BGYM_HT_FIVE_KIND, BGYM_HT_FLUSH_HOUSE, BGYM_HT_FLUSH_FIVE
+};
+/* cards.py:63-91 — card16 = code(6b) | enhancement<<6 (4b) | edition<<10 (3b) | seal<<13 (3b)
+ * code = (rank-2)*4 + suit (cards.py:103), suit: clubs 0 diamonds 1 hearts 2 spades 3 */
+enum { BGYM_ENH_NONE = 0, BGYM_ENH_BONUS, BGYM_ENH_MULT, BGYM_ENH_WILD, BGYM_ENH_GLASS, BGYM_ENH_STEEL,
+       BGYM_ENH_STONE, BGYM_ENH_GOLD, BGYM_ENH_LUCKY };
+enum { BGYM_ED_NONE = 0, BGYM_ED_FOIL, BGYM_ED_HOLO, BGYM_ED_POLY, BGYM_ED_NEGATIVE };
+enum { BGYM_SEAL_NONE = 0, BGYM_SEAL_GOLD, BGYM_SEAL_RED, BGYM_SEAL_BLUE, BGYM_SEAL_PURPLE };
+/* shop.py:17-21 */
+enum { BGYM_ITEM_PACK = 1, BGYM_ITEM_CARD = 2, BGYM_ITEM_JOKER = 3, BGYM_ITEM_VOUCHER = 4 };
+/* shop item_id for packs / vouchers (shop.py:27-35 key order) */
+enum { BGYM_PACK_STANDARD = 0, BGYM_PACK_JOKER = 1, BGYM_PACK_TAROT = 2, BGYM_PACK_PLANET = 3, BGYM_PACK_SPECTRAL = 4 };
+enum { BGYM_VOUCHER_MAGIC_TRICK = 0, BGYM_VOUCHER_MINIMALIST = 1 };
+
+/* consumable ids = the reference's observation id map (balatro_env_2.py:1545-1567):
+ *   tarots 1..22, planets 30..41, spectrals 50..67.  Tarots created by The Emperor carry
+ *   enum-style names ('THE_FOOL', consumables.py:172) that resolve on use but observe as 0:
+ *   they are stored as 100 + tarot id. */
+#define BGYM_CONS_TAROT_BASE     1
+#define BGYM_CONS_PLANET_BASE    30
+#define BGYM_CONS_SPECTRAL_BASE  50
+#define BGYM_CONS_ENUMSTYLE_BASE 100
+
+/* error codes in BgymInfo.error_code */
+enum {
+  BGYM_ERR_NONE = 0,
+  BGYM_ERR_INVALID_ACTION = 1,   /* masked action: reward -1.0, state unchanged (balatro_env_2.py:626-627) */
+  BGYM_ERR_BOSS_RESTRICTION = 2, /* can_play_hand false: reward -1.0 (balatro_env_2.py:677-680) */
+  BGYM_ERR_CONSUMABLE_FAILED = 3,/* use_consumable success False: reward -1.0 (balatro_env_2.py:1167-1169) */
+  BGYM_ERR_SHOP = 4,             /* shop.step error (joker slots full, reroll unaffordable): reward -1.0 */
+  BGYM_ERR_REF_EXCEPTION = 5,    /* the reference raises here; we return the
+                                    SafeBalatroEnv convention: reward -100.0, terminated, state unchanged
+                                    (train_balatro_fixed.py:262-269) */
+  BGYM_ERR_UNSUPPORTED = 6       /* consumable outside the supported set (spectrals that rebuild the deck) */
+};
+/* BgymInfo.flags */
+enum { BGYM_F_BEAT_BLIND = 1, BGYM_F_FAILED = 2, BGYM_F_GUARD_TERMINATED = 4, BGYM_F_PLAYED = 8,
+       BGYM_F_AUTORESET_DONE = 16, BGYM_F_SHOP_DONE = 32 };
+
+/* flags argument of bgym_reset / bgym_step */
+enum {
+  BGYM_FLAG_AUTORESET = 1,  /* step: a terminated env is re-initialised in place (native Philox shuffle)
+                               and the returned observation is the first of the new episode */
+  BGYM_FLAG_NO_OBS = 2      /* skip observation emission (obs may be NULL) */
+};
+/* flags argument of bgym_score_hands */
+enum {
+  BGYM_SCORE_TABLE_NAMES = 1 /* hand names as complete_joker_effects.py:64-80 expects ('Pair',
+                                'Three of a Kind', 'Four of a Kind'); default = the env's own names
+                                ('One Pair', 'Three Kind', 'Four Kind', balatro_env_2.py:674) */
+};
+
+#define BGYM_E_ARG     (-1)
+#define BGYM_E_NODEV   (-2)
+#define BGYM_E_ALIGN   (-3)
+
+/* ---- per-env state record (320 B, 16-byte aligned) ------------------------
+ * Restates UnifiedGameState (balatro_env_2.py:166-211) + BalatroGame (balatro_game.py:16-28)
+ * + ScoreEngine levels/counts (scoring_engine.py:65-69) + BossBlindManager.blind_state
+ * (boss_blinds.py:311-319) + Shop inventory (shop.py:96-148).  SURVEY.md Appendix D. */
+typedef struct BgymState {
+  /* hot block, bytes 0..127 */
+  uint8_t  hand[8];            /*   0 hand_indexes: deck index per hand slot, 0xFF = empty          */
+  uint8_t  hand_code[8];       /*   8 cache: card code of deck[hand[i]], 0xFF = none                */
+  uint8_t  hand_n;             /*  16 len(hand_indexes)                                             */
+  uint8_t  hand_size;          /*  17 state.hand_size / game.hand_size                              */
+  uint8_t  sel_n;              /*  18 len(selected_cards)                                           */
+  uint8_t  highlight_mask;     /*  19 game.highlighted_indexes as a bit set over hand slots         */
+  uint32_t sel_order;          /*  20 selected_cards, ordered: nibble k = slot of k-th selection    */
+  uint8_t  face_down_mask;     /*  24 face_down_cards as a bit set over hand slots                  */
+  uint8_t  phase;              /*  25                                                               */
+  uint8_t  round;              /*  26 1 small, 2 big, 3 boss                                        */
+  uint8_t  boss_type;          /*  27 active BossBlindType (boss_blinds.py:18-47), 0 = none         */
+  uint8_t  hands_left;         /*  28                                                               */
+  uint8_t  discards_left;      /*  29                                                               */
+  uint8_t  joker_n;            /*  30                                                               */
+  uint8_t  cons_n;             /*  31                                                               */
+  uint8_t  joker_slots;        /*  32                                                               */
+  uint8_t  cons_slots;         /*  33                                                               */
+  uint8_t  n_magic_trick;      /*  34 vouchers.count('Magic Trick')                                 */
+  uint8_t  n_minimalist;       /*  35 vouchers.count('Minimalist')                                  */
+  int16_t  ante;               /*  36                                                               */
+  int16_t  jokers_sold;        /*  38                                                               */
+  int32_t  money;              /*  40                                                               */
+  int32_t  chips_needed;       /*  44                                                               */
+  int64_t  round_chips;        /*  48 round_chips_scored                                            */
+  int64_t  chips_scored;       /*  56                                                               */
+  int32_t  best_hand;          /*  64 best_hand_this_ante (saturating)                              */
+  int32_t  hands_played_total; /*  68                                                               */
+  int16_t  hands_played_ante;  /*  72                                                               */
+  uint8_t  boss_flags;         /*  74 bit0 = blind_state['first_hand']                              */
+  uint8_t  boss_cards_required;/*  75 blind_state['cards_required'] (The Verdant)                   */
+  uint16_t boss_played_types;  /*  76 blind_state['played_hand_types'] as a bit set over HandType   */
+  uint8_t  boss_hands_played;  /*  78 blind_state['hands_played']                                   */
+  uint8_t  deck_n;             /*  79 len(deck)                                                     */
+  uint64_t boss_played_cards;  /*  80 blind_state['played_cards'] as a bit set over deck indices    */
+  uint8_t  joker_id[8];        /*  88 JOKER_LIBRARY ids (jokers.py:11-162), 0 = empty               */
+  uint8_t  cons_id[8];         /*  96 consumable ids, 0 = empty                                     */
+  uint8_t  hand_level[12];     /* 104 state.hand_levels (uncapped); engine level = min(level, 15)   */
+  int32_t  shop_reroll_state;  /* 116 state.shop_reroll_cost (stale copy used by the mask)          */
+  uint32_t rng_seed;           /* 120 native mode: Philox key word 0                                */
+  uint32_t rng_ctr;            /* 124 native mode: Philox counter (blocks consumed)                 */
+  /* deck block, bytes 128..255 */
+  uint16_t deck[52];           /* 128 card16 per deck index                                         */
+  uint16_t hand_play_count[12];/* 232 engine.hand_play_counts                                       */
+  /* shop block, bytes 256..319 */
+  uint8_t  item_type[9];       /* 256 shop.inventory[i].item_type                                   */
+  uint8_t  item_id[9];         /* 265 joker id / pack kind / voucher kind / card int                */
+  uint8_t  n_items;            /* 274                                                               */
+  uint8_t  _pad0;              /* 275                                                               */
+  int32_t  item_cost[9];       /* 276                                                               */
+  int32_t  reroll_cost;        /* 312 shop.reroll_cost (grows x1.35 per reroll)                     */
+  uint32_t ep_len;             /* 316 steps taken in the current episode                            */
+} BgymState;
+
+/* ---- observation record (240 B) ---------------------------------------------
+ * The 31 keys the reference actually emits (balatro_env_2.py:1488-1531), same dtypes
+ * except selected_cards / face_down_cards (int8 here, platform int there). */
+typedef struct BgymObs {
+  int8_t   hand[8];             /*   0 card code or -1                  */
+  int8_t   selected_cards[8];   /*   8                                  */
+  int8_t   face_down_cards[8];  /*  16                                  */
+  int64_t  chips_scored;        /*  24                                  */
+  int32_t  round_chips_scored;  /*  32                                  */
+  float    progress_ratio;      /*  36 float32(min(2.0, round/max(1,needed))) */
+  int32_t  mult;                /*  40 constant 1                       */
+  int32_t  chips_needed;        /*  44                                  */
+  int32_t  money;               /*  48                                  */
+  int32_t  hands_played;        /*  52                                  */
+  int32_t  best_hand_this_ante; /*  56                                  */
+  int16_t  ante;                /*  60                                  */
+  int16_t  shop_rerolls;        /*  62 state.shop_reroll_cost           */
+  int16_t  joker_ids[10];       /*  64                                  */
+  int16_t  consumables[5];      /*  84                                  */
+  int16_t  shop_items[10];      /*  94                                  */
+  int16_t  shop_costs[10];      /* 114                                  */
+  int8_t   hand_levels[12];     /* 134                                  */
+  int8_t   hand_size;           /* 146 len(hand_indexes)                */
+  int8_t   deck_size;           /* 147                                  */
+  int8_t   round;               /* 148                                  */
+  int8_t   hands_left;          /* 149                                  */
+  int8_t   discards_left;       /* 150                                  */
+  int8_t   joker_count;         /* 151                                  */
+  int8_t   joker_slots;         /* 152                                  */
+  int8_t   consumable_count;    /* 153                                  */
+  int8_t   consumable_slots;    /* 154                                  */
+  int8_t   phase;               /* 155                                  */
+  int8_t   boss_blind_active;   /* 156                                  */
+  int8_t   boss_blind_type;     /* 157                                  */
+  uint8_t  _pad0[2];            /* 158                                  */
+  uint64_t action_mask_bits;    /* 160 bit a = action a legal (extra: the mask as one word) */
+  int8_t   action_mask[60];     /* 168                                  */
+  uint8_t  _pad1[12];           /* 228                                  */
+} BgymObs;
+
+/* ---- per-step info record (32 B) --------------------------------------------
+ * Fixed-width restatement of the numeric entries of the reference's info dict
+ * (balatro_env_2.py:895-925). */
+typedef struct BgymInfo {
+  int64_t final_score;  /*  0 info['final_score'] (0 when no hand was scored)          */
+  double  x_mult;       /*  8 score_breakdown['final_x_mult']                          */
+  int32_t chips;        /* 16 score_breakdown['final_chips']                           */
+  int32_t mult;         /* 20 score_breakdown['final_mult']                            */
+  int8_t  hand_type;    /* 24 info['hand_type'] or -1                                  */
+  uint8_t error_code;   /* 25 BGYM_ERR_*                                               */
+  uint8_t flags;        /* 26 BGYM_F_*                                                 */
+  uint8_t cards_played; /* 27 info['cards_played']                                     */
+  int32_t base_score;   /* 28 UnifiedScorer result before steel/boss/retrigger         */
+} BgymInfo;
+
+/* ---- replay draws (256 B per env per step) -----------------------------------
+ * Replay mode: the random draws the reference made during the same step, recorded
+ * on the host (oracle/reftap.py), consumed by the kernel in order instead of Philox.
+ *   u[]: results of random()/uniform(0,1) calls, in call order
+ *   k[]: results of randint/choice/sample calls as 0-based indices into the
+ *        population (sample contributes one entry per element drawn) */
+typedef struct BgymDraws {
+  double  u[24];
+  uint8_t k[32];
+  uint8_t n_u, n_k;    /* number of valid entries (for validation) */
+  uint8_t _pad[30];
+} BgymDraws;
+
+/* ---- score_hands context (16 B per hand) -------------------------------------
+ * The game_state entries the joker tables read (complete_joker_effects.py:39-50). */
+typedef struct BgymScoreCtx {
+  uint8_t hands_left;      /* Acrobat                                */
+  uint8_t discards_left;   /* Mystic Summit, Banner                  */
+  uint8_t deck_len;        /* Blue Joker: 2 * len(deck)              */
+  uint8_t misprint[5];     /* replay: randint(0,23) result for the i-th Misprint joker */
+  uint8_t bloodstone_bits; /* replay: bit c = (random() < 0.5) for scoring card c, first Bloodstone joker */
+  uint8_t use_replay;      /* 0 = native Philox draws keyed by (seed, hand index), 1 = use the fields above */
+  uint8_t _pad[6];
+} BgymScoreCtx;
+
+/* ---- device entry points ------------------------------------------------------ */
+int bgym_abi_version(void);
+const char* bgym_last_error(void);
+int bgym_device_count(void);
+
+/* reset: for every env i with reset_mask == NULL || reset_mask[i] != 0 build a fresh episode
+ * (balatro_env_2.py:505-558).  seeds[i] keys the native Philox stream.  decks52 != NULL
+ * (n x 52 card codes) replays a supplied permutation (the reference's shuffle stream);
+ * NULL = native Fisher-Yates from Philox.  obs may be NULL with BGYM_FLAG_NO_OBS. */
+int bgym_reset(BgymState* state, BgymObs* obs, const uint8_t* reset_mask, const uint32_t* seeds,
+               const uint8_t* decks52, int64_t n, int flags, void* stream);
+
+/* step: one BalatroEnv.step per env (balatro_env_2.py:616-1064, 1174-1392).
+ * draws == NULL -> native Philox mode.  info may be NULL. truncated is always 0. */
+int bgym_step(BgymState* state, const int32_t* actions, const BgymDraws* draws, BgymObs* obs,
+              double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
+              int64_t n, int flags, void* stream);
+
+/* action mask as one 64-bit word per env (balatro_env_2.py:1426-1471) */
+int bgym_action_mask(const BgymState* state, uint64_t* mask, int64_t n, void* stream);
+
+/* uniform random legal action per env from BgymObs.action_mask_bits (the policy the
+ * reference benchmarks are driven with: random legal actions from obs['action_mask']) */
+int bgym_sample_actions(const BgymObs* obs, int32_t* actions, uint32_t seed, uint64_t step,
+                        int64_t n, void* stream);
+
+/* hand scoring: classify cards (balatro_game.py:40-93), per-card chip values
+ * (balatro_env_2.py:287-325, cards.py:262-267), joker pipeline (unified_scoring.py:111-299).
+ *   cards8  n x 8 card codes (0..51), entries >= n_cards[i] ignored
+ *   mods8   n x 8 (enhancement | edition<<4 | seal<<8), NULL = no modifiers
+ *   n_cards n, 1..8 (NULL = 5)
+ *   jokers8 n x 8 joker ids, 0 = empty (NULL = no jokers)
+ *   levels12 n x 12 hand levels (NULL = all 1)
+ *   ctx     n (NULL = hands_left 4, discards_left 3, deck_len 52, native draws) */
+int bgym_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8_t* n_cards,
+                     const uint8_t* jokers8, const uint8_t* levels12, const BgymScoreCtx* ctx,
+                     uint8_t* hand_type, int32_t* chips, int32_t* mult, double* x_mult,
+                     int64_t* score, int32_t* money, uint32_t seed, int64_t n, int flags, void* stream);
+
+/* per-slab episode statistics: folds (reward, terminated) of one step into
+ * stats[0]=episodes, [1]=sum return, [2]=sum length, [3]=steps, [4]=sum reward.
+ * ret_acc / len_acc are n-sized per-env accumulators owned by the caller. */
+int bgym_episode_stats(const double* reward, const uint8_t* terminated, double* ret_acc,
+                       uint32_t* len_acc, double* stats, int64_t n, void* stream);
+
+/* ---- host-buffer entry points (what a non-torch caller binds) ------------------ */
+typedef struct BgymVec BgymVec;
+/* allocates device state/obs/outputs and pinned staging for n envs on `device` */
+int bgym_vec_create(BgymVec** out, int64_t n, int device);
+int bgym_vec_destroy(BgymVec* v);
+/* host pointers; copies are done inside on the handle's stream and the call returns
+ * after the results are in the host buffers */
+int bgym_vec_reset_host(BgymVec* v, const uint32_t* seeds, const uint8_t* decks52, BgymObs* obs_out);
+int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draws, BgymObs* obs_out,
+                       double* reward_out, uint8_t* terminated_out, uint8_t* truncated_out,
+                       BgymInfo* info_out, int flags);
+/* raw device pointers of the handle (for zero-copy consumers) */
+int bgym_vec_pointers(BgymVec* v, void** state, void** obs, void** reward, void** terminated);
+/* copy state records to / from host (checkpointing: save_state/load_state,
+ * balatro_env_2.py:1575-1615) */
+int bgym_vec_get_state(BgymVec* v, BgymState* host_out);
+int bgym_vec_set_state(BgymVec* v, const BgymState* host_in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGYM_H */

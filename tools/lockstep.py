@@ -1,0 +1,126 @@
+#!/usr/bin/env python
+"""Lock-step differential run: unmodified reference (oracle/refenv.py) vs the C oracle.
+
+Usage: python tools/lockstep.py --episodes 200 --config c1|c3|c4 [--seed0 1]
+Each step: the reference steps first (all RNG tapped), the recorded draws are replayed into the
+C oracle, then state record, observation record, reward, terminated and info numerics are compared.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import coracle  # noqa: E402
+from oracle.refenv import RefEnv, state_diff, obs_diff  # noqa: E402
+from balatro_gym_b200 import layout as L  # noqa: E402
+
+
+def inject_c3(ref: RefEnv, ov: coracle.OracleVec, rng: np.random.Generator, boss=True):
+    """SURVEY §8(d) C3 state generator, applied identically to both sides."""
+    costs = {j.id: j.base_cost for j in ref.R.jokers.JOKER_LIBRARY}
+    pool = [i for i in range(1, 151) if costs[i] > 0]
+    jk = rng.choice(pool, size=5, replace=False)
+    ref.inject_jokers([int(x) for x in jk])
+    s = ov.state[0]
+    s["joker_id"][:5] = jk
+    s["joker_n"] = 5
+    for idx in range(52):
+        enh = int(rng.integers(1, 9)) if rng.random() < 0.25 else 0
+        ed = int(rng.integers(1, 4)) if rng.random() < 0.1 else 0
+        seal = int(rng.integers(1, 5)) if rng.random() < 0.1 else 0
+        if enh or ed or seal:
+            ref.inject_card_mod(idx, enh, ed, seal)
+            s["deck"][idx] = L.card16(int(s["deck"][idx]) & 63, enh, ed, seal)
+
+
+def run(args):
+    rng = np.random.default_rng(args.seed0)
+    ref = RefEnv(seed=1)
+    ov = coracle.OracleVec(1)
+    n_steps = 0
+    n_mismatch = 0
+    t0 = time.time()
+    hist = np.zeros(60, dtype=np.int64)
+    for ep in range(args.episodes):
+        seed = args.seed0 + ep
+        obs, _ = ref.reset(seed)
+        ov.reset([seed], decks52=ref.deck_codes()[None, :])
+        if args.config in ("c3", "c4"):
+            inject_c3(ref, ov, rng)
+        first = True
+        for t in range(args.max_steps):
+            legal = ref.legal_actions()
+            if args.config == "c1" and first:
+                a = 45
+            elif args.config == "c3" and first:
+                a = 47
+            else:
+                a = int(rng.choice(legal))
+                if args.invalid and rng.random() < 0.02:
+                    a = int(rng.integers(0, 60))
+            first = False
+            hist[a] += 1
+            try:
+                obs, r, term, trunc, info = ref.step(a)
+                exc = None
+            except Exception as e:  # the reference raises on some consumables
+                exc = e
+            draws = ref.step_draws().reshape(1)
+            ov.step([a], draws=draws)
+            n_steps += 1
+            if isinstance(exc, OverflowError) and 'int16' in str(exc):
+                break  # numpy-2-only failure of the reference's obs cast (pinned numpy 1.26 wraps): stop episode
+            if exc is not None:
+                ok = ov.info[0]["error_code"] == L.ERR_REF_EXCEPTION and ov.terminated[0] == 1 and ov.reward[0] == -100.0
+                if not ok:
+                    print("EXC mismatch", ep, t, a, repr(exc), ov.info[0])
+                    n_mismatch += 1
+                break
+            rs = ref.extract_state()
+            d = state_diff(rs, ov.state[0])
+            od = obs_diff(RefEnv.obs_record(obs), ov.obs[0])
+            # reward is bit-exact except the ante>3 branch, which goes through np.log10 (SVML on AVX512
+            # hosts, 1 ulp off glibc on ~1.7% of arguments): compare that branch to 1e-13 relative
+            r_ok = float(r) == float(ov.reward[0]) or (
+                rs['ante'] > 3 and 'final_score' in info and abs(float(r) - float(ov.reward[0])) <= 1e-13 * abs(float(r)))
+            bad = bool(d) or bool(od) or not r_ok or bool(term) != bool(ov.terminated[0])
+            if 'final_score' in info:
+                bad |= int(info['final_score']) != int(ov.info[0]['final_score'])
+                bad |= int(info['hand_type']) != int(ov.info[0]['hand_type'])
+                bad |= int(info['score_breakdown']['final_chips']) != int(ov.info[0]['chips'])
+                bad |= int(info['score_breakdown']['final_mult']) != int(ov.info[0]['mult'])
+            if ('error' in info) != (ov.info[0]['error_code'] != 0):
+                bad = True
+            nu, nk = int(draws[0]['n_u']), int(draws[0]['n_k'])
+            if bad:
+                n_mismatch += 1
+                print(f"MISMATCH ep={ep} seed={seed} t={t} action={a} reward ref={r} or={ov.reward[0]} term={term}/{ov.terminated[0]}")
+                print("  info", {k: v for k, v in info.items() if k not in ('score_breakdown', 'reward_breakdown')}, ov.info[0])
+                print("  state diff", d)
+                print("  obs diff", od)
+                print("  draws", nu, nk)
+                if n_mismatch > args.max_mismatch:
+                    return n_steps, n_mismatch
+                break
+            if term:
+                break
+    dt = time.time() - t0
+    print(f"{n_steps} steps, {args.episodes} episodes, {n_mismatch} mismatches, {n_steps/dt:.0f} steps/s")
+    print("action histogram:", {i: int(c) for i, c in enumerate(hist) if c})
+    return n_steps, n_mismatch
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--episodes", type=int, default=50)
+    ap.add_argument("--config", default="c1")
+    ap.add_argument("--seed0", type=int, default=1)
+    ap.add_argument("--max-steps", type=int, default=2000)
+    ap.add_argument("--max-mismatch", type=int, default=5)
+    ap.add_argument("--invalid", action="store_true")
+    a = ap.parse_args()
+    _, bad = run(a)
+    sys.exit(1 if bad else 0)
