@@ -1,0 +1,26 @@
+"""balatro_gym_b200 — B200-native batched Balatro environment (drop-in for the step path of
+cassiusfive/balatro-gym).  Public surface:
+
+    BalatroVecEnv      vector-env entry point (device-resident state, sm_100a kernels)
+    BalatroEnv         Gymnasium facade over one env; make("BalatroGym-v0")
+    score_hands        batched hand scoring microkernel
+    build              compile the CUDA library in-tree
+"""
+from . import layout
+from ._lib import build, load, BgymError, SO_PATH
+
+__all__ = ["BalatroVecEnv", "BalatroEnv", "make", "make_balatro_env", "score_hands", "build", "load",
+           "BgymError", "layout", "SO_PATH"]
+
+
+def __getattr__(name):  # lazy: importing the package must not need torch/CUDA
+    if name == "BalatroVecEnv":
+        from .vec_env import BalatroVecEnv
+        return BalatroVecEnv
+    if name in ("BalatroEnv", "make", "make_balatro_env", "register_envs", "reference_deck"):
+        from . import env
+        return getattr(env, name)
+    if name == "score_hands":
+        from .score import score_hands
+        return score_hands
+    raise AttributeError(name)

@@ -1,0 +1,109 @@
+"""ctypes binding of the C-ABI shared library (include/bgym.h -> libbgym.so).
+
+The library is built in-tree by `build()` (nvcc, sm_100a).  There is NO fallback: if the
+library is missing or a CUDA device is absent, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+from . import layout as L
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_PKG)
+SO_PATH = os.path.join(_PKG, "libbgym.so")
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("bgym_kernels.cu", "bgym_env.cuh", "bgym_device.cuh")]
+HEADERS = [os.path.join(_REPO, "include", f) for f in ("bgym.h", "bgym_tables.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              # Python-float semantics: no fused multiply-add contraction anywhere on the path
+              "-fmad=false", "-shared", "-Xcompiler", "-fPIC"]
+
+_lib = None
+
+
+class BgymError(RuntimeError):
+    pass
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/bgym_kernels.cu for sm_100a into balatro_gym_b200/libbgym.so (in-tree)."""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise BgymError("nvcc not found: cannot build libbgym.so")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, SOURCES[0]]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise BgymError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return SO_PATH
+
+
+_vp, _i64, _i32, _u32, _u64 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint64
+
+# every symbol include/bgym.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "bgym_abi_version": (_i32, []),
+    "bgym_last_error": (C.c_char_p, []),
+    "bgym_device_count": (_i32, []),
+    "bgym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bgym_action_mask": (_i32, [_vp, _vp, _i64, _vp]),
+    "bgym_sample_actions": (_i32, [_vp, _vp, _u32, _u64, _i64, _vp]),
+    "bgym_score_hands": (_i32, [_vp] * 12 + [_u32, _i64, _i32, _vp]),
+    "bgym_episode_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "bgym_vec_create": (_i32, [C.POINTER(_vp), _i64, _i32]),
+    "bgym_vec_destroy": (_i32, [_vp]),
+    "bgym_vec_reset_host": (_i32, [_vp, _vp, _vp, _vp]),
+    "bgym_vec_step_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "bgym_vec_pointers": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "bgym_vec_get_state": (_i32, [_vp, _vp]),
+    "bgym_vec_set_state": (_i32, [_vp, _vp]),
+}
+
+
+def load():
+    """Load libbgym.so (building it first if sources are newer and nvcc is present)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            build()
+        elif not os.path.exists(SO_PATH):
+            raise BgymError(f"{SO_PATH} is missing and nvcc is not available; run __graft_entry__.build()")
+    lib = C.CDLL(SO_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.bgym_abi_version() != 1:
+        raise BgymError("libbgym.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().bgym_last_error().decode()
+        raise BgymError(f"{what} failed (rc={rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise BgymError("balatro_gym_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch

@@ -1,0 +1,219 @@
+// bgym_device.cuh — device-side building blocks shared by the sm_100a kernels:
+// PTX wrappers (mbarrier, 1-D bulk async copies = TMA without a tensor map), Philox4x32-10,
+// packed-byte helpers, constant tables.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bgym.h"
+#include "../../include/bgym_tables.h"
+
+namespace bgym {
+
+// ---------------------------------------------------------------------------------------------
+// constant tables (values generated from the reference's data tables, include/bgym_tables.h)
+// ---------------------------------------------------------------------------------------------
+__constant__ uint8_t c_joker_cost[BGYM_NUM_JOKERS + 1] = BGYM_JOKER_COST_INIT;
+__constant__ BgymJokerFx c_joker_fx[BGYM_NUM_JOKERS + 1] = BGYM_JOKER_FX_INIT;
+__constant__ int c_base_chips[12] = BGYM_BASE_CHIPS_INIT;
+__constant__ int c_base_mult[12] = BGYM_BASE_MULT_INIT;
+__constant__ int c_blind_chips[8][3] = BGYM_BLIND_CHIPS_INIT;
+__constant__ int c_pack_cost[5] = BGYM_PACK_COST_INIT;
+__constant__ int c_voucher_cost[2] = BGYM_VOUCHER_COST_INIT;
+__constant__ double c_pow_1_15[101] = BGYM_POW_1_15_INIT;
+__constant__ double c_pow_0_8[9] = BGYM_POW_0_8_INIT;
+__constant__ double c_pow_1_5[101] = BGYM_POW_1_5_INIT;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk async copy (SASS: UBLKCP), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk async copy
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make this thread's generic-proxy shared-memory writes visible to the async proxy
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void sts128(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based; Salmon et al. SC'11 constants)
+// ---------------------------------------------------------------------------------------------
+#define BGYM_PHILOX_KEY1 0xB200CAFEu
+#define BGYM_POLICY_KEY1 0x5A17AC71u
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// Draw source of one env for one step: native Philox word stream (seed/counter in the state) or
+// replay of the reference's recorded draws (BgymDraws).  Left-over words of the current block are
+// dropped at the end of the call; the counter counts blocks.
+struct Draws {
+  const BgymDraws* tape;  // nullptr = native
+  uint32_t seed, ctr;
+  uint32_t buf0, buf1, buf2, buf3;
+  int pos, iu, ik;
+
+  __device__ __forceinline__ void init(uint32_t seed_, uint32_t ctr_, const BgymDraws* tape_) {
+    tape = tape_; seed = seed_; ctr = ctr_; pos = 4; iu = 0; ik = 0;
+    buf0 = buf1 = buf2 = buf3 = 0;
+  }
+  __device__ __forceinline__ uint32_t word() {
+    if (pos == 4) {
+      uint4 b = philox4x32_10(ctr++, 0, 0, 0, seed, BGYM_PHILOX_KEY1);
+      buf0 = b.x; buf1 = b.y; buf2 = b.z; buf3 = b.w; pos = 0;
+    }
+    uint32_t w = pos == 0 ? buf0 : pos == 1 ? buf1 : pos == 2 ? buf2 : buf3;
+    pos++;
+    return w;
+  }
+  // CPython random.random(): (a >> 5, b >> 6) -> 53 bits
+  __device__ __forceinline__ double u01() {
+    if (tape) return tape->u[iu++];
+    uint32_t a = word() >> 5;
+    uint32_t b = word() >> 6;
+    return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+  }
+  // unbiased integer in [0, n): Lemire multiply-shift with rejection
+  __device__ __forceinline__ int below(int n) {
+    if (tape) return tape->k[ik++];
+    uint32_t un = (uint32_t)n;
+    uint64_t m = (uint64_t)word() * un;
+    uint32_t l = (uint32_t)m;
+    if (l < un) {
+      uint32_t t = (0u - un) % un;
+      while (l < t) {
+        m = (uint64_t)word() * un;
+        l = (uint32_t)m;
+      }
+    }
+    return (int)(m >> 32);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// packed-byte helpers (8 x u8 in a u64, 8 x u4 in a u32)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int byte_at(uint64_t v, int i) { return (int)((v >> (8 * i)) & 0xFF); }
+__device__ __forceinline__ uint64_t with_byte(uint64_t v, int i, int b) {
+  return (v & ~(0xFFull << (8 * i))) | ((uint64_t)(b & 0xFF) << (8 * i));
+}
+__device__ __forceinline__ int nib_at(uint32_t v, int i) { return (int)((v >> (4 * i)) & 15); }
+// 4 mask bits -> 4 bytes of 0/1
+__device__ __forceinline__ uint32_t spread4(uint32_t bits) { return ((bits & 0xF) * 0x00204081u) & 0x01010101u; }
+__device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// card16 fields
+__device__ __forceinline__ int c16_code(int c) { return c & 63; }
+__device__ __forceinline__ int c16_enh(int c) { return (c >> 6) & 15; }
+__device__ __forceinline__ int c16_edition(int c) { return (c >> 10) & 7; }
+__device__ __forceinline__ int c16_seal(int c) { return (c >> 13) & 7; }
+
+// chip value of one card: Rank.base_chips (cards.py:52-60) + CardState.calculate_chip_bonus
+// (cards.py:262-267).  r = code >> 2 = rank - 2.
+__device__ __forceinline__ int card_chips(int code, int enh, int edition) {
+  int r = code >> 2;
+  int v = min(r + 2, 10) + (r == 12);
+  v += (enh == BGYM_ENH_BONUS) ? 30 : 0;
+  v += (enh == BGYM_ENH_STONE) ? 50 : 0;
+  v += (edition == BGYM_ED_FOIL) ? 50 : 0;
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// poker-hand classification, balatro_game.py:40-93, on register histograms:
+//   cnt  : 13 rank counters, 4 bits each (counts <= 4 because the cards are distinct)
+//   rmask: rank presence bits, smask: suit presence bits, n: number of cards
+// ---------------------------------------------------------------------------------------------
+struct HandHist {
+  uint64_t cnt;
+  uint32_t rmask, smask;
+  int n;
+  __device__ __forceinline__ void clear() { cnt = 0; rmask = 0; smask = 0; n = 0; }
+  __device__ __forceinline__ void add(int code) {
+    int r = code >> 2;
+    cnt += 1ull << (4 * r);
+    rmask |= 1u << r;
+    smask |= 1u << (code & 3);
+    n++;
+  }
+};
+
+__device__ __forceinline__ int classify(const HandHist& h) {
+  if (h.n == 0) return BGYM_HT_HIGH_CARD;
+  const uint64_t ones = 0x1111111111111ull;
+  uint64_t b0 = h.cnt & ones, b1 = (h.cnt >> 1) & ones, b2 = (h.cnt >> 2) & ones;
+  uint64_t is4 = b2, is3 = b0 & b1, is2 = b1 & ~b0;
+  int n2 = __popcll(is2), n3 = __popcll(is3);
+  bool flush = (__popc(h.smask) == 1) && h.n >= 5;
+  uint32_t rm = h.rmask;
+  bool straight = ((rm & (rm >> 1) & (rm >> 2) & (rm >> 3) & (rm >> 4)) != 0) || ((rm & 0x100Fu) == 0x100Fu);
+  straight = straight && (__popc(rm) >= 5);
+  if (straight && flush) return BGYM_HT_STRAIGHT_FLUSH;
+  if (is4) return BGYM_HT_FOUR_KIND;
+  if (n3 == 1 && n2 >= 1) return BGYM_HT_FULL_HOUSE;   // sorted counts start [3, 2, ...]
+  if (flush) return BGYM_HT_FLUSH;
+  if (straight) return BGYM_HT_STRAIGHT;
+  if (n3 >= 1) return BGYM_HT_THREE_KIND;
+  if (n2 >= 2) return BGYM_HT_TWO_PAIR;
+  if (n2 == 1) return BGYM_HT_ONE_PAIR;
+  return BGYM_HT_HIGH_CARD;
+}
+
+// ScoreEngine.get_hand_chips_mult scoring_engine.py:87-101 (engine level = min(level, 15))
+__device__ __forceinline__ void hand_base(int ht, int level, int& chips, int& mult) {
+  int lv = min(max(level, 1), 15) - 1;
+  chips = c_base_chips[ht] + 10 * lv;
+  mult = c_base_mult[ht] + lv;
+}
+
+}  // namespace bgym

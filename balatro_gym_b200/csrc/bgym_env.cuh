@@ -1,0 +1,920 @@
+// bgym_env.cuh — per-env game logic of the fused step kernel (device functions).
+//
+// One thread owns one env.  The env's 320 B record sits in shared memory (staged there by a bulk
+// async copy); the 128 B hot block is unpacked into registers (struct Hot), the deck block and
+// the shop block are accessed in shared memory because they are indexed dynamically.
+//
+// Semantics follow the reference's *effective* behaviour; each function
+// cites the reference lines it implements.
+#pragma once
+#include "bgym_device.cuh"
+
+namespace bgym {
+
+// offsets inside the record (include/bgym.h)
+constexpr int OFF_DECK = 128, OFF_HPC = 232, OFF_ITEM_TYPE = 244, OFF_ITEM_ID = 253, OFF_N_ITEMS = 262,
+              OFF_ITEM_COST = 264, OFF_REROLL = 300;
+
+enum { B_HOOK = 1, B_WALL, B_WHEEL, B_HOUSE, B_MARK, B_FISH, B_PSYCHIC, B_GOAD, B_WATER, B_WINDOW,
+       B_MANACLE, B_EYE, B_MOUTH, B_PLANT, B_SERPENT, B_PILLAR, B_NEEDLE, B_HEAD, B_CLUB, B_TOOTH,
+       B_FLINT, B_OXIDE, B_ARM, B_VIOLET, B_VERDANT, B_AMBER, B_CRIMSON, B_CERULEAN };
+
+// ---------------------------------------------------------------------------------------------
+// hot block in registers
+// ---------------------------------------------------------------------------------------------
+struct Hot {
+  uint64_t hand;                     // 8 packed bytes
+  int hand_n, hand_size, sel_n, highlight;
+  uint32_t sel_order;
+  int face_down, phase, round, boss_type;
+  int hands_left, discards_left, joker_n, cons_n;
+  int joker_slots, cons_slots, n_magic, n_minimalist;
+  int ante, jokers_sold, money, chips_needed;
+  long long round_chips, chips_scored;
+  int best_hand, hands_played_total, hands_played_ante;
+  int boss_flags, boss_cards_required, boss_played_types, boss_hands_played, deck_n;
+  uint64_t boss_played_cards, jokers, cons;
+  uint32_t lv0, lv1, lv2;            // 12 hand levels, packed bytes
+  int shop_reroll_state;
+  uint32_t rng_seed, rng_ctr, ep_len, episode;
+};
+
+__device__ __forceinline__ void unpack_hot(const uint8_t* rec, Hot& h) {
+  uint4 q0 = lds128(rec), q1 = lds128(rec + 16), q2 = lds128(rec + 32), q3 = lds128(rec + 48);
+  uint4 q4 = lds128(rec + 64), q5 = lds128(rec + 80), q6 = lds128(rec + 96), q7 = lds128(rec + 112);
+  h.hand = u64_of(q0.x, q0.y);
+  h.hand_n = q0.z & 0xFF; h.hand_size = (q0.z >> 8) & 0xFF; h.sel_n = (q0.z >> 16) & 0xFF; h.highlight = q0.z >> 24;
+  h.sel_order = q0.w;
+  h.face_down = q1.x & 0xFF; h.phase = (q1.x >> 8) & 0xFF; h.round = (q1.x >> 16) & 0xFF; h.boss_type = q1.x >> 24;
+  h.hands_left = q1.y & 0xFF; h.discards_left = (q1.y >> 8) & 0xFF; h.joker_n = (q1.y >> 16) & 0xFF; h.cons_n = q1.y >> 24;
+  h.joker_slots = q1.z & 0xFF; h.cons_slots = (q1.z >> 8) & 0xFF; h.n_magic = (q1.z >> 16) & 0xFF; h.n_minimalist = q1.z >> 24;
+  h.ante = (int)(short)(q1.w & 0xFFFF); h.jokers_sold = (int)(short)(q1.w >> 16);
+  h.money = (int)q2.x; h.chips_needed = (int)q2.y;
+  h.round_chips = (long long)u64_of(q2.z, q2.w); h.chips_scored = (long long)u64_of(q3.x, q3.y);
+  h.best_hand = (int)q3.z; h.hands_played_total = (int)q3.w;
+  h.hands_played_ante = (int)(short)(q4.x & 0xFFFF); h.boss_flags = (q4.x >> 16) & 0xFF; h.boss_cards_required = q4.x >> 24;
+  h.boss_played_types = q4.y & 0xFFFF; h.boss_hands_played = (q4.y >> 16) & 0xFF; h.deck_n = q4.y >> 24;
+  h.boss_played_cards = u64_of(q4.z, q4.w);
+  h.jokers = u64_of(q5.x, q5.y); h.cons = u64_of(q5.z, q5.w);
+  h.lv0 = q6.x; h.lv1 = q6.y; h.lv2 = q6.z; h.shop_reroll_state = (int)q6.w;
+  h.rng_seed = q7.x; h.rng_ctr = q7.y; h.ep_len = q7.z; h.episode = q7.w;
+}
+
+__device__ __forceinline__ void pack_hot(uint8_t* rec, const Hot& h) {
+  uint4 q;
+  q.x = (uint32_t)h.hand; q.y = (uint32_t)(h.hand >> 32);
+  q.z = (h.hand_n & 0xFF) | ((h.hand_size & 0xFF) << 8) | ((h.sel_n & 0xFF) << 16) | ((uint32_t)(h.highlight & 0xFF) << 24);
+  q.w = h.sel_order;
+  sts128(rec, q);
+  q.x = (h.face_down & 0xFF) | ((h.phase & 0xFF) << 8) | ((h.round & 0xFF) << 16) | ((uint32_t)(h.boss_type & 0xFF) << 24);
+  q.y = (h.hands_left & 0xFF) | ((h.discards_left & 0xFF) << 8) | ((h.joker_n & 0xFF) << 16) | ((uint32_t)(h.cons_n & 0xFF) << 24);
+  q.z = (h.joker_slots & 0xFF) | ((h.cons_slots & 0xFF) << 8) | ((h.n_magic & 0xFF) << 16) | ((uint32_t)(h.n_minimalist & 0xFF) << 24);
+  q.w = (h.ante & 0xFFFF) | ((uint32_t)(h.jokers_sold & 0xFFFF) << 16);
+  sts128(rec + 16, q);
+  q.x = (uint32_t)h.money; q.y = (uint32_t)h.chips_needed;
+  q.z = (uint32_t)h.round_chips; q.w = (uint32_t)((uint64_t)h.round_chips >> 32);
+  sts128(rec + 32, q);
+  q.x = (uint32_t)h.chips_scored; q.y = (uint32_t)((uint64_t)h.chips_scored >> 32);
+  q.z = (uint32_t)h.best_hand; q.w = (uint32_t)h.hands_played_total;
+  sts128(rec + 48, q);
+  q.x = (h.hands_played_ante & 0xFFFF) | ((h.boss_flags & 0xFF) << 16) | ((uint32_t)(h.boss_cards_required & 0xFF) << 24);
+  q.y = (h.boss_played_types & 0xFFFF) | ((h.boss_hands_played & 0xFF) << 16) | ((uint32_t)(h.deck_n & 0xFF) << 24);
+  q.z = (uint32_t)h.boss_played_cards; q.w = (uint32_t)(h.boss_played_cards >> 32);
+  sts128(rec + 64, q);
+  q.x = (uint32_t)h.jokers; q.y = (uint32_t)(h.jokers >> 32); q.z = (uint32_t)h.cons; q.w = (uint32_t)(h.cons >> 32);
+  sts128(rec + 80, q);
+  q.x = h.lv0; q.y = h.lv1; q.z = h.lv2; q.w = (uint32_t)h.shop_reroll_state;
+  sts128(rec + 96, q);
+  q.x = h.rng_seed; q.y = h.rng_ctr; q.z = h.ep_len; q.w = h.episode;
+  sts128(rec + 112, q);
+}
+
+__device__ __forceinline__ int hand_level(const Hot& h, int ht) {
+  uint32_t w = ht < 4 ? h.lv0 : (ht < 8 ? h.lv1 : h.lv2);
+  return (w >> (8 * (ht & 3))) & 0xFF;
+}
+__device__ __forceinline__ void bump_hand_level(Hot& h, int ht) {  // state.hand_levels[..] += 1, u8 saturating
+  int lv = hand_level(h, ht);
+  if (lv >= 255) return;
+  uint32_t inc = 1u << (8 * (ht & 3));
+  if (ht < 4) h.lv0 += inc; else if (ht < 8) h.lv1 += inc; else h.lv2 += inc;
+}
+
+__device__ __forceinline__ int deck16(const uint8_t* rec, int idx) {
+  return *reinterpret_cast<const uint16_t*>(rec + OFF_DECK + 2 * idx);
+}
+__device__ __forceinline__ void set_deck16(uint8_t* rec, int idx, int v) {
+  *reinterpret_cast<uint16_t*>(rec + OFF_DECK + 2 * idx) = (uint16_t)v;
+}
+__device__ __forceinline__ bool owns_joker(const Hot& h, int id) {
+  // byte-wise equality over the 8 packed joker ids (id != 0)
+  uint64_t x = h.jokers ^ (0x0101010101010101ull * (uint64_t)id);
+  return (((x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull) != 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// action mask, balatro_env_2.py:1426-1471
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t action_mask(const Hot& h, const uint8_t* rec) {
+  uint64_t m = 0;
+  if (h.phase == BGYM_PHASE_PLAY) {
+    m = ((1ull << min(h.hand_n, 8)) - 1) << BGYM_A_SELECT_BASE;
+    if (h.sel_n > 0) m |= 1ull << BGYM_A_PLAY_HAND;
+    if (h.sel_n > 0 && h.discards_left > 0) m |= 1ull << BGYM_A_DISCARD;
+    m |= ((1ull << h.cons_n) - 1) << BGYM_A_USE_CONS_BASE;
+  } else if (h.phase == BGYM_PHASE_SHOP) {
+    int n_items = rec[OFF_N_ITEMS];
+    for (int i = 0; i < n_items; i++) {
+      int cost = *reinterpret_cast<const int*>(rec + OFF_ITEM_COST + 4 * i);
+      if (h.money >= cost) m |= 1ull << (BGYM_A_SHOP_BUY_BASE + i);
+    }
+    if (h.money >= h.shop_reroll_state) m |= 1ull << BGYM_A_SHOP_REROLL;
+    m |= 1ull << BGYM_A_SHOP_END;
+    m |= ((1ull << h.joker_n) - 1) << BGYM_A_SELL_JOKER_BASE;
+  } else if (h.phase == BGYM_PHASE_BLIND_SELECT) {
+    m = 0xFull << BGYM_A_SELECT_BLIND_BASE;  // 45,46,47 + SKIP_BLIND 48
+  }
+  return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hand list operations
+// ---------------------------------------------------------------------------------------------
+// BalatroGame._draw_cards balatro_game.py:95-109: top up with the lowest deck indices not in hand
+__device__ __forceinline__ void draw_cards(Hot& h) {
+  int want = h.hand_size - h.hand_n;
+  if (want <= 0) return;
+  uint64_t in_hand = 0;
+  for (int i = 0; i < h.hand_n; i++) in_hand |= 1ull << byte_at(h.hand, i);
+  uint64_t avail = ~in_hand & ((h.deck_n >= 64) ? ~0ull : ((1ull << h.deck_n) - 1));
+  while (want > 0 && avail && h.hand_n < 8) {
+    int idx = __ffsll((long long)avail) - 1;
+    avail &= avail - 1;
+    h.hand = with_byte(h.hand, h.hand_n, idx);
+    h.hand_n++;
+    want--;
+  }
+}
+// remove the hand slots in `slots` (bit set), keeping order
+__device__ __forceinline__ void remove_slots(Hot& h, int slots) {
+  uint64_t out = ~0ull;
+  int n = 0;
+  for (int i = 0; i < h.hand_n; i++) {
+    if ((slots >> i) & 1) continue;
+    out = with_byte(out, n, byte_at(h.hand, i));
+    n++;
+  }
+  h.hand = out;
+  h.hand_n = n;
+}
+// ---------------------------------------------------------------------------------------------
+// shop, shop.py:96-205 and balatro_env_2.py:1383-1392
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shop_cost_mult(const Hot& h) {  // shop.py:105-109
+  double m = c_pow_1_15[min(max(h.ante - 1, 0), 100)];
+  if (h.n_magic > 0) m *= 0.9;
+  return m;
+}
+
+__device__ __forceinline__ void shop_put(uint8_t* rec, int i, int type, int id, int cost) {
+  rec[OFF_ITEM_TYPE + i] = (uint8_t)type;
+  rec[OFF_ITEM_ID + i] = (uint8_t)id;
+  *reinterpret_cast<int*>(rec + OFF_ITEM_COST + 4 * i) = cost;
+}
+
+// shop.py:112-139.  The joker pool is "ids with base_cost > 0 not owned", which is ids
+// 1..BGYM_NUM_SHOP_JOKERS minus the owned ones, so pool position p maps to an id by skipping
+// owned ids in increasing order.
+__device__ void shop_generate_inventory(Hot& h, uint8_t* rec, Draws& rng) {
+  double mult = shop_cost_mult(h);
+  int third = BGYM_PACK_TAROT + rng.below(3);
+  shop_put(rec, 0, BGYM_ITEM_PACK, BGYM_PACK_STANDARD, (int)(c_pack_cost[BGYM_PACK_STANDARD] * mult));
+  shop_put(rec, 1, BGYM_ITEM_PACK, BGYM_PACK_JOKER, (int)(c_pack_cost[BGYM_PACK_JOKER] * mult));
+  shop_put(rec, 2, BGYM_ITEM_PACK, third, (int)(c_pack_cost[third] * mult));
+  // owned shop-eligible ids, sorted ascending (<= 8 entries)
+  int owned[8], n_owned = 0;
+  for (int i = 0; i < h.joker_n; i++) {
+    int id = byte_at(h.jokers, i);
+    if (id >= 1 && id <= BGYM_NUM_SHOP_JOKERS) {
+      int k = n_owned++;
+      while (k > 0 && owned[k - 1] > id) { owned[k] = owned[k - 1]; k--; }
+      owned[k] = id;
+    }
+  }
+  // distinct owned ids only (Ankh-style duplicates cannot occur in-env, but stay safe)
+  int m = 0;
+  for (int i = 0; i < n_owned; i++) if (i == 0 || owned[i] != owned[i - 1]) owned[m++] = owned[i];
+  n_owned = m;
+  int pool = BGYM_NUM_SHOP_JOKERS - n_owned;
+  int k = min(3, pool);
+  int n = 3;
+  int chosen[3];
+  for (int t = 0; t < k; t++) {
+    int p;
+    if (rng.tape) {
+      p = rng.below(pool);  // replay: population index recorded from the reference
+    } else {
+      // native: t-th element of a uniform ordered sample without replacement
+      p = rng.below(pool - t);
+      // map to the p-th not-yet-chosen position (chosen kept sorted)
+      for (int a = 0; a < t; a++) if (chosen[a] <= p) p++;
+    }
+    // keep `chosen` sorted ascending for the skip logic above
+    int c = t;
+    while (c > 0 && chosen[c - 1] > p) { chosen[c] = chosen[c - 1]; c--; }
+    chosen[c] = p;
+    int id = p + 1;
+    for (int a = 0; a < n_owned; a++) if (owned[a] <= id) id++;
+    shop_put(rec, n++, BGYM_ITEM_JOKER, id, (int)(c_joker_cost[id] * mult));
+  }
+  int v = rng.below(2);
+  shop_put(rec, n++, BGYM_ITEM_VOUCHER, v, (int)(c_voucher_cost[v] * mult));
+  for (int i = 0; i < 2; i++) {
+    int c = rng.below(52);
+    shop_put(rec, n++, BGYM_ITEM_CARD, c, BGYM_CARD_COST);
+  }
+  rec[OFF_N_ITEMS] = (uint8_t)n;
+  for (int i = n; i < 9; i++) shop_put(rec, i, 0, 0, 0);
+}
+
+__device__ __forceinline__ void generate_shop(Hot& h, uint8_t* rec, Draws& rng) {  // balatro_env_2.py:1383-1392
+  *reinterpret_cast<int*>(rec + OFF_REROLL) = BGYM_REROLL_BASE;
+  shop_generate_inventory(h, rec, rng);
+  h.shop_reroll_state = (int)(BGYM_REROLL_BASE * shop_cost_mult(h));
+}
+
+// ---------------------------------------------------------------------------------------------
+// round advance, balatro_env_2.py:1326-1381
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void boss_deactivate(Hot& h) {
+  h.boss_type = 0; h.boss_flags = 0; h.boss_cards_required = 0; h.boss_played_types = 0;
+  h.boss_hands_played = 0; h.boss_played_cards = 0;
+}
+
+__device__ void advance_round(Hot& h, uint8_t* rec, Draws& rng) {
+  int gold = 0;
+  for (int i = 0; i < h.hand_n; i++) {
+    int idx = byte_at(h.hand, i);
+    if (idx < 52 && c16_enh(deck16(rec, idx)) == BGYM_ENH_GOLD) gold += 3;
+  }
+  h.money += gold;
+  if (h.boss_type) {
+    h.money += 5;  // BossBlind.money_reward, boss_blinds.py:60
+    boss_deactivate(h);
+    h.face_down = 0;
+  }
+  h.round_chips = 0; h.best_hand = 0; h.hands_played_ante = 0;
+  if (h.round == 3) {
+    h.ante += 1; h.round = 1;
+    if (h.ante > 100) return;
+  } else {
+    h.round += 1;
+  }
+  h.money += 25 * h.round + (h.round == 3 ? 10 : 0);
+  h.hands_left = 4; h.discards_left = 3;
+  h.phase = BGYM_PHASE_SHOP;
+  generate_shop(h, rec, rng);
+}
+
+// ---------------------------------------------------------------------------------------------
+// consumables, balatro_env_2.py:1066-1172 + consumables.py:115-655
+// Table-driven: each consumable id maps to an (op, arg) pair; the op set is small.
+// ---------------------------------------------------------------------------------------------
+enum ConsOp : uint8_t {
+  CO_NONE = 0,
+  CO_ENH_N,        // set enhancement `arg & 15` on the first `arg >> 4` targets (>= 1 target needed)
+  CO_AFFECT_N,     // targets only "affected" (effect lost in the reference): first `arg` targets
+  CO_STRENGTH,     // first 2 targets, affected only when rank < ace
+  CO_DEATH,        // needs 2 targets, 2 affected
+  CO_HERMIT, CO_TEMPERANCE,
+  CO_WHEEL,        // 25% roll then edition
+  CO_FOOL, CO_PRIESTESS, CO_EMPEROR, CO_JUDGEMENT,
+  CO_RAISE_IF_TARGET,   // reference raises when a target is selected, fails otherwise
+  CO_RAISE_IF_HAND,     // Sigil / Ouija: draws then raises (arg = population)
+  CO_PLANET,       // arg = hand type
+  CO_SEAL,         // arg = raw seal value stored (consumables.Seal numbering)
+  CO_AURA, CO_WRAITH, CO_ECTOPLASM, CO_ANKH, CO_HEX, CO_SOUL, CO_BLACK_HOLE,
+  CO_UNSUPPORTED
+};
+struct ConsRow { uint8_t op, arg; };
+
+__device__ __forceinline__ ConsRow cons_row(int cid) {
+  int t = (cid >= 101 && cid <= 122) ? cid - 100 : cid;  // enum-style tarot names resolve the same way
+  switch (t) {
+    case 1: return {CO_FOOL, 0};
+    case 2: return {CO_ENH_N, (2 << 4) | BGYM_ENH_LUCKY};
+    case 3: return {CO_PRIESTESS, 0};
+    case 4: return {CO_ENH_N, (2 << 4) | BGYM_ENH_MULT};
+    case 5: return {CO_EMPEROR, 0};
+    case 6: return {CO_ENH_N, (2 << 4) | BGYM_ENH_BONUS};
+    case 7: return {CO_ENH_N, (1 << 4) | BGYM_ENH_WILD};
+    case 8: return {CO_ENH_N, (1 << 4) | BGYM_ENH_STEEL};
+    case 9: return {CO_STRENGTH, 0};
+    case 10: return {CO_HERMIT, 0};
+    case 11: return {CO_WHEEL, 0};
+    case 12: return {CO_ENH_N, (1 << 4) | BGYM_ENH_GLASS};
+    case 13: return {CO_RAISE_IF_TARGET, 0};
+    case 14: return {CO_DEATH, 0};
+    case 15: return {CO_TEMPERANCE, 0};
+    case 16: return {CO_ENH_N, (1 << 4) | BGYM_ENH_GOLD};
+    case 17: return {CO_ENH_N, (1 << 4) | BGYM_ENH_STONE};
+    case 18: case 19: case 20: case 22: return {CO_AFFECT_N, 3};
+    case 21: return {CO_JUDGEMENT, 0};
+    // planets 30..41 -> hand type (balatro_env_2.py:1103-1116)
+    case 30: return {CO_PLANET, 1}; case 31: return {CO_PLANET, 2}; case 32: return {CO_PLANET, 3};
+    case 33: return {CO_PLANET, 4}; case 34: return {CO_PLANET, 5}; case 35: return {CO_PLANET, 6};
+    case 36: return {CO_PLANET, 7}; case 37: return {CO_PLANET, 8}; case 38: return {CO_PLANET, 0};
+    case 39: return {CO_PLANET, 9}; case 40: return {CO_PLANET, 10}; case 41: return {CO_PLANET, 11};
+    // spectrals 50..67 (consumables.py:344-362)
+    case 50: case 51: case 52: return {CO_RAISE_IF_TARGET, 0};
+    case 53: return {CO_SEAL, 3};   // Talisman: consumables.Seal.GOLD == 3
+    case 54: return {CO_AURA, 0};
+    case 55: return {CO_WRAITH, 0};
+    case 56: return {CO_RAISE_IF_HAND, 4};
+    case 57: return {CO_RAISE_IF_HAND, 13};
+    case 58: return {CO_ECTOPLASM, 0};
+    case 60: return {CO_ANKH, 0};
+    case 61: return {CO_SEAL, 1};   // Deja Vu: consumables.Seal.RED == 1
+    case 62: return {CO_HEX, 0};
+    case 63: return {CO_SEAL, 2};   // Trance: consumables.Seal.BLUE == 2
+    case 64: return {CO_SEAL, 4};   // Medium: PURPLE == 4
+    case 66: return {CO_SOUL, 0};
+    case 67: return {CO_BLACK_HOLE, 0};
+    case 59: case 65: return {CO_UNSUPPORTED, 0};  // Immolate, Cryptid rebuild the deck list
+  }
+  return {CO_NONE, 0};
+}
+
+__device__ __forceinline__ void cons_append(Hot& h, int cid) {
+  if (h.cons_n < 8) { h.cons = with_byte(h.cons, h.cons_n, cid); h.cons_n++; }
+}
+__device__ __forceinline__ void cons_pop(Hot& h, int idx) {
+  uint64_t lo = h.cons & ((1ull << (8 * idx)) - 1);
+  uint64_t hi = (idx >= 7) ? 0 : (h.cons >> (8 * (idx + 1))) << (8 * idx);
+  h.cons = lo | hi;
+  h.cons_n--;
+}
+
+__device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int& err, int& terminated) {
+  int cid = byte_at(h.cons, cidx);
+  ConsRow row = cons_row(cid);
+  // targets: selected cards in selection order (balatro_env_2.py:1074-1083)
+  int tgt[8], nT = 0;
+  for (int k = 0; k < h.sel_n; k++) {
+    int sl = nib_at(h.sel_order, k);
+    if (sl < h.hand_n) { int idx = byte_at(h.hand, sl); if (idx < h.deck_n) tgt[nT++] = idx; }
+  }
+  bool success = false, raise = false, unsupported = false;
+  int money_gained = 0, planet_ht = -1, n_affected = 0, n_jokers_created = 0, add_joker = 0;
+  int items[2], n_items = 0, hand_size_change = 0;
+  switch (row.op) {
+    case CO_ENH_N: {
+      int cnt = min(nT, row.arg >> 4);
+      for (int i = 0; i < cnt; i++) { int c = deck16(rec, tgt[i]); set_deck16(rec, tgt[i], (c & ~(15 << 6)) | ((row.arg & 15) << 6)); }
+      n_affected = cnt; success = nT > 0;
+      break;
+    }
+    case CO_AFFECT_N: n_affected = min(nT, (int)row.arg); success = nT > 0; break;
+    case CO_STRENGTH:
+      for (int i = 0; i < min(nT, 2); i++) n_affected += (c16_code(deck16(rec, tgt[i])) >> 2) < 12;
+      success = nT > 0;
+      break;
+    case CO_DEATH: if (nT >= 2) { n_affected = 2; success = true; } break;
+    case CO_HERMIT: money_gained = min(h.money, 20); success = true; break;
+    case CO_TEMPERANCE: money_gained = min(5 * h.joker_n, 50); success = true; break;
+    case CO_WHEEL:
+      if (nT > 0 && rng.u01() < 0.25) {
+        int ed = BGYM_ED_FOIL + rng.below(3);
+        int c = deck16(rec, tgt[0]); set_deck16(rec, tgt[0], (c & ~(7 << 10)) | (ed << 10));
+        n_affected = 1; success = true;
+      }
+      break;
+    case CO_FOOL: {  // appends to the aliased list without a slot check
+      int copied = byte_at(h.cons, rng.below(h.cons_n));
+      cons_append(h, copied); items[n_items++] = copied; success = true;
+      break;
+    }
+    case CO_PRIESTESS:
+      for (int i = 0; i < 2; i++) {
+        int p = BGYM_CONS_PLANET_BASE + rng.below(9);
+        if (h.cons_n < h.cons_slots) { cons_append(h, p); items[n_items++] = p; }
+      }
+      success = true;
+      break;
+    case CO_EMPEROR:
+      for (int i = 0; i < 2; i++)
+        if (h.cons_n < h.cons_slots) {
+          int t = BGYM_CONS_ENUMSTYLE_BASE + 1 + rng.below(22);
+          cons_append(h, t); items[n_items++] = t;
+        }
+      success = true;
+      break;
+    case CO_JUDGEMENT: {
+      int p = BGYM_CONS_PLANET_BASE + rng.below(9);
+      if (h.cons_n < h.cons_slots) { cons_append(h, p); items[n_items++] = p; }
+      success = true;
+      break;
+    }
+    case CO_RAISE_IF_TARGET: raise = nT >= 1; break;
+    case CO_RAISE_IF_HAND: if (h.hand_n > 0) { (void)rng.below(row.arg); raise = true; } break;
+    case CO_PLANET: planet_ht = row.arg; success = true; break;
+    case CO_SEAL:
+      if (nT >= 1) { int c = deck16(rec, tgt[0]); set_deck16(rec, tgt[0], (c & ~(7 << 13)) | (row.arg << 13)); n_affected = 1; success = true; }
+      break;
+    case CO_AURA:
+      if (nT >= 1) {
+        int ed = BGYM_ED_FOIL + rng.below(3);
+        int c = deck16(rec, tgt[0]); set_deck16(rec, tgt[0], (c & ~(7 << 10)) | (ed << 10));
+        n_affected = 1; success = true;
+      }
+      break;
+    case CO_WRAITH:
+      if (h.joker_n < h.joker_slots) {
+        // consumables.py:479-481; 'Drivers License' (index 4) is not a library name -> nothing added
+        int j = rng.below(14);
+        add_joker = j < 4 ? BGYM_J_INVISIBLE_JOKER + j : (j == 4 ? 0 : BGYM_J_CARTOMANCER + (j - 5));
+        n_jokers_created = 1; hand_size_change = -1; success = true;
+      }
+      break;
+    case CO_ECTOPLASM: if (h.joker_n > 0) { hand_size_change = -1; success = true; } break;
+    case CO_ANKH: if (h.joker_n > 0) { (void)rng.below(h.joker_n); n_jokers_created = 1; success = true; } break;
+    case CO_HEX: if (h.joker_n > 0) { (void)rng.below(h.joker_n); success = true; } break;
+    case CO_SOUL:
+      if (h.joker_n < h.joker_slots) { add_joker = BGYM_J_CANIO + rng.below(5); n_jokers_created = 1; success = true; }
+      break;
+    case CO_BLACK_HOLE: success = true; break;
+    case CO_UNSUPPORTED: unsupported = true; break;
+    default: break;
+  }
+  if (raise) {  // SafeBalatroEnv convention, train_balatro_fixed.py:262-269
+    err = BGYM_ERR_REF_EXCEPTION; terminated = 1;
+    return -100.0;
+  }
+  double reward = 0.0;
+  if (unsupported) { err = BGYM_ERR_UNSUPPORTED; reward = -1.0; }
+  else if (success) {
+    cons_pop(h, cidx);
+    if (money_gained > 0) { h.money += money_gained; reward += money_gained / 10.0; }
+    if (planet_ht >= 0) { bump_hand_level(h, planet_ht); reward += 10.0; }
+    if (n_affected > 0) reward += n_affected * 2.0;
+    if (n_jokers_created > 0) {
+      if (add_joker != 0 && h.joker_n < h.joker_slots && h.joker_n < 8) { h.jokers = with_byte(h.jokers, h.joker_n, add_joker); h.joker_n++; }
+      reward += n_jokers_created * 15.0;
+    }
+    if (n_items > 0) {
+      for (int i = 0; i < n_items; i++) if (h.cons_n < h.cons_slots) cons_append(h, items[i]);
+      reward += n_items * 5.0;
+    }
+    if (hand_size_change) h.hand_size = max(h.hand_size + hand_size_change, 0);
+  } else {
+    reward = -1.0; err = BGYM_ERR_CONSUMABLE_FAILED;
+  }
+  h.sel_n = 0; h.sel_order = 0;
+  return reward;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset, balatro_env_2.py:505-558 (UnifiedGameState defaults :166-211)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t next_episode_seed(uint32_t seed) {
+  uint32_t x = seed + 0x9E3779B9u;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x ? x : 1u;
+}
+
+// writes the deck/shop blocks into the record and returns the hot block in registers
+__device__ void reset_env(Hot& h, uint8_t* rec, uint32_t seed, const uint8_t* deck52 /*global, nullable*/) {
+  // zero deck + shop blocks
+#pragma unroll
+  for (int o = 128; o < 304; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
+  h.hand = ~0ull;
+  h.hand_n = 0; h.hand_size = 8; h.sel_n = 0; h.highlight = 0; h.sel_order = 0;
+  h.face_down = 0; h.phase = BGYM_PHASE_BLIND_SELECT; h.round = 1; h.boss_type = 0;
+  h.hands_left = 4; h.discards_left = 3; h.joker_n = 0; h.cons_n = 0;
+  h.joker_slots = 5; h.cons_slots = 2; h.n_magic = 0; h.n_minimalist = 0;
+  h.ante = 1; h.jokers_sold = 0; h.money = 4; h.chips_needed = 300;
+  h.round_chips = 0; h.chips_scored = 0; h.best_hand = 0; h.hands_played_total = 0; h.hands_played_ante = 0;
+  h.boss_flags = 0; h.boss_cards_required = 0; h.boss_played_types = 0; h.boss_hands_played = 0; h.deck_n = 52;
+  h.boss_played_cards = 0; h.jokers = 0; h.cons = 0;
+  h.lv0 = h.lv1 = h.lv2 = 0x01010101u;
+  h.shop_reroll_state = 5;
+  h.rng_seed = seed; h.rng_ctr = 0; h.ep_len = 0; h.episode = 0;
+  if (deck52) {
+    for (int i = 0; i < 52; i++) set_deck16(rec, i, deck52[i]);
+  } else {
+    // suit-major build (:519-522) + Fisher-Yates as random.shuffle does it:
+    // for i in reversed(range(1, n)): j = randbelow(i + 1); swap
+    int k = 0;
+    for (int suit = 0; suit < 4; suit++)
+      for (int r = 0; r < 13; r++) set_deck16(rec, k++, r * 4 + suit);
+    Draws rng;
+    rng.init(seed, 0, nullptr);
+    for (int i = 51; i >= 1; i--) {
+      int j = rng.below(i + 1);
+      int a = deck16(rec, i), b = deck16(rec, j);
+      set_deck16(rec, i, b); set_deck16(rec, j, a);
+    }
+    h.rng_ctr = rng.ctr;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-step outputs
+// ---------------------------------------------------------------------------------------------
+struct StepInfo {
+  long long final_score;
+  double x_mult;
+  int chips, mult, hand_type, error_code, flags, cards_played, base_score;
+};
+
+// ---------------------------------------------------------------------------------------------
+// the step, balatro_env_2.py:616-1064 (play), :1174-1253 (shop), :1255-1318 (blind select)
+// ---------------------------------------------------------------------------------------------
+__device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const BgymDraws* tape, double& reward_out,
+                         int& terminated_out, StepInfo& info) {
+  info.final_score = 0; info.x_mult = 1.0; info.chips = 0; info.mult = 0; info.hand_type = -1;
+  info.error_code = 0; info.flags = 0; info.cards_played = 0; info.base_score = 0;
+  reward_out = 0.0; terminated_out = 0;
+  if (h.ante > 100 || h.chips_scored > 1000000000LL) {  // :619-623
+    info.flags = BGYM_F_GUARD_TERMINATED; terminated_out = 1;
+    return;
+  }
+  if (action < 0 || action >= BGYM_NUM_ACTIONS || !((mask >> action) & 1)) {  // :626-627
+    info.error_code = BGYM_ERR_INVALID_ACTION; reward_out = -1.0;
+    return;
+  }
+  h.ep_len++;
+  Draws rng;
+  rng.init(h.rng_seed, h.rng_ctr, tape);
+  double reward = 0.0;
+  int terminated = 0;
+
+  if (action >= BGYM_A_SELECT_BASE && action < BGYM_A_SELECT_BASE + 8) {
+    // toggle in the ordered selection list (:1052-1058); legal only in PLAY phase by the mask
+    int slot = action - BGYM_A_SELECT_BASE;
+    int found = -1;
+    for (int k = 0; k < h.sel_n; k++) if (nib_at(h.sel_order, k) == slot) found = k;
+    if (found >= 0) {
+      uint32_t lo = h.sel_order & ((1u << (4 * found)) - 1);
+      uint32_t hi = (found == 7) ? 0u : ((h.sel_order >> (4 * (found + 1))) << (4 * found));
+      h.sel_order = lo | hi; h.sel_n--;
+    } else {
+      h.sel_order |= (uint32_t)slot << (4 * h.sel_n); h.sel_n++;
+    }
+  } else if (action == BGYM_A_PLAY_HAND) {
+    // ---- gather the played cards in selection order (:650-660) ----
+    int sel_slots = 0;                 // bit set of selected hand slots
+    uint64_t played_bits = 0;          // bit set over deck indices of the played cards
+    int n_played = 0, card_chip_sum = 0, faces_ge11 = 0, extra_money = 0, n_red = 0, n_blue = 0;
+    int boss = h.boss_type, debuffed = 0;
+    for (int k = 0; k < h.sel_n; k++) {
+      int sl = nib_at(h.sel_order, k);
+      if (sl >= h.hand_n) continue;
+      sel_slots |= 1 << sl;
+      int idx = byte_at(h.hand, sl);
+      if (idx >= h.deck_n) continue;
+      int c = deck16(rec, idx);
+      int code = c16_code(c), enh = c16_enh(c), seal = c16_seal(c);
+      n_played++;
+      played_bits |= 1ull << idx;
+      card_chip_sum += card_chips(code, enh, c16_edition(c));
+      int r = code >> 2;                       // rank - 2
+      faces_ge11 += r >= 9;                    // J Q K A (:862 counts rank.value >= 11)
+      bool jqk = r >= 9 && r <= 11;
+      // boss debuffs (boss_blinds.py:447-478): Plant = face ranks, Violet = all, Pillar = played before
+      debuffed += (boss == B_PLANT && jqk) || boss == B_VIOLET || (boss == B_PILLAR && ((h.boss_played_cards >> idx) & 1));
+      // per-card enhancement / seal loop (:703-734), draws in selection order
+      if (enh == BGYM_ENH_GLASS) { (void)rng.u01(); }
+      else if (enh == BGYM_ENH_LUCKY) { (void)rng.u01(); if (rng.u01() < 0.0667) extra_money += 20; }
+      extra_money += (seal == BGYM_SEAL_GOLD) ? 3 : 0;
+      n_red += seal == BGYM_SEAL_RED;
+      // blue seal: room is tested against the list as it is now, creation re-tests (:733, :765-767)
+      n_blue += (seal == BGYM_SEAL_BLUE) && (h.cons_n < h.cons_slots);
+    }
+    // ---- highlight + classification on deck[slot] of every highlighted slot (:663-671) ----
+    h.highlight |= sel_slots;
+    HandHist hist;
+    hist.clear();
+    for (int sl = 0; sl < 8; sl++) if ((h.highlight >> sl) & 1) hist.add(c16_code(deck16(rec, sl)));
+    int ht = classify(hist);
+    // ---- boss gate (boss_blinds.py:380-407) ----
+    bool allowed = true;
+    if (boss == B_PSYCHIC) allowed = n_played == 5;
+    else if (boss == B_EYE) allowed = !((h.boss_played_types >> ht) & 1);
+    else if (boss == B_MOUTH) allowed = (h.boss_played_types == 0) || ((h.boss_played_types >> ht) & 1);
+    else if (boss == B_VERDANT) allowed = n_played >= h.boss_cards_required;
+    if (!allowed) {
+      info.error_code = BGYM_ERR_BOSS_RESTRICTION; reward_out = -1.0;
+      return;  // highlight stays modified, exactly as in the reference
+    }
+    // ---- score: jokers never fire in-env, x_mult = 1.0 ----
+    int bc, bm;
+    hand_base(ht, hand_level(h, ht), bc, bm);
+    int chips = bc + card_chip_sum, mult = bm;
+    long long base_score = (long long)chips * mult;
+    long long fs = base_score;
+    // steel cards left in hand (:560-570)
+    int n_steel = 0;
+    for (int i = 0; i < h.hand_n; i++) {
+      int idx = byte_at(h.hand, i);
+      if (!((sel_slots >> i) & 1) && idx < 52 && c16_enh(deck16(rec, idx)) == BGYM_ENH_STEEL) n_steel++;
+    }
+    fs = (long long)((double)fs * c_pow_1_5[n_steel]);
+    // boss modification ratio (:745-755, boss_blinds.py:409-445)
+    if (boss) {
+      int mc = bc, mm = bm;
+      if (boss == B_FLINT) { mc = mc / 2; mm = mm / 2; }
+      else if (boss == B_OXIDE) { mc = 0; }
+      else if (boss == B_ARM) { mc = (int)(mc * 0.75); mm = (int)(mm * 0.75); }
+      if (debuffed > 0) { double p = c_pow_0_8[debuffed]; mc = (int)(mc * p); mm = (int)(mm * p); }
+      double cr = (double)mc / (double)bc, mr = (double)mm / (double)bm;
+      fs = (long long)((double)fs * cr * mr);
+    }
+    fs = (long long)((double)fs * (1 + n_red * 0.5));  // retriggers :757-759
+    h.money += extra_money;
+    {  // blue seals -> planet of this hand type (cards.py:228-246)
+      int planet = ht == 0 ? 38 : (ht <= 8 ? 29 + ht : 30 + ht);
+      for (int i = 0; i < n_blue; i++) if (h.cons_n < h.cons_slots) cons_append(h, planet);
+    }
+    double needed = (double)max(h.chips_needed, 1);
+    double old_progress = fmin(1.0, (double)h.round_chips / needed);
+    h.round_chips += fs; h.chips_scored += fs;
+    h.hands_played_total++; h.hands_played_ante++;
+    if (fs > (long long)h.best_hand) h.best_hand = (int)min(fs, 2147483647LL);
+    if (rec[OFF_HPC + ht] < 255) rec[OFF_HPC + ht]++;
+    if (boss) {  // on_hand_scored boss_blinds.py:480-507
+      h.boss_played_types |= 1 << ht;
+      h.boss_flags &= ~1;
+      h.boss_hands_played = (h.boss_hands_played + 1) & 0xFF;
+      if (boss == B_PILLAR) h.boss_played_cards |= played_bits;
+      if (boss == B_VERDANT) h.boss_cards_required = min(7, h.boss_cards_required + 1);
+    }
+    h.sel_n = 0; h.sel_order = 0;
+    // ---- reward shaping (:799-892) ----
+    double new_progress = fmin(1.0, (double)h.round_chips / needed);
+    double milestone = 0.0;
+    if (old_progress < 0.25 && 0.25 <= new_progress) milestone = 5.0;
+    else if (old_progress < 0.5 && 0.5 <= new_progress) milestone = 10.0;
+    else if (old_progress < 0.75 && 0.75 <= new_progress) milestone = 15.0;
+    else if (old_progress < 1.0 && 1.0 <= new_progress) milestone = 25.0;
+    double score_reward = (h.ante <= 3) ? fmin(10.0, (double)fs / 100.0)
+                                        : fmin(10.0, 3.0 * log10((double)max(fs, 1LL)));
+    double hq = ht == 0 ? 0.1 : ht == 1 ? 0.5 : ht == 2 ? 1.0 : ht == 3 ? 2.0 : (ht == 4 || ht == 5) ? 2.5
+              : ht == 6 ? 3.5 : ht == 7 ? 5.0 : ht == 8 ? 7.0 : ht == 9 ? 10.0 : 0.0;
+    double eff = 0.0;
+    if (ht >= BGYM_HT_THREE_KIND && n_played <= 3) eff = 2.0;
+    else if (ht >= BGYM_HT_FLUSH && n_played == 5) eff = 1.0;
+    else if (n_played <= 4 && h.hands_left <= 2) eff = 1.5;
+    double syn = 0.0;
+    if (h.joker_n > 0) {
+      if (ht == BGYM_HT_FLUSH && (owns_joker(h, BGYM_J_SMEARED_JOKER) || owns_joker(h, BGYM_J_FOUR_FINGERS) || owns_joker(h, BGYM_J_SHORTCUT))) syn += 2.0;
+      if (ht >= BGYM_HT_ONE_PAIR && ht <= BGYM_HT_THREE_KIND &&
+          (owns_joker(h, BGYM_J_ODD_TODD) || owns_joker(h, BGYM_J_EVEN_STEVEN) || owns_joker(h, BGYM_J_JOLLY_JOKER) || owns_joker(h, BGYM_J_ZANY_JOKER))) syn += 1.5;
+      if (faces_ge11 > 0 && (owns_joker(h, BGYM_J_SCARY_FACE) || owns_joker(h, BGYM_J_SMILEY_FACE) || owns_joker(h, BGYM_J_BUSINESS_CARD))) syn += 0.5 * faces_ge11;
+    }
+    double strat = 0.0;
+    if (new_progress > 0.7 && h.hands_left >= 3) strat = 2.0;
+    else if (new_progress < 0.3 && ht >= BGYM_HT_FLUSH) strat = 3.0;
+    double ante_bonus = (h.ante >= 4) ? fmin(5.0, (h.ante - 3) * 0.5) : 0.0;
+    reward = 15.0 * new_progress + milestone + score_reward + hq * 2.0 + eff * 1.5 + syn * 3.0 + strat * 2.0 + ante_bonus;
+    reward = fmin(reward, 100.0);
+    info.final_score = fs; info.base_score = (int)min(base_score, 2147483647LL); info.chips = chips; info.mult = mult;
+    info.hand_type = ht; info.cards_played = n_played; info.flags |= BGYM_F_PLAYED;
+    // ---- round end (:914-960) ----
+    if (h.round_chips >= (long long)h.chips_needed) {
+      reward += fmin(50.0, 25.0 + 10.0 * h.ante);
+      advance_round(h, rec, rng);
+      info.flags |= BGYM_F_BEAT_BLIND;
+    } else if (h.hands_left <= 1) {
+      reward += -50.0 * (1.0 - new_progress);
+      terminated = 1;
+      info.flags |= BGYM_F_FAILED;
+    } else {
+      h.hands_left--;
+      draw_cards(h);
+      if (boss) {  // on_hand_drawn boss_blinds.py:343-378 (first_hand is already False here)
+        int face = 0;
+        if (boss == B_HOOK) {
+          if (h.hand_n >= 2) {
+            int a, b;
+            if (rng.tape) { a = rng.below(h.hand_n); b = rng.below(h.hand_n); }
+            else { a = rng.below(h.hand_n); b = rng.below(h.hand_n - 1); b += (b >= a); }
+            remove_slots(h, (1 << a) | (1 << b));
+          }
+        } else if (boss == B_WHEEL) {
+          for (int i = 0; i < h.hand_n; i++) if (rng.u01() < 1.0 / 7) face |= 1 << i;
+        } else if (boss == B_MARK) {
+          for (int i = 0; i < h.hand_n; i++) {
+            int r = c16_code(deck16(rec, byte_at(h.hand, i))) >> 2;
+            if (r >= 9 && r <= 11) face |= 1 << i;
+          }
+        } else if (boss == B_FISH) {
+          face = (1 << h.hand_n) - 1;
+        }
+        h.face_down = face;
+      }
+    }
+  } else if (action == BGYM_A_DISCARD) {
+    // ---- :962-1050 ----
+    int sel_slots = 0, n_disc = 0, purple = 0, faces = 0;
+    for (int k = 0; k < h.sel_n; k++) {
+      int sl = nib_at(h.sel_order, k);
+      if (sl >= h.hand_n) continue;
+      sel_slots |= 1 << sl;
+      int idx = byte_at(h.hand, sl);
+      if (idx >= h.deck_n) continue;
+      int c = deck16(rec, idx);
+      int r = c16_code(c) >> 2;
+      n_disc++;
+      purple += c16_seal(c) == BGYM_SEAL_PURPLE;
+      faces += r >= 9 && r <= 11;
+    }
+    int money_from_discards = 0, n_discard_jokers = 0;
+    for (int j = 0; j < h.joker_n; j++) {  // discard-phase joker effects, complete_joker_effects.py:186-209
+      int id = byte_at(h.jokers, j);
+      int money = (id == BGYM_J_TRADING_CARD && h.discards_left == 3 && n_disc == 1) ? 3
+                : (id == BGYM_J_FACELESS_JOKER && faces >= 3) ? 5 : 0;
+      money_from_discards += money;
+      n_discard_jokers += (id == BGYM_J_FACELESS_JOKER || id == BGYM_J_HIT_THE_ROAD || id == BGYM_J_RESERVED_PARKING || id == BGYM_J_LUCHADOR);
+    }
+    h.money += money_from_discards;
+    // discard_hand (balatro_game.py:111-127): every highlighted slot goes, stale ones too
+    remove_slots(h, h.highlight | sel_slots);
+    h.highlight = 0;
+    draw_cards(h);
+    h.discards_left--;
+    h.sel_n = 0; h.sel_order = 0;
+    for (int i = 0; i < purple; i++)  // purple seals -> tarots (:1021-1032)
+      if (h.cons_n < h.cons_slots) cons_append(h, BGYM_CONS_TAROT_BASE + rng.below(22));
+    reward = 0.2;
+    if (n_discard_jokers) reward += 0.5 * n_discard_jokers;
+    if (money_from_discards > 0) reward += money_from_discards / 5.0;
+    double progress = (double)h.round_chips / (double)max(h.chips_needed, 1);
+    if (progress < 0.5 && h.discards_left > 1) reward += 0.5;
+    else if (progress > 0.8 && h.discards_left > 1) reward -= 0.3;
+  } else if (action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) {
+    int err = 0;
+    reward = use_consumable(h, rec, action - BGYM_A_USE_CONS_BASE, rng, err, terminated);
+    info.error_code = err;
+  } else if (action == BGYM_A_SHOP_END) {
+    h.phase = BGYM_PHASE_PLAY;
+    draw_cards(h);
+    info.flags |= BGYM_F_SHOP_DONE;
+  } else if (action == BGYM_A_SHOP_REROLL) {
+    int* rr = reinterpret_cast<int*>(rec + OFF_REROLL);
+    int cost = (int)(*rr * shop_cost_mult(h));  // shop.py:172
+    if (h.money < cost) { reward = -1.0; info.error_code = BGYM_ERR_SHOP; }
+    else {
+      h.money -= cost;
+      *rr = (int)(*rr * 1.35);
+      shop_generate_inventory(h, rec, rng);
+    }
+  } else if (action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SHOP_BUY_BASE + 10) {
+    int i = action - BGYM_A_SHOP_BUY_BASE;
+    int n_items = rec[OFF_N_ITEMS];
+    int type = rec[OFF_ITEM_TYPE + i], id = rec[OFF_ITEM_ID + i];
+    int cost = *reinterpret_cast<int*>(rec + OFF_ITEM_COST + 4 * i);
+    h.money -= cost;  // shop.py:185-187: pay, pop the item
+    for (int k = i; k + 1 < n_items; k++)
+      shop_put(rec, k, rec[OFF_ITEM_TYPE + k + 1], rec[OFF_ITEM_ID + k + 1], *reinterpret_cast<int*>(rec + OFF_ITEM_COST + 4 * (k + 1)));
+    shop_put(rec, n_items - 1, 0, 0, 0);
+    rec[OFF_N_ITEMS] = (uint8_t)(n_items - 1);
+    if (type == BGYM_ITEM_PACK) {
+      int count = (id == BGYM_PACK_STANDARD) ? 3 : 1;  // shop.py:150-157: cards go to player.deck only
+      for (int k = 0; k < count; k++) (void)rng.below(52);
+      reward = 5.0;
+    } else if (type == BGYM_ITEM_CARD) {
+      reward = 3.0;
+    } else if (type == BGYM_ITEM_JOKER) {
+      if (h.joker_n >= 5) { reward = -1.0; info.error_code = BGYM_ERR_SHOP; }  // shop.py:196-197
+      else { h.jokers = with_byte(h.jokers, h.joker_n, id); h.joker_n++; reward = 15.0; }
+    } else {
+      if (id == BGYM_VOUCHER_MAGIC_TRICK) h.n_magic = min(h.n_magic + 1, 255); else h.n_minimalist = min(h.n_minimalist + 1, 255);
+      reward = 10.0;
+    }
+  } else if (action >= BGYM_A_SELL_JOKER_BASE && action < BGYM_A_SELL_JOKER_BASE + 5) {
+    int j = action - BGYM_A_SELL_JOKER_BASE;
+    int id = byte_at(h.jokers, j);
+    uint64_t lo = h.jokers & ((1ull << (8 * j)) - 1);
+    uint64_t hi = (j >= 7) ? 0 : (h.jokers >> (8 * (j + 1))) << (8 * j);
+    h.jokers = lo | hi; h.joker_n--;
+    int sell = max(3, (int)c_joker_cost[id] / 2);
+    h.money += sell; h.jokers_sold++;
+    reward = sell / 5.0;
+  } else if (action >= BGYM_A_SELECT_BLIND_BASE && action < BGYM_A_SELECT_BLIND_BASE + 3) {
+    int bt = action - BGYM_A_SELECT_BLIND_BASE;
+    h.round = bt + 1;
+    long long needed = (h.ante <= 8) ? (long long)c_blind_chips[max(h.ante, 1) - 1][bt]
+                                     : (long long)(c_blind_chips[7][bt] * c_pow_1_5[min(h.ante - 8, 100)]);
+    if (bt == 2) {
+      int boss = 1 + rng.below(28);  // select_boss_blind boss_blinds.py:522-532
+      h.boss_type = boss;            // activate_boss_blind :308-341
+      h.boss_flags = 1; h.boss_cards_required = 5; h.boss_played_types = 0; h.boss_hands_played = 0; h.boss_played_cards = 0;
+      needed = (long long)((double)needed * (boss == B_WALL ? 2.0 : 1.0));
+      if (boss == B_WATER) h.discards_left = 0;
+      if (boss == B_MANACLE) h.hand_size -= 1;
+      if (boss == B_NEEDLE) h.hands_left = 1;
+      reward = 10.0;
+    }
+    h.chips_needed = (int)min(needed, 2147483647LL);
+    h.phase = BGYM_PHASE_PLAY;
+    draw_cards(h);
+  } else if (action == BGYM_A_SKIP_BLIND) {
+    reward = -5.0;
+    advance_round(h, rec, rng);
+  }
+  if (!tape) h.rng_ctr = rng.ctr;
+  reward_out = reward;
+  terminated_out = terminated;
+}
+
+// ---------------------------------------------------------------------------------------------
+// observation record (balatro_env_2.py:1473-1573) assembled in registers, 15 x 16 B
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int obs_cons_id(int cid) { return cid >= BGYM_CONS_ENUMSTYLE_BASE ? 0 : cid; }
+
+__device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs /*smem, 240 B*/) {
+  uint4 q;
+  uint32_t selm = 0;
+  for (int k = 0; k < h.sel_n; k++) selm |= 1u << nib_at(h.sel_order, k);
+  // 0: hand[8] | selected_cards[8]   (hand codes = deck[hand[i]], -1 when empty)
+  uint64_t codes = ~0ull;
+  for (int i = 0; i < h.hand_n; i++) {
+    int idx = byte_at(h.hand, i);
+    if (idx < h.deck_n) codes = with_byte(codes, i, c16_code(deck16(rec, idx)));
+  }
+  q.x = (uint32_t)codes; q.y = (uint32_t)(codes >> 32);
+  q.z = spread4(selm); q.w = spread4(selm >> 4);
+  sts128(obs, q);
+  // 16: face_down_cards[8] | chips_scored
+  q.x = spread4(h.face_down); q.y = spread4(h.face_down >> 4);
+  q.z = (uint32_t)h.chips_scored; q.w = (uint32_t)((uint64_t)h.chips_scored >> 32);
+  sts128(obs + 16, q);
+  // 32: round_chips_scored, progress_ratio, mult, chips_needed
+  double p = (double)h.round_chips / (double)max(h.chips_needed, 1);
+  q.x = (uint32_t)h.round_chips; q.y = __float_as_uint((float)fmin(p, 2.0)); q.z = 1u; q.w = (uint32_t)h.chips_needed;
+  sts128(obs + 32, q);
+  // 48: money, hands_played, best_hand_this_ante, ante | shop_rerolls
+  q.x = (uint32_t)h.money; q.y = (uint32_t)h.hands_played_total; q.z = (uint32_t)h.best_hand;
+  q.w = (h.ante & 0xFFFF) | ((uint32_t)(h.shop_reroll_state & 0xFFFF) << 16);
+  sts128(obs + 48, q);
+  // 64..159: int16 arrays and int8 scalars, built as 16-bit lanes
+  // joker_ids[10] @64
+  uint32_t j[5];
+#pragma unroll
+  for (int i = 0; i < 4; i++) j[i] = (uint32_t)byte_at(h.jokers, 2 * i) | ((uint32_t)byte_at(h.jokers, 2 * i + 1) << 16);
+  q.x = j[0]; q.y = j[1]; q.z = j[2]; q.w = j[3];
+  sts128(obs + 64, q);
+  // 80: joker_ids[8..9] (always 0) | consumables[0..4] (84..93) | shop_items[0] (94)
+  int c0 = h.cons_n > 0 ? obs_cons_id(byte_at(h.cons, 0)) : 0, c1 = h.cons_n > 1 ? obs_cons_id(byte_at(h.cons, 1)) : 0;
+  int c2 = h.cons_n > 2 ? obs_cons_id(byte_at(h.cons, 2)) : 0, c3 = h.cons_n > 3 ? obs_cons_id(byte_at(h.cons, 3)) : 0;
+  int c4 = h.cons_n > 4 ? obs_cons_id(byte_at(h.cons, 4)) : 0;
+  bool shop = h.phase == BGYM_PHASE_SHOP;
+  int n_items = shop ? rec[OFF_N_ITEMS] : 0;
+  int it[10], ic[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    bool on = i < n_items && i < 9;
+    it[i] = on ? rec[OFF_ITEM_TYPE + (i < 9 ? i : 8)] : 0;
+    ic[i] = on ? (*reinterpret_cast<const int*>(rec + OFF_ITEM_COST + 4 * (i < 9 ? i : 8)) & 0xFFFF) : 0;
+  }
+  q.x = 0; q.y = (uint32_t)c0 | ((uint32_t)c1 << 16); q.z = (uint32_t)c2 | ((uint32_t)c3 << 16); q.w = (uint32_t)c4 | ((uint32_t)it[0] << 16);
+  sts128(obs + 80, q);
+  // 96: shop_items[1..8]
+  q.x = it[1] | (it[2] << 16); q.y = it[3] | (it[4] << 16); q.z = it[5] | (it[6] << 16); q.w = it[7] | (it[8] << 16);
+  sts128(obs + 96, q);
+  // 112: shop_items[9] | shop_costs[0..6]
+  q.x = it[9] | (ic[0] << 16); q.y = ic[1] | (ic[2] << 16); q.z = ic[3] | (ic[4] << 16); q.w = ic[5] | (ic[6] << 16);
+  sts128(obs + 112, q);
+  // 128: shop_costs[7..9] (128..133) | hand_levels[0..9] (134..143)
+  q.x = ic[7] | (ic[8] << 16);
+  q.y = ic[9] | ((h.lv0 & 0xFFFF) << 16);
+  q.z = (h.lv0 >> 16) | ((h.lv1 & 0xFFFF) << 16);
+  q.w = (h.lv1 >> 16) | ((h.lv2 & 0xFFFF) << 16);
+  sts128(obs + 128, q);
+  // 144: hand_levels[10..11] | hand_size, deck_size | round, hands_left, discards_left, joker_count |
+  //      joker_slots, consumable_count, consumable_slots, phase | boss_active, boss_type, pad, pad
+  q.x = (h.lv2 >> 16) | ((uint32_t)(h.hand_n & 0xFF) << 16) | ((uint32_t)(h.deck_n & 0xFF) << 24);
+  q.y = (h.round & 0xFF) | ((h.hands_left & 0xFF) << 8) | ((h.discards_left & 0xFF) << 16) | ((uint32_t)(h.joker_n & 0xFF) << 24);
+  q.z = (h.joker_slots & 0xFF) | ((h.cons_n & 0xFF) << 8) | ((h.cons_slots & 0xFF) << 16) | ((uint32_t)(h.phase & 0xFF) << 24);
+  q.w = (h.boss_type != 0 ? 1u : 0u) | ((uint32_t)(h.boss_type & 0xFF) << 8);
+  sts128(obs + 144, q);
+  // 160: action_mask_bits | action_mask[0..7]
+  uint32_t mlo = (uint32_t)mask, mhi = (uint32_t)(mask >> 32);
+  q.x = mlo; q.y = mhi; q.z = spread4(mlo); q.w = spread4(mlo >> 4);
+  sts128(obs + 160, q);
+  // 176: action_mask[8..23]
+  q.x = spread4(mlo >> 8); q.y = spread4(mlo >> 12); q.z = spread4(mlo >> 16); q.w = spread4(mlo >> 20);
+  sts128(obs + 176, q);
+  // 192: action_mask[24..39]
+  q.x = spread4(mlo >> 24); q.y = spread4(mlo >> 28); q.z = spread4(mhi); q.w = spread4(mhi >> 4);
+  sts128(obs + 192, q);
+  // 208: action_mask[40..55]
+  q.x = spread4(mhi >> 8); q.y = spread4(mhi >> 12); q.z = spread4(mhi >> 16); q.w = spread4(mhi >> 20);
+  sts128(obs + 208, q);
+  // 224: action_mask[56..59] | pad
+  q.x = spread4(mhi >> 24); q.y = 0; q.z = 0; q.w = 0;
+  sts128(obs + 224, q);
+}
+
+}  // namespace bgym

@@ -1,0 +1,181 @@
+"""BalatroEnv — the Gymnasium facade (N = 1) over the device vector env.
+
+Same public surface as the reference class `balatro_gym/balatro_env_2.py::BalatroEnv` (:354):
+    BalatroEnv(*, render_mode=None, seed=None)          :359
+    reset(*, seed=None, options=None) -> (obs, info)     :505
+    step(action) -> (obs, reward, terminated, truncated, info)   :616
+    action_space = Discrete(60)                          :368
+    observation_space = Dict(...)                        :386-470 (the 31 keys actually emitted)
+    save_state() / load_state()                          :1575 / :1595
+    make_balatro_env(**kw) thunk                         :1803
+Error convention as in the reference: a masked action returns reward -1.0 and
+info['error'] without raising (:626-627).
+
+Replaying the reference's shuffle: the reference shuffles with CPython's
+`random.Random(seed % 2**32).shuffle` (stream 0 of DeterministicRNG, :84-106, :525); pass
+`options={'shuffle': 'reference'}` (default when a seed is given) to replay that permutation
+stream on reset so episodes start from the same deck as `BalatroEnv(seed=s)` in the reference;
+`options={'shuffle': 'philox'}` uses the native counter-based stream.
+"""
+from __future__ import annotations
+
+import random as _pyrandom
+from typing import Optional
+
+import numpy as np
+
+from . import layout as L
+from .vec_env import BalatroVecEnv
+
+try:  # real gymnasium if present, else the constructor-only stand-ins
+    import gymnasium as _gym
+    from gymnasium import spaces as _spaces
+    _EnvBase = _gym.Env
+except Exception:  # pragma: no cover - this image has no gymnasium
+    _gym = None
+    from . import _spaces
+    _EnvBase = object
+
+_HAND_TYPE_NAMES = ["HIGH_CARD", "ONE_PAIR", "TWO_PAIR", "THREE_KIND", "STRAIGHT", "FLUSH", "FULL_HOUSE",
+                    "FOUR_KIND", "STRAIGHT_FLUSH", "FIVE_KIND", "FLUSH_HOUSE", "FLUSH_FIVE"]
+_ERR_TEXT = {L.ERR_INVALID_ACTION: "Invalid action", L.ERR_BOSS_RESTRICTION: "Boss blind restriction",
+             L.ERR_CONSUMABLE_FAILED: "Failed to use consumable", L.ERR_SHOP: "Shop error",
+             L.ERR_REF_EXCEPTION: "reference raises here (SafeBalatroEnv convention applied)",
+             L.ERR_UNSUPPORTED: "unsupported consumable"}
+
+
+def reference_deck(seed: int) -> np.ndarray:
+    """The deck the reference builds for `seed`: suit-major/rank-minor order (:519-522) shuffled by
+    `random.Random((seed + 0*1000) % 2**32).shuffle` (:105, :525).  Returns 52 card codes."""
+    deck = [(rank - 2) * 4 + suit for suit in range(4) for rank in range(2, 15)]
+    _pyrandom.Random(seed % (2 ** 32)).shuffle(deck)
+    return np.asarray(deck, dtype=np.uint8)
+
+
+def observation_space():
+    S = _spaces
+    return S.Dict({
+        'hand': S.Box(-1, 51, (8,), dtype=np.int8), 'hand_size': S.Box(0, 12, (), dtype=np.int8),
+        'deck_size': S.Box(0, 52, (), dtype=np.int8), 'selected_cards': S.MultiBinary(8),
+        'chips_scored': S.Box(0, 10_000_000_000, (), dtype=np.int64),
+        'round_chips_scored': S.Box(0, 10_000_000, (), dtype=np.int32),
+        'progress_ratio': S.Box(0.0, 2.0, (), dtype=np.float32), 'mult': S.Box(0, 10_000, (), dtype=np.int32),
+        'chips_needed': S.Box(0, 10_000_000, (), dtype=np.int32), 'money': S.Box(-20, 999, (), dtype=np.int32),
+        'ante': S.Box(1, 1000, (), dtype=np.int16), 'round': S.Box(1, 3, (), dtype=np.int8),
+        'hands_left': S.Box(0, 12, (), dtype=np.int8), 'discards_left': S.Box(0, 10, (), dtype=np.int8),
+        'joker_count': S.Box(0, 10, (), dtype=np.int8), 'joker_ids': S.Box(0, 200, (10,), dtype=np.int16),
+        'joker_slots': S.Box(0, 10, (), dtype=np.int8), 'consumable_count': S.Box(0, 5, (), dtype=np.int8),
+        'consumables': S.Box(0, 100, (5,), dtype=np.int16), 'consumable_slots': S.Box(0, 5, (), dtype=np.int8),
+        'shop_items': S.Box(0, 300, (10,), dtype=np.int16), 'shop_costs': S.Box(0, 5000, (10,), dtype=np.int16),
+        'shop_rerolls': S.Box(0, 999, (), dtype=np.int16), 'hand_levels': S.Box(0, 15, (12,), dtype=np.int8),
+        'phase': S.Box(0, 3, (), dtype=np.int8), 'action_mask': S.MultiBinary(L.NUM_ACTIONS),
+        'hands_played': S.Box(0, 10000, (), dtype=np.int32),
+        'best_hand_this_ante': S.Box(0, 10_000_000, (), dtype=np.int32),
+        'boss_blind_active': S.Box(0, 1, (), dtype=np.int8), 'boss_blind_type': S.Box(0, 30, (), dtype=np.int8),
+        'face_down_cards': S.MultiBinary(8),
+    })
+
+
+class BalatroEnv(_EnvBase):
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 4}
+
+    def __init__(self, *, render_mode: Optional[str] = None, seed: Optional[int] = None, device="cuda"):
+        self.render_mode = render_mode
+        self._seed = seed if seed else int(np.random.randint(1, 2 ** 31 - 1))
+        self.vec = BalatroVecEnv(1, device=device, seed=self._seed, autoreset=False)
+        self.action_space = _spaces.Discrete(L.NUM_ACTIONS)
+        self.observation_space = observation_space()
+        self.reset()
+
+    # -- conversions ---------------------------------------------------------------------------------
+    def _obs(self):
+        rec = self.vec.obs_numpy()[0]
+        out = {}
+        for k in L.OBS_KEYS:
+            v = rec[k]
+            out[k] = v.copy() if isinstance(v, np.ndarray) else v
+        return out
+
+    def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
+        if seed is not None and seed != 0:
+            self._seed = int(seed)
+        mode = (options or {}).get("shuffle", "reference")
+        torch = self.vec.torch
+        seeds = torch.tensor([self._seed], dtype=torch.int64)
+        decks = torch.from_numpy(reference_deck(self._seed)[None, :]) if mode == "reference" else None
+        self.vec.reset(seeds=seeds, decks52=decks)
+        return self._obs(), {}
+
+    def step(self, action: int):
+        torch = self.vec.torch
+        a = torch.tensor([int(action)], dtype=torch.int32, device=self.vec.device)
+        self.vec.step(a)
+        inf = self.vec.info_numpy()[0]
+        info = {}
+        if inf["error_code"]:
+            info["error"] = _ERR_TEXT.get(int(inf["error_code"]), "error")
+        if inf["flags"] & L.F_PLAYED:
+            info["final_score"] = int(inf["final_score"])
+            info["hand_type"] = int(inf["hand_type"])
+            info["hand_type_name"] = _HAND_TYPE_NAMES[int(inf["hand_type"])]
+            info["cards_played"] = int(inf["cards_played"])
+            info["score_breakdown"] = {"final_chips": int(inf["chips"]), "final_mult": int(inf["mult"]),
+                                       "final_x_mult": float(inf["x_mult"]), "final_score": int(inf["base_score"])}
+        if inf["flags"] & L.F_BEAT_BLIND:
+            info["beat_blind"] = True
+        if inf["flags"] & L.F_FAILED:
+            info["failed"] = True
+        if inf["flags"] & L.F_GUARD_TERMINATED:
+            info["terminated"] = "guard"
+        reward = float(self.vec.reward.cpu()[0])
+        terminated = bool(self.vec.terminated.cpu()[0])
+        return self._obs(), reward, terminated, False, info
+
+    def action_masks(self):
+        return self._obs()["action_mask"].astype(bool)
+
+    @property
+    def state(self):
+        """Host copy of the env's state record (numpy record of layout.STATE_DTYPE)."""
+        return self.vec.state_numpy()[0]
+
+    def save_state(self):
+        return self.vec.save_state()
+
+    def load_state(self, saved):
+        self.vec.load_state(saved)
+
+    def render(self):
+        if self.render_mode != "human":
+            return
+        s = self.state
+        print(f"Ante {s['ante']} Round {s['round']} Phase {s['phase']} | score {s['round_chips']}/{s['chips_needed']} "
+              f"| total {s['chips_scored']} | ${s['money']} | hands {s['hands_left']} discards {s['discards_left']}")
+
+    def close(self):
+        return None
+
+
+def make_balatro_env(**kwargs):
+    """Factory thunk, as balatro_env_2.py:1803-1807."""
+    def _init():
+        return BalatroEnv(**kwargs)
+    return _init
+
+
+_REGISTRY = {"BalatroGym-v0": BalatroEnv}
+
+
+def make(id: str, **kwargs):
+    """`gym.make("BalatroGym-v0")` (README.md:37 of the reference, which never registers it)."""
+    if _gym is not None:
+        return _gym.make(id, **kwargs)
+    return _REGISTRY[id](**kwargs)
+
+
+def register_envs():
+    if _gym is not None:
+        try:
+            _gym.register(id="BalatroGym-v0", entry_point="balatro_gym_b200.env:BalatroEnv")
+        except Exception:
+            pass

@@ -1,0 +1,258 @@
+"""BalatroVecEnv — the vector-env entry point: N Balatro envs as device-resident record arrays
+advanced by the sm_100a kernels through the C-ABI (include/bgym.h).
+
+Mirrors the reference's step path for N envs at once:
+    BalatroEnv.reset   balatro_gym/balatro_env_2.py:505-558
+    BalatroEnv.step    balatro_gym/balatro_env_2.py:616-1064, 1174-1392
+and the vector conventions of its consumers (SB3 `SubprocVecEnv`, hpc_train.py:57-72):
+same-step autoreset, `step_async/step_wait`, observations as a dict of arrays.
+
+PyTorch is used for device memory and streams only; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import layout as L
+from . import _lib
+
+# observation field -> (byte offset, torch dtype name, count)
+_OBS_FIELDS = {}
+for _name in L.OBS_DTYPE.names:
+    _dt, _off = L.OBS_DTYPE.fields[_name][:2]
+    _base = _dt.base
+    _cnt = int(np.prod(_dt.shape)) if _dt.shape else 0
+    _OBS_FIELDS[_name] = (_off, _base.str, _cnt)
+
+_TORCH_DT = {"|i1": "int8", "|u1": "uint8", "<i2": "int16", "<i4": "int32", "<i8": "int64", "<f4": "float32",
+             "<u8": "int64", "<u4": "int32", "<u2": "int16"}
+
+
+def _field_view(torch, buf_u8, dtype_np, name):
+    """Zero-copy typed view of one record field over a [N, record_bytes] uint8 tensor."""
+    dt, off = dtype_np.fields[name][:2]
+    base = dt.base
+    size = dt.itemsize
+    tdt = getattr(torch, _TORCH_DT[base.str])
+    v = buf_u8[:, off:off + size]
+    if base.itemsize > 1:
+        v = v.view(tdt)
+    elif base.str == "|i1":
+        v = v.view(torch.int8)
+    return v if dt.shape else v[:, 0]
+
+
+class BalatroVecEnv:
+    """N environments on one GPU.
+
+    Parameters
+    ----------
+    num_envs : number of environments in this slab
+    device   : torch device (must be CUDA)
+    seed     : base seed; env i of rank r gets seed `seed + env_offset + i` (>= 1)
+    autoreset: re-initialise terminated envs inside the step kernel (same-step autoreset)
+    env_offset: global index of the first env of this slab (multi-GPU: results do not depend on
+               the number of GPUs because seeds are a function of the global env index)
+    """
+
+    num_actions = L.NUM_ACTIONS
+
+    def __init__(self, num_envs: int, device="cuda", seed: int = 1, autoreset: bool = True, env_offset: int = 0):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.BgymError("BalatroVecEnv needs a CUDA device; there is no CPU fallback")
+        self.num_envs = int(num_envs)
+        self.autoreset = bool(autoreset)
+        self.base_seed = int(seed)
+        self.env_offset = int(env_offset)
+        n, dev = self.num_envs, self.device
+        with torch.cuda.device(dev):
+            self.state = torch.zeros((n, L.STATE_BYTES), dtype=torch.uint8, device=dev)
+            self.obs_buf = torch.zeros((n, L.OBS_BYTES), dtype=torch.uint8, device=dev)
+            self.info_buf = torch.zeros((n, L.INFO_BYTES), dtype=torch.uint8, device=dev)
+            self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
+            self.terminated = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self.truncated = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self.actions = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._mask64 = torch.zeros(n, dtype=torch.int64, device=dev)
+            # episode statistics (K6)
+            self._ret_acc = torch.zeros(n, dtype=torch.float64, device=dev)
+            self._len_acc = torch.zeros(n, dtype=torch.int32, device=dev)
+            self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._obs_views: Optional[Dict[str, "torch.Tensor"]] = None
+        self._step_count = 0
+        self._pending_actions = None
+        self.observation_keys = list(L.OBS_KEYS)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ptr(self, t):
+        return None if t is None else t.data_ptr()
+
+    def default_seeds(self):
+        torch = self.torch
+        s = torch.arange(self.num_envs, dtype=torch.int64, device=self.device) + (self.base_seed + self.env_offset)
+        s = s % (2 ** 32)
+        s = torch.where(s == 0, torch.ones_like(s), s)  # seed 0 is "random" in the reference
+        return s.to(torch.int64)
+
+    @property
+    def obs(self) -> Dict[str, "object"]:
+        """The 31-key observation dict of the reference as zero-copy views of the obs records."""
+        if self._obs_views is None:
+            self._obs_views = {k: _field_view(self.torch, self.obs_buf, L.OBS_DTYPE, k) for k in L.OBS_KEYS}
+            self._obs_views["action_mask_bits"] = _field_view(self.torch, self.obs_buf, L.OBS_DTYPE, "action_mask_bits")
+        return self._obs_views
+
+    def info_field(self, name):
+        return _field_view(self.torch, self.info_buf, L.INFO_DTYPE, name)
+
+    def state_field(self, name):
+        return _field_view(self.torch, self.state, L.STATE_DTYPE, name)
+
+    # -- reset -------------------------------------------------------------------------------------
+    def reset(self, seeds=None, decks52=None, reset_mask=None):
+        """Reset envs (all, or those with reset_mask != 0).
+
+        seeds   : int64/uint32 tensor [N] (default: base_seed + global env index)
+        decks52 : optional uint8 tensor [N, 52] of card codes = replay of the reference's shuffle
+                  (deck[i] = code of the i-th card after `random.Random(seed).shuffle`)
+        """
+        torch = self.torch
+        if seeds is None:
+            seeds = self.default_seeds()
+        # int32 storage holds the uint32 bit pattern
+        seeds32 = (torch.as_tensor(seeds, device=self.device).to(torch.int64) & 0xFFFFFFFF)
+        seeds32 = torch.where(seeds32 >= 2 ** 31, seeds32 - 2 ** 32, seeds32).to(torch.int32).contiguous()
+        if decks52 is not None:
+            decks52 = torch.as_tensor(decks52, device=self.device).to(torch.uint8).contiguous()
+            assert decks52.shape == (self.num_envs, 52)
+        if reset_mask is not None:
+            reset_mask = torch.as_tensor(reset_mask, device=self.device).to(torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            rc = self.lib.bgym_reset(self.state.data_ptr(), self.obs_buf.data_ptr(), self._ptr(reset_mask),
+                                     seeds32.data_ptr(), self._ptr(decks52), self.num_envs, 0, self._stream())
+        _lib.check(rc, "bgym_reset")
+        self._keep = (seeds32, decks52, reset_mask)  # keep inputs alive until the stream has consumed them
+        return self.obs
+
+    # -- step --------------------------------------------------------------------------------------
+    def step(self, actions=None, draws=None, random_policy: bool = False, want_info: bool = True):
+        """One step for all envs.  Returns (obs, reward, terminated, truncated, info_buf).
+
+        actions : int32 tensor [N] on the device (ignored with random_policy=True, in which case the
+                  kernel samples a uniform legal action per env and writes it to self.actions)
+        draws   : optional uint8 tensor [N, 256] of BgymDraws records (replay mode)
+        """
+        torch = self.torch
+        if not random_policy:
+            if actions is None:
+                raise ValueError("actions is required unless random_policy=True")
+            if actions.dtype != torch.int32 or actions.device != self.device or not actions.is_contiguous():
+                actions = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
+            act = actions
+        else:
+            act = self.actions
+        flags = (L.FLAG_AUTORESET if self.autoreset else 0) | (4 if random_policy else 0)
+        if draws is not None:
+            draws = torch.as_tensor(draws, device=self.device).contiguous()
+            assert draws.dtype == torch.uint8 and draws.shape == (self.num_envs, L.DRAWS_BYTES)
+        with torch.cuda.device(self.device):
+            rc = self.lib.bgym_step(self.state.data_ptr(), act.data_ptr(), self._ptr(draws), self.obs_buf.data_ptr(),
+                                    self.reward.data_ptr(), self.terminated.data_ptr(), self.truncated.data_ptr(),
+                                    self.info_buf.data_ptr() if want_info else None, self.num_envs, flags, self._stream())
+        _lib.check(rc, "bgym_step")
+        self._keep = (act, draws)
+        self._step_count += 1
+        return self.obs, self.reward, self.terminated, self.truncated, self.info_buf
+
+    # SB3 VecEnv-style split call
+    def step_async(self, actions):
+        self._pending_actions = actions
+
+    def step_wait(self):
+        out = self.step(self._pending_actions)
+        self._pending_actions = None
+        return out
+
+    def sample_actions(self, seed: int = 0, out=None):
+        """Uniform random legal action per env from the current observation's mask word."""
+        out = self.actions if out is None else out
+        with self.torch.cuda.device(self.device):
+            rc = self.lib.bgym_sample_actions(self.obs_buf.data_ptr(), out.data_ptr(), seed & 0xFFFFFFFF,
+                                              self._step_count, self.num_envs, self._stream())
+        _lib.check(rc, "bgym_sample_actions")
+        return out
+
+    def action_masks(self):
+        """uint64 mask word per env computed from the state (bit a = action a legal), as int64."""
+        with self.torch.cuda.device(self.device):
+            rc = self.lib.bgym_action_mask(self.state.data_ptr(), self._mask64.data_ptr(), self.num_envs, self._stream())
+        _lib.check(rc, "bgym_action_mask")
+        return self._mask64
+
+    def accumulate_stats(self):
+        """Fold the last step's (reward, terminated) into the slab statistics (device side)."""
+        with self.torch.cuda.device(self.device):
+            rc = self.lib.bgym_episode_stats(self.reward.data_ptr(), self.terminated.data_ptr(), self._ret_acc.data_ptr(),
+                                             self._len_acc.data_ptr(), self.stats.data_ptr(), self.num_envs, self._stream())
+        _lib.check(rc, "bgym_episode_stats")
+        return self.stats
+
+    # -- checkpoint (save_state / load_state, balatro_env_2.py:1575-1615) ----------------------------
+    def save_state(self):
+        return {"state": self.state.clone(), "step_count": self._step_count,
+                "ret_acc": self._ret_acc.clone(), "len_acc": self._len_acc.clone()}
+
+    def load_state(self, ckpt):
+        self.state.copy_(ckpt["state"])
+        self._step_count = ckpt["step_count"]
+        self._ret_acc.copy_(ckpt["ret_acc"])
+        self._len_acc.copy_(ckpt["len_acc"])
+
+    # -- state injection (the C3 state generator of SURVEY §8d; reference: Appendix E) ---------------
+    def inject_numpy(self, state_np: np.ndarray):
+        """Overwrite all state records from a host array of L.STATE_DTYPE."""
+        assert state_np.dtype == L.STATE_DTYPE and state_np.shape == (self.num_envs,)
+        t = self.torch.from_numpy(state_np.view(np.uint8).reshape(self.num_envs, L.STATE_BYTES).copy())
+        self.state.copy_(t)
+
+    def state_numpy(self) -> np.ndarray:
+        return self.state.cpu().numpy().reshape(-1).view(L.STATE_DTYPE).copy()
+
+    def obs_numpy(self) -> np.ndarray:
+        return self.obs_buf.cpu().numpy().reshape(-1).view(L.OBS_DTYPE).copy()
+
+    def info_numpy(self) -> np.ndarray:
+        return self.info_buf.cpu().numpy().reshape(-1).view(L.INFO_DTYPE).copy()
+
+    def randomize_c3(self, seed: int = 0):
+        """Config-3 state generator, applied on the device right after reset():
+        5 distinct random shop-eligible jokers, per-deck-card modifiers i.i.d. (enhancement != NONE
+        w.p. 0.25 uniform over 8; edition w.p. 0.1 over {FOIL,HOLO,POLY}; seal w.p. 0.1 over 4)."""
+        torch = self.torch
+        n, dev = self.num_envs, self.device
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed + 7919 * (self.env_offset + 1))
+        # 5 distinct jokers out of ids 1..145: top-5 of random keys
+        keys = torch.rand((n, 145), device=dev, generator=g)
+        jk = (keys.topk(5, dim=1).indices + 1).to(torch.uint8)
+        self.state[:, 80:85] = jk
+        self.state[:, 22] = 5
+        enh = torch.where(torch.rand((n, 52), device=dev, generator=g) < 0.25,
+                          torch.randint(1, 9, (n, 52), device=dev, generator=g), torch.zeros((n, 52), dtype=torch.int64, device=dev))
+        ed = torch.where(torch.rand((n, 52), device=dev, generator=g) < 0.1,
+                         torch.randint(1, 4, (n, 52), device=dev, generator=g), torch.zeros((n, 52), dtype=torch.int64, device=dev))
+        seal = torch.where(torch.rand((n, 52), device=dev, generator=g) < 0.1,
+                           torch.randint(1, 5, (n, 52), device=dev, generator=g), torch.zeros((n, 52), dtype=torch.int64, device=dev))
+        deck = self.state[:, 128:232].view(torch.int16).to(torch.int64) & 63
+        deck = deck | (enh << 6) | (ed << 10) | (seal << 13)
+        deck = torch.where(deck >= 2 ** 15, deck - 2 ** 16, deck).to(torch.int16)
+        self.state[:, 128:232] = deck.view(torch.uint8)

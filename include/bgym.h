@@ -36,7 +36,7 @@ extern "C" {
 #define BGYM_ABI_VERSION 1
 
 /* ---- sizes ------------------------------------------------------------- */
-#define BGYM_STATE_BYTES 320
+#define BGYM_STATE_BYTES 304
 #define BGYM_OBS_BYTES   240
 #define BGYM_INFO_BYTES  32
 #define BGYM_DRAWS_BYTES 256
@@ -102,7 +102,10 @@ enum { BGYM_F_BEAT_BLIND = 1, BGYM_F_FAILED = 2, BGYM_F_GUARD_TERMINATED = 4, BG
 enum {
   BGYM_FLAG_AUTORESET = 1,  /* step: a terminated env is re-initialised in place (native Philox shuffle)
                                and the returned observation is the first of the new episode */
-  BGYM_FLAG_NO_OBS = 2      /* skip observation emission (obs may be NULL) */
+  BGYM_FLAG_NO_OBS = 2,     /* skip observation emission (obs may be NULL) */
+  BGYM_FLAG_RANDOM_POLICY = 4 /* step: every env draws its own uniform random LEGAL action from its mask
+                               (the policy the reference is benchmarked with); `actions` becomes an
+                               OUTPUT array that receives the chosen actions */
 };
 /* flags argument of bgym_score_hands */
 enum {
@@ -115,63 +118,66 @@ enum {
 #define BGYM_E_NODEV   (-2)
 #define BGYM_E_ALIGN   (-3)
 
-/* ---- per-env state record (320 B, 16-byte aligned) ------------------------
+/* ---- per-env state record (304 B = 19 x 16 B, 16-byte aligned) --------------
  * Restates UnifiedGameState (balatro_env_2.py:166-211) + BalatroGame (balatro_game.py:16-28)
  * + ScoreEngine levels/counts (scoring_engine.py:65-69) + BossBlindManager.blind_state
- * (boss_blinds.py:311-319) + Shop inventory (shop.py:96-148).  SURVEY.md Appendix D. */
+ * (boss_blinds.py:311-319) + Shop inventory (shop.py:96-148).  SURVEY.md Appendix D counts the
+ * same information as 320 B; the physical record is 304 B so that a tile of records staged in
+ * shared memory has an odd 16-byte stride (bank-conflict-free 128-bit access per lane). */
 typedef struct BgymState {
   /* hot block, bytes 0..127 */
   uint8_t  hand[8];            /*   0 hand_indexes: deck index per hand slot, 0xFF = empty          */
-  uint8_t  hand_code[8];       /*   8 cache: card code of deck[hand[i]], 0xFF = none                */
-  uint8_t  hand_n;             /*  16 len(hand_indexes)                                             */
-  uint8_t  hand_size;          /*  17 state.hand_size / game.hand_size                              */
-  uint8_t  sel_n;              /*  18 len(selected_cards)                                           */
-  uint8_t  highlight_mask;     /*  19 game.highlighted_indexes as a bit set over hand slots         */
-  uint32_t sel_order;          /*  20 selected_cards, ordered: nibble k = slot of k-th selection    */
-  uint8_t  face_down_mask;     /*  24 face_down_cards as a bit set over hand slots                  */
-  uint8_t  phase;              /*  25                                                               */
-  uint8_t  round;              /*  26 1 small, 2 big, 3 boss                                        */
-  uint8_t  boss_type;          /*  27 active BossBlindType (boss_blinds.py:18-47), 0 = none         */
-  uint8_t  hands_left;         /*  28                                                               */
-  uint8_t  discards_left;      /*  29                                                               */
-  uint8_t  joker_n;            /*  30                                                               */
-  uint8_t  cons_n;             /*  31                                                               */
-  uint8_t  joker_slots;        /*  32                                                               */
-  uint8_t  cons_slots;         /*  33                                                               */
-  uint8_t  n_magic_trick;      /*  34 vouchers.count('Magic Trick')                                 */
-  uint8_t  n_minimalist;       /*  35 vouchers.count('Minimalist')                                  */
-  int16_t  ante;               /*  36                                                               */
-  int16_t  jokers_sold;        /*  38                                                               */
-  int32_t  money;              /*  40                                                               */
-  int32_t  chips_needed;       /*  44                                                               */
-  int64_t  round_chips;        /*  48 round_chips_scored                                            */
-  int64_t  chips_scored;       /*  56                                                               */
-  int32_t  best_hand;          /*  64 best_hand_this_ante (saturating)                              */
-  int32_t  hands_played_total; /*  68                                                               */
-  int16_t  hands_played_ante;  /*  72                                                               */
-  uint8_t  boss_flags;         /*  74 bit0 = blind_state['first_hand']                              */
-  uint8_t  boss_cards_required;/*  75 blind_state['cards_required'] (The Verdant)                   */
-  uint16_t boss_played_types;  /*  76 blind_state['played_hand_types'] as a bit set over HandType   */
-  uint8_t  boss_hands_played;  /*  78 blind_state['hands_played']                                   */
-  uint8_t  deck_n;             /*  79 len(deck)                                                     */
-  uint64_t boss_played_cards;  /*  80 blind_state['played_cards'] as a bit set over deck indices    */
-  uint8_t  joker_id[8];        /*  88 JOKER_LIBRARY ids (jokers.py:11-162), 0 = empty               */
-  uint8_t  cons_id[8];         /*  96 consumable ids, 0 = empty                                     */
-  uint8_t  hand_level[12];     /* 104 state.hand_levels (uncapped); engine level = min(level, 15)   */
-  int32_t  shop_reroll_state;  /* 116 state.shop_reroll_cost (stale copy used by the mask)          */
-  uint32_t rng_seed;           /* 120 native mode: Philox key word 0                                */
-  uint32_t rng_ctr;            /* 124 native mode: Philox counter (blocks consumed)                 */
-  /* deck block, bytes 128..255 */
+  uint8_t  hand_n;             /*   8 len(hand_indexes)                                             */
+  uint8_t  hand_size;          /*   9 state.hand_size / game.hand_size                              */
+  uint8_t  sel_n;              /*  10 len(selected_cards)                                           */
+  uint8_t  highlight_mask;     /*  11 game.highlighted_indexes as a bit set over hand slots         */
+  uint32_t sel_order;          /*  12 selected_cards, ordered: nibble k = slot of k-th selection    */
+  uint8_t  face_down_mask;     /*  16 face_down_cards as a bit set over hand slots                  */
+  uint8_t  phase;              /*  17                                                               */
+  uint8_t  round;              /*  18 1 small, 2 big, 3 boss                                        */
+  uint8_t  boss_type;          /*  19 active BossBlindType (boss_blinds.py:18-47), 0 = none         */
+  uint8_t  hands_left;         /*  20                                                               */
+  uint8_t  discards_left;      /*  21                                                               */
+  uint8_t  joker_n;            /*  22                                                               */
+  uint8_t  cons_n;             /*  23                                                               */
+  uint8_t  joker_slots;        /*  24                                                               */
+  uint8_t  cons_slots;         /*  25                                                               */
+  uint8_t  n_magic_trick;      /*  26 vouchers.count('Magic Trick')                                 */
+  uint8_t  n_minimalist;       /*  27 vouchers.count('Minimalist')                                  */
+  int16_t  ante;               /*  28                                                               */
+  int16_t  jokers_sold;        /*  30                                                               */
+  int32_t  money;              /*  32                                                               */
+  int32_t  chips_needed;       /*  36                                                               */
+  int64_t  round_chips;        /*  40 round_chips_scored                                            */
+  int64_t  chips_scored;       /*  48                                                               */
+  int32_t  best_hand;          /*  56 best_hand_this_ante (saturating)                              */
+  int32_t  hands_played_total; /*  60                                                               */
+  int16_t  hands_played_ante;  /*  64                                                               */
+  uint8_t  boss_flags;         /*  66 bit0 = blind_state['first_hand']                              */
+  uint8_t  boss_cards_required;/*  67 blind_state['cards_required'] (The Verdant)                   */
+  uint16_t boss_played_types;  /*  68 blind_state['played_hand_types'] as a bit set over HandType   */
+  uint8_t  boss_hands_played;  /*  70 blind_state['hands_played']                                   */
+  uint8_t  deck_n;             /*  71 len(deck)                                                     */
+  uint64_t boss_played_cards;  /*  72 blind_state['played_cards'] as a bit set over deck indices    */
+  uint8_t  joker_id[8];        /*  80 JOKER_LIBRARY ids (jokers.py:11-162), 0 = empty               */
+  uint8_t  cons_id[8];         /*  88 consumable ids, 0 = empty                                     */
+  uint8_t  hand_level[12];     /*  96 state.hand_levels (uncapped); engine level = min(level, 15)   */
+  int32_t  shop_reroll_state;  /* 108 state.shop_reroll_cost (stale copy used by the mask)          */
+  uint32_t rng_seed;           /* 112 native mode: Philox key word 0                                */
+  uint32_t rng_ctr;            /* 116 native mode: Philox counter (blocks consumed)                 */
+  uint32_t ep_len;             /* 120 valid steps taken in the current episode                      */
+  uint32_t episode;            /* 124 episodes finished by in-kernel autoreset                      */
+  /* deck block, bytes 128..243 */
   uint16_t deck[52];           /* 128 card16 per deck index                                         */
-  uint16_t hand_play_count[12];/* 232 engine.hand_play_counts                                       */
-  /* shop block, bytes 256..319 */
-  uint8_t  item_type[9];       /* 256 shop.inventory[i].item_type                                   */
-  uint8_t  item_id[9];         /* 265 joker id / pack kind / voucher kind / card int                */
-  uint8_t  n_items;            /* 274                                                               */
-  uint8_t  _pad0;              /* 275                                                               */
-  int32_t  item_cost[9];       /* 276                                                               */
-  int32_t  reroll_cost;        /* 312 shop.reroll_cost (grows x1.35 per reroll)                     */
-  uint32_t ep_len;             /* 316 steps taken in the current episode                            */
+  uint8_t  hand_play_count[12];/* 232 engine.hand_play_counts, saturating at 255 (never read by the
+                                      reference's step path; kept for save_state)                   */
+  /* shop block, bytes 244..303 */
+  uint8_t  item_type[9];       /* 244 shop.inventory[i].item_type                                   */
+  uint8_t  item_id[9];         /* 253 joker id / pack kind / voucher kind / card int                */
+  uint8_t  n_items;            /* 262                                                               */
+  uint8_t  _pad0;              /* 263                                                               */
+  int32_t  item_cost[9];       /* 264                                                               */
+  int32_t  reroll_cost;        /* 300 shop.reroll_cost (grows x1.35 per reroll)                     */
 } BgymState;
 
 /* ---- observation record (240 B) ---------------------------------------------
@@ -267,8 +273,9 @@ int bgym_reset(BgymState* state, BgymObs* obs, const uint8_t* reset_mask, const 
                const uint8_t* decks52, int64_t n, int flags, void* stream);
 
 /* step: one BalatroEnv.step per env (balatro_env_2.py:616-1064, 1174-1392).
- * draws == NULL -> native Philox mode.  info may be NULL. truncated is always 0. */
-int bgym_step(BgymState* state, const int32_t* actions, const BgymDraws* draws, BgymObs* obs,
+ * draws == NULL -> native Philox mode.  info may be NULL. truncated is always 0.
+ * `actions` is read (written instead with BGYM_FLAG_RANDOM_POLICY). */
+int bgym_step(BgymState* state, int32_t* actions, const BgymDraws* draws, BgymObs* obs,
               double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
               int64_t n, int flags, void* stream);
 

@@ -55,30 +55,46 @@ typedef struct Rng {
   BgymState* s;            /* native: seed/counter live in the state */
   const BgymDraws* tape;   /* replay: NULL in native mode */
   int iu, ik;
+  uint32_t buf[4]; int pos; /* native: words of the current Philox block; pos == 4 -> empty.
+                               Left-over words are dropped at the end of each step/reset call. */
 } Rng;
 
-/* uniform in [0,1) with CPython's 53-bit construction (random.random) */
+static void rng_init(Rng* r, BgymState* s, const BgymDraws* tape) {
+  r->s = s; r->tape = tape; r->iu = 0; r->ik = 0; r->pos = 4;
+}
+
+static uint32_t rng_word(Rng* r) {
+  if (r->pos == 4) {
+    philox4x32_10(r->s->rng_ctr++, 0, 0, 0, r->s->rng_seed, PHILOX_KEY1, r->buf);
+    r->pos = 0;
+  }
+  return r->buf[r->pos++];
+}
+
+/* uniform in [0,1) with CPython's 53-bit construction (random.random: (a>>5, b>>6)) */
 static double rng_u01(Rng* r) {
   if (r->tape) return r->tape->u[r->iu++];
-  uint32_t w[4];
-  philox4x32_10(r->s->rng_ctr++, 0, 0, 0, r->s->rng_seed, PHILOX_KEY1, w);
-  uint32_t a = w[0] >> 5, b = w[1] >> 6;
+  uint32_t a = rng_word(r) >> 5;
+  uint32_t b = rng_word(r) >> 6;
   return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
 }
 
-/* uniform integer in [0,n): CPython's _randbelow_with_getrandbits (rejection on bit_length(n) bits) */
+/* unbiased uniform integer in [0,n): Lemire's multiply-shift with rejection on 32-bit words
+ * (same distribution as CPython's _randbelow; the mapping from words differs, which is why parity
+ * with the reference goes through replay) */
 static int rng_below(Rng* r, int n) {
   if (r->tape) return r->tape->k[r->ik++];
-  int k = 0;
-  while ((n >> k) != 0) k++;
-  for (;;) {
-    uint32_t w[4];
-    philox4x32_10(r->s->rng_ctr++, 0, 0, 0, r->s->rng_seed, PHILOX_KEY1, w);
-    for (int i = 0; i < 4; i++) {
-      uint32_t v = w[i] >> (32 - k);
-      if ((int)v < n) return (int)v;
+  uint32_t un = (uint32_t)n;
+  uint64_t m = (uint64_t)rng_word(r) * un;
+  uint32_t l = (uint32_t)m;
+  if (l < un) {
+    uint32_t t = (0u - un) % un;
+    while (l < t) {
+      m = (uint64_t)rng_word(r) * un;
+      l = (uint32_t)m;
     }
   }
+  return (int)(m >> 32);
 }
 
 /* k distinct indices out of n, in draw order (random.sample semantics; replay gives them directly) */
@@ -191,7 +207,7 @@ typedef struct ScoreIn {
   /* draws */
   const BgymScoreCtx* replay;                /* non-NULL: use recorded draws */
   uint32_t seed; uint64_t index;             /* native: Philox keyed by (seed, hand index) */
-  uint32_t ctr;
+  uint32_t ctr; uint32_t buf[4]; int pos;
 } ScoreIn;
 
 typedef struct ScoreOut { int chips, mult; double x_mult; int64_t score; int money; } ScoreOut;
@@ -211,23 +227,27 @@ static int name_matches(int ht, int table_names, int hn) {
   return 0;
 }
 
+static uint32_t score_word(ScoreIn* in) {
+  if (in->pos == 4) {
+    philox4x32_10(in->ctr++, (uint32_t)in->index, (uint32_t)(in->index >> 32), 1, in->seed, PHILOX_KEY1, in->buf);
+    in->pos = 0;
+  }
+  return in->buf[in->pos++];
+}
 static double score_u01(ScoreIn* in) {
-  uint32_t w[4];
-  philox4x32_10(in->ctr++, (uint32_t)in->index, (uint32_t)(in->index >> 32), 1, in->seed, PHILOX_KEY1, w);
-  uint32_t a = w[0] >> 5, b = w[1] >> 6;
+  uint32_t a = score_word(in) >> 5;
+  uint32_t b = score_word(in) >> 6;
   return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
 }
 static int score_below(ScoreIn* in, int n) {
-  int k = 0;
-  while ((n >> k) != 0) k++;
-  for (;;) {
-    uint32_t w[4];
-    philox4x32_10(in->ctr++, (uint32_t)in->index, (uint32_t)(in->index >> 32), 1, in->seed, PHILOX_KEY1, w);
-    for (int i = 0; i < 4; i++) {
-      uint32_t v = w[i] >> (32 - k);
-      if ((int)v < n) return (int)v;
-    }
+  uint32_t un = (uint32_t)n;
+  uint64_t m = (uint64_t)score_word(in) * un;
+  uint32_t l = (uint32_t)m;
+  if (l < un) {
+    uint32_t t = (0u - un) % un;
+    while (l < t) { m = (uint64_t)score_word(in) * un; l = (uint32_t)m; }
   }
+  return (int)(m >> 32);
 }
 
 static void score_hand(ScoreIn* in, ScoreOut* out, const uint8_t* levels) {
@@ -381,7 +401,7 @@ int oracle_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8
     in.discards_left = ctx ? ctx[i].discards_left : 3;
     in.deck_len = ctx ? ctx[i].deck_len : 52;
     in.replay = (ctx && ctx[i].use_replay) ? &ctx[i] : NULL;
-    in.seed = seed; in.index = (uint64_t)i; in.ctr = 0;
+    in.seed = seed; in.index = (uint64_t)i; in.ctr = 0; in.pos = 4;
     ScoreOut out;
     score_hand(&in, &out, levels12 ? levels12 + i * 12 : ones);
     hand_type[i] = (uint8_t)in.hand_type;
@@ -398,8 +418,6 @@ int oracle_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8
  * ---------------------------------------------------------------------------------------- */
 static void refresh_hand_codes(BgymState* s) {
   for (int i = 0; i < 8; i++) {
-    if (i < s->hand_n && s->hand[i] < s->deck_n) s->hand_code[i] = (uint8_t)c16_code(s->deck[s->hand[i]]);
-    else s->hand_code[i] = 0xFF;
     if (i >= s->hand_n) s->hand[i] = 0xFF;
   }
 }
@@ -476,7 +494,7 @@ static void write_obs(const BgymState* s, BgymObs* o) {
   for (int k = 0; k < s->sel_n; k++) { int sl = sel_slot(s, k); if (sl < 8) o->selected_cards[sl] = 1; }
   for (int i = 0; i < 8; i++) o->face_down_cards[i] = (s->face_down_mask >> i) & 1;
   o->chips_scored = s->chips_scored;
-  o->round_chips_scored = clamp_i32(s->round_chips);
+  o->round_chips_scored = (int32_t)(uint32_t)(uint64_t)s->round_chips;
   {
     double needed = (double)(s->chips_needed > 1 ? s->chips_needed : 1);
     double p = (double)s->round_chips / needed;
@@ -534,7 +552,6 @@ static void reset_env(BgymState* s, uint32_t seed, const uint8_t* deck52) {
   for (int i = 0; i < 12; i++) s->hand_level[i] = 1;
   s->deck_n = 52;
   memset(s->hand, 0xFF, 8);
-  memset(s->hand_code, 0xFF, 8);
   s->rng_seed = seed; s->rng_ctr = 0;
   if (deck52) {
     for (int i = 0; i < 52; i++) s->deck[i] = deck52[i];
@@ -544,7 +561,8 @@ static void reset_env(BgymState* s, uint32_t seed, const uint8_t* deck52) {
     int k = 0;
     for (int suit = 0; suit < 4; suit++)
       for (int rank = 2; rank <= 14; rank++) s->deck[k++] = (uint16_t)((rank - 2) * 4 + suit);
-    Rng r = {s, NULL, 0, 0};
+    Rng r;
+    rng_init(&r, s, NULL);
     for (int i = 51; i >= 1; i--) {
       int j = rng_below(&r, i + 1);
       uint16_t t = s->deck[i]; s->deck[i] = s->deck[j]; s->deck[j] = t;
@@ -896,7 +914,8 @@ static int joker_named(const BgymState* s, int id) { return joker_owned(s, id); 
 
 static void step_env(BgymState* s, int action, const BgymDraws* tape, double* reward_out,
                      uint8_t* term_out, BgymInfo* info) {
-  Rng rng = {s, tape, 0, 0};
+  Rng rng;
+  rng_init(&rng, s, tape);
   double reward = 0.0;
   int terminated = 0;
   memset(info, 0, sizeof *info);
@@ -1014,7 +1033,7 @@ static void step_env(BgymState* s, int action, const BgymDraws* tape, double* re
       s->hands_played_total += 1;
       s->hands_played_ante += 1;
       if (final_score > s->best_hand) s->best_hand = clamp_i32(final_score);
-      s->hand_play_count[ht]++;
+      if (s->hand_play_count[ht] < 255) s->hand_play_count[ht]++;
       /* boss on_hand_scored :480-507 (Tooth / Serpent write into a throw-away dict — SURVEY Q15) */
       if (s->boss_type) {
         s->boss_played_types |= (uint16_t)(1u << ht);
@@ -1244,15 +1263,30 @@ static void step_env(BgymState* s, int action, const BgymDraws* tape, double* re
   *term_out = (uint8_t)terminated;
 }
 
-int oracle_step(BgymState* state, const int32_t* actions, const BgymDraws* draws, BgymObs* obs,
+int oracle_step(BgymState* state, int32_t* actions, const BgymDraws* draws, BgymObs* obs,
                 double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
                 int64_t n, int flags) {
   for (int64_t i = 0; i < n; i++) {
     BgymInfo inf;
+    if (flags & BGYM_FLAG_RANDOM_POLICY) {
+      /* uniform legal action: Philox keyed (rng_seed, policy key), counter = steps in the episode */
+      uint64_t m = action_mask(&state[i]);
+      int cnt = __builtin_popcountll(m), act = 0;
+      if (cnt) {
+        uint32_t w[4];
+        philox4x32_10(state[i].ep_len, 0, 0, 0, state[i].rng_seed, 0x5A17AC71u, w);
+        int k = (int)(((uint64_t)w[0] * (uint64_t)cnt) >> 32);
+        for (int t = 0; t < k; t++) m &= m - 1;
+        act = __builtin_ctzll(m);
+      }
+      actions[i] = act;
+    }
     step_env(&state[i], actions[i], draws ? &draws[i] : NULL, &reward[i], &terminated[i], &inf);
     if (truncated) truncated[i] = 0;
     if (terminated[i] && (flags & BGYM_FLAG_AUTORESET)) {
+      uint32_t episode = state[i].episode + 1;
       reset_env(&state[i], next_episode_seed(state[i].rng_seed), NULL);
+      state[i].episode = episode;
       inf.flags |= BGYM_F_AUTORESET_DONE;
     }
     if (info) info[i] = inf;

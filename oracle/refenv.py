@@ -113,6 +113,12 @@ class TapRandom(random.Random):
     def Random(self, seed=None):  # lets an instance stand in for the `random` module (shop.py:99)
         return TapRandom(seed, self.log)
 
+    def getrandbits(self, k):
+        # Defining getrandbits keeps Random.__init_subclass__ from switching _randbelow to the
+        # random()-based variant (it does that for subclasses that override random() only), so the
+        # integer draws consume the Mersenne Twister exactly as a plain random.Random does.
+        return super().getrandbits(k)
+
     def random(self):
         v = super().random()
         self.log.append(("u", v))
@@ -269,11 +275,8 @@ class RefEnv:
         hand = list(st.hand_indexes)
         assert len(hand) <= 8
         s["hand"][:] = 0xFF
-        s["hand_code"][:] = 0xFF
         for i, idx in enumerate(hand):
             s["hand"][i] = idx
-            if idx < len(deck):
-                s["hand_code"][i] = card_code(deck[idx])
         s["hand_n"] = len(hand)
         s["hand_size"] = st.hand_size
         sel = list(st.selected_cards)
@@ -336,7 +339,7 @@ class RefEnv:
             s["hand_level"][int(ht)] = st.hand_levels.get(ht, 0)
             assert env.engine.hand_levels[ht] == min(15, max(1, st.hand_levels.get(ht, 1))), \
                 "engine/state hand levels diverged beyond the min(level,15) relation"
-            s["hand_play_count"][int(ht)] = env.engine.hand_play_counts[ht]
+            s["hand_play_count"][int(ht)] = min(255, env.engine.hand_play_counts[ht])
         s["shop_reroll_state"] = st.shop_reroll_cost
         for i, c in enumerate(deck[:52]):
             cs = st.card_states.get(i)
@@ -378,7 +381,7 @@ class RefEnv:
 
 
 # fields of BgymState that have no counterpart in the reference (native RNG bookkeeping)
-STATE_NOCOMPARE = ("rng_seed", "rng_ctr", "ep_len")
+STATE_NOCOMPARE = ("rng_seed", "rng_ctr", "ep_len", "episode")
 
 
 def state_diff(a: np.ndarray, b: np.ndarray, skip=STATE_NOCOMPARE):

@@ -133,6 +133,10 @@ def main():
     w("#include <stdint.h>")
     w("")
     w("#define BGYM_NUM_JOKERS %d" % len(lib))
+    # shop-eligible jokers (base_cost > 0, shop.py:126) are exactly ids 1..K: the kernels rely on it
+    elig = [j.id for j in lib if j.base_cost > 0]
+    assert elig == list(range(1, len(elig) + 1)), "shop-eligible joker ids are not contiguous from 1"
+    w("#define BGYM_NUM_SHOP_JOKERS %d" % len(elig))
     for j in lib:
         w("#define BGYM_J_%s %d" % (ident(j.name), j.id))
     w("")
