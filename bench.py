@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s (and hands-scored/s) of the B200-native Balatro step path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm, one rank per GPU (torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU path
+
+A "step" is one pass of the hot path over one batch of synthetic input: every env of the slab
+takes one uniform-random LEGAL action (sampler kernel + fused step kernel).  The workload is
+BASELINE.json configs[3] ("full run incl. shop, rerolls, planets and consumables, 2^20 envs/GPU",
+state generator = configs[2]: 5 random jokers, enhancements/editions/seals, boss blinds, autoreset);
+configs[1] (2^24-hand scoring microbench) is reported in the same line under "hands".
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each number is taken.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+B_STEP = 872   # canonical algorithmic bytes per env-step
+B_HAND = 32    # canonical algorithmic bytes per scored hand
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            if "hbm_gbs" in d:
+                return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the one place bench.py executes oracle/)
+# -------------------------------------------------------------------------------------------------
+def cpu_env_baseline(config, rounds, warmup_rounds, steps_per_round=1024):
+    from oracle import refenv, refbaseline
+    root = refenv.reference_available()
+    if root is None:
+        # no reference on this box: time the C port instead (kind "port", 1 core)
+        import numpy as np
+        from oracle import coracle
+        from balatro_gym_b200 import layout as L
+        n = 4096
+        ov = coracle.OracleVec(n)
+        ov.reset(np.arange(1, n + 1))
+        act = np.zeros(n, np.int32)
+        ts = []
+        for r in range(rounds + warmup_rounds):
+            t0 = time.perf_counter()
+            for _ in range(16):
+                coracle.step(ov.state, act, ov.obs, ov.reward, ov.terminated, ov.truncated, ov.info, None, flags=L.FLAG_AUTORESET | 4)
+            ts.append(time.perf_counter() - t0)
+        ts = ts[warmup_rounds:]
+        return {"value": n * 16 * len(ts) / sum(ts), "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"C oracle, {n} envs x 16 steps x {len(ts)} rounds, fused random-legal policy, autoreset"}, ts
+    res = refbaseline.run_env_baseline(config, steps_per_round=steps_per_round, rounds=rounds, warmup_rounds=warmup_rounds)
+    total = res["steps_per_round_total"] * len(res["per_round_s"])
+    return {"value": total / sum(res["per_round_s"]), "unit": UNIT, "cores": res["cores"], "kind": "reference",
+            "sample": (f"unmodified reference BalatroEnv ({'byte-compiled oracle/_ref' if root.endswith('_ref') else root}), "
+                       f"{res['cores']} worker processes x {steps_per_round} env-steps x {len(res['per_round_s'])} rounds, "
+                       f"config {config} state generator, random legal actions, no per-step IPC (upper bound of an AsyncVectorEnv)")}, res["per_round_s"]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cfg = "c4"
+    base, per_round = cpu_env_baseline(cfg, rounds=max(1, args.steps), warmup_rounds=max(0, args.warmup), steps_per_round=1024)
+    ms = 1000.0 * sum(per_round) / max(1, len(per_round))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
+        "config": workload_config(args, 0),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n_envs):
+    return {"workload": "BASELINE configs[3]: full run incl. shop/rerolls/planets/consumables with the configs[2] state "
+                        "generator (5 random jokers, enhancements/editions/seals, boss blinds), random legal actions, autoreset",
+            "envs_per_gpu": n_envs, "policy": "uniform random legal action per env",
+            "l2": "inputs larger than L2 (state+obs records of one step = %.0f MB per GPU)" % (n_envs * (304 + 240) / 1e6)}
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import balatro_gym_b200 as b
+    from balatro_gym_b200 import dist as bdist
+    from balatro_gym_b200 import layout as L
+
+    rank, local_rank, ws = bdist.init_process_group("nccl")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    n = args.envs
+    K, W = args.steps, max(args.warmup, 3)
+    peak, peak_src = measured_peak()
+
+    env = b.BalatroVecEnv(n, device=dev, seed=1, autoreset=True, env_offset=rank * n)
+    env.reset()
+    env.randomize_c3(seed=1)
+    launches = 0
+
+    def rollout_step():
+        env.sample_actions(seed=2024)
+        env.step(env.actions, want_info=False)
+
+    # spread the envs over game phases before timing (episodes desynchronise within ~100 steps)
+    for _ in range(args.burn_in):
+        rollout_step()
+    for _ in range(W):
+        rollout_step()
+    torch.cuda.synchronize(dev)
+    bdist.barrier()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 2)]
+    torch.cuda.synchronize(dev)
+    ev[0].record()
+    for k in range(K):
+        env.sample_actions(seed=2024)
+        ev[1 + 2 * k].record()          # step kernel bracket (same stream as the launches)
+        env.step(env.actions, want_info=False)
+        ev[2 + 2 * k].record()
+        launches += 2
+    ev[2 * K + 1].record()
+    torch.cuda.synchronize(dev)
+    bdist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[2 * K + 1])
+    step_kernel_ms = sum(ev[1 + 2 * k].elapsed_time(ev[2 + 2 * k]) for k in range(K)) / K
+    total_ms = bdist.max_over_ranks(total_ms, dev)
+    step_kernel_ms_max = bdist.max_over_ranks(step_kernel_ms, dev)
+    value = ws * n * K / (total_ms / 1000.0)
+    achieved = n * B_STEP / (step_kernel_ms_max / 1000.0) / 1e9      # GB/s, algorithmic bytes
+
+    # fused rollout (policy inside the step kernel): one launch per step
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        env.step(random_policy=True, want_info=False)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    fused_ms = bdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    fused_value = ws * n * K / (fused_ms / 1000.0)
+
+    # episode statistics: one tiny all-reduce per rollout, off the step path
+    env.accumulate_stats()
+    stats = bdist.allreduce_stats(env.stats.clone())
+
+    # ---- e2e: the public API with HOST buffers (pinned), copies inside the timed region ----
+    Ke = max(3, min(K, args.e2e_steps))
+    h_act = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    h_obs = torch.empty((n, L.OBS_BYTES), dtype=torch.uint8, pin_memory=True)
+    h_rew = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    h_term = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d_act = torch.empty(n, dtype=torch.int32, device=dev)
+
+    def e2e_step():
+        env.sample_actions(seed=7)                       # the agent's decision, made on the device
+        h_act.copy_(env.actions, non_blocking=True)      # ... and handed to the host, as a host-driven loop has it
+        torch.cuda.current_stream(dev).synchronize()
+        d_act.copy_(h_act, non_blocking=True)            # H2D of this step's inputs from pinned memory
+        env.step(d_act, want_info=False)
+        h_obs.copy_(env.obs_buf, non_blocking=True)      # D2H of the step's results
+        h_rew.copy_(env.reward, non_blocking=True)
+        h_term.copy_(env.terminated, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    bdist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = bdist.max_over_ranks(e2e_s, dev)
+    e2e_value = ws * n * Ke / e2e_s
+
+    # ---- hands microbench (configs[1]) ----
+    hands = None
+    if rank == 0 and not args.no_hands:
+        hands = bench_hands(torch, b, dev, peak, args)
+
+    if rank != 0:
+        return 0
+    cpu_base = None
+    if not args.no_cpu_baseline and ws == 1:
+        cpu_base, _ = cpu_env_baseline("c4", rounds=3, warmup_rounds=1, steps_per_round=4096)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64+f64", "data": "synthetic", "config": workload_config(args, n),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "env_kernel<MODE_STEP> (fused step)", "bytes_per_unit": B_STEP,
+                     "units_per_launch": n, "kernel_ms": step_kernel_ms_max, "peak_source": peak_src,
+                     "physical_bytes_per_unit": 304 * 2 + 240 + 4 + 8 + 1 + 1},
+        "cpu_baseline": cpu_base,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (L.OBS_BYTES + 8 + 1 + 4) * n,
+                "steps": Ke},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "fused_rollout": {"value": fused_value, "unit": UNIT, "ms_per_step": fused_ms / K,
+                          "note": "policy sampled inside the step kernel (one launch per step)"},
+        "hands": hands,
+        "episode_stats": {"episodes": float(stats[0]), "mean_return": float(stats[1] / max(1.0, float(stats[0]))),
+                          "mean_length": float(stats[2] / max(1.0, float(stats[0])))},
+        "variant": os.environ.get("BGYM_VARIANT", "0"),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def bench_hands(torch, b, dev, peak, args):
+    """configs[1]: 2^24 random 5-card plays, no jokers, base hand levels."""
+    from balatro_gym_b200.score import score_hands
+    n = args.hands
+    g = torch.Generator(device=dev); g.manual_seed(0x5EED)
+    cards = torch.zeros((n, 8), dtype=torch.uint8, device=dev)
+    chunk = 1 << 22
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        cards[s:s + m, :5] = torch.rand((m, 52), device=dev, generator=g).topk(5, dim=1).indices.to(torch.uint8)
+    out = score_hands(cards, want_x_mult=False, want_money=False)
+    for _ in range(5):
+        score_hands(cards, want_x_mult=False, want_money=False, out=out)
+    torch.cuda.synchronize(dev)
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        score_hands(cards, want_x_mult=False, want_money=False, out=out)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    value = n / (ms / 1000.0)
+    ach = n * B_HAND / (ms / 1000.0) / 1e9
+    # e2e: host cards in pinned memory -> device -> scores back
+    h_cards = torch.empty((n, 8), dtype=torch.uint8, pin_memory=True); h_cards.copy_(cards)
+    h_score = torch.empty(n, dtype=torch.int64, pin_memory=True)
+    h_type = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cards.copy_(h_cards, non_blocking=True)
+        score_hands(cards, want_x_mult=False, want_money=False, out=out)
+        h_score.copy_(out["score"], non_blocking=True); h_type.copy_(out["hand_type"], non_blocking=True)
+        torch.cuda.synchronize(dev)
+    e2e = 3 * n / (time.perf_counter() - t0)
+    res = {"metric": "hands_scored_per_sec", "value": value, "unit": "hands/s", "n_hands": n, "ms_per_launch": ms,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "bytes_per_unit": B_HAND, "kernel": "score_hands_kernel"},
+           "e2e": {"value": e2e, "unit": "hands/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * n}}
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import refenv, refbaseline
+            if refenv.reference_available():
+                sample = cards[: 1 << 15].cpu().numpy()
+                r = refbaseline.run_hands_baseline(sample)
+                res["cpu_baseline"] = {"value": r["hands"] / r["seconds"], "unit": "hands/s", "cores": r["cores"], "kind": "reference",
+                                       "sample": f"first {r['hands']} hands of the same input through classify + to_scoring_format + UnifiedScorer.score_hand"}
+                assert r["checksum"] == int(out["score"][: 1 << 15].sum().item()), "hands checksum differs from the reference"
+                res["cpu_baseline"]["checksum_matches_gpu"] = True
+        except AssertionError:
+            raise
+        except Exception as e:  # baseline is a reported number, never a reason to lose the bench line
+            res["cpu_baseline"] = {"unavailable": repr(e)}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--hands", type=int, default=1 << 24)
+    ap.add_argument("--burn-in", type=int, default=150)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-hands", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against
+  (1) golden traces recorded from the unmodified reference (replay mode, bit-exact),
+  (2) the C oracle on identical seeded inputs (native Philox mode, bit-exact, 10^6+ env-steps),
+  (3) size-independent properties at BASELINE.json's full sizes (2^24 hands, 2^20 envs).
+All marked gpu; they run on the B200 box only."""
+import numpy as np
+import pytest
+
+from conftest import load_trace, assert_records_equal, STATE_SKIP, reward_close
+from balatro_gym_b200 import layout as L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _loaded_native_lib():
+    import balatro_gym_b200 as b
+    b.load()
+    maps = open("/proc/self/maps").read()
+    assert "libbgym.so" in maps, "native library not loaded"
+
+
+# ---------------------------------------------------------------------------------------------
+# (1) golden traces from the reference, replay mode
+# ---------------------------------------------------------------------------------------------
+class CudaStepper:
+    def __init__(self, torch, E):
+        from balatro_gym_b200 import BalatroVecEnv
+        self.torch = torch
+        self.v = BalatroVecEnv(E, autoreset=False)
+
+    def reset(self, seeds, decks):
+        t = self.torch
+        self.v.reset(seeds=t.from_numpy(seeds % (2 ** 32)), decks52=t.from_numpy(decks))
+
+    def set_state(self, init_state):
+        cur = self.v.state_numpy()
+        new = init_state.copy()
+        for k in STATE_SKIP:
+            new[k] = cur[k]
+        self.v.inject_numpy(new)
+
+    def step(self, actions, draws):
+        t = self.torch
+        d = t.from_numpy(np.ascontiguousarray(draws).view(np.uint8).reshape(len(actions), L.DRAWS_BYTES).copy())
+        self.v.step(t.from_numpy(actions.astype(np.int32)).cuda(), draws=d.cuda())
+        return (self.v.state_numpy(), self.v.obs_numpy(), self.v.reward.cpu().numpy(), self.v.terminated.cpu().numpy(),
+                self.v.info_numpy())
+
+
+@pytest.mark.parametrize("name", ["c1", "c3", "c4"])
+def test_cuda_replays_reference_trace(torch, name):
+    from test_oracle_golden import replay
+    tr = load_trace(name)
+    n = replay(tr, CudaStepper(torch, tr["action"].shape[1]))
+    assert n == int(tr["length"].sum())
+    _loaded_native_lib()
+
+
+# ---------------------------------------------------------------------------------------------
+# (2) CUDA vs C oracle, native mode
+# ---------------------------------------------------------------------------------------------
+def _compare_step(v, ov, t, check_info=True):
+    st, ob = v.state_numpy(), v.obs_numpy()
+    assert_records_equal(ov.state, st, L.STATE_DTYPE, (), f"step {t} state")
+    assert_records_equal(ov.obs, ob, L.OBS_DTYPE, (), f"step {t} obs")
+    assert np.array_equal(ov.terminated, v.terminated.cpu().numpy()), t
+    r = v.reward.cpu().numpy()
+    # the pre-step ante is not kept; use a safe superset: tolerance only where rewards differ AND a hand was played
+    inf = v.info_numpy()
+    rc = (ov.reward == r) | (((inf["flags"] & L.F_PLAYED) != 0) & (np.abs(ov.reward - r) <= 1e-12 * np.maximum(1, np.abs(r))))
+    assert rc.all(), (t, ov.reward[~rc][:4], r[~rc][:4])
+    if check_info:
+        assert_records_equal(ov.info, inf, L.INFO_DTYPE, (), f"step {t} info")
+
+
+@pytest.mark.parametrize("n,steps,c3", [(4096, 260, False), (4096, 260, True), (1000, 120, True)])
+def test_cuda_vs_oracle_native_rollout(torch, n, steps, c3):
+    """Fused random-legal policy + autoreset on both sides: > 10^6 env-steps compared record by record."""
+    from balatro_gym_b200 import BalatroVecEnv
+    from oracle import coracle
+    v = BalatroVecEnv(n, seed=1, autoreset=True)
+    v.reset()
+    if c3:
+        v.randomize_c3(seed=5)
+    ov = coracle.OracleVec(n)
+    ov.reset(np.arange(1, n + 1))
+    st0 = v.state_numpy()
+    if not c3:
+        assert_records_equal(ov.state, st0, L.STATE_DTYPE, (), "reset state")   # native Philox shuffle parity
+        assert_records_equal(ov.obs, v.obs_numpy(), L.OBS_DTYPE, (), "reset obs")
+    ov.state[:] = st0
+    rng = np.random.default_rng(3)
+    for t in range(steps):
+        if t % 7 == 3:   # explicit actions incl. masked / out-of-range ones
+            act = rng.integers(-2, 62, size=n).astype(np.int32)
+            v.step(torch.from_numpy(act).cuda())
+            ov.step(act, flags=L.FLAG_AUTORESET)
+        else:
+            v.step(random_policy=True)
+            oact = np.zeros(n, np.int32)
+            coracle.step(ov.state, oact, ov.obs, ov.reward, ov.terminated, ov.truncated, ov.info, None,
+                         flags=L.FLAG_AUTORESET | 4)
+            assert np.array_equal(oact, v.actions.cpu().numpy()), f"policy actions differ at step {t}"
+        _compare_step(v, ov, t)
+    assert int(v.state_numpy()["episode"].sum()) > 0      # autoreset happened
+
+
+def test_sampler_kernel_and_mask_kernel(torch):
+    from balatro_gym_b200 import BalatroVecEnv
+    from oracle import coracle
+    n = 5000
+    v = BalatroVecEnv(n, seed=77, autoreset=True)
+    v.reset()
+    for t in range(40):
+        a = v.sample_actions(seed=123)
+        obs = v.obs_numpy()
+        exp = coracle.sample_actions(obs, 123, v._step_count)
+        got = a.cpu().numpy()
+        assert np.array_equal(exp, got)
+        assert ((obs["action_mask_bits"] >> got.astype(np.uint64)) & 1).all()      # always legal
+        m = v.action_masks().cpu().numpy().view(np.uint64)
+        assert np.array_equal(m, obs["action_mask_bits"])
+        assert np.array_equal(m, coracle.action_mask(v.state_numpy()))
+        v.step(a)
+
+
+def test_host_buffer_handle_api(torch):
+    """bgym_vec_* (what a non-torch caller binds): host pointers in, host pointers out."""
+    import ctypes as C
+    from balatro_gym_b200 import _lib
+    from oracle import coracle
+    lib = _lib.load()
+    n = 777
+    h = C.c_void_p()
+    _lib.check(lib.bgym_vec_create(C.byref(h), n, 0), "create")
+    seeds = np.arange(10, 10 + n, dtype=np.uint32)
+    obs = np.zeros(n, L.OBS_DTYPE)
+    _lib.check(lib.bgym_vec_reset_host(h, seeds.ctypes.data, None, obs.ctypes.data), "reset_host")
+    ov = coracle.OracleVec(n)
+    ov.reset(seeds)
+    assert_records_equal(ov.obs, obs, L.OBS_DTYPE, (), "host reset obs")
+    reward = np.zeros(n); term = np.zeros(n, np.uint8); trunc = np.zeros(n, np.uint8); info = np.zeros(n, L.INFO_DTYPE)
+    for t in range(30):
+        act = coracle.sample_actions(obs, 5, t)
+        _lib.check(lib.bgym_vec_step_host(h, act.ctypes.data, None, obs.ctypes.data, reward.ctypes.data, term.ctypes.data,
+                                          trunc.ctypes.data, info.ctypes.data, L.FLAG_AUTORESET), "step_host")
+        ov.step(act, flags=L.FLAG_AUTORESET)
+        assert_records_equal(ov.obs, obs, L.OBS_DTYPE, (), f"host step {t}")
+        assert np.array_equal(ov.terminated, term)
+    st = np.zeros(n, L.STATE_DTYPE)
+    _lib.check(lib.bgym_vec_get_state(h, st.ctypes.data), "get_state")
+    assert_records_equal(ov.state, st, L.STATE_DTYPE, (), "host state")
+    _lib.check(lib.bgym_vec_destroy(h), "destroy")
+
+
+# ---------------------------------------------------------------------------------------------
+# hand scoring
+# ---------------------------------------------------------------------------------------------
+def _random_hands(n, seed, jokers=True, mods=True):
+    rng = np.random.default_rng(seed)
+    keys = rng.random((n, 52))
+    cards = np.argsort(keys, axis=1)[:, :8].astype(np.uint8)
+    nc = rng.integers(1, 9, size=n).astype(np.uint8)
+    m = np.zeros((n, 8), np.uint16)
+    if mods:
+        enh = np.where(rng.random((n, 8)) < 0.3, rng.integers(1, 9, (n, 8)), 0)
+        ed = np.where(rng.random((n, 8)) < 0.15, rng.integers(1, 4, (n, 8)), 0)
+        seal = np.where(rng.random((n, 8)) < 0.1, rng.integers(1, 5, (n, 8)), 0)
+        m = (enh | (ed << 4) | (seal << 8)).astype(np.uint16)
+    jk = np.zeros((n, 8), np.uint8)
+    if jokers:
+        jk[:, :5] = np.argsort(rng.random((n, 150)), axis=1)[:, :5] + 1
+        jk[rng.random((n, 8)) < 0.3] = 0
+    lv = rng.integers(1, 17, (n, 12)).astype(np.uint8)
+    ctx = np.zeros(n, L.SCORE_CTX_DTYPE)
+    ctx["hands_left"] = rng.integers(1, 5, n); ctx["discards_left"] = rng.integers(0, 4, n)
+    ctx["deck_len"] = rng.integers(40, 53, n)
+    return cards, m, nc, jk, lv, ctx
+
+
+@pytest.mark.parametrize("table_names", [False, True])
+def test_score_hands_cuda_vs_oracle(torch, table_names):
+    from balatro_gym_b200 import score_hands
+    from oracle import coracle
+    n = 1 << 18
+    cards, m, nc, jk, lv, ctx = _random_hands(n, 11)
+    exp = coracle.score_hands(cards, m, nc, jk, lv, ctx, seed=99, flags=int(table_names))
+    t = lambda a: torch.from_numpy(a.view(np.uint8).reshape(n, -1) if a.dtype.fields else a).cuda()
+    out = score_hands(t(cards), t(m), t(nc), t(jk), t(lv), t(ctx), seed=99, table_names=table_names)
+    for k in ("hand_type", "chips", "mult", "x_mult", "score", "money"):
+        assert np.array_equal(exp[k], out[k].cpu().numpy()), k
+
+
+def test_score_hands_replayed_reference_cases(torch, reference):
+    """Reference O2 cases (jokers by name, tapped Misprint/Bloodstone draws) straight into the CUDA kernel."""
+    from balatro_gym_b200 import score_hands
+    from test_oracle_vs_reference import make_score_cases, _pack, check_scores
+    for tn in (False, True):
+        hands = make_score_cases(reference, 800, 1234 + tn, tn)
+        cards, mods, nc, jk, lv, ctx = _pack(hands)
+        t = lambda a: torch.from_numpy(a.view(np.uint8).reshape(len(hands), -1) if a.dtype.fields else a).cuda()
+        out = score_hands(t(cards), t(mods), t(nc), t(jk), t(lv), t(ctx), table_names=tn)
+        check_scores(hands, {k: v.cpu().numpy() for k, v in out.items()})
+
+
+def test_known_answers_cuda(torch):
+    from balatro_gym_b200 import score_hands
+    from test_known_answers import known_arrays
+    cards, n, ht, score = known_arrays()
+    out = score_hands(torch.from_numpy(cards).cuda(), n_cards=torch.from_numpy(n).cuda())
+    assert out["hand_type"].cpu().tolist() == ht.tolist()
+    assert out["score"].cpu().tolist() == score.tolist()
+
+
+def test_score_hands_full_size_properties(torch):
+    """BASELINE config 2 at full size (2^24 five-card plays, no jokers, level 1): properties that do
+    not need the oracle at that size + an oracle check on a 2^16 sample."""
+    from balatro_gym_b200 import score_hands
+    from oracle import coracle
+    n = 1 << 24
+    g = torch.Generator(device="cuda"); g.manual_seed(0x5EED)
+    keys = torch.rand((n, 52), device="cuda", generator=g)
+    cards = torch.zeros((n, 8), dtype=torch.uint8, device="cuda")
+    cards[:, :5] = keys.topk(5, dim=1).indices.to(torch.uint8)
+    del keys
+    out = score_hands(cards, want_x_mult=False, want_money=False)
+    ht = out["hand_type"]; chips = out["chips"].long(); mult = out["mult"].long(); score = out["score"]
+    assert bool((score == chips * mult).all())                      # x_mult == 1 without jokers
+    # card-order invariance (classification and chip sums are symmetric)
+    perm = cards.clone(); perm[:, :5] = cards[:, [4, 2, 0, 3, 1]]
+    out2 = score_hands(perm, want_x_mult=False, want_money=False)
+    assert bool((out2["score"] == score).all()) and bool((out2["hand_type"] == ht).all())
+    # hand-type mix of uniform 5-card draws (exact combinatorics): HC .5012 1P .4226 2P .0475 3K .0211 S .0039 F .0020 FH .0014 4K .00024 SF .000015
+    frac = torch.bincount(ht.long(), minlength=12).double() / n
+    expect = [0.501177, 0.422569, 0.047539, 0.021128, 0.003925, 0.001965, 0.001441, 0.000240, 0.0000154]
+    for i, e in enumerate(expect):
+        assert abs(float(frac[i]) - e) < 4 * (e * (1 - e) / n) ** 0.5 + 1e-6, (i, float(frac[i]), e)
+    assert float(frac[9:].sum()) == 0.0
+    # chips lower bound: base chips of the hand type + at least 5 cards x 2
+    idx = torch.arange(0, n, 256, device="cuda")
+    sub = cards[idx].cpu().numpy()
+    exp = coracle.score_hands(sub)
+    assert np.array_equal(exp["score"], score[idx].cpu().numpy())
+    assert np.array_equal(exp["hand_type"], ht[idx].cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------
+# native Philox mode: distributional tests (the reference's MT19937 shuffles are matched by replay)
+# ---------------------------------------------------------------------------------------------
+def test_native_shuffle_is_uniform(torch):
+    from balatro_gym_b200 import BalatroVecEnv
+    n = 1 << 17
+    v = BalatroVecEnv(n, seed=12345, autoreset=False)
+    v.reset()
+    deck = (v.state[:, 128:232].view(torch.int16) & 63).long()
+    assert bool((deck.sort(dim=1).values == torch.arange(52, device="cuda")).all())     # every deck is a permutation
+    # position x card contingency table: chi-square against uniform, 51*51 dof
+    table = torch.zeros((52, 52), dtype=torch.float64, device="cuda")
+    pos = torch.arange(52, device="cuda").expand(n, 52)
+    table.index_put_((pos.reshape(-1), deck.reshape(-1)), torch.ones(n * 52, dtype=torch.float64, device="cuda"), accumulate=True)
+    e = n / 52.0
+    chi2 = float(((table - e) ** 2 / e).sum())
+    dof = 51 * 51
+    assert abs(chi2 - dof) < 6 * (2 * dof) ** 0.5, chi2
+    # different seeds give different decks; same seed reproduces
+    v2 = BalatroVecEnv(n, seed=12345, autoreset=False)
+    v2.reset()
+    assert bool((v2.state == v.state).all())
+    assert int((deck[1:] == deck[:-1]).all(dim=1).sum()) == 0
+
+
+def test_full_size_rollout_properties(torch):
+    """BASELINE configs 3/4 at full per-GPU size (2^20 envs): invariants that hold for every env after
+    many fused random-policy steps with autoreset."""
+    from balatro_gym_b200 import BalatroVecEnv
+    n = 1 << 20
+    v = BalatroVecEnv(n, seed=1, autoreset=True)
+    v.reset()
+    v.randomize_c3(seed=1)
+    for t in range(96):
+        v.step(random_policy=True, want_info=False)
+    torch.cuda.synchronize()
+    st = v.state
+    hand_n = st[:, 8].long(); phase = st[:, 17].long(); deck = (st[:, 128:232].view(torch.int16) & 63).long()
+    assert bool((deck.sort(dim=1).values == torch.arange(52, device="cuda")).all())
+    assert bool((hand_n <= 8).all()) and bool((phase <= 2).all())
+    hand = st[:, 0:8].long()
+    valid = torch.arange(8, device="cuda")[None, :] < hand_n[:, None]
+    assert bool(((hand < 52) | ~valid).all()) and bool(((hand == 255) | valid).all())
+    # hand slots hold distinct deck indices
+    h = torch.where(valid, hand, torch.arange(100, 108, device="cuda")[None, :].expand(n, 8))
+    assert bool((h.sort(dim=1).values.diff(dim=1) != 0).all())
+    # the obs mask word equals the mask recomputed from the state, and every sampled action was legal
+    m = v.action_masks()
+    assert bool((m == v.obs["action_mask_bits"]).all())
+    ob = v.obs
+    assert bool((ob["money"] == v.state_field("money")).all())
+    assert bool((ob["phase"].long() == phase).all())
+    bits = ((m[:, None] >> torch.arange(60, device="cuda")[None, :]) & 1).to(torch.int8)
+    assert bool((bits == ob["action_mask"]).all())
+    # rewards are finite and terminations happened and were reset in place
+    assert bool(torch.isfinite(v.reward).all())
+    assert int(v.state_field("episode").long().sum()) > n // 4
+
+
+def test_gym_facade_matches_reference_episode(torch, reference):
+    """BalatroEnv (N=1 facade) against the unmodified reference on whole episodes: same seed -> same
+    deck (replayed MT19937 shuffle), then identical obs / reward / termination for small-blind episodes
+    (config 1: no further random draws are consumed)."""
+    from balatro_gym_b200.env import BalatroEnv
+    from oracle.refenv import RefEnv
+    rng = np.random.default_rng(0)
+    for seed in (3, 17, 91):
+        ref = RefEnv(seed=seed, tap=False)
+        env = BalatroEnv(seed=seed)
+        ro, _ = ref.reset(seed)
+        eo, _ = env.reset(seed=seed)
+        for t in range(300):
+            for k in L.OBS_KEYS:
+                assert np.array_equal(np.asarray(ro[k]), np.asarray(eo[k])), (seed, t, k)
+            if ref.env.state.phase == 1:       # shop draws need replay; stop the facade check there
+                break
+            a = 45 if t == 0 else int(rng.choice(np.flatnonzero(ro["action_mask"])))
+            ro, rr, rt, _, ri = ref.step(a)
+            eo, er, et, _, ei = env.step(a)
+            if ref.env.state.phase == 1:
+                break
+            assert rr == er and rt == et, (seed, t, rr, er)
+            assert ("error" in ri) == ("error" in ei)
+            if rt:
+                break
