@@ -80,10 +80,13 @@ __device__ __forceinline__ void sts128(void* p, uint4 v) { *reinterpret_cast<uin
 // ---------------------------------------------------------------------------------------------
 #define BGYM_PHILOX_KEY1 0xB200CAFEu
 #define BGYM_POLICY_KEY1 0x5A17AC71u
+#define BGYM_SHUFFLE_KEY1 0xB200DECCu
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                               uint32_t k1) {
-#pragma unroll
+// noinline on purpose: draws are rare (a few percent of env-steps) and the step kernel has ~20 draw
+// sites; one shared copy keeps the kernel inside the instruction cache.
+__device__ __noinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                            uint32_t k1) {
+#pragma unroll 1
   for (int r = 0; r < 10; r++) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -116,29 +119,44 @@ struct Draws {
     pos++;
     return w;
   }
-  // CPython random.random(): (a >> 5, b >> 6) -> 53 bits
-  __device__ __forceinline__ double u01() {
-    if (tape) return tape->u[iu++];
-    uint32_t a = word() >> 5;
-    uint32_t b = word() >> 6;
-    return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
-  }
-  // unbiased integer in [0, n): Lemire multiply-shift with rejection
-  __device__ __forceinline__ int below(int n) {
-    if (tape) return tape->k[ik++];
-    uint32_t un = (uint32_t)n;
-    uint64_t m = (uint64_t)word() * un;
-    uint32_t l = (uint32_t)m;
-    if (l < un) {
-      uint32_t t = (0u - un) % un;
-      while (l < t) {
-        m = (uint64_t)word() * un;
-        l = (uint32_t)m;
-      }
-    }
-    return (int)(m >> 32);
-  }
+  __device__ double u01();
+  __device__ int below(int n);
 };
+
+// Out of line (one copy each): the step kernel has ~25 draw sites, all on rare paths.
+// CPython random.random(): (a >> 5, b >> 6) -> 53 bits
+__device__ __noinline__ double Draws::u01() {
+  if (tape) return tape->u[iu++];
+  uint32_t a = word() >> 5;
+  uint32_t b = word() >> 6;
+  return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+}
+// unbiased integer in [0, n): Lemire multiply-shift with rejection
+__device__ __noinline__ int Draws::below(int n) {
+  if (tape) return tape->k[ik++];
+  uint32_t un = (uint32_t)n;
+  uint64_t m = (uint64_t)word() * un;
+  uint32_t l = (uint32_t)m;
+  if (l < un) {
+    uint32_t t = (0u - un) % un;
+    while (l < t) {
+      m = (uint64_t)word() * un;
+      l = (uint32_t)m;
+    }
+  }
+  return (int)(m >> 32);
+}
+
+// j for Fisher-Yates position i (1..51) of the native shuffle: Philox block (i-1)/2 keyed
+// (seed, shuffle key), words (x,y) for odd i, (z,w) for even i; Lemire multiply-shift, second word
+// on rejection.  Independent per i, so a warp computes all 51 in parallel.
+__device__ __forceinline__ int shuffle_j_from_block(uint4 b, int i) {
+  uint32_t w0 = ((i - 1) & 1) ? b.z : b.x, w1 = ((i - 1) & 1) ? b.w : b.y;
+  uint32_t un = (uint32_t)(i + 1);
+  uint64_t m = (uint64_t)w0 * un;
+  if ((uint32_t)m < (0u - un) % un) m = (uint64_t)w1 * un;
+  return (int)(m >> 32);
+}
 
 // ---------------------------------------------------------------------------------------------
 // packed-byte helpers (8 x u8 in a u64, 8 x u4 in a u32)

@@ -124,6 +124,7 @@ __device__ __forceinline__ uint64_t action_mask(const Hot& h, const uint8_t* rec
     m |= ((1ull << h.cons_n) - 1) << BGYM_A_USE_CONS_BASE;
   } else if (h.phase == BGYM_PHASE_SHOP) {
     int n_items = rec[OFF_N_ITEMS];
+    #pragma unroll 1
     for (int i = 0; i < n_items; i++) {
       int cost = *reinterpret_cast<const int*>(rec + OFF_ITEM_COST + 4 * i);
       if (h.money >= cost) m |= 1ull << (BGYM_A_SHOP_BUY_BASE + i);
@@ -145,8 +146,10 @@ __device__ __forceinline__ void draw_cards(Hot& h) {
   int want = h.hand_size - h.hand_n;
   if (want <= 0) return;
   uint64_t in_hand = 0;
+  #pragma unroll 1
   for (int i = 0; i < h.hand_n; i++) in_hand |= 1ull << byte_at(h.hand, i);
   uint64_t avail = ~in_hand & ((h.deck_n >= 64) ? ~0ull : ((1ull << h.deck_n) - 1));
+  #pragma unroll 1
   while (want > 0 && avail && h.hand_n < 8) {
     int idx = __ffsll((long long)avail) - 1;
     avail &= avail - 1;
@@ -159,6 +162,7 @@ __device__ __forceinline__ void draw_cards(Hot& h) {
 __device__ __forceinline__ void remove_slots(Hot& h, int slots) {
   uint64_t out = ~0ull;
   int n = 0;
+  #pragma unroll 1
   for (int i = 0; i < h.hand_n; i++) {
     if ((slots >> i) & 1) continue;
     out = with_byte(out, n, byte_at(h.hand, i));
@@ -193,22 +197,26 @@ __device__ void shop_generate_inventory(Hot& h, uint8_t* rec, Draws& rng) {
   shop_put(rec, 2, BGYM_ITEM_PACK, third, (int)(c_pack_cost[third] * mult));
   // owned shop-eligible ids, sorted ascending (<= 8 entries)
   int owned[8], n_owned = 0;
+  #pragma unroll 1
   for (int i = 0; i < h.joker_n; i++) {
     int id = byte_at(h.jokers, i);
     if (id >= 1 && id <= BGYM_NUM_SHOP_JOKERS) {
       int k = n_owned++;
+      #pragma unroll 1
       while (k > 0 && owned[k - 1] > id) { owned[k] = owned[k - 1]; k--; }
       owned[k] = id;
     }
   }
   // distinct owned ids only (Ankh-style duplicates cannot occur in-env, but stay safe)
   int m = 0;
+  #pragma unroll 1
   for (int i = 0; i < n_owned; i++) if (i == 0 || owned[i] != owned[i - 1]) owned[m++] = owned[i];
   n_owned = m;
   int pool = BGYM_NUM_SHOP_JOKERS - n_owned;
   int k = min(3, pool);
   int n = 3;
   int chosen[3];
+  #pragma unroll 1
   for (int t = 0; t < k; t++) {
     int p;
     if (rng.tape) {
@@ -217,23 +225,28 @@ __device__ void shop_generate_inventory(Hot& h, uint8_t* rec, Draws& rng) {
       // native: t-th element of a uniform ordered sample without replacement
       p = rng.below(pool - t);
       // map to the p-th not-yet-chosen position (chosen kept sorted)
+      #pragma unroll 1
       for (int a = 0; a < t; a++) if (chosen[a] <= p) p++;
     }
     // keep `chosen` sorted ascending for the skip logic above
     int c = t;
+    #pragma unroll 1
     while (c > 0 && chosen[c - 1] > p) { chosen[c] = chosen[c - 1]; c--; }
     chosen[c] = p;
     int id = p + 1;
+    #pragma unroll 1
     for (int a = 0; a < n_owned; a++) if (owned[a] <= id) id++;
     shop_put(rec, n++, BGYM_ITEM_JOKER, id, (int)(c_joker_cost[id] * mult));
   }
   int v = rng.below(2);
   shop_put(rec, n++, BGYM_ITEM_VOUCHER, v, (int)(c_voucher_cost[v] * mult));
+  #pragma unroll 1
   for (int i = 0; i < 2; i++) {
     int c = rng.below(52);
     shop_put(rec, n++, BGYM_ITEM_CARD, c, BGYM_CARD_COST);
   }
   rec[OFF_N_ITEMS] = (uint8_t)n;
+  #pragma unroll 1
   for (int i = n; i < 9; i++) shop_put(rec, i, 0, 0, 0);
 }
 
@@ -253,6 +266,7 @@ __device__ __forceinline__ void boss_deactivate(Hot& h) {
 
 __device__ void advance_round(Hot& h, uint8_t* rec, Draws& rng) {
   int gold = 0;
+  #pragma unroll 1
   for (int i = 0; i < h.hand_n; i++) {
     int idx = byte_at(h.hand, i);
     if (idx < 52 && c16_enh(deck16(rec, idx)) == BGYM_ENH_GOLD) gold += 3;
@@ -360,6 +374,7 @@ __device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int
   ConsRow row = cons_row(cid);
   // targets: selected cards in selection order (balatro_env_2.py:1074-1083)
   int tgt[8], nT = 0;
+  #pragma unroll 1
   for (int k = 0; k < h.sel_n; k++) {
     int sl = nib_at(h.sel_order, k);
     if (sl < h.hand_n) { int idx = byte_at(h.hand, sl); if (idx < h.deck_n) tgt[nT++] = idx; }
@@ -370,12 +385,14 @@ __device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int
   switch (row.op) {
     case CO_ENH_N: {
       int cnt = min(nT, row.arg >> 4);
+      #pragma unroll 1
       for (int i = 0; i < cnt; i++) { int c = deck16(rec, tgt[i]); set_deck16(rec, tgt[i], (c & ~(15 << 6)) | ((row.arg & 15) << 6)); }
       n_affected = cnt; success = nT > 0;
       break;
     }
     case CO_AFFECT_N: n_affected = min(nT, (int)row.arg); success = nT > 0; break;
     case CO_STRENGTH:
+      #pragma unroll 1
       for (int i = 0; i < min(nT, 2); i++) n_affected += (c16_code(deck16(rec, tgt[i])) >> 2) < 12;
       success = nT > 0;
       break;
@@ -395,6 +412,7 @@ __device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int
       break;
     }
     case CO_PRIESTESS:
+      #pragma unroll 1
       for (int i = 0; i < 2; i++) {
         int p = BGYM_CONS_PLANET_BASE + rng.below(9);
         if (h.cons_n < h.cons_slots) { cons_append(h, p); items[n_items++] = p; }
@@ -402,6 +420,7 @@ __device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int
       success = true;
       break;
     case CO_EMPEROR:
+      #pragma unroll 1
       for (int i = 0; i < 2; i++)
         if (h.cons_n < h.cons_slots) {
           int t = BGYM_CONS_ENUMSTYLE_BASE + 1 + rng.below(22);
@@ -462,6 +481,7 @@ __device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int
       reward += n_jokers_created * 15.0;
     }
     if (n_items > 0) {
+      #pragma unroll 1
       for (int i = 0; i < n_items; i++) if (h.cons_n < h.cons_slots) cons_append(h, items[i]);
       reward += n_items * 5.0;
     }
@@ -482,11 +502,8 @@ __device__ __forceinline__ uint32_t next_episode_seed(uint32_t seed) {
   return x ? x : 1u;
 }
 
-// writes the deck/shop blocks into the record and returns the hot block in registers
-__device__ void reset_env(Hot& h, uint8_t* rec, uint32_t seed, const uint8_t* deck52 /*global, nullable*/) {
-  // zero deck + shop blocks
-#pragma unroll
-  for (int o = 128; o < 304; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
+// hot block of a fresh episode (UnifiedGameState defaults)
+__device__ __forceinline__ void reset_hot(Hot& h, uint32_t seed) {
   h.hand = ~0ull;
   h.hand_n = 0; h.hand_size = 8; h.sel_n = 0; h.highlight = 0; h.sel_order = 0;
   h.face_down = 0; h.phase = BGYM_PHASE_BLIND_SELECT; h.round = 1; h.boss_type = 0;
@@ -499,24 +516,88 @@ __device__ void reset_env(Hot& h, uint8_t* rec, uint32_t seed, const uint8_t* de
   h.lv0 = h.lv1 = h.lv2 = 0x01010101u;
   h.shop_reroll_state = 5;
   h.rng_seed = seed; h.rng_ctr = 0; h.ep_len = 0; h.episode = 0;
+}
+
+// deck + shop blocks of a fresh episode, one lane doing all the work (reset kernel: every lane of
+// the warp resets, so per-lane serial work is already converged).
+//   deck52 != nullptr: replay of a supplied permutation (the reference's MT19937 shuffle stream)
+//   else: suit-major build (balatro_env_2.py:519-522) + Fisher-Yates in random.shuffle's order
+//         (for i in reversed(range(1, n)): j = randbelow(i + 1); swap) with native Philox draws
+__device__ __noinline__ void reset_blocks_serial(uint8_t* rec, uint32_t seed, const uint8_t* deck52) {
+#pragma unroll 1
+  for (int o = 128; o < 304; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
   if (deck52) {
+#pragma unroll 1
     for (int i = 0; i < 52; i++) set_deck16(rec, i, deck52[i]);
-  } else {
-    // suit-major build (:519-522) + Fisher-Yates as random.shuffle does it:
-    // for i in reversed(range(1, n)): j = randbelow(i + 1); swap
-    int k = 0;
-    for (int suit = 0; suit < 4; suit++)
-      for (int r = 0; r < 13; r++) set_deck16(rec, k++, r * 4 + suit);
-    Draws rng;
-    rng.init(seed, 0, nullptr);
-    for (int i = 51; i >= 1; i--) {
-      int j = rng.below(i + 1);
-      int a = deck16(rec, i), b = deck16(rec, j);
-      set_deck16(rec, i, b); set_deck16(rec, j, a);
-    }
-    h.rng_ctr = rng.ctr;
+    return;
+  }
+#pragma unroll 1
+  for (int i = 0; i < 52; i++) set_deck16(rec, i, (i % 13) * 4 + i / 13);
+  uint4 blk = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+  for (int i = 51; i >= 1; i--) {
+    if ((i & 1) == 0 || i == 51) blk = philox4x32_10((uint32_t)((i - 1) >> 1), 0, 0, 0, seed, BGYM_SHUFFLE_KEY1);
+    int j = shuffle_j_from_block(blk, i);
+    int a = deck16(rec, i), b = deck16(rec, j);
+    set_deck16(rec, i, b); set_deck16(rec, j, a);
   }
 }
+
+// The same reset done by the whole warp for ONE env (in-kernel autoreset: only a few lanes of a
+// warp terminate in a given step, so their resets are executed cooperatively instead of serially
+// inside a divergent branch): lanes build the ordered deck and compute all 51 Fisher-Yates draws
+// in parallel (one Philox block per lane), then the swaps are applied in order.
+__device__ __forceinline__ void reset_blocks_warp(uint8_t* rec_of_src, uint32_t seed, int lane) {
+  if (lane < 11) sts128(rec_of_src + 128 + 16 * lane, make_uint4(0, 0, 0, 0));
+  __syncwarp();
+  set_deck16(rec_of_src, lane, (lane % 13) * 4 + lane / 13);
+  if (lane < 20) set_deck16(rec_of_src, lane + 32, ((lane + 32) % 13) * 4 + (lane + 32) / 13);
+  // lane l (< 26) owns block l -> draws for i = 2l+1 and i = 2l+2
+  uint4 blk = philox4x32_10((uint32_t)lane, 0, 0, 0, seed, BGYM_SHUFFLE_KEY1);
+  int j_odd = shuffle_j_from_block(blk, 2 * lane + 1);
+  int j_even = shuffle_j_from_block(blk, 2 * lane + 2);
+  __syncwarp();
+#pragma unroll 1
+  for (int i = 51; i >= 1; i--) {
+    int j = __shfl_sync(0xffffffffu, (i & 1) ? j_odd : j_even, (i - 1) >> 1);
+    if (lane == 0) {
+      int a = deck16(rec_of_src, i), b = deck16(rec_of_src, j);
+      set_deck16(rec_of_src, i, b); set_deck16(rec_of_src, j, a);
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// rare paths, out of line.  They work on the PACKED record so the step kernel's hot instruction
+// stream stays small and register-resident: pack_hot -> rare_dispatch -> unpack_hot at one site.
+// ---------------------------------------------------------------------------------------------
+enum { RARE_NONE = 0, RARE_ADVANCE = 1, RARE_REROLL = 2, RARE_CONSUMABLE = 3 };
+struct RareOut { double reward; int err; int terminated; };
+
+__device__ __noinline__ void rare_dispatch(uint8_t* rec, int op, int arg, Draws* rng, RareOut* out) {
+  Hot h;
+  unpack_hot(rec, h);
+  out->reward = 0.0; out->err = 0; out->terminated = 0;
+  if (op == RARE_ADVANCE) {
+    advance_round(h, rec, *rng);
+  } else if (op == RARE_REROLL) {
+    int* rr = reinterpret_cast<int*>(rec + OFF_REROLL);
+    int cost = (int)(*rr * shop_cost_mult(h));  // shop.py:172
+    if (h.money < cost) { out->reward = -1.0; out->err = BGYM_ERR_SHOP; }
+    else {
+      h.money -= cost;
+      *rr = (int)(*rr * 1.35);
+      shop_generate_inventory(h, rec, *rng);
+    }
+  } else if (op == RARE_CONSUMABLE) {
+    out->reward = use_consumable(h, rec, arg, *rng, out->err, out->terminated);
+  }
+  pack_hot(rec, h);
+}
+
+// the ante > 3 score reward goes through log10 (balatro_env_2.py:821); kept out of line
+__device__ __noinline__ double log10_out_of_line(double x) { return log10(x); }
 
 // ---------------------------------------------------------------------------------------------
 // per-step outputs
@@ -548,11 +629,13 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
   rng.init(h.rng_seed, h.rng_ctr, tape);
   double reward = 0.0;
   int terminated = 0;
+  int rare_op = RARE_NONE, rare_arg = 0;
 
   if (action >= BGYM_A_SELECT_BASE && action < BGYM_A_SELECT_BASE + 8) {
     // toggle in the ordered selection list (:1052-1058); legal only in PLAY phase by the mask
     int slot = action - BGYM_A_SELECT_BASE;
     int found = -1;
+    #pragma unroll 1
     for (int k = 0; k < h.sel_n; k++) if (nib_at(h.sel_order, k) == slot) found = k;
     if (found >= 0) {
       uint32_t lo = h.sel_order & ((1u << (4 * found)) - 1);
@@ -567,6 +650,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     uint64_t played_bits = 0;          // bit set over deck indices of the played cards
     int n_played = 0, card_chip_sum = 0, faces_ge11 = 0, extra_money = 0, n_red = 0, n_blue = 0;
     int boss = h.boss_type, debuffed = 0;
+    #pragma unroll 1
     for (int k = 0; k < h.sel_n; k++) {
       int sl = nib_at(h.sel_order, k);
       if (sl >= h.hand_n) continue;
@@ -595,6 +679,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     h.highlight |= sel_slots;
     HandHist hist;
     hist.clear();
+    #pragma unroll 1
     for (int sl = 0; sl < 8; sl++) if ((h.highlight >> sl) & 1) hist.add(c16_code(deck16(rec, sl)));
     int ht = classify(hist);
     // ---- boss gate (boss_blinds.py:380-407) ----
@@ -615,6 +700,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     long long fs = base_score;
     // steel cards left in hand (:560-570)
     int n_steel = 0;
+    #pragma unroll 1
     for (int i = 0; i < h.hand_n; i++) {
       int idx = byte_at(h.hand, i);
       if (!((sel_slots >> i) & 1) && idx < 52 && c16_enh(deck16(rec, idx)) == BGYM_ENH_STEEL) n_steel++;
@@ -634,6 +720,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     h.money += extra_money;
     {  // blue seals -> planet of this hand type (cards.py:228-246)
       int planet = ht == 0 ? 38 : (ht <= 8 ? 29 + ht : 30 + ht);
+      #pragma unroll 1
       for (int i = 0; i < n_blue; i++) if (h.cons_n < h.cons_slots) cons_append(h, planet);
     }
     double needed = (double)max(h.chips_needed, 1);
@@ -658,7 +745,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     else if (old_progress < 0.75 && 0.75 <= new_progress) milestone = 15.0;
     else if (old_progress < 1.0 && 1.0 <= new_progress) milestone = 25.0;
     double score_reward = (h.ante <= 3) ? fmin(10.0, (double)fs / 100.0)
-                                        : fmin(10.0, 3.0 * log10((double)max(fs, 1LL)));
+                                        : fmin(10.0, 3.0 * log10_out_of_line((double)max(fs, 1LL)));
     double hq = ht == 0 ? 0.1 : ht == 1 ? 0.5 : ht == 2 ? 1.0 : ht == 3 ? 2.0 : (ht == 4 || ht == 5) ? 2.5
               : ht == 6 ? 3.5 : ht == 7 ? 5.0 : ht == 8 ? 7.0 : ht == 9 ? 10.0 : 0.0;
     double eff = 0.0;
@@ -683,7 +770,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     // ---- round end (:914-960) ----
     if (h.round_chips >= (long long)h.chips_needed) {
       reward += fmin(50.0, 25.0 + 10.0 * h.ante);
-      advance_round(h, rec, rng);
+      rare_op = RARE_ADVANCE;
       info.flags |= BGYM_F_BEAT_BLIND;
     } else if (h.hands_left <= 1) {
       reward += -50.0 * (1.0 - new_progress);
@@ -702,8 +789,10 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
             remove_slots(h, (1 << a) | (1 << b));
           }
         } else if (boss == B_WHEEL) {
+          #pragma unroll 1
           for (int i = 0; i < h.hand_n; i++) if (rng.u01() < 1.0 / 7) face |= 1 << i;
         } else if (boss == B_MARK) {
+          #pragma unroll 1
           for (int i = 0; i < h.hand_n; i++) {
             int r = c16_code(deck16(rec, byte_at(h.hand, i))) >> 2;
             if (r >= 9 && r <= 11) face |= 1 << i;
@@ -717,6 +806,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
   } else if (action == BGYM_A_DISCARD) {
     // ---- :962-1050 ----
     int sel_slots = 0, n_disc = 0, purple = 0, faces = 0;
+    #pragma unroll 1
     for (int k = 0; k < h.sel_n; k++) {
       int sl = nib_at(h.sel_order, k);
       if (sl >= h.hand_n) continue;
@@ -730,6 +820,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
       faces += r >= 9 && r <= 11;
     }
     int money_from_discards = 0, n_discard_jokers = 0;
+    #pragma unroll 1
     for (int j = 0; j < h.joker_n; j++) {  // discard-phase joker effects, complete_joker_effects.py:186-209
       int id = byte_at(h.jokers, j);
       int money = (id == BGYM_J_TRADING_CARD && h.discards_left == 3 && n_disc == 1) ? 3
@@ -744,6 +835,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     draw_cards(h);
     h.discards_left--;
     h.sel_n = 0; h.sel_order = 0;
+    #pragma unroll 1
     for (int i = 0; i < purple; i++)  // purple seals -> tarots (:1021-1032)
       if (h.cons_n < h.cons_slots) cons_append(h, BGYM_CONS_TAROT_BASE + rng.below(22));
     reward = 0.2;
@@ -753,34 +845,27 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     if (progress < 0.5 && h.discards_left > 1) reward += 0.5;
     else if (progress > 0.8 && h.discards_left > 1) reward -= 0.3;
   } else if (action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) {
-    int err = 0;
-    reward = use_consumable(h, rec, action - BGYM_A_USE_CONS_BASE, rng, err, terminated);
-    info.error_code = err;
+    rare_op = RARE_CONSUMABLE; rare_arg = action - BGYM_A_USE_CONS_BASE;
   } else if (action == BGYM_A_SHOP_END) {
     h.phase = BGYM_PHASE_PLAY;
     draw_cards(h);
     info.flags |= BGYM_F_SHOP_DONE;
   } else if (action == BGYM_A_SHOP_REROLL) {
-    int* rr = reinterpret_cast<int*>(rec + OFF_REROLL);
-    int cost = (int)(*rr * shop_cost_mult(h));  // shop.py:172
-    if (h.money < cost) { reward = -1.0; info.error_code = BGYM_ERR_SHOP; }
-    else {
-      h.money -= cost;
-      *rr = (int)(*rr * 1.35);
-      shop_generate_inventory(h, rec, rng);
-    }
+    rare_op = RARE_REROLL;
   } else if (action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SHOP_BUY_BASE + 10) {
     int i = action - BGYM_A_SHOP_BUY_BASE;
     int n_items = rec[OFF_N_ITEMS];
     int type = rec[OFF_ITEM_TYPE + i], id = rec[OFF_ITEM_ID + i];
     int cost = *reinterpret_cast<int*>(rec + OFF_ITEM_COST + 4 * i);
     h.money -= cost;  // shop.py:185-187: pay, pop the item
+    #pragma unroll 1
     for (int k = i; k + 1 < n_items; k++)
       shop_put(rec, k, rec[OFF_ITEM_TYPE + k + 1], rec[OFF_ITEM_ID + k + 1], *reinterpret_cast<int*>(rec + OFF_ITEM_COST + 4 * (k + 1)));
     shop_put(rec, n_items - 1, 0, 0, 0);
     rec[OFF_N_ITEMS] = (uint8_t)(n_items - 1);
     if (type == BGYM_ITEM_PACK) {
       int count = (id == BGYM_PACK_STANDARD) ? 3 : 1;  // shop.py:150-157: cards go to player.deck only
+      #pragma unroll 1
       for (int k = 0; k < count; k++) (void)rng.below(52);
       reward = 5.0;
     } else if (type == BGYM_ITEM_CARD) {
@@ -821,7 +906,14 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     draw_cards(h);
   } else if (action == BGYM_A_SKIP_BLIND) {
     reward = -5.0;
-    advance_round(h, rec, rng);
+    rare_op = RARE_ADVANCE;
+  }
+  if (rare_op != RARE_NONE) {   // ONE out-of-line site for every rare path
+    RareOut ro;
+    pack_hot(rec, h);
+    rare_dispatch(rec, rare_op, rare_arg, &rng, &ro);
+    unpack_hot(rec, h);
+    if (rare_op != RARE_ADVANCE) { reward = ro.reward; info.error_code = ro.err; terminated = ro.terminated; }
   }
   if (!tape) h.rng_ctr = rng.ctr;
   reward_out = reward;
@@ -836,9 +928,11 @@ __device__ __forceinline__ int obs_cons_id(int cid) { return cid >= BGYM_CONS_EN
 __device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs /*smem, 240 B*/) {
   uint4 q;
   uint32_t selm = 0;
+  #pragma unroll 1
   for (int k = 0; k < h.sel_n; k++) selm |= 1u << nib_at(h.sel_order, k);
   // 0: hand[8] | selected_cards[8]   (hand codes = deck[hand[i]], -1 when empty)
   uint64_t codes = ~0ull;
+  #pragma unroll 1
   for (int i = 0; i < h.hand_n; i++) {
     int idx = byte_at(h.hand, i);
     if (idx < h.deck_n) codes = with_byte(codes, i, c16_code(deck16(rec, idx)));

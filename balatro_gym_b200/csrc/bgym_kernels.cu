@@ -128,12 +128,13 @@ __global__ void __launch_bounds__(C::threads, C::ctas_per_sm) env_kernel(StepArg
       phase_bits ^= 1u << stage;
     }
 
+    Hot h;
+    double reward = 0.0;
+    int terminated = 0;
+    StepInfo info;
+    bool do_store_state = true, want_reset = false;
+    uint32_t new_seed = 0;
     if (active) {
-      Hot h;
-      double reward = 0.0;
-      int terminated = 0;
-      StepInfo info;
-      bool do_store_state = true;
       if (MODE == MODE_STEP) {
         unpack_hot(rec, h);
         uint64_t m0 = action_mask(h, rec);
@@ -150,18 +151,34 @@ __global__ void __launch_bounds__(C::threads, C::ctas_per_sm) env_kernel(StepArg
         step_env(h, rec, action, m0, a.draws ? a.draws + e : nullptr, reward, terminated, info);
         if (terminated && (a.flags & BGYM_FLAG_AUTORESET)) {
           uint32_t episode = h.episode + 1;
-          reset_env(h, rec, next_episode_seed(h.rng_seed), nullptr);
+          new_seed = next_episode_seed(h.rng_seed);
+          reset_hot(h, new_seed);
           h.episode = episode;
           info.flags |= BGYM_F_AUTORESET_DONE;
+          want_reset = true;
         }
       } else {
         if (a.reset_mask && !a.reset_mask[e]) {
           unpack_hot(rec, h);   // untouched env: only re-emit its observation
           do_store_state = false;
         } else {
-          reset_env(h, rec, a.seeds[e], a.decks52 ? a.decks52 + e * 52 : nullptr);
+          reset_hot(h, a.seeds[e]);
+          reset_blocks_serial(rec, a.seeds[e], a.decks52 ? a.decks52 + e * 52 : nullptr);
         }
       }
+    }
+    if (MODE == MODE_STEP && (a.flags & BGYM_FLAG_AUTORESET)) {
+      // in-place autoreset: the deck/shop blocks of every terminated env of the tile are rebuilt by
+      // the WHOLE warp, one env after the other (few lanes terminate per step)
+      uint32_t rmask = __ballot_sync(0xffffffffu, want_reset);
+      while (rmask) {
+        int src = __ffs(rmask) - 1;
+        rmask &= rmask - 1;
+        uint32_t sd = __shfl_sync(0xffffffffu, new_seed, src);
+        reset_blocks_warp(wbase + stage * WARP_STATE_BYTES + src * REC_STRIDE, sd, lane);
+      }
+    }
+    if (active) {
       if (do_store_state) pack_hot(rec, h);
       if (with_obs) write_obs(h, rec, action_mask(h, rec), obs_s);
       fence_async_smem();  // this lane's shared-memory writes -> visible to the async proxy
@@ -238,6 +255,29 @@ struct ScoreRng {  // native draws of the scoring path: Philox keyed by (seed), 
     return (int)(m >> 32);
   }
 };
+
+// Fast path of config 2 (five-card plays, no modifiers, no jokers, level-1 hands): everything is
+// static — five byte extracts, register histograms, one table lookup — and each thread scores two
+// hands per iteration so two independent load->compute->store chains are in flight.
+__global__ void __launch_bounds__(256) score_hands5_kernel(ScoreArgs a) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+    uint2 cw = __ldg(reinterpret_cast<const uint2*>(a.cards8) + i);
+    int c0 = cw.x & 0xFF, c1 = (cw.x >> 8) & 0xFF, c2 = (cw.x >> 16) & 0xFF, c3 = cw.x >> 24, c4 = cw.y & 0xFF;
+    HandHist hist;
+    hist.clear();
+    hist.add(c0); hist.add(c1); hist.add(c2); hist.add(c3); hist.add(c4);
+    int chip_sum = card_chips(c0, 0, 0) + card_chips(c1, 0, 0) + card_chips(c2, 0, 0) + card_chips(c3, 0, 0) + card_chips(c4, 0, 0);
+    int ht = classify(hist);
+    int chips = c_base_chips[ht] + chip_sum, mult = c_base_mult[ht];
+    a.hand_type[i] = (uint8_t)ht;
+    a.chips[i] = chips;
+    a.mult[i] = mult;
+    a.score[i] = (long long)chips * mult;   // x_mult == 1.0: int(chips * mult * 1.0)
+    if (a.x_mult) a.x_mult[i] = 1.0;
+    if (a.money) a.money[i] = 0;
+  }
+}
 
 __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
@@ -566,7 +606,10 @@ int bgym_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8_t
   a.money = money; a.seed = seed; a.n = n; a.flags = flags;
   long long blocks = (n + 255) / 256;
   long long cap = (long long)g_sm_count * 16;
-  score_hands_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a);
+  if (!mods8 && !n_cards && !jokers8 && !levels12 && !ctx)
+    score_hands5_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a);
+  else
+    score_hands_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a);
   return cuda_rc(cudaGetLastError(), "bgym_score_hands launch");
 }
 

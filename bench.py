@@ -114,7 +114,7 @@ def cpu_env_baseline(config, rounds, warmup_rounds, steps_per_round=1024):
     res = refbaseline.run_env_baseline(config, steps_per_round=steps_per_round, rounds=rounds, warmup_rounds=warmup_rounds)
     total = res["steps_per_round_total"] * len(res["per_round_s"])
     return {"value": total / sum(res["per_round_s"]), "unit": UNIT, "cores": res["cores"], "kind": "reference",
-            "sample": (f"unmodified reference BalatroEnv ({'byte-compiled oracle/_ref' if root.endswith('_ref') else root}), "
+            "sample": (f"unmodified reference BalatroEnv ({'byte-compiled oracle/_ref' if '_ref' in root else root}), "
                        f"{res['cores']} worker processes x {steps_per_round} env-steps x {len(res['per_round_s'])} rounds, "
                        f"config {config} state generator, random legal actions, no per-step IPC (upper bound of an AsyncVectorEnv)")}, res["per_round_s"]
 

@@ -561,10 +561,18 @@ static void reset_env(BgymState* s, uint32_t seed, const uint8_t* deck52) {
     int k = 0;
     for (int suit = 0; suit < 4; suit++)
       for (int rank = 2; rank <= 14; rank++) s->deck[k++] = (uint16_t)((rank - 2) * 4 + suit);
-    Rng r;
-    rng_init(&r, s, NULL);
+    /* native draws of the shuffle: j_i comes from Philox block (i-1)/2 keyed (seed, SHUFFLE key),
+     * words (0,1) for odd i, (2,3) for even i, so the 51 draws are independent of each other (the
+     * kernel computes them lane-parallel); bounded by Lemire's multiply-shift, second word on the
+     * (probability < n/2^32) rejection.  The step stream (rng_ctr) is not touched. */
     for (int i = 51; i >= 1; i--) {
-      int j = rng_below(&r, i + 1);
+      uint32_t w[4];
+      philox4x32_10((uint32_t)((i - 1) / 2), 0, 0, 0, seed, 0xB200DECCu, w);
+      uint32_t w0 = w[((i - 1) & 1) * 2], w1 = w[((i - 1) & 1) * 2 + 1];
+      uint32_t un = (uint32_t)(i + 1);
+      uint64_t m = (uint64_t)w0 * un;
+      if ((uint32_t)m < (0u - un) % un) m = (uint64_t)w1 * un;
+      int j = (int)(m >> 32);
       uint16_t t = s->deck[i]; s->deck[i] = s->deck[j]; s->deck[j] = t;
     }
   }

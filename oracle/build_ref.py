@@ -26,7 +26,14 @@ def main():
     for m in MODULES:
         py_compile.compile(os.path.join(SRC, m + ".py"), cfile=os.path.join(DST, m + ".pyc"),
                            dfile=f"balatro_gym/{m}.py", doraise=True, optimize=0)
-    print(f"build_ref: {len(MODULES)} modules -> {DST}")
+    # the same files as one zip archive (zipimport loads sourceless .pyc): a second carrier in case
+    # a sync tool filters *.pyc files
+    import zipfile
+    zpath = os.path.join(HERE, "_ref", "balatro_gym_ref.zip")
+    with zipfile.ZipFile(zpath, "w", zipfile.ZIP_DEFLATED) as z:
+        for m in MODULES:
+            z.write(os.path.join(DST, m + ".pyc"), f"balatro_gym/{m}.pyc")
+    print(f"build_ref: {len(MODULES)} modules -> {DST} and {zpath}")
     return 0
 
 

@@ -41,6 +41,8 @@ def reference_available() -> Optional[str]:
         return REFERENCE_ROOT
     if os.path.isfile(os.path.join(REF_COMPILED, "balatro_gym", "balatro_env_2.pyc")):
         return REF_COMPILED
+    if os.path.isfile(os.path.join(REF_COMPILED, "balatro_gym_ref.zip")):
+        return os.path.join(REF_COMPILED, "balatro_gym_ref.zip")
     return None
 
 
