@@ -543,28 +543,51 @@ __device__ __noinline__ void reset_blocks_serial(uint8_t* rec, uint32_t seed, co
   }
 }
 
-// The same reset done by the whole warp for ONE env (in-kernel autoreset: only a few lanes of a
-// warp terminate in a given step, so their resets are executed cooperatively instead of serially
-// inside a divergent branch): lanes build the ordered deck and compute all 51 Fisher-Yates draws
-// in parallel (one Philox block per lane), then the swaps are applied in order.
-__device__ __forceinline__ void reset_blocks_warp(uint8_t* rec_of_src, uint32_t seed, int lane) {
+// In-kernel autoreset of the deck/shop blocks, split in two so that several terminated lanes of a
+// warp cost little more than one:
+//   prepare (whole warp, once per terminated env): zero the blocks, build the ordered deck and
+//            compute all 51 Fisher-Yates draws lane-parallel (one Philox block per lane); the draws
+//            are parked as bytes in the (just zeroed) shop block of the record;
+//   finish  (each terminated lane for itself, all of them in parallel): apply the 51 swaps in
+//            random.shuffle's order, then clear the parked draws.
+constexpr int OFF_RESET_SCRATCH = 244;  // shop block, 52 bytes used
+__device__ __forceinline__ void reset_blocks_prepare(uint8_t* rec_of_src, uint32_t seed, int lane) {
   if (lane < 11) sts128(rec_of_src + 128 + 16 * lane, make_uint4(0, 0, 0, 0));
   __syncwarp();
   set_deck16(rec_of_src, lane, (lane % 13) * 4 + lane / 13);
   if (lane < 20) set_deck16(rec_of_src, lane + 32, ((lane + 32) % 13) * 4 + (lane + 32) / 13);
   // lane l (< 26) owns block l -> draws for i = 2l+1 and i = 2l+2
   uint4 blk = philox4x32_10((uint32_t)lane, 0, 0, 0, seed, BGYM_SHUFFLE_KEY1);
-  int j_odd = shuffle_j_from_block(blk, 2 * lane + 1);
-  int j_even = shuffle_j_from_block(blk, 2 * lane + 2);
-  __syncwarp();
+  if (lane < 26) {
+    rec_of_src[OFF_RESET_SCRATCH + 2 * lane + 1] = (uint8_t)shuffle_j_from_block(blk, 2 * lane + 1);
+    if (2 * lane + 2 <= 51) rec_of_src[OFF_RESET_SCRATCH + 2 * lane + 2] = (uint8_t)shuffle_j_from_block(blk, 2 * lane + 2);
+  }
+}
+__device__ __forceinline__ void reset_blocks_finish(uint8_t* rec) {
 #pragma unroll 1
   for (int i = 51; i >= 1; i--) {
-    int j = __shfl_sync(0xffffffffu, (i & 1) ? j_odd : j_even, (i - 1) >> 1);
-    if (lane == 0) {
-      int a = deck16(rec_of_src, i), b = deck16(rec_of_src, j);
-      set_deck16(rec_of_src, i, b); set_deck16(rec_of_src, j, a);
-    }
+    int j = rec[OFF_RESET_SCRATCH + i];
+    int a = deck16(rec, i), b = deck16(rec, j);
+    set_deck16(rec, i, b); set_deck16(rec, j, a);
   }
+#pragma unroll 1
+  for (int o = 240; o < 304; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
+}
+// warp-level driver: `want_reset` lanes get fresh deck/shop blocks in their record `my_rec`
+__device__ __forceinline__ void autoreset_warp(bool want_reset, uint32_t new_seed, uint8_t* my_rec, int lane) {
+  uint32_t rmask = __ballot_sync(0xffffffffu, want_reset);
+  if (!rmask) return;
+  unsigned long long my_ptr = reinterpret_cast<unsigned long long>(my_rec);
+  uint32_t m = rmask;
+  while (m) {
+    int src = __ffs(m) - 1;
+    m &= m - 1;
+    uint32_t sd = __shfl_sync(0xffffffffu, new_seed, src);
+    uint8_t* rec_src = reinterpret_cast<uint8_t*>(__shfl_sync(0xffffffffu, my_ptr, src));
+    reset_blocks_prepare(rec_src, sd, lane);
+  }
+  __syncwarp();
+  if (want_reset) reset_blocks_finish(my_rec);
   __syncwarp();
 }
 
@@ -611,6 +634,10 @@ struct StepInfo {
 // ---------------------------------------------------------------------------------------------
 // the step, balatro_env_2.py:616-1064 (play), :1174-1253 (shop), :1255-1318 (blind select)
 // ---------------------------------------------------------------------------------------------
+// CATS: which action categories this instantiation compiles in (the partitioned step runs one small
+// kernel per category so that every warp in flight executes the same short code).
+enum { CAT_SELECT = 1, CAT_PLAY = 2, CAT_DISCARD = 4, CAT_OTHER = 8, CAT_ALL = 15 };
+template <int CATS>
 __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const BgymDraws* tape, double& reward_out,
                          int& terminated_out, StepInfo& info) {
   info.final_score = 0; info.x_mult = 1.0; info.chips = 0; info.mult = 0; info.hand_type = -1;
@@ -631,7 +658,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
   int terminated = 0;
   int rare_op = RARE_NONE, rare_arg = 0;
 
-  if (action >= BGYM_A_SELECT_BASE && action < BGYM_A_SELECT_BASE + 8) {
+  if ((CATS & CAT_SELECT) && action >= BGYM_A_SELECT_BASE && action < BGYM_A_SELECT_BASE + 8) {
     // toggle in the ordered selection list (:1052-1058); legal only in PLAY phase by the mask
     int slot = action - BGYM_A_SELECT_BASE;
     int found = -1;
@@ -644,7 +671,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     } else {
       h.sel_order |= (uint32_t)slot << (4 * h.sel_n); h.sel_n++;
     }
-  } else if (action == BGYM_A_PLAY_HAND) {
+  } else if ((CATS & CAT_PLAY) && action == BGYM_A_PLAY_HAND) {
     // ---- gather the played cards in selection order (:650-660) ----
     int sel_slots = 0;                 // bit set of selected hand slots
     uint64_t played_bits = 0;          // bit set over deck indices of the played cards
@@ -803,7 +830,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
         h.face_down = face;
       }
     }
-  } else if (action == BGYM_A_DISCARD) {
+  } else if ((CATS & CAT_DISCARD) && action == BGYM_A_DISCARD) {
     // ---- :962-1050 ----
     int sel_slots = 0, n_disc = 0, purple = 0, faces = 0;
     #pragma unroll 1
@@ -844,15 +871,15 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     double progress = (double)h.round_chips / (double)max(h.chips_needed, 1);
     if (progress < 0.5 && h.discards_left > 1) reward += 0.5;
     else if (progress > 0.8 && h.discards_left > 1) reward -= 0.3;
-  } else if (action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) {
+  } else if ((CATS & CAT_OTHER) && action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) {
     rare_op = RARE_CONSUMABLE; rare_arg = action - BGYM_A_USE_CONS_BASE;
-  } else if (action == BGYM_A_SHOP_END) {
+  } else if ((CATS & CAT_OTHER) && action == BGYM_A_SHOP_END) {
     h.phase = BGYM_PHASE_PLAY;
     draw_cards(h);
     info.flags |= BGYM_F_SHOP_DONE;
-  } else if (action == BGYM_A_SHOP_REROLL) {
+  } else if ((CATS & CAT_OTHER) && action == BGYM_A_SHOP_REROLL) {
     rare_op = RARE_REROLL;
-  } else if (action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SHOP_BUY_BASE + 10) {
+  } else if ((CATS & CAT_OTHER) && action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SHOP_BUY_BASE + 10) {
     int i = action - BGYM_A_SHOP_BUY_BASE;
     int n_items = rec[OFF_N_ITEMS];
     int type = rec[OFF_ITEM_TYPE + i], id = rec[OFF_ITEM_ID + i];
@@ -877,7 +904,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
       if (id == BGYM_VOUCHER_MAGIC_TRICK) h.n_magic = min(h.n_magic + 1, 255); else h.n_minimalist = min(h.n_minimalist + 1, 255);
       reward = 10.0;
     }
-  } else if (action >= BGYM_A_SELL_JOKER_BASE && action < BGYM_A_SELL_JOKER_BASE + 5) {
+  } else if ((CATS & CAT_OTHER) && action >= BGYM_A_SELL_JOKER_BASE && action < BGYM_A_SELL_JOKER_BASE + 5) {
     int j = action - BGYM_A_SELL_JOKER_BASE;
     int id = byte_at(h.jokers, j);
     uint64_t lo = h.jokers & ((1ull << (8 * j)) - 1);
@@ -886,7 +913,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     int sell = max(3, (int)c_joker_cost[id] / 2);
     h.money += sell; h.jokers_sold++;
     reward = sell / 5.0;
-  } else if (action >= BGYM_A_SELECT_BLIND_BASE && action < BGYM_A_SELECT_BLIND_BASE + 3) {
+  } else if ((CATS & CAT_OTHER) && action >= BGYM_A_SELECT_BLIND_BASE && action < BGYM_A_SELECT_BLIND_BASE + 3) {
     int bt = action - BGYM_A_SELECT_BLIND_BASE;
     h.round = bt + 1;
     long long needed = (h.ante <= 8) ? (long long)c_blind_chips[max(h.ante, 1) - 1][bt]
@@ -904,11 +931,11 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     h.chips_needed = (int)min(needed, 2147483647LL);
     h.phase = BGYM_PHASE_PLAY;
     draw_cards(h);
-  } else if (action == BGYM_A_SKIP_BLIND) {
+  } else if ((CATS & CAT_OTHER) && action == BGYM_A_SKIP_BLIND) {
     reward = -5.0;
     rare_op = RARE_ADVANCE;
   }
-  if (rare_op != RARE_NONE) {   // ONE out-of-line site for every rare path
+  if ((CATS & (CAT_PLAY | CAT_OTHER)) && rare_op != RARE_NONE) {   // ONE out-of-line site for every rare path
     RareOut ro;
     pack_hot(rec, h);
     rare_dispatch(rec, rare_op, rare_arg, &rng, &ro);

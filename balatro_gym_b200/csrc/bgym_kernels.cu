@@ -34,15 +34,20 @@ constexpr int WARP_OBS_BYTES = 32 * OBS_STRIDE;                // 7680
 // Two staging variants (picked at run time, BGYM_VARIANT=0/1):
 //   V0: single state buffer per warp, 4 warps/CTA, 3 CTAs/SM  -> 12 warps/SM hide each other's loads
 //   V1: double-buffered state per warp, 8 warps/CTA, 1 CTA/SM -> 8 warps/SM, next tile prefetched
-template <int STAGES, int WARPS>
+//   V6/V7: single state buffer, observation written straight to global with 128-bit stores (no obs
+//          staging) -> 9.7 KB of shared memory per warp, 20+ warps/SM
+template <int STAGES, int WARPS, bool OBS_DIRECT = false, int CTAS = 0>
 struct Cfg {
   static constexpr int stages = STAGES, warps = WARPS, threads = WARPS * 32;
-  static constexpr int warp_smem = STAGES * WARP_STATE_BYTES + WARP_OBS_BYTES;
+  static constexpr bool obs_direct = OBS_DIRECT;
+  static constexpr int warp_smem = STAGES * WARP_STATE_BYTES + (OBS_DIRECT ? 0 : WARP_OBS_BYTES);
   static constexpr int cta_smem = WARPS * warp_smem + 16 * WARPS;  // + mbarriers
-  static constexpr int ctas_per_sm = (227 * 1024) / cta_smem;
+  static constexpr int ctas_per_sm = CTAS ? CTAS : (227 * 1024) / cta_smem;
 };
 using CfgV0 = Cfg<1, 4>;
 using CfgV1 = Cfg<2, 8>;
+using CfgV6 = Cfg<1, 4, true, 5>;
+using CfgV7 = Cfg<1, 3, true, 7>;
 
 struct StepArgs {
   uint8_t* state;            // n x 320
@@ -60,9 +65,18 @@ struct StepArgs {
   const uint8_t* decks52;    // n x 52 (nullable)
   long long n;
   int flags;
+  // partitioned step: three device lists of deferred env indices + their counters
+  int* part_lists;           // [3][part_cap]
+  int* part_counters;        // [4] (index c = category c; 0 unused)
+  long long part_cap;
 };
 
 enum { MODE_STEP = 0, MODE_RESET = 1 };
+
+}  // namespace bgym
+#include "bgym_step_sorted.cuh"
+#include "bgym_step_part.cuh"
+namespace bgym {
 
 template <int MODE, typename C>
 __global__ void __launch_bounds__(C::threads, C::ctas_per_sm) env_kernel(StepArgs a) {
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(C::threads, C::ctas_per_sm) env_kernel(StepArg
     const long long e = tile * 32 + lane;
     const bool active = e < a.n;
     uint8_t* rec = wbase + stage * WARP_STATE_BYTES + lane * REC_STRIDE;
-    uint8_t* obs_s = obs_buf + lane * OBS_STRIDE;
+    uint8_t* obs_s = C::obs_direct ? (a.obs + e * BGYM_OBS_BYTES) : (obs_buf + lane * OBS_STRIDE);
 
     // the buffer about to be overwritten (and the obs buffer) were last READ by the bulk stores
     // lane 0 issued in the previous iteration: wait for those reads to finish
@@ -148,7 +162,7 @@ __global__ void __launch_bounds__(C::threads, C::ctas_per_sm) env_kernel(StepArg
           action = cnt ? __ffsll((long long)mm) - 1 : 0;
           if (a.actions_out) a.actions_out[e] = action;
         }
-        step_env(h, rec, action, m0, a.draws ? a.draws + e : nullptr, reward, terminated, info);
+        step_env<CAT_ALL>(h, rec, action, m0, a.draws ? a.draws + e : nullptr, reward, terminated, info);
         if (terminated && (a.flags & BGYM_FLAG_AUTORESET)) {
           uint32_t episode = h.episode + 1;
           new_seed = next_episode_seed(h.rng_seed);
@@ -170,13 +184,7 @@ __global__ void __launch_bounds__(C::threads, C::ctas_per_sm) env_kernel(StepArg
     if (MODE == MODE_STEP && (a.flags & BGYM_FLAG_AUTORESET)) {
       // in-place autoreset: the deck/shop blocks of every terminated env of the tile are rebuilt by
       // the WHOLE warp, one env after the other (few lanes terminate per step)
-      uint32_t rmask = __ballot_sync(0xffffffffu, want_reset);
-      while (rmask) {
-        int src = __ffs(rmask) - 1;
-        rmask &= rmask - 1;
-        uint32_t sd = __shfl_sync(0xffffffffu, new_seed, src);
-        reset_blocks_warp(wbase + stage * WARP_STATE_BYTES + src * REC_STRIDE, sd, lane);
-      }
+      autoreset_warp(want_reset, new_seed, rec, lane);
     }
     if (active) {
       if (do_store_state) pack_hot(rec, h);
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(C::threads, C::ctas_per_sm) env_kernel(StepArg
       // ONE bulk store per warp tile for the state records and one for the observation records
       uint32_t cnt = (uint32_t)min(32LL, a.n - tile * 32);
       bulk_s2g(a.state + tile * 32 * BGYM_STATE_BYTES, wbase + stage * WARP_STATE_BYTES, cnt * BGYM_STATE_BYTES);
-      if (with_obs) bulk_s2g(a.obs + tile * 32 * BGYM_OBS_BYTES, obs_buf, cnt * BGYM_OBS_BYTES);
+      if (with_obs && !C::obs_direct) bulk_s2g(a.obs + tile * 32 * BGYM_OBS_BYTES, obs_buf, cnt * BGYM_OBS_BYTES);
       bulk_commit();
     }
   }
@@ -488,7 +496,15 @@ static int cuda_rc(cudaError_t e, const char* where) {
 
 static int g_sm_count = 0;
 static bool g_attr_set = false;
-static int g_variant = 0;
+// step-kernel variants (BGYM_VARIANT): 0/1 fixed lane<->env mapping (single / double buffered),
+// 2..5 CTA-level path sorting with 4x3, 6x2, 8x1, 12x1 (warps per CTA x CTAs per SM)
+//   8 category-partitioned step (main pass + one gather pass per rare category)  <- default
+#define BGYM_DEFAULT_VARIANT 8
+using SortedA = SortedCfg<4, 3>;
+using SortedB = SortedCfg<6, 2>;
+using SortedC = SortedCfg<8, 1>;
+using SortedD = SortedCfg<12, 1>;
+static int g_variant = BGYM_DEFAULT_VARIANT;
 static int ensure_device_setup() {
   if (g_attr_set) return 0;
   int dev = 0;
@@ -502,10 +518,105 @@ static int ensure_device_setup() {
   if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(reset v0)");
   e = cudaFuncSetAttribute(env_kernel<MODE_STEP, CfgV1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgV1::cta_smem);
   if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(step v1)");
+  e = cudaFuncSetAttribute(env_kernel<MODE_STEP, CfgV6>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgV6::cta_smem);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(step v6)");
+  e = cudaFuncSetAttribute(env_kernel<MODE_STEP, CfgV7>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgV7::cta_smem);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(step v7)");
+  e = cudaFuncSetAttribute(env_step_sorted_kernel<SortedA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortedA::cta_smem);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(sorted A)");
+  e = cudaFuncSetAttribute(env_step_sorted_kernel<SortedB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortedB::cta_smem);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(sorted B)");
+  e = cudaFuncSetAttribute(env_step_sorted_kernel<SortedC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortedC::cta_smem);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(sorted C)");
+  e = cudaFuncSetAttribute(env_step_sorted_kernel<SortedD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortedD::cta_smem);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(sorted D)");
+  e = cudaFuncSetAttribute(env_step_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_CTA_SMEM);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(part main)");
+  e = cudaFuncSetAttribute(env_step_gather_kernel<CAT_PLAY, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_CTA_SMEM);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(part play)");
+  e = cudaFuncSetAttribute(env_step_gather_kernel<CAT_DISCARD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_CTA_SMEM);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(part discard)");
+  e = cudaFuncSetAttribute(env_step_gather_kernel<CAT_OTHER, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_CTA_SMEM);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(part other)");
   const char* v = getenv("BGYM_VARIANT");
-  g_variant = (v && v[0] == '1') ? 1 : 0;
+  g_variant = (v && v[0] >= '0' && v[0] <= '8') ? (v[0] - '0') : BGYM_DEFAULT_VARIANT;
   g_attr_set = true;
   return 0;
+}
+
+// scratch of the partitioned step (deferred-env lists + counters), one per (device, stream)
+struct PartScratch { int dev; void* stream; long long cap; int* lists; int* counters;
+                     cudaStream_t side[2]; cudaEvent_t ev_main, ev_side[2]; bool streams_ok; };
+static PartScratch g_scratch[16];
+static int g_n_scratch = 0;
+static int get_part_scratch(long long n, void* stream, PartScratch** out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  PartScratch* sc = nullptr;
+  for (int i = 0; i < g_n_scratch; i++)
+    if (g_scratch[i].dev == dev && g_scratch[i].stream == stream) sc = &g_scratch[i];
+  if (!sc) {
+    if (g_n_scratch == 16) return set_err(BGYM_E_ARG, "bgym_step: too many (device, stream) pairs in use");
+    sc = &g_scratch[g_n_scratch++];
+    sc->dev = dev; sc->stream = stream; sc->cap = 0; sc->lists = nullptr; sc->counters = nullptr;
+    // the three gather passes touch disjoint envs and are latency-bound: run them concurrently
+    sc->streams_ok = cudaStreamCreateWithFlags(&sc->side[0], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaStreamCreateWithFlags(&sc->side[1], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&sc->ev_main, cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&sc->ev_side[0], cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&sc->ev_side[1], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (sc->cap < n) {
+    if (sc->lists) cudaFree(sc->lists);
+    cudaError_t e = cudaMalloc(&sc->lists, (size_t)(3 * n + 4) * sizeof(int));
+    if (e != cudaSuccess) { sc->cap = 0; sc->lists = nullptr; return cuda_rc(e, "cudaMalloc(step scratch)"); }
+    sc->cap = n;
+    sc->counters = sc->lists + 3 * n;
+  }
+  *out = sc;
+  return 0;
+}
+
+static int launch_partitioned(StepArgs& a, cudaStream_t s) {
+  PartScratch* sc = nullptr;
+  int rc = get_part_scratch(a.n, (void*)s, &sc);
+  if (rc) return rc;
+  a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_cap = sc->cap;
+  cudaError_t e = cudaMemsetAsync(sc->counters, 0, 4 * sizeof(int), s);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaMemsetAsync(step counters)");
+  long long tiles = (a.n + 31) / 32;
+  long long ctas = (tiles + PART_WARPS - 1) / PART_WARPS;
+  long long cap = (long long)g_sm_count * PART_CTAS_PER_SM;
+  int grid = (int)(ctas < cap ? ctas : cap);
+  env_step_main_kernel<<<grid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
+  // the list lengths live on the device: launch resident-size grids, idle warps exit at once
+  long long gcap = (ctas + 3) / 4 < cap ? (ctas + 3) / 4 : cap;
+  int ggrid = (int)(gcap < 1 ? 1 : gcap);
+  static const bool serial = getenv("BGYM_SERIAL_GATHER") != nullptr;
+  if (sc->streams_ok && !serial) {
+    cudaEventRecord(sc->ev_main, s);
+    cudaStreamWaitEvent(sc->side[0], sc->ev_main, 0);
+    env_step_gather_kernel<CAT_PLAY, 0><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, sc->side[0]>>>(a);
+    cudaEventRecord(sc->ev_side[0], sc->side[0]);
+    cudaStreamWaitEvent(sc->side[1], sc->ev_main, 0);
+    env_step_gather_kernel<CAT_OTHER, 2><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, sc->side[1]>>>(a);
+    cudaEventRecord(sc->ev_side[1], sc->side[1]);
+    env_step_gather_kernel<CAT_DISCARD, 1><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
+    cudaStreamWaitEvent(s, sc->ev_side[0], 0);
+    cudaStreamWaitEvent(s, sc->ev_side[1], 0);
+  } else {
+    env_step_gather_kernel<CAT_PLAY, 0><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
+    env_step_gather_kernel<CAT_DISCARD, 1><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
+    env_step_gather_kernel<CAT_OTHER, 2><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
+  }
+  return 0;
+}
+
+template <typename C>
+static void launch_sorted(const StepArgs& a, cudaStream_t s) {
+  long long tiles = (a.n + C::T - 1) / C::T;
+  long long cap = (long long)g_sm_count * C::ctas_per_sm;
+  env_step_sorted_kernel<C><<<(int)(tiles < cap ? tiles : cap), C::threads, C::cta_smem, s>>>(a);
 }
 
 template <typename C>
@@ -563,10 +674,18 @@ int bgym_step(BgymState* state, int32_t* actions, const BgymDraws* draws, BgymOb
   a.draws = draws; a.obs = reinterpret_cast<uint8_t*>(obs);
   a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.info = info;
   a.n = n; a.flags = flags;
-  if (g_variant == 1)
-    env_kernel<MODE_STEP, CfgV1><<<env_grid<CfgV1>(n), CfgV1::threads, CfgV1::cta_smem, (cudaStream_t)stream>>>(a);
-  else
-    env_kernel<MODE_STEP, CfgV0><<<env_grid<CfgV0>(n), CfgV0::threads, CfgV0::cta_smem, (cudaStream_t)stream>>>(a);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (g_variant) {
+    case 0: env_kernel<MODE_STEP, CfgV0><<<env_grid<CfgV0>(n), CfgV0::threads, CfgV0::cta_smem, s>>>(a); break;
+    case 1: env_kernel<MODE_STEP, CfgV1><<<env_grid<CfgV1>(n), CfgV1::threads, CfgV1::cta_smem, s>>>(a); break;
+    case 2: launch_sorted<SortedA>(a, s); break;
+    case 4: launch_sorted<SortedC>(a, s); break;
+    case 5: launch_sorted<SortedD>(a, s); break;
+    case 6: env_kernel<MODE_STEP, CfgV6><<<env_grid<CfgV6>(n), CfgV6::threads, CfgV6::cta_smem, s>>>(a); break;
+    case 7: env_kernel<MODE_STEP, CfgV7><<<env_grid<CfgV7>(n), CfgV7::threads, CfgV7::cta_smem, s>>>(a); break;
+    case 3: launch_sorted<SortedB>(a, s); break;
+    default: { int prc = launch_partitioned(a, s); if (prc) return prc; } break;
+  }
   return cuda_rc(cudaGetLastError(), "bgym_step launch");
 }
 

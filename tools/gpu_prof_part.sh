@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:"env_step_(main|gather)" -s 400 -c 4 -f -o gpurun_out/prof_part python bench.py --steps 20 --warmup 3 --burn-in 100 --no-cpu-baseline --no-hands --e2e-steps 3 > gpurun_out/ncu_part.log 2>&1
+tail -3 gpurun_out/ncu_part.log
