@@ -15,7 +15,7 @@ from . import layout as L
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "libbgym.so")
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("bgym_kernels.cu", "bgym_env.cuh", "bgym_device.cuh")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("bgym_kernels.cu", "bgym_step_part.cuh", "bgym_env.cuh", "bgym_device.cuh")]
 HEADERS = [os.path.join(_REPO, "include", f) for f in ("bgym.h", "bgym_tables.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -59,9 +59,9 @@ SYMBOLS = {
     "bgym_abi_version": (_i32, []),
     "bgym_last_error": (C.c_char_p, []),
     "bgym_device_count": (_i32, []),
-    "bgym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "bgym_action_mask": (_i32, [_vp, _vp, _i64, _vp]),
+    "bgym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bgym_action_mask": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "bgym_sample_actions": (_i32, [_vp, _vp, _u32, _u64, _i64, _vp]),
     "bgym_score_hands": (_i32, [_vp] * 12 + [_u32, _i64, _i32, _vp]),
     "bgym_episode_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
@@ -69,7 +69,7 @@ SYMBOLS = {
     "bgym_vec_destroy": (_i32, [_vp]),
     "bgym_vec_reset_host": (_i32, [_vp, _vp, _vp, _vp]),
     "bgym_vec_step_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
-    "bgym_vec_pointers": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "bgym_vec_pointers": (_i32, [_vp] + [C.POINTER(_vp)] * 5),
     "bgym_vec_get_state": (_i32, [_vp, _vp]),
     "bgym_vec_set_state": (_i32, [_vp, _vp]),
 }

@@ -1,8 +1,9 @@
 // bgym_env.cuh — per-env game logic of the fused step kernel (device functions).
 //
-// One thread owns one env.  The env's 320 B record sits in shared memory (staged there by a bulk
-// async copy); the 128 B hot block is unpacked into registers (struct Hot), the deck block and
-// the shop block are accessed in shared memory because they are indexed dynamically.
+// One thread owns one env.  The env's hot record (144 B) and cold record (176 B: deck + shop) sit
+// in shared memory, staged there by bulk async copies; the hot record is unpacked into registers
+// (struct Hot), the cold record is accessed in shared memory because it is indexed dynamically.
+// In every function below `rec` is the COLD record pointer; `hot` is the hot record pointer.
 //
 // Semantics follow the reference's *effective* behaviour; each function
 // cites the reference lines it implements.
@@ -11,9 +12,9 @@
 
 namespace bgym {
 
-// offsets inside the record (include/bgym.h)
-constexpr int OFF_DECK = 128, OFF_HPC = 232, OFF_ITEM_TYPE = 244, OFF_ITEM_ID = 253, OFF_N_ITEMS = 262,
-              OFF_ITEM_COST = 264, OFF_REROLL = 300;
+// offsets inside the cold record (BgymCold, include/bgym.h)
+constexpr int OFF_DECK = 0, OFF_HPC = 104, OFF_ITEM_TYPE = 116, OFF_ITEM_ID = 125, OFF_N_ITEMS = 134,
+              OFF_ITEM_COST = 136, OFF_REROLL = 172;
 
 enum { B_HOOK = 1, B_WALL, B_WHEEL, B_HOUSE, B_MARK, B_FISH, B_PSYCHIC, B_GOAD, B_WATER, B_WINDOW,
        B_MANACLE, B_EYE, B_MOUTH, B_PLANT, B_SERPENT, B_PILLAR, B_NEEDLE, B_HEAD, B_CLUB, B_TOOTH,
@@ -23,7 +24,7 @@ enum { B_HOOK = 1, B_WALL, B_WHEEL, B_HOUSE, B_MARK, B_FISH, B_PSYCHIC, B_GOAD, 
 // hot block in registers
 // ---------------------------------------------------------------------------------------------
 struct Hot {
-  uint64_t hand;                     // 8 packed bytes
+  uint64_t hand, hand_code;          // 8 packed bytes each
   int hand_n, hand_size, sel_n, highlight;
   uint32_t sel_order;
   int face_down, phase, round, boss_type;
@@ -39,54 +40,57 @@ struct Hot {
   uint32_t rng_seed, rng_ctr, ep_len, episode;
 };
 
-__device__ __forceinline__ void unpack_hot(const uint8_t* rec, Hot& h) {
-  uint4 q0 = lds128(rec), q1 = lds128(rec + 16), q2 = lds128(rec + 32), q3 = lds128(rec + 48);
-  uint4 q4 = lds128(rec + 64), q5 = lds128(rec + 80), q6 = lds128(rec + 96), q7 = lds128(rec + 112);
-  h.hand = u64_of(q0.x, q0.y);
-  h.hand_n = q0.z & 0xFF; h.hand_size = (q0.z >> 8) & 0xFF; h.sel_n = (q0.z >> 16) & 0xFF; h.highlight = q0.z >> 24;
-  h.sel_order = q0.w;
-  h.face_down = q1.x & 0xFF; h.phase = (q1.x >> 8) & 0xFF; h.round = (q1.x >> 16) & 0xFF; h.boss_type = q1.x >> 24;
-  h.hands_left = q1.y & 0xFF; h.discards_left = (q1.y >> 8) & 0xFF; h.joker_n = (q1.y >> 16) & 0xFF; h.cons_n = q1.y >> 24;
-  h.joker_slots = q1.z & 0xFF; h.cons_slots = (q1.z >> 8) & 0xFF; h.n_magic = (q1.z >> 16) & 0xFF; h.n_minimalist = q1.z >> 24;
-  h.ante = (int)(short)(q1.w & 0xFFFF); h.jokers_sold = (int)(short)(q1.w >> 16);
-  h.money = (int)q2.x; h.chips_needed = (int)q2.y;
-  h.round_chips = (long long)u64_of(q2.z, q2.w); h.chips_scored = (long long)u64_of(q3.x, q3.y);
-  h.best_hand = (int)q3.z; h.hands_played_total = (int)q3.w;
-  h.hands_played_ante = (int)(short)(q4.x & 0xFFFF); h.boss_flags = (q4.x >> 16) & 0xFF; h.boss_cards_required = q4.x >> 24;
-  h.boss_played_types = q4.y & 0xFFFF; h.boss_hands_played = (q4.y >> 16) & 0xFF; h.deck_n = q4.y >> 24;
-  h.boss_played_cards = u64_of(q4.z, q4.w);
-  h.jokers = u64_of(q5.x, q5.y); h.cons = u64_of(q5.z, q5.w);
-  h.lv0 = q6.x; h.lv1 = q6.y; h.lv2 = q6.z; h.shop_reroll_state = (int)q6.w;
-  h.rng_seed = q7.x; h.rng_ctr = q7.y; h.ep_len = q7.z; h.episode = q7.w;
+__device__ __forceinline__ void unpack_hot(const uint8_t* hot, Hot& h) {
+  uint4 q0 = lds128(hot), q1 = lds128(hot + 16), q2 = lds128(hot + 32), q3 = lds128(hot + 48);
+  uint4 q4 = lds128(hot + 64), q5 = lds128(hot + 80), q6 = lds128(hot + 96), q7 = lds128(hot + 112);
+  uint4 q8 = lds128(hot + 128);
+  h.hand = u64_of(q0.x, q0.y); h.hand_code = u64_of(q0.z, q0.w);
+  h.hand_n = q1.x & 0xFF; h.hand_size = (q1.x >> 8) & 0xFF; h.sel_n = (q1.x >> 16) & 0xFF; h.highlight = q1.x >> 24;
+  h.sel_order = q1.y;
+  h.face_down = q1.z & 0xFF; h.phase = (q1.z >> 8) & 0xFF; h.round = (q1.z >> 16) & 0xFF; h.boss_type = q1.z >> 24;
+  h.hands_left = q1.w & 0xFF; h.discards_left = (q1.w >> 8) & 0xFF; h.joker_n = (q1.w >> 16) & 0xFF; h.cons_n = q1.w >> 24;
+  h.joker_slots = q2.x & 0xFF; h.cons_slots = (q2.x >> 8) & 0xFF; h.n_magic = (q2.x >> 16) & 0xFF; h.n_minimalist = q2.x >> 24;
+  h.ante = (int)(short)(q2.y & 0xFFFF); h.jokers_sold = (int)(short)(q2.y >> 16);
+  h.money = (int)q2.z; h.chips_needed = (int)q2.w;
+  h.round_chips = (long long)u64_of(q3.x, q3.y); h.chips_scored = (long long)u64_of(q3.z, q3.w);
+  h.best_hand = (int)q4.x; h.hands_played_total = (int)q4.y;
+  h.hands_played_ante = (int)(short)(q4.z & 0xFFFF); h.boss_flags = (q4.z >> 16) & 0xFF; h.boss_cards_required = q4.z >> 24;
+  h.boss_played_types = q4.w & 0xFFFF; h.boss_hands_played = (q4.w >> 16) & 0xFF; h.deck_n = q4.w >> 24;
+  h.boss_played_cards = u64_of(q5.x, q5.y); h.jokers = u64_of(q5.z, q5.w);
+  h.cons = u64_of(q6.x, q6.y); h.lv0 = q6.z; h.lv1 = q6.w;
+  h.lv2 = q7.x; h.shop_reroll_state = (int)q7.y; h.rng_seed = q7.z; h.rng_ctr = q7.w;
+  h.ep_len = q8.x; h.episode = q8.y;
 }
 
-__device__ __forceinline__ void pack_hot(uint8_t* rec, const Hot& h) {
+__device__ __forceinline__ void pack_hot(uint8_t* hot, const Hot& h) {
   uint4 q;
-  q.x = (uint32_t)h.hand; q.y = (uint32_t)(h.hand >> 32);
-  q.z = (h.hand_n & 0xFF) | ((h.hand_size & 0xFF) << 8) | ((h.sel_n & 0xFF) << 16) | ((uint32_t)(h.highlight & 0xFF) << 24);
-  q.w = h.sel_order;
-  sts128(rec, q);
-  q.x = (h.face_down & 0xFF) | ((h.phase & 0xFF) << 8) | ((h.round & 0xFF) << 16) | ((uint32_t)(h.boss_type & 0xFF) << 24);
-  q.y = (h.hands_left & 0xFF) | ((h.discards_left & 0xFF) << 8) | ((h.joker_n & 0xFF) << 16) | ((uint32_t)(h.cons_n & 0xFF) << 24);
-  q.z = (h.joker_slots & 0xFF) | ((h.cons_slots & 0xFF) << 8) | ((h.n_magic & 0xFF) << 16) | ((uint32_t)(h.n_minimalist & 0xFF) << 24);
-  q.w = (h.ante & 0xFFFF) | ((uint32_t)(h.jokers_sold & 0xFFFF) << 16);
-  sts128(rec + 16, q);
-  q.x = (uint32_t)h.money; q.y = (uint32_t)h.chips_needed;
-  q.z = (uint32_t)h.round_chips; q.w = (uint32_t)((uint64_t)h.round_chips >> 32);
-  sts128(rec + 32, q);
-  q.x = (uint32_t)h.chips_scored; q.y = (uint32_t)((uint64_t)h.chips_scored >> 32);
-  q.z = (uint32_t)h.best_hand; q.w = (uint32_t)h.hands_played_total;
-  sts128(rec + 48, q);
-  q.x = (h.hands_played_ante & 0xFFFF) | ((h.boss_flags & 0xFF) << 16) | ((uint32_t)(h.boss_cards_required & 0xFF) << 24);
-  q.y = (h.boss_played_types & 0xFFFF) | ((h.boss_hands_played & 0xFF) << 16) | ((uint32_t)(h.deck_n & 0xFF) << 24);
-  q.z = (uint32_t)h.boss_played_cards; q.w = (uint32_t)(h.boss_played_cards >> 32);
-  sts128(rec + 64, q);
-  q.x = (uint32_t)h.jokers; q.y = (uint32_t)(h.jokers >> 32); q.z = (uint32_t)h.cons; q.w = (uint32_t)(h.cons >> 32);
-  sts128(rec + 80, q);
-  q.x = h.lv0; q.y = h.lv1; q.z = h.lv2; q.w = (uint32_t)h.shop_reroll_state;
-  sts128(rec + 96, q);
-  q.x = h.rng_seed; q.y = h.rng_ctr; q.z = h.ep_len; q.w = h.episode;
-  sts128(rec + 112, q);
+  q.x = (uint32_t)h.hand; q.y = (uint32_t)(h.hand >> 32); q.z = (uint32_t)h.hand_code; q.w = (uint32_t)(h.hand_code >> 32);
+  sts128(hot, q);
+  q.x = (h.hand_n & 0xFF) | ((h.hand_size & 0xFF) << 8) | ((h.sel_n & 0xFF) << 16) | ((uint32_t)(h.highlight & 0xFF) << 24);
+  q.y = h.sel_order;
+  q.z = (h.face_down & 0xFF) | ((h.phase & 0xFF) << 8) | ((h.round & 0xFF) << 16) | ((uint32_t)(h.boss_type & 0xFF) << 24);
+  q.w = (h.hands_left & 0xFF) | ((h.discards_left & 0xFF) << 8) | ((h.joker_n & 0xFF) << 16) | ((uint32_t)(h.cons_n & 0xFF) << 24);
+  sts128(hot + 16, q);
+  q.x = (h.joker_slots & 0xFF) | ((h.cons_slots & 0xFF) << 8) | ((h.n_magic & 0xFF) << 16) | ((uint32_t)(h.n_minimalist & 0xFF) << 24);
+  q.y = (h.ante & 0xFFFF) | ((uint32_t)(h.jokers_sold & 0xFFFF) << 16);
+  q.z = (uint32_t)h.money; q.w = (uint32_t)h.chips_needed;
+  sts128(hot + 32, q);
+  q.x = (uint32_t)h.round_chips; q.y = (uint32_t)((uint64_t)h.round_chips >> 32);
+  q.z = (uint32_t)h.chips_scored; q.w = (uint32_t)((uint64_t)h.chips_scored >> 32);
+  sts128(hot + 48, q);
+  q.x = (uint32_t)h.best_hand; q.y = (uint32_t)h.hands_played_total;
+  q.z = (h.hands_played_ante & 0xFFFF) | ((h.boss_flags & 0xFF) << 16) | ((uint32_t)(h.boss_cards_required & 0xFF) << 24);
+  q.w = (h.boss_played_types & 0xFFFF) | ((h.boss_hands_played & 0xFF) << 16) | ((uint32_t)(h.deck_n & 0xFF) << 24);
+  sts128(hot + 64, q);
+  q.x = (uint32_t)h.boss_played_cards; q.y = (uint32_t)(h.boss_played_cards >> 32);
+  q.z = (uint32_t)h.jokers; q.w = (uint32_t)(h.jokers >> 32);
+  sts128(hot + 80, q);
+  q.x = (uint32_t)h.cons; q.y = (uint32_t)(h.cons >> 32); q.z = h.lv0; q.w = h.lv1;
+  sts128(hot + 96, q);
+  q.x = h.lv2; q.y = (uint32_t)h.shop_reroll_state; q.z = h.rng_seed; q.w = h.rng_ctr;
+  sts128(hot + 112, q);
+  q.x = h.ep_len; q.y = h.episode; q.z = 0; q.w = 0;
+  sts128(hot + 128, q);
 }
 
 __device__ __forceinline__ int hand_level(const Hot& h, int ht) {
@@ -171,6 +175,18 @@ __device__ __forceinline__ void remove_slots(Hot& h, int slots) {
   h.hand = out;
   h.hand_n = n;
 }
+// hand_code cache: card code of every hand slot (what obs['hand'] shows), refreshed whenever the
+// hand list changes so that passes that only have the hot record can emit the observation
+__device__ __forceinline__ void refresh_hand_codes(Hot& h, const uint8_t* rec) {
+  uint64_t codes = ~0ull;
+#pragma unroll 1
+  for (int i = 0; i < h.hand_n; i++) {
+    int idx = byte_at(h.hand, i);
+    if (idx < h.deck_n) codes = with_byte(codes, i, c16_code(deck16(rec, idx)));
+  }
+  h.hand_code = codes;
+}
+
 // ---------------------------------------------------------------------------------------------
 // shop, shop.py:96-205 and balatro_env_2.py:1383-1392
 // ---------------------------------------------------------------------------------------------
@@ -504,7 +520,7 @@ __device__ __forceinline__ uint32_t next_episode_seed(uint32_t seed) {
 
 // hot block of a fresh episode (UnifiedGameState defaults)
 __device__ __forceinline__ void reset_hot(Hot& h, uint32_t seed) {
-  h.hand = ~0ull;
+  h.hand = ~0ull; h.hand_code = ~0ull;
   h.hand_n = 0; h.hand_size = 8; h.sel_n = 0; h.highlight = 0; h.sel_order = 0;
   h.face_down = 0; h.phase = BGYM_PHASE_BLIND_SELECT; h.round = 1; h.boss_type = 0;
   h.hands_left = 4; h.discards_left = 3; h.joker_n = 0; h.cons_n = 0;
@@ -525,7 +541,7 @@ __device__ __forceinline__ void reset_hot(Hot& h, uint32_t seed) {
 //         (for i in reversed(range(1, n)): j = randbelow(i + 1); swap) with native Philox draws
 __device__ __noinline__ void reset_blocks_serial(uint8_t* rec, uint32_t seed, const uint8_t* deck52) {
 #pragma unroll 1
-  for (int o = 128; o < 304; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
+  for (int o = 0; o < BGYM_COLD_BYTES; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
   if (deck52) {
 #pragma unroll 1
     for (int i = 0; i < 52; i++) set_deck16(rec, i, deck52[i]);
@@ -550,9 +566,9 @@ __device__ __noinline__ void reset_blocks_serial(uint8_t* rec, uint32_t seed, co
 //            are parked as bytes in the (just zeroed) shop block of the record;
 //   finish  (each terminated lane for itself, all of them in parallel): apply the 51 swaps in
 //            random.shuffle's order, then clear the parked draws.
-constexpr int OFF_RESET_SCRATCH = 244;  // shop block, 52 bytes used
+constexpr int OFF_RESET_SCRATCH = 116;  // shop part of the cold record, 52 bytes used
 __device__ __forceinline__ void reset_blocks_prepare(uint8_t* rec_of_src, uint32_t seed, int lane) {
-  if (lane < 11) sts128(rec_of_src + 128 + 16 * lane, make_uint4(0, 0, 0, 0));
+  if (lane < 11) sts128(rec_of_src + 16 * lane, make_uint4(0, 0, 0, 0));
   __syncwarp();
   set_deck16(rec_of_src, lane, (lane % 13) * 4 + lane / 13);
   if (lane < 20) set_deck16(rec_of_src, lane + 32, ((lane + 32) % 13) * 4 + (lane + 32) / 13);
@@ -571,7 +587,7 @@ __device__ __forceinline__ void reset_blocks_finish(uint8_t* rec) {
     set_deck16(rec, i, b); set_deck16(rec, j, a);
   }
 #pragma unroll 1
-  for (int o = 240; o < 304; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
+  for (int o = 112; o < BGYM_COLD_BYTES; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
 }
 // warp-level driver: `want_reset` lanes get fresh deck/shop blocks in their record `my_rec`
 __device__ __forceinline__ void autoreset_warp(bool want_reset, uint32_t new_seed, uint8_t* my_rec, int lane) {
@@ -598,9 +614,9 @@ __device__ __forceinline__ void autoreset_warp(bool want_reset, uint32_t new_see
 enum { RARE_NONE = 0, RARE_ADVANCE = 1, RARE_REROLL = 2, RARE_CONSUMABLE = 3 };
 struct RareOut { double reward; int err; int terminated; };
 
-__device__ __noinline__ void rare_dispatch(uint8_t* rec, int op, int arg, Draws* rng, RareOut* out) {
+__device__ __noinline__ void rare_dispatch(uint8_t* hot, uint8_t* rec, int op, int arg, Draws* rng, RareOut* out) {
   Hot h;
-  unpack_hot(rec, h);
+  unpack_hot(hot, h);
   out->reward = 0.0; out->err = 0; out->terminated = 0;
   if (op == RARE_ADVANCE) {
     advance_round(h, rec, *rng);
@@ -616,7 +632,7 @@ __device__ __noinline__ void rare_dispatch(uint8_t* rec, int op, int arg, Draws*
   } else if (op == RARE_CONSUMABLE) {
     out->reward = use_consumable(h, rec, arg, *rng, out->err, out->terminated);
   }
-  pack_hot(rec, h);
+  pack_hot(hot, h);
 }
 
 // the ante > 3 score reward goes through log10 (balatro_env_2.py:821); kept out of line
@@ -638,7 +654,7 @@ struct StepInfo {
 // kernel per category so that every warp in flight executes the same short code).
 enum { CAT_SELECT = 1, CAT_PLAY = 2, CAT_DISCARD = 4, CAT_OTHER = 8, CAT_ALL = 15 };
 template <int CATS>
-__device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const BgymDraws* tape, double& reward_out,
+__device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_t mask, const BgymDraws* tape, double& reward_out,
                          int& terminated_out, StepInfo& info) {
   info.final_score = 0; info.x_mult = 1.0; info.chips = 0; info.mult = 0; info.hand_type = -1;
   info.error_code = 0; info.flags = 0; info.cards_played = 0; info.base_score = 0;
@@ -657,6 +673,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
   double reward = 0.0;
   int terminated = 0;
   int rare_op = RARE_NONE, rare_arg = 0;
+  bool hand_changed = false;
 
   if ((CATS & CAT_SELECT) && action >= BGYM_A_SELECT_BASE && action < BGYM_A_SELECT_BASE + 8) {
     // toggle in the ordered selection list (:1052-1058); legal only in PLAY phase by the mask
@@ -806,6 +823,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     } else {
       h.hands_left--;
       draw_cards(h);
+      hand_changed = true;
       if (boss) {  // on_hand_drawn boss_blinds.py:343-378 (first_hand is already False here)
         int face = 0;
         if (boss == B_HOOK) {
@@ -860,6 +878,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     remove_slots(h, h.highlight | sel_slots);
     h.highlight = 0;
     draw_cards(h);
+    hand_changed = true;
     h.discards_left--;
     h.sel_n = 0; h.sel_order = 0;
     #pragma unroll 1
@@ -876,6 +895,7 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
   } else if ((CATS & CAT_OTHER) && action == BGYM_A_SHOP_END) {
     h.phase = BGYM_PHASE_PLAY;
     draw_cards(h);
+    hand_changed = true;
     info.flags |= BGYM_F_SHOP_DONE;
   } else if ((CATS & CAT_OTHER) && action == BGYM_A_SHOP_REROLL) {
     rare_op = RARE_REROLL;
@@ -931,17 +951,19 @@ __device__ void step_env(Hot& h, uint8_t* rec, int action, uint64_t mask, const 
     h.chips_needed = (int)min(needed, 2147483647LL);
     h.phase = BGYM_PHASE_PLAY;
     draw_cards(h);
+    hand_changed = true;
   } else if ((CATS & CAT_OTHER) && action == BGYM_A_SKIP_BLIND) {
     reward = -5.0;
     rare_op = RARE_ADVANCE;
   }
   if ((CATS & (CAT_PLAY | CAT_OTHER)) && rare_op != RARE_NONE) {   // ONE out-of-line site for every rare path
     RareOut ro;
-    pack_hot(rec, h);
-    rare_dispatch(rec, rare_op, rare_arg, &rng, &ro);
-    unpack_hot(rec, h);
+    pack_hot(hot, h);
+    rare_dispatch(hot, rec, rare_op, rare_arg, &rng, &ro);
+    unpack_hot(hot, h);
     if (rare_op != RARE_ADVANCE) { reward = ro.reward; info.error_code = ro.err; terminated = ro.terminated; }
   }
+  if ((CATS & (CAT_PLAY | CAT_DISCARD | CAT_OTHER)) && hand_changed) refresh_hand_codes(h, rec);
   if (!tape) h.rng_ctr = rng.ctr;
   reward_out = reward;
   terminated_out = terminated;
@@ -958,13 +980,7 @@ __device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint
   #pragma unroll 1
   for (int k = 0; k < h.sel_n; k++) selm |= 1u << nib_at(h.sel_order, k);
   // 0: hand[8] | selected_cards[8]   (hand codes = deck[hand[i]], -1 when empty)
-  uint64_t codes = ~0ull;
-  #pragma unroll 1
-  for (int i = 0; i < h.hand_n; i++) {
-    int idx = byte_at(h.hand, i);
-    if (idx < h.deck_n) codes = with_byte(codes, i, c16_code(deck16(rec, idx)));
-  }
-  q.x = (uint32_t)codes; q.y = (uint32_t)(codes >> 32);
+  q.x = (uint32_t)h.hand_code; q.y = (uint32_t)(h.hand_code >> 32);
   q.z = spread4(selm); q.w = spread4(selm >> 4);
   sts128(obs, q);
   // 16: face_down_cards[8] | chips_scored

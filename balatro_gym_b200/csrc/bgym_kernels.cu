@@ -1,21 +1,20 @@
 // bgym_kernels.cu — sm_100a kernels and the C-ABI (include/bgym.h) of the batched Balatro env.
 //
 // Kernels
-//   env_step_kernel     K2  fused BalatroEnv.step: mask check -> phase dispatch -> scoring -> boss ->
+//   env_step_main_kernel / env_step_gather_kernel   K2  the fused, category-partitioned BalatroEnv.step
+//                           (bgym_step_part.cuh): mask check -> phase dispatch -> scoring -> boss ->
 //                           round advance / shop generation -> reward -> observation + mask emission,
-//                           optional in-place autoreset (K3) and fused random-legal policy.
-//   env_reset_kernel    K3  reset + first observation (same staging as K2)
-//   score_hands_kernel  K1  classify + chips x mult + joker interpreter (K4) per hand
+//                           in-place autoreset (K3) and an optional fused random-legal policy
+//   env_reset_kernel    K3  reset + first observation
+//   score_hands5_kernel / score_hands_kernel   K1  classify + chips x mult + joker interpreter (K4)
 //   action_mask_kernel, sample_actions_kernel, episode_stats_kernel (K6)
 //
-// Data movement of K2/K3: state is a dense array of 320 B records.  Each warp owns a tile of 32
-// envs; every lane pulls its own record into shared memory with ONE 1-D bulk async copy
-// (cp.async.bulk, SASS UBLKCP — the TMA engine without a tensor map) that completes on the warp's
-// mbarrier, works on it in place, assembles the 240 B observation record in shared memory with
-// 128-bit stores, and pushes both back with bulk async stores.  Shared-memory strides are odd
-// multiples of 16 B (336 / 240) so the 128-bit accesses of a quarter-warp hit distinct bank groups.
-// Tiles are double buffered per warp: the bulk loads of the next tile are in flight while the
-// current one is computed.
+// Data movement of K2/K3: env state is two dense arrays, hot[n] (144 B records) and cold[n] (176 B
+// records).  A warp owns a tile of 32 envs; a tile of records is contiguous, so it moves between
+// global and shared memory with ONE 1-D bulk async copy (cp.async.bulk, SASS UBLKCP — the TMA engine
+// without a tensor map) that completes on the warp's mbarrier; each lane then works on its record
+// with 128-bit shared-memory accesses (record strides 144 / 176 / 240 B are odd multiples of 16 B,
+// so a quarter-warp hits 8 distinct bank groups), and results leave with bulk async stores.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -26,32 +25,10 @@
 
 namespace bgym {
 
-constexpr int REC_STRIDE = BGYM_STATE_BYTES;  // 304 = 19 x 16 B: odd 16-byte stride, no padding needed
-constexpr int OBS_STRIDE = BGYM_OBS_BYTES;    // 240 = 15 x 16 B
-constexpr int WARP_STATE_BYTES = 32 * REC_STRIDE;              // 9728
-constexpr int WARP_OBS_BYTES = 32 * OBS_STRIDE;                // 7680
-
-// Two staging variants (picked at run time, BGYM_VARIANT=0/1):
-//   V0: single state buffer per warp, 4 warps/CTA, 3 CTAs/SM  -> 12 warps/SM hide each other's loads
-//   V1: double-buffered state per warp, 8 warps/CTA, 1 CTA/SM -> 8 warps/SM, next tile prefetched
-//   V6/V7: single state buffer, observation written straight to global with 128-bit stores (no obs
-//          staging) -> 9.7 KB of shared memory per warp, 20+ warps/SM
-template <int STAGES, int WARPS, bool OBS_DIRECT = false, int CTAS = 0>
-struct Cfg {
-  static constexpr int stages = STAGES, warps = WARPS, threads = WARPS * 32;
-  static constexpr bool obs_direct = OBS_DIRECT;
-  static constexpr int warp_smem = STAGES * WARP_STATE_BYTES + (OBS_DIRECT ? 0 : WARP_OBS_BYTES);
-  static constexpr int cta_smem = WARPS * warp_smem + 16 * WARPS;  // + mbarriers
-  static constexpr int ctas_per_sm = CTAS ? CTAS : (227 * 1024) / cta_smem;
-};
-using CfgV0 = Cfg<1, 4>;
-using CfgV1 = Cfg<2, 8>;
-using CfgV6 = Cfg<1, 4, true, 5>;
-using CfgV7 = Cfg<1, 3, true, 7>;
-
 struct StepArgs {
-  uint8_t* state;            // n x 320
-  const int32_t* actions;    // n (nullable with BGYM_FLAG_RANDOM_POLICY)
+  uint8_t* hot;              // n x 144
+  uint8_t* cold;             // n x 176
+  const int32_t* actions;    // n (read; written instead with BGYM_FLAG_RANDOM_POLICY)
   int32_t* actions_out;      // n (written with BGYM_FLAG_RANDOM_POLICY, nullable)
   const BgymDraws* draws;    // n (nullable)
   uint8_t* obs;              // n x 240 (nullable)
@@ -71,153 +48,71 @@ struct StepArgs {
   long long part_cap;
 };
 
-enum { MODE_STEP = 0, MODE_RESET = 1 };
-
 }  // namespace bgym
-#include "bgym_step_sorted.cuh"
 #include "bgym_step_part.cuh"
 namespace bgym {
 
-template <int MODE, typename C>
-__global__ void __launch_bounds__(C::threads, C::ctas_per_sm) env_kernel(StepArgs a) {
+// ---------------------------------------------------------------------------------------------
+// K3: reset.  Per-warp tiles; with a reset mask the untouched envs are loaded and re-emitted.
+// ---------------------------------------------------------------------------------------------
+constexpr int RESET_WARPS = 4;
+constexpr int RESET_WARP_SMEM = 32 * (BGYM_HOT_BYTES + BGYM_COLD_BYTES + BGYM_OBS_BYTES);
+constexpr int RESET_CTA_SMEM = RESET_WARPS * RESET_WARP_SMEM + 16 * RESET_WARPS;
+
+__global__ void __launch_bounds__(RESET_WARPS * 32, 3) env_reset_kernel(StepArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int STAGES = C::stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* wbase = smem + warp * C::warp_smem;
-  uint8_t* obs_buf = wbase + STAGES * WARP_STATE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::warps * C::warp_smem) + warp * 2;
-
-  if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_fence_init();
-  }
+  uint8_t* hot_buf = smem + warp * RESET_WARP_SMEM;
+  uint8_t* cold_buf = hot_buf + 32 * BGYM_HOT_BYTES;
+  uint8_t* obs_buf = cold_buf + 32 * BGYM_COLD_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + RESET_WARPS * RESET_WARP_SMEM) + warp * 2;
+  if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncwarp();
-
   const long long n_tiles = (a.n + 31) >> 5;
-  const long long warp_gid = (long long)blockIdx.x * C::warps + warp;
-  const long long warp_cnt = (long long)gridDim.x * C::warps;
+  const long long warp_gid = (long long)blockIdx.x * RESET_WARPS + warp;
+  const long long warp_cnt = (long long)gridDim.x * RESET_WARPS;
   const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
-
-  // a reset of ALL envs needs no state load at all
-  const bool need_load = (MODE == MODE_STEP) || (a.reset_mask != nullptr);
-
-  auto issue_load = [&](long long tile, int stage) {
-    // ONE bulk copy per warp tile: 32 consecutive records are contiguous in global and in shared
-    if (lane == 0) {
-      uint32_t bytes = (uint32_t)(min(32LL, a.n - tile * 32) * BGYM_STATE_BYTES);
-      mbar_arrive_expect_tx(&bars[stage], bytes);
-      bulk_g2s(wbase + stage * WARP_STATE_BYTES, a.state + tile * 32 * BGYM_STATE_BYTES, bytes, &bars[stage]);
-    }
-  };
-
-  long long tile = warp_gid;
-  int stage = 0;
-  uint32_t phase_bits = 0;  // parity per stage
-  if (STAGES == 2 && need_load && tile < n_tiles) issue_load(tile, 0);
-
-  for (; tile < n_tiles; tile += warp_cnt, stage = (STAGES == 2) ? (stage ^ 1) : 0) {
+  const bool need_load = a.reset_mask != nullptr;   // a reset of ALL envs needs no state load
+  uint32_t parity = 0;
+  for (long long tile = warp_gid; tile < n_tiles; tile += warp_cnt) {
     const long long e = tile * 32 + lane;
     const bool active = e < a.n;
-    uint8_t* rec = wbase + stage * WARP_STATE_BYTES + lane * REC_STRIDE;
-    uint8_t* obs_s = C::obs_direct ? (a.obs + e * BGYM_OBS_BYTES) : (obs_buf + lane * OBS_STRIDE);
-
-    // the buffer about to be overwritten (and the obs buffer) were last READ by the bulk stores
-    // lane 0 issued in the previous iteration: wait for those reads to finish
+    const uint32_t cnt = (uint32_t)min(32LL, a.n - tile * 32);
+    uint8_t* hot = hot_buf + lane * BGYM_HOT_BYTES;
+    uint8_t* cold = cold_buf + lane * BGYM_COLD_BYTES;
+    uint8_t* obs_s = obs_buf + lane * BGYM_OBS_BYTES;
     if (lane == 0) bulk_wait_read0();
     __syncwarp();
-    if (STAGES == 2) {
-      const long long next = tile + warp_cnt;
-      if (need_load && next < n_tiles) issue_load(next, stage ^ 1);
-    } else {
-      if (need_load) issue_load(tile, 0);
-    }
-
-    // inputs that do not depend on the state: fetch while the bulk copy lands
-    int action = 0;
-    if (MODE == MODE_STEP && active && a.actions && !(a.flags & BGYM_FLAG_RANDOM_POLICY)) action = __ldg(a.actions + e);
-
     if (need_load) {
-      mbar_wait(&bars[stage], (phase_bits >> stage) & 1);
-      phase_bits ^= 1u << stage;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar, cnt * (BGYM_HOT_BYTES + BGYM_COLD_BYTES));
+        bulk_g2s(hot_buf, a.hot + tile * 32 * BGYM_HOT_BYTES, cnt * BGYM_HOT_BYTES, bar);
+        bulk_g2s(cold_buf, a.cold + tile * 32 * BGYM_COLD_BYTES, cnt * BGYM_COLD_BYTES, bar);
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1;
     }
-
-    Hot h;
-    double reward = 0.0;
-    int terminated = 0;
-    StepInfo info;
-    bool do_store_state = true, want_reset = false;
-    uint32_t new_seed = 0;
     if (active) {
-      if (MODE == MODE_STEP) {
-        unpack_hot(rec, h);
-        uint64_t m0 = action_mask(h, rec);
-        if (a.flags & BGYM_FLAG_RANDOM_POLICY) {
-          // uniform legal action: Philox keyed by (seed, policy key), counter = episode step
-          int cnt = __popcll(m0);
-          uint4 w = philox4x32_10(h.ep_len, 0, 0, 0, h.rng_seed, BGYM_POLICY_KEY1);
-          int k = (int)__umulhi(w.x, (uint32_t)cnt);
-          uint64_t mm = m0;
-          for (int i = 0; i < k; i++) mm &= mm - 1;
-          action = cnt ? __ffsll((long long)mm) - 1 : 0;
-          if (a.actions_out) a.actions_out[e] = action;
-        }
-        step_env<CAT_ALL>(h, rec, action, m0, a.draws ? a.draws + e : nullptr, reward, terminated, info);
-        if (terminated && (a.flags & BGYM_FLAG_AUTORESET)) {
-          uint32_t episode = h.episode + 1;
-          new_seed = next_episode_seed(h.rng_seed);
-          reset_hot(h, new_seed);
-          h.episode = episode;
-          info.flags |= BGYM_F_AUTORESET_DONE;
-          want_reset = true;
-        }
+      Hot h;
+      if (a.reset_mask && !a.reset_mask[e]) {
+        unpack_hot(hot, h);   // untouched env: only re-emit its observation
       } else {
-        if (a.reset_mask && !a.reset_mask[e]) {
-          unpack_hot(rec, h);   // untouched env: only re-emit its observation
-          do_store_state = false;
-        } else {
-          reset_hot(h, a.seeds[e]);
-          reset_blocks_serial(rec, a.seeds[e], a.decks52 ? a.decks52 + e * 52 : nullptr);
-        }
+        reset_hot(h, a.seeds[e]);
+        reset_blocks_serial(cold, a.seeds[e], a.decks52 ? a.decks52 + e * 52 : nullptr);
+        pack_hot(hot, h);
       }
+      if (with_obs) write_obs(h, cold, action_mask(h, cold), obs_s);
     }
-    if (MODE == MODE_STEP && (a.flags & BGYM_FLAG_AUTORESET)) {
-      // in-place autoreset: the deck/shop blocks of every terminated env of the tile are rebuilt by
-      // the WHOLE warp, one env after the other (few lanes terminate per step)
-      autoreset_warp(want_reset, new_seed, rec, lane);
-    }
-    if (active) {
-      if (do_store_state) pack_hot(rec, h);
-      if (with_obs) write_obs(h, rec, action_mask(h, rec), obs_s);
-      fence_async_smem();  // this lane's shared-memory writes -> visible to the async proxy
-      if (MODE == MODE_STEP) {
-        a.reward[e] = reward;
-        a.terminated[e] = (uint8_t)terminated;
-        if (a.truncated) a.truncated[e] = 0;
-        if (a.info) {
-          uint4 i0, i1;
-          i0.x = (uint32_t)info.final_score; i0.y = (uint32_t)((uint64_t)info.final_score >> 32);
-          unsigned long long xb = (unsigned long long)__double_as_longlong(info.x_mult);
-          i0.z = (uint32_t)xb; i0.w = (uint32_t)(xb >> 32);
-          i1.x = (uint32_t)info.chips; i1.y = (uint32_t)info.mult;
-          i1.z = (uint32_t)(info.hand_type & 0xFF) | ((uint32_t)(info.error_code & 0xFF) << 8) |
-                 ((uint32_t)(info.flags & 0xFF) << 16) | ((uint32_t)(info.cards_played & 0xFF) << 24);
-          i1.w = (uint32_t)info.base_score;
-          uint4* ip = reinterpret_cast<uint4*>(a.info + e);
-          ip[0] = i0; ip[1] = i1;
-        }
-      }
-    }
+    fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-      // ONE bulk store per warp tile for the state records and one for the observation records
-      uint32_t cnt = (uint32_t)min(32LL, a.n - tile * 32);
-      bulk_s2g(a.state + tile * 32 * BGYM_STATE_BYTES, wbase + stage * WARP_STATE_BYTES, cnt * BGYM_STATE_BYTES);
-      if (with_obs && !C::obs_direct) bulk_s2g(a.obs + tile * 32 * BGYM_OBS_BYTES, obs_buf, cnt * BGYM_OBS_BYTES);
+      bulk_s2g(a.hot + tile * 32 * BGYM_HOT_BYTES, hot_buf, cnt * BGYM_HOT_BYTES);
+      bulk_s2g(a.cold + tile * 32 * BGYM_COLD_BYTES, cold_buf, cnt * BGYM_COLD_BYTES);
+      if (with_obs) bulk_s2g(a.obs + tile * 32 * BGYM_OBS_BYTES, obs_buf, cnt * BGYM_OBS_BYTES);
       bulk_commit();
     }
   }
-  if (lane == 0) bulk_wait0();  // every bulk store of this warp has completed before exit
+  if (lane == 0) bulk_wait0();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -405,26 +300,28 @@ __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
   }
 }
 
+
 // ---------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void action_mask_kernel(const uint8_t* state, uint64_t* mask, long long n) {
+__global__ void action_mask_kernel(const uint8_t* hot, const uint8_t* cold, uint64_t* mask, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const uint8_t* rec = state + i * BGYM_STATE_BYTES;
+    const uint8_t* hr = hot + i * BGYM_HOT_BYTES;
+    const uint8_t* cr = cold + i * BGYM_COLD_BYTES;
     uint64_t m = 0;
-    int phase = rec[17];
+    int phase = hr[25];
     if (phase == BGYM_PHASE_PLAY) {
-      int hand_n = rec[8], sel_n = rec[10], discards_left = rec[21], cons_n = rec[23];
+      int hand_n = hr[16], sel_n = hr[18], discards_left = hr[29], cons_n = hr[31];
       m = ((1ull << min(hand_n, 8)) - 1) << BGYM_A_SELECT_BASE;
       if (sel_n > 0) m |= 1ull << BGYM_A_PLAY_HAND;
       if (sel_n > 0 && discards_left > 0) m |= 1ull << BGYM_A_DISCARD;
       m |= ((1ull << cons_n) - 1) << BGYM_A_USE_CONS_BASE;
     } else if (phase == BGYM_PHASE_SHOP) {
-      int money = *reinterpret_cast<const int*>(rec + 32), joker_n = rec[22];
-      int n_items = rec[OFF_N_ITEMS];
+      int money = *reinterpret_cast<const int*>(hr + 40), joker_n = hr[30];
+      int n_items = cr[OFF_N_ITEMS];
       for (int k = 0; k < n_items; k++)
-        if (money >= *reinterpret_cast<const int*>(rec + OFF_ITEM_COST + 4 * k)) m |= 1ull << (BGYM_A_SHOP_BUY_BASE + k);
-      if (money >= *reinterpret_cast<const int*>(rec + 108)) m |= 1ull << BGYM_A_SHOP_REROLL;
+        if (money >= *reinterpret_cast<const int*>(cr + OFF_ITEM_COST + 4 * k)) m |= 1ull << (BGYM_A_SHOP_BUY_BASE + k);
+      if (money >= *reinterpret_cast<const int*>(hr + 116)) m |= 1ull << BGYM_A_SHOP_REROLL;
       m |= 1ull << BGYM_A_SHOP_END;
       m |= ((1ull << joker_n) - 1) << BGYM_A_SELL_JOKER_BASE;
     } else if (phase == BGYM_PHASE_BLIND_SELECT) {
@@ -433,6 +330,7 @@ __global__ void action_mask_kernel(const uint8_t* state, uint64_t* mask, long lo
     mask[i] = m;
   }
 }
+
 
 // uniform random legal action from obs.action_mask_bits; Philox keyed (seed, policy key),
 // counter (env index, step)
@@ -476,6 +374,7 @@ __global__ void episode_stats_kernel(const double* reward, const uint8_t* termin
   }
 }
 
+
 }  // namespace bgym
 
 // =================================================================================================
@@ -496,15 +395,6 @@ static int cuda_rc(cudaError_t e, const char* where) {
 
 static int g_sm_count = 0;
 static bool g_attr_set = false;
-// step-kernel variants (BGYM_VARIANT): 0/1 fixed lane<->env mapping (single / double buffered),
-// 2..5 CTA-level path sorting with 4x3, 6x2, 8x1, 12x1 (warps per CTA x CTAs per SM)
-//   8 category-partitioned step (main pass + one gather pass per rare category)  <- default
-#define BGYM_DEFAULT_VARIANT 8
-using SortedA = SortedCfg<4, 3>;
-using SortedB = SortedCfg<6, 2>;
-using SortedC = SortedCfg<8, 1>;
-using SortedD = SortedCfg<12, 1>;
-static int g_variant = BGYM_DEFAULT_VARIANT;
 static int ensure_device_setup() {
   if (g_attr_set) return 0;
   int dev = 0;
@@ -512,39 +402,23 @@ static int ensure_device_setup() {
   if (e != cudaSuccess) return cuda_rc(e, "cudaGetDevice");
   e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return cuda_rc(e, "cudaDeviceGetAttribute");
-  e = cudaFuncSetAttribute(env_kernel<MODE_STEP, CfgV0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgV0::cta_smem);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(step v0)");
-  e = cudaFuncSetAttribute(env_kernel<MODE_RESET, CfgV0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgV0::cta_smem);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(reset v0)");
-  e = cudaFuncSetAttribute(env_kernel<MODE_STEP, CfgV1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgV1::cta_smem);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(step v1)");
-  e = cudaFuncSetAttribute(env_kernel<MODE_STEP, CfgV6>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgV6::cta_smem);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(step v6)");
-  e = cudaFuncSetAttribute(env_kernel<MODE_STEP, CfgV7>, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgV7::cta_smem);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(step v7)");
-  e = cudaFuncSetAttribute(env_step_sorted_kernel<SortedA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortedA::cta_smem);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(sorted A)");
-  e = cudaFuncSetAttribute(env_step_sorted_kernel<SortedB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortedB::cta_smem);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(sorted B)");
-  e = cudaFuncSetAttribute(env_step_sorted_kernel<SortedC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortedC::cta_smem);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(sorted C)");
-  e = cudaFuncSetAttribute(env_step_sorted_kernel<SortedD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SortedD::cta_smem);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(sorted D)");
-  e = cudaFuncSetAttribute(env_step_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_CTA_SMEM);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(part main)");
-  e = cudaFuncSetAttribute(env_step_gather_kernel<CAT_PLAY, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_CTA_SMEM);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(part play)");
-  e = cudaFuncSetAttribute(env_step_gather_kernel<CAT_DISCARD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_CTA_SMEM);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(part discard)");
-  e = cudaFuncSetAttribute(env_step_gather_kernel<CAT_OTHER, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PART_CTA_SMEM);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(part other)");
-  const char* v = getenv("BGYM_VARIANT");
-  g_variant = (v && v[0] >= '0' && v[0] <= '8') ? (v[0] - '0') : BGYM_DEFAULT_VARIANT;
+#define BGYM_SET_SMEM(kernel, bytes)                                                                 \
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);             \
+  if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(" #kernel ")");
+  BGYM_SET_SMEM(env_reset_kernel, RESET_CTA_SMEM)
+  BGYM_SET_SMEM(env_step_main_kernel, MAIN_CTA_SMEM)
+  BGYM_SET_SMEM((env_step_gather_kernel<CAT_PLAY, 0, true>), GATHER_CTA_SMEM)
+  BGYM_SET_SMEM((env_step_gather_kernel<CAT_DISCARD, 1, false>), GATHER_CTA_SMEM)
+  BGYM_SET_SMEM((env_step_gather_kernel<CAT_OTHER, 2, true>), GATHER_CTA_SMEM)
+#undef BGYM_SET_SMEM
   g_attr_set = true;
   return 0;
 }
 
-// scratch of the partitioned step (deferred-env lists + counters), one per (device, stream)
+static bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
+
+// scratch of the partitioned step (deferred-env lists + counters) and the side streams of the
+// concurrent gather passes, one set per (device, stream)
 struct PartScratch { int dev; void* stream; long long cap; int* lists; int* counters;
                      cudaStream_t side[2]; cudaEvent_t ev_main, ev_side[2]; bool streams_ok; };
 static PartScratch g_scratch[16];
@@ -559,7 +433,6 @@ static int get_part_scratch(long long n, void* stream, PartScratch** out) {
     if (g_n_scratch == 16) return set_err(BGYM_E_ARG, "bgym_step: too many (device, stream) pairs in use");
     sc = &g_scratch[g_n_scratch++];
     sc->dev = dev; sc->stream = stream; sc->cap = 0; sc->lists = nullptr; sc->counters = nullptr;
-    // the three gather passes touch disjoint envs and are latency-bound: run them concurrently
     sc->streams_ok = cudaStreamCreateWithFlags(&sc->side[0], cudaStreamNonBlocking) == cudaSuccess &&
                      cudaStreamCreateWithFlags(&sc->side[1], cudaStreamNonBlocking) == cudaSuccess &&
                      cudaEventCreateWithFlags(&sc->ev_main, cudaEventDisableTiming) == cudaSuccess &&
@@ -577,57 +450,12 @@ static int get_part_scratch(long long n, void* stream, PartScratch** out) {
   return 0;
 }
 
-static int launch_partitioned(StepArgs& a, cudaStream_t s) {
-  PartScratch* sc = nullptr;
-  int rc = get_part_scratch(a.n, (void*)s, &sc);
-  if (rc) return rc;
-  a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_cap = sc->cap;
-  cudaError_t e = cudaMemsetAsync(sc->counters, 0, 4 * sizeof(int), s);
-  if (e != cudaSuccess) return cuda_rc(e, "cudaMemsetAsync(step counters)");
-  long long tiles = (a.n + 31) / 32;
-  long long ctas = (tiles + PART_WARPS - 1) / PART_WARPS;
-  long long cap = (long long)g_sm_count * PART_CTAS_PER_SM;
-  int grid = (int)(ctas < cap ? ctas : cap);
-  env_step_main_kernel<<<grid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
-  // the list lengths live on the device: launch resident-size grids, idle warps exit at once
-  long long gcap = (ctas + 3) / 4 < cap ? (ctas + 3) / 4 : cap;
-  int ggrid = (int)(gcap < 1 ? 1 : gcap);
-  static const bool serial = getenv("BGYM_SERIAL_GATHER") != nullptr;
-  if (sc->streams_ok && !serial) {
-    cudaEventRecord(sc->ev_main, s);
-    cudaStreamWaitEvent(sc->side[0], sc->ev_main, 0);
-    env_step_gather_kernel<CAT_PLAY, 0><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, sc->side[0]>>>(a);
-    cudaEventRecord(sc->ev_side[0], sc->side[0]);
-    cudaStreamWaitEvent(sc->side[1], sc->ev_main, 0);
-    env_step_gather_kernel<CAT_OTHER, 2><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, sc->side[1]>>>(a);
-    cudaEventRecord(sc->ev_side[1], sc->side[1]);
-    env_step_gather_kernel<CAT_DISCARD, 1><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
-    cudaStreamWaitEvent(s, sc->ev_side[0], 0);
-    cudaStreamWaitEvent(s, sc->ev_side[1], 0);
-  } else {
-    env_step_gather_kernel<CAT_PLAY, 0><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
-    env_step_gather_kernel<CAT_DISCARD, 1><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
-    env_step_gather_kernel<CAT_OTHER, 2><<<ggrid, PART_WARPS * 32, PART_CTA_SMEM, s>>>(a);
-  }
-  return 0;
-}
-
-template <typename C>
-static void launch_sorted(const StepArgs& a, cudaStream_t s) {
-  long long tiles = (a.n + C::T - 1) / C::T;
-  long long cap = (long long)g_sm_count * C::ctas_per_sm;
-  env_step_sorted_kernel<C><<<(int)(tiles < cap ? tiles : cap), C::threads, C::cta_smem, s>>>(a);
-}
-
-template <typename C>
-static int env_grid(long long n) {
+static int tile_grid(long long n, int warps, int ctas_per_sm) {
   long long tiles = (n + 31) / 32;
-  long long ctas = (tiles + C::warps - 1) / C::warps;
-  long long cap = (long long)g_sm_count * C::ctas_per_sm;  // persistent: resident CTAs only
+  long long ctas = (tiles + warps - 1) / warps;
+  long long cap = (long long)g_sm_count * ctas_per_sm;   // persistent: resident CTAs only
   return (int)(ctas < cap ? ctas : cap);
 }
-
-static bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
 
 extern "C" {
 
@@ -639,63 +467,84 @@ int bgym_device_count(void) {
   return n;
 }
 
-int bgym_reset(BgymState* state, BgymObs* obs, const uint8_t* reset_mask, const uint32_t* seeds,
+int bgym_reset(BgymHot* hot, BgymCold* cold, BgymObs* obs, const uint8_t* reset_mask, const uint32_t* seeds,
                const uint8_t* decks52, int64_t n, int flags, void* stream) {
-  if (n < 0 || !state || !seeds) return set_err(BGYM_E_ARG, "bgym_reset: null state/seeds or negative n");
+  if (n < 0 || !hot || !cold || !seeds) return set_err(BGYM_E_ARG, "bgym_reset: null hot/cold/seeds or negative n");
   if (!obs && !(flags & BGYM_FLAG_NO_OBS)) return set_err(BGYM_E_ARG, "bgym_reset: obs is NULL without BGYM_FLAG_NO_OBS");
-  if (misaligned(state, 16) || misaligned(obs, 16)) return set_err(BGYM_E_ALIGN, "bgym_reset: state/obs must be 16-byte aligned");
+  if (misaligned(hot, 16) || misaligned(cold, 16) || misaligned(obs, 16))
+    return set_err(BGYM_E_ALIGN, "bgym_reset: hot/cold/obs must be 16-byte aligned");
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
   StepArgs a;
   memset(&a, 0, sizeof a);
-  a.state = reinterpret_cast<uint8_t*>(state); a.obs = reinterpret_cast<uint8_t*>(obs);
+  a.hot = reinterpret_cast<uint8_t*>(hot); a.cold = reinterpret_cast<uint8_t*>(cold); a.obs = reinterpret_cast<uint8_t*>(obs);
   a.reset_mask = reset_mask; a.seeds = seeds; a.decks52 = decks52; a.n = n; a.flags = flags;
-  env_kernel<MODE_RESET, CfgV0><<<env_grid<CfgV0>(n), CfgV0::threads, CfgV0::cta_smem, (cudaStream_t)stream>>>(a);
+  env_reset_kernel<<<tile_grid(n, RESET_WARPS, 3), RESET_WARPS * 32, RESET_CTA_SMEM, (cudaStream_t)stream>>>(a);
   return cuda_rc(cudaGetLastError(), "bgym_reset launch");
 }
 
-int bgym_step(BgymState* state, int32_t* actions, const BgymDraws* draws, BgymObs* obs,
+int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* draws, BgymObs* obs,
               double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
               int64_t n, int flags, void* stream) {
-  if (n < 0 || !state || !reward || !terminated) return set_err(BGYM_E_ARG, "bgym_step: null state/reward/terminated or negative n");
+  if (n < 0 || !hot || !cold || !reward || !terminated)
+    return set_err(BGYM_E_ARG, "bgym_step: null hot/cold/reward/terminated or negative n");
   if (!actions) return set_err(BGYM_E_ARG, "bgym_step: actions is NULL");
   if (!obs && !(flags & BGYM_FLAG_NO_OBS)) return set_err(BGYM_E_ARG, "bgym_step: obs is NULL without BGYM_FLAG_NO_OBS");
-  if (misaligned(state, 16) || misaligned(obs, 16) || misaligned(info, 16) || misaligned(draws, 8))
-    return set_err(BGYM_E_ALIGN, "bgym_step: state/obs/info must be 16-byte aligned");
+  if (misaligned(hot, 16) || misaligned(cold, 16) || misaligned(obs, 16) || misaligned(info, 16) || misaligned(draws, 8))
+    return set_err(BGYM_E_ALIGN, "bgym_step: hot/cold/obs/info must be 16-byte aligned");
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  PartScratch* sc = nullptr;
+  rc = get_part_scratch(n, stream, &sc);
+  if (rc) return rc;
   StepArgs a;
   memset(&a, 0, sizeof a);
-  a.state = reinterpret_cast<uint8_t*>(state);
+  a.hot = reinterpret_cast<uint8_t*>(hot); a.cold = reinterpret_cast<uint8_t*>(cold);
   a.actions = actions;
   a.actions_out = (flags & BGYM_FLAG_RANDOM_POLICY) ? actions : nullptr;
   a.draws = draws; a.obs = reinterpret_cast<uint8_t*>(obs);
   a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.info = info;
   a.n = n; a.flags = flags;
-  cudaStream_t s = (cudaStream_t)stream;
-  switch (g_variant) {
-    case 0: env_kernel<MODE_STEP, CfgV0><<<env_grid<CfgV0>(n), CfgV0::threads, CfgV0::cta_smem, s>>>(a); break;
-    case 1: env_kernel<MODE_STEP, CfgV1><<<env_grid<CfgV1>(n), CfgV1::threads, CfgV1::cta_smem, s>>>(a); break;
-    case 2: launch_sorted<SortedA>(a, s); break;
-    case 4: launch_sorted<SortedC>(a, s); break;
-    case 5: launch_sorted<SortedD>(a, s); break;
-    case 6: env_kernel<MODE_STEP, CfgV6><<<env_grid<CfgV6>(n), CfgV6::threads, CfgV6::cta_smem, s>>>(a); break;
-    case 7: env_kernel<MODE_STEP, CfgV7><<<env_grid<CfgV7>(n), CfgV7::threads, CfgV7::cta_smem, s>>>(a); break;
-    case 3: launch_sorted<SortedB>(a, s); break;
-    default: { int prc = launch_partitioned(a, s); if (prc) return prc; } break;
+  a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_cap = sc->cap;
+  cudaError_t e = cudaMemsetAsync(sc->counters, 0, 4 * sizeof(int), s);
+  if (e != cudaSuccess) return cuda_rc(e, "cudaMemsetAsync(step counters)");
+  env_step_main_kernel<<<tile_grid(n, MAIN_WARPS, MAIN_CTAS_PER_SM), MAIN_WARPS * 32, MAIN_CTA_SMEM, s>>>(a);
+  // the list lengths live on the device: launch resident-size grids, idle warps exit at once
+  int ggrid = tile_grid((n + 3) / 4, GATHER_WARPS, GATHER_CTAS_PER_SM);
+  if (ggrid < 1) ggrid = 1;
+  static const bool serial = getenv("BGYM_SERIAL_GATHER") != nullptr;
+  const int gt = GATHER_WARPS * 32;
+  if (sc->streams_ok && !serial) {
+    // the three gather passes touch disjoint envs and are latency-bound: run them concurrently
+    cudaEventRecord(sc->ev_main, s);
+    cudaStreamWaitEvent(sc->side[0], sc->ev_main, 0);
+    env_step_gather_kernel<CAT_PLAY, 0, true><<<ggrid, gt, GATHER_CTA_SMEM, sc->side[0]>>>(a);
+    cudaEventRecord(sc->ev_side[0], sc->side[0]);
+    cudaStreamWaitEvent(sc->side[1], sc->ev_main, 0);
+    env_step_gather_kernel<CAT_OTHER, 2, true><<<ggrid, gt, GATHER_CTA_SMEM, sc->side[1]>>>(a);
+    cudaEventRecord(sc->ev_side[1], sc->side[1]);
+    env_step_gather_kernel<CAT_DISCARD, 1, false><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
+    cudaStreamWaitEvent(s, sc->ev_side[0], 0);
+    cudaStreamWaitEvent(s, sc->ev_side[1], 0);
+  } else {
+    env_step_gather_kernel<CAT_PLAY, 0, true><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
+    env_step_gather_kernel<CAT_DISCARD, 1, false><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
+    env_step_gather_kernel<CAT_OTHER, 2, true><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
   }
   return cuda_rc(cudaGetLastError(), "bgym_step launch");
 }
 
-int bgym_action_mask(const BgymState* state, uint64_t* mask, int64_t n, void* stream) {
-  if (n < 0 || !state || !mask) return set_err(BGYM_E_ARG, "bgym_action_mask: bad arguments");
+int bgym_action_mask(const BgymHot* hot, const BgymCold* cold, uint64_t* mask, int64_t n, void* stream) {
+  if (n < 0 || !hot || !cold || !mask) return set_err(BGYM_E_ARG, "bgym_action_mask: bad arguments");
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
   int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 8 ? (n + 255) / 256 : (long long)g_sm_count * 8);
-  action_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(state), mask, n);
+  action_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(hot),
+                                                             reinterpret_cast<const uint8_t*>(cold), mask, n);
   return cuda_rc(cudaGetLastError(), "bgym_action_mask launch");
 }
 
@@ -746,11 +595,11 @@ int bgym_episode_stats(const double* reward, const uint8_t* terminated, double* 
 // ---- host-buffer handle API ---------------------------------------------------------------------
 struct BgymVec {
   int64_t n; int device; cudaStream_t stream;
-  uint8_t *d_state, *d_obs, *d_term, *d_trunc, *d_decks; double* d_reward; BgymInfo* d_info; int32_t* d_actions;
+  uint8_t *d_hot, *d_cold, *d_obs, *d_term, *d_trunc, *d_decks; double* d_reward; BgymInfo* d_info; int32_t* d_actions;
   uint32_t* d_seeds; BgymDraws* d_draws;
   // pinned staging
-  uint8_t *h_obs, *h_term, *h_trunc, *h_decks; double* h_reward; BgymInfo* h_info; int32_t* h_actions; uint32_t* h_seeds;
-  BgymDraws* h_draws;
+  uint8_t *h_hot, *h_cold, *h_obs, *h_term, *h_trunc, *h_decks; double* h_reward; BgymInfo* h_info; int32_t* h_actions;
+  uint32_t* h_seeds; BgymDraws* h_draws;
 };
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_rc(_e, #x); } while (0)
@@ -765,14 +614,17 @@ int bgym_vec_create(BgymVec** out, int64_t n, int device) {
   memset(v, 0, sizeof *v);
   v->n = n; v->device = device;
   CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
-  CK(cudaMalloc(&v->d_state, n * BGYM_STATE_BYTES)); CK(cudaMalloc(&v->d_obs, n * BGYM_OBS_BYTES));
+  CK(cudaMalloc(&v->d_hot, n * BGYM_HOT_BYTES)); CK(cudaMalloc(&v->d_cold, n * BGYM_COLD_BYTES));
+  CK(cudaMalloc(&v->d_obs, n * BGYM_OBS_BYTES));
   CK(cudaMalloc(&v->d_term, n)); CK(cudaMalloc(&v->d_trunc, n)); CK(cudaMalloc(&v->d_decks, n * 52));
   CK(cudaMalloc(&v->d_reward, n * 8)); CK(cudaMalloc(&v->d_info, n * BGYM_INFO_BYTES)); CK(cudaMalloc(&v->d_actions, n * 4));
   CK(cudaMalloc(&v->d_seeds, n * 4)); CK(cudaMalloc(&v->d_draws, n * BGYM_DRAWS_BYTES));
+  CK(cudaMallocHost(&v->h_hot, n * BGYM_HOT_BYTES)); CK(cudaMallocHost(&v->h_cold, n * BGYM_COLD_BYTES));
   CK(cudaMallocHost(&v->h_obs, n * BGYM_OBS_BYTES)); CK(cudaMallocHost(&v->h_term, n)); CK(cudaMallocHost(&v->h_trunc, n));
   CK(cudaMallocHost(&v->h_decks, n * 52)); CK(cudaMallocHost(&v->h_reward, n * 8)); CK(cudaMallocHost(&v->h_info, n * BGYM_INFO_BYTES));
   CK(cudaMallocHost(&v->h_actions, n * 4)); CK(cudaMallocHost(&v->h_seeds, n * 4)); CK(cudaMallocHost(&v->h_draws, n * BGYM_DRAWS_BYTES));
-  CK(cudaMemsetAsync(v->d_state, 0, n * BGYM_STATE_BYTES, v->stream));
+  CK(cudaMemsetAsync(v->d_hot, 0, n * BGYM_HOT_BYTES, v->stream));
+  CK(cudaMemsetAsync(v->d_cold, 0, n * BGYM_COLD_BYTES, v->stream));
   *out = v;
   return 0;
 }
@@ -781,10 +633,11 @@ int bgym_vec_destroy(BgymVec* v) {
   if (!v) return 0;
   cudaSetDevice(v->device);
   cudaStreamSynchronize(v->stream);
-  cudaFree(v->d_state); cudaFree(v->d_obs); cudaFree(v->d_term); cudaFree(v->d_trunc); cudaFree(v->d_decks);
+  cudaFree(v->d_hot); cudaFree(v->d_cold); cudaFree(v->d_obs); cudaFree(v->d_term); cudaFree(v->d_trunc); cudaFree(v->d_decks);
   cudaFree(v->d_reward); cudaFree(v->d_info); cudaFree(v->d_actions); cudaFree(v->d_seeds); cudaFree(v->d_draws);
-  cudaFreeHost(v->h_obs); cudaFreeHost(v->h_term); cudaFreeHost(v->h_trunc); cudaFreeHost(v->h_decks);
-  cudaFreeHost(v->h_reward); cudaFreeHost(v->h_info); cudaFreeHost(v->h_actions); cudaFreeHost(v->h_seeds); cudaFreeHost(v->h_draws);
+  cudaFreeHost(v->h_hot); cudaFreeHost(v->h_cold); cudaFreeHost(v->h_obs); cudaFreeHost(v->h_term); cudaFreeHost(v->h_trunc);
+  cudaFreeHost(v->h_decks); cudaFreeHost(v->h_reward); cudaFreeHost(v->h_info); cudaFreeHost(v->h_actions);
+  cudaFreeHost(v->h_seeds); cudaFreeHost(v->h_draws);
   cudaStreamDestroy(v->stream);
   delete v;
   return 0;
@@ -799,8 +652,8 @@ int bgym_vec_reset_host(BgymVec* v, const uint32_t* seeds, const uint8_t* decks5
     memcpy(v->h_decks, decks52, v->n * 52);
     CK(cudaMemcpyAsync(v->d_decks, v->h_decks, v->n * 52, cudaMemcpyHostToDevice, v->stream));
   }
-  int rc = bgym_reset(reinterpret_cast<BgymState*>(v->d_state), reinterpret_cast<BgymObs*>(v->d_obs), nullptr, v->d_seeds,
-                      decks52 ? v->d_decks : nullptr, v->n, 0, v->stream);
+  int rc = bgym_reset(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymCold*>(v->d_cold),
+                      reinterpret_cast<BgymObs*>(v->d_obs), nullptr, v->d_seeds, decks52 ? v->d_decks : nullptr, v->n, 0, v->stream);
   if (rc) return rc;
   if (obs_out) CK(cudaMemcpyAsync(v->h_obs, v->d_obs, v->n * BGYM_OBS_BYTES, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaStreamSynchronize(v->stream));
@@ -819,9 +672,9 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
     memcpy(v->h_draws, draws, v->n * BGYM_DRAWS_BYTES);
     CK(cudaMemcpyAsync(v->d_draws, v->h_draws, v->n * BGYM_DRAWS_BYTES, cudaMemcpyHostToDevice, v->stream));
   }
-  int rc = bgym_step(reinterpret_cast<BgymState*>(v->d_state), v->d_actions, draws ? v->d_draws : nullptr,
-                     reinterpret_cast<BgymObs*>(v->d_obs), v->d_reward, v->d_term, v->d_trunc, v->d_info, v->n,
-                     flags & ~BGYM_FLAG_NO_OBS, v->stream);
+  int rc = bgym_step(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymCold*>(v->d_cold), v->d_actions,
+                     draws ? v->d_draws : nullptr, reinterpret_cast<BgymObs*>(v->d_obs), v->d_reward, v->d_term, v->d_trunc,
+                     v->d_info, v->n, flags & ~BGYM_FLAG_NO_OBS, v->stream);
   if (rc) return rc;
   if (obs_out) CK(cudaMemcpyAsync(v->h_obs, v->d_obs, v->n * BGYM_OBS_BYTES, cudaMemcpyDeviceToHost, v->stream));
   if (reward_out) CK(cudaMemcpyAsync(v->h_reward, v->d_reward, v->n * 8, cudaMemcpyDeviceToHost, v->stream));
@@ -837,27 +690,41 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
   return 0;
 }
 
-int bgym_vec_pointers(BgymVec* v, void** state, void** obs, void** reward, void** terminated) {
+int bgym_vec_pointers(BgymVec* v, void** hot, void** cold, void** obs, void** reward, void** terminated) {
   if (!v) return set_err(BGYM_E_ARG, "bgym_vec_pointers: null handle");
-  if (state) *state = v->d_state;
+  if (hot) *hot = v->d_hot;
+  if (cold) *cold = v->d_cold;
   if (obs) *obs = v->d_obs;
   if (reward) *reward = v->d_reward;
   if (terminated) *terminated = v->d_term;
   return 0;
 }
 
+// host-side BgymState records = {hot, cold} back to back
 int bgym_vec_get_state(BgymVec* v, BgymState* host_out) {
   if (!v || !host_out) return set_err(BGYM_E_ARG, "bgym_vec_get_state: bad arguments");
   CK(cudaSetDevice(v->device));
-  CK(cudaMemcpyAsync(host_out, v->d_state, v->n * BGYM_STATE_BYTES, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaMemcpyAsync(v->h_hot, v->d_hot, v->n * BGYM_HOT_BYTES, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaMemcpyAsync(v->h_cold, v->d_cold, v->n * BGYM_COLD_BYTES, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaStreamSynchronize(v->stream));
+  uint8_t* o = reinterpret_cast<uint8_t*>(host_out);
+  for (int64_t i = 0; i < v->n; i++) {
+    memcpy(o + i * BGYM_STATE_BYTES, v->h_hot + i * BGYM_HOT_BYTES, BGYM_HOT_BYTES);
+    memcpy(o + i * BGYM_STATE_BYTES + BGYM_HOT_BYTES, v->h_cold + i * BGYM_COLD_BYTES, BGYM_COLD_BYTES);
+  }
   return 0;
 }
 
 int bgym_vec_set_state(BgymVec* v, const BgymState* host_in) {
   if (!v || !host_in) return set_err(BGYM_E_ARG, "bgym_vec_set_state: bad arguments");
   CK(cudaSetDevice(v->device));
-  CK(cudaMemcpyAsync(v->d_state, host_in, v->n * BGYM_STATE_BYTES, cudaMemcpyHostToDevice, v->stream));
+  const uint8_t* in = reinterpret_cast<const uint8_t*>(host_in);
+  for (int64_t i = 0; i < v->n; i++) {
+    memcpy(v->h_hot + i * BGYM_HOT_BYTES, in + i * BGYM_STATE_BYTES, BGYM_HOT_BYTES);
+    memcpy(v->h_cold + i * BGYM_COLD_BYTES, in + i * BGYM_STATE_BYTES + BGYM_HOT_BYTES, BGYM_COLD_BYTES);
+  }
+  CK(cudaMemcpyAsync(v->d_hot, v->h_hot, v->n * BGYM_HOT_BYTES, cudaMemcpyHostToDevice, v->stream));
+  CK(cudaMemcpyAsync(v->d_cold, v->h_cold, v->n * BGYM_COLD_BYTES, cudaMemcpyHostToDevice, v->stream));
   CK(cudaStreamSynchronize(v->stream));
   return 0;
 }

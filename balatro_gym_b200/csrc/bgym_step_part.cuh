@@ -1,35 +1,36 @@
-// bgym_step_part.cuh — the category-partitioned step (default variant).
+// bgym_step_part.cuh — the category-partitioned step.
 //
-// Measured on B200 (profiles/): with every action category compiled into one kernel the step is
-// bound by instruction fetch (84 KB of SASS walked by 12 warps at different PCs, ~11 of 32 lanes
-// active), while a converged select-only step already runs at ~85 % of the HBM roofline.  So one
-// env-step pass is split by ACTION CATEGORY into kernels whose code is small and whose warps all
-// execute the same path:
+// Why it is split (measured on B200, profiles/r01_ncu_summary.md): with every action category
+// compiled into one kernel the step was bound by instruction fetch (84 KB of SASS walked by 12
+// warps at different PCs, ~11 of 32 lanes active, 18 % of HBM peak), while a converged select-only
+// step already ran at ~85 % of the HBM roofline.  So one env-step is split by ACTION CATEGORY into
+// kernels whose code is small and whose warps all execute the same path:
 //
-//   main pass   (every env)   bulk-stages each warp's tile, fully handles SELECT toggles (~83 % of
-//                             random-legal steps) + masked/guarded actions, and appends the env index
-//                             of every PLAY / DISCARD / OTHER action to one of three device lists
-//                             (warp-aggregated atomics);
-//   gather pass (one per list) each lane pulls ONE listed env's record with its own bulk copy, runs
-//                             the category's path converged, pushes state + observation back.
+//   main pass   (every env)    stages ONLY the hot records of each warp's tile (one bulk copy of
+//                              32 x 144 B), fully handles SELECT toggles (~83 % of random-legal
+//                              steps) and never-legal action ids of envs in PLAY phase, and appends
+//                              the env index of everything else to one of three device lists
+//                              (warp-aggregated atomics).  The cold records are never touched.
+//   gather pass (one per list) each lane pulls ONE listed env's hot + cold record with its own bulk
+//                              copies, runs the category's path converged, pushes hot (+ cold) +
+//                              observation back.  The three passes run concurrently.
 //
-// All four launches are stream ordered; they touch disjoint envs after the main pass, so results do
-// not depend on list order.
+// The launches are stream ordered after the main pass and touch disjoint envs, so results do not
+// depend on list order.
 #pragma once
 #include "bgym_env.cuh"
 
 namespace bgym {
 
+// 0 = handled by the main pass, 1 = PLAY list, 2 = DISCARD list, 3 = OTHER list
 __device__ __forceinline__ int action_category_part(int action) {
   if (action == BGYM_A_PLAY_HAND) return 1;
   if (action == BGYM_A_DISCARD) return 2;
   if (action >= BGYM_A_SELECT_BASE && action < BGYM_A_SELECT_BASE + 8) return 0;
-  // everything else that can be legal in some phase goes to OTHER; ids that are never legal
-  // (out of range, sell-consumable, pack actions) are rejected by the mask in the main pass
   if ((action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) ||
       (action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SELL_JOKER_BASE + 5) ||
       (action >= BGYM_A_SELECT_BLIND_BASE && action <= BGYM_A_SKIP_BLIND)) return 3;
-  return 0;
+  return 0;  // ids that are never legal: rejected by the mask wherever they are handled
 }
 
 __device__ __forceinline__ void write_step_outputs(const StepArgs& a, long long e, double reward, int terminated,
@@ -51,38 +52,50 @@ __device__ __forceinline__ void write_step_outputs(const StepArgs& a, long long 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// main pass: per-warp tiles, one bulk load + two bulk stores per tile (as the unpartitioned kernel)
-// ------------------------------------------------------------------------------------------------
-constexpr int PART_WARPS = 4;
-constexpr int PART_WARP_SMEM = 32 * BGYM_STATE_BYTES + 32 * BGYM_OBS_BYTES;   // 17408
-constexpr int PART_CTA_SMEM = PART_WARPS * PART_WARP_SMEM + 16 * PART_WARPS;
-constexpr int PART_CTAS_PER_SM = 3;
+// uniform legal action of the fused random policy: Philox keyed (seed, policy key), counter = steps
+// taken in the episode
+__device__ __forceinline__ int policy_action(const Hot& h, uint64_t mask) {
+  int cnt = __popcll(mask);
+  if (!cnt) return 0;
+  uint4 w = philox4x32_10(h.ep_len, 0, 0, 0, h.rng_seed, BGYM_POLICY_KEY1);
+  int k = (int)__umulhi(w.x, (uint32_t)cnt);
+#pragma unroll 1
+  for (int i = 0; i < k; i++) mask &= mask - 1;
+  return __ffsll((long long)mask) - 1;
+}
 
-__global__ void __launch_bounds__(PART_WARPS * 32, PART_CTAS_PER_SM) env_step_main_kernel(StepArgs a) {
+// ------------------------------------------------------------------------------------------------
+// main pass: per-warp tiles of 32 hot records, one bulk load + two bulk stores per tile
+// ------------------------------------------------------------------------------------------------
+constexpr int MAIN_WARPS = 4;
+constexpr int MAIN_WARP_SMEM = 32 * BGYM_HOT_BYTES + 32 * BGYM_OBS_BYTES;   // 4608 + 7680
+constexpr int MAIN_CTA_SMEM = MAIN_WARPS * MAIN_WARP_SMEM + 16 * MAIN_WARPS;
+constexpr int MAIN_CTAS_PER_SM = 4;
+
+__global__ void __launch_bounds__(MAIN_WARPS * 32, MAIN_CTAS_PER_SM) env_step_main_kernel(StepArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* st_buf = smem + warp * PART_WARP_SMEM;
-  uint8_t* obs_buf = st_buf + 32 * BGYM_STATE_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + PART_WARPS * PART_WARP_SMEM) + warp * 2;
+  uint8_t* hot_buf = smem + warp * MAIN_WARP_SMEM;
+  uint8_t* obs_buf = hot_buf + 32 * BGYM_HOT_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MAIN_WARPS * MAIN_WARP_SMEM) + warp * 2;
   if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncwarp();
   const long long n_tiles = (a.n + 31) >> 5;
-  const long long warp_gid = (long long)blockIdx.x * PART_WARPS + warp;
-  const long long warp_cnt = (long long)gridDim.x * PART_WARPS;
+  const long long warp_gid = (long long)blockIdx.x * MAIN_WARPS + warp;
+  const long long warp_cnt = (long long)gridDim.x * MAIN_WARPS;
   const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
   const bool fused_policy = (a.flags & BGYM_FLAG_RANDOM_POLICY) != 0;
   uint32_t parity = 0;
   for (long long tile = warp_gid; tile < n_tiles; tile += warp_cnt) {
     const long long e = tile * 32 + lane;
     const bool active = e < a.n;
-    uint8_t* rec = st_buf + lane * BGYM_STATE_BYTES;
+    uint8_t* hot = hot_buf + lane * BGYM_HOT_BYTES;
     uint8_t* obs_s = obs_buf + lane * BGYM_OBS_BYTES;
     if (lane == 0) {
-      bulk_wait_read0();   // previous tile's bulk stores have finished reading shared memory
-      uint32_t bytes = (uint32_t)(min(32LL, a.n - tile * 32) * BGYM_STATE_BYTES);
+      bulk_wait_read0();   // the previous tile's bulk stores have finished reading shared memory
+      uint32_t bytes = (uint32_t)(min(32LL, a.n - tile * 32) * BGYM_HOT_BYTES);
       mbar_arrive_expect_tx(bar, bytes);
-      bulk_g2s(st_buf, a.state + tile * 32 * BGYM_STATE_BYTES, bytes, bar);
+      bulk_g2s(hot_buf, a.hot + tile * 32 * BGYM_HOT_BYTES, bytes, bar);
     }
     int action = 0;
     if (active && !fused_policy) action = __ldg(a.actions + e);
@@ -93,34 +106,32 @@ __global__ void __launch_bounds__(PART_WARPS * 32, PART_CTAS_PER_SM) env_step_ma
     double reward = 0.0;
     int terminated = 0;
     StepInfo info;
-    bool want_reset = false, mine = false;
-    uint32_t new_seed = 0;
+    bool mine = false;
     int cat = 4;
     if (active) {
-      unpack_hot(rec, h);
-      uint64_t m0 = action_mask(h, rec);
+      unpack_hot(hot, h);
+      // the PLAY-phase mask needs the hot record only; other phases are not served here
+      const bool play_phase = h.phase == BGYM_PHASE_PLAY;
+      uint64_t m0 = play_phase ? action_mask(h, nullptr) : 0ull;
       if (fused_policy) {
-        int cnt = __popcll(m0);
-        uint4 w = philox4x32_10(h.ep_len, 0, 0, 0, h.rng_seed, BGYM_POLICY_KEY1);
-        int k = (int)__umulhi(w.x, (uint32_t)cnt);
-        uint64_t mm = m0;
-#pragma unroll 1
-        for (int i = 0; i < k; i++) mm &= mm - 1;
-        action = cnt ? __ffsll((long long)mm) - 1 : 0;
-        if (a.actions_out) a.actions_out[e] = action;
+        if (play_phase) {
+          action = policy_action(h, m0);
+          if (a.actions_out) a.actions_out[e] = action;
+        } else {
+          action = -1;     // the gather pass has the cold record: it samples there
+        }
       }
       cat = action_category_part(action);
+      // guard-terminated envs need a deck rebuild (cold record) -> OTHER list; so does every env
+      // outside PLAY phase (its observation and mask read the shop block)
+      const bool guard = h.ante > 100 || h.chips_scored > 1000000000LL;
+      if (!play_phase || guard) cat = 3;
       mine = cat == 0;
       if (mine) {
-        step_env<CAT_SELECT>(h, rec, action, m0, nullptr, reward, terminated, info);
-        if (terminated && (a.flags & BGYM_FLAG_AUTORESET)) {   // guard termination only
-          uint32_t episode = h.episode + 1;
-          new_seed = next_episode_seed(h.rng_seed);
-          reset_hot(h, new_seed);
-          h.episode = episode;
-          info.flags |= BGYM_F_AUTORESET_DONE;
-          want_reset = true;
-        }
+        step_env<CAT_SELECT>(h, hot, nullptr, action, m0, nullptr, reward, terminated, info);
+        pack_hot(hot, h);
+        if (with_obs) write_obs(h, nullptr, action_mask(h, nullptr), obs_s);
+        write_step_outputs(a, e, reward, terminated, info);
       }
     }
     // defer the other categories: warp-aggregated append to the category's list
@@ -135,19 +146,11 @@ __global__ void __launch_bounds__(PART_WARPS * 32, PART_CTAS_PER_SM) env_step_ma
         if (cat == c) a.part_lists[(long long)(c - 1) * a.part_cap + basei + __popc(bal & ((1u << lane) - 1))] = (int)e;
       }
     }
-    if (a.flags & BGYM_FLAG_AUTORESET) {
-      autoreset_warp(want_reset, new_seed, rec, lane);
-    }
-    if (mine) {
-      pack_hot(rec, h);
-      if (with_obs) write_obs(h, rec, action_mask(h, rec), obs_s);
-      write_step_outputs(a, e, reward, terminated, info);
-    }
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
       uint32_t cnt = (uint32_t)min(32LL, a.n - tile * 32);
-      bulk_s2g(a.state + tile * 32 * BGYM_STATE_BYTES, st_buf, cnt * BGYM_STATE_BYTES);
+      bulk_s2g(a.hot + tile * 32 * BGYM_HOT_BYTES, hot_buf, cnt * BGYM_HOT_BYTES);
       // deferred envs' observation slots hold stale bytes; their gather pass rewrites them afterwards
       if (with_obs) bulk_s2g(a.obs + tile * 32 * BGYM_OBS_BYTES, obs_buf, cnt * BGYM_OBS_BYTES);
       bulk_commit();
@@ -157,36 +160,47 @@ __global__ void __launch_bounds__(PART_WARPS * 32, PART_CTAS_PER_SM) env_step_ma
 }
 
 // ------------------------------------------------------------------------------------------------
-// gather pass: one listed env per lane, per-lane bulk copies
+// gather pass: one listed env per lane, per-lane bulk copies of its hot and cold record
 // ------------------------------------------------------------------------------------------------
-template <int CATS, int LIST>
-__global__ void __launch_bounds__(PART_WARPS * 32, PART_CTAS_PER_SM) env_step_gather_kernel(StepArgs a) {
+constexpr int GATHER_WARPS = 4;
+constexpr int GATHER_WARP_SMEM = 32 * (BGYM_HOT_BYTES + BGYM_COLD_BYTES + BGYM_OBS_BYTES);  // 17920
+constexpr int GATHER_CTA_SMEM = GATHER_WARPS * GATHER_WARP_SMEM + 16 * GATHER_WARPS;
+constexpr int GATHER_CTAS_PER_SM = 3;
+
+template <int CATS, int LIST, bool STORE_COLD>
+__global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_step_gather_kernel(StepArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* st_buf = smem + warp * PART_WARP_SMEM;
-  uint8_t* obs_buf = st_buf + 32 * BGYM_STATE_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + PART_WARPS * PART_WARP_SMEM) + warp * 2;
+  uint8_t* hot_buf = smem + warp * GATHER_WARP_SMEM;
+  uint8_t* cold_buf = hot_buf + 32 * BGYM_HOT_BYTES;
+  uint8_t* obs_buf = cold_buf + 32 * BGYM_COLD_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GATHER_WARPS * GATHER_WARP_SMEM) + warp * 2;
   if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncwarp();
   const int count = a.part_counters[LIST + 1];
   const int* list = a.part_lists + (long long)LIST * a.part_cap;
   const int n_tiles = (count + 31) >> 5;
-  const int warp_gid = blockIdx.x * PART_WARPS + warp;
-  const int warp_cnt = gridDim.x * PART_WARPS;
+  const int warp_gid = blockIdx.x * GATHER_WARPS + warp;
+  const int warp_cnt = gridDim.x * GATHER_WARPS;
   const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
+  const bool fused_policy = (a.flags & BGYM_FLAG_RANDOM_POLICY) != 0;
   uint32_t parity = 0;
   for (int tile = warp_gid; tile < n_tiles; tile += warp_cnt) {
     const int idx = tile * 32 + lane;
     const bool active = idx < count;
     const long long e = active ? (long long)list[idx] : -1;
-    uint8_t* rec = st_buf + lane * BGYM_STATE_BYTES;
+    uint8_t* hot = hot_buf + lane * BGYM_HOT_BYTES;
+    uint8_t* cold = cold_buf + lane * BGYM_COLD_BYTES;
     uint8_t* obs_s = obs_buf + lane * BGYM_OBS_BYTES;
     bulk_wait_read0();    // this lane's bulk stores of the previous tile have read their slots
     __syncwarp();
-    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)min(32, count - tile * 32) * BGYM_STATE_BYTES);
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)min(32, count - tile * 32) * (BGYM_HOT_BYTES + BGYM_COLD_BYTES));
     __syncwarp();
-    if (active) bulk_g2s(rec, a.state + e * BGYM_STATE_BYTES, BGYM_STATE_BYTES, bar);
-    int action = active ? a.actions[e] : 0;   // plain load: the fused policy wrote it in the main pass
+    if (active) {
+      bulk_g2s(hot, a.hot + e * BGYM_HOT_BYTES, BGYM_HOT_BYTES, bar);
+      bulk_g2s(cold, a.cold + e * BGYM_COLD_BYTES, BGYM_COLD_BYTES, bar);
+    }
+    int action = (active && !(fused_policy && LIST == 2)) ? a.actions[e] : 0;
     mbar_wait(bar, parity);
     parity ^= 1;
 
@@ -197,9 +211,17 @@ __global__ void __launch_bounds__(PART_WARPS * 32, PART_CTAS_PER_SM) env_step_ga
     bool want_reset = false;
     uint32_t new_seed = 0;
     if (active) {
-      unpack_hot(rec, h);
-      uint64_t m0 = action_mask(h, rec);
-      step_env<CATS>(h, rec, action, m0, a.draws ? a.draws + e : nullptr, reward, terminated, info);
+      unpack_hot(hot, h);
+      uint64_t m0 = action_mask(h, cold);
+      if (fused_policy && LIST == 2) {
+        // envs outside PLAY phase (and guard-terminated ones) sample here, where the mask is complete;
+        // PLAY-phase envs already carry the action the main pass sampled
+        if (h.phase == BGYM_PHASE_PLAY) action = a.actions[e];
+        else { action = policy_action(h, m0); if (a.actions_out) a.actions_out[e] = action; }
+      }
+      // the OTHER list also receives SELECT / never-legal ids of envs the main pass does not serve
+      step_env<(LIST == 2) ? (CAT_OTHER | CAT_SELECT) : CATS>(h, hot, cold, action, m0, a.draws ? a.draws + e : nullptr,
+                                                            reward, terminated, info);
       if (terminated && (a.flags & BGYM_FLAG_AUTORESET)) {
         uint32_t episode = h.episode + 1;
         new_seed = next_episode_seed(h.rng_seed);
@@ -209,18 +231,17 @@ __global__ void __launch_bounds__(PART_WARPS * 32, PART_CTAS_PER_SM) env_step_ga
         want_reset = true;
       }
     }
-    if (a.flags & BGYM_FLAG_AUTORESET) {
-      autoreset_warp(want_reset, new_seed, rec, lane);
-    }
+    if (a.flags & BGYM_FLAG_AUTORESET) autoreset_warp(want_reset, new_seed, cold, lane);
     if (active) {
-      pack_hot(rec, h);
-      if (with_obs) write_obs(h, rec, action_mask(h, rec), obs_s);
+      pack_hot(hot, h);
+      if (with_obs) write_obs(h, cold, action_mask(h, cold), obs_s);
       write_step_outputs(a, e, reward, terminated, info);
     }
     fence_async_smem();   // every lane: a cooperative reset writes other lanes' slots
     __syncwarp();
     if (active) {
-      bulk_s2g(a.state + e * BGYM_STATE_BYTES, rec, BGYM_STATE_BYTES);
+      bulk_s2g(a.hot + e * BGYM_HOT_BYTES, hot, BGYM_HOT_BYTES);
+      if (STORE_COLD || want_reset) bulk_s2g(a.cold + e * BGYM_COLD_BYTES, cold, BGYM_COLD_BYTES);
       if (with_obs) bulk_s2g(a.obs + e * BGYM_OBS_BYTES, obs_s, BGYM_OBS_BYTES);
       bulk_commit();
     }

@@ -8,7 +8,9 @@ from __future__ import annotations
 
 import numpy as np
 
-STATE_BYTES = 304
+STATE_BYTES = 320
+HOT_BYTES = 144
+COLD_BYTES = 176
 OBS_BYTES = 240
 INFO_BYTES = 32
 DRAWS_BYTES = 256
@@ -34,27 +36,35 @@ def _dt(fields, size):
                      "itemsize": size})
 
 
-STATE_DTYPE = _dt([
-    ("hand", "(8,)u1", 0),
-    ("hand_n", "u1", 8), ("hand_size", "u1", 9), ("sel_n", "u1", 10), ("highlight_mask", "u1", 11),
-    ("sel_order", "<u4", 12),
-    ("face_down_mask", "u1", 16), ("phase", "u1", 17), ("round", "u1", 18), ("boss_type", "u1", 19),
-    ("hands_left", "u1", 20), ("discards_left", "u1", 21), ("joker_n", "u1", 22), ("cons_n", "u1", 23),
-    ("joker_slots", "u1", 24), ("cons_slots", "u1", 25), ("n_magic_trick", "u1", 26), ("n_minimalist", "u1", 27),
-    ("ante", "<i2", 28), ("jokers_sold", "<i2", 30),
-    ("money", "<i4", 32), ("chips_needed", "<i4", 36),
-    ("round_chips", "<i8", 40), ("chips_scored", "<i8", 48),
-    ("best_hand", "<i4", 56), ("hands_played_total", "<i4", 60),
-    ("hands_played_ante", "<i2", 64), ("boss_flags", "u1", 66), ("boss_cards_required", "u1", 67),
-    ("boss_played_types", "<u2", 68), ("boss_hands_played", "u1", 70), ("deck_n", "u1", 71),
-    ("boss_played_cards", "<u8", 72),
-    ("joker_id", "(8,)u1", 80), ("cons_id", "(8,)u1", 88), ("hand_level", "(12,)u1", 96),
-    ("shop_reroll_state", "<i4", 108), ("rng_seed", "<u4", 112), ("rng_ctr", "<u4", 116),
-    ("ep_len", "<u4", 120), ("episode", "<u4", 124),
-    ("deck", "(52,)<u2", 128), ("hand_play_count", "(12,)u1", 232),
-    ("item_type", "(9,)u1", 244), ("item_id", "(9,)u1", 253), ("n_items", "u1", 262),
-    ("item_cost", "(9,)<i4", 264), ("reroll_cost", "<i4", 300),
-], STATE_BYTES)
+_HOT_FIELDS = [
+    ("hand", "(8,)u1", 0), ("hand_code", "(8,)u1", 8),
+    ("hand_n", "u1", 16), ("hand_size", "u1", 17), ("sel_n", "u1", 18), ("highlight_mask", "u1", 19),
+    ("sel_order", "<u4", 20),
+    ("face_down_mask", "u1", 24), ("phase", "u1", 25), ("round", "u1", 26), ("boss_type", "u1", 27),
+    ("hands_left", "u1", 28), ("discards_left", "u1", 29), ("joker_n", "u1", 30), ("cons_n", "u1", 31),
+    ("joker_slots", "u1", 32), ("cons_slots", "u1", 33), ("n_magic_trick", "u1", 34), ("n_minimalist", "u1", 35),
+    ("ante", "<i2", 36), ("jokers_sold", "<i2", 38),
+    ("money", "<i4", 40), ("chips_needed", "<i4", 44),
+    ("round_chips", "<i8", 48), ("chips_scored", "<i8", 56),
+    ("best_hand", "<i4", 64), ("hands_played_total", "<i4", 68),
+    ("hands_played_ante", "<i2", 72), ("boss_flags", "u1", 74), ("boss_cards_required", "u1", 75),
+    ("boss_played_types", "<u2", 76), ("boss_hands_played", "u1", 78), ("deck_n", "u1", 79),
+    ("boss_played_cards", "<u8", 80),
+    ("joker_id", "(8,)u1", 88), ("cons_id", "(8,)u1", 96), ("hand_level", "(12,)u1", 104),
+    ("shop_reroll_state", "<i4", 116), ("rng_seed", "<u4", 120), ("rng_ctr", "<u4", 124),
+    ("ep_len", "<u4", 128), ("episode", "<u4", 132),
+]
+_COLD_FIELDS = [
+    ("deck", "(52,)<u2", 0), ("hand_play_count", "(12,)u1", 104),
+    ("item_type", "(9,)u1", 116), ("item_id", "(9,)u1", 125), ("n_items", "u1", 134),
+    ("item_cost", "(9,)<i4", 136), ("reroll_cost", "<i4", 172),
+]
+HOT_DTYPE = _dt(_HOT_FIELDS, HOT_BYTES)
+COLD_DTYPE = _dt(_COLD_FIELDS, COLD_BYTES)
+# host-side combined record {hot, cold} back to back (checkpoints and tests)
+STATE_DTYPE = _dt(_HOT_FIELDS + [(n, f, o + HOT_BYTES) for n, f, o in _COLD_FIELDS], STATE_BYTES)
+HOT_FIELD_NAMES = [f[0] for f in _HOT_FIELDS]
+COLD_FIELD_NAMES = [f[0] for f in _COLD_FIELDS]
 
 OBS_DTYPE = _dt([
     ("hand", "(8,)i1", 0), ("selected_cards", "(8,)i1", 8), ("face_down_cards", "(8,)i1", 16),

@@ -72,7 +72,9 @@ class BalatroVecEnv:
         self.env_offset = int(env_offset)
         n, dev = self.num_envs, self.device
         with torch.cuda.device(dev):
-            self.state = torch.zeros((n, L.STATE_BYTES), dtype=torch.uint8, device=dev)
+            # env state = two dense record arrays (include/bgym.h): hot (144 B) and cold (176 B)
+            self.hot = torch.zeros((n, L.HOT_BYTES), dtype=torch.uint8, device=dev)
+            self.cold = torch.zeros((n, L.COLD_BYTES), dtype=torch.uint8, device=dev)
             self.obs_buf = torch.zeros((n, L.OBS_BYTES), dtype=torch.uint8, device=dev)
             self.info_buf = torch.zeros((n, L.INFO_BYTES), dtype=torch.uint8, device=dev)
             self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -115,7 +117,10 @@ class BalatroVecEnv:
         return _field_view(self.torch, self.info_buf, L.INFO_DTYPE, name)
 
     def state_field(self, name):
-        return _field_view(self.torch, self.state, L.STATE_DTYPE, name)
+        """Zero-copy typed view of one state field (from the hot or the cold record array)."""
+        if name in L.HOT_FIELD_NAMES:
+            return _field_view(self.torch, self.hot, L.HOT_DTYPE, name)
+        return _field_view(self.torch, self.cold, L.COLD_DTYPE, name)
 
     # -- reset -------------------------------------------------------------------------------------
     def reset(self, seeds=None, decks52=None, reset_mask=None):
@@ -137,7 +142,7 @@ class BalatroVecEnv:
         if reset_mask is not None:
             reset_mask = torch.as_tensor(reset_mask, device=self.device).to(torch.uint8).contiguous()
         with torch.cuda.device(self.device):
-            rc = self.lib.bgym_reset(self.state.data_ptr(), self.obs_buf.data_ptr(), self._ptr(reset_mask),
+            rc = self.lib.bgym_reset(self.hot.data_ptr(), self.cold.data_ptr(), self.obs_buf.data_ptr(), self._ptr(reset_mask),
                                      seeds32.data_ptr(), self._ptr(decks52), self.num_envs, 0, self._stream())
         _lib.check(rc, "bgym_reset")
         self._keep = (seeds32, decks52, reset_mask)  # keep inputs alive until the stream has consumed them
@@ -165,7 +170,7 @@ class BalatroVecEnv:
             draws = torch.as_tensor(draws, device=self.device).contiguous()
             assert draws.dtype == torch.uint8 and draws.shape == (self.num_envs, L.DRAWS_BYTES)
         with torch.cuda.device(self.device):
-            rc = self.lib.bgym_step(self.state.data_ptr(), act.data_ptr(), self._ptr(draws), self.obs_buf.data_ptr(),
+            rc = self.lib.bgym_step(self.hot.data_ptr(), self.cold.data_ptr(), act.data_ptr(), self._ptr(draws), self.obs_buf.data_ptr(),
                                     self.reward.data_ptr(), self.terminated.data_ptr(), self.truncated.data_ptr(),
                                     self.info_buf.data_ptr() if want_info else None, self.num_envs, flags, self._stream())
         _lib.check(rc, "bgym_step")
@@ -194,7 +199,7 @@ class BalatroVecEnv:
     def action_masks(self):
         """uint64 mask word per env computed from the state (bit a = action a legal), as int64."""
         with self.torch.cuda.device(self.device):
-            rc = self.lib.bgym_action_mask(self.state.data_ptr(), self._mask64.data_ptr(), self.num_envs, self._stream())
+            rc = self.lib.bgym_action_mask(self.hot.data_ptr(), self.cold.data_ptr(), self._mask64.data_ptr(), self.num_envs, self._stream())
         _lib.check(rc, "bgym_action_mask")
         return self._mask64
 
@@ -208,11 +213,12 @@ class BalatroVecEnv:
 
     # -- checkpoint (save_state / load_state, balatro_env_2.py:1575-1615) ----------------------------
     def save_state(self):
-        return {"state": self.state.clone(), "step_count": self._step_count,
+        return {"hot": self.hot.clone(), "cold": self.cold.clone(), "step_count": self._step_count,
                 "ret_acc": self._ret_acc.clone(), "len_acc": self._len_acc.clone()}
 
     def load_state(self, ckpt):
-        self.state.copy_(ckpt["state"])
+        self.hot.copy_(ckpt["hot"])
+        self.cold.copy_(ckpt["cold"])
         self._step_count = ckpt["step_count"]
         self._ret_acc.copy_(ckpt["ret_acc"])
         self._len_acc.copy_(ckpt["len_acc"])
@@ -221,11 +227,14 @@ class BalatroVecEnv:
     def inject_numpy(self, state_np: np.ndarray):
         """Overwrite all state records from a host array of L.STATE_DTYPE."""
         assert state_np.dtype == L.STATE_DTYPE and state_np.shape == (self.num_envs,)
-        t = self.torch.from_numpy(state_np.view(np.uint8).reshape(self.num_envs, L.STATE_BYTES).copy())
-        self.state.copy_(t)
+        raw = state_np.view(np.uint8).reshape(self.num_envs, L.STATE_BYTES)
+        self.hot.copy_(self.torch.from_numpy(np.ascontiguousarray(raw[:, :L.HOT_BYTES])))
+        self.cold.copy_(self.torch.from_numpy(np.ascontiguousarray(raw[:, L.HOT_BYTES:])))
 
     def state_numpy(self) -> np.ndarray:
-        return self.state.cpu().numpy().reshape(-1).view(L.STATE_DTYPE).copy()
+        """Host copy of all envs as combined {hot, cold} records (L.STATE_DTYPE)."""
+        raw = np.concatenate([self.hot.cpu().numpy(), self.cold.cpu().numpy()], axis=1)
+        return np.ascontiguousarray(raw).reshape(-1).view(L.STATE_DTYPE).copy()
 
     def obs_numpy(self) -> np.ndarray:
         return self.obs_buf.cpu().numpy().reshape(-1).view(L.OBS_DTYPE).copy()
@@ -244,15 +253,15 @@ class BalatroVecEnv:
         # 5 distinct jokers out of ids 1..145: top-5 of random keys
         keys = torch.rand((n, 145), device=dev, generator=g)
         jk = (keys.topk(5, dim=1).indices + 1).to(torch.uint8)
-        self.state[:, 80:85] = jk
-        self.state[:, 22] = 5
+        self.state_field("joker_id")[:, :5] = jk
+        self.state_field("joker_n")[:] = 5
         enh = torch.where(torch.rand((n, 52), device=dev, generator=g) < 0.25,
                           torch.randint(1, 9, (n, 52), device=dev, generator=g), torch.zeros((n, 52), dtype=torch.int64, device=dev))
         ed = torch.where(torch.rand((n, 52), device=dev, generator=g) < 0.1,
                          torch.randint(1, 4, (n, 52), device=dev, generator=g), torch.zeros((n, 52), dtype=torch.int64, device=dev))
         seal = torch.where(torch.rand((n, 52), device=dev, generator=g) < 0.1,
                            torch.randint(1, 5, (n, 52), device=dev, generator=g), torch.zeros((n, 52), dtype=torch.int64, device=dev))
-        deck = self.state[:, 128:232].view(torch.int16).to(torch.int64) & 63
+        deck_view = self.state_field("deck")                     # int16 view of the 52 card16 entries
+        deck = deck_view.to(torch.int64) & 63
         deck = deck | (enh << 6) | (ed << 10) | (seal << 13)
-        deck = torch.where(deck >= 2 ** 15, deck - 2 ** 16, deck).to(torch.int16)
-        self.state[:, 128:232] = deck.view(torch.uint8)
+        deck_view.copy_(torch.where(deck >= 2 ** 15, deck - 2 ** 16, deck).to(torch.int16))

@@ -36,7 +36,9 @@ extern "C" {
 #define BGYM_ABI_VERSION 1
 
 /* ---- sizes ------------------------------------------------------------- */
-#define BGYM_STATE_BYTES 304
+#define BGYM_STATE_BYTES 320
+#define BGYM_HOT_BYTES   144
+#define BGYM_COLD_BYTES  176
 #define BGYM_OBS_BYTES   240
 #define BGYM_INFO_BYTES  32
 #define BGYM_DRAWS_BYTES 256
@@ -118,67 +120,62 @@ enum {
 #define BGYM_E_NODEV   (-2)
 #define BGYM_E_ALIGN   (-3)
 
-/* ---- per-env state record (304 B = 19 x 16 B, 16-byte aligned) --------------
+/* ---- per-env state (320 B) = hot record (144 B) + cold record (176 B) ----------
  * Restates UnifiedGameState (balatro_env_2.py:166-211) + BalatroGame (balatro_game.py:16-28)
  * + ScoreEngine levels/counts (scoring_engine.py:65-69) + BossBlindManager.blind_state
- * (boss_blinds.py:311-319) + Shop inventory (shop.py:96-148).  SURVEY.md Appendix D counts the
- * same information as 320 B; the physical record is 304 B so that a tile of records staged in
- * shared memory has an odd 16-byte stride (bank-conflict-free 128-bit access per lane). */
-typedef struct BgymState {
-  /* hot block, bytes 0..127 */
-  uint8_t  hand[8];            /*   0 hand_indexes: deck index per hand slot, 0xFF = empty          */
-  uint8_t  hand_n;             /*   8 len(hand_indexes)                                             */
-  uint8_t  hand_size;          /*   9 state.hand_size / game.hand_size                              */
-  uint8_t  sel_n;              /*  10 len(selected_cards)                                           */
-  uint8_t  highlight_mask;     /*  11 game.highlighted_indexes as a bit set over hand slots         */
-  uint32_t sel_order;          /*  12 selected_cards, ordered: nibble k = slot of k-th selection    */
-  uint8_t  face_down_mask;     /*  16 face_down_cards as a bit set over hand slots                  */
-  uint8_t  phase;              /*  17                                                               */
-  uint8_t  round;              /*  18 1 small, 2 big, 3 boss                                        */
-  uint8_t  boss_type;          /*  19 active BossBlindType (boss_blinds.py:18-47), 0 = none         */
-  uint8_t  hands_left;         /*  20                                                               */
-  uint8_t  discards_left;      /*  21                                                               */
-  uint8_t  joker_n;            /*  22                                                               */
-  uint8_t  cons_n;             /*  23                                                               */
-  uint8_t  joker_slots;        /*  24                                                               */
-  uint8_t  cons_slots;         /*  25                                                               */
-  uint8_t  n_magic_trick;      /*  26 vouchers.count('Magic Trick')                                 */
-  uint8_t  n_minimalist;       /*  27 vouchers.count('Minimalist')                                  */
-  int16_t  ante;               /*  28                                                               */
-  int16_t  jokers_sold;        /*  30                                                               */
-  int32_t  money;              /*  32                                                               */
-  int32_t  chips_needed;       /*  36                                                               */
-  int64_t  round_chips;        /*  40 round_chips_scored                                            */
-  int64_t  chips_scored;       /*  48                                                               */
-  int32_t  best_hand;          /*  56 best_hand_this_ante (saturating)                              */
-  int32_t  hands_played_total; /*  60                                                               */
-  int16_t  hands_played_ante;  /*  64                                                               */
-  uint8_t  boss_flags;         /*  66 bit0 = blind_state['first_hand']                              */
-  uint8_t  boss_cards_required;/*  67 blind_state['cards_required'] (The Verdant)                   */
-  uint16_t boss_played_types;  /*  68 blind_state['played_hand_types'] as a bit set over HandType   */
-  uint8_t  boss_hands_played;  /*  70 blind_state['hands_played']                                   */
-  uint8_t  deck_n;             /*  71 len(deck)                                                     */
-  uint64_t boss_played_cards;  /*  72 blind_state['played_cards'] as a bit set over deck indices    */
-  uint8_t  joker_id[8];        /*  80 JOKER_LIBRARY ids (jokers.py:11-162), 0 = empty               */
-  uint8_t  cons_id[8];         /*  88 consumable ids, 0 = empty                                     */
-  uint8_t  hand_level[12];     /*  96 state.hand_levels (uncapped); engine level = min(level, 15)   */
-  int32_t  shop_reroll_state;  /* 108 state.shop_reroll_cost (stale copy used by the mask)          */
-  uint32_t rng_seed;           /* 112 native mode: Philox key word 0                                */
-  uint32_t rng_ctr;            /* 116 native mode: Philox counter (blocks consumed)                 */
-  uint32_t ep_len;             /* 120 valid steps taken in the current episode                      */
-  uint32_t episode;            /* 124 episodes finished by in-kernel autoreset                      */
-  /* deck block, bytes 128..243 */
-  uint16_t deck[52];           /* 128 card16 per deck index                                         */
-  uint8_t  hand_play_count[12];/* 232 engine.hand_play_counts, saturating at 255 (never read by the
-                                      reference's step path; kept for save_state)                   */
-  /* shop block, bytes 244..303 */
-  uint8_t  item_type[9];       /* 244 shop.inventory[i].item_type                                   */
-  uint8_t  item_id[9];         /* 253 joker id / pack kind / voucher kind / card int                */
-  uint8_t  n_items;            /* 262                                                               */
-  uint8_t  _pad0;              /* 263                                                               */
-  int32_t  item_cost[9];       /* 264                                                               */
-  int32_t  reroll_cost;        /* 300 shop.reroll_cost (grows x1.35 per reroll)                     */
-} BgymState;
+ * (boss_blinds.py:311-319) + Shop inventory (shop.py:96-148).  SURVEY.md Appendix D.
+ *
+ * ON THE DEVICE the two halves live in two dense arrays, hot[n] (BgymHot, 144 B = 9 x 16) and
+ * cold[n] (BgymCold, 176 B = 11 x 16): card-select toggles (~83 % of steps) touch only the hot
+ * array, and both strides are odd multiples of 16 B so a tile staged in shared memory is
+ * bank-conflict free for 128-bit per-lane access.  BgymState = {hot, cold} back to back is the
+ * HOST-side record (checkpoints, bgym_vec_get_state/set_state, the test oracle). */
+/* hot record, 144 B (offset: field)
+ *   0 hand[8]             hand_indexes: deck index per hand slot, 0xFF = empty
+ *   8 hand_code[8]        cache: card code of deck[hand[i]], 0xFF = none (obs['hand'])
+ *  16 hand_n, 17 hand_size, 18 sel_n, 19 highlight_mask (game.highlighted_indexes as a slot bit set)
+ *  20 sel_order           selected_cards, ordered: nibble k = slot of the k-th selection
+ *  24 face_down_mask, 25 phase, 26 round (1 small 2 big 3 boss), 27 boss_type (BossBlindType, 0 none)
+ *  28 hands_left, 29 discards_left, 30 joker_n, 31 cons_n
+ *  32 joker_slots, 33 cons_slots, 34 n_magic_trick, 35 n_minimalist (voucher counts)
+ *  36 ante i16, 38 jokers_sold i16, 40 money i32, 44 chips_needed i32
+ *  48 round_chips i64 (round_chips_scored), 56 chips_scored i64
+ *  64 best_hand i32 (best_hand_this_ante, saturating), 68 hands_played_total i32
+ *  72 hands_played_ante i16, 74 boss_flags (bit0 = blind_state['first_hand']),
+ *  75 boss_cards_required (Verdant), 76 boss_played_types u16 (bit set over HandType),
+ *  78 boss_hands_played, 79 deck_n (len(deck)), 80 boss_played_cards u64 (bit set over deck indices)
+ *  88 joker_id[8] (JOKER_LIBRARY ids, 0 empty), 96 cons_id[8] (consumable ids, 0 empty)
+ * 104 hand_level[12]      state.hand_levels (uncapped); engine level = min(level, 15)
+ * 116 shop_reroll_state   state.shop_reroll_cost (stale copy used by the mask)
+ * 120 rng_seed, 124 rng_ctr (native Philox key word / block counter)
+ * 128 ep_len (valid steps this episode), 132 episode (in-kernel autoresets so far), 136 pad[8] */
+#define BGYM_HOT_FIELDS \
+  uint8_t hand[8]; uint8_t hand_code[8]; \
+  uint8_t hand_n; uint8_t hand_size; uint8_t sel_n; uint8_t highlight_mask; uint32_t sel_order; \
+  uint8_t face_down_mask; uint8_t phase; uint8_t round; uint8_t boss_type; \
+  uint8_t hands_left; uint8_t discards_left; uint8_t joker_n; uint8_t cons_n; \
+  uint8_t joker_slots; uint8_t cons_slots; uint8_t n_magic_trick; uint8_t n_minimalist; \
+  int16_t ante; int16_t jokers_sold; int32_t money; int32_t chips_needed; \
+  int64_t round_chips; int64_t chips_scored; int32_t best_hand; int32_t hands_played_total; \
+  int16_t hands_played_ante; uint8_t boss_flags; uint8_t boss_cards_required; \
+  uint16_t boss_played_types; uint8_t boss_hands_played; uint8_t deck_n; uint64_t boss_played_cards; \
+  uint8_t joker_id[8]; uint8_t cons_id[8]; uint8_t hand_level[12]; int32_t shop_reroll_state; \
+  uint32_t rng_seed; uint32_t rng_ctr; uint32_t ep_len; uint32_t episode; uint8_t _hot_pad[8];
+
+/* cold record, 176 B (offset: field)
+ *   0 deck[52] u16        card16 per deck index
+ * 104 hand_play_count[12] engine.hand_play_counts, saturating at 255 (never read by the reference's
+ *                         step path; kept for save_state)
+ * 116 item_type[9], 125 item_id[9] (joker id / pack kind / voucher kind / card int), 134 n_items
+ * 136 item_cost[9] i32, 172 reroll_cost i32 (shop.reroll_cost, grows x1.35 per reroll) */
+#define BGYM_COLD_FIELDS \
+  uint16_t deck[52]; uint8_t hand_play_count[12]; \
+  uint8_t item_type[9]; uint8_t item_id[9]; uint8_t n_items; uint8_t _pad0; \
+  int32_t item_cost[9]; int32_t reroll_cost;
+
+typedef struct BgymHot { BGYM_HOT_FIELDS } BgymHot;
+typedef struct BgymCold { BGYM_COLD_FIELDS } BgymCold;
+typedef struct BgymState { BGYM_HOT_FIELDS BGYM_COLD_FIELDS } BgymState;
 
 /* ---- observation record (240 B) ---------------------------------------------
  * The 31 keys the reference actually emits (balatro_env_2.py:1488-1531), same dtypes
@@ -269,18 +266,18 @@ int bgym_device_count(void);
  * (balatro_env_2.py:505-558).  seeds[i] keys the native Philox stream.  decks52 != NULL
  * (n x 52 card codes) replays a supplied permutation (the reference's shuffle stream);
  * NULL = native Fisher-Yates from Philox.  obs may be NULL with BGYM_FLAG_NO_OBS. */
-int bgym_reset(BgymState* state, BgymObs* obs, const uint8_t* reset_mask, const uint32_t* seeds,
+int bgym_reset(BgymHot* hot, BgymCold* cold, BgymObs* obs, const uint8_t* reset_mask, const uint32_t* seeds,
                const uint8_t* decks52, int64_t n, int flags, void* stream);
 
 /* step: one BalatroEnv.step per env (balatro_env_2.py:616-1064, 1174-1392).
  * draws == NULL -> native Philox mode.  info may be NULL. truncated is always 0.
  * `actions` is read (written instead with BGYM_FLAG_RANDOM_POLICY). */
-int bgym_step(BgymState* state, int32_t* actions, const BgymDraws* draws, BgymObs* obs,
+int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* draws, BgymObs* obs,
               double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
               int64_t n, int flags, void* stream);
 
 /* action mask as one 64-bit word per env (balatro_env_2.py:1426-1471) */
-int bgym_action_mask(const BgymState* state, uint64_t* mask, int64_t n, void* stream);
+int bgym_action_mask(const BgymHot* hot, const BgymCold* cold, uint64_t* mask, int64_t n, void* stream);
 
 /* uniform random legal action per env from BgymObs.action_mask_bits (the policy the
  * reference benchmarks are driven with: random legal actions from obs['action_mask']) */
@@ -318,7 +315,7 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
                        double* reward_out, uint8_t* terminated_out, uint8_t* truncated_out,
                        BgymInfo* info_out, int flags);
 /* raw device pointers of the handle (for zero-copy consumers) */
-int bgym_vec_pointers(BgymVec* v, void** state, void** obs, void** reward, void** terminated);
+int bgym_vec_pointers(BgymVec* v, void** hot, void** cold, void** obs, void** reward, void** terminated);
 /* copy state records to / from host (checkpointing: save_state/load_state,
  * balatro_env_2.py:1575-1615) */
 int bgym_vec_get_state(BgymVec* v, BgymState* host_out);

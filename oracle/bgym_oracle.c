@@ -416,9 +416,12 @@ int oracle_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8
 /* ------------------------------------------------------------------------------------------
  * env: list helpers over the hand
  * ---------------------------------------------------------------------------------------- */
+/* hand_code[i] = card code shown by obs['hand'][i] (cache kept in the hot record), 0xFF = -1 */
 static void refresh_hand_codes(BgymState* s) {
   for (int i = 0; i < 8; i++) {
     if (i >= s->hand_n) s->hand[i] = 0xFF;
+    if (i < s->hand_n && s->hand[i] < s->deck_n) s->hand_code[i] = (uint8_t)c16_code(s->deck[s->hand[i]]);
+    else s->hand_code[i] = 0xFF;
   }
 }
 
@@ -552,6 +555,7 @@ static void reset_env(BgymState* s, uint32_t seed, const uint8_t* deck52) {
   for (int i = 0; i < 12; i++) s->hand_level[i] = 1;
   s->deck_n = 52;
   memset(s->hand, 0xFF, 8);
+  memset(s->hand_code, 0xFF, 8);
   s->rng_seed = seed; s->rng_ctr = 0;
   if (deck52) {
     for (int i = 0; i < 52; i++) s->deck[i] = deck52[i];

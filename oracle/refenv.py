@@ -277,8 +277,11 @@ class RefEnv:
         hand = list(st.hand_indexes)
         assert len(hand) <= 8
         s["hand"][:] = 0xFF
+        s["hand_code"][:] = 0xFF
         for i, idx in enumerate(hand):
             s["hand"][i] = idx
+            if idx < len(deck):
+                s["hand_code"][i] = card_code(deck[idx])
         s["hand_n"] = len(hand)
         s["hand_size"] = st.hand_size
         sel = list(st.selected_cards)

@@ -25,9 +25,9 @@ def test_library_exports_all_declared_symbols():
 
 def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
-    assert lib.bgym_step(None, None, None, None, None, None, None, None, 4, 0, None) < 0
+    assert lib.bgym_step(None, None, None, None, None, None, None, None, None, 4, 0, None) < 0
     assert b"bgym_step" in lib.bgym_last_error()
-    assert lib.bgym_reset(None, None, None, None, None, 4, 0, None) < 0
+    assert lib.bgym_reset(None, None, None, None, None, None, 4, 0, None) < 0
 
 
 def _c_offsets(struct, fields):
@@ -46,13 +46,16 @@ def _c_offsets(struct, fields):
 
 
 def test_struct_layouts_match_numpy_dtypes():
-    for struct, dt in (("BgymState", L.STATE_DTYPE), ("BgymObs", L.OBS_DTYPE), ("BgymInfo", L.INFO_DTYPE),
+    for struct, dt in (("BgymState", L.STATE_DTYPE), ("BgymHot", L.HOT_DTYPE), ("BgymCold", L.COLD_DTYPE),
+                       ("BgymObs", L.OBS_DTYPE), ("BgymInfo", L.INFO_DTYPE),
                        ("BgymDraws", L.DRAWS_DTYPE), ("BgymScoreCtx", L.SCORE_CTX_DTYPE)):
         size, offs = _c_offsets(struct, dt.names)
         assert size == dt.itemsize, struct
         assert offs == [dt.fields[n][1] for n in dt.names], struct
-    assert L.STATE_DTYPE.itemsize == 304 and L.STATE_DTYPE.itemsize % 32 == 16  # odd multiple of 16 B
-    assert L.OBS_DTYPE.itemsize == 240
+    # device record strides are odd multiples of 16 B (bank-conflict-free 128-bit access per lane)
+    for dt, size in ((L.HOT_DTYPE, 144), (L.COLD_DTYPE, 176), (L.OBS_DTYPE, 240)):
+        assert dt.itemsize == size and dt.itemsize % 32 == 16
+    assert L.STATE_DTYPE.itemsize == 320 == L.HOT_BYTES + L.COLD_BYTES
 
 
 def test_product_never_imports_the_oracle():

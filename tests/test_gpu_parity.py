@@ -260,7 +260,7 @@ def test_native_shuffle_is_uniform(torch):
     n = 1 << 17
     v = BalatroVecEnv(n, seed=12345, autoreset=False)
     v.reset()
-    deck = (v.state[:, 128:232].view(torch.int16) & 63).long()
+    deck = (v.state_field("deck") & 63).long()
     assert bool((deck.sort(dim=1).values == torch.arange(52, device="cuda")).all())     # every deck is a permutation
     # position x card contingency table: chi-square against uniform, 51*51 dof
     table = torch.zeros((52, 52), dtype=torch.float64, device="cuda")
@@ -273,7 +273,7 @@ def test_native_shuffle_is_uniform(torch):
     # different seeds give different decks; same seed reproduces
     v2 = BalatroVecEnv(n, seed=12345, autoreset=False)
     v2.reset()
-    assert bool((v2.state == v.state).all())
+    assert bool((v2.hot == v.hot).all()) and bool((v2.cold == v.cold).all())
     assert int((deck[1:] == deck[:-1]).all(dim=1).sum()) == 0
 
 
@@ -288,11 +288,16 @@ def test_full_size_rollout_properties(torch):
     for t in range(96):
         v.step(random_policy=True, want_info=False)
     torch.cuda.synchronize()
-    st = v.state
-    hand_n = st[:, 8].long(); phase = st[:, 17].long(); deck = (st[:, 128:232].view(torch.int16) & 63).long()
+    hand_n = v.state_field("hand_n").long(); phase = v.state_field("phase").long()
+    deck = (v.state_field("deck") & 63).long()
     assert bool((deck.sort(dim=1).values == torch.arange(52, device="cuda")).all())
     assert bool((hand_n <= 8).all()) and bool((phase <= 2).all())
-    hand = st[:, 0:8].long()
+    hand = v.state_field("hand").long()
+    # the hand_code cache of the hot record agrees with deck[hand[i]]
+    codes = v.state_field("hand_code").long()
+    look = torch.gather(deck, 1, hand.clamp(max=51))
+    okc = torch.where(torch.arange(8, device="cuda")[None, :] < hand_n[:, None], codes == look, codes == 255)
+    assert bool(okc.all())
     valid = torch.arange(8, device="cuda")[None, :] < hand_n[:, None]
     assert bool(((hand < 52) | ~valid).all()) and bool(((hand == 255) | valid).all())
     # hand slots hold distinct deck indices
