@@ -406,7 +406,8 @@ static int ensure_device_setup() {
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);             \
   if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(" #kernel ")");
   BGYM_SET_SMEM(env_reset_kernel, RESET_CTA_SMEM)
-  BGYM_SET_SMEM(env_step_main_kernel, MAIN_CTA_SMEM)
+  BGYM_SET_SMEM(env_step_main_kernel<1>, MainCfg<1>::cta_smem)
+  BGYM_SET_SMEM(env_step_main_kernel<2>, MainCfg<2>::cta_smem)
   BGYM_SET_SMEM((env_step_gather_kernel<CAT_PLAY, 0, true>), GATHER_CTA_SMEM)
   BGYM_SET_SMEM((env_step_gather_kernel<CAT_DISCARD, 1, false>), GATHER_CTA_SMEM)
   BGYM_SET_SMEM((env_step_gather_kernel<CAT_OTHER, 2, true>), GATHER_CTA_SMEM)
@@ -511,7 +512,11 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
   a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_cap = sc->cap;
   cudaError_t e = cudaMemsetAsync(sc->counters, 0, 4 * sizeof(int), s);
   if (e != cudaSuccess) return cuda_rc(e, "cudaMemsetAsync(step counters)");
-  env_step_main_kernel<<<tile_grid(n, MAIN_WARPS, MAIN_CTAS_PER_SM), MAIN_WARPS * 32, MAIN_CTA_SMEM, s>>>(a);
+  static const int main_stages = (getenv("BGYM_MAIN_STAGES") && getenv("BGYM_MAIN_STAGES")[0] == '1') ? 1 : 2;
+  if (main_stages == 2)
+    env_step_main_kernel<2><<<tile_grid(n, MAIN_WARPS, MainCfg<2>::ctas_per_sm), MAIN_WARPS * 32, MainCfg<2>::cta_smem, s>>>(a);
+  else
+    env_step_main_kernel<1><<<tile_grid(n, MAIN_WARPS, MainCfg<1>::ctas_per_sm), MAIN_WARPS * 32, MainCfg<1>::cta_smem, s>>>(a);
   // the list lengths live on the device: launch resident-size grids, idle warps exit at once
   int ggrid = tile_grid((n + 3) / 4, GATHER_WARPS, GATHER_CTAS_PER_SM);
   if (ggrid < 1) ggrid = 1;

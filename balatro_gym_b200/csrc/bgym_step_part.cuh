@@ -68,39 +68,57 @@ __device__ __forceinline__ int policy_action(const Hot& h, uint64_t mask) {
 // main pass: per-warp tiles of 32 hot records, one bulk load + two bulk stores per tile
 // ------------------------------------------------------------------------------------------------
 constexpr int MAIN_WARPS = 4;
-constexpr int MAIN_WARP_SMEM = 32 * BGYM_HOT_BYTES + 32 * BGYM_OBS_BYTES;   // 4608 + 7680
-constexpr int MAIN_CTA_SMEM = MAIN_WARPS * MAIN_WARP_SMEM + 16 * MAIN_WARPS;
-constexpr int MAIN_CTAS_PER_SM = 4;
+constexpr int MAIN_HOT_TILE = 32 * BGYM_HOT_BYTES;   // 4608
+// STAGES = 1: one hot buffer per warp, 4 CTAs/SM (16 warps hide each other's loads)
+// STAGES = 2: the next tile's hot records are prefetched while the current tile is served, 3 CTAs/SM
+template <int STAGES>
+struct MainCfg {
+  static constexpr int warp_smem = STAGES * MAIN_HOT_TILE + 32 * BGYM_OBS_BYTES;
+  static constexpr int cta_smem = MAIN_WARPS * warp_smem + 16 * MAIN_WARPS;
+  static constexpr int ctas_per_sm = (227 * 1024) / cta_smem;
+};
 
-__global__ void __launch_bounds__(MAIN_WARPS * 32, MAIN_CTAS_PER_SM) env_step_main_kernel(StepArgs a) {
+template <int STAGES>
+__global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm) env_step_main_kernel(StepArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int MAIN_WARP_SMEM = MainCfg<STAGES>::warp_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* hot_buf = smem + warp * MAIN_WARP_SMEM;
-  uint8_t* obs_buf = hot_buf + 32 * BGYM_HOT_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + MAIN_WARPS * MAIN_WARP_SMEM) + warp * 2;
-  if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  uint8_t* hot_base = smem + warp * MAIN_WARP_SMEM;
+  uint8_t* obs_buf = hot_base + STAGES * MAIN_HOT_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MAIN_WARPS * MAIN_WARP_SMEM) + warp * 2;
+  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   __syncwarp();
   const long long n_tiles = (a.n + 31) >> 5;
   const long long warp_gid = (long long)blockIdx.x * MAIN_WARPS + warp;
   const long long warp_cnt = (long long)gridDim.x * MAIN_WARPS;
   const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
   const bool fused_policy = (a.flags & BGYM_FLAG_RANDOM_POLICY) != 0;
-  uint32_t parity = 0;
-  for (long long tile = warp_gid; tile < n_tiles; tile += warp_cnt) {
+  uint32_t parity_bits = 0;
+  int stage = 0;
+  auto issue_load = [&](long long t, int st) {   // lane 0 only
+    uint32_t bytes = (uint32_t)(min(32LL, a.n - t * 32) * BGYM_HOT_BYTES);
+    mbar_arrive_expect_tx(&bars[st], bytes);
+    bulk_g2s(hot_base + st * MAIN_HOT_TILE, a.hot + t * 32 * BGYM_HOT_BYTES, bytes, &bars[st]);
+  };
+  if (STAGES == 2 && lane == 0 && warp_gid < n_tiles) issue_load(warp_gid, 0);
+  for (long long tile = warp_gid; tile < n_tiles; tile += warp_cnt, stage = (STAGES == 2) ? (stage ^ 1) : 0) {
     const long long e = tile * 32 + lane;
     const bool active = e < a.n;
+    uint8_t* hot_buf = hot_base + stage * MAIN_HOT_TILE;
     uint8_t* hot = hot_buf + lane * BGYM_HOT_BYTES;
     uint8_t* obs_s = obs_buf + lane * BGYM_OBS_BYTES;
     if (lane == 0) {
-      bulk_wait_read0();   // the previous tile's bulk stores have finished reading shared memory
-      uint32_t bytes = (uint32_t)(min(32LL, a.n - tile * 32) * BGYM_HOT_BYTES);
-      mbar_arrive_expect_tx(bar, bytes);
-      bulk_g2s(hot_buf, a.hot + tile * 32 * BGYM_HOT_BYTES, bytes, bar);
+      // the previous tile's bulk stores have finished READING shared memory (its hot buffer is the one
+      // the next load overwrites; the obs buffer is rewritten below)
+      bulk_wait_read0();
+      if (STAGES == 2) { if (tile + warp_cnt < n_tiles) issue_load(tile + warp_cnt, stage ^ 1); }
+      else issue_load(tile, 0);
     }
     int action = 0;
     if (active && !fused_policy) action = __ldg(a.actions + e);
-    mbar_wait(bar, parity);
-    parity ^= 1;
+    __syncwarp();   // lane 0 has passed its wait: the obs buffer is free for every lane
+    mbar_wait(&bars[stage], (parity_bits >> stage) & 1);
+    parity_bits ^= 1u << stage;
 
     Hot h;
     double reward = 0.0;
