@@ -267,7 +267,11 @@ def run_ours(args):
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64+f64", "data": "synthetic", "config": workload_config(args, n),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "one env-step = env_step_main_kernel + 3 concurrent env_step_gather_kernel passes (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the four launches of one step at
+                     # 2^20 envs, from the committed ncu --set full capture (profiles/r01_ncu_summary_final.md):
+                     # main 161+354 MB, PLAY 54+18, OTHER 38+6, DISCARD 31+1 -> 663 MB = 632 B per env-step
+                     "traffic": 663e6 * n / float(1 << 20), "traffic_unit": "bytes per step launch set (ncu, profiles/)",
+                     "kernel": "one env-step = env_step_main_kernel + 3 concurrent env_step_gather_kernel passes (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
                      "units_per_launch": n, "kernel_ms": step_kernel_ms_max, "peak_source": peak_src,
                      "physical_bytes_per_unit": "main pass 144*2+240+14 = 542 B per env; gather passes add (144+176)*2+240 B for the ~17 % deferred envs"},
         "cpu_baseline": cpu_base,
@@ -280,7 +284,6 @@ def run_ours(args):
         "hands": hands,
         "episode_stats": {"episodes": float(stats[0]), "mean_return": float(stats[1] / max(1.0, float(stats[0]))),
                           "mean_length": float(stats[2] / max(1.0, float(stats[0])))},
-        "variant": os.environ.get("BGYM_VARIANT", "0"),
     }
     print(json.dumps(line))
     return 0
@@ -358,7 +361,14 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
-    return run_ours(args)
+    rc = run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+    return rc
 
 
 if __name__ == "__main__":
