@@ -44,7 +44,7 @@ struct StepArgs {
   int flags;
   // partitioned step: three device lists of deferred env indices + their counters
   int* part_lists;           // [3][part_cap]
-  int* part_counters;        // [4] (index c = category c; 0 unused)
+  int* part_counters;        // [4 * PART_CTR_STRIDE] (counter of category c at c * PART_CTR_STRIDE; 0 unused)
   long long part_cap;
 };
 
@@ -442,7 +442,7 @@ static int get_part_scratch(long long n, void* stream, PartScratch** out) {
   }
   if (sc->cap < n) {
     if (sc->lists) cudaFree(sc->lists);
-    cudaError_t e = cudaMalloc(&sc->lists, (size_t)(3 * n + 4) * sizeof(int));
+    cudaError_t e = cudaMalloc(&sc->lists, (size_t)(3 * n + 4 * PART_CTR_STRIDE) * sizeof(int));
     if (e != cudaSuccess) { sc->cap = 0; sc->lists = nullptr; return cuda_rc(e, "cudaMalloc(step scratch)"); }
     sc->cap = n;
     sc->counters = sc->lists + 3 * n;
@@ -510,7 +510,7 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
   a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.info = info;
   a.n = n; a.flags = flags;
   a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_cap = sc->cap;
-  cudaError_t e = cudaMemsetAsync(sc->counters, 0, 4 * sizeof(int), s);
+  cudaError_t e = cudaMemsetAsync(sc->counters, 0, 4 * PART_CTR_STRIDE * sizeof(int), s);
   if (e != cudaSuccess) return cuda_rc(e, "cudaMemsetAsync(step counters)");
   static const int main_stages = (getenv("BGYM_MAIN_STAGES") && getenv("BGYM_MAIN_STAGES")[0] == '1') ? 1 : 2;
   if (main_stages == 2)

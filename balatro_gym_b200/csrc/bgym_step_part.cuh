@@ -69,12 +69,18 @@ __device__ __forceinline__ int policy_action(const Hot& h, uint64_t mask) {
 // ------------------------------------------------------------------------------------------------
 constexpr int MAIN_WARPS = 4;
 constexpr int MAIN_HOT_TILE = 32 * BGYM_HOT_BYTES;   // 4608
+// Deferred env indices are staged per warp in shared memory and appended to the device lists in
+// runs of >= 32 (one atomic per run).  One atomic per tile and list kept a single L2 slice busy for
+// most of the pass (~10^5 same-sector atomics per 2^20 envs); the counters also sit 128 B apart.
+constexpr int PART_STAGE = 64;
+constexpr int PART_CTR_STRIDE = 32;   // ints between list counters
 // STAGES = 1: one hot buffer per warp, 4 CTAs/SM (16 warps hide each other's loads)
 // STAGES = 2: the next tile's hot records are prefetched while the current tile is served, 3 CTAs/SM
 template <int STAGES>
 struct MainCfg {
   static constexpr int warp_smem = STAGES * MAIN_HOT_TILE + 32 * BGYM_OBS_BYTES;
-  static constexpr int cta_smem = MAIN_WARPS * warp_smem + 16 * MAIN_WARPS;
+  // + per-warp staging of the three deferred lists (PART_STAGE entries each), then the mbarriers
+  static constexpr int cta_smem = MAIN_WARPS * warp_smem + MAIN_WARPS * 3 * PART_STAGE * 4 + 16 * MAIN_WARPS;
   static constexpr int ctas_per_sm = (227 * 1024) / cta_smem;
 };
 
@@ -85,9 +91,22 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* hot_base = smem + warp * MAIN_WARP_SMEM;
   uint8_t* obs_buf = hot_base + STAGES * MAIN_HOT_TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MAIN_WARPS * MAIN_WARP_SMEM) + warp * 2;
+  int* stage_list = reinterpret_cast<int*>(smem + MAIN_WARPS * MAIN_WARP_SMEM) + warp * 3 * PART_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MAIN_WARPS * MAIN_WARP_SMEM + MAIN_WARPS * 3 * PART_STAGE * 4) + warp * 2;
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   __syncwarp();
+  int staged[3] = {0, 0, 0};   // warp-uniform fill of the three staging lists
+  auto flush_list = [&](int c) {   // whole warp; c = 0..2
+    __syncwarp();
+    const int cnt = staged[c];
+    int basei = 0;
+    if (lane == 0) basei = atomicAdd(a.part_counters + (c + 1) * PART_CTR_STRIDE, cnt);
+    basei = __shfl_sync(0xffffffffu, basei, 0);
+    int* dst = a.part_lists + (long long)c * a.part_cap + basei;
+    for (int i = lane; i < cnt; i += 32) dst[i] = stage_list[c * PART_STAGE + i];
+    staged[c] = 0;
+    __syncwarp();
+  };
   const long long n_tiles = (a.n + 31) >> 5;
   const long long warp_gid = (long long)blockIdx.x * MAIN_WARPS + warp;
   const long long warp_cnt = (long long)gridDim.x * MAIN_WARPS;
@@ -152,16 +171,14 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
         write_step_outputs(a, e, reward, terminated, info);
       }
     }
-    // defer the other categories: warp-aggregated append to the category's list
+    // defer the other categories: stage the env index in the warp's list, flush runs of >= 32
 #pragma unroll
-    for (int c = 1; c <= 3; c++) {
-      uint32_t bal = __ballot_sync(0xffffffffu, cat == c);
+    for (int c = 0; c < 3; c++) {
+      uint32_t bal = __ballot_sync(0xffffffffu, cat == c + 1);
       if (bal) {
-        int leader = __ffs(bal) - 1;
-        int basei = 0;
-        if (lane == leader) basei = atomicAdd(a.part_counters + c, __popc(bal));
-        basei = __shfl_sync(0xffffffffu, basei, leader);
-        if (cat == c) a.part_lists[(long long)(c - 1) * a.part_cap + basei + __popc(bal & ((1u << lane) - 1))] = (int)e;
+        if (cat == c + 1) stage_list[c * PART_STAGE + staged[c] + __popc(bal & ((1u << lane) - 1))] = (int)e;
+        staged[c] += __popc(bal);
+        if (staged[c] >= 32) flush_list(c);
       }
     }
     fence_async_smem();
@@ -174,6 +191,8 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
       bulk_commit();
     }
   }
+#pragma unroll
+  for (int c = 0; c < 3; c++) if (staged[c]) flush_list(c);
   if (lane == 0) bulk_wait0();
 }
 
@@ -195,7 +214,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_ste
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GATHER_WARPS * GATHER_WARP_SMEM) + warp * 2;
   if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncwarp();
-  const int count = a.part_counters[LIST + 1];
+  const int count = a.part_counters[(LIST + 1) * PART_CTR_STRIDE];
   const int* list = a.part_lists + (long long)LIST * a.part_cap;
   const int n_tiles = (count + 31) >> 5;
   const int warp_gid = blockIdx.x * GATHER_WARPS + warp;
