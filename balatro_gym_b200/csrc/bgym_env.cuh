@@ -974,7 +974,28 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int obs_cons_id(int cid) { return cid >= BGYM_CONS_ENUMSTYLE_BASE ? 0 : cid; }
 
-__device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs /*smem, 240 B*/) {
+// the shop block of the observation (shop_items[10], shop_costs[10] as int16 pairs in record order):
+// the only part of the observation that reads the cold record
+struct ShopObs { uint32_t w[11]; };   // it0 | it1,2 | it3,4 | it5,6 | it7,8 | it9,ic0 | ic1,2 | ic3,4 | ic5,6 | ic7,8 | ic9
+
+__device__ __forceinline__ void obs_shop_block(const Hot& h, const uint8_t* rec, ShopObs& so) {
+  bool shop = h.phase == BGYM_PHASE_SHOP;
+  int n_items = shop ? rec[OFF_N_ITEMS] : 0;
+  int it[10], ic[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    bool on = i < n_items && i < 9;
+    it[i] = on ? rec[OFF_ITEM_TYPE + (i < 9 ? i : 8)] : 0;
+    ic[i] = on ? (*reinterpret_cast<const int*>(rec + OFF_ITEM_COST + 4 * (i < 9 ? i : 8)) & 0xFFFF) : 0;
+  }
+  so.w[0] = it[0];
+  so.w[1] = it[1] | (it[2] << 16); so.w[2] = it[3] | (it[4] << 16); so.w[3] = it[5] | (it[6] << 16); so.w[4] = it[7] | (it[8] << 16);
+  so.w[5] = it[9] | (ic[0] << 16);
+  so.w[6] = ic[1] | (ic[2] << 16); so.w[7] = ic[3] | (ic[4] << 16); so.w[8] = ic[5] | (ic[6] << 16);
+  so.w[9] = ic[7] | (ic[8] << 16); so.w[10] = ic[9];
+}
+
+__device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, uint64_t mask, uint8_t* obs /*smem, 240 B*/) {
   uint4 q;
   uint32_t selm = 0;
   #pragma unroll 1
@@ -1006,26 +1027,17 @@ __device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint
   int c0 = h.cons_n > 0 ? obs_cons_id(byte_at(h.cons, 0)) : 0, c1 = h.cons_n > 1 ? obs_cons_id(byte_at(h.cons, 1)) : 0;
   int c2 = h.cons_n > 2 ? obs_cons_id(byte_at(h.cons, 2)) : 0, c3 = h.cons_n > 3 ? obs_cons_id(byte_at(h.cons, 3)) : 0;
   int c4 = h.cons_n > 4 ? obs_cons_id(byte_at(h.cons, 4)) : 0;
-  bool shop = h.phase == BGYM_PHASE_SHOP;
-  int n_items = shop ? rec[OFF_N_ITEMS] : 0;
-  int it[10], ic[10];
-#pragma unroll
-  for (int i = 0; i < 10; i++) {
-    bool on = i < n_items && i < 9;
-    it[i] = on ? rec[OFF_ITEM_TYPE + (i < 9 ? i : 8)] : 0;
-    ic[i] = on ? (*reinterpret_cast<const int*>(rec + OFF_ITEM_COST + 4 * (i < 9 ? i : 8)) & 0xFFFF) : 0;
-  }
-  q.x = 0; q.y = (uint32_t)c0 | ((uint32_t)c1 << 16); q.z = (uint32_t)c2 | ((uint32_t)c3 << 16); q.w = (uint32_t)c4 | ((uint32_t)it[0] << 16);
+  q.x = 0; q.y = (uint32_t)c0 | ((uint32_t)c1 << 16); q.z = (uint32_t)c2 | ((uint32_t)c3 << 16); q.w = (uint32_t)c4 | (so.w[0] << 16);
   sts128(obs + 80, q);
   // 96: shop_items[1..8]
-  q.x = it[1] | (it[2] << 16); q.y = it[3] | (it[4] << 16); q.z = it[5] | (it[6] << 16); q.w = it[7] | (it[8] << 16);
+  q.x = so.w[1]; q.y = so.w[2]; q.z = so.w[3]; q.w = so.w[4];
   sts128(obs + 96, q);
   // 112: shop_items[9] | shop_costs[0..6]
-  q.x = it[9] | (ic[0] << 16); q.y = ic[1] | (ic[2] << 16); q.z = ic[3] | (ic[4] << 16); q.w = ic[5] | (ic[6] << 16);
+  q.x = so.w[5]; q.y = so.w[6]; q.z = so.w[7]; q.w = so.w[8];
   sts128(obs + 112, q);
   // 128: shop_costs[7..9] (128..133) | hand_levels[0..9] (134..143)
-  q.x = ic[7] | (ic[8] << 16);
-  q.y = ic[9] | ((h.lv0 & 0xFFFF) << 16);
+  q.x = so.w[9];
+  q.y = so.w[10] | ((h.lv0 & 0xFFFF) << 16);
   q.z = (h.lv0 >> 16) | ((h.lv1 & 0xFFFF) << 16);
   q.w = (h.lv1 >> 16) | ((h.lv2 & 0xFFFF) << 16);
   sts128(obs + 128, q);
@@ -1052,6 +1064,16 @@ __device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint
   // 224: action_mask[56..59] | pad
   q.x = spread4(mhi >> 24); q.y = 0; q.z = 0; q.w = 0;
   sts128(obs + 224, q);
+}
+
+__device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs /*smem, 240 B*/) {
+  ShopObs so;
+  if (rec) obs_shop_block(h, rec, so);
+  else {
+#pragma unroll
+    for (int i = 0; i < 11; i++) so.w[i] = 0;   // PLAY phase (main pass): the shop block is all zeros
+  }
+  write_obs_regs(h, so, mask, obs);
 }
 
 }  // namespace bgym

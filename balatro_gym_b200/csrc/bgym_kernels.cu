@@ -362,15 +362,20 @@ __global__ void episode_stats_kernel(const double* reward, const uint8_t* termin
     if (terminated[i]) { eps += 1; sret += acc; slen += len; acc = 0; len = 0; }
     ret_acc[i] = acc; len_acc[i] = len;
   }
-  // warp reduce, one atomic per warp and statistic
+  // warp reduce, then block reduce through shared memory: one atomic per CTA and statistic
   for (int o = 16; o > 0; o >>= 1) {
     eps += __shfl_xor_sync(0xffffffffu, eps, o); sret += __shfl_xor_sync(0xffffffffu, sret, o);
     slen += __shfl_xor_sync(0xffffffffu, slen, o); steps += __shfl_xor_sync(0xffffffffu, steps, o);
     srew += __shfl_xor_sync(0xffffffffu, srew, o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    if (eps != 0) { atomicAdd(&stats[0], eps); atomicAdd(&stats[1], sret); atomicAdd(&stats[2], slen); }
-    atomicAdd(&stats[3], steps); atomicAdd(&stats[4], srew);
+  __shared__ double part[8][5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { part[warp][0] = eps; part[warp][1] = sret; part[warp][2] = slen; part[warp][3] = steps; part[warp][4] = srew; }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double v = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += part[w][threadIdx.x];
+    if (v != 0) atomicAdd(&stats[threadIdx.x], v);
   }
 }
 
@@ -510,6 +515,13 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
   a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.info = info;
   a.n = n; a.flags = flags;
   a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_cap = sc->cap;
+  // BGYM_STEP_TIMING=1 (diagnostic): synchronising per-phase timing of the launch set, printed every 64 calls
+  static const bool timing = getenv("BGYM_STEP_TIMING") != nullptr;
+  static cudaEvent_t tev[3];
+  static double tsum[2] = {0, 0};
+  static int tcalls = 0;
+  if (timing && tcalls == 0 && tsum[0] == 0) for (int i = 0; i < 3; i++) cudaEventCreate(&tev[i]);
+  if (timing) cudaEventRecord(tev[0], s);
   cudaError_t e = cudaMemsetAsync(sc->counters, 0, 4 * PART_CTR_STRIDE * sizeof(int), s);
   if (e != cudaSuccess) return cuda_rc(e, "cudaMemsetAsync(step counters)");
   static const int main_stages = (getenv("BGYM_MAIN_STAGES") && getenv("BGYM_MAIN_STAGES")[0] == '1') ? 1 : 2;
@@ -517,6 +529,7 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
     env_step_main_kernel<2><<<tile_grid(n, MAIN_WARPS, MainCfg<2>::ctas_per_sm), MAIN_WARPS * 32, MainCfg<2>::cta_smem, s>>>(a);
   else
     env_step_main_kernel<1><<<tile_grid(n, MAIN_WARPS, MainCfg<1>::ctas_per_sm), MAIN_WARPS * 32, MainCfg<1>::cta_smem, s>>>(a);
+  if (timing) cudaEventRecord(tev[1], s);
   // the list lengths live on the device: launch resident-size grids, idle warps exit at once
   int ggrid = tile_grid((n + 3) / 4, GATHER_WARPS, GATHER_CTAS_PER_SM);
   if (ggrid < 1) ggrid = 1;
@@ -539,6 +552,17 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
     env_step_gather_kernel<CAT_DISCARD, 1, false><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
     env_step_gather_kernel<CAT_OTHER, 2, true><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
   }
+  if (timing) {
+    cudaEventRecord(tev[2], s);
+    cudaEventSynchronize(tev[2]);
+    float m0 = 0, m1 = 0;
+    cudaEventElapsedTime(&m0, tev[0], tev[1]); cudaEventElapsedTime(&m1, tev[1], tev[2]);
+    tsum[0] += m0; tsum[1] += m1;
+    if (++tcalls % 64 == 0) {
+      fprintf(stderr, "[bgym timing] main %.1f us, gathers %.1f us (mean of 64 steps)\n", tsum[0] / 64 * 1e3, tsum[1] / 64 * 1e3);
+      tsum[0] = tsum[1] = 1e-30;
+    }
+  }
   return cuda_rc(cudaGetLastError(), "bgym_step launch");
 }
 
@@ -558,7 +582,9 @@ int bgym_sample_actions(const BgymObs* obs, int32_t* actions, uint32_t seed, uin
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
-  int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 8 ? (n + 255) / 256 : (long long)g_sm_count * 8);
+  // one thread per env up to 64 resident-size waves: the 8-byte mask reads are 240-B strided and
+  // latency-bound, so keep as many in flight as the machine holds
+  int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 512 ? (n + 255) / 256 : (long long)g_sm_count * 512);
   sample_actions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), actions, seed, step, n);
   return cuda_rc(cudaGetLastError(), "bgym_sample_actions launch");
 }

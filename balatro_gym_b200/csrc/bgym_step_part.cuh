@@ -200,9 +200,15 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
 // gather pass: one listed env per lane, per-lane bulk copies of its hot and cold record
 // ------------------------------------------------------------------------------------------------
 constexpr int GATHER_WARPS = 4;
-constexpr int GATHER_WARP_SMEM = 32 * (BGYM_HOT_BYTES + BGYM_COLD_BYTES + BGYM_OBS_BYTES);  // 17920
+// the observation tile (32 x 240 B) is staged OVER the hot + cold tiles once their stores have read
+// them, so a warp needs 10 KB and an SM holds BGYM_GATHER_CTAS x 4 warps (the passes are bound by
+// dependent integer latency: resident warps are what buys throughput)
+constexpr int GATHER_WARP_SMEM = 32 * (BGYM_HOT_BYTES + BGYM_COLD_BYTES);  // 10240 >= 32 * 240
 constexpr int GATHER_CTA_SMEM = GATHER_WARPS * GATHER_WARP_SMEM + 16 * GATHER_WARPS;
-constexpr int GATHER_CTAS_PER_SM = 3;
+#ifndef BGYM_GATHER_CTAS
+#define BGYM_GATHER_CTAS 4
+#endif
+constexpr int GATHER_CTAS_PER_SM = BGYM_GATHER_CTAS;
 
 template <int CATS, int LIST, bool STORE_COLD>
 __global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_step_gather_kernel(StepArgs a) {
@@ -210,7 +216,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_ste
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* hot_buf = smem + warp * GATHER_WARP_SMEM;
   uint8_t* cold_buf = hot_buf + 32 * BGYM_HOT_BYTES;
-  uint8_t* obs_buf = cold_buf + 32 * BGYM_COLD_BYTES;
+  uint8_t* obs_buf = hot_buf;     // overlay, see GATHER_WARP_SMEM
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GATHER_WARPS * GATHER_WARP_SMEM) + warp * 2;
   if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncwarp();
@@ -269,9 +275,11 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_ste
       }
     }
     if (a.flags & BGYM_FLAG_AUTORESET) autoreset_warp(want_reset, new_seed, cold, lane);
+    ShopObs so;
+    uint64_t m1 = 0;
     if (active) {
       pack_hot(hot, h);
-      if (with_obs) write_obs(h, cold, action_mask(h, cold), obs_s);
+      if (with_obs) { m1 = action_mask(h, cold); obs_shop_block(h, cold, so); }   // last reads of the cold slot
       write_step_outputs(a, e, reward, terminated, info);
     }
     fence_async_smem();   // every lane: a cooperative reset writes other lanes' slots
@@ -279,8 +287,14 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_ste
     if (active) {
       bulk_s2g(a.hot + e * BGYM_HOT_BYTES, hot, BGYM_HOT_BYTES);
       if (STORE_COLD || want_reset) bulk_s2g(a.cold + e * BGYM_COLD_BYTES, cold, BGYM_COLD_BYTES);
-      if (with_obs) bulk_s2g(a.obs + e * BGYM_OBS_BYTES, obs_s, BGYM_OBS_BYTES);
       bulk_commit();
+    }
+    if (with_obs) {
+      bulk_wait_read0();  // this lane's record stores have read shared memory ...
+      __syncwarp();       // ... and so have all the others': the tile is free for the observations
+      if (active) write_obs_regs(h, so, m1, obs_s);
+      fence_async_smem();
+      if (active) { bulk_s2g(a.obs + e * BGYM_OBS_BYTES, obs_s, BGYM_OBS_BYTES); bulk_commit(); }
     }
   }
   bulk_wait0();
