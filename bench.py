@@ -269,8 +269,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the four launches of one step at
                      # 2^20 envs, from the committed ncu --set full capture (profiles/r01_ncu_summary_final.md):
-                     # main 161+354 MB, PLAY 54+18, OTHER 38+6, DISCARD 31+1 -> 663 MB = 632 B per env-step
-                     "traffic": 663e6 * n / float(1 << 20), "traffic_unit": "bytes per step launch set (ncu, profiles/)",
+                     # main 161+354 MB, PLAY 54+22, OTHER 38+6, DISCARD 31+1 -> 667 MB = 636 B per env-step
+                     "traffic": 667e6 * n / float(1 << 20), "traffic_unit": "bytes per step launch set (ncu, profiles/)",
                      "kernel": "one env-step = env_step_main_kernel + 3 concurrent env_step_gather_kernel passes (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
                      "units_per_launch": n, "kernel_ms": step_kernel_ms_max, "peak_source": peak_src,
                      "physical_bytes_per_unit": "main pass 144*2+240+14 = 542 B per env; gather passes add (144+176)*2+240 B for the ~17 % deferred envs"},
