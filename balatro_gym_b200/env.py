@@ -76,6 +76,27 @@ def observation_space():
     })
 
 
+def info_dict(inf) -> dict:
+    """Step-info dict from one BgymInfo record, with the reference's keys (balatro_env_2.py:626-627, 925-960)."""
+    info = {}
+    if inf["error_code"]:
+        info["error"] = _ERR_TEXT.get(int(inf["error_code"]), "error")
+    if inf["flags"] & L.F_PLAYED:
+        info["final_score"] = int(inf["final_score"])
+        info["hand_type"] = int(inf["hand_type"])
+        info["hand_type_name"] = _HAND_TYPE_NAMES[int(inf["hand_type"])]
+        info["cards_played"] = int(inf["cards_played"])
+        info["score_breakdown"] = {"final_chips": int(inf["chips"]), "final_mult": int(inf["mult"]),
+                                   "final_x_mult": float(inf["x_mult"]), "final_score": int(inf["base_score"])}
+    if inf["flags"] & L.F_BEAT_BLIND:
+        info["beat_blind"] = True
+    if inf["flags"] & L.F_FAILED:
+        info["failed"] = True
+    if inf["flags"] & L.F_GUARD_TERMINATED:
+        info["terminated"] = "guard"
+    return info
+
+
 class BalatroEnv(_EnvBase):
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 4}
 
@@ -110,23 +131,7 @@ class BalatroEnv(_EnvBase):
         torch = self.vec.torch
         a = torch.tensor([int(action)], dtype=torch.int32, device=self.vec.device)
         self.vec.step(a)
-        inf = self.vec.info_numpy()[0]
-        info = {}
-        if inf["error_code"]:
-            info["error"] = _ERR_TEXT.get(int(inf["error_code"]), "error")
-        if inf["flags"] & L.F_PLAYED:
-            info["final_score"] = int(inf["final_score"])
-            info["hand_type"] = int(inf["hand_type"])
-            info["hand_type_name"] = _HAND_TYPE_NAMES[int(inf["hand_type"])]
-            info["cards_played"] = int(inf["cards_played"])
-            info["score_breakdown"] = {"final_chips": int(inf["chips"]), "final_mult": int(inf["mult"]),
-                                       "final_x_mult": float(inf["x_mult"]), "final_score": int(inf["base_score"])}
-        if inf["flags"] & L.F_BEAT_BLIND:
-            info["beat_blind"] = True
-        if inf["flags"] & L.F_FAILED:
-            info["failed"] = True
-        if inf["flags"] & L.F_GUARD_TERMINATED:
-            info["terminated"] = "guard"
+        info = info_dict(self.vec.info_numpy()[0])
         reward = float(self.vec.reward.cpu()[0])
         terminated = bool(self.vec.terminated.cpu()[0])
         return self._obs(), reward, terminated, False, info

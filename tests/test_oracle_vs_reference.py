@@ -108,3 +108,11 @@ def test_every_joker_row_vs_reference(reference):
         cards, mods, nc, jk, lv, ctx = _pack(sub)
         out = coracle.score_hands(cards, mods, nc, jk, lv, ctx, flags=1 if tn else 0)
         check_scores(sub, out)
+
+
+def test_validator_port_accepts_the_reference(reference):
+    """balatro_gym_b200.validate.BalatroEnvValidator is duck-typed: the unmodified reference passes it,
+    so a failure on the device env is a real divergence and not a stricter check."""
+    from balatro_gym_b200.validate import BalatroEnvValidator
+    assert BalatroEnvValidator.validate_determinism(reference.BalatroEnv, seed=42, steps=100)
+    assert BalatroEnvValidator.validate_action_masking(reference.BalatroEnv(seed=42))
