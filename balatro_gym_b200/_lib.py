@@ -15,7 +15,7 @@ from . import layout as L
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "libbgym.so")
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("bgym_kernels.cu", "bgym_step_part.cuh", "bgym_env.cuh", "bgym_device.cuh")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("bgym_kernels.cu", "bgym_step_part.cuh", "bgym_rollout.cuh", "bgym_env.cuh", "bgym_device.cuh")]
 HEADERS = [os.path.join(_REPO, "include", f) for f in ("bgym.h", "bgym_tables.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -65,6 +65,9 @@ SYMBOLS = {
     "bgym_sample_actions": (_i32, [_vp, _vp, _u32, _u64, _i64, _vp]),
     "bgym_score_hands": (_i32, [_vp] * 12 + [_u32, _i64, _i32, _vp]),
     "bgym_episode_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "bgym_featurize": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "bgym_masked_sample": (_i32, [_vp, _i32, _vp, _vp, _u32, _u64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "bgym_gae": (_i32, [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _i64, _i64, _vp]),
     "bgym_vec_create": (_i32, [C.POINTER(_vp), _i64, _i32]),
     "bgym_vec_destroy": (_i32, [_vp]),
     "bgym_vec_reset_host": (_i32, [_vp, _vp, _vp, _vp]),

@@ -81,6 +81,7 @@ __device__ __forceinline__ void sts128(void* p, uint4 v) { *reinterpret_cast<uin
 #define BGYM_PHILOX_KEY1 0xB200CAFEu
 #define BGYM_POLICY_KEY1 0x5A17AC71u
 #define BGYM_SHUFFLE_KEY1 0xB200DECCu
+#define BGYM_SAMPLE_KEY1 0xCA7E6031u
 
 // noinline on purpose: draws are rare (a few percent of env-steps) and the step kernel has ~20 draw
 // sites; one shared copy keeps the kernel inside the instruction cache.

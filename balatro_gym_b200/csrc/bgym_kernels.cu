@@ -50,6 +50,7 @@ struct StepArgs {
 
 }  // namespace bgym
 #include "bgym_step_part.cuh"
+#include "bgym_rollout.cuh"
 namespace bgym {
 
 // ---------------------------------------------------------------------------------------------
@@ -621,6 +622,58 @@ int bgym_episode_stats(const double* reward, const uint8_t* terminated, double* 
   int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 8 ? (n + 255) / 256 : (long long)g_sm_count * 8);
   episode_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reward, terminated, ret_acc, len_acc, stats, n);
   return cuda_rc(cudaGetLastError(), "bgym_episode_stats launch");
+}
+
+// ---- rollout collection kernels (bgym_rollout.cuh) ------------------------------------------------
+int bgym_featurize(const BgymObs* obs, void* features, int64_t n, int dtype, void* stream) {
+  if (n < 0 || !obs || !features) return set_err(BGYM_E_ARG, "bgym_featurize: bad arguments");
+  if (dtype != BGYM_DT_F32 && dtype != BGYM_DT_BF16) return set_err(BGYM_E_ARG, "bgym_featurize: dtype must be BGYM_DT_F32 or BGYM_DT_BF16");
+  if (misaligned(obs, 16) || misaligned(features, 16)) return set_err(BGYM_E_ALIGN, "bgym_featurize: obs/features must be 16-byte aligned");
+  if (n == 0) return 0;
+  int rc = ensure_device_setup();
+  if (rc) return rc;
+  long long blocks = (n + FEAT_ENVS_PER_CTA - 1) / FEAT_ENVS_PER_CTA;
+  long long cap = (long long)g_sm_count * 64;
+  int grid = (int)(blocks < cap ? blocks : cap);
+  const int ft = FEAT_ENVS_PER_CTA * FEAT_CHUNKS;
+  if (dtype == BGYM_DT_F32)
+    featurize_kernel<float><<<grid, ft, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<float*>(features), n);
+  else
+    featurize_kernel<__nv_bfloat16><<<grid, ft, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<__nv_bfloat16*>(features), n);
+  return cuda_rc(cudaGetLastError(), "bgym_featurize launch");
+}
+
+int bgym_masked_sample(const void* logits, int dtype, const BgymObs* obs, const float* uniforms,
+                       uint32_t seed, uint64_t step, int64_t env_offset,
+                       int32_t* actions, float* logp, float* entropy, int64_t n, void* stream) {
+  if (n < 0 || !logits || !obs || !actions || !logp) return set_err(BGYM_E_ARG, "bgym_masked_sample: bad arguments");
+  if (dtype != BGYM_DT_F32 && dtype != BGYM_DT_BF16) return set_err(BGYM_E_ARG, "bgym_masked_sample: dtype must be BGYM_DT_F32 or BGYM_DT_BF16");
+  if (misaligned(obs, 16) || misaligned(logits, dtype == BGYM_DT_F32 ? 16 : 8))
+    return set_err(BGYM_E_ALIGN, "bgym_masked_sample: obs needs 16-byte, logits 16-byte (f32) / 8-byte (bf16) alignment");
+  if (n == 0) return 0;
+  int rc = ensure_device_setup();
+  if (rc) return rc;
+  long long blocks = (n * 16 + 255) / 256;
+  if (blocks > 0x7fffffffLL) return set_err(BGYM_E_ARG, "bgym_masked_sample: n too large for one launch");
+  if (dtype == BGYM_DT_F32)
+    masked_sample_kernel<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(logits), reinterpret_cast<const uint8_t*>(obs),
+        uniforms, seed, step, env_offset, actions, logp, entropy, n);
+  else
+    masked_sample_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), reinterpret_cast<const uint8_t*>(obs),
+        uniforms, seed, step, env_offset, actions, logp, entropy, n);
+  return cuda_rc(cudaGetLastError(), "bgym_masked_sample launch");
+}
+
+int bgym_gae(const float* rewards, const float* values, const uint8_t* dones, float gamma, float lam,
+             float* advantages, float* returns, int64_t T, int64_t n, void* stream) {
+  if (n < 0 || T < 0 || !rewards || !values || !dones || !advantages || !returns) return set_err(BGYM_E_ARG, "bgym_gae: bad arguments");
+  if (n == 0 || T == 0) return 0;
+  int rc = ensure_device_setup();
+  if (rc) return rc;
+  long long blocks = (n + 255) / 256;
+  long long cap = (long long)g_sm_count * 32;
+  gae_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, gamma, lam, advantages, returns, T, n);
+  return cuda_rc(cudaGetLastError(), "bgym_gae launch");
 }
 
 // ---- host-buffer handle API ---------------------------------------------------------------------

@@ -54,3 +54,20 @@ def barrier():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+def allreduce_mean_grads(params):
+    """Average the gradients of `params` over ranks with ONE all-reduce on a flat buffer (the policy-side
+    exchange of a data-parallel PPO update; the env step path itself has no collective)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    params = [p for p in params if p.grad is not None]
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= dist.get_world_size()
+    o = 0
+    for p in params:
+        p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
+        o += p.numel()

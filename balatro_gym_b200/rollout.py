@@ -1,0 +1,253 @@
+"""On-device PPO rollout collection (BASELINE config 5).
+
+What the reference does per rollout (train_balatro_agent.py:269-475 through stable_baselines3):
+N subprocess envs step on CPU, observations are pickled to the trainer, `BalatroFeaturesExtractor`
+(:42-119) one-hots the hand on the GPU, PPO samples an action per env, and after `n_steps` the
+RolloutBuffer computes GAE(gamma=0.99, lambda=0.95) (:328-336).
+
+Here the whole loop stays on the device: the env step kernels write observation records, a
+featurize kernel turns them into the extractor's dense input, the policy MLP runs under bf16
+autocast (cuBLAS — policy side, not part of the env path), a masked-categorical kernel samples
+actions from the logits and the observation's legal-action word, and a GAE kernel closes the
+rollout.  Nothing crosses PCIe.  Multi-GPU: one collector per rank over its env slab
+(`BalatroVecEnv(env_offset=...)`); the only collective is the gradient all-reduce of the PPO
+update (`ppo_update`), which is policy side.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+from . import layout as L
+from . import _lib
+
+FEATURE_DIM = 448
+_DT = {"float32": 0, "bfloat16": 1}
+
+
+def _torch():
+    return _lib.require_cuda()
+
+
+def featurize(obs_records, out=None, dtype=None):
+    """[n, 240] uint8 observation records -> [n, 448] features (bgym_featurize)."""
+    torch = _torch()
+    lib = _lib.load()
+    n = obs_records.shape[0]
+    assert obs_records.dtype == torch.uint8 and obs_records.shape[1] == L.OBS_BYTES and obs_records.is_contiguous()
+    if out is None:
+        out = torch.empty((n, FEATURE_DIM), dtype=dtype or torch.float32, device=obs_records.device)
+    code = _DT[str(out.dtype).split(".")[-1]]
+    with torch.cuda.device(obs_records.device):
+        rc = lib.bgym_featurize(obs_records.data_ptr(), out.data_ptr(), n, code, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "bgym_featurize")
+    return out
+
+
+def masked_sample(logits, obs_records, seed: int = 0, step: int = 0, env_offset: int = 0, uniforms=None,
+                  actions=None, logp=None, entropy=None):
+    """Sample one legal action per env from softmax(logits | legal) (bgym_masked_sample).
+    Returns (actions int32 [n], logp float32 [n], entropy float32 [n])."""
+    torch = _torch()
+    lib = _lib.load()
+    n = logits.shape[0]
+    assert logits.shape[1] == L.NUM_ACTIONS and logits.is_contiguous()
+    code = _DT[str(logits.dtype).split(".")[-1]]
+    dev = logits.device
+    actions = torch.empty(n, dtype=torch.int32, device=dev) if actions is None else actions
+    logp = torch.empty(n, dtype=torch.float32, device=dev) if logp is None else logp
+    entropy = torch.empty(n, dtype=torch.float32, device=dev) if entropy is None else entropy
+    with torch.cuda.device(dev):
+        rc = lib.bgym_masked_sample(logits.data_ptr(), code, obs_records.data_ptr(),
+                                    None if uniforms is None else uniforms.data_ptr(), seed & 0xFFFFFFFF, step, env_offset,
+                                    actions.data_ptr(), logp.data_ptr(), entropy.data_ptr(), n,
+                                    torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "bgym_masked_sample")
+    return actions, logp, entropy
+
+
+def gae(rewards, values, dones, gamma: float = 0.99, lam: float = 0.95, advantages=None, returns=None):
+    """rewards [T, n] f32, values [T+1, n] f32, dones [T, n] u8 -> (advantages, returns) [T, n] (bgym_gae)."""
+    torch = _torch()
+    lib = _lib.load()
+    T, n = rewards.shape
+    assert values.shape == (T + 1, n) and dones.shape == (T, n)
+    assert rewards.dtype == torch.float32 and values.dtype == torch.float32 and dones.dtype == torch.uint8
+    assert rewards.is_contiguous() and values.is_contiguous() and dones.is_contiguous()
+    advantages = torch.empty_like(rewards) if advantages is None else advantages
+    returns = torch.empty_like(rewards) if returns is None else returns
+    with torch.cuda.device(rewards.device):
+        rc = lib.bgym_gae(rewards.data_ptr(), values.data_ptr(), dones.data_ptr(), gamma, lam,
+                          advantages.data_ptr(), returns.data_ptr(), T, n, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "bgym_gae")
+    return advantages, returns
+
+
+def make_policy(features_dim: int = 512, pi=(256, 256), vf=(256, 256), device="cuda", seed: int = 0):
+    """Actor-critic with the reference's extractor topology (train_balatro_agent.py:48-81, heads :341).
+    The reference declares joker_dim = 160 and game_state_dim = 32 but feeds 10 and 21 columns
+    (:98, :102-113) — it cannot run as written; the widths here are the ones the data has."""
+    torch = _torch()
+    nn = torch.nn
+
+    class BalatroPolicy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.hand_net = nn.Sequential(nn.Linear(416, 256), nn.ReLU(), nn.Linear(256, 128), nn.ReLU())
+            self.joker_net = nn.Sequential(nn.Linear(10, 128), nn.ReLU(), nn.Linear(128, 64), nn.ReLU())
+            self.game_state_net = nn.Sequential(nn.Linear(21, 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU())
+            self.combined_net = nn.Sequential(nn.Linear(224, features_dim), nn.ReLU(),
+                                              nn.Linear(features_dim, features_dim), nn.ReLU())
+
+            def head(widths, out):
+                layers, d = [], features_dim
+                for w in widths:
+                    layers += [nn.Linear(d, w), nn.Tanh()]
+                    d = w
+                return nn.Sequential(*layers, nn.Linear(d, out))
+            self.pi = head(pi, L.NUM_ACTIONS)
+            self.vf = head(vf, 1)
+
+        def forward(self, feats):
+            h = self.hand_net(feats[:, :416])
+            j = self.joker_net(feats[:, 416:426])
+            g = self.game_state_net(feats[:, 426:447])
+            z = self.combined_net(torch.cat([h, j, g], dim=1))
+            return self.pi(z), self.vf(z).squeeze(-1)
+
+    # same seed -> same initial weights on every rank, without disturbing the caller's RNG stream
+    state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    try:
+        policy = BalatroPolicy()
+    finally:
+        torch.random.set_rng_state(state)
+    return policy.to(device)
+
+
+class RolloutCollector:
+    """`n_steps` of experience for every env of a slab, collected without leaving the device.
+
+    Buffers are time-major [T(+1), n, ...]: obs (raw 240-byte records; features are recomputed
+    on demand, 3.7x smaller than storing bf16 features), actions, logp, values, rewards, dones,
+    advantages, returns.
+    """
+
+    def __init__(self, vec, policy, n_steps: int = 128, gamma: float = 0.99, gae_lambda: float = 0.95,
+                 seed: int = 0, autocast: bool = True):
+        torch = vec.torch
+        self.torch = torch
+        self.vec, self.policy = vec, policy
+        self.T, self.n = int(n_steps), vec.num_envs
+        self.gamma, self.lam, self.seed = gamma, gae_lambda, seed
+        self.autocast = autocast
+        dev, T, n = vec.device, self.T, self.n
+        self.obs = torch.empty((T + 1, n, L.OBS_BYTES), dtype=torch.uint8, device=dev)
+        self.actions = torch.empty((T, n), dtype=torch.int32, device=dev)
+        self.logp = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.entropy = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.values = torch.empty((T + 1, n), dtype=torch.float32, device=dev)
+        self.rewards = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.dones = torch.empty((T, n), dtype=torch.uint8, device=dev)
+        self.advantages = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self.returns = torch.empty((T, n), dtype=torch.float32, device=dev)
+        self._feats = torch.empty((n, FEATURE_DIM), dtype=torch.bfloat16 if autocast else torch.float32, device=dev)
+        self.global_step = 0
+
+    def _forward(self, obs_records):
+        torch = self.torch
+        featurize(obs_records, out=self._feats)
+        if self.autocast:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits, value = self.policy(self._feats)
+        else:
+            logits, value = self.policy(self._feats)
+        return logits.float().contiguous(), value.float()
+
+    def collect(self):
+        """Run T steps from the vec env's CURRENT observations (call vec.reset() once before the first)."""
+        torch = self.torch
+        vec = self.vec
+        with torch.no_grad():
+            self.obs[0].copy_(vec.obs_buf)
+            for t in range(self.T):
+                logits, value = self._forward(self.obs[t])
+                masked_sample(logits, self.obs[t], seed=self.seed, step=self.global_step, env_offset=vec.env_offset,
+                              actions=self.actions[t], logp=self.logp[t], entropy=self.entropy[t])
+                self.values[t].copy_(value)
+                vec.step(self.actions[t], want_info=False)
+                self.rewards[t].copy_(vec.reward)
+                self.dones[t].copy_(vec.terminated)
+                self.obs[t + 1].copy_(vec.obs_buf)
+                self.global_step += 1
+            _, value = self._forward(self.obs[self.T])
+            self.values[self.T].copy_(value)
+            gae(self.rewards, self.values, self.dones, self.gamma, self.lam, self.advantages, self.returns)
+        return self
+
+    def stats(self):
+        """(env-steps, episodes finished, mean reward per step) of the last rollout, as python numbers."""
+        return self.T * self.n, int(self.dones.sum().item()), float(self.rewards.mean().item())
+
+
+def legal_mask(obs_records):
+    """[B, 240] uint8 records -> [B, 60] bool from the packed legal-action word."""
+    torch = _torch()
+    bits = obs_records[:, 160:168].contiguous().view(torch.int64)
+    return ((bits >> torch.arange(L.NUM_ACTIONS, device=obs_records.device)) & 1).bool()
+
+
+def evaluate_actions(policy, obs_records, actions, autocast: bool = True):
+    """log-prob, entropy, value of `actions` under the masked policy — the differentiable twin of
+    the sampling kernel (torch ops, used by the PPO update)."""
+    torch = _torch()
+    feats = featurize(obs_records, dtype=torch.bfloat16 if autocast else torch.float32)
+    if autocast:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits, value = policy(feats)
+    else:
+        logits, value = policy(feats)
+    mask = legal_mask(obs_records)
+    mask[:, 0] |= ~mask.any(dim=1)
+    logits = logits.float().masked_fill(~mask, float("-inf"))
+    logp_all = torch.log_softmax(logits, dim=1)
+    logp = logp_all.gather(1, actions.long().unsqueeze(1)).squeeze(1)
+    p = logp_all.exp()
+    entropy = -(p * logp_all.masked_fill(~mask, 0.0)).sum(dim=1)
+    return logp, entropy, value.float()
+
+
+def ppo_update(policy, optimizer, rollout: RolloutCollector, n_epochs: int = 4, minibatch: int = 1 << 16,
+               clip_range: float = 0.2, ent_coef: float = 0.01, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
+               generator=None):
+    """Clipped-surrogate PPO over one rollout (the SB3 defaults the reference uses,
+    train_balatro_agent.py:328-336).  With torch.distributed initialised, gradients are averaged
+    over ranks with one all-reduce per minibatch on a flat buffer."""
+    torch = _torch()
+    from . import dist as bdist
+    T, n = rollout.T, rollout.n
+    N = T * n
+    obs = rollout.obs[:T].view(N, L.OBS_BYTES)
+    actions, old_logp = rollout.actions.view(N), rollout.logp.view(N)
+    adv_all, ret_all = rollout.advantages.view(N), rollout.returns.view(N)
+    params = [p for p in policy.parameters() if p.requires_grad]
+    last = {}
+    for _ in range(n_epochs):
+        perm = torch.randperm(N, device=obs.device, generator=generator)
+        for s in range(0, N, minibatch):
+            idx = perm[s:s + minibatch]
+            logp, entropy, value = evaluate_actions(policy, obs[idx], actions[idx], autocast=rollout.autocast)
+            adv = adv_all[idx]
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+            ratio = torch.exp(logp - old_logp[idx])
+            pg_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - clip_range, 1 + clip_range)).mean()
+            v_loss = torch.nn.functional.mse_loss(value, ret_all[idx])
+            ent = entropy.mean()
+            loss = pg_loss + vf_coef * v_loss - ent_coef * ent
+            optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+            bdist.allreduce_mean_grads(params)
+            torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+            optimizer.step()
+            last = {"loss": loss.detach(), "pg_loss": pg_loss.detach(), "v_loss": v_loss.detach(), "entropy": ent.detach(),
+                    "approx_kl": ((ratio - 1) - torch.log(ratio)).mean().detach()}
+    return {k: float(v.item()) for k, v in last.items()}

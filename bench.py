@@ -257,6 +257,11 @@ def run_ours(args):
     if rank == 0 and not args.no_hands:
         hands = bench_hands(torch, b, dev, peak, args)
 
+    # ---- PPO rollout collection (configs[4]; every rank runs its env slab) ----
+    ppo = None
+    if not args.no_ppo:
+        ppo = bench_ppo_rollout(torch, bdist, dev, args, rank, ws)
+
     if rank != 0:
         return 0
     cpu_base = None
@@ -282,11 +287,62 @@ def run_ours(args):
         "fused_rollout": {"value": fused_value, "unit": UNIT, "ms_per_step": fused_ms / K,
                           "note": "policy sampled inside the step kernel (one launch per step)"},
         "hands": hands,
+        "ppo_rollout": ppo,
         "episode_stats": {"episodes": float(stats[0]), "mean_return": float(stats[1] / max(1.0, float(stats[0]))),
                           "mean_length": float(stats[2] / max(1.0, float(stats[0])))},
     }
     print(json.dumps(line))
     return 0
+
+
+def bench_ppo_rollout(torch, bdist, dev, args, rank, ws):
+    """configs[4]: PPO rollout collection with the policy on the device — 2^19 envs per GPU
+    (2^22 over 8), observations -> features -> MLP (bf16 autocast) -> masked categorical -> env step,
+    GAE at the end; nothing leaves the device.  Reported as whole-job env-steps/s, max over ranks."""
+    from balatro_gym_b200 import BalatroVecEnv
+    from balatro_gym_b200.rollout import RolloutCollector, make_policy, featurize, masked_sample, gae
+    n, T = args.ppo_envs, args.ppo_steps
+    vec = BalatroVecEnv(n, device=dev, seed=1, env_offset=rank * n)
+    vec.reset(); vec.randomize_c3(0)
+    for _ in range(32):
+        vec.step(random_policy=True)
+    policy = make_policy(device=dev, seed=0)
+    roll = RolloutCollector(vec, policy, n_steps=T, seed=1)
+    roll.collect()                                   # warm-up: cuBLAS heuristics, allocator
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    bdist.barrier(); torch.cuda.synchronize(dev)
+    ev[0].record(); roll.collect(); ev[1].record()
+    torch.cuda.synchronize(dev)
+    ms = bdist.max_over_ranks(ev[0].elapsed_time(ev[1]), dev)
+
+    def timed(fn, reps=5):
+        fn(); torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+    obs0 = roll.obs[0]
+    with torch.no_grad():
+        t_feat = timed(lambda: featurize(obs0, out=roll._feats))
+        def fwd():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return policy(roll._feats)
+        t_fwd = timed(fwd)
+        logits = fwd()[0].float().contiguous()
+        t_samp = timed(lambda: masked_sample(logits, obs0, seed=1, step=0, actions=roll.actions[0], logp=roll.logp[0], entropy=roll.entropy[0]))
+        t_step = timed(lambda: vec.step(roll.actions[0], want_info=False))
+        t_copy = timed(lambda: roll.obs[1].copy_(vec.obs_buf))
+        t_gae = timed(lambda: gae(roll.rewards, roll.values, roll.dones, 0.99, 0.95, roll.advantages, roll.returns))
+    if rank != 0:
+        return None
+    return {"value": ws * n * T / (ms / 1e3), "unit": "env-steps/s", "envs_per_gpu": n, "rollout_steps": T,
+            "ms_per_step": ms / T,
+            "breakdown_ms": {"featurize": t_feat, "policy_forward_bf16": t_fwd, "masked_sample": t_samp, "env_step": t_step,
+                             "obs_copy": t_copy, "gae_whole_rollout": t_gae},
+            "policy": "BalatroFeaturesExtractor topology (416|10|21 -> 224 -> 512 -> 512) + pi/vf [256,256] heads, bf16 autocast (cuBLAS)",
+            "note": "the MLP forward (policy side, library GEMMs) dominates; the env path's own kernels are featurize + masked_sample + env_step + gae"}
 
 
 def bench_hands(torch, b, dev, peak, args):
@@ -358,6 +414,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-hands", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--ppo-envs", type=int, default=1 << 19, help="envs per GPU of the PPO rollout block (configs[4]: 2^22 over 8)")
+    ap.add_argument("--ppo-steps", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -43,6 +43,9 @@ extern "C" {
 #define BGYM_INFO_BYTES  32
 #define BGYM_DRAWS_BYTES 256
 #define BGYM_NUM_ACTIONS 60
+#define BGYM_FEATURE_DIM 448   /* bgym_featurize row: 416 one-hot + 10 joker ids + 21 scalars + 1 pad */
+#define BGYM_DT_F32  0
+#define BGYM_DT_BF16 1
 #define BGYM_NUM_HAND_TYPES 12
 #define BGYM_MAX_HAND 8
 #define BGYM_DECK_SLOTS 52
@@ -302,6 +305,34 @@ int bgym_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8_t
  * ret_acc / len_acc are n-sized per-env accumulators owned by the caller. */
 int bgym_episode_stats(const double* reward, const uint8_t* terminated, double* ret_acc,
                        uint32_t* len_acc, double* stats, int64_t n, void* stream);
+
+/* ---- on-device PPO rollout collection (config 5) ------------------ */
+/* Observation records -> the dense input of the reference's BalatroFeaturesExtractor.forward
+ * (train_balatro_agent.py:84-113): per env BGYM_FEATURE_DIM columns =
+ *   [0,416)   one-hot of hand[8] over 52 card codes (empty slot = all zero)      :86-93
+ *   [416,426) joker_ids[10] as floats                                            :98
+ *   [426,447) chips_scored/1e6, chips_needed/1e5, progress_ratio, money/100, ante/10, round/3,
+ *             hands_left/10, discards_left/5, hand_levels[12]/10, phase/3        :102-113
+ *   [447]     0 (pad to a 16-byte multiple)
+ * features: n x BGYM_FEATURE_DIM of dtype BGYM_DT_F32 or BGYM_DT_BF16, 16-byte aligned. */
+int bgym_featurize(const BgymObs* obs, void* features, int64_t n, int dtype, void* stream);
+
+/* Masked categorical policy head: for each env, softmax over logits[60] restricted to the legal
+ * actions of obs[i].action_mask_bits; draws one action by inverse CDF, returns its log-probability
+ * and the entropy of the masked distribution (entropy may be NULL).  The uniform comes from
+ * uniforms[i] when given, else from Philox keyed (seed, sample key) at counter (env_offset + i, step).
+ * logits: n x 60, dtype BGYM_DT_F32 (16-byte aligned rows) or BGYM_DT_BF16 (8-byte aligned).
+ * An env with no legal action gets action 0, logp 0, entropy 0. */
+int bgym_masked_sample(const void* logits, int dtype, const BgymObs* obs, const float* uniforms,
+                       uint32_t seed, uint64_t step, int64_t env_offset,
+                       int32_t* actions, float* logp, float* entropy, int64_t n, void* stream);
+
+/* GAE(gamma, lambda) over a [T, n] rollout stored time-major (what SB3's
+ * RolloutBuffer.compute_returns_and_advantage computes for the reference's PPO,
+ * train_balatro_agent.py:328-336): values is [T+1, n] (last row = bootstrap value),
+ * dones[t] = 1 when step t ended its episode. */
+int bgym_gae(const float* rewards, const float* values, const uint8_t* dones, float gamma, float lam,
+             float* advantages, float* returns, int64_t T, int64_t n, void* stream);
 
 /* ---- host-buffer entry points (what a non-torch caller binds) ------------------ */
 typedef struct BgymVec BgymVec;

@@ -42,6 +42,12 @@ def _worker(rank, ws, port, total, q):
     stats = torch.tensor([count, float(seeds.sum()), 2.0 * count, 10.0 * count, -1.0 * count, 0, 0, 0], dtype=torch.float64)
     bdist.allreduce_stats(stats)
     t = bdist.max_over_ranks(float(rank + 1))
+    # policy-side gradient averaging of the data-parallel PPO update (rollout.ppo_update)
+    lin = torch.nn.Linear(3, 2)
+    for p in lin.parameters():
+        p.grad = torch.full_like(p, float(rank + 1))
+    bdist.allreduce_mean_grads(list(lin.parameters()))
+    assert all(bool((p.grad == 1.5).all()) for p in lin.parameters())
     bdist.barrier()
     q.put((rank, start, count, stats.tolist(), t, seeds[:3].tolist()))
     dist.destroy_process_group()
