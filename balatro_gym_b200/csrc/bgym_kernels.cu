@@ -160,27 +160,57 @@ struct ScoreRng {  // native draws of the scoring path: Philox keyed by (seed), 
   }
 };
 
-// Fast path of config 2 (five-card plays, no modifiers, no jokers, level-1 hands): everything is
-// static — five byte extracts, register histograms, one table lookup — and each thread scores two
-// hands per iteration so two independent load->compute->store chains are in flight.
+// Fast path of config 2 (five-card plays, no modifiers, no jokers, level-1 hands).  The kernel is
+// bound by instruction issue before HBM (one thread per hand, 32 B per hand), so classification is
+// done on 13-bit rank masks instead of the general 4-bit-per-rank histogram: s_k = ranks seen at
+// least k times, updated with four LOP3 per card; flush by XOR-ing the packed codes against card 0;
+// a straight is five distinct ranks whose mask is 31 << lowest, or the wheel.  Same priority order
+// as classify() (balatro_game.py:40-93) for ANY five codes, duplicates included.
+__device__ __forceinline__ void score_hand5(const ScoreArgs& a, long long i, const uint2 cw) {
+  const uint32_t c0 = cw.x & 0xFF, c1 = (cw.x >> 8) & 0xFF, c2 = (cw.x >> 16) & 0xFF, c3 = cw.x >> 24, c4 = cw.y & 0xFF;
+  const uint32_t m1 = 1u << (c1 >> 2), m2 = 1u << (c2 >> 2), m3 = 1u << (c3 >> 2), m4 = 1u << (c4 >> 2);
+  uint32_t s1 = 1u << (c0 >> 2), s2 = 0, s3 = 0, s4 = 0;
+  s2 |= s1 & m1; s1 |= m1;
+  s3 |= s2 & m2; s2 |= s1 & m2; s1 |= m2;
+  s4 |= s3 & m3; s3 |= s2 & m3; s2 |= s1 & m3; s1 |= m3;
+  s4 |= s3 & m4; s3 |= s2 & m4; s2 |= s1 & m4; s1 |= m4;
+  const bool flush = ((((cw.x ^ (c0 * 0x01010101u)) & 0x03030303u) | ((cw.y ^ c0) & 3u)) == 0u);
+  const uint32_t low = s1 & (0u - s1);
+  const bool straight = (s2 == 0u) && (s1 == low * 31u || s1 == 0x100Fu);
+  const int n2 = __popc(s2);
+  int ht = n2 == 1 ? BGYM_HT_ONE_PAIR : BGYM_HT_HIGH_CARD;
+  ht = n2 == 2 ? BGYM_HT_TWO_PAIR : ht;
+  ht = s3 ? BGYM_HT_THREE_KIND : ht;
+  ht = straight ? BGYM_HT_STRAIGHT : ht;
+  ht = flush ? BGYM_HT_FLUSH : ht;
+  ht = (s3 && n2 == 2) ? BGYM_HT_FULL_HOUSE : ht;
+  ht = s4 ? BGYM_HT_FOUR_KIND : ht;
+  ht = (straight && flush) ? BGYM_HT_STRAIGHT_FLUSH : ht;
+  const int chip_sum = card_chips(c0, 0, 0) + card_chips(c1, 0, 0) + card_chips(c2, 0, 0) + card_chips(c3, 0, 0) + card_chips(c4, 0, 0);
+  const int chips = c_base_chips[ht] + chip_sum, mult = c_base_mult[ht];
+  a.hand_type[i] = (uint8_t)ht;
+  a.chips[i] = chips;
+  a.mult[i] = mult;
+  a.score[i] = (long long)chips * mult;   // x_mult == 1.0: int(chips * mult * 1.0)
+  if (a.x_mult) a.x_mult[i] = 1.0;
+  if (a.money) a.money[i] = 0;
+}
+
+// four hands per thread and iteration: the four 8-byte loads are issued before any of them is used,
+// so a resident warp keeps 1 KB in flight instead of 256 B (the pass was load-latency bound)
+constexpr int HANDS5_UNROLL = 4;
 __global__ void __launch_bounds__(256) score_hands5_kernel(ScoreArgs a) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-    uint2 cw = __ldg(reinterpret_cast<const uint2*>(a.cards8) + i);
-    int c0 = cw.x & 0xFF, c1 = (cw.x >> 8) & 0xFF, c2 = (cw.x >> 16) & 0xFF, c3 = cw.x >> 24, c4 = cw.y & 0xFF;
-    HandHist hist;
-    hist.clear();
-    hist.add(c0); hist.add(c1); hist.add(c2); hist.add(c3); hist.add(c4);
-    int chip_sum = card_chips(c0, 0, 0) + card_chips(c1, 0, 0) + card_chips(c2, 0, 0) + card_chips(c3, 0, 0) + card_chips(c4, 0, 0);
-    int ht = classify(hist);
-    int chips = c_base_chips[ht] + chip_sum, mult = c_base_mult[ht];
-    a.hand_type[i] = (uint8_t)ht;
-    a.chips[i] = chips;
-    a.mult[i] = mult;
-    a.score[i] = (long long)chips * mult;   // x_mult == 1.0: int(chips * mult * 1.0)
-    if (a.x_mult) a.x_mult[i] = 1.0;
-    if (a.money) a.money[i] = 0;
+  const uint2* src = reinterpret_cast<const uint2*>(a.cards8);
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (HANDS5_UNROLL - 1) * stride < a.n; i += HANDS5_UNROLL * stride) {
+    uint2 cw[HANDS5_UNROLL];
+#pragma unroll
+    for (int u = 0; u < HANDS5_UNROLL; u++) cw[u] = __ldg(src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < HANDS5_UNROLL; u++) score_hand5(a, i + u * stride, cw[u]);
   }
+  for (; i < a.n; i += stride) score_hand5(a, i, __ldg(src + i));
 }
 
 __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
