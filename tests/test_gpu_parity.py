@@ -113,6 +113,41 @@ def test_cuda_vs_oracle_native_rollout(torch, n, steps, c3):
     assert int(v.state_numpy()["episode"].sum()) > 0      # autoreset happened
 
 
+@pytest.mark.parametrize("n", [1, 31, 33, 97])
+def test_ragged_and_tiny_slabs_match_the_oracle(torch, n):
+    """Slab sizes that are not a multiple of the 32-env tile, down to a single env."""
+    from balatro_gym_b200 import BalatroVecEnv
+    from oracle import coracle
+    v = BalatroVecEnv(n, seed=11, autoreset=True)
+    v.reset()
+    ov = coracle.OracleVec(n)
+    ov.reset(np.arange(11, n + 11))
+    assert_records_equal(ov.state, v.state_numpy(), L.STATE_DTYPE, (), "reset state")
+    for t in range(150):
+        v.step(random_policy=True)
+        oact = np.zeros(n, np.int32)
+        coracle.step(ov.state, oact, ov.obs, ov.reward, ov.terminated, ov.truncated, ov.info, None,
+                     flags=L.FLAG_AUTORESET | 4)
+        assert np.array_equal(oact, v.actions.cpu().numpy())
+        _compare_step(v, ov, t)
+
+
+def test_empty_slab_calls_are_noops(torch):
+    import balatro_gym_b200 as b
+    lib = b.load()
+    z = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    p = z.data_ptr()
+    assert lib.bgym_reset(p, p, p, None, p, None, 0, 0, None) == 0
+    assert lib.bgym_step(p, p, p, None, p, p, p, p, None, 0, 0, None) == 0
+    assert lib.bgym_action_mask(p, p, p, 0, None) == 0
+    assert lib.bgym_featurize(p, p, 0, 0, None) == 0
+    assert lib.bgym_gae(p, p, p, 0.99, 0.95, p, p, 0, 0, None) == 0
+    # argument errors come back as negative codes with a message, never a crash
+    assert lib.bgym_step(None, p, p, None, p, p, p, p, None, 4, 0, None) < 0
+    assert b"bgym_step" in lib.bgym_last_error()
+    assert lib.bgym_featurize(p, p, 4, 7, None) < 0
+
+
 def test_sampler_kernel_and_mask_kernel(torch):
     from balatro_gym_b200 import BalatroVecEnv
     from oracle import coracle
