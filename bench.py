@@ -22,6 +22,11 @@ import sys
 import threading
 import time
 
+# rank 0's stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at
+# NCCL_DEBUG=VERSION) out of it; an explicit INFO/TRACE request is left alone
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
