@@ -105,12 +105,21 @@ struct Draws {
   const BgymDraws* tape;  // nullptr = native
   uint32_t seed, ctr;
   uint32_t buf0, buf1, buf2, buf3;
+  uint32_t first;
   int pos, iu, ik;
 
   __device__ __forceinline__ void init(uint32_t seed_, uint32_t ctr_, const BgymDraws* tape_) {
-    tape = tape_; seed = seed_; ctr = ctr_; pos = 4; iu = 0; ik = 0;
+    tape = tape_; seed = seed_; ctr = ctr_; first = ctr_; pos = 4; iu = 0; ik = 0;
     buf0 = buf1 = buf2 = buf3 = 0;
   }
+  // Generate the first block now, with the whole warp converged, instead of inside whichever divergent
+  // branch draws first.  The stream is unchanged: an unused prefetched block is not counted (blocks()).
+  __device__ __forceinline__ void prefetch() {
+    uint4 b = philox4x32_10(ctr, 0, 0, 0, seed, BGYM_PHILOX_KEY1);
+    if (!tape) { ctr++; buf0 = b.x; buf1 = b.y; buf2 = b.z; buf3 = b.w; pos = 0; }
+  }
+  // number of blocks consumed so far (= the counter to store back)
+  __device__ __forceinline__ uint32_t blocks() const { return (pos == 0 && ctr == first + 1) ? first : ctr; }
   __device__ __forceinline__ uint32_t word() {
     if (pos == 4) {
       uint4 b = philox4x32_10(ctr++, 0, 0, 0, seed, BGYM_PHILOX_KEY1);
@@ -155,7 +164,10 @@ __device__ __forceinline__ int shuffle_j_from_block(uint4 b, int i) {
   uint32_t w0 = ((i - 1) & 1) ? b.z : b.x, w1 = ((i - 1) & 1) ? b.w : b.y;
   uint32_t un = (uint32_t)(i + 1);
   uint64_t m = (uint64_t)w0 * un;
-  if ((uint32_t)m < (0u - un) % un) m = (uint64_t)w1 * un;
+  uint32_t l = (uint32_t)m;
+  if (l < un) {                       // p < 52 / 2^32: only then is the exact threshold needed
+    if (l < (0u - un) % un) m = (uint64_t)w1 * un;
+  }
   return (int)(m >> 32);
 }
 

@@ -670,6 +670,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
   h.ep_len++;
   Draws rng;
   rng.init(h.rng_seed, h.rng_ctr, tape);
+  if (CATS & CAT_PLAY) rng.prefetch();   // glass / lucky rolls of the card loop: one converged Philox call
   double reward = 0.0;
   int terminated = 0;
   int rare_op = RARE_NONE, rare_arg = 0;
@@ -964,7 +965,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     if (rare_op != RARE_ADVANCE) { reward = ro.reward; info.error_code = ro.err; terminated = ro.terminated; }
   }
   if ((CATS & (CAT_PLAY | CAT_DISCARD | CAT_OTHER)) && hand_changed) refresh_hand_codes(h, rec);
-  if (!tape) h.rng_ctr = rng.ctr;
+  if (!tape) h.rng_ctr = rng.blocks();
   reward_out = reward;
   terminated_out = terminated;
 }
