@@ -153,14 +153,44 @@ class RolloutCollector:
         self._feats = torch.empty((n, FEATURE_DIM), dtype=torch.bfloat16 if autocast else torch.float32, device=dev)
         self.global_step = 0
 
+    def refresh_inference_weights(self):
+        """bf16 copies of the policy's weights for the no-grad rollout forward (call after each update;
+        `collect` does it on entry)."""
+        torch = self.torch
+        with torch.no_grad():
+            self._w16 = {k: v.detach().to(torch.bfloat16).contiguous() for k, v in self.policy.state_dict().items()}
+
+    def _mlp(self, x, prefix, n_layers, last_plain=False, act="relu"):
+        """Sequential of Linear(+activation) from the cached bf16 weights; ReLU layers use the cuBLASLt
+        bias+ReLU epilogue (`torch._addmm_activation`), so an activation never makes its own HBM round trip."""
+        torch = self.torch
+        w = self._w16
+        for li in range(n_layers):
+            W, b = w[f"{prefix}.{2 * li}.weight"], w[f"{prefix}.{2 * li}.bias"]
+            last = li == n_layers - 1
+            if last and last_plain:
+                x = torch.addmm(b, x, W.t())
+            elif act == "relu":
+                x = torch._addmm_activation(b, x, W.t(), use_gelu=False)
+            else:
+                x = torch.tanh_(torch.addmm(b, x, W.t()))
+        return x
+
     def _forward(self, obs_records):
         torch = self.torch
         featurize(obs_records, out=self._feats)
-        if self.autocast:
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                logits, value = self.policy(self._feats)
-        else:
+        if not self.autocast:
             logits, value = self.policy(self._feats)
+            return logits.float().contiguous(), value.float()
+        f = self._feats
+        # the column slices are strided views: cuBLAS takes them as they are for the hand block (lda = 448);
+        # the two narrow blocks are copied (10 and 21 columns: their row pitch is not 16-byte aligned)
+        h = self._mlp(f[:, :416], "hand_net", 2)
+        j = self._mlp(f[:, 416:426].contiguous(), "joker_net", 2)
+        g = self._mlp(f[:, 426:447].contiguous(), "game_state_net", 2)
+        z = self._mlp(torch.cat([h, j, g], dim=1), "combined_net", 2)
+        logits = self._mlp(z, "pi", 3, last_plain=True, act="tanh")
+        value = self._mlp(z, "vf", 3, last_plain=True, act="tanh").squeeze(-1)
         return logits.float().contiguous(), value.float()
 
     def collect(self):
@@ -168,6 +198,8 @@ class RolloutCollector:
         torch = self.torch
         vec = self.vec
         with torch.no_grad():
+            if self.autocast:
+                self.refresh_inference_weights()
             self.obs[0].copy_(vec.obs_buf)
             for t in range(self.T):
                 logits, value = self._forward(self.obs[t])

@@ -331,11 +331,9 @@ def bench_ppo_rollout(torch, bdist, dev, args, rank, ws):
     obs0 = roll.obs[0]
     with torch.no_grad():
         t_feat = timed(lambda: featurize(obs0, out=roll._feats))
-        def fwd():
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                return policy(roll._feats)
-        t_fwd = timed(fwd)
-        logits = fwd()[0].float().contiguous()
+        roll.refresh_inference_weights()
+        t_fwd = timed(lambda: roll._forward(obs0)) - t_feat      # _forward = featurize + MLP
+        logits = roll._forward(obs0)[0]
         t_samp = timed(lambda: masked_sample(logits, obs0, seed=1, step=0, actions=roll.actions[0], logp=roll.logp[0], entropy=roll.entropy[0]))
         t_step = timed(lambda: vec.step(roll.actions[0], want_info=False))
         t_copy = timed(lambda: roll.obs[1].copy_(vec.obs_buf))
@@ -346,7 +344,7 @@ def bench_ppo_rollout(torch, bdist, dev, args, rank, ws):
             "ms_per_step": ms / T,
             "breakdown_ms": {"featurize": t_feat, "policy_forward_bf16": t_fwd, "masked_sample": t_samp, "env_step": t_step,
                              "obs_copy": t_copy, "gae_whole_rollout": t_gae},
-            "policy": "BalatroFeaturesExtractor topology (416|10|21 -> 224 -> 512 -> 512) + pi/vf [256,256] heads, bf16 autocast (cuBLAS)",
+            "policy": "BalatroFeaturesExtractor topology (416|10|21 -> 224 -> 512 -> 512) + pi/vf [256,256] heads, bf16 weights, cuBLASLt bias+ReLU epilogues",
             "note": "the MLP forward (policy side, library GEMMs) dominates; the env path's own kernels are featurize + masked_sample + env_step + gae"}
 
 
