@@ -213,7 +213,33 @@ __global__ void __launch_bounds__(256) score_hands5_kernel(ScoreArgs a) {
   for (; i < a.n; i += stride) score_hand5(a, i, __ldg(src + i));
 }
 
+// One joker-effect row as registers (BgymJokerFx is 16 bytes: kind u8 | pad | arg u16 || chips i16 | mult i16 || xmult f32 || money i16 | pad)
+struct FxRow {
+  uint4 q;
+  __device__ __forceinline__ int kind() const { return (int)(q.x & 0xFF); }
+  __device__ __forceinline__ int arg() const { return (int)(q.x >> 16); }
+  __device__ __forceinline__ int chips() const { return (int)(short)(q.y & 0xFFFF); }
+  __device__ __forceinline__ int mult() const { return (int)(short)(q.y >> 16); }
+  __device__ __forceinline__ float xmult() const { return __uint_as_float(q.z); }
+  __device__ __forceinline__ int money() const { return (int)(short)(q.w & 0xFFFF); }
+};
+
+// The effect table is staged in SHARED memory and each hand's (up to 8) rows are lifted into
+// registers once: per-lane joker ids index the table divergently, which the constant cache serialises
+// (one replay per distinct address in the warp) — in the (card x joker) loop that was ~99 % of the
+// kernel's time.
 __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
+  __shared__ uint4 s_fx[BGYM_NUM_JOKERS + 1];
+  for (int t = threadIdx.x; t < BGYM_NUM_JOKERS + 1; t += blockDim.x) {
+    const BgymJokerFx f = c_joker_fx[t];
+    uint4 q;
+    q.x = (uint32_t)f.kind | ((uint32_t)f.arg << 16);
+    q.y = (uint32_t)(uint16_t)f.chips | ((uint32_t)(uint16_t)f.mult << 16);
+    q.z = __float_as_uint(f.xmult);
+    q.w = (uint32_t)(uint16_t)f.money;
+    s_fx[t] = q;
+  }
+  __syncthreads();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
     uint2 cw = __ldg(reinterpret_cast<const uint2*>(a.cards8) + i);
     uint64_t cards = u64_of(cw.x, cw.y);
@@ -263,30 +289,39 @@ __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
       if (a.ctx) cx = a.ctx[i];
       bool table_names = (a.flags & BGYM_SCORE_TABLE_NAMES) != 0;
       ScoreRng rng; rng.seed = a.seed; rng.ctr = 0; rng.index = (unsigned long long)i; rng.pos = 4;
-      // individual phase: card-major, joker-minor (:173-209)
+      // individual phase: card-major, joker-minor (:173-209).  A card is a bit set {rank 0..14} u
+      // {16 + suit 0..4}; a rank-set / face / suit joker is a mask over the same bits, so "fires" is one
+      // AND.  The loops are not unrolled (one small body instead of 64 copies) and everything but the
+      // Bloodstone roll is branch-free.
       int ind_chips = 0, ind_mult = 0; double ind_x = 1.0;
+#pragma unroll 1
       for (int c = 0; c < nc; c++) {
-        int rank = byte_at(rank8, c), suit = nib_at(suit8, c);
+        const uint32_t cardbits = (1u << byte_at(rank8, c)) | (1u << (16 + nib_at(suit8, c)));
+#pragma unroll 1
         for (int j = 0; j < nj; j++) {
-          const BgymJokerFx fx = c_joker_fx[byte_at(jk, j)];
-          bool fire = false;
-          if (fx.kind == BGYM_FX_IND_RANKSET || fx.kind == BGYM_FX_IND_FACE) fire = (fx.arg >> rank) & 1;
-          else if (fx.kind == BGYM_FX_IND_SUIT) {
-            fire = suit == (fx.arg & 3);
-            if (fx.arg & 0x80) {  // Bloodstone: one roll per (card, joker) pair (:161)
-              bool hit = cx.use_replay ? ((cx.bloodstone_bits >> c) & 1) : (rng.u01() < 0.5);
-              fire = fire && hit;
-            }
+          const FxRow fx = {s_fx[min(byte_at(jk, j), BGYM_NUM_JOKERS)]};
+          const int kind = fx.kind(), arg = fx.arg();
+          const uint32_t jm = (kind == BGYM_FX_IND_RANKSET || kind == BGYM_FX_IND_FACE) ? (uint32_t)arg
+                            : (kind == BGYM_FX_IND_SUIT) ? (1u << (16 + (arg & 3))) : 0u;
+          bool fire = (cardbits & jm) != 0u;
+          if (kind == BGYM_FX_IND_SUIT && (arg & 0x80)) {  // Bloodstone: one roll per (card, joker) pair, matching suit or not (:161)
+            const bool hit = cx.use_replay ? ((cx.bloodstone_bits >> c) & 1) : (rng.u01() < 0.5);
+            fire = fire && hit;
           }
-          if (fire) { ind_chips += fx.chips; ind_mult += fx.mult; ind_x *= (double)fx.xmult; money += fx.money; }
+          ind_chips += fire ? fx.chips() : 0;
+          ind_mult += fire ? fx.mult() : 0;
+          money += fire ? fx.money() : 0;
+          ind_x *= fire ? (double)fx.xmult() : 1.0;
         }
       }
       chips += ind_chips; mult += ind_mult; x_mult *= ind_x;
       // main phase, joker order (:211-244)
       int misprint_seen = 0;
       int n_suit_names = __popc(suit_present) + (int)stone_present;
+#pragma unroll 1
       for (int j = 0; j < nj; j++) {
-        const BgymJokerFx fx = c_joker_fx[byte_at(jk, j)];
+        const FxRow row = {s_fx[min(byte_at(jk, j), BGYM_NUM_JOKERS)]};
+        struct { int kind, arg, chips, mult; float xmult; } fx = {row.kind(), row.arg(), row.chips(), row.mult(), row.xmult()};
         int ec = 0, em = 0; double ex = 1.0;
         switch (fx.kind) {
           case BGYM_FX_MAIN_ALWAYS: ec = fx.chips; em = fx.mult; ex = fx.xmult; break;
