@@ -294,24 +294,32 @@ __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
       // AND.  The loops are not unrolled (one small body instead of 64 copies) and everything but the
       // Bloodstone roll is branch-free.
       int ind_chips = 0, ind_mult = 0; double ind_x = 1.0;
+      // per-joker match masks, once per hand (individual-phase jokers are ~8 % of the ids: most are 0);
+      // bit 31 marks Bloodstone, which rolls for every card whether the suit matches or not
+      uint32_t jm[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t w0 = j < nj ? s_fx[min(byte_at(jk, j), BGYM_NUM_JOKERS)].x : 0u;
+        const int kind = (int)(w0 & 0xFF), arg = (int)(w0 >> 16);
+        jm[j] = (kind == BGYM_FX_IND_RANKSET || kind == BGYM_FX_IND_FACE) ? (uint32_t)arg
+              : (kind == BGYM_FX_IND_SUIT) ? ((1u << (16 + (arg & 3))) | ((arg & 0x80) ? 0x80000000u : 0u)) : 0u;
+      }
 #pragma unroll 1
       for (int c = 0; c < nc; c++) {
-        const uint32_t cardbits = (1u << byte_at(rank8, c)) | (1u << (16 + nib_at(suit8, c)));
-#pragma unroll 1
-        for (int j = 0; j < nj; j++) {
-          const FxRow fx = {s_fx[min(byte_at(jk, j), BGYM_NUM_JOKERS)]};
-          const int kind = fx.kind(), arg = fx.arg();
-          const uint32_t jm = (kind == BGYM_FX_IND_RANKSET || kind == BGYM_FX_IND_FACE) ? (uint32_t)arg
-                            : (kind == BGYM_FX_IND_SUIT) ? (1u << (16 + (arg & 3))) : 0u;
-          bool fire = (cardbits & jm) != 0u;
-          if (kind == BGYM_FX_IND_SUIT && (arg & 0x80)) {  // Bloodstone: one roll per (card, joker) pair, matching suit or not (:161)
-            const bool hit = cx.use_replay ? ((cx.bloodstone_bits >> c) & 1) : (rng.u01() < 0.5);
-            fire = fire && hit;
+        const uint32_t cardbits = (1u << byte_at(rank8, c)) | (1u << (16 + nib_at(suit8, c))) | 0x80000000u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (cardbits & jm[j]) {          // rare: the card matches, or the joker is Bloodstone
+            bool fire = (cardbits & jm[j] & 0x7FFFFFFFu) != 0u;
+            if (jm[j] & 0x80000000u) {     // Bloodstone: one roll per (card, joker) pair (:161)
+              const bool hit = cx.use_replay ? ((cx.bloodstone_bits >> c) & 1) : (rng.u01() < 0.5);
+              fire = fire && hit;
+            }
+            if (fire) {
+              const FxRow fx = {s_fx[min(byte_at(jk, j), BGYM_NUM_JOKERS)]};
+              ind_chips += fx.chips(); ind_mult += fx.mult(); money += fx.money(); ind_x *= (double)fx.xmult();
+            }
           }
-          ind_chips += fire ? fx.chips() : 0;
-          ind_mult += fire ? fx.mult() : 0;
-          money += fire ? fx.money() : 0;
-          ind_x *= fire ? (double)fx.xmult() : 1.0;
         }
       }
       chips += ind_chips; mult += ind_mult; x_mult *= ind_x;
