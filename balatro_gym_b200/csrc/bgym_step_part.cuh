@@ -120,6 +120,10 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
     bulk_g2s(hot_base + st * MAIN_HOT_TILE, a.hot + t * 32 * BGYM_HOT_BYTES, bytes, &bars[st]);
   };
   if (STAGES == 2 && lane == 0 && warp_gid < n_tiles) issue_load(warp_gid, 0);
+  // the action of this lane's env in the NEXT tile is fetched one iteration ahead (its DRAM latency would
+  // otherwise sit between the tile's arrival and the first use)
+  int action_next = 0;
+  if (!fused_policy && warp_gid * 32 + lane < a.n) action_next = __ldg(a.actions + warp_gid * 32 + lane);
   for (long long tile = warp_gid; tile < n_tiles; tile += warp_cnt, stage = (STAGES == 2) ? (stage ^ 1) : 0) {
     const long long e = tile * 32 + lane;
     const bool active = e < a.n;
@@ -133,8 +137,11 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
       if (STAGES == 2) { if (tile + warp_cnt < n_tiles) issue_load(tile + warp_cnt, stage ^ 1); }
       else issue_load(tile, 0);
     }
-    int action = 0;
-    if (active && !fused_policy) action = __ldg(a.actions + e);
+    int action = action_next;
+    {
+      const long long en = (tile + warp_cnt) * 32 + lane;
+      if (!fused_policy && en < a.n) action_next = __ldg(a.actions + en);
+    }
     __syncwarp();   // lane 0 has passed its wait: the obs buffer is free for every lane
     mbar_wait(&bars[stage], (parity_bits >> stage) & 1);
     parity_bits ^= 1u << stage;
