@@ -217,13 +217,86 @@ constexpr int GATHER_CTA_SMEM = GATHER_WARPS * GATHER_WARP_SMEM + 16 * GATHER_WA
 #endif
 constexpr int GATHER_CTAS_PER_SM = BGYM_GATHER_CTAS;
 
+// One gather tile: lane `lane` serves listed env `e` (active lanes only; n_active of them, lanes 0..n_active-1).
+// hot_buf / cold_buf are the warp's 32-slot staging tiles, the observation tile is staged over them.
+template <int CATS, int LIST, bool STORE_COLD>
+__device__ __forceinline__ void gather_tile(const StepArgs& a, uint8_t* hot_buf, uint8_t* cold_buf, uint64_t* bar,
+                                            uint32_t& parity, long long e, bool active, int n_active, int lane) {
+  const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
+  const bool fused_policy = (a.flags & BGYM_FLAG_RANDOM_POLICY) != 0;
+  uint8_t* hot = hot_buf + lane * BGYM_HOT_BYTES;
+  uint8_t* cold = cold_buf + lane * BGYM_COLD_BYTES;
+  uint8_t* obs_s = hot_buf + lane * BGYM_OBS_BYTES;     // overlay, see GATHER_WARP_SMEM
+  bulk_wait_read0();    // this lane's bulk stores of the previous tile have read their slots
+  __syncwarp();
+  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)n_active * (BGYM_HOT_BYTES + BGYM_COLD_BYTES));
+  __syncwarp();
+  if (active) {
+    bulk_g2s(hot, a.hot + e * BGYM_HOT_BYTES, BGYM_HOT_BYTES, bar);
+    bulk_g2s(cold, a.cold + e * BGYM_COLD_BYTES, BGYM_COLD_BYTES, bar);
+  }
+  // L2 loads: in the fused step kernel these actions may have been written by a producer warp of another SM
+  int action = (active && !(fused_policy && LIST == 2)) ? __ldcg(a.actions + e) : 0;
+  mbar_wait(bar, parity);
+  parity ^= 1;
+
+  Hot h;
+  double reward = 0.0;
+  int terminated = 0;
+  StepInfo info;
+  bool want_reset = false;
+  uint32_t new_seed = 0;
+  if (active) {
+    unpack_hot(hot, h);
+    uint64_t m0 = action_mask(h, cold);
+    if (fused_policy && LIST == 2) {
+      // envs outside PLAY phase (and guard-terminated ones) sample here, where the mask is complete;
+      // PLAY-phase envs already carry the action the main pass sampled
+      if (h.phase == BGYM_PHASE_PLAY) action = __ldcg(a.actions + e);
+      else { action = policy_action(h, m0); if (a.actions_out) a.actions_out[e] = action; }
+    }
+    // the OTHER list also receives SELECT / never-legal ids of envs the main pass does not serve
+    step_env<(LIST == 2) ? (CAT_OTHER | CAT_SELECT) : CATS>(h, hot, cold, action, m0, a.draws ? a.draws + e : nullptr,
+                                                          reward, terminated, info);
+    if (terminated && (a.flags & BGYM_FLAG_AUTORESET)) {
+      uint32_t episode = h.episode + 1;
+      new_seed = next_episode_seed(h.rng_seed);
+      reset_hot(h, new_seed);
+      h.episode = episode;
+      info.flags |= BGYM_F_AUTORESET_DONE;
+      want_reset = true;
+    }
+  }
+  if (a.flags & BGYM_FLAG_AUTORESET) autoreset_warp(want_reset, new_seed, cold, lane);
+  ShopObs so;
+  uint64_t m1 = 0;
+  if (active) {
+    pack_hot(hot, h);
+    if (with_obs) { m1 = action_mask(h, cold); obs_shop_block(h, cold, so); }   // last reads of the cold slot
+    write_step_outputs(a, e, reward, terminated, info);
+  }
+  fence_async_smem();   // every lane: a cooperative reset writes other lanes' slots
+  __syncwarp();
+  if (active) {
+    bulk_s2g(a.hot + e * BGYM_HOT_BYTES, hot, BGYM_HOT_BYTES);
+    if (STORE_COLD || want_reset) bulk_s2g(a.cold + e * BGYM_COLD_BYTES, cold, BGYM_COLD_BYTES);
+    bulk_commit();
+  }
+  if (with_obs) {
+    bulk_wait_read0();  // this lane's record stores have read shared memory ...
+    __syncwarp();       // ... and so have all the others': the tile is free for the observations
+    if (active) write_obs_regs(h, so, m1, obs_s);
+    fence_async_smem();
+    if (active) { bulk_s2g(a.obs + e * BGYM_OBS_BYTES, obs_s, BGYM_OBS_BYTES); bulk_commit(); }
+  }
+}
+
 template <int CATS, int LIST, bool STORE_COLD>
 __global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_step_gather_kernel(StepArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* hot_buf = smem + warp * GATHER_WARP_SMEM;
   uint8_t* cold_buf = hot_buf + 32 * BGYM_HOT_BYTES;
-  uint8_t* obs_buf = hot_buf;     // overlay, see GATHER_WARP_SMEM
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GATHER_WARPS * GATHER_WARP_SMEM) + warp * 2;
   if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
   __syncwarp();
@@ -232,77 +305,12 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_ste
   const int n_tiles = (count + 31) >> 5;
   const int warp_gid = blockIdx.x * GATHER_WARPS + warp;
   const int warp_cnt = gridDim.x * GATHER_WARPS;
-  const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
-  const bool fused_policy = (a.flags & BGYM_FLAG_RANDOM_POLICY) != 0;
   uint32_t parity = 0;
   for (int tile = warp_gid; tile < n_tiles; tile += warp_cnt) {
     const int idx = tile * 32 + lane;
     const bool active = idx < count;
     const long long e = active ? (long long)list[idx] : -1;
-    uint8_t* hot = hot_buf + lane * BGYM_HOT_BYTES;
-    uint8_t* cold = cold_buf + lane * BGYM_COLD_BYTES;
-    uint8_t* obs_s = obs_buf + lane * BGYM_OBS_BYTES;
-    bulk_wait_read0();    // this lane's bulk stores of the previous tile have read their slots
-    __syncwarp();
-    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)min(32, count - tile * 32) * (BGYM_HOT_BYTES + BGYM_COLD_BYTES));
-    __syncwarp();
-    if (active) {
-      bulk_g2s(hot, a.hot + e * BGYM_HOT_BYTES, BGYM_HOT_BYTES, bar);
-      bulk_g2s(cold, a.cold + e * BGYM_COLD_BYTES, BGYM_COLD_BYTES, bar);
-    }
-    int action = (active && !(fused_policy && LIST == 2)) ? a.actions[e] : 0;
-    mbar_wait(bar, parity);
-    parity ^= 1;
-
-    Hot h;
-    double reward = 0.0;
-    int terminated = 0;
-    StepInfo info;
-    bool want_reset = false;
-    uint32_t new_seed = 0;
-    if (active) {
-      unpack_hot(hot, h);
-      uint64_t m0 = action_mask(h, cold);
-      if (fused_policy && LIST == 2) {
-        // envs outside PLAY phase (and guard-terminated ones) sample here, where the mask is complete;
-        // PLAY-phase envs already carry the action the main pass sampled
-        if (h.phase == BGYM_PHASE_PLAY) action = a.actions[e];
-        else { action = policy_action(h, m0); if (a.actions_out) a.actions_out[e] = action; }
-      }
-      // the OTHER list also receives SELECT / never-legal ids of envs the main pass does not serve
-      step_env<(LIST == 2) ? (CAT_OTHER | CAT_SELECT) : CATS>(h, hot, cold, action, m0, a.draws ? a.draws + e : nullptr,
-                                                            reward, terminated, info);
-      if (terminated && (a.flags & BGYM_FLAG_AUTORESET)) {
-        uint32_t episode = h.episode + 1;
-        new_seed = next_episode_seed(h.rng_seed);
-        reset_hot(h, new_seed);
-        h.episode = episode;
-        info.flags |= BGYM_F_AUTORESET_DONE;
-        want_reset = true;
-      }
-    }
-    if (a.flags & BGYM_FLAG_AUTORESET) autoreset_warp(want_reset, new_seed, cold, lane);
-    ShopObs so;
-    uint64_t m1 = 0;
-    if (active) {
-      pack_hot(hot, h);
-      if (with_obs) { m1 = action_mask(h, cold); obs_shop_block(h, cold, so); }   // last reads of the cold slot
-      write_step_outputs(a, e, reward, terminated, info);
-    }
-    fence_async_smem();   // every lane: a cooperative reset writes other lanes' slots
-    __syncwarp();
-    if (active) {
-      bulk_s2g(a.hot + e * BGYM_HOT_BYTES, hot, BGYM_HOT_BYTES);
-      if (STORE_COLD || want_reset) bulk_s2g(a.cold + e * BGYM_COLD_BYTES, cold, BGYM_COLD_BYTES);
-      bulk_commit();
-    }
-    if (with_obs) {
-      bulk_wait_read0();  // this lane's record stores have read shared memory ...
-      __syncwarp();       // ... and so have all the others': the tile is free for the observations
-      if (active) write_obs_regs(h, so, m1, obs_s);
-      fence_async_smem();
-      if (active) { bulk_s2g(a.obs + e * BGYM_OBS_BYTES, obs_s, BGYM_OBS_BYTES); bulk_commit(); }
-    }
+    gather_tile<CATS, LIST, STORE_COLD>(a, hot_buf, cold_buf, bar, parity, e, active, min(32, count - tile * 32), lane);
   }
   bulk_wait0();
 }
