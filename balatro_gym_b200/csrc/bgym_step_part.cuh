@@ -235,7 +235,7 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, uint8_t* hot_buf,
     bulk_g2s(hot, a.hot + e * BGYM_HOT_BYTES, BGYM_HOT_BYTES, bar);
     bulk_g2s(cold, a.cold + e * BGYM_COLD_BYTES, BGYM_COLD_BYTES, bar);
   }
-  // L2 loads: in the fused step kernel these actions may have been written by a producer warp of another SM
+  // read once, straight from L2
   int action = (active && !(fused_policy && LIST == 2)) ? __ldcg(a.actions + e) : 0;
   mbar_wait(bar, parity);
   parity ^= 1;
