@@ -386,7 +386,9 @@ def bench_hands(torch, b, dev, peak, args):
     e2e = 3 * n / (time.perf_counter() - t0)
     res = {"metric": "hands_scored_per_sec", "value": value, "unit": "hands/s", "n_hands": n, "ms_per_launch": ms,
            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                        "bytes_per_unit": B_HAND, "kernel": "score_hands_kernel"},
+                        "bytes_per_unit": B_HAND, "kernel": "score_hands5_kernel",
+                        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^24 hands (ncu, profiles/): 134 + 233 MB
+                        "traffic": 367.5e6 * n / float(1 << 24)},
            "e2e": {"value": e2e, "unit": "hands/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * n}}
     res["with_jokers"] = bench_hands_jokers(torch, dev, peak)
     if not args.no_cpu_baseline:
