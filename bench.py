@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -201,7 +201,6 @@ def run_ours(args):
     ev[2 * K + 1].record()
     torch.cuda.synchronize(dev)
     bdist.barrier()
-    clk = clocks.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[2 * K + 1])
     step_kernel_ms = sum(ev[1 + 2 * k].elapsed_time(ev[2 + 2 * k]) for k in range(K)) / K
     total_ms = bdist.max_over_ranks(total_ms, dev)
@@ -219,6 +218,9 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     fused_ms = bdist.max_over_ranks(e0.elapsed_time(e1), dev)
     fused_value = ws * n * K / (fused_ms / 1000.0)
+    # clocks were sampled (nvidia-smi, 20 ms period) from the start of the timed steps to here: both loops run
+    # the same step kernels back to back
+    clk = clocks.stop() if rank == 0 else None
 
     # episode statistics (K6): folded per step on the device over a short untimed rollout, then ONE tiny
     # all-reduce per rollout, off the step path
