@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 #include "bgym_env.cuh"
 
@@ -472,13 +473,20 @@ static int cuda_rc(cudaError_t e, const char* where) {
   return (int)e;
 }
 
-static int g_sm_count = 0;
-static bool g_attr_set = false;
+// Per-device one-time setup (kernel attributes are per device) under a mutex: the entry points may be called
+// from several host threads / for several devices of one process.  g_sm_count is the calling thread's device.
+constexpr int BGYM_MAX_DEVICES = 64;
+static std::mutex g_mu;
+static bool g_dev_ready[BGYM_MAX_DEVICES];
+static int g_dev_sms[BGYM_MAX_DEVICES];
+static thread_local int g_sm_count = 0;
 static int ensure_device_setup() {
-  if (g_attr_set) return 0;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_rc(e, "cudaGetDevice");
+  if (dev < 0 || dev >= BGYM_MAX_DEVICES) return set_err(BGYM_E_ARG, "device ordinal out of range");
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (g_dev_ready[dev]) { g_sm_count = g_dev_sms[dev]; return 0; }
   e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return cuda_rc(e, "cudaDeviceGetAttribute");
 #define BGYM_SET_SMEM(kernel, bytes)                                                                 \
@@ -491,7 +499,8 @@ static int ensure_device_setup() {
   BGYM_SET_SMEM((env_step_gather_kernel<CAT_DISCARD, 1, false>), GATHER_CTA_SMEM)
   BGYM_SET_SMEM((env_step_gather_kernel<CAT_OTHER, 2, true>), GATHER_CTA_SMEM)
 #undef BGYM_SET_SMEM
-  g_attr_set = true;
+  g_dev_sms[dev] = g_sm_count;
+  g_dev_ready[dev] = true;
   return 0;
 }
 
@@ -501,16 +510,17 @@ static bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintp
 // concurrent gather passes, one set per (device, stream)
 struct PartScratch { int dev; void* stream; long long cap; int* lists; int* counters;
                      cudaStream_t side[2]; cudaEvent_t ev_main, ev_side[2]; bool streams_ok; };
-static PartScratch g_scratch[16];
+static PartScratch g_scratch[64];
 static int g_n_scratch = 0;
 static int get_part_scratch(long long n, void* stream, PartScratch** out) {
   int dev = 0;
   cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_mu);
   PartScratch* sc = nullptr;
   for (int i = 0; i < g_n_scratch; i++)
     if (g_scratch[i].dev == dev && g_scratch[i].stream == stream) sc = &g_scratch[i];
   if (!sc) {
-    if (g_n_scratch == 16) return set_err(BGYM_E_ARG, "bgym_step: too many (device, stream) pairs in use");
+    if (g_n_scratch == 64) return set_err(BGYM_E_ARG, "bgym_step: too many (device, stream) pairs in use");
     sc = &g_scratch[g_n_scratch++];
     sc->dev = dev; sc->stream = stream; sc->cap = 0; sc->lists = nullptr; sc->counters = nullptr;
     sc->streams_ok = cudaStreamCreateWithFlags(&sc->side[0], cudaStreamNonBlocking) == cudaSuccess &&
