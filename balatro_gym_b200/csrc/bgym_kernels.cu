@@ -50,6 +50,9 @@ struct StepArgs {
 };
 
 }  // namespace bgym
+#ifndef BGYM_SMALL_N_DEFAULT
+#define BGYM_SMALL_N_DEFAULT 65536
+#endif
 #include "bgym_step_part.cuh"
 #include "bgym_rollout.cuh"
 namespace bgym {
@@ -498,6 +501,7 @@ static int ensure_device_setup() {
   BGYM_SET_SMEM((env_step_gather_kernel<CAT_PLAY, 0, true>), GATHER_CTA_SMEM)
   BGYM_SET_SMEM((env_step_gather_kernel<CAT_DISCARD, 1, false>), GATHER_CTA_SMEM)
   BGYM_SET_SMEM((env_step_gather_kernel<CAT_OTHER, 2, true>), GATHER_CTA_SMEM)
+  BGYM_SET_SMEM(env_step_small_kernel, GATHER_CTA_SMEM)
 #undef BGYM_SET_SMEM
   g_dev_sms[dev] = g_sm_count;
   g_dev_ready[dev] = true;
@@ -606,6 +610,12 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
   static int tcalls = 0;
   if (timing && tcalls == 0 && tsum[0] == 0) for (int i = 0; i < 3; i++) cudaEventCreate(&tev[i]);
   if (timing) cudaEventRecord(tev[0], s);
+  // small slabs: one launch (bgym_step_part.cuh, env_step_small_kernel); BGYM_SMALL_N overrides the threshold
+  static const long long small_n = []() { const char* v = getenv("BGYM_SMALL_N"); return v ? atoll(v) : (long long)BGYM_SMALL_N_DEFAULT; }();
+  if (n <= small_n && !timing) {
+    env_step_small_kernel<<<tile_grid(n, GATHER_WARPS, GATHER_CTAS_PER_SM), GATHER_WARPS * 32, GATHER_CTA_SMEM, s>>>(a);
+    return cuda_rc(cudaGetLastError(), "bgym_step launch");
+  }
   cudaError_t e = cudaMemsetAsync(sc->counters, 0, 4 * PART_CTR_STRIDE * sizeof(int), s);
   if (e != cudaSuccess) return cuda_rc(e, "cudaMemsetAsync(step counters)");
   static const int main_stages = (getenv("BGYM_MAIN_STAGES") && getenv("BGYM_MAIN_STAGES")[0] == '1') ? 1 : 2;
@@ -767,6 +777,9 @@ struct BgymVec {
   // pinned staging
   uint8_t *h_hot, *h_cold, *h_obs, *h_term, *h_trunc, *h_decks; double* h_reward; BgymInfo* h_info; int32_t* h_actions;
   uint32_t* h_seeds; BgymDraws* h_draws;
+  // the step's outputs (obs | reward | info | terminated | truncated) live in ONE device block with a pinned mirror,
+  // so a step is one device->host copy however many outputs are asked for
+  uint8_t *d_block, *h_block; size_t block_bytes;
 };
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_rc(_e, #x); } while (0)
@@ -782,13 +795,19 @@ int bgym_vec_create(BgymVec** out, int64_t n, int device) {
   v->n = n; v->device = device;
   CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&v->d_hot, n * BGYM_HOT_BYTES)); CK(cudaMalloc(&v->d_cold, n * BGYM_COLD_BYTES));
-  CK(cudaMalloc(&v->d_obs, n * BGYM_OBS_BYTES));
-  CK(cudaMalloc(&v->d_term, n)); CK(cudaMalloc(&v->d_trunc, n)); CK(cudaMalloc(&v->d_decks, n * 52));
-  CK(cudaMalloc(&v->d_reward, n * 8)); CK(cudaMalloc(&v->d_info, n * BGYM_INFO_BYTES)); CK(cudaMalloc(&v->d_actions, n * 4));
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t off_rew = up16((size_t)n * BGYM_OBS_BYTES), off_info = up16(off_rew + (size_t)n * 8);
+  const size_t off_term = up16(off_info + (size_t)n * BGYM_INFO_BYTES), off_trunc = up16(off_term + (size_t)n);
+  v->block_bytes = up16(off_trunc + (size_t)n);
+  CK(cudaMalloc(&v->d_block, v->block_bytes)); CK(cudaMallocHost(&v->h_block, v->block_bytes));
+  v->d_obs = v->d_block; v->d_reward = reinterpret_cast<double*>(v->d_block + off_rew);
+  v->d_info = reinterpret_cast<BgymInfo*>(v->d_block + off_info); v->d_term = v->d_block + off_term; v->d_trunc = v->d_block + off_trunc;
+  v->h_obs = v->h_block; v->h_reward = reinterpret_cast<double*>(v->h_block + off_rew);
+  v->h_info = reinterpret_cast<BgymInfo*>(v->h_block + off_info); v->h_term = v->h_block + off_term; v->h_trunc = v->h_block + off_trunc;
+  CK(cudaMalloc(&v->d_decks, n * 52)); CK(cudaMalloc(&v->d_actions, n * 4));
   CK(cudaMalloc(&v->d_seeds, n * 4)); CK(cudaMalloc(&v->d_draws, n * BGYM_DRAWS_BYTES));
   CK(cudaMallocHost(&v->h_hot, n * BGYM_HOT_BYTES)); CK(cudaMallocHost(&v->h_cold, n * BGYM_COLD_BYTES));
-  CK(cudaMallocHost(&v->h_obs, n * BGYM_OBS_BYTES)); CK(cudaMallocHost(&v->h_term, n)); CK(cudaMallocHost(&v->h_trunc, n));
-  CK(cudaMallocHost(&v->h_decks, n * 52)); CK(cudaMallocHost(&v->h_reward, n * 8)); CK(cudaMallocHost(&v->h_info, n * BGYM_INFO_BYTES));
+  CK(cudaMallocHost(&v->h_decks, n * 52));
   CK(cudaMallocHost(&v->h_actions, n * 4)); CK(cudaMallocHost(&v->h_seeds, n * 4)); CK(cudaMallocHost(&v->h_draws, n * BGYM_DRAWS_BYTES));
   CK(cudaMemsetAsync(v->d_hot, 0, n * BGYM_HOT_BYTES, v->stream));
   CK(cudaMemsetAsync(v->d_cold, 0, n * BGYM_COLD_BYTES, v->stream));
@@ -800,10 +819,10 @@ int bgym_vec_destroy(BgymVec* v) {
   if (!v) return 0;
   cudaSetDevice(v->device);
   cudaStreamSynchronize(v->stream);
-  cudaFree(v->d_hot); cudaFree(v->d_cold); cudaFree(v->d_obs); cudaFree(v->d_term); cudaFree(v->d_trunc); cudaFree(v->d_decks);
-  cudaFree(v->d_reward); cudaFree(v->d_info); cudaFree(v->d_actions); cudaFree(v->d_seeds); cudaFree(v->d_draws);
-  cudaFreeHost(v->h_hot); cudaFreeHost(v->h_cold); cudaFreeHost(v->h_obs); cudaFreeHost(v->h_term); cudaFreeHost(v->h_trunc);
-  cudaFreeHost(v->h_decks); cudaFreeHost(v->h_reward); cudaFreeHost(v->h_info); cudaFreeHost(v->h_actions);
+  cudaFree(v->d_hot); cudaFree(v->d_cold); cudaFree(v->d_block); cudaFree(v->d_decks);
+  cudaFree(v->d_actions); cudaFree(v->d_seeds); cudaFree(v->d_draws);
+  cudaFreeHost(v->h_hot); cudaFreeHost(v->h_cold); cudaFreeHost(v->h_block);
+  cudaFreeHost(v->h_decks); cudaFreeHost(v->h_actions);
   cudaFreeHost(v->h_seeds); cudaFreeHost(v->h_draws);
   cudaStreamDestroy(v->stream);
   delete v;
@@ -843,11 +862,12 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
                      draws ? v->d_draws : nullptr, reinterpret_cast<BgymObs*>(v->d_obs), v->d_reward, v->d_term, v->d_trunc,
                      v->d_info, v->n, flags & ~BGYM_FLAG_NO_OBS, v->stream);
   if (rc) return rc;
-  if (obs_out) CK(cudaMemcpyAsync(v->h_obs, v->d_obs, v->n * BGYM_OBS_BYTES, cudaMemcpyDeviceToHost, v->stream));
-  if (reward_out) CK(cudaMemcpyAsync(v->h_reward, v->d_reward, v->n * 8, cudaMemcpyDeviceToHost, v->stream));
-  if (terminated_out) CK(cudaMemcpyAsync(v->h_term, v->d_term, v->n, cudaMemcpyDeviceToHost, v->stream));
-  if (truncated_out) CK(cudaMemcpyAsync(v->h_trunc, v->d_trunc, v->n, cudaMemcpyDeviceToHost, v->stream));
-  if (info_out) CK(cudaMemcpyAsync(v->h_info, v->d_info, v->n * BGYM_INFO_BYTES, cudaMemcpyDeviceToHost, v->stream));
+  if (obs_out) {
+    CK(cudaMemcpyAsync(v->h_block, v->d_block, v->block_bytes, cudaMemcpyDeviceToHost, v->stream));      // everything, one copy
+  } else {   // without observations: skip the 240 B/env part
+    const size_t off = reinterpret_cast<uint8_t*>(v->d_reward) - v->d_block;
+    CK(cudaMemcpyAsync(v->h_block + off, v->d_block + off, v->block_bytes - off, cudaMemcpyDeviceToHost, v->stream));
+  }
   CK(cudaStreamSynchronize(v->stream));
   if (obs_out) memcpy(obs_out, v->h_obs, v->n * BGYM_OBS_BYTES);
   if (reward_out) memcpy(reward_out, v->h_reward, v->n * 8);

@@ -236,7 +236,7 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, uint8_t* hot_buf,
     bulk_g2s(cold, a.cold + e * BGYM_COLD_BYTES, BGYM_COLD_BYTES, bar);
   }
   // read once, straight from L2
-  int action = (active && !(fused_policy && LIST == 2)) ? __ldcg(a.actions + e) : 0;
+  int action = (active && !(fused_policy && LIST >= 2)) ? __ldcg(a.actions + e) : 0;
   mbar_wait(bar, parity);
   parity ^= 1;
 
@@ -249,10 +249,11 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, uint8_t* hot_buf,
   if (active) {
     unpack_hot(hot, h);
     uint64_t m0 = action_mask(h, cold);
-    if (fused_policy && LIST == 2) {
+    if (fused_policy && LIST >= 2) {
       // envs outside PLAY phase (and guard-terminated ones) sample here, where the mask is complete;
-      // PLAY-phase envs already carry the action the main pass sampled
-      if (h.phase == BGYM_PHASE_PLAY) action = __ldcg(a.actions + e);
+      // PLAY-phase envs already carry the action the main pass sampled (LIST 3 = small-slab kernel: no
+      // main pass ran, every env samples here)
+      if (LIST == 2 && h.phase == BGYM_PHASE_PLAY) action = __ldcg(a.actions + e);
       else { action = policy_action(h, m0); if (a.actions_out) a.actions_out[e] = action; }
     }
     // the OTHER list also receives SELECT / never-legal ids of envs the main pass does not serve
@@ -289,6 +290,28 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, uint8_t* hot_buf,
     fence_async_smem();
     if (active) { bulk_s2g(a.obs + e * BGYM_OBS_BYTES, obs_s, BGYM_OBS_BYTES); bulk_commit(); }
   }
+}
+
+// Small slabs (n <= BGYM_SMALL_N): ONE launch, every env served by the gather tile code with all action
+// categories compiled in (LIST 3 = identity list).  A step of a few thousand envs is bound by launch latency
+// and one tile's dependent chain, not by bandwidth or instruction fetch, so the five-launch split only adds
+// to it: this is what makes the N = 1 Gymnasium facade usable.
+__global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_step_small_kernel(StepArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* hot_buf = smem + warp * GATHER_WARP_SMEM;
+  uint8_t* cold_buf = hot_buf + 32 * BGYM_HOT_BYTES;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GATHER_WARPS * GATHER_WARP_SMEM) + warp * 2;
+  if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+  __syncwarp();
+  const long long n_tiles = (a.n + 31) >> 5;
+  uint32_t parity = 0;
+  for (long long tile = (long long)blockIdx.x * GATHER_WARPS + warp; tile < n_tiles; tile += (long long)gridDim.x * GATHER_WARPS) {
+    const long long e = tile * 32 + lane;
+    const bool active = e < a.n;
+    gather_tile<CAT_ALL, 3, true>(a, hot_buf, cold_buf, bar, parity, active ? e : -1, active, (int)min(32LL, a.n - tile * 32), lane);
+  }
+  bulk_wait0();
 }
 
 template <int CATS, int LIST, bool STORE_COLD>

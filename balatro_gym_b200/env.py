@@ -25,7 +25,6 @@ from typing import Optional
 import numpy as np
 
 from . import layout as L
-from .vec_env import BalatroVecEnv
 
 try:  # real gymnasium if present, else the constructor-only stand-ins
     import gymnasium as _gym
@@ -98,19 +97,41 @@ def info_dict(inf) -> dict:
 
 
 class BalatroEnv(_EnvBase):
+    """One env behind the Gymnasium protocol, driven through the C-ABI's host-buffer handle
+    (`bgym_vec_create / reset_host / step_host`, include/bgym.h): per step ONE C call = action H2D, one kernel
+    launch (small-slab step), one D2H of {obs, reward, info, flags} into numpy buffers.  No torch involved."""
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 4}
 
-    def __init__(self, *, render_mode: Optional[str] = None, seed: Optional[int] = None, device="cuda"):
+    def __init__(self, *, render_mode: Optional[str] = None, seed: Optional[int] = None, device=0):
+        import ctypes as C
+        from . import _lib
         self.render_mode = render_mode
         self._seed = seed if seed else int(np.random.randint(1, 2 ** 31 - 1))
-        self.vec = BalatroVecEnv(1, device=device, seed=self._seed, autoreset=False)
+        self.lib = _lib.load()
+        if self.lib.bgym_device_count() < 1:
+            raise _lib.BgymError("balatro_gym_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if isinstance(device, str):
+            device = int(device.split(":")[1]) if ":" in device else 0
+        elif not isinstance(device, int):        # torch.device
+            device = device.index or 0
+        self._h = C.c_void_p()
+        _lib.check(self.lib.bgym_vec_create(C.byref(self._h), 1, int(device)), "bgym_vec_create")
+        self._act = np.zeros(1, dtype=np.int32)
+        self._seeds = np.zeros(1, dtype=np.uint32)
+        self._obs_rec = np.zeros(1, dtype=L.OBS_DTYPE)
+        self._rew = np.zeros(1, dtype=np.float64)
+        self._term = np.zeros(1, dtype=np.uint8)
+        self._trunc = np.zeros(1, dtype=np.uint8)
+        self._info = np.zeros(1, dtype=L.INFO_DTYPE)
+        self._state = np.zeros(1, dtype=L.STATE_DTYPE)
+        self._p = {k: getattr(self, "_" + k).ctypes.data for k in ("act", "seeds", "obs_rec", "rew", "term", "trunc", "info", "state")}
         self.action_space = _spaces.Discrete(L.NUM_ACTIONS)
         self.observation_space = observation_space()
         self.reset()
 
     # -- conversions ---------------------------------------------------------------------------------
     def _obs(self):
-        rec = self.vec.obs_numpy()[0]
+        rec = self._obs_rec[0]
         out = {}
         for k in L.OBS_KEYS:
             v = rec[k]
@@ -121,34 +142,40 @@ class BalatroEnv(_EnvBase):
         if seed is not None and seed != 0:
             self._seed = int(seed)
         mode = (options or {}).get("shuffle", "reference")
-        torch = self.vec.torch
-        seeds = torch.tensor([self._seed], dtype=torch.int64)
-        decks = torch.from_numpy(reference_deck(self._seed)[None, :]) if mode == "reference" else None
-        self.vec.reset(seeds=seeds, decks52=decks)
+        self._seeds[0] = self._seed % (2 ** 32)
+        deck = reference_deck(self._seed) if mode == "reference" else None
+        from . import _lib
+        rc = self.lib.bgym_vec_reset_host(self._h, self._p["seeds"], None if deck is None else deck.ctypes.data, self._p["obs_rec"])
+        _lib.check(rc, "bgym_vec_reset_host")
         return self._obs(), {}
 
     def step(self, action: int):
-        torch = self.vec.torch
-        a = torch.tensor([int(action)], dtype=torch.int32, device=self.vec.device)
-        self.vec.step(a)
-        info = info_dict(self.vec.info_numpy()[0])
-        reward = float(self.vec.reward.cpu()[0])
-        terminated = bool(self.vec.terminated.cpu()[0])
-        return self._obs(), reward, terminated, False, info
+        self._act[0] = int(action)
+        p = self._p
+        rc = self.lib.bgym_vec_step_host(self._h, p["act"], None, p["obs_rec"], p["rew"], p["term"], p["trunc"], p["info"], 0)
+        if rc:
+            from . import _lib
+            _lib.check(rc, "bgym_vec_step_host")
+        return self._obs(), float(self._rew[0]), bool(self._term[0]), False, info_dict(self._info[0])
 
     def action_masks(self):
-        return self._obs()["action_mask"].astype(bool)
+        return self._obs_rec[0]["action_mask"].astype(bool)
 
     @property
     def state(self):
         """Host copy of the env's state record (numpy record of layout.STATE_DTYPE)."""
-        return self.vec.state_numpy()[0]
+        from . import _lib
+        _lib.check(self.lib.bgym_vec_get_state(self._h, self._p["state"]), "bgym_vec_get_state")
+        return self._state[0].copy()
 
     def save_state(self):
-        return self.vec.save_state()
+        return {"state": self.state, "obs": self._obs_rec.copy()}
 
     def load_state(self, saved):
-        self.vec.load_state(saved)
+        from . import _lib
+        self._state[0] = saved["state"]
+        _lib.check(self.lib.bgym_vec_set_state(self._h, self._p["state"]), "bgym_vec_set_state")
+        self._obs_rec[:] = saved["obs"]
 
     def render(self):
         if self.render_mode != "human":
@@ -158,7 +185,16 @@ class BalatroEnv(_EnvBase):
               f"| total {s['chips_scored']} | ${s['money']} | hands {s['hands_left']} discards {s['discards_left']}")
 
     def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self.lib.bgym_vec_destroy(h)
         return None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def make_balatro_env(**kwargs):

@@ -179,7 +179,10 @@ class BalatroSB3VecEnv(_VecEnvBase):
         terminated = self._h_term.numpy().astype(bool)
         info_rec = self._h_info.numpy().reshape(-1).view(L.INFO_DTYPE)
         truncated = np.zeros(self.num_envs, dtype=bool)
-        infos: List[dict] = [info_dict(info_rec[i]) for i in range(self.num_envs)]
+        # most steps carry nothing in info (a card toggle): only records with an error or flags become dicts
+        infos: List[dict] = [{} for _ in range(self.num_envs)]
+        for i in np.flatnonzero((info_rec["error_code"] != 0) | (info_rec["flags"] != 0)):
+            infos[i] = info_dict(info_rec[i])
 
         # SafeBalatroEnv guards (train_balatro_fixed.py:240-258)
         self._ep_len += 1

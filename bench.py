@@ -271,6 +271,7 @@ def run_ours(args):
 
     if rank != 0:
         return 0
+    host_facing = None if args.no_facade else bench_host_facing()
     cpu_base = None
     if not args.no_cpu_baseline and ws == 1:
         cpu_base, _ = cpu_env_baseline("c4", rounds=3, warmup_rounds=1, steps_per_round=4096)
@@ -295,6 +296,7 @@ def run_ours(args):
                           "note": "policy sampled inside the step kernel (one launch per step)"},
         "hands": hands,
         "ppo_rollout": ppo,
+        "host_facing": host_facing,
         "episode_stats": {"episodes": float(stats[0]), "mean_return": float(stats[1] / max(1.0, float(stats[0]))),
                           "mean_length": float(stats[2] / max(1.0, float(stats[0])))},
     }
@@ -410,6 +412,46 @@ def bench_hands(torch, b, dev, peak, args):
     return res
 
 
+def bench_host_facing():
+    """The reference-shaped entry points a Python caller drives from the host, random legal play: the N = 1
+    Gymnasium facade (one C call per step through bgym_vec_step_host) and the SB3 VecEnv adapter at the
+    reference trainers' slab sizes.  Wall clock, everything included (observation dicts built on the host)."""
+    import numpy as np
+    from balatro_gym_b200.env import BalatroEnv
+    from balatro_gym_b200.sb3_vec_env import BalatroSB3VecEnv
+    rng = np.random.default_rng(0)
+    env = BalatroEnv(seed=3)
+    obs, _ = env.reset(seed=3)
+
+    def run(k):
+        nonlocal obs
+        t0 = time.perf_counter()
+        for _ in range(k):
+            obs, r, term, trunc, info = env.step(int(rng.choice(np.flatnonzero(obs["action_mask"]))))
+            if term:
+                obs, _ = env.reset()
+        return k / (time.perf_counter() - t0)
+    run(200)
+    out = {"gym_facade_n1": {"value": run(4000), "unit": "env-steps/s"}}
+    env.close()
+    for n in (8, 64):
+        v = BalatroSB3VecEnv(n, seed=1)
+        o = v.reset()
+
+        def vrun(k):
+            nonlocal o
+            t0 = time.perf_counter()
+            for _ in range(k):
+                m = o["action_mask"]
+                o, r, d, i = v.step((rng.random(m.shape) * m).argmax(axis=1))
+            return k * n / (time.perf_counter() - t0)
+        vrun(20)
+        out[f"sb3_vec_env_n{n}"] = {"value": vrun(300), "unit": "env-steps/s"}
+        v.close()
+    out["note"] = "reference on one host core: ~1.3e4 env-steps/s per BalatroEnv process (SURVEY 6)"
+    return out
+
+
 def bench_hands_jokers(torch, dev, peak):
     """The general scoring kernel (joker interpreter K4): 2^22 plays of 1..8 cards, 5 distinct random jokers,
     config-3 modifiers, random hand levels.  64 B per hand (+8 joker ids +16 mods +8 x_mult)."""
@@ -457,6 +499,7 @@ def main():
     ap.add_argument("--no-hands", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--no-facade", action="store_true")
     ap.add_argument("--ppo-envs", type=int, default=1 << 19, help="envs per GPU of the PPO rollout block (configs[4]: 2^22 over 8)")
     ap.add_argument("--ppo-steps", type=int, default=16)
     args = ap.parse_args()
