@@ -71,6 +71,7 @@ SYMBOLS = {
     "bgym_vec_create": (_i32, [C.POINTER(_vp), _i64, _i32]),
     "bgym_vec_destroy": (_i32, [_vp]),
     "bgym_vec_reset_host": (_i32, [_vp, _vp, _vp, _vp]),
+    "bgym_vec_reset_masked_host": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "bgym_vec_step_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
     "bgym_vec_pointers": (_i32, [_vp] + [C.POINTER(_vp)] * 5),
     "bgym_vec_get_state": (_i32, [_vp, _vp]),

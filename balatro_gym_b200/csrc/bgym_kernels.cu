@@ -780,6 +780,7 @@ struct BgymVec {
   // the step's outputs (obs | reward | info | terminated | truncated) live in ONE device block with a pinned mirror,
   // so a step is one device->host copy however many outputs are asked for
   uint8_t *d_block, *h_block; size_t block_bytes;
+  uint8_t *d_mask, *h_mask;   // reset mask of bgym_vec_reset_masked_host
 };
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_rc(_e, #x); } while (0)
@@ -805,6 +806,7 @@ int bgym_vec_create(BgymVec** out, int64_t n, int device) {
   v->h_obs = v->h_block; v->h_reward = reinterpret_cast<double*>(v->h_block + off_rew);
   v->h_info = reinterpret_cast<BgymInfo*>(v->h_block + off_info); v->h_term = v->h_block + off_term; v->h_trunc = v->h_block + off_trunc;
   CK(cudaMalloc(&v->d_decks, n * 52)); CK(cudaMalloc(&v->d_actions, n * 4));
+  CK(cudaMalloc(&v->d_mask, n)); CK(cudaMallocHost(&v->h_mask, n));
   CK(cudaMalloc(&v->d_seeds, n * 4)); CK(cudaMalloc(&v->d_draws, n * BGYM_DRAWS_BYTES));
   CK(cudaMallocHost(&v->h_hot, n * BGYM_HOT_BYTES)); CK(cudaMallocHost(&v->h_cold, n * BGYM_COLD_BYTES));
   CK(cudaMallocHost(&v->h_decks, n * 52));
@@ -819,7 +821,7 @@ int bgym_vec_destroy(BgymVec* v) {
   if (!v) return 0;
   cudaSetDevice(v->device);
   cudaStreamSynchronize(v->stream);
-  cudaFree(v->d_hot); cudaFree(v->d_cold); cudaFree(v->d_block); cudaFree(v->d_decks);
+  cudaFree(v->d_hot); cudaFree(v->d_cold); cudaFree(v->d_block); cudaFree(v->d_decks); cudaFree(v->d_mask); cudaFreeHost(v->h_mask);
   cudaFree(v->d_actions); cudaFree(v->d_seeds); cudaFree(v->d_draws);
   cudaFreeHost(v->h_hot); cudaFreeHost(v->h_cold); cudaFreeHost(v->h_block);
   cudaFreeHost(v->h_decks); cudaFreeHost(v->h_actions);
@@ -830,8 +832,16 @@ int bgym_vec_destroy(BgymVec* v) {
 }
 
 int bgym_vec_reset_host(BgymVec* v, const uint32_t* seeds, const uint8_t* decks52, BgymObs* obs_out) {
+  return bgym_vec_reset_masked_host(v, nullptr, seeds, decks52, obs_out);
+}
+
+int bgym_vec_reset_masked_host(BgymVec* v, const uint8_t* reset_mask, const uint32_t* seeds, const uint8_t* decks52, BgymObs* obs_out) {
   if (!v || !seeds) return set_err(BGYM_E_ARG, "bgym_vec_reset_host: bad arguments");
   CK(cudaSetDevice(v->device));
+  if (reset_mask) {
+    memcpy(v->h_mask, reset_mask, v->n);
+    CK(cudaMemcpyAsync(v->d_mask, v->h_mask, v->n, cudaMemcpyHostToDevice, v->stream));
+  }
   memcpy(v->h_seeds, seeds, v->n * 4);
   CK(cudaMemcpyAsync(v->d_seeds, v->h_seeds, v->n * 4, cudaMemcpyHostToDevice, v->stream));
   if (decks52) {
@@ -839,7 +849,8 @@ int bgym_vec_reset_host(BgymVec* v, const uint32_t* seeds, const uint8_t* decks5
     CK(cudaMemcpyAsync(v->d_decks, v->h_decks, v->n * 52, cudaMemcpyHostToDevice, v->stream));
   }
   int rc = bgym_reset(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymCold*>(v->d_cold),
-                      reinterpret_cast<BgymObs*>(v->d_obs), nullptr, v->d_seeds, decks52 ? v->d_decks : nullptr, v->n, 0, v->stream);
+                      reinterpret_cast<BgymObs*>(v->d_obs), reset_mask ? v->d_mask : nullptr, v->d_seeds, decks52 ? v->d_decks : nullptr,
+                      v->n, 0, v->stream);
   if (rc) return rc;
   if (obs_out) CK(cudaMemcpyAsync(v->h_obs, v->d_obs, v->n * BGYM_OBS_BYTES, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaStreamSynchronize(v->stream));

@@ -21,10 +21,11 @@ kernels, with the SB3 conventions the trainers rely on
   * `env_method('action_masks')` for sb3-contrib's MaskablePPO, `get_attr / set_attr / seed`.
 
 It subclasses `stable_baselines3.common.vec_env.VecEnv` when SB3 is importable and is a duck-typed
-stand-in otherwise (this image has no SB3).  The device path is the same as `BalatroVecEnv`; what
-this adapter adds is host-side bookkeeping on [num_envs] numpy arrays and ONE device->host copy
-of the observation records per step.  For throughput use `BalatroVecEnv` / `RolloutCollector`,
-which never leave the device.
+stand-in otherwise (this image has no SB3).  It drives the C-ABI's host-buffer handle (`bgym_vec_*`,
+numpy buffers, no torch): a step is ONE C call = actions H2D, the step kernels, ONE device->host copy
+of {observations, rewards, infos, flags}; what the adapter adds is host-side bookkeeping on
+[num_envs] numpy arrays.  For throughput at scale use `BalatroVecEnv` / `RolloutCollector`, which
+never leave the device.
 """
 from __future__ import annotations
 
@@ -36,7 +37,6 @@ import numpy as np
 
 from . import layout as L
 from .env import observation_space as _observation_space, info_dict
-from .vec_env import BalatroVecEnv
 
 try:  # pragma: no cover - not in this image
     from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
@@ -70,11 +70,22 @@ class BalatroSB3VecEnv(_VecEnvBase):
               the first, balatro_env_2.py:384,505-525).
     """
 
-    def __init__(self, num_envs: int, seed: int = 1, device="cuda", shuffle: str = "philox",
+    def __init__(self, num_envs: int, seed: int = 1, device=0, shuffle: str = "philox",
                  max_invalid_actions: Optional[int] = None, max_episode_steps: Optional[int] = None,
                  monitor: bool = True):
+        import ctypes as C
+        from . import _lib
         assert shuffle in ("philox", "reference")
-        self.vec = BalatroVecEnv(num_envs, device=device, seed=seed, autoreset=False)
+        self._libmod = _lib
+        self.lib = _lib.load()
+        if self.lib.bgym_device_count() < 1:
+            raise _lib.BgymError("balatro_gym_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if isinstance(device, str):
+            device = int(device.split(":")[1]) if ":" in device else 0
+        elif not isinstance(device, int):
+            device = device.index or 0
+        self._h = C.c_void_p()
+        _lib.check(self.lib.bgym_vec_create(C.byref(self._h), int(num_envs), int(device)), "bgym_vec_create")
         self.shuffle = shuffle
         self.max_invalid_actions = max_invalid_actions
         self.max_episode_steps = max_episode_steps
@@ -89,14 +100,15 @@ class BalatroSB3VecEnv(_VecEnvBase):
             self.action_space = act_space
             self.reset_infos: List[dict] = [{} for _ in range(num_envs)]
         self.render_mode = None
-        torch = self.vec.torch
         n = num_envs
-        # pinned staging: one copy of the observation records, rewards, flags and infos per step
-        self._h_obs = torch.empty((n, L.OBS_BYTES), dtype=torch.uint8).pin_memory()
-        self._h_reward = torch.empty(n, dtype=torch.float64).pin_memory()
-        self._h_term = torch.empty(n, dtype=torch.uint8).pin_memory()
-        self._h_info = torch.empty((n, L.INFO_BYTES), dtype=torch.uint8).pin_memory()
-        self._actions_dev = torch.zeros(n, dtype=torch.int32, device=self.vec.device)
+        # host buffers the C-ABI fills (one device->host copy per step, include/bgym.h bgym_vec_step_host)
+        self._rec = np.zeros(n, dtype=L.OBS_DTYPE)
+        self._reward = np.zeros(n, dtype=np.float64)
+        self._term = np.zeros(n, dtype=np.uint8)
+        self._trunc = np.zeros(n, dtype=np.uint8)
+        self._info = np.zeros(n, dtype=L.INFO_DTYPE)
+        self._actions = np.zeros(n, dtype=np.int32)
+        self._state = np.zeros(n, dtype=L.STATE_DTYPE)
         self._seeds = (np.arange(n, dtype=np.int64) + seed) % (2 ** 32)
         self._seeds[self._seeds == 0] = 1
         self._seeds = self._seeds.astype(np.uint32)
@@ -108,15 +120,12 @@ class BalatroSB3VecEnv(_VecEnvBase):
         self._pending = None
 
     # -- observation plumbing ----------------------------------------------------------------------
-    def _pull_obs(self):
-        self._h_obs.copy_(self.vec.obs_buf, non_blocking=True)
-
     def _obs_dict(self, rec: np.ndarray) -> dict:
         """Fresh arrays, as `_get_observation` allocates them (balatro_env_2.py:1488)."""
         return {k: np.array(rec[k]) for k in L.OBS_KEYS}
 
     def _host_records(self) -> np.ndarray:
-        return self._h_obs.numpy().reshape(-1).view(L.OBS_DTYPE)
+        return self._rec
 
     def _reference_decks(self, idx: Sequence[int]) -> np.ndarray:
         decks = np.empty((len(idx), 52), dtype=np.uint8)
@@ -127,18 +136,19 @@ class BalatroSB3VecEnv(_VecEnvBase):
         return decks
 
     def _device_reset(self, mask: Optional[np.ndarray]):
-        """Reset the envs selected by mask (all if None) with their current seeds / next decks."""
-        torch = self.vec.torch
+        """Reset the envs selected by mask (all if None) with their current seeds / next decks; the
+        observation records of ALL envs come back in self._rec."""
         n = self.num_envs
         decks = None
         if self.shuffle == "reference":
             idx = np.arange(n) if mask is None else np.flatnonzero(mask)
-            full = np.zeros((n, 52), dtype=np.uint8)
-            full[idx] = self._reference_decks(idx)
-            decks = torch.from_numpy(full)
-        seeds = torch.from_numpy(self._seeds.astype(np.int64))
-        self.vec.reset(seeds=seeds, decks52=decks,
-                       reset_mask=None if mask is None else torch.from_numpy(mask.astype(np.uint8)))
+            decks = np.zeros((n, 52), dtype=np.uint8)
+            decks[idx] = self._reference_decks(idx)
+        m8 = None if mask is None else np.ascontiguousarray(mask.astype(np.uint8))
+        seeds = np.ascontiguousarray(self._seeds)
+        rc = self.lib.bgym_vec_reset_masked_host(self._h, None if m8 is None else m8.ctypes.data, seeds.ctypes.data,
+                                                 None if decks is None else decks.ctypes.data, self._rec.ctypes.data)
+        self._libmod.check(rc, "bgym_vec_reset_masked_host")
 
     # -- VecEnv protocol -----------------------------------------------------------------------------
     def seed(self, seed: Optional[int] = None):
@@ -156,28 +166,22 @@ class BalatroSB3VecEnv(_VecEnvBase):
             for i in range(self.num_envs):   # the reference constructor's own reset() (:384)
                 self._mt[i].shuffle(list(range(52)))
         self._device_reset(None)
-        self._pull_obs()
-        self.vec.torch.cuda.current_stream(self.vec.device).synchronize()
         self._ep_ret[:] = 0; self._ep_len[:] = 0; self._invalid_run[:] = 0
         self.reset_infos = [{} for _ in range(self.num_envs)]
-        return self._obs_dict(self._host_records())
+        return self._obs_dict(self._rec)
 
     def step_async(self, actions):
         self._pending = np.asarray(actions).astype(np.int32).reshape(self.num_envs)
 
     def step_wait(self):
-        torch = self.vec.torch
-        vec = self.vec
-        self._actions_dev.copy_(torch.from_numpy(self._pending), non_blocking=True)
-        vec.step(self._actions_dev)
-        self._pull_obs()
-        self._h_reward.copy_(vec.reward, non_blocking=True)
-        self._h_term.copy_(vec.terminated, non_blocking=True)
-        self._h_info.copy_(vec.info_buf, non_blocking=True)
-        torch.cuda.current_stream(vec.device).synchronize()
-        rewards = self._h_reward.numpy().copy()
-        terminated = self._h_term.numpy().astype(bool)
-        info_rec = self._h_info.numpy().reshape(-1).view(L.INFO_DTYPE)
+        self._actions[:] = self._pending
+        rc = self.lib.bgym_vec_step_host(self._h, self._actions.ctypes.data, None, self._rec.ctypes.data, self._reward.ctypes.data,
+                                         self._term.ctypes.data, self._trunc.ctypes.data, self._info.ctypes.data, 0)
+        if rc:
+            self._libmod.check(rc, "bgym_vec_step_host")
+        rewards = self._reward.copy()
+        terminated = self._term.astype(bool)
+        info_rec = self._info
         truncated = np.zeros(self.num_envs, dtype=bool)
         # most steps carry nothing in info (a card toggle): only records with an error or flags become dicts
         infos: List[dict] = [{} for _ in range(self.num_envs)]
@@ -201,7 +205,7 @@ class BalatroSB3VecEnv(_VecEnvBase):
             truncated = over
         self._ep_ret += rewards
         dones = terminated | truncated
-        obs = self._obs_dict(self._host_records())
+        obs = self._obs_dict(self._rec)
 
         if dones.any():
             idx = np.flatnonzero(dones)
@@ -214,11 +218,8 @@ class BalatroSB3VecEnv(_VecEnvBase):
             if self.shuffle == "philox":
                 self._seeds[idx] = next_episode_seed(self._seeds[idx])
             self._device_reset(dones)
-            self._pull_obs()
-            torch.cuda.current_stream(vec.device).synchronize()
-            rec = self._host_records()
             for k in L.OBS_KEYS:
-                obs[k][idx] = rec[k][idx]
+                obs[k][idx] = self._rec[k][idx]
             self._ep_ret[idx] = 0; self._ep_len[idx] = 0; self._invalid_run[idx] = 0
             for i in idx:
                 self.reset_infos[i] = {}
@@ -229,11 +230,19 @@ class BalatroSB3VecEnv(_VecEnvBase):
         return self.step_wait()
 
     def close(self):
-        self.vec = None
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self.lib.bgym_vec_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def action_masks(self) -> np.ndarray:
         """[num_envs, 60] bool, from the observation records already on the host."""
-        return self._host_records()['action_mask'].astype(bool)
+        return self._rec['action_mask'].astype(bool)
 
     def env_method(self, method_name: str, *args, indices=None, **kwargs):
         idx = self._indices(indices)
@@ -242,13 +251,17 @@ class BalatroSB3VecEnv(_VecEnvBase):
             return [m[i] for i in idx]
         raise AttributeError(f"env_method({method_name!r}) is not available on the device vector env")
 
+    def _pull_state(self) -> np.ndarray:
+        self._libmod.check(self.lib.bgym_vec_get_state(self._h, self._state.ctypes.data), "bgym_vec_get_state")
+        return self._state
+
     def get_attr(self, attr_name: str, indices=None) -> List[Any]:
         idx = self._indices(indices)
         if attr_name == "render_mode":
             return [None for _ in idx]
         if attr_name in L.HOT_FIELD_NAMES or attr_name in L.COLD_FIELD_NAMES:
-            col = self.vec.state_field(attr_name).cpu().numpy()
-            return [col[i] for i in idx]
+            col = self._pull_state()[attr_name]
+            return [col[i].copy() if isinstance(col[i], np.ndarray) else col[i] for i in idx]
         if hasattr(self, attr_name):
             return [getattr(self, attr_name) for _ in idx]
         raise AttributeError(attr_name)
@@ -256,9 +269,9 @@ class BalatroSB3VecEnv(_VecEnvBase):
     def set_attr(self, attr_name: str, value, indices=None):
         idx = self._indices(indices)
         if attr_name in L.HOT_FIELD_NAMES or attr_name in L.COLD_FIELD_NAMES:
-            torch = self.vec.torch
-            view = self.vec.state_field(attr_name)
-            view[torch.as_tensor(idx, device=self.vec.device)] = torch.as_tensor(value, device=self.vec.device).to(view.dtype)
+            st = self._pull_state()
+            st[attr_name][idx] = value
+            self._libmod.check(self.lib.bgym_vec_set_state(self._h, st.ctypes.data), "bgym_vec_set_state")
             return
         setattr(self, attr_name, value)
 

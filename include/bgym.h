@@ -342,6 +342,10 @@ int bgym_vec_destroy(BgymVec* v);
 /* host pointers; copies are done inside on the handle's stream and the call returns
  * after the results are in the host buffers */
 int bgym_vec_reset_host(BgymVec* v, const uint32_t* seeds, const uint8_t* decks52, BgymObs* obs_out);
+/* same, for the envs with reset_mask[i] != 0 only (the auto-reset of a host-driven vector env: SB3's
+ * DummyVecEnv.step_wait resets finished envs one by one); untouched envs get their observation re-emitted */
+int bgym_vec_reset_masked_host(BgymVec* v, const uint8_t* reset_mask, const uint32_t* seeds, const uint8_t* decks52,
+                               BgymObs* obs_out);
 int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draws, BgymObs* obs_out,
                        double* reward_out, uint8_t* terminated_out, uint8_t* truncated_out,
                        BgymInfo* info_out, int flags);
