@@ -59,6 +59,7 @@ SYMBOLS = {
     "bgym_abi_version": (_i32, []),
     "bgym_last_error": (C.c_char_p, []),
     "bgym_device_count": (_i32, []),
+    "bgym_set_option": (_i32, [_i32, _i64]),
     "bgym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "bgym_action_mask": (_i32, [_vp, _vp, _vp, _i64, _vp]),

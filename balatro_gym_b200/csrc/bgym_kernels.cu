@@ -508,6 +508,14 @@ static int ensure_device_setup() {
   return 0;
 }
 
+// slabs of at most this many envs take the one-launch step (BGYM_SMALL_N in the environment, or bgym_set_option)
+static long long g_small_n = -1;
+static long long small_slab_threshold() {
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (g_small_n < 0) { const char* v = getenv("BGYM_SMALL_N"); g_small_n = v ? atoll(v) : (long long)BGYM_SMALL_N_DEFAULT; }
+  return g_small_n;
+}
+
 static bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
 
 // scratch of the partitioned step (deferred-env lists + counters) and the side streams of the
@@ -554,6 +562,15 @@ static int tile_grid(long long n, int warps, int ctas_per_sm) {
 extern "C" {
 
 int bgym_abi_version(void) { return BGYM_ABI_VERSION; }
+int bgym_set_option(int option, int64_t value) {
+  if (option == BGYM_OPT_SMALL_SLAB) {
+    if (value < 0) return set_err(BGYM_E_ARG, "bgym_set_option: BGYM_OPT_SMALL_SLAB needs a value >= 0");
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_small_n = value;
+    return 0;
+  }
+  return set_err(BGYM_E_ARG, "bgym_set_option: unknown option");
+}
 const char* bgym_last_error(void) { return g_err; }
 int bgym_device_count(void) {
   int n = 0;
@@ -611,8 +628,7 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
   if (timing && tcalls == 0 && tsum[0] == 0) for (int i = 0; i < 3; i++) cudaEventCreate(&tev[i]);
   if (timing) cudaEventRecord(tev[0], s);
   // small slabs: one launch (bgym_step_part.cuh, env_step_small_kernel); BGYM_SMALL_N overrides the threshold
-  static const long long small_n = []() { const char* v = getenv("BGYM_SMALL_N"); return v ? atoll(v) : (long long)BGYM_SMALL_N_DEFAULT; }();
-  if (n <= small_n && !timing) {
+  if (n <= small_slab_threshold() && !timing) {
     env_step_small_kernel<<<tile_grid(n, GATHER_WARPS, GATHER_CTAS_PER_SM), GATHER_WARPS * 32, GATHER_CTA_SMEM, s>>>(a);
     return cuda_rc(cudaGetLastError(), "bgym_step launch");
   }

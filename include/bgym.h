@@ -263,6 +263,11 @@ typedef struct BgymScoreCtx {
 /* ---- device entry points ------------------------------------------------------ */
 int bgym_abi_version(void);
 const char* bgym_last_error(void);
+/* process-wide tunables.  BGYM_OPT_SMALL_SLAB: slabs of at most `value` envs are stepped by the one-launch
+ * kernel, larger ones by the main + gather passes (default 65536; 0 = always the multi-pass step).  Both give
+ * identical results; the choice is a launch-latency / throughput trade. */
+#define BGYM_OPT_SMALL_SLAB 1
+int bgym_set_option(int option, int64_t value);
 int bgym_device_count(void);
 
 /* reset: for every env i with reset_mask == NULL || reset_mask[i] != 0 build a fresh episode

@@ -20,6 +20,17 @@ def torch():
     return torch
 
 
+@pytest.fixture(params=["multi_pass", "one_launch"])
+def step_path(request):
+    """Both launch structures of bgym_step give identical results: `multi_pass` = main pass + three gather
+    passes (what large slabs use), `one_launch` = the small-slab kernel (default for n <= 65536)."""
+    import balatro_gym_b200 as b
+    lib = b.load()
+    assert lib.bgym_set_option(1, 0 if request.param == "multi_pass" else 1 << 40) == 0
+    yield request.param
+    assert lib.bgym_set_option(1, 65536) == 0
+
+
 def _loaded_native_lib():
     import balatro_gym_b200 as b
     b.load()
@@ -56,7 +67,7 @@ class CudaStepper:
 
 
 @pytest.mark.parametrize("name", ["c1", "c3", "c4"])
-def test_cuda_replays_reference_trace(torch, name):
+def test_cuda_replays_reference_trace(torch, name, step_path):
     from test_oracle_golden import replay
     tr = load_trace(name)
     n = replay(tr, CudaStepper(torch, tr["action"].shape[1]))
@@ -82,7 +93,7 @@ def _compare_step(v, ov, t, check_info=True):
 
 
 @pytest.mark.parametrize("n,steps,c3", [(4096, 260, False), (4096, 260, True), (1000, 120, True)])
-def test_cuda_vs_oracle_native_rollout(torch, n, steps, c3):
+def test_cuda_vs_oracle_native_rollout(torch, n, steps, c3, step_path):
     """Fused random-legal policy + autoreset on both sides: > 10^6 env-steps compared record by record."""
     from balatro_gym_b200 import BalatroVecEnv
     from oracle import coracle
@@ -114,7 +125,7 @@ def test_cuda_vs_oracle_native_rollout(torch, n, steps, c3):
 
 
 @pytest.mark.parametrize("n", [1, 31, 33, 97])
-def test_ragged_and_tiny_slabs_match_the_oracle(torch, n):
+def test_ragged_and_tiny_slabs_match_the_oracle(torch, n, step_path):
     """Slab sizes that are not a multiple of the 32-env tile, down to a single env."""
     from balatro_gym_b200 import BalatroVecEnv
     from oracle import coracle

@@ -23,8 +23,11 @@ def main():
     ap.add_argument("--episodes", type=int, default=600, help="episodes per configuration")
     ap.add_argument("--seed0", type=int, default=500001)
     ap.add_argument("--max-steps", type=int, default=600)
+    ap.add_argument("--one-launch", action="store_true", help="exercise the small-slab kernel instead of the multi-pass step")
     args = ap.parse_args()
     import torch
+    import balatro_gym_b200
+    assert balatro_gym_b200.load().bgym_set_option(1, (1 << 40) if args.one_launch else 0) == 0
     from make_golden import record
     from test_oracle_golden import replay
     from test_gpu_parity import CudaStepper
@@ -40,6 +43,7 @@ def main():
         total += n
         lines.append(f"config {cfg}: {args.episodes} episodes (seeds {args.seed0 + 100000 * k}..), {n} reference steps replayed on CUDA, "
                      f"{int(tr['exc'].sum())} steps where the reference raised (SafeBalatroEnv convention checked), 0 mismatches")
+    lines.append(f"step path: {'one-launch small-slab kernel' if args.one_launch else 'multi-pass (main + gather kernels)'}")
     lines.append(f"total {total} steps, 0 mismatches, wall {time.time() - t0:.0f} s (reference = byte-compiled copy of the unmodified "
                  f"sources, run live on this box; comparison = tests/test_oracle_golden.py::replay)")
     msg = "\n".join(lines)

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--envs", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--one-launch", action="store_true", help="exercise the small-slab kernel instead of the multi-pass step")
     args = ap.parse_args()
     import torch
     from balatro_gym_b200 import BalatroVecEnv, layout as L
@@ -29,6 +30,8 @@ def main():
     from conftest import assert_records_equal
 
     n = args.envs
+    import balatro_gym_b200
+    assert balatro_gym_b200.load().bgym_set_option(1, (1 << 40) if args.one_launch else 0) == 0
     v = BalatroVecEnv(n, seed=args.seed, autoreset=True)
     v.reset()
     v.randomize_c3(seed=args.seed)
@@ -67,7 +70,7 @@ def main():
         episodes += int(ov.terminated.sum())
         phases += np.bincount(st["phase"] & 3, minlength=4)
         max_ante = max(max_ante, int(st["ante"].max()))
-    msg = (f"soak: {n} envs x {args.steps} steps = {n * args.steps} env-steps, 0 mismatches "
+    msg = (f"soak ({'one-launch small-slab kernel' if args.one_launch else 'multi-pass step: main + gather kernels'}): {n} envs x {args.steps} steps = {n * args.steps} env-steps, 0 mismatches "
            f"(state, obs, terminated, info bit-exact every step; rewards bit-exact except {ulp_cases} last-place log10 cases "
            f"within 1e-12); episodes finished {episodes}; "
            f"env-steps by phase PLAY/SHOP/BLIND_SELECT/PACK_OPEN = {phases.tolist()}; max ante reached {max_ante}; "
