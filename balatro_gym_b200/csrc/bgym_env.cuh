@@ -1049,22 +1049,9 @@ __device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, 
   q.z = (h.joker_slots & 0xFF) | ((h.cons_n & 0xFF) << 8) | ((h.cons_slots & 0xFF) << 16) | ((uint32_t)(h.phase & 0xFF) << 24);
   q.w = (h.boss_type != 0 ? 1u : 0u) | ((uint32_t)(h.boss_type & 0xFF) << 8);
   sts128(obs + 144, q);
-  // 160: action_mask_bits | action_mask[0..7]
-  uint32_t mlo = (uint32_t)mask, mhi = (uint32_t)(mask >> 32);
-  q.x = mlo; q.y = mhi; q.z = spread4(mlo); q.w = spread4(mlo >> 4);
+  // 160: action_mask_bits | pad
+  q.x = (uint32_t)mask; q.y = (uint32_t)(mask >> 32); q.z = 0; q.w = 0;
   sts128(obs + 160, q);
-  // 176: action_mask[8..23]
-  q.x = spread4(mlo >> 8); q.y = spread4(mlo >> 12); q.z = spread4(mlo >> 16); q.w = spread4(mlo >> 20);
-  sts128(obs + 176, q);
-  // 192: action_mask[24..39]
-  q.x = spread4(mlo >> 24); q.y = spread4(mlo >> 28); q.z = spread4(mhi); q.w = spread4(mhi >> 4);
-  sts128(obs + 192, q);
-  // 208: action_mask[40..55]
-  q.x = spread4(mhi >> 8); q.y = spread4(mhi >> 12); q.z = spread4(mhi >> 16); q.w = spread4(mhi >> 20);
-  sts128(obs + 208, q);
-  // 224: action_mask[56..59] | pad
-  q.x = spread4(mhi >> 24); q.y = 0; q.z = 0; q.w = 0;
-  sts128(obs + 224, q);
 }
 
 __device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs /*smem, 240 B*/) {

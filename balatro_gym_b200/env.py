@@ -134,7 +134,7 @@ class BalatroEnv(_EnvBase):
         rec = self._obs_rec[0]
         out = {}
         for k in L.OBS_KEYS:
-            v = rec[k]
+            v = L.obs_value(rec, k)
             out[k] = v.copy() if isinstance(v, np.ndarray) else v
         return out
 
@@ -159,7 +159,7 @@ class BalatroEnv(_EnvBase):
         return self._obs(), float(self._rew[0]), bool(self._term[0]), False, info_dict(self._info[0])
 
     def action_masks(self):
-        return self._obs_rec[0]["action_mask"].astype(bool)
+        return L.mask_from_bits(self._obs_rec[0]["action_mask_bits"]).astype(bool)
 
     @property
     def state(self):

@@ -11,7 +11,7 @@ import numpy as np
 STATE_BYTES = 320
 HOT_BYTES = 144
 COLD_BYTES = 176
-OBS_BYTES = 240
+OBS_BYTES = 176
 INFO_BYTES = 32
 DRAWS_BYTES = 256
 NUM_ACTIONS = 60
@@ -77,8 +77,19 @@ OBS_DTYPE = _dt([
     ("discards_left", "i1", 150), ("joker_count", "i1", 151), ("joker_slots", "i1", 152),
     ("consumable_count", "i1", 153), ("consumable_slots", "i1", 154), ("phase", "i1", 155),
     ("boss_blind_active", "i1", 156), ("boss_blind_type", "i1", 157),
-    ("action_mask_bits", "<u8", 160), ("action_mask", "(60,)i1", 168),
+    ("action_mask_bits", "<u8", 160),
 ], OBS_BYTES)
+
+
+def mask_from_bits(bits) -> np.ndarray:
+    """The reference's obs['action_mask'] (int8[..., 60], balatro_env_2.py:1522) from the packed word(s)."""
+    b = np.asarray(bits, dtype=np.uint64)
+    return ((b[..., None] >> np.arange(NUM_ACTIONS, dtype=np.uint64)) & np.uint64(1)).astype(np.int8)
+
+
+def obs_value(rec, key):
+    """Field `key` of an observation record (array) in the reference's dict form; 'action_mask' is expanded."""
+    return mask_from_bits(rec["action_mask_bits"]) if key == "action_mask" else rec[key]
 
 # the 31 observation keys the reference emits, in its dict order (balatro_env_2.py:1488-1531)
 OBS_KEYS = [

@@ -29,7 +29,7 @@ def _torch():
 
 
 def featurize(obs_records, out=None, dtype=None):
-    """[n, 240] uint8 observation records -> [n, 448] features (bgym_featurize)."""
+    """[n, 176] uint8 observation records -> [n, 448] features (bgym_featurize)."""
     torch = _torch()
     lib = _lib.load()
     n = obs_records.shape[0]
@@ -127,8 +127,8 @@ def make_policy(features_dim: int = 512, pi=(256, 256), vf=(256, 256), device="c
 class RolloutCollector:
     """`n_steps` of experience for every env of a slab, collected without leaving the device.
 
-    Buffers are time-major [T(+1), n, ...]: obs (raw 240-byte records; features are recomputed
-    on demand, 3.7x smaller than storing bf16 features), actions, logp, values, rewards, dones,
+    Buffers are time-major [T(+1), n, ...]: obs (raw 176-byte records; features are recomputed
+    on demand, 5x smaller than storing bf16 features), actions, logp, values, rewards, dones,
     advantages, returns.
     """
 
@@ -222,7 +222,7 @@ class RolloutCollector:
 
 
 def legal_mask(obs_records):
-    """[B, 240] uint8 records -> [B, 60] bool from the packed legal-action word."""
+    """[B, 176] uint8 records -> [B, 60] bool from the packed legal-action word."""
     torch = _torch()
     bits = obs_records[:, 160:168].contiguous().view(torch.int64)
     return ((bits >> torch.arange(L.NUM_ACTIONS, device=obs_records.device)) & 1).bool()

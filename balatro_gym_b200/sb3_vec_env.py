@@ -122,7 +122,7 @@ class BalatroSB3VecEnv(_VecEnvBase):
     # -- observation plumbing ----------------------------------------------------------------------
     def _obs_dict(self, rec: np.ndarray) -> dict:
         """Fresh arrays, as `_get_observation` allocates them (balatro_env_2.py:1488)."""
-        return {k: np.array(rec[k]) for k in L.OBS_KEYS}
+        return {k: np.array(L.obs_value(rec, k)) for k in L.OBS_KEYS}
 
     def _host_records(self) -> np.ndarray:
         return self._rec
@@ -219,7 +219,7 @@ class BalatroSB3VecEnv(_VecEnvBase):
                 self._seeds[idx] = next_episode_seed(self._seeds[idx])
             self._device_reset(dones)
             for k in L.OBS_KEYS:
-                obs[k][idx] = self._rec[k][idx]
+                obs[k][idx] = L.obs_value(self._rec[idx], k)
             self._ep_ret[idx] = 0; self._ep_len[idx] = 0; self._invalid_run[idx] = 0
             for i in idx:
                 self.reset_infos[i] = {}
@@ -242,7 +242,7 @@ class BalatroSB3VecEnv(_VecEnvBase):
 
     def action_masks(self) -> np.ndarray:
         """[num_envs, 60] bool, from the observation records already on the host."""
-        return self._rec['action_mask'].astype(bool)
+        return L.mask_from_bits(self._rec['action_mask_bits']).astype(bool)
 
     def env_method(self, method_name: str, *args, indices=None, **kwargs):
         idx = self._indices(indices)

@@ -44,6 +44,43 @@ def _field_view(torch, buf_u8, dtype_np, name):
     return v if dt.shape else v[:, 0]
 
 
+class _ObsViews(dict):
+    """The observation dict of a slab: zero-copy views of the record fields, plus 'action_mask' — the reference's
+    int8 [N, 60] array — which is NOT stored in the records (they carry the packed word `action_mask_bits`) and
+    is expanded only when somebody asks for it."""
+
+    def __init__(self, views, expand):
+        super().__init__(views)
+        self._expand = expand
+
+    def __getitem__(self, key):
+        if key == "action_mask":
+            return self._expand()
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __contains__(self, key):
+        return key == "action_mask" or dict.__contains__(self, key)
+
+    def __iter__(self):
+        yield from dict.__iter__(self)
+        yield "action_mask"
+
+    def __len__(self):
+        return dict.__len__(self) + 1
+
+    def keys(self):
+        return list(iter(self))
+
+    def items(self):
+        return [(k, self[k]) for k in self]
+
+    def values(self):
+        return [self[k] for k in self]
+
+
 class BalatroVecEnv:
     """N environments on one GPU.
 
@@ -107,10 +144,15 @@ class BalatroVecEnv:
 
     @property
     def obs(self) -> Dict[str, "object"]:
-        """The 31-key observation dict of the reference as zero-copy views of the obs records."""
+        """The 31-key observation dict of the reference: zero-copy views of the obs records, plus
+        `action_mask_bits` (the packed legal-action word, int64) and `action_mask` — the reference's int8[N, 60]
+        array, expanded from the word on access (it is not stored: 8 B instead of 60 B per record)."""
         if self._obs_views is None:
-            self._obs_views = {k: _field_view(self.torch, self.obs_buf, L.OBS_DTYPE, k) for k in L.OBS_KEYS}
+            self._obs_views = {k: _field_view(self.torch, self.obs_buf, L.OBS_DTYPE, k) for k in L.OBS_KEYS if k != "action_mask"}
             self._obs_views["action_mask_bits"] = _field_view(self.torch, self.obs_buf, L.OBS_DTYPE, "action_mask_bits")
+            shifts = self.torch.arange(L.NUM_ACTIONS, device=self.device)
+            bits = self._obs_views["action_mask_bits"]
+            self._obs_views = _ObsViews(self._obs_views, lambda: ((bits.unsqueeze(1) >> shifts) & 1).to(self.torch.int8))
         return self._obs_views
 
     def info_field(self, name):

@@ -31,6 +31,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+L_OBS = 176    # bytes of one observation record (include/bgym.h BgymObs)
 B_STEP = 872   # canonical algorithmic bytes per env-step
 B_HAND = 32    # canonical algorithmic bytes per scored hand
 METRIC = "env_steps_per_sec"
@@ -148,7 +149,7 @@ def workload_config(args, n_envs):
     return {"workload": "BASELINE configs[3]: full run incl. shop/rerolls/planets/consumables with the configs[2] state "
                         "generator (5 random jokers, enhancements/editions/seals, boss blinds), random legal actions, autoreset",
             "envs_per_gpu": n_envs, "policy": "uniform random legal action per env",
-            "l2": "inputs larger than L2 (state+obs records of one step = %.0f MB per GPU)" % (n_envs * (320 + 240) / 1e6)}
+            "l2": "inputs larger than L2 (state+obs records of one step = %.0f MB per GPU)" % (n_envs * (320 + L_OBS) / 1e6)}
 
 
 # -------------------------------------------------------------------------------------------------
@@ -286,7 +287,7 @@ def run_ours(args):
                      "traffic": 667e6 * n / float(1 << 20), "traffic_unit": "bytes per step launch set (ncu, profiles/)",
                      "kernel": "one env-step = env_step_main_kernel + 3 concurrent env_step_gather_kernel passes (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
                      "units_per_launch": n, "kernel_ms": step_kernel_ms_max, "peak_source": peak_src,
-                     "physical_bytes_per_unit": "main pass 144*2+240+14 = 542 B per env; gather passes add (144+176)*2+240 B for the ~17 % deferred envs"},
+                     "physical_bytes_per_unit": "main pass 144*2+176+14 = 478 B per env; gather passes add (144+176)*2+176 B for the ~17 % deferred envs"},
         "cpu_baseline": cpu_base,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (L.OBS_BYTES + 8 + 1 + 4) * n,
                 "steps": Ke},

@@ -39,7 +39,7 @@ extern "C" {
 #define BGYM_STATE_BYTES 320
 #define BGYM_HOT_BYTES   144
 #define BGYM_COLD_BYTES  176
-#define BGYM_OBS_BYTES   240
+#define BGYM_OBS_BYTES   176
 #define BGYM_INFO_BYTES  32
 #define BGYM_DRAWS_BYTES 256
 #define BGYM_NUM_ACTIONS 60
@@ -180,9 +180,13 @@ typedef struct BgymHot { BGYM_HOT_FIELDS } BgymHot;
 typedef struct BgymCold { BGYM_COLD_FIELDS } BgymCold;
 typedef struct BgymState { BGYM_HOT_FIELDS BGYM_COLD_FIELDS } BgymState;
 
-/* ---- observation record (240 B) ---------------------------------------------
+/* ---- observation record (176 B) ---------------------------------------------
  * The 31 keys the reference actually emits (balatro_env_2.py:1488-1531), same dtypes
- * except selected_cards / face_down_cards (int8 here, platform int there). */
+ * except selected_cards / face_down_cards (int8 here, platform int there) and the action
+ * mask: the reference's int8[60] `action_mask` (:1522) travels as ONE 64-bit word,
+ * action_mask_bits (bit a = action a legal) — 8 bytes instead of 60 on every record written
+ * to HBM and copied over PCIe.  The Python layers expand it back into obs['action_mask']
+ * (layout.mask_from_bits) wherever a caller asks for the reference's dict. */
 typedef struct BgymObs {
   int8_t   hand[8];             /*   0 card code or -1                  */
   int8_t   selected_cards[8];   /*   8                                  */
@@ -215,9 +219,8 @@ typedef struct BgymObs {
   int8_t   boss_blind_active;   /* 156                                  */
   int8_t   boss_blind_type;     /* 157                                  */
   uint8_t  _pad0[2];            /* 158                                  */
-  uint64_t action_mask_bits;    /* 160 bit a = action a legal (extra: the mask as one word) */
-  int8_t   action_mask[60];     /* 168                                  */
-  uint8_t  _pad1[12];           /* 228                                  */
+  uint64_t action_mask_bits;    /* 160 bit a = action a legal (obs['action_mask'][a], :1522) */
+  uint8_t  _pad1[8];            /* 168 (record stride 176 = 11 x 16 B)  */
 } BgymObs;
 
 /* ---- per-step info record (32 B) --------------------------------------------

@@ -533,7 +533,7 @@ static void write_obs(const BgymState* s, BgymObs* o) {
   o->boss_blind_type = (int8_t)s->boss_type;
   uint64_t m = action_mask(s);
   o->action_mask_bits = m;
-  for (int a = 0; a < BGYM_NUM_ACTIONS; a++) o->action_mask[a] = (m >> a) & 1;
+  /* the int8[60] action_mask of the reference (:1522) is carried as action_mask_bits only */
 }
 
 /* ------------------------------------------------------------------------------------------

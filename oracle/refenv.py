@@ -377,7 +377,8 @@ class RefEnv:
     def obs_record(obs: dict) -> np.ndarray:
         o = np.zeros((), dtype=L.OBS_DTYPE)
         for k in L.OBS_KEYS:
-            o[k] = obs[k]
+            if k != "action_mask":       # carried as action_mask_bits (include/bgym.h)
+                o[k] = obs[k]
         bits = 0
         for a in np.flatnonzero(obs["action_mask"]):
             bits |= 1 << int(a)

@@ -53,7 +53,7 @@ def test_struct_layouts_match_numpy_dtypes():
         assert size == dt.itemsize, struct
         assert offs == [dt.fields[n][1] for n in dt.names], struct
     # device record strides are odd multiples of 16 B (bank-conflict-free 128-bit access per lane)
-    for dt, size in ((L.HOT_DTYPE, 144), (L.COLD_DTYPE, 176), (L.OBS_DTYPE, 240)):
+    for dt, size in ((L.HOT_DTYPE, 144), (L.COLD_DTYPE, 176), (L.OBS_DTYPE, 176)):
         assert dt.itemsize == size and dt.itemsize % 32 == 16
     assert L.STATE_DTYPE.itemsize == 320 == L.HOT_BYTES + L.COLD_BYTES
 
