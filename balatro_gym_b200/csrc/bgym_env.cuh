@@ -971,7 +971,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
 }
 
 // ---------------------------------------------------------------------------------------------
-// observation record (balatro_env_2.py:1473-1573) assembled in registers, 15 x 16 B
+// observation record (balatro_env_2.py:1473-1573) assembled in registers, 11 x 16 B
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int obs_cons_id(int cid) { return cid >= BGYM_CONS_ENUMSTYLE_BASE ? 0 : cid; }
 
@@ -996,7 +996,7 @@ __device__ __forceinline__ void obs_shop_block(const Hot& h, const uint8_t* rec,
   so.w[9] = ic[7] | (ic[8] << 16); so.w[10] = ic[9];
 }
 
-__device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, uint64_t mask, uint8_t* obs /*smem, 240 B*/) {
+__device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, uint64_t mask, uint8_t* obs /*smem, 176 B*/) {
   uint4 q;
   uint32_t selm = 0;
   #pragma unroll 1
@@ -1054,7 +1054,7 @@ __device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, 
   sts128(obs + 160, q);
 }
 
-__device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs /*smem, 240 B*/) {
+__device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs /*smem, 176 B*/) {
   ShopObs so;
   if (rec) obs_shop_block(h, rec, so);
   else {

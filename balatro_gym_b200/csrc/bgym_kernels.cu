@@ -13,7 +13,7 @@
 // records).  A warp owns a tile of 32 envs; a tile of records is contiguous, so it moves between
 // global and shared memory with ONE 1-D bulk async copy (cp.async.bulk, SASS UBLKCP — the TMA engine
 // without a tensor map) that completes on the warp's mbarrier; each lane then works on its record
-// with 128-bit shared-memory accesses (record strides 144 / 176 / 240 B are odd multiples of 16 B,
+// with 128-bit shared-memory accesses (record strides 144 / 176 / 176 B are odd multiples of 16 B,
 // so a quarter-warp hits 8 distinct bank groups), and results leave with bulk async stores.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,7 +32,7 @@ struct StepArgs {
   const int32_t* actions;    // n (read; written instead with BGYM_FLAG_RANDOM_POLICY)
   int32_t* actions_out;      // n (written with BGYM_FLAG_RANDOM_POLICY, nullable)
   const BgymDraws* draws;    // n (nullable)
-  uint8_t* obs;              // n x 240 (nullable)
+  uint8_t* obs;              // n x 176 (nullable)
   double* reward;            // n
   uint8_t* terminated;       // n
   uint8_t* truncated;        // n (nullable)
@@ -692,7 +692,7 @@ int bgym_sample_actions(const BgymObs* obs, int32_t* actions, uint32_t seed, uin
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
-  // one thread per env up to 64 resident-size waves: the 8-byte mask reads are 240-B strided and
+  // one thread per env up to 64 resident-size waves: the 8-byte mask reads are 176-B strided and
   // latency-bound, so keep as many in flight as the machine holds
   int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 512 ? (n + 255) / 256 : (long long)g_sm_count * 512);
   sample_actions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), actions, seed, step, n);
@@ -891,7 +891,7 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
   if (rc) return rc;
   if (obs_out) {
     CK(cudaMemcpyAsync(v->h_block, v->d_block, v->block_bytes, cudaMemcpyDeviceToHost, v->stream));      // everything, one copy
-  } else {   // without observations: skip the 240 B/env part
+  } else {   // without observations: skip the 176 B/env part
     const size_t off = reinterpret_cast<uint8_t*>(v->d_reward) - v->d_block;
     CK(cudaMemcpyAsync(v->h_block + off, v->d_block + off, v->block_bytes - off, cudaMemcpyDeviceToHost, v->stream));
   }

@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
 // gather pass: one listed env per lane, per-lane bulk copies of its hot and cold record
 // ------------------------------------------------------------------------------------------------
 constexpr int GATHER_WARPS = 4;
-// the observation tile (32 x 240 B) is staged OVER the hot + cold tiles once their stores have read
+// the observation tile (32 x 176 B) is staged OVER the hot + cold tiles once their stores have read
 // them, so a warp needs 10 KB and an SM holds BGYM_GATHER_CTAS x 4 warps (the passes are bound by
 // dependent integer latency: resident warps are what buys throughput)
-constexpr int GATHER_WARP_SMEM = 32 * (BGYM_HOT_BYTES + BGYM_COLD_BYTES);  // 10240 >= 32 * 240
+constexpr int GATHER_WARP_SMEM = 32 * (BGYM_HOT_BYTES + BGYM_COLD_BYTES);  // 10240 >= 32 * 176
 constexpr int GATHER_CTA_SMEM = GATHER_WARPS * GATHER_WARP_SMEM + 16 * GATHER_WARPS;
 #ifndef BGYM_GATHER_CTAS
 #define BGYM_GATHER_CTAS 4
