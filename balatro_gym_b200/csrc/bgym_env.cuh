@@ -48,7 +48,7 @@ __device__ __forceinline__ void unpack_hot(const uint8_t* hot, Hot& h) {
   h.hand_n = q1.x & 0xFF; h.hand_size = (q1.x >> 8) & 0xFF; h.sel_n = (q1.x >> 16) & 0xFF; h.highlight = q1.x >> 24;
   h.sel_order = q1.y;
   h.face_down = q1.z & 0xFF; h.phase = (q1.z >> 8) & 0xFF; h.round = (q1.z >> 16) & 0xFF; h.boss_type = q1.z >> 24;
-  h.hands_left = q1.w & 0xFF; h.discards_left = (q1.w >> 8) & 0xFF; h.joker_n = (q1.w >> 16) & 0xFF; h.cons_n = q1.w >> 24;
+  h.ep_len = q1.w;
   h.joker_slots = q2.x & 0xFF; h.cons_slots = (q2.x >> 8) & 0xFF; h.n_magic = (q2.x >> 16) & 0xFF; h.n_minimalist = q2.x >> 24;
   h.ante = (int)(short)(q2.y & 0xFFFF); h.jokers_sold = (int)(short)(q2.y >> 16);
   h.money = (int)q2.z; h.chips_needed = (int)q2.w;
@@ -59,18 +59,26 @@ __device__ __forceinline__ void unpack_hot(const uint8_t* hot, Hot& h) {
   h.boss_played_cards = u64_of(q5.x, q5.y); h.jokers = u64_of(q5.z, q5.w);
   h.cons = u64_of(q6.x, q6.y); h.lv0 = q6.z; h.lv1 = q6.w;
   h.lv2 = q7.x; h.shop_reroll_state = (int)q7.y; h.rng_seed = q7.z; h.rng_ctr = q7.w;
-  h.ep_len = q8.x; h.episode = q8.y;
+  h.hands_left = q8.x & 0xFF; h.discards_left = (q8.x >> 8) & 0xFF; h.joker_n = (q8.x >> 16) & 0xFF; h.cons_n = q8.x >> 24;
+  h.episode = q8.y;
+}
+
+// bytes 16..31 of the hot record: hand_n | hand_size | sel_n | highlight, sel_order, face_down | phase | round | boss,
+// ep_len — everything a SELECT toggle changes
+__device__ __forceinline__ uint4 hot_chunk1(const Hot& h) {
+  uint4 q;
+  q.x = (h.hand_n & 0xFF) | ((h.hand_size & 0xFF) << 8) | ((h.sel_n & 0xFF) << 16) | ((uint32_t)(h.highlight & 0xFF) << 24);
+  q.y = h.sel_order;
+  q.z = (h.face_down & 0xFF) | ((h.phase & 0xFF) << 8) | ((h.round & 0xFF) << 16) | ((uint32_t)(h.boss_type & 0xFF) << 24);
+  q.w = h.ep_len;
+  return q;
 }
 
 __device__ __forceinline__ void pack_hot(uint8_t* hot, const Hot& h) {
   uint4 q;
   q.x = (uint32_t)h.hand; q.y = (uint32_t)(h.hand >> 32); q.z = (uint32_t)h.hand_code; q.w = (uint32_t)(h.hand_code >> 32);
   sts128(hot, q);
-  q.x = (h.hand_n & 0xFF) | ((h.hand_size & 0xFF) << 8) | ((h.sel_n & 0xFF) << 16) | ((uint32_t)(h.highlight & 0xFF) << 24);
-  q.y = h.sel_order;
-  q.z = (h.face_down & 0xFF) | ((h.phase & 0xFF) << 8) | ((h.round & 0xFF) << 16) | ((uint32_t)(h.boss_type & 0xFF) << 24);
-  q.w = (h.hands_left & 0xFF) | ((h.discards_left & 0xFF) << 8) | ((h.joker_n & 0xFF) << 16) | ((uint32_t)(h.cons_n & 0xFF) << 24);
-  sts128(hot + 16, q);
+  sts128(hot + 16, hot_chunk1(h));
   q.x = (h.joker_slots & 0xFF) | ((h.cons_slots & 0xFF) << 8) | ((h.n_magic & 0xFF) << 16) | ((uint32_t)(h.n_minimalist & 0xFF) << 24);
   q.y = (h.ante & 0xFFFF) | ((uint32_t)(h.jokers_sold & 0xFFFF) << 16);
   q.z = (uint32_t)h.money; q.w = (uint32_t)h.chips_needed;
@@ -89,7 +97,8 @@ __device__ __forceinline__ void pack_hot(uint8_t* hot, const Hot& h) {
   sts128(hot + 96, q);
   q.x = h.lv2; q.y = (uint32_t)h.shop_reroll_state; q.z = h.rng_seed; q.w = h.rng_ctr;
   sts128(hot + 112, q);
-  q.x = h.ep_len; q.y = h.episode; q.z = 0; q.w = 0;
+  q.x = (h.hands_left & 0xFF) | ((h.discards_left & 0xFF) << 8) | ((h.joker_n & 0xFF) << 16) | ((uint32_t)(h.cons_n & 0xFF) << 24);
+  q.y = h.episode; q.z = 0; q.w = 0;
   sts128(hot + 128, q);
 }
 

@@ -389,13 +389,13 @@ __global__ void action_mask_kernel(const uint8_t* hot, const uint8_t* cold, uint
     uint64_t m = 0;
     int phase = hr[25];
     if (phase == BGYM_PHASE_PLAY) {
-      int hand_n = hr[16], sel_n = hr[18], discards_left = hr[29], cons_n = hr[31];
+      int hand_n = hr[16], sel_n = hr[18], discards_left = hr[129], cons_n = hr[131];
       m = ((1ull << min(hand_n, 8)) - 1) << BGYM_A_SELECT_BASE;
       if (sel_n > 0) m |= 1ull << BGYM_A_PLAY_HAND;
       if (sel_n > 0 && discards_left > 0) m |= 1ull << BGYM_A_DISCARD;
       m |= ((1ull << cons_n) - 1) << BGYM_A_USE_CONS_BASE;
     } else if (phase == BGYM_PHASE_SHOP) {
-      int money = *reinterpret_cast<const int*>(hr + 40), joker_n = hr[30];
+      int money = *reinterpret_cast<const int*>(hr + 40), joker_n = hr[130];
       int n_items = cr[OFF_N_ITEMS];
       for (int k = 0; k < n_items; k++)
         if (money >= *reinterpret_cast<const int*>(cr + OFF_ITEM_COST + 4 * k)) m |= 1ull << (BGYM_A_SHOP_BUY_BASE + k);

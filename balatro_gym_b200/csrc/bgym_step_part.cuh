@@ -173,7 +173,10 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
       mine = cat == 0;
       if (mine) {
         step_env<CAT_SELECT>(h, hot, nullptr, action, m0, nullptr, reward, terminated, info);
-        pack_hot(hot, h);
+        // a card toggle changes bytes 16..31 of the hot record and nothing else (include/bgym.h): that chunk goes
+        // straight from registers to its place — one 32-byte sector per env instead of the 144-byte record; a
+        // rejected action changes nothing at all
+        if (info.error_code == 0) *reinterpret_cast<uint4*>(a.hot + e * BGYM_HOT_BYTES + 16) = hot_chunk1(h);
         if (with_obs) write_obs(h, nullptr, action_mask(h, nullptr), obs_s);
         write_step_outputs(a, e, reward, terminated, info);
       }
@@ -192,7 +195,6 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
     __syncwarp();
     if (lane == 0) {
       uint32_t cnt = (uint32_t)min(32LL, a.n - tile * 32);
-      bulk_s2g(a.hot + tile * 32 * BGYM_HOT_BYTES, hot_buf, cnt * BGYM_HOT_BYTES);
       // deferred envs' observation slots hold stale bytes; their gather pass rewrites them afterwards
       if (with_obs) bulk_s2g(a.obs + tile * 32 * BGYM_OBS_BYTES, obs_buf, cnt * BGYM_OBS_BYTES);
       bulk_commit();

@@ -41,7 +41,7 @@ _HOT_FIELDS = [
     ("hand_n", "u1", 16), ("hand_size", "u1", 17), ("sel_n", "u1", 18), ("highlight_mask", "u1", 19),
     ("sel_order", "<u4", 20),
     ("face_down_mask", "u1", 24), ("phase", "u1", 25), ("round", "u1", 26), ("boss_type", "u1", 27),
-    ("hands_left", "u1", 28), ("discards_left", "u1", 29), ("joker_n", "u1", 30), ("cons_n", "u1", 31),
+    ("ep_len", "<u4", 28),
     ("joker_slots", "u1", 32), ("cons_slots", "u1", 33), ("n_magic_trick", "u1", 34), ("n_minimalist", "u1", 35),
     ("ante", "<i2", 36), ("jokers_sold", "<i2", 38),
     ("money", "<i4", 40), ("chips_needed", "<i4", 44),
@@ -52,7 +52,8 @@ _HOT_FIELDS = [
     ("boss_played_cards", "<u8", 80),
     ("joker_id", "(8,)u1", 88), ("cons_id", "(8,)u1", 96), ("hand_level", "(12,)u1", 104),
     ("shop_reroll_state", "<i4", 116), ("rng_seed", "<u4", 120), ("rng_ctr", "<u4", 124),
-    ("ep_len", "<u4", 128), ("episode", "<u4", 132),
+    ("hands_left", "u1", 128), ("discards_left", "u1", 129), ("joker_n", "u1", 130), ("cons_n", "u1", 131),
+    ("episode", "<u4", 132),
 ]
 _COLD_FIELDS = [
     ("deck", "(52,)<u2", 0), ("hand_play_count", "(12,)u1", 104),

@@ -139,7 +139,8 @@ enum {
  *  16 hand_n, 17 hand_size, 18 sel_n, 19 highlight_mask (game.highlighted_indexes as a slot bit set)
  *  20 sel_order           selected_cards, ordered: nibble k = slot of the k-th selection
  *  24 face_down_mask, 25 phase, 26 round (1 small 2 big 3 boss), 27 boss_type (BossBlindType, 0 none)
- *  28 hands_left, 29 discards_left, 30 joker_n, 31 cons_n
+ *  28 ep_len              valid steps this episode.  Bytes 16..31 are everything a card toggle changes:
+ *                         the main pass writes back only this 16-byte chunk for the envs it serves
  *  32 joker_slots, 33 cons_slots, 34 n_magic_trick, 35 n_minimalist (voucher counts)
  *  36 ante i16, 38 jokers_sold i16, 40 money i32, 44 chips_needed i32
  *  48 round_chips i64 (round_chips_scored), 56 chips_scored i64
@@ -151,19 +152,21 @@ enum {
  * 104 hand_level[12]      state.hand_levels (uncapped); engine level = min(level, 15)
  * 116 shop_reroll_state   state.shop_reroll_cost (stale copy used by the mask)
  * 120 rng_seed, 124 rng_ctr (native Philox key word / block counter)
- * 128 ep_len (valid steps this episode), 132 episode (in-kernel autoresets so far), 136 pad[8] */
+ * 128 hands_left, 129 discards_left, 130 joker_n, 131 cons_n
+ * 132 episode (in-kernel autoresets so far), 136 pad[8] */
 #define BGYM_HOT_FIELDS \
   uint8_t hand[8]; uint8_t hand_code[8]; \
   uint8_t hand_n; uint8_t hand_size; uint8_t sel_n; uint8_t highlight_mask; uint32_t sel_order; \
   uint8_t face_down_mask; uint8_t phase; uint8_t round; uint8_t boss_type; \
-  uint8_t hands_left; uint8_t discards_left; uint8_t joker_n; uint8_t cons_n; \
+  uint32_t ep_len; \
   uint8_t joker_slots; uint8_t cons_slots; uint8_t n_magic_trick; uint8_t n_minimalist; \
   int16_t ante; int16_t jokers_sold; int32_t money; int32_t chips_needed; \
   int64_t round_chips; int64_t chips_scored; int32_t best_hand; int32_t hands_played_total; \
   int16_t hands_played_ante; uint8_t boss_flags; uint8_t boss_cards_required; \
   uint16_t boss_played_types; uint8_t boss_hands_played; uint8_t deck_n; uint64_t boss_played_cards; \
   uint8_t joker_id[8]; uint8_t cons_id[8]; uint8_t hand_level[12]; int32_t shop_reroll_state; \
-  uint32_t rng_seed; uint32_t rng_ctr; uint32_t ep_len; uint32_t episode; uint8_t _hot_pad[8];
+  uint32_t rng_seed; uint32_t rng_ctr; uint8_t hands_left; uint8_t discards_left; uint8_t joker_n; uint8_t cons_n; \
+  uint32_t episode; uint8_t _hot_pad[8];
 
 /* cold record, 176 B (offset: field)
  *   0 deck[52] u16        card16 per deck index
