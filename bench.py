@@ -283,11 +283,11 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of the four launches of one step at
                      # 2^20 envs, from the committed ncu --set full capture (profiles/r01_ncu_summary_final.md):
-                     # main 161+354 MB, PLAY 54+22, OTHER 38+6, DISCARD 31+1 -> 667 MB = 636 B per env-step
-                     "traffic": 667e6 * n / float(1 << 20), "traffic_unit": "bytes per step launch set (ncu, profiles/)",
+                     # main 160+179 MB, PLAY 54+17, OTHER 38+5, DISCARD 31+1 -> 485 MB = 462 B per env-step
+                     "traffic": 485e6 * n / float(1 << 20), "traffic_unit": "bytes per step launch set (ncu, profiles/)",
                      "kernel": "one env-step = env_step_main_kernel + 3 concurrent env_step_gather_kernel passes (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
                      "units_per_launch": n, "kernel_ms": step_kernel_ms_max, "peak_source": peak_src,
-                     "physical_bytes_per_unit": "main pass 144*2+176+14 = 478 B per env; gather passes add (144+176)*2+176 B for the ~17 % deferred envs"},
+                     "physical_bytes_per_unit": "main pass 144 (hot read) + 16 (the chunk a toggle changes) + 176 (obs) + 14 = 350 B per env; gather passes add (144+176)*2+176 B for the ~17 % deferred envs"},
         "cpu_baseline": cpu_base,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (L.OBS_BYTES + 8 + 1 + 4) * n,
                 "steps": Ke},
