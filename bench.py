@@ -22,10 +22,6 @@ import sys
 import threading
 import time
 
-# rank 0's stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at
-# NCCL_DEBUG=VERSION) out of it; an explicit INFO/TRACE request is left alone
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
@@ -161,11 +157,24 @@ def run_ours(args):
     from balatro_gym_b200 import dist as bdist
     from balatro_gym_b200 import layout as L
 
-    rank, local_rank, ws = bdist.init_process_group("nccl")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    dev = torch.device("cuda", local_rank)
-    torch.cuda.set_device(dev)
+    # rank 0's stdout carries exactly one JSON line.  NCCL prints its version banner to stdout when the first
+    # communicator is created (whatever NCCL_DEBUG says from VERSION up), so the process group is brought up —
+    # first collective included — with fd 1 pointing at stderr.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local_rank, ws = bdist.init_process_group("nccl")
+        dev = torch.device("cuda", local_rank)
+        torch.cuda.set_device(dev)
+        bdist.max_over_ranks(0.0, dev)
+        torch.cuda.synchronize(dev)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     n = args.envs
     K, W = args.steps, max(args.warmup, 3)
     peak, peak_src = measured_peak()
