@@ -64,6 +64,7 @@ SYMBOLS = {
     "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "bgym_action_mask": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "bgym_sample_actions": (_i32, [_vp, _vp, _u32, _u64, _i64, _vp]),
+    "bgym_sample_actions_ctr": (_i32, [_vp, _vp, _u32, _vp, _i64, _vp]),
     "bgym_score_hands": (_i32, [_vp] * 12 + [_u32, _i64, _i32, _vp]),
     "bgym_episode_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "bgym_featurize": (_i32, [_vp, _vp, _i64, _i32, _vp]),

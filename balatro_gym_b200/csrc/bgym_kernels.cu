@@ -412,7 +412,12 @@ __global__ void action_mask_kernel(const uint8_t* hot, const uint8_t* cold, uint
 
 // uniform random legal action from obs.action_mask_bits; Philox keyed (seed, policy key),
 // counter (env index, step)
-__global__ void sample_actions_kernel(const uint8_t* obs, int32_t* actions, uint32_t seed, unsigned long long step, long long n) {
+// step_dev != nullptr: the step number lives on the device (launches replayed from a CUDA graph cannot take it as
+// a kernel argument); bump_counter_kernel advances it after the sampler
+__global__ void bump_counter_kernel(unsigned long long* ctr) { *ctr += 1; }
+__global__ void sample_actions_kernel(const uint8_t* obs, int32_t* actions, uint32_t seed, unsigned long long step,
+                                      const unsigned long long* step_dev, long long n) {
+  if (step_dev) step += *step_dev;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     uint64_t m = *reinterpret_cast<const uint64_t*>(obs + i * BGYM_OBS_BYTES + 160);
     int cnt = __popcll(m);
@@ -695,8 +700,20 @@ int bgym_sample_actions(const BgymObs* obs, int32_t* actions, uint32_t seed, uin
   // one thread per env up to 64 resident-size waves: the 8-byte mask reads are 176-B strided and
   // latency-bound, so keep as many in flight as the machine holds
   int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 512 ? (n + 255) / 256 : (long long)g_sm_count * 512);
-  sample_actions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), actions, seed, step, n);
+  sample_actions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), actions, seed, step, nullptr, n);
   return cuda_rc(cudaGetLastError(), "bgym_sample_actions launch");
+}
+
+int bgym_sample_actions_ctr(const BgymObs* obs, int32_t* actions, uint32_t seed, uint64_t* step_counter, int64_t n, void* stream) {
+  if (n < 0 || !obs || !actions || !step_counter) return set_err(BGYM_E_ARG, "bgym_sample_actions_ctr: bad arguments");
+  if (n == 0) return 0;
+  int rc = ensure_device_setup();
+  if (rc) return rc;
+  int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 512 ? (n + 255) / 256 : (long long)g_sm_count * 512);
+  sample_actions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), actions, seed, 0ull,
+                                                                reinterpret_cast<const unsigned long long*>(step_counter), n);
+  bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(step_counter));
+  return cuda_rc(cudaGetLastError(), "bgym_sample_actions_ctr launch");
 }
 
 int bgym_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8_t* n_cards,

@@ -238,6 +238,41 @@ class BalatroVecEnv:
         _lib.check(rc, "bgym_sample_actions")
         return out
 
+    def graphed_rollout_step(self, policy: str = "sampler", seed: int = 0):
+        """One env-step (policy + step kernels) captured in a CUDA graph; returns a zero-argument callable that
+        replays it on the current stream.  A step is six short launches chained by events: replaying them from a
+        graph removes the launch gaps between them.  policy = 'sampler' (uniform legal action from the
+        observation's mask word, step number kept in a device counter) or 'fused' (sampled inside the step
+        kernels).  Results land in the usual buffers (self.obs_buf, self.reward, self.terminated, self.actions)."""
+        torch = self.torch
+        assert policy in ("sampler", "fused")
+        if not hasattr(self, "_step_ctr"):
+            self._step_ctr = torch.zeros(1, dtype=torch.int64, device=self.device)
+        flags = (L.FLAG_AUTORESET if self.autoreset else 0) | (4 if policy == "fused" else 0)
+
+        def launch():
+            st = self._stream()
+            if policy == "sampler":
+                rc = self.lib.bgym_sample_actions_ctr(self.obs_buf.data_ptr(), self.actions.data_ptr(), seed & 0xFFFFFFFF,
+                                                      self._step_ctr.data_ptr(), self.num_envs, st)
+                _lib.check(rc, "bgym_sample_actions_ctr")
+            rc = self.lib.bgym_step(self.hot.data_ptr(), self.cold.data_ptr(), self.actions.data_ptr(), None, self.obs_buf.data_ptr(),
+                                    self.reward.data_ptr(), self.terminated.data_ptr(), self.truncated.data_ptr(), None,
+                                    self.num_envs, flags, st)
+            _lib.check(rc, "bgym_step")
+
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):          # warm-up on the capture stream: per-stream scratch is allocated here
+            for _ in range(2):
+                launch()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            launch()
+        self._graphs = getattr(self, "_graphs", []) + [graph]
+        return graph.replay
+
     def action_masks(self):
         """uint64 mask word per env computed from the state (bit a = action a legal), as int64."""
         with self.torch.cuda.device(self.device):

@@ -228,7 +228,21 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     fused_ms = bdist.max_over_ranks(e0.elapsed_time(e1), dev)
     fused_value = ws * n * K / (fused_ms / 1000.0)
-    # clocks were sampled (nvidia-smi, 20 ms period) from the start of the timed steps to here: both loops run
+    # the same two loops replayed from CUDA graphs (BalatroVecEnv.graphed_rollout_step): no launch gaps
+    graph_vals = {}
+    for pol in ("sampler", "fused"):
+        replay = env.graphed_rollout_step(pol, seed=2024)
+        for _ in range(W):
+            replay()
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for k in range(K):
+            replay()
+        g1.record()
+        torch.cuda.synchronize(dev)
+        graph_vals[pol] = ws * n * K / (bdist.max_over_ranks(g0.elapsed_time(g1), dev) / 1000.0)
+    # clocks were sampled (nvidia-smi, 20 ms period) from the start of the timed steps to here: all loops run
     # the same step kernels back to back
     clk = clocks.stop() if rank == 0 else None
 
@@ -304,6 +318,8 @@ def run_ours(args):
         "clocks": clk,
         "fused_rollout": {"value": fused_value, "unit": UNIT, "ms_per_step": fused_ms / K,
                           "note": "policy sampled inside the step kernel (one launch per step)"},
+        "graph_replay": {"sampler_plus_step": graph_vals["sampler"], "fused": graph_vals["fused"], "unit": UNIT,
+                         "note": "the value / fused_rollout loops replayed from a CUDA graph per step"},
         "hands": hands,
         "ppo_rollout": ppo,
         "host_facing": host_facing,

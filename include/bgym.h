@@ -317,6 +317,11 @@ int bgym_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8_t
 int bgym_episode_stats(const double* reward, const uint8_t* terminated, double* ret_acc,
                        uint32_t* len_acc, double* stats, int64_t n, void* stream);
 
+/* bgym_sample_actions with the step number kept on the device (*step_counter is read by the sampler and then
+ * incremented): the form a CUDA graph can replay, since a replayed launch cannot take a new kernel argument */
+int bgym_sample_actions_ctr(const BgymObs* obs, int32_t* actions, uint32_t seed, uint64_t* step_counter,
+                            int64_t n, void* stream);
+
 /* ---- on-device PPO rollout collection (config 5) ------------------ */
 /* Observation records -> the dense input of the reference's BalatroFeaturesExtractor.forward
  * (train_balatro_agent.py:84-113): per env BGYM_FEATURE_DIM columns =

@@ -123,3 +123,31 @@ def test_validators_batched(torch):
     assert validate.validate_determinism_vec(num_envs=8192, seed=42, steps=120)
     assert validate.validate_action_masking_vec(num_envs=8192, seed=42)
     assert validate.validate_checkpoint_roundtrip(num_envs=8192, seed=3, steps=60)
+
+
+def test_graphed_rollout_step_matches_eager(torch):
+    """The env-step replayed from a CUDA graph (sampler or fused policy) leaves exactly the state, observations,
+    rewards and actions that call-by-call launches leave."""
+    from balatro_gym_b200 import BalatroVecEnv
+    n = 1 << 17            # above the small-slab threshold: the multi-pass step with its forked gather streams
+    for policy in ("fused", "sampler"):
+        a, b = BalatroVecEnv(n, seed=9), BalatroVecEnv(n, seed=9)
+        for v in (a, b):
+            v.reset()
+            v.randomize_c3(2)
+
+        def eager():
+            if policy == "fused":
+                a.step(random_policy=True, want_info=False)
+            else:
+                a.step(a.sample_actions(seed=5), want_info=False)   # step numbers 0, 1, 2, ... like the device counter
+        replay = b.graphed_rollout_step(policy, seed=5)     # runs two real warm-up steps; the capture pass runs nothing
+        eager(); eager()
+        for _ in range(40):
+            replay()
+            eager()
+        torch.cuda.synchronize()
+        if policy == "sampler":
+            assert int(b._step_ctr.item()) == 42
+        for name in ("hot", "cold", "obs_buf", "reward", "terminated", "actions"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), (policy, name)
