@@ -1,13 +1,14 @@
 // bgym_kernels.cu — sm_100a kernels and the C-ABI (include/bgym.h) of the batched Balatro env.
 //
 // Kernels
-//   env_step_main_kernel / env_step_gather_kernel   K2  the fused, category-partitioned BalatroEnv.step
+//   env_step_main_kernel / env_step_gather_kernel / env_step_small_kernel   K2  the fused, category-partitioned BalatroEnv.step
 //                           (bgym_step_part.cuh): mask check -> phase dispatch -> scoring -> boss ->
 //                           round advance / shop generation -> reward -> observation + mask emission,
 //                           in-place autoreset (K3) and an optional fused random-legal policy
 //   env_reset_kernel    K3  reset + first observation
 //   score_hands5_kernel / score_hands_kernel   K1  classify + chips x mult + joker interpreter (K4)
 //   action_mask_kernel, sample_actions_kernel, episode_stats_kernel (K6)
+//   featurize_kernel, masked_sample_kernel, gae_kernel (bgym_rollout.cuh)   on-device PPO rollout collection
 //
 // Data movement of K2/K3: env state is two dense arrays, hot[n] (144 B records) and cold[n] (176 B
 // records).  A warp owns a tile of 32 envs; a tile of records is contiguous, so it moves between

@@ -1,6 +1,6 @@
 // bgym_step_part.cuh — the category-partitioned step.
 //
-// Why it is split (measured on B200, profiles/r01_ncu_summary.md): with every action category
+// Why it is split (measured on B200, profiles/r01_ncu_summary_history.md): with every action category
 // compiled into one kernel the step was bound by instruction fetch (84 KB of SASS walked by 12
 // warps at different PCs, ~11 of 32 lanes active, 18 % of HBM peak), while a converged select-only
 // step already ran at ~85 % of the HBM roofline.  So one env-step is split by ACTION CATEGORY into
@@ -8,12 +8,16 @@
 //
 //   main pass   (every env)    stages ONLY the hot records of each warp's tile (one bulk copy of
 //                              32 x 144 B), fully handles SELECT toggles (~83 % of random-legal
-//                              steps) and never-legal action ids of envs in PLAY phase, and appends
-//                              the env index of everything else to one of three device lists
-//                              (warp-aggregated atomics).  The cold records are never touched.
+//                              steps) and never-legal action ids of envs in PLAY phase — writing back only
+//                              the 16-byte chunk of the hot record a toggle changes — and appends the env
+//                              index of everything else to one of three device lists (staged per warp,
+//                              one atomic per run of >= 32).  The cold records are never touched.
 //   gather pass (one per list) each lane pulls ONE listed env's hot + cold record with its own bulk
 //                              copies, runs the category's path converged, pushes hot (+ cold) +
 //                              observation back.  The three passes run concurrently.
+//
+//   small slabs (n <= 65536)   one launch of the gather tile code over all envs with every category compiled
+//                              in (env_step_small_kernel): such a step is launch- and latency-bound
 //
 // The launches are stream ordered after the main pass and touch disjoint envs, so results do not
 // depend on list order.
