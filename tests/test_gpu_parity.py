@@ -143,6 +143,31 @@ def test_ragged_and_tiny_slabs_match_the_oracle(torch, n, step_path):
         _compare_step(v, ov, t)
 
 
+def test_step_without_observations(torch, step_path):
+    """BGYM_FLAG_NO_OBS with obs = NULL: same state, rewards and terminations as the observing step."""
+    import balatro_gym_b200 as b
+    from balatro_gym_b200 import BalatroVecEnv
+    lib = b.load()
+    n = 3000
+    x, y = BalatroVecEnv(n, seed=4), BalatroVecEnv(n, seed=4)
+    for v in (x, y):
+        v.reset()
+        v.randomize_c3(4)
+    flags = L.FLAG_AUTORESET | 4
+    for t in range(120):
+        x.step(random_policy=True)
+        rc = lib.bgym_step(y.hot.data_ptr(), y.cold.data_ptr(), y.actions.data_ptr(), None, None, y.reward.data_ptr(),
+                           y.terminated.data_ptr(), y.truncated.data_ptr(), y.info_buf.data_ptr(), n, flags | L.FLAG_NO_OBS,
+                           torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+    torch.cuda.synchronize()
+    for name in ("hot", "cold", "reward", "terminated", "actions", "info_buf"):
+        assert torch.equal(getattr(x, name), getattr(y, name)), name
+    # and obs = NULL without the flag is an argument error, not a crash
+    assert lib.bgym_step(y.hot.data_ptr(), y.cold.data_ptr(), y.actions.data_ptr(), None, None, y.reward.data_ptr(),
+                         y.terminated.data_ptr(), y.truncated.data_ptr(), None, n, flags, None) < 0
+
+
 def test_empty_slab_calls_are_noops(torch):
     import balatro_gym_b200 as b
     lib = b.load()
