@@ -780,13 +780,13 @@ int bgym_masked_sample(const void* logits, int dtype, const BgymObs* obs, const 
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
-  long long blocks = (n * 16 + 255) / 256;
+  long long blocks = (n + 127) / 128;
   if (blocks > 0x7fffffffLL) return set_err(BGYM_E_ARG, "bgym_masked_sample: n too large for one launch");
   if (dtype == BGYM_DT_F32)
-    masked_sample_kernel<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(logits), reinterpret_cast<const uint8_t*>(obs),
+    masked_sample_kernel<float><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(logits), reinterpret_cast<const uint8_t*>(obs),
         uniforms, seed, step, env_offset, actions, logp, entropy, n);
   else
-    masked_sample_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), reinterpret_cast<const uint8_t*>(obs),
+    masked_sample_kernel<__nv_bfloat16><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), reinterpret_cast<const uint8_t*>(obs),
         uniforms, seed, step, env_offset, actions, logp, entropy, n);
   return cuda_rc(cudaGetLastError(), "bgym_masked_sample launch");
 }

@@ -90,99 +90,74 @@ __global__ void __launch_bounds__(FEAT_ENVS_PER_CTA * FEAT_CHUNKS) featurize_ker
 }
 
 // ------------------------------------------------------------------------------------------------
-// masked categorical: 16 lanes per env (two envs per warp), lane s holds logits 4s..4s+3
+// masked categorical: one thread per env, the 60 logits of its row in registers (15 x 16-byte loads; the
+// two halves of every 32-byte sector are consumed by consecutive loads, so L1 absorbs the 240-byte row
+// stride).  Three passes over registers: max, sum of exp (+ entropy numerator), inverse-CDF scan.
+// (A 16-lanes-per-env version with half-warp shuffles was 4x the instructions per env: one Philox call per
+// two envs instead of one per 32, and reductions instead of serial adds.)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float half_max(float v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float half_sum(float v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ int half_min(int v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
 template <typename T>
-__global__ void __launch_bounds__(256) masked_sample_kernel(const T* __restrict__ logits, const uint8_t* __restrict__ obs,
+__global__ void __launch_bounds__(128) masked_sample_kernel(const T* __restrict__ logits, const uint8_t* __restrict__ obs,
                                                             const float* __restrict__ uniforms, uint32_t seed,
                                                             unsigned long long step, long long env_offset,
                                                             int32_t* __restrict__ actions, float* __restrict__ logp,
                                                             float* __restrict__ entropy, long long n) {
-  const long long gl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long env = gl >> 4;
-  const int sub = (int)(gl & 15), lane = threadIdx.x & 31;
-  const bool active = env < n;      // a whole half-warp is active or not
-  unsigned long long mask = active ? *reinterpret_cast<const unsigned long long*>(obs + env * BGYM_OBS_BYTES + 160) : 0ull;
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  unsigned long long mask = *reinterpret_cast<const unsigned long long*>(obs + env * BGYM_OBS_BYTES + 160);
   mask &= (1ull << BGYM_NUM_ACTIONS) - 1;
-  float x[4];
-  bool legal[4];
-  if (active && sub < 15) {
-    if constexpr (sizeof(T) == 4) {
-      float4 q = *reinterpret_cast<const float4*>(logits + env * BGYM_NUM_ACTIONS + sub * 4);
-      x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-    } else {
-      uint2 q = *reinterpret_cast<const uint2*>(logits + env * BGYM_NUM_ACTIONS + sub * 4);
-      __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&q.x), b = *reinterpret_cast<__nv_bfloat162*>(&q.y);
-      x[0] = __low2float(a); x[1] = __high2float(a); x[2] = __low2float(b); x[3] = __high2float(b);
+  float x[BGYM_NUM_ACTIONS];
+  if constexpr (sizeof(T) == 4) {
+    const float4* row = reinterpret_cast<const float4*>(logits + env * BGYM_NUM_ACTIONS);
+#pragma unroll
+    for (int q = 0; q < BGYM_NUM_ACTIONS / 4; q++) {
+      const float4 v = row[q];
+      x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
     }
   } else {
-    x[0] = x[1] = x[2] = x[3] = 0.0f;
-  }
+    const uint2* row = reinterpret_cast<const uint2*>(logits + env * BGYM_NUM_ACTIONS);
 #pragma unroll
-  for (int k = 0; k < 4; k++) legal[k] = sub < 15 && ((mask >> (sub * 4 + k)) & 1ull);
+    for (int q = 0; q < BGYM_NUM_ACTIONS / 4; q++) {
+      uint2 v = row[q];
+      const __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&v.x), b = *reinterpret_cast<__nv_bfloat162*>(&v.y);
+      x[4 * q] = __low2float(a); x[4 * q + 1] = __high2float(a); x[4 * q + 2] = __low2float(b); x[4 * q + 3] = __high2float(b);
+    }
+  }
   float m = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < 4; k++) if (legal[k]) m = fmaxf(m, x[k]);
-  m = half_max(m);
-  float e[4], s = 0.0f, sx = 0.0f;
+  for (int k = 0; k < BGYM_NUM_ACTIONS; k++) if ((mask >> k) & 1ull) m = fmaxf(m, x[k]);
+  float S = 0.0f, SX = 0.0f;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    e[k] = legal[k] ? expf(x[k] - m) : 0.0f;
-    s += e[k];
-    sx += legal[k] ? e[k] * (x[k] - m) : 0.0f;
-  }
-  const float S = half_sum(s);
-  const float SX = half_sum(sx);
-  // inclusive scan of the per-lane sums inside the half-warp
-  float incl = s;
-#pragma unroll
-  for (int o = 1; o < 16; o <<= 1) {
-    float up = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((lane & 15) >= o) incl += up;
+  for (int k = 0; k < BGYM_NUM_ACTIONS; k++) {
+    const bool legal = (mask >> k) & 1ull;
+    const float d = x[k] - m;
+    const float e = legal ? expf(d) : 0.0f;
+    x[k] = e;                       // the row becomes the unnormalised probabilities
+    S += e;
+    SX += legal ? e * d : 0.0f;
   }
   float u;
-  if (uniforms) u = active ? uniforms[env] : 0.0f;
+  if (uniforms) u = uniforms[env];
   else {
-    unsigned long long ge = (unsigned long long)(env + env_offset);
-    uint4 w = philox4x32_10((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)step, (uint32_t)(step >> 32), seed, BGYM_SAMPLE_KEY1);
+    const unsigned long long ge = (unsigned long long)(env + env_offset);
+    const uint4 w = philox4x32_10((uint32_t)ge, (uint32_t)(ge >> 32), (uint32_t)step, (uint32_t)(step >> 32), seed, BGYM_SAMPLE_KEY1);
     u = (float)(w.x >> 8) * (1.0f / 16777216.0f);
   }
   const float target = u * S;
-  float run = incl - s;
-  int cand = 64;
+  float run = 0.0f;
+  int a = -1;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    run += e[k];
-    if (cand == 64 && legal[k] && run > target) cand = sub * 4 + k;
+  for (int k = 0; k < BGYM_NUM_ACTIONS; k++) {
+    run += x[k];
+    a = (a < 0 && ((mask >> k) & 1ull) && run > target) ? k : a;
   }
-  int a = half_min(cand);
-  if (a == 64) a = mask ? 63 - __clzll((long long)mask) : 0;   // u*S rounded up to the total: last legal action
-  const float logZ = logf(S);                                   // relative to m
-  const int k = a & 3;
-  float mine = k == 0 ? x[0] : k == 1 ? x[1] : k == 2 ? x[2] : x[3];
-  float xa = __shfl_sync(0xffffffffu, mine, (lane & 16) | (a >> 2));
-  if (active && sub == 0) {
-    const bool any = mask != 0ull;
-    actions[env] = a;
-    logp[env] = any ? (xa - m) - logZ : 0.0f;
-    if (entropy) entropy[env] = any ? logZ - SX / S : 0.0f;
-  }
+  if (a < 0) a = mask ? 63 - __clzll((long long)mask) : 0;   // u * S rounded up to the total: last legal action
+  const bool any = mask != 0ull;
+  const float logS = logf(S);
+  const float xa = (float)logits[env * BGYM_NUM_ACTIONS + a];   // the chosen logit again (an L1 hit)
+  actions[env] = a;
+  logp[env] = any ? (xa - m) - logS : 0.0f;
+  if (entropy) entropy[env] = any ? logS - SX / S : 0.0f;
 }
 
 // ------------------------------------------------------------------------------------------------
