@@ -75,3 +75,32 @@ def test_no_cpu_fallback_without_cuda():
     import balatro_gym_b200 as b
     with pytest.raises(b.BgymError):
         b.BalatroVecEnv(4)
+
+
+def test_mask_word_expands_to_the_reference_action_mask():
+    """obs['action_mask'] of the reference (int8[60]) is carried as one 64-bit word; the Python layers expand it."""
+    rng = np.random.default_rng(0)
+    bits = rng.integers(0, 1 << 60, size=257, dtype=np.uint64)
+    m = L.mask_from_bits(bits)
+    assert m.shape == (257, 60) and m.dtype == np.int8
+    back = (m.astype(np.uint64) << np.arange(60, dtype=np.uint64)).sum(axis=1, dtype=np.uint64)
+    assert np.array_equal(back, bits)
+    assert L.mask_from_bits(np.uint64(0b1011)).tolist()[:5] == [1, 1, 0, 1, 0]
+    rec = np.zeros(3, dtype=L.OBS_DTYPE)
+    rec["action_mask_bits"] = [1, 2, (1 << 59)]
+    assert L.obs_value(rec, "action_mask")[:, [0, 1, 59]].tolist() == [[1, 0, 0], [0, 1, 0], [0, 0, 1]]
+    assert L.obs_value(rec, "money") is not None and "action_mask" in L.OBS_KEYS and "action_mask" not in L.OBS_DTYPE.names
+    assert len(L.OBS_KEYS) == 31
+
+
+def test_sb3_seed_chain_matches_the_kernels_constants():
+    """next_episode_seed (host mirror of the in-kernel autoreset seed chain): fixed vectors."""
+    from balatro_gym_b200.sb3_vec_env import next_episode_seed
+    def ref(x):
+        x = (x + 0x9E3779B9) & 0xFFFFFFFF
+        x ^= x >> 16; x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+        x ^= x >> 13; x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+        x ^= x >> 16
+        return x or 1
+    xs = np.array([1, 2, 12345, 0xFFFFFFFF, 0x61C88647], dtype=np.uint32)
+    assert next_episode_seed(xs).tolist() == [ref(int(x)) for x in xs]
