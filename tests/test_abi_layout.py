@@ -104,3 +104,15 @@ def test_sb3_seed_chain_matches_the_kernels_constants():
         return x or 1
     xs = np.array([1, 2, 12345, 0xFFFFFFFF, 0x61C88647], dtype=np.uint32)
     assert next_episode_seed(xs).tolist() == [ref(int(x)) for x in xs]
+
+
+def test_plain_c_caller_compiles_and_links():
+    """examples/host_loop.c: the boundary is usable from C with nothing but include/bgym.h and libbgym.so."""
+    _lib.load()
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "host_loop")
+        subprocess.check_call(["gcc", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"), "-o", exe,
+                               os.path.join(REPO, "examples", "host_loop.c"), "-L", os.path.dirname(_lib.SO_PATH), "-lbgym",
+                               "-Wl,-rpath," + os.path.dirname(_lib.SO_PATH)])
+        rc = subprocess.call([exe, "16", "2"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert rc in (0, 2)     # 2 = "no CUDA device" (this container); 0 on a GPU box

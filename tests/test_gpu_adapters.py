@@ -151,3 +151,19 @@ def test_graphed_rollout_step_matches_eager(torch):
             assert int(b._step_ctr.item()) == 42
         for name in ("hot", "cold", "obs_buf", "reward", "terminated", "actions"):
             assert torch.equal(getattr(a, name), getattr(b, name)), (policy, name)
+
+
+def test_plain_c_caller_runs(torch, tmp_path):
+    """examples/host_loop.c against the library on the GPU: a C program steps 4096 envs from host buffers."""
+    import os
+    import subprocess
+    from conftest import REPO
+    from balatro_gym_b200 import _lib
+    exe = str(tmp_path / "host_loop")
+    subprocess.check_call(["gcc", "-Wall", "-I", os.path.join(REPO, "include"), "-o", exe,
+                           os.path.join(REPO, "examples", "host_loop.c"), "-L", os.path.dirname(_lib.SO_PATH), "-lbgym",
+                           "-Wl,-rpath," + os.path.dirname(_lib.SO_PATH)])
+    out = subprocess.check_output([exe, "4096", "200"], text=True)
+    assert "env-steps/s" in out and "episodes finished" in out
+    episodes = int(out.split("env-steps/s,")[1].split("episodes")[0])
+    assert episodes > 1000        # random play ends episodes all the time: the autoreset path ran
