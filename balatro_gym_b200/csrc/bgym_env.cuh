@@ -527,6 +527,51 @@ __device__ __forceinline__ uint32_t next_episode_seed(uint32_t seed) {
   return x ? x : 1u;
 }
 
+// ---------------------------------------------------------------------------------------------
+// synthetic-state generator of BASELINE configs[2]/[3] (BGYM_FLAG_GEN_C3 / BGYM_FLAG_GEN_CONS; the law is
+// specified in include/bgym.h, the reference-side counterpart is the injection recipe of SURVEY Appendix E)
+// ---------------------------------------------------------------------------------------------
+// modifier bits (enhancement << 6 | edition << 10 | seal << 13) of card k = suit * 13 + rank - 2
+__device__ __forceinline__ int gen_card_mods(uint32_t seed, int k) {
+  const uint4 b = philox4x32_10((uint32_t)k, 0, 0, 0, seed, BGYM_GEN_KEY1);
+  const int enh = (b.x >> 30) == 0u ? 1 + (int)((b.x >> 27) & 7u) : 0;
+  const int e = (int)__umulhi(b.y, 30u), sl = (int)__umulhi(b.z, 40u);
+  return (enh << 6) | ((e < 3 ? 1 + e : 0) << 10) | ((sl < 4 ? 1 + sl : 0) << 13);
+}
+__device__ __forceinline__ int gen_cons_id(uint32_t w) {
+  const int i = (int)__umulhi(w, 52u);
+  return i < 22 ? BGYM_CONS_TAROT_BASE + i : (i < 34 ? BGYM_CONS_PLANET_BASE + (i - 22) : BGYM_CONS_SPECTRAL_BASE + (i - 34));
+}
+// jokers (five distinct shop-eligible ids, draw order) and, with BGYM_FLAG_GEN_CONS, both consumable slots
+__device__ __noinline__ void gen_hot_fields(uint32_t seed, int flags, uint64_t* jokers_out, uint32_t* cons_out) {
+  const uint4 a = philox4x32_10(64u, 0, 0, 0, seed, BGYM_GEN_KEY1);
+  const uint4 b = philox4x32_10(65u, 0, 0, 0, seed, BGYM_GEN_KEY1);
+  const uint32_t w[5] = {a.x, a.y, a.z, a.w, b.x};
+  int chosen[5];   // pool positions picked so far, ascending
+  uint64_t jk = 0;
+#pragma unroll
+  for (int t = 0; t < 5; t++) {
+    int p = (int)__umulhi(w[t], (uint32_t)(BGYM_NUM_SHOP_JOKERS - t));
+#pragma unroll
+    for (int q = 0; q < t; q++) if (chosen[q] <= p) p++;      // p-th position not picked yet
+    jk |= (uint64_t)(p + 1) << (8 * t);
+    chosen[t] = p;                                            // one bubble pass keeps `chosen` ascending
+#pragma unroll
+    for (int q = t; q > 0; q--) {
+      const int lo = min(chosen[q - 1], chosen[q]), hi = max(chosen[q - 1], chosen[q]);
+      chosen[q - 1] = lo; chosen[q] = hi;
+    }
+  }
+  *jokers_out = jk;
+  *cons_out = (flags & BGYM_FLAG_GEN_CONS) ? ((uint32_t)gen_cons_id(b.y) | ((uint32_t)gen_cons_id(b.z) << 8)) : 0u;
+}
+__device__ __forceinline__ void gen_hot(Hot& h, uint32_t seed, int flags) {
+  uint64_t jk; uint32_t cs;
+  gen_hot_fields(seed, flags, &jk, &cs);
+  h.jokers = jk; h.joker_n = 5;
+  if (flags & BGYM_FLAG_GEN_CONS) { h.cons = cs; h.cons_n = 2; }
+}
+
 // hot block of a fresh episode (UnifiedGameState defaults)
 __device__ __forceinline__ void reset_hot(Hot& h, uint32_t seed) {
   h.hand = ~0ull; h.hand_code = ~0ull;
@@ -548,16 +593,19 @@ __device__ __forceinline__ void reset_hot(Hot& h, uint32_t seed) {
 //   deck52 != nullptr: replay of a supplied permutation (the reference's MT19937 shuffle stream)
 //   else: suit-major build (balatro_env_2.py:519-522) + Fisher-Yates in random.shuffle's order
 //         (for i in reversed(range(1, n)): j = randbelow(i + 1); swap) with native Philox draws
-__device__ __noinline__ void reset_blocks_serial(uint8_t* rec, uint32_t seed, const uint8_t* deck52) {
+__device__ __noinline__ void reset_blocks_serial(uint8_t* rec, uint32_t seed, const uint8_t* deck52, bool gen) {
 #pragma unroll 1
   for (int o = 0; o < BGYM_COLD_BYTES; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
   if (deck52) {
 #pragma unroll 1
-    for (int i = 0; i < 52; i++) set_deck16(rec, i, deck52[i]);
+    for (int i = 0; i < 52; i++) {
+      const int code = deck52[i];
+      set_deck16(rec, i, code | (gen ? gen_card_mods(seed, (code & 3) * 13 + (code >> 2)) : 0));
+    }
     return;
   }
 #pragma unroll 1
-  for (int i = 0; i < 52; i++) set_deck16(rec, i, (i % 13) * 4 + i / 13);
+  for (int i = 0; i < 52; i++) set_deck16(rec, i, ((i % 13) * 4 + i / 13) | (gen ? gen_card_mods(seed, i) : 0));
   uint4 blk = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
   for (int i = 51; i >= 1; i--) {
@@ -576,11 +624,12 @@ __device__ __noinline__ void reset_blocks_serial(uint8_t* rec, uint32_t seed, co
 //   finish  (each terminated lane for itself, all of them in parallel): apply the 51 swaps in
 //            random.shuffle's order, then clear the parked draws.
 constexpr int OFF_RESET_SCRATCH = 116;  // shop part of the cold record, 52 bytes used
-__device__ __forceinline__ void reset_blocks_prepare(uint8_t* rec_of_src, uint32_t seed, int lane) {
+__device__ __forceinline__ void reset_blocks_prepare(uint8_t* rec_of_src, uint32_t seed, int lane, bool gen) {
   if (lane < 11) sts128(rec_of_src + 16 * lane, make_uint4(0, 0, 0, 0));
   __syncwarp();
-  set_deck16(rec_of_src, lane, (lane % 13) * 4 + lane / 13);
-  if (lane < 20) set_deck16(rec_of_src, lane + 32, ((lane + 32) % 13) * 4 + (lane + 32) / 13);
+  // generated modifiers are attached to the card before the shuffle and travel with it (include/bgym.h)
+  set_deck16(rec_of_src, lane, ((lane % 13) * 4 + lane / 13) | (gen ? gen_card_mods(seed, lane) : 0));
+  if (lane < 20) set_deck16(rec_of_src, lane + 32, (((lane + 32) % 13) * 4 + (lane + 32) / 13) | (gen ? gen_card_mods(seed, lane + 32) : 0));
   // lane l (< 26) owns block l -> draws for i = 2l+1 and i = 2l+2
   uint4 blk = philox4x32_10((uint32_t)lane, 0, 0, 0, seed, BGYM_SHUFFLE_KEY1);
   if (lane < 26) {
@@ -599,7 +648,7 @@ __device__ __forceinline__ void reset_blocks_finish(uint8_t* rec) {
   for (int o = 112; o < BGYM_COLD_BYTES; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
 }
 // warp-level driver: `want_reset` lanes get fresh deck/shop blocks in their record `my_rec`
-__device__ __forceinline__ void autoreset_warp(bool want_reset, uint32_t new_seed, uint8_t* my_rec, int lane) {
+__device__ __forceinline__ void autoreset_warp(bool want_reset, uint32_t new_seed, uint8_t* my_rec, int lane, bool gen) {
   uint32_t rmask = __ballot_sync(0xffffffffu, want_reset);
   if (!rmask) return;
   unsigned long long my_ptr = reinterpret_cast<unsigned long long>(my_rec);
@@ -609,7 +658,7 @@ __device__ __forceinline__ void autoreset_warp(bool want_reset, uint32_t new_see
     m &= m - 1;
     uint32_t sd = __shfl_sync(0xffffffffu, new_seed, src);
     uint8_t* rec_src = reinterpret_cast<uint8_t*>(__shfl_sync(0xffffffffu, my_ptr, src));
-    reset_blocks_prepare(rec_src, sd, lane);
+    reset_blocks_prepare(rec_src, sd, lane, gen);
   }
   __syncwarp();
   if (want_reset) reset_blocks_finish(my_rec);

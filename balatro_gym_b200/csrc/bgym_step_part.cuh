@@ -269,12 +269,13 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, uint8_t* hot_buf,
       uint32_t episode = h.episode + 1;
       new_seed = next_episode_seed(h.rng_seed);
       reset_hot(h, new_seed);
+      if (a.flags & BGYM_FLAG_GEN_C3) gen_hot(h, new_seed, a.flags);
       h.episode = episode;
       info.flags |= BGYM_F_AUTORESET_DONE;
       want_reset = true;
     }
   }
-  if (a.flags & BGYM_FLAG_AUTORESET) autoreset_warp(want_reset, new_seed, cold, lane);
+  if (a.flags & BGYM_FLAG_AUTORESET) autoreset_warp(want_reset, new_seed, cold, lane, (a.flags & BGYM_FLAG_GEN_C3) != 0);
   ShopObs so;
   uint64_t m1 = 0;
   if (active) {

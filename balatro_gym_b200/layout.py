@@ -26,7 +26,9 @@ A_SELECT_BLIND_BASE, A_SKIP_BLIND = 45, 48
 ERR_NONE, ERR_INVALID_ACTION, ERR_BOSS_RESTRICTION, ERR_CONSUMABLE_FAILED = 0, 1, 2, 3
 ERR_SHOP, ERR_REF_EXCEPTION, ERR_UNSUPPORTED = 4, 5, 6
 F_BEAT_BLIND, F_FAILED, F_GUARD_TERMINATED, F_PLAYED, F_AUTORESET_DONE, F_SHOP_DONE = 1, 2, 4, 8, 16, 32
-FLAG_AUTORESET, FLAG_NO_OBS = 1, 2
+FLAG_AUTORESET, FLAG_NO_OBS, FLAG_RANDOM_POLICY, FLAG_GEN_C3, FLAG_GEN_CONS = 1, 2, 4, 8, 16
+# state generator of BASELINE configs[2] / configs[3] (include/bgym.h): applied by reset AND by the in-kernel autoreset
+GENERATORS = {None: 0, "c3": FLAG_GEN_C3, "c4": FLAG_GEN_C3 | FLAG_GEN_CONS}
 SCORE_TABLE_NAMES = 1
 
 

@@ -92,11 +92,16 @@ class BalatroVecEnv:
     autoreset: re-initialise terminated envs inside the step kernel (same-step autoreset)
     env_offset: global index of the first env of this slab (multi-GPU: results do not depend on
                the number of GPUs because seeds are a function of the global env index)
+    generator: None (the reference's reset state), "c3" or "c4": every episode — the ones started by
+               reset() and the ones started by the in-kernel autoreset — begins from the synthetic state of
+               BASELINE configs[2] / configs[3] (5 random jokers, card enhancements / editions / seals;
+               "c4" also fills the two consumable slots); BGYM_FLAG_GEN_C3 / BGYM_FLAG_GEN_CONS in include/bgym.h
     """
 
     num_actions = L.NUM_ACTIONS
 
-    def __init__(self, num_envs: int, device="cuda", seed: int = 1, autoreset: bool = True, env_offset: int = 0):
+    def __init__(self, num_envs: int, device="cuda", seed: int = 1, autoreset: bool = True, env_offset: int = 0,
+                 generator: Optional[str] = None):
         torch = _lib.require_cuda()
         self.torch = torch
         self.lib = _lib.load()
@@ -107,6 +112,10 @@ class BalatroVecEnv:
         self.autoreset = bool(autoreset)
         self.base_seed = int(seed)
         self.env_offset = int(env_offset)
+        if generator not in L.GENERATORS:
+            raise ValueError(f"generator must be one of {list(L.GENERATORS)}")
+        self.generator = generator
+        self._gen_flags = L.GENERATORS[generator]
         n, dev = self.num_envs, self.device
         with torch.cuda.device(dev):
             # env state = two dense record arrays (include/bgym.h): hot (144 B) and cold (176 B)
@@ -185,7 +194,7 @@ class BalatroVecEnv:
             reset_mask = torch.as_tensor(reset_mask, device=self.device).to(torch.uint8).contiguous()
         with torch.cuda.device(self.device):
             rc = self.lib.bgym_reset(self.hot.data_ptr(), self.cold.data_ptr(), self.obs_buf.data_ptr(), self._ptr(reset_mask),
-                                     seeds32.data_ptr(), self._ptr(decks52), self.num_envs, 0, self._stream())
+                                     seeds32.data_ptr(), self._ptr(decks52), self.num_envs, self._gen_flags, self._stream())
         _lib.check(rc, "bgym_reset")
         self._keep = (seeds32, decks52, reset_mask)  # keep inputs alive until the stream has consumed them
         return self.obs
@@ -207,7 +216,7 @@ class BalatroVecEnv:
             act = actions
         else:
             act = self.actions
-        flags = (L.FLAG_AUTORESET if self.autoreset else 0) | (4 if random_policy else 0)
+        flags = (L.FLAG_AUTORESET if self.autoreset else 0) | (L.FLAG_RANDOM_POLICY if random_policy else 0) | self._gen_flags
         if draws is not None:
             draws = torch.as_tensor(draws, device=self.device).contiguous()
             assert draws.dtype == torch.uint8 and draws.shape == (self.num_envs, L.DRAWS_BYTES)
@@ -248,7 +257,7 @@ class BalatroVecEnv:
         assert policy in ("sampler", "fused")
         if not hasattr(self, "_step_ctr"):
             self._step_ctr = torch.zeros(1, dtype=torch.int64, device=self.device)
-        flags = (L.FLAG_AUTORESET if self.autoreset else 0) | (4 if policy == "fused" else 0)
+        flags = (L.FLAG_AUTORESET if self.autoreset else 0) | (L.FLAG_RANDOM_POLICY if policy == "fused" else 0) | self._gen_flags
 
         def launch():
             st = self._stream()

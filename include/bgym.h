@@ -108,10 +108,27 @@ enum {
   BGYM_FLAG_AUTORESET = 1,  /* step: a terminated env is re-initialised in place (native Philox shuffle)
                                and the returned observation is the first of the new episode */
   BGYM_FLAG_NO_OBS = 2,     /* skip observation emission (obs may be NULL) */
-  BGYM_FLAG_RANDOM_POLICY = 4 /* step: every env draws its own uniform random LEGAL action from its mask
+  BGYM_FLAG_RANDOM_POLICY = 4,/* step: every env draws its own uniform random LEGAL action from its mask
                                (the policy the reference is benchmarked with); `actions` becomes an
                                OUTPUT array that receives the chosen actions */
+  /* Synthetic-state generator of BASELINE configs[2]/[3] (the reference-side
+   * counterpart is the injection recipe of SURVEY Appendix E, oracle/refbaseline.py::_inject_c3).
+   * Honoured by bgym_reset AND by the in-kernel autoreset of bgym_step, so every episode of a long
+   * rollout starts from a generated state, not only the first.  All draws come from Philox4x32-10
+   * keyed (episode seed, BGYM_GEN_KEY1); integer draws are floor(word * n / 2^32) (|p - 1/n| < n / 2^32).
+   *   card k of the freshly built deck (k = suit * 13 + rank - 2, balatro_env_2.py:519-522), block counter k:
+   *     enhancement: word x, top two bits zero (p = 1/4) -> 1 + next three bits (uniform over the 8)
+   *     edition:     e = floor(y * 30 / 2^32) < 3 (p = 1/10) -> 1 + e (FOIL, HOLO, POLY)
+   *     seal:        s = floor(z * 40 / 2^32) < 4 (p = 1/10) -> 1 + s
+   *     the modifiers travel with the card through the shuffle (i.i.d., so position-keyed is the same law)
+   *   jokers: blocks 64, 65: five draws without replacement over the BGYM_NUM_SHOP_JOKERS ids with
+   *     base_cost > 0 (draw t picks the floor(w_t * (145 - t) / 2^32)-th id not chosen yet), in draw order */
+  BGYM_FLAG_GEN_C3 = 8,
+  /* with BGYM_FLAG_GEN_C3: additionally fill both consumable slots, each uniform over the 52 consumable
+   * names of the reference (tarots 1..22, planets 30..41, spectrals 50..67): words y, z of block 65 */
+  BGYM_FLAG_GEN_CONS = 16
 };
+#define BGYM_GEN_KEY1 0xB200C3C4u
 /* flags argument of bgym_score_hands */
 enum {
   BGYM_SCORE_TABLE_NAMES = 1 /* hand names as complete_joker_effects.py:64-80 expects ('Pair',

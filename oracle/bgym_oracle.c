@@ -545,7 +545,46 @@ static uint32_t next_episode_seed(uint32_t seed) { /* autoreset: seed of the fol
   return x ? x : 1u;
 }
 
-static void reset_env(BgymState* s, uint32_t seed, const uint8_t* deck52) {
+/* Synthetic-state generator of BASELINE configs[2]/[3] (BGYM_FLAG_GEN_C3 / BGYM_FLAG_GEN_CONS).  This is
+ * not reference code: the reference has no generator (SURVEY 8(d) C3/C4 defines the distributions, Appendix E
+ * the injection recipe); the law below is the one include/bgym.h specifies, restated with lists. */
+static uint32_t gen_scaled(uint32_t word, uint32_t n) { return (uint32_t)(((uint64_t)word * n) >> 32); }
+
+static uint16_t gen_card_mods(uint32_t seed, int k) { /* card k = suit * 13 + rank - 2 */
+  uint32_t w[4];
+  philox4x32_10((uint32_t)k, 0, 0, 0, seed, BGYM_GEN_KEY1, w);
+  unsigned enh = 0, ed = 0, seal = 0;
+  if ((w[0] >> 30) == 0) enh = 1 + ((w[0] >> 27) & 7);          /* 1/4, then uniform over the 8 enhancements */
+  uint32_t e = gen_scaled(w[1], 30); if (e < 3) ed = 1 + e;     /* 1/10 over FOIL, HOLO, POLY */
+  uint32_t t = gen_scaled(w[2], 40); if (t < 4) seal = 1 + t;   /* 1/10 over the four seals */
+  return (uint16_t)((enh << 6) | (ed << 10) | (seal << 13));
+}
+
+static void gen_jokers_consumables(BgymState* s, uint32_t seed, int flags) {
+  uint32_t a[4], b[4];
+  philox4x32_10(64, 0, 0, 0, seed, BGYM_GEN_KEY1, a);
+  philox4x32_10(65, 0, 0, 0, seed, BGYM_GEN_KEY1, b);
+  uint32_t words[5] = {a[0], a[1], a[2], a[3], b[0]};
+  int pool[BGYM_NUM_SHOP_JOKERS], n_pool = BGYM_NUM_SHOP_JOKERS;   /* ids with base_cost > 0, ascending */
+  for (int i = 0; i < n_pool; i++) pool[i] = i + 1;
+  for (int t = 0; t < 5; t++) {                                    /* sample without replacement, draw order */
+    int p = (int)gen_scaled(words[t], (uint32_t)n_pool);
+    s->joker_id[t] = (uint8_t)pool[p];
+    for (int i = p; i + 1 < n_pool; i++) pool[i] = pool[i + 1];
+    n_pool--;
+  }
+  s->joker_n = 5;
+  if (flags & BGYM_FLAG_GEN_CONS) {
+    static const uint8_t ALL_IDS[52] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22,
+                                        30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41,
+                                        50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65, 66, 67};
+    s->cons_id[0] = ALL_IDS[gen_scaled(b[1], 52)];
+    s->cons_id[1] = ALL_IDS[gen_scaled(b[2], 52)];
+    s->cons_n = 2;
+  }
+}
+
+static void reset_env(BgymState* s, uint32_t seed, const uint8_t* deck52, int flags) {
   memset(s, 0, sizeof *s);
   s->ante = 1; s->round = 1; s->phase = BGYM_PHASE_BLIND_SELECT;
   s->chips_needed = 300; s->money = 4;
@@ -557,14 +596,20 @@ static void reset_env(BgymState* s, uint32_t seed, const uint8_t* deck52) {
   memset(s->hand, 0xFF, 8);
   memset(s->hand_code, 0xFF, 8);
   s->rng_seed = seed; s->rng_ctr = 0;
+  const int gen = (flags & BGYM_FLAG_GEN_C3) != 0;
+  if (gen) gen_jokers_consumables(s, seed, flags);
   if (deck52) {
-    for (int i = 0; i < 52; i++) s->deck[i] = deck52[i];
+    for (int i = 0; i < 52; i++) {
+      int rank = code_rank(deck52[i]), suit = code_suit(deck52[i]);
+      s->deck[i] = (uint16_t)(deck52[i] | (gen ? gen_card_mods(seed, suit * 13 + rank - 2) : 0));
+    }
   } else {
     /* suit-major, rank-minor build (:519-522) then Fisher-Yates exactly as random.shuffle:
      * for i in reversed(range(1, n)): j = randbelow(i + 1); swap */
     int k = 0;
     for (int suit = 0; suit < 4; suit++)
-      for (int rank = 2; rank <= 14; rank++) s->deck[k++] = (uint16_t)((rank - 2) * 4 + suit);
+      for (int rank = 2; rank <= 14; rank++, k++)
+        s->deck[k] = (uint16_t)(((rank - 2) * 4 + suit) | (gen ? gen_card_mods(seed, k) : 0));
     /* native draws of the shuffle: j_i comes from Philox block (i-1)/2 keyed (seed, SHUFFLE key),
      * words (0,1) for odd i, (2,3) for even i, so the 51 draws are independent of each other (the
      * kernel computes them lane-parallel); bounded by Lemire's multiply-shift, second word on the
@@ -586,7 +631,7 @@ int oracle_reset(BgymState* state, BgymObs* obs, const uint8_t* reset_mask, cons
                  const uint8_t* decks52, int64_t n, int flags) {
   for (int64_t i = 0; i < n; i++) {
     if (reset_mask && !reset_mask[i]) continue;
-    reset_env(&state[i], seeds[i], decks52 ? decks52 + i * 52 : NULL);
+    reset_env(&state[i], seeds[i], decks52 ? decks52 + i * 52 : NULL, flags);
     if (obs && !(flags & BGYM_FLAG_NO_OBS)) write_obs(&state[i], &obs[i]);
   }
   return 0;
@@ -1297,7 +1342,7 @@ int oracle_step(BgymState* state, int32_t* actions, const BgymDraws* draws, Bgym
     if (truncated) truncated[i] = 0;
     if (terminated[i] && (flags & BGYM_FLAG_AUTORESET)) {
       uint32_t episode = state[i].episode + 1;
-      reset_env(&state[i], next_episode_seed(state[i].rng_seed), NULL);
+      reset_env(&state[i], next_episode_seed(state[i].rng_seed), NULL, flags);
       state[i].episode = episode;
       inf.flags |= BGYM_F_AUTORESET_DONE;
     }

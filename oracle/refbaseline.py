@@ -13,7 +13,18 @@ import time
 import numpy as np
 
 
-def _inject_c3(env, R, rng):
+_ALL_CONSUMABLES = None
+
+
+def _inject_c3(env, R, rng, consumables=False):
+    """SURVEY 8(d) C3 state generator (Appendix E recipe), per episode; consumables=True adds config 4's two random
+    consumables over all 52 names (the device-side counterpart is BGYM_FLAG_GEN_C3 | BGYM_FLAG_GEN_CONS)."""
+    global _ALL_CONSUMABLES
+    if consumables:
+        if _ALL_CONSUMABLES is None:
+            from balatro_gym_b200 import layout as L
+            _ALL_CONSUMABLES = L.TAROT_NAMES + L.PLANET_NAMES + L.SPECTRAL_NAMES
+        env.state.consumables = [_ALL_CONSUMABLES[int(rng.integers(0, 52))] for _ in range(2)]
     costs = [j for j in R.jokers.JOKER_LIBRARY if j.base_cost > 0]
     idx = rng.choice(len(costs), size=5, replace=False)
     env.state.jokers = [costs[i] for i in idx]
@@ -38,7 +49,7 @@ def _env_worker(rank, config, steps_per_round, rounds, q):
         seed += 1
         obs, _ = env.reset(seed=seed)
         if config != "c1":
-            _inject_c3(env, R, rng)
+            _inject_c3(env, R, rng, consumables=(config == "c4"))
         return obs
 
     obs = new_episode()

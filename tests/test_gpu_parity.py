@@ -92,20 +92,26 @@ def _compare_step(v, ov, t, check_info=True):
         assert_records_equal(ov.info, inf, L.INFO_DTYPE, (), f"step {t} info")
 
 
-@pytest.mark.parametrize("n,steps,c3", [(4096, 260, False), (4096, 260, True), (1000, 120, True)])
-def test_cuda_vs_oracle_native_rollout(torch, n, steps, c3, step_path):
-    """Fused random-legal policy + autoreset on both sides: > 10^6 env-steps compared record by record."""
+@pytest.mark.parametrize("n,steps,mode", [(4096, 260, "vanilla"), (4096, 260, "host_c3"), (1000, 120, "host_c3"),
+                                          (4096, 260, "c3"), (4096, 400, "c4"), (1000, 120, "c4")])
+def test_cuda_vs_oracle_native_rollout(torch, n, steps, mode, step_path):
+    """Fused random-legal policy + autoreset on both sides: > 10^6 env-steps compared record by record.
+    mode: vanilla = the reference's reset state; host_c3 = config-3 state scattered once from the host;
+    c3 / c4 = the device-side state generator (BGYM_FLAG_GEN_C3 [| BGYM_FLAG_GEN_CONS]) applied by reset and by
+    every in-kernel autoreset, mirrored by the oracle."""
     from balatro_gym_b200 import BalatroVecEnv
     from oracle import coracle
-    v = BalatroVecEnv(n, seed=1, autoreset=True)
+    gen = mode if mode in ("c3", "c4") else None
+    gflags = L.GENERATORS[gen]
+    v = BalatroVecEnv(n, seed=1, autoreset=True, generator=gen)
     v.reset()
-    if c3:
+    if mode == "host_c3":
         v.randomize_c3(seed=5)
     ov = coracle.OracleVec(n)
-    ov.reset(np.arange(1, n + 1))
+    coracle.reset(ov.state, ov.obs, np.arange(1, n + 1), flags=gflags)
     st0 = v.state_numpy()
-    if not c3:
-        assert_records_equal(ov.state, st0, L.STATE_DTYPE, (), "reset state")   # native Philox shuffle parity
+    if mode != "host_c3":
+        assert_records_equal(ov.state, st0, L.STATE_DTYPE, (), "reset state")   # native Philox shuffle (+ generator) parity
         assert_records_equal(ov.obs, v.obs_numpy(), L.OBS_DTYPE, (), "reset obs")
     ov.state[:] = st0
     rng = np.random.default_rng(3)
@@ -113,15 +119,73 @@ def test_cuda_vs_oracle_native_rollout(torch, n, steps, c3, step_path):
         if t % 7 == 3:   # explicit actions incl. masked / out-of-range ones
             act = rng.integers(-2, 62, size=n).astype(np.int32)
             v.step(torch.from_numpy(act).cuda())
-            ov.step(act, flags=L.FLAG_AUTORESET)
+            ov.step(act, flags=L.FLAG_AUTORESET | gflags)
         else:
             v.step(random_policy=True)
             oact = np.zeros(n, np.int32)
             coracle.step(ov.state, oact, ov.obs, ov.reward, ov.terminated, ov.truncated, ov.info, None,
-                         flags=L.FLAG_AUTORESET | 4)
+                         flags=L.FLAG_AUTORESET | L.FLAG_RANDOM_POLICY | gflags)
             assert np.array_equal(oact, v.actions.cpu().numpy()), f"policy actions differ at step {t}"
         _compare_step(v, ov, t)
-    assert int(v.state_numpy()["episode"].sum()) > 0      # autoreset happened
+    st = v.state_numpy()
+    assert int(st["episode"].sum()) > 0      # autoreset happened
+    if gen:
+        # every env still carries generator state, however many episodes it has been through
+        assert ((st["deck"] >> 6) != 0).any(axis=1).all()
+        if gen == "c4":     # consumables were used (the OTHER gather list's rare path ran)
+            assert int((st["cons_n"] < 2).sum()) > n // 8
+
+
+def test_generator_reset_law_and_replayed_decks(torch):
+    """BGYM_FLAG_GEN_C3 | BGYM_FLAG_GEN_CONS at reset: CUDA == oracle bit for bit (native shuffle and a replayed
+    permutation), and the generated state follows SURVEY 8(d) C3: 5 distinct shop-eligible jokers, enhancement w.p.
+    1/4 over 8, edition w.p. 1/10 over 3, seal w.p. 1/10 over 4, two consumables over the 52 names."""
+    from balatro_gym_b200 import BalatroVecEnv
+    from oracle import coracle
+    n = 1 << 16
+    v = BalatroVecEnv(n, seed=1000, autoreset=False, generator="c4")
+    v.reset()
+    ov = coracle.OracleVec(n)
+    coracle.reset(ov.state, ov.obs, np.arange(1000, n + 1000), flags=L.GENERATORS["c4"])
+    st = v.state_numpy()
+    assert_records_equal(ov.state, st, L.STATE_DTYPE, (), "generated reset state")
+    assert_records_equal(ov.obs, v.obs_numpy(), L.OBS_DTYPE, (), "generated reset obs")
+    jk = st["joker_id"][:, :5].astype(int)
+    assert (st["joker_n"] == 5).all() and jk.min() >= 1 and jk.max() <= 145 and (st["joker_id"][:, 5:] == 0).all()
+    assert (np.diff(np.sort(jk, axis=1), axis=1) > 0).all()                      # distinct
+    cnt = np.bincount(jk.ravel(), minlength=146)[1:]
+    e = n * 5 / 145.0
+    assert abs(((cnt - e) ** 2 / e).sum() - 144) < 6 * (2 * 144) ** 0.5          # every id equally likely
+    deck = st["deck"].astype(int)
+    assert (np.sort(deck & 63, axis=1) == np.arange(52)).all()
+    enh, ed, seal = (deck >> 6) & 15, (deck >> 10) & 7, (deck >> 13) & 7
+    N = n * 52
+    for arr, p, k in ((enh, 0.25, 8), (ed, 0.1, 3), (seal, 0.1, 4)):
+        assert arr.max() == k
+        assert abs((arr != 0).mean() - p) < 5 * (p * (1 - p) / N) ** 0.5
+        c = np.bincount(arr.ravel(), minlength=k + 1)[1:]
+        assert abs(((c - c.mean()) ** 2 / c.mean()).sum() - (k - 1)) < 6 * (2 * (k - 1)) ** 0.5 + 6
+    cons = st["cons_id"][:, :2].astype(int)
+    assert (st["cons_n"] == 2).all()
+    ids = np.array(list(range(1, 23)) + list(range(30, 42)) + list(range(50, 68)))
+    assert np.isin(cons, ids).all()
+    cc = np.array([(cons == i).sum() for i in ids])
+    e = n * 2 / 52.0
+    assert abs(((cc - e) ** 2 / e).sum() - 51) < 6 * (2 * 51) ** 0.5
+    # a replayed permutation (the reference's shuffle stream) keeps each card's generated modifiers
+    rng = np.random.default_rng(0)
+    m = 512
+    decks = np.argsort(rng.random((m, 52)), axis=1).astype(np.uint8)
+    v2 = BalatroVecEnv(m, seed=1000, autoreset=False, generator="c3")
+    v2.reset(decks52=torch.from_numpy(decks))
+    ov2 = coracle.OracleVec(m)
+    coracle.reset(ov2.state, ov2.obs, np.arange(1000, m + 1000), decks52=decks, flags=L.GENERATORS["c3"])
+    s2 = v2.state_numpy()
+    assert_records_equal(ov2.state, s2, L.STATE_DTYPE, (), "generated reset state, replayed decks")
+    assert (s2["deck"] & 63 == decks).all() and (s2["cons_n"] == 0).all()
+    a = np.take_along_axis(s2["deck"], np.argsort(s2["deck"] & 63, axis=1), axis=1)      # by card identity
+    b = np.take_along_axis(st["deck"][:m], np.argsort(st["deck"][:m] & 63, axis=1), axis=1)
+    assert (a == b).all()
 
 
 @pytest.mark.parametrize("n", [1, 31, 33, 97])
