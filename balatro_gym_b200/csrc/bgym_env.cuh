@@ -14,7 +14,10 @@ namespace bgym {
 
 // offsets inside the cold record (BgymCold, include/bgym.h)
 constexpr int OFF_DECK = 0, OFF_HPC = 104, OFF_ITEM_TYPE = 116, OFF_ITEM_ID = 125, OFF_N_ITEMS = 134,
-              OFF_ITEM_COST = 136, OFF_REROLL = 172;
+              OFF_EXTRA_N = 135, OFF_ITEM_COST = 136, OFF_REROLL = 172;
+// hot record bytes 136..143: deck_extra[4] (cards appended by Cryptid).  They are NOT part of struct Hot: only the
+// consumable path reads or writes them, in the packed record; pack_hot leaves them alone.
+constexpr int OFF_HOT_EXTRA = 136, MAX_DECK_EXTRA = 4;
 
 enum { B_HOOK = 1, B_WALL, B_WHEEL, B_HOUSE, B_MARK, B_FISH, B_PSYCHIC, B_GOAD, B_WATER, B_WINDOW,
        B_MANACLE, B_EYE, B_MOUTH, B_PLANT, B_SERPENT, B_PILLAR, B_NEEDLE, B_HEAD, B_CLUB, B_TOOTH,
@@ -98,9 +101,10 @@ __device__ __forceinline__ void pack_hot(uint8_t* hot, const Hot& h) {
   q.x = h.lv2; q.y = (uint32_t)h.shop_reroll_state; q.z = h.rng_seed; q.w = h.rng_ctr;
   sts128(hot + 112, q);
   q.x = (h.hands_left & 0xFF) | ((h.discards_left & 0xFF) << 8) | ((h.joker_n & 0xFF) << 16) | ((uint32_t)(h.cons_n & 0xFF) << 24);
-  q.y = h.episode; q.z = 0; q.w = 0;
-  sts128(hot + 128, q);
+  q.y = h.episode;
+  *reinterpret_cast<uint2*>(hot + 128) = make_uint2(q.x, q.y);   // bytes 136..143 (deck_extra) stay as they are
 }
+__device__ __forceinline__ void hot_clear_extra(uint8_t* hot) { *reinterpret_cast<uint2*>(hot + OFF_HOT_EXTRA) = make_uint2(0u, 0u); }
 
 __device__ __forceinline__ int hand_level(const Hot& h, int ht) {
   uint32_t w = ht < 4 ? h.lv0 : (ht < 8 ? h.lv1 : h.lv2);
@@ -333,7 +337,7 @@ enum ConsOp : uint8_t {
   CO_PLANET,       // arg = hand type
   CO_SEAL,         // arg = raw seal value stored (consumables.Seal numbering)
   CO_AURA, CO_WRAITH, CO_ECTOPLASM, CO_ANKH, CO_HEX, CO_SOUL, CO_BLACK_HOLE,
-  CO_UNSUPPORTED
+  CO_IMMOLATE, CO_CRYPTID
 };
 struct ConsRow { uint8_t op, arg; };
 
@@ -379,7 +383,8 @@ __device__ __forceinline__ ConsRow cons_row(int cid) {
     case 64: return {CO_SEAL, 4};   // Medium: PURPLE == 4
     case 66: return {CO_SOUL, 0};
     case 67: return {CO_BLACK_HOLE, 0};
-    case 59: case 65: return {CO_UNSUPPORTED, 0};  // Immolate, Cryptid rebuild the deck list
+    case 59: return {CO_IMMOLATE, 0};
+    case 65: return {CO_CRYPTID, 0};
   }
   return {CO_NONE, 0};
 }
@@ -394,7 +399,60 @@ __device__ __forceinline__ void cons_pop(Hot& h, int idx) {
   h.cons_n--;
 }
 
-__device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int& err, int& terminated) {
+// Immolate (consumables.py:520-532): random.sample(deck, min(5, len)) then deck.remove(card) for each — the deck list
+// really shrinks, hand_indexes are not re-mapped, card_states stay keyed by deck INDEX.  The deck is always
+// [surviving original cards, in order] ++ [cards appended by Cryptid, in order]; list.remove takes the first EQUAL
+// element: an original card (cards.Card, rank+suit equality, :112-115) is only equal to itself, an appended card
+// (consumables.Card dataclass) is equal to any appended card with the same rank, suit and copy-time modifiers.
+__device__ __noinline__ int immolate(Hot& h, uint8_t* hotrec, uint8_t* rec, Draws& rng) {
+  const int n = h.deck_n, n_ex = rec[OFF_EXTRA_N], n_orig = n - n_ex;
+  uint16_t* ex = reinterpret_cast<uint16_t*>(hotrec + OFF_HOT_EXTRA);
+  const int k = min(5, n);
+  uint64_t sampled = 0, removed = 0;
+#pragma unroll 1
+  for (int t = 0; t < k; t++) {
+    int idx;
+    if (rng.tape) idx = rng.below(n);            // replay: population index recorded from the reference
+    else {                                       // native: t-th element of a uniform sample without replacement
+      int p = rng.below(n - t);
+      uint64_t fr = ~sampled & ((n >= 64) ? ~0ull : ((1ull << n) - 1));
+#pragma unroll 1
+      for (int i = 0; i < p; i++) fr &= fr - 1;
+      idx = __ffsll((long long)fr) - 1;
+    }
+    sampled |= 1ull << idx;
+    int victim = idx;
+    if (idx >= n_orig) {
+      const int id = ex[idx - n_orig];
+#pragma unroll 1
+      for (int j = n_ex - 1; j >= 0; j--) if (!((removed >> (n_orig + j)) & 1) && ex[j] == id) victim = n_orig + j;
+    }
+    removed |= 1ull << victim;
+  }
+  // compact: codes move down with the cards, modifiers stay with the deck index
+  int w = 0, w_ex = 0;
+  uint64_t pillar = 0;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    if ((removed >> i) & 1) continue;
+    const int id = i < n_orig ? 0 : ex[i - n_orig];
+    const int code = i < n_orig ? c16_code(deck16(rec, i)) : (id & 63);
+    if (w < 52) set_deck16(rec, w, (deck16(rec, w) & ~63) | code);
+    if (i >= n_orig) ex[w_ex++] = (uint16_t)id;
+    pillar |= ((h.boss_played_cards >> i) & 1ull) << w;
+    w++;
+  }
+#pragma unroll 1
+  for (int i = w; i < 52; i++) set_deck16(rec, i, deck16(rec, i) & ~63);
+#pragma unroll 1
+  for (int j = w_ex; j < MAX_DECK_EXTRA; j++) ex[j] = 0;
+  rec[OFF_EXTRA_N] = (uint8_t)w_ex;
+  h.deck_n = w;
+  h.boss_played_cards = pillar;
+  return k;
+}
+
+__device__ double use_consumable(Hot& h, uint8_t* hotrec, uint8_t* rec, int cidx, Draws& rng, int& err, int& terminated) {
   int cid = byte_at(h.cons, cidx);
   ConsRow row = cons_row(cid);
   // targets: selected cards in selection order (balatro_env_2.py:1074-1083)
@@ -406,7 +464,7 @@ __device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int
   }
   bool success = false, raise = false, unsupported = false;
   int money_gained = 0, planet_ht = -1, n_affected = 0, n_jokers_created = 0, add_joker = 0;
-  int items[2], n_items = 0, hand_size_change = 0;
+  int items[2], n_items = 0, hand_size_change = 0, n_created = 0, n_destroyed = 0;
   switch (row.op) {
     case CO_ENH_N: {
       int cnt = min(nT, row.arg >> 4);
@@ -487,7 +545,23 @@ __device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int
       if (h.joker_n < h.joker_slots) { add_joker = BGYM_J_CANIO + rng.below(5); n_jokers_created = 1; success = true; }
       break;
     case CO_BLACK_HOLE: success = true; break;
-    case CO_UNSUPPORTED: unsupported = true; break;
+    case CO_IMMOLATE: n_destroyed = immolate(h, hotrec, rec, rng); money_gained = 20; success = true; break;
+    case CO_CRYPTID:   // consumables.py:582-592: two copies of the first target are appended to the deck list
+      if (nT >= 1) {
+        const int n_ex = rec[OFF_EXTRA_N];
+        if (n_ex + 2 > MAX_DECK_EXTRA || h.deck_n + 2 > 56) { unsupported = true; break; }   // capacity, include/bgym.h
+        uint16_t* ex = reinterpret_cast<uint16_t*>(hotrec + OFF_HOT_EXTRA);
+        const int id = deck16(rec, tgt[0]);
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+          ex[n_ex + q] = (uint16_t)id;
+          if (h.deck_n < 52) set_deck16(rec, h.deck_n, (deck16(rec, h.deck_n) & ~63) | (id & 63));
+          h.deck_n++;
+        }
+        rec[OFF_EXTRA_N] = (uint8_t)(n_ex + 2);
+        n_created = 2; success = true;
+      }
+      break;
     default: break;
   }
   if (raise) {  // SafeBalatroEnv convention, train_balatro_fixed.py:262-269
@@ -501,6 +575,8 @@ __device__ double use_consumable(Hot& h, uint8_t* rec, int cidx, Draws& rng, int
     if (money_gained > 0) { h.money += money_gained; reward += money_gained / 10.0; }
     if (planet_ht >= 0) { bump_hand_level(h, planet_ht); reward += 10.0; }
     if (n_affected > 0) reward += n_affected * 2.0;
+    if (n_created > 0) reward += n_created * 3.0;          // :1140-1141
+    if (n_destroyed > 0) reward += n_destroyed * 1.0;      // :1143-1144
     if (n_jokers_created > 0) {
       if (add_joker != 0 && h.joker_n < h.joker_slots && h.joker_n < 8) { h.jokers = with_byte(h.jokers, h.joker_n, add_joker); h.joker_n++; }
       reward += n_jokers_created * 15.0;
@@ -688,7 +764,8 @@ __device__ __noinline__ void rare_dispatch(uint8_t* hot, uint8_t* rec, int op, i
       shop_generate_inventory(h, rec, *rng);
     }
   } else if (op == RARE_CONSUMABLE) {
-    out->reward = use_consumable(h, rec, arg, *rng, out->err, out->terminated);
+    out->reward = use_consumable(h, hot, rec, arg, *rng, out->err, out->terminated);
+    refresh_hand_codes(h, rec);   // Immolate moves cards under the hand's deck indices
   }
   pack_hot(hot, h);
 }

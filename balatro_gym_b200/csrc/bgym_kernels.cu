@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(RESET_WARPS * 32, 3) env_reset_kernel(StepArgs
         if (a.flags & BGYM_FLAG_GEN_C3) gen_hot(h, a.seeds[e], a.flags);
         reset_blocks_serial(cold, a.seeds[e], a.decks52 ? a.decks52 + e * 52 : nullptr, (a.flags & BGYM_FLAG_GEN_C3) != 0);
         pack_hot(hot, h);
+        hot_clear_extra(hot);
       }
       if (with_obs) write_obs(h, cold, action_mask(h, cold), obs_s);
     }

@@ -280,6 +280,7 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, uint8_t* hot_buf,
   uint64_t m1 = 0;
   if (active) {
     pack_hot(hot, h);
+    if (want_reset) hot_clear_extra(hot);
     if (with_obs) { m1 = action_mask(h, cold); obs_shop_block(h, cold, so); }   // last reads of the cold slot
     write_step_outputs(a, e, reward, terminated, info);
   }

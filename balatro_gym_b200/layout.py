@@ -55,11 +55,11 @@ _HOT_FIELDS = [
     ("joker_id", "(8,)u1", 88), ("cons_id", "(8,)u1", 96), ("hand_level", "(12,)u1", 104),
     ("shop_reroll_state", "<i4", 116), ("rng_seed", "<u4", 120), ("rng_ctr", "<u4", 124),
     ("hands_left", "u1", 128), ("discards_left", "u1", 129), ("joker_n", "u1", 130), ("cons_n", "u1", 131),
-    ("episode", "<u4", 132),
+    ("episode", "<u4", 132), ("deck_extra", "(4,)<u2", 136),
 ]
 _COLD_FIELDS = [
     ("deck", "(52,)<u2", 0), ("hand_play_count", "(12,)u1", 104),
-    ("item_type", "(9,)u1", 116), ("item_id", "(9,)u1", 125), ("n_items", "u1", 134),
+    ("item_type", "(9,)u1", 116), ("item_id", "(9,)u1", 125), ("n_items", "u1", 134), ("deck_extra_n", "u1", 135),
     ("item_cost", "(9,)<i4", 136), ("reroll_cost", "<i4", 172),
 ]
 HOT_DTYPE = _dt(_HOT_FIELDS, HOT_BYTES)

@@ -97,7 +97,8 @@ enum {
   BGYM_ERR_REF_EXCEPTION = 5,    /* the reference raises here; we return the
                                     SafeBalatroEnv convention: reward -100.0, terminated, state unchanged
                                     (train_balatro_fixed.py:262-269) */
-  BGYM_ERR_UNSUPPORTED = 6       /* consumable outside the supported set (spectrals that rebuild the deck) */
+  BGYM_ERR_UNSUPPORTED = 6       /* a Cryptid that would exceed the 4 appended cards deck_extra holds: reward -1.0,
+                                    state unchanged (every consumable of the reference is otherwise implemented) */
 };
 /* BgymInfo.flags */
 enum { BGYM_F_BEAT_BLIND = 1, BGYM_F_FAILED = 2, BGYM_F_GUARD_TERMINATED = 4, BGYM_F_PLAYED = 8,
@@ -170,7 +171,12 @@ enum {
  * 116 shop_reroll_state   state.shop_reroll_cost (stale copy used by the mask)
  * 120 rng_seed, 124 rng_ctr (native Philox key word / block counter)
  * 128 hands_left, 129 discards_left, 130 joker_n, 131 cons_n
- * 132 episode (in-kernel autoresets so far), 136 pad[8] */
+ * 132 episode (in-kernel autoresets so far)
+ * 136 deck_extra[4] u16   cards appended to the deck list by Cryptid (consumables.py:582-592), oldest first:
+ *                         card code | the target's modifiers at copy time (card16 layout; the modifiers only serve the
+ *                         dataclass equality list.remove uses in Immolate).  The deck is [surviving original cards] ++
+ *                         [deck_extra[0..deck_extra_n)]; deck_n = len(deck) counts both.  Capacity: 4 appended cards
+ *                         (two Cryptid uses outstanding); a Cryptid beyond that returns BGYM_ERR_UNSUPPORTED. */
 #define BGYM_HOT_FIELDS \
   uint8_t hand[8]; uint8_t hand_code[8]; \
   uint8_t hand_n; uint8_t hand_size; uint8_t sel_n; uint8_t highlight_mask; uint32_t sel_order; \
@@ -183,17 +189,20 @@ enum {
   uint16_t boss_played_types; uint8_t boss_hands_played; uint8_t deck_n; uint64_t boss_played_cards; \
   uint8_t joker_id[8]; uint8_t cons_id[8]; uint8_t hand_level[12]; int32_t shop_reroll_state; \
   uint32_t rng_seed; uint32_t rng_ctr; uint8_t hands_left; uint8_t discards_left; uint8_t joker_n; uint8_t cons_n; \
-  uint32_t episode; uint8_t _hot_pad[8];
+  uint32_t episode; uint16_t deck_extra[4];
 
 /* cold record, 176 B (offset: field)
- *   0 deck[52] u16        card16 per deck index
+ *   0 deck[52] u16        card16 per deck index: code of the card now at that index of the deck list (0 beyond
+ *                         deck_n) | the modifiers of state.card_states[index] (they are keyed by INDEX in the
+ *                         reference, so Immolate moves codes but not modifiers)
  * 104 hand_play_count[12] engine.hand_play_counts, saturating at 255 (never read by the reference's
  *                         step path; kept for save_state)
- * 116 item_type[9], 125 item_id[9] (joker id / pack kind / voucher kind / card int), 134 n_items
+ * 116 item_type[9], 125 item_id[9] (joker id / pack kind / voucher kind / card int), 134 n_items,
+ * 135 deck_extra_n (valid entries of the hot record's deck_extra)
  * 136 item_cost[9] i32, 172 reroll_cost i32 (shop.reroll_cost, grows x1.35 per reroll) */
 #define BGYM_COLD_FIELDS \
   uint16_t deck[52]; uint8_t hand_play_count[12]; \
-  uint8_t item_type[9]; uint8_t item_id[9]; uint8_t n_items; uint8_t _pad0; \
+  uint8_t item_type[9]; uint8_t item_id[9]; uint8_t n_items; uint8_t deck_extra_n; \
   int32_t item_cost[9]; int32_t reroll_cost;
 
 typedef struct BgymHot { BGYM_HOT_FIELDS } BgymHot;

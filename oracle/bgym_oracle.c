@@ -788,6 +788,39 @@ static const int WRAITH_JOKER[14] = {BGYM_J_INVISIBLE_JOKER, BGYM_J_BRAINSTORM, 
   BGYM_J_ASTRONOMER, BGYM_J_BURNT_JOKER, BGYM_J_BOOTSTRAPS, BGYM_J_CANIO, BGYM_J_TRIBOULET,
   BGYM_J_YORICK, BGYM_J_CHICOT, BGYM_J_PERKEO}; /* consumables.py:479-481 */
 
+
+/* The deck as the Python list it is in the reference (state.deck): elements in list order.  An element is either one
+ * of the original cards.Card objects (equal only to itself: rank + suit equality over 52 distinct cards,
+ * cards.py:112-115) or a consumables.Card appended by Cryptid (dataclass equality over rank, suit and the modifiers it
+ * was created with, consumables.py:63-70).  card_states stay keyed by list INDEX (balatro_env_2.py:1122-1138). */
+typedef struct DeckElem { int code; int appended; int ident; } DeckElem;
+
+static int deck_to_list(const BgymState* s, DeckElem* out) {
+  int n = s->deck_n, n_orig = n - s->deck_extra_n;
+  for (int i = 0; i < n; i++) {
+    if (i < n_orig) { out[i].code = c16_code(s->deck[i]); out[i].appended = 0; out[i].ident = 0; }
+    else { out[i].ident = s->deck_extra[i - n_orig]; out[i].code = out[i].ident & 63; out[i].appended = 1; }
+  }
+  return n;
+}
+
+static void list_to_deck(BgymState* s, const DeckElem* list, int n) {
+  int n_extra = 0;
+  for (int i = 0; i < 52; i++) {                       /* modifiers belong to the index, codes to the list */
+    uint16_t mods = (uint16_t)(s->deck[i] & ~63u);
+    s->deck[i] = (uint16_t)(mods | (i < n ? list[i].code : 0));
+  }
+  memset(s->deck_extra, 0, sizeof s->deck_extra);
+  for (int i = 0; i < n; i++) if (list[i].appended) s->deck_extra[n_extra++] = (uint16_t)list[i].ident;
+  s->deck_extra_n = (uint8_t)n_extra;
+  s->deck_n = (uint8_t)n;
+}
+
+static int elems_equal(const DeckElem* a, const DeckElem* b) {
+  if (a->appended != b->appended) return 0;            /* different classes never compare equal */
+  return a->appended ? a->ident == b->ident : a->code == b->code;
+}
+
 /* returns reward; *err gets the error code */
 static double use_consumable(BgymState* s, int cidx, Rng* r, int* err, int* terminated) {
   *err = BGYM_ERR_NONE;
@@ -800,7 +833,7 @@ static double use_consumable(BgymState* s, int cidx, Rng* r, int* err, int* term
   }
   int success = 0, money_gained = 0, planet_ht = -1, n_affected = 0, n_jokers_created = 0;
   int items[4], n_items = 0, hand_size_change = 0, exception = 0, unsupported = 0;
-  int add_jokers[2] = {0, 0}, n_add_jokers = 0;
+  int add_jokers[2] = {0, 0}, n_add_jokers = 0, n_created = 0, n_destroyed = 0;
   int tarot = 0;
   if (cid >= 1 && cid <= 22) tarot = cid;
   else if (cid >= 101 && cid <= 122) tarot = cid - 100;
@@ -925,7 +958,41 @@ static double use_consumable(BgymState* s, int cidx, Rng* r, int* err, int* term
         }
         break;
       case 17: success = 1; break; /* Black Hole :604-611 */
-      default: unsupported = 1; break; /* Immolate, Cryptid: rebuild the deck list */
+      case 9: { /* Immolate :520-532 — random.sample(deck, min(5, len(deck))), then deck.remove(card) one by one */
+        DeckElem list[64], victims[5];
+        int n = deck_to_list(s, list);
+        int k = n < 5 ? n : 5, picked[5];
+        rng_sample(r, n, k, picked);
+        for (int t = 0; t < k; t++) victims[t] = list[picked[t]];
+        /* the blind's played_cards set holds id(card): it follows the card objects through the removals */
+        int pillar[64];
+        for (int i = 0; i < n; i++) pillar[i] = (int)((s->boss_played_cards >> i) & 1);
+        for (int t = 0; t < k; t++) {
+          int at = 0;
+          while (!elems_equal(&list[at], &victims[t])) at++;   /* list.remove: first equal element */
+          for (int i = at; i + 1 < n; i++) { list[i] = list[i + 1]; pillar[i] = pillar[i + 1]; }
+          n--;
+        }
+        list_to_deck(s, list, n);
+        s->boss_played_cards = 0;
+        for (int i = 0; i < n; i++) if (pillar[i]) s->boss_played_cards |= 1ull << i;
+        money_gained = 20; n_destroyed = k; success = 1;
+        break;
+      }
+      case 15: /* Cryptid :582-592 — two consumables.Card copies of the first target go to the end of the deck list */
+        if (nT >= 1) {
+          if (s->deck_extra_n + 2 > 4) { unsupported = 1; break; }  /* capacity of BgymHot.deck_extra (include/bgym.h) */
+          DeckElem list[64];
+          int n = deck_to_list(s, list);
+          for (int q = 0; q < 2; q++) {
+            list[n].code = c16_code(s->deck[tgt[0]]); list[n].appended = 1; list[n].ident = s->deck[tgt[0]];
+            n++;
+          }
+          list_to_deck(s, list, n);
+          n_created = 2; success = 1;
+        }
+        break;
+      default: break;
     }
   }
 
@@ -943,6 +1010,8 @@ static double use_consumable(BgymState* s, int cidx, Rng* r, int* err, int* term
       reward += 10.0;
     }
     if (n_affected > 0) reward += n_affected * 2.0;                      /* :1122-1138 */
+    if (n_created > 0) reward += n_created * 3.0;                        /* :1140-1141 */
+    if (n_destroyed > 0) reward += n_destroyed * 1.0;                    /* :1143-1144 */
     if (n_jokers_created > 0) {                                          /* :1146-1154 */
       for (int i = 0; i < n_add_jokers; i++)
         if (s->joker_n < s->joker_slots && add_jokers[i] != 0 && s->joker_n < 8) s->joker_id[s->joker_n++] = (uint8_t)add_jokers[i];

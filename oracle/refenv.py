@@ -50,6 +50,10 @@ class _Ref:
     pass
 
 
+class DeckCapacity(Exception):
+    """The reference's deck list holds more Cryptid copies than BgymHot.deck_extra can (include/bgym.h)."""
+
+
 def load_reference():
     """Import the reference package; returns a namespace with the modules we use."""
     global _ref
@@ -333,7 +337,8 @@ class RefEnv:
             ids = {id(c): i for i, c in enumerate(deck)}
             pm = 0
             for cid in bs.get("played_cards", ()):
-                pm |= 1 << ids[cid]
+                if cid in ids:             # a played card Immolate destroyed since is no longer in the deck
+                    pm |= 1 << ids[cid]
             s["boss_played_cards"] = pm
         s["deck_n"] = len(deck)
         for i, j in enumerate(st.jokers):
@@ -346,12 +351,23 @@ class RefEnv:
                 "engine/state hand levels diverged beyond the min(level,15) relation"
             s["hand_play_count"][int(ht)] = min(255, env.engine.hand_play_counts[ht])
         s["shop_reroll_state"] = st.shop_reroll_cost
-        for i, c in enumerate(deck[:52]):
+        # deck[i] = code of the card now at list index i (0 beyond the list) | card_states[i], which the reference keys
+        # by INDEX; cards appended by Cryptid (consumables.Card objects, always a suffix of the list) are also listed
+        # in deck_extra with the modifiers they were created with (their dataclass equality, include/bgym.h)
+        for i in range(52):
+            code = card_code(deck[i]) if i < len(deck) else 0
             cs = st.card_states.get(i)
             if cs is not None:
-                s["deck"][i] = L.card16(card_code(c), int(cs.enhancement), int(cs.edition), int(cs.seal))
+                s["deck"][i] = L.card16(code, int(cs.enhancement), int(cs.edition), int(cs.seal))
             else:
-                s["deck"][i] = L.card16(card_code(c))
+                s["deck"][i] = L.card16(code)
+        extra = [c for c in deck if isinstance(c, R.cons.Card)]
+        if len(extra) > 4:
+            raise DeckCapacity(len(extra))
+        assert all(isinstance(c, R.cons.Card) for c in deck[len(deck) - len(extra):])
+        for j, c in enumerate(extra):
+            s["deck_extra"][j] = L.card16(card_code(c), int(c.enhancement), int(c.edition), int(c.seal))
+        s["deck_extra_n"] = len(extra)
         shop = env.shop
         if shop is not None:
             inv = shop.inventory

@@ -66,7 +66,7 @@ class CudaStepper:
                 self.v.info_numpy())
 
 
-@pytest.mark.parametrize("name", ["c1", "c3", "c4"])
+@pytest.mark.parametrize("name", ["c1", "c3", "c4", "c4x"])
 def test_cuda_replays_reference_trace(torch, name, step_path):
     from test_oracle_golden import replay
     tr = load_trace(name)

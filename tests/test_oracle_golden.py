@@ -63,8 +63,43 @@ class OracleStepper:
         return self.v.state, self.v.obs, self.v.reward, self.v.terminated, self.v.info
 
 
-@pytest.mark.parametrize("name", ["c1", "c3", "c4"])
+@pytest.mark.parametrize("name", ["c1", "c3", "c4", "c4x"])
 def test_oracle_replays_reference_trace(name):
     tr = load_trace(name)
     n = replay(tr, OracleStepper(tr["action"].shape[1]))
     assert n == int(tr["length"].sum())
+
+
+def consumables_used(tr):
+    """(ids whose use succeeded, ids whose use made the reference raise) over a trace: a USE_CONSUMABLE step whose
+    pre-step state lists consumable i at the used slot, reported without error / with an exception."""
+    T, E = tr["action"].shape
+    ok, raised = set(), set()
+    for e in range(E):
+        prev = tr["init_state"][e]
+        for t in range(int(tr["length"][e])):
+            a = int(tr["action"][t, e])
+            if 10 <= a < 15 and prev["phase"] == L.PHASE_PLAY and a - 10 < prev["cons_n"]:
+                cid = int(prev["cons_id"][a - 10])
+                if tr["exc"][t, e]:
+                    raised.add(cid)
+                elif tr["info"][t, e, 4] == 0:
+                    ok.add(cid)
+            if not tr["exc"][t, e]:
+                prev = tr["state"][t, e]
+    return ok, raised
+
+
+def test_c4x_trace_covers_every_consumable():
+    """Every consumable id of the reference — tarots 1..22, planets 30..41, spectrals 50..67 and the enum-style
+    tarots 101..122 The Emperor creates — is USED in the committed reference trace."""
+    tr = load_trace("c4x")
+    ok, raised = consumables_used(tr)
+    every = set(range(1, 23)) | set(range(30, 42)) | set(range(50, 68)) | set(range(101, 123))
+    assert every <= (ok | raised), sorted(every - (ok | raised))
+    # where the reference raises (SURVEY Q19): Hanged Man, Familiar, Grim, Incantation with a target; Sigil, Ouija
+    assert {13, 113, 50, 51, 52, 56, 57} <= raised
+    assert {59, 65} <= ok                                   # Immolate and Cryptid really rebuild the deck list
+    st = tr["state"]
+    assert int(st["deck_n"].max()) > 52 and int(st["deck_n"][st["deck_n"] > 0].min()) < 50
+    assert int(st["deck_extra_n"].max()) == 4

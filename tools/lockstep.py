@@ -14,7 +14,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import coracle  # noqa: E402
-from oracle.refenv import RefEnv, state_diff, obs_diff  # noqa: E402
+from oracle.refenv import RefEnv, DeckCapacity, state_diff, obs_diff  # noqa: E402
 from balatro_gym_b200 import layout as L  # noqa: E402
 
 
@@ -36,6 +36,21 @@ def inject_c3(ref: RefEnv, ov: coracle.OracleVec, rng: np.random.Generator, boss
             s["deck"][idx] = L.card16(int(s["deck"][idx]) & 63, enh, ed, seal)
 
 
+def inject_consumables(ref: RefEnv, ov: coracle.OracleVec, rng: np.random.Generator):
+    """config c4x: 1-4 consumables over EVERY name the reference resolves, enum-style tarot names included."""
+    names = L.TAROT_NAMES + L.PLANET_NAMES + L.SPECTRAL_NAMES + [t.upper().replace(' ', '_') for t in L.TAROT_NAMES]
+    picked = [names[int(i)] for i in rng.integers(0, len(names), size=int(rng.integers(1, 5)))]
+    ref.inject_consumables(picked)
+    s = ov.state[0]
+    s["cons_n"] = len(picked)
+    s["cons_id"][:len(picked)] = [L.consumable_id(n) for n in picked]
+    if rng.random() < 0.3:                       # free joker slots: Wraith / The Soul can add their joker
+        keep = int(rng.integers(0, 5))
+        ref.env.state.jokers = ref.env.state.jokers[:keep]
+        s["joker_id"][keep:] = 0
+        s["joker_n"] = keep
+
+
 def run(args):
     rng = np.random.default_rng(args.seed0)
     ref = RefEnv(seed=1)
@@ -48,8 +63,10 @@ def run(args):
         seed = args.seed0 + ep
         obs, _ = ref.reset(seed)
         ov.reset([seed], decks52=ref.deck_codes()[None, :])
-        if args.config in ("c3", "c4"):
+        if args.config in ("c3", "c4", "c4x"):
             inject_c3(ref, ov, rng)
+        if args.config == "c4x":
+            inject_consumables(ref, ov, rng)
         first = True
         for t in range(args.max_steps):
             legal = ref.legal_actions()
@@ -65,7 +82,10 @@ def run(args):
             hist[a] += 1
             try:
                 obs, r, term, trunc, info = ref.step(a)
+                rs = ref.extract_state()
                 exc = None
+            except DeckCapacity:
+                break  # > 4 cards appended by Cryptid: outside BgymHot.deck_extra's capacity (include/bgym.h)
             except Exception as e:  # the reference raises on some consumables
                 exc = e
             draws = ref.step_draws().reshape(1)
@@ -79,7 +99,6 @@ def run(args):
                     print("EXC mismatch", ep, t, a, repr(exc), ov.info[0])
                     n_mismatch += 1
                 break
-            rs = ref.extract_state()
             d = state_diff(rs, ov.state[0])
             od = obs_diff(RefEnv.obs_record(obs), ov.obs[0])
             # reward is bit-exact except the ante>3 branch, which goes through np.log10 (SVML on AVX512
