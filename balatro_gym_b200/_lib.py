@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise BgymError("nvcc not found: cannot build libbgym.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, SOURCES[0]]
+    extra = os.environ.get("BGYM_NVCC_EXTRA", "").split()        # experiments only (e.g. -DBGYM_GATHER_CTAS=6)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, SOURCES[0]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise BgymError("nvcc failed:\n" + res.stdout + res.stderr)
@@ -62,6 +63,7 @@ SYMBOLS = {
     "bgym_set_option": (_i32, [_i32, _i64]),
     "bgym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bgym_release_stream": (_i32, [_vp]),
     "bgym_action_mask": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "bgym_sample_actions": (_i32, [_vp, _vp, _u32, _u64, _i64, _vp]),
     "bgym_sample_actions_ctr": (_i32, [_vp, _vp, _u32, _vp, _i64, _vp]),

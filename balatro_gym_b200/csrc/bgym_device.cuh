@@ -72,6 +72,15 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // make this thread's generic-proxy shared-memory writes visible to the async proxy
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 16-byte asynchronous global -> shared copy (SASS: LDGSTS), L2 only
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void sts128(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 
@@ -82,6 +91,20 @@ __device__ __forceinline__ void sts128(void* p, uint4 v) { *reinterpret_cast<uin
 #define BGYM_POLICY_KEY1 0x5A17AC71u
 #define BGYM_SHUFFLE_KEY1 0xB200DECCu
 #define BGYM_SAMPLE_KEY1 0xCA7E6031u
+
+// inline form, for code that generates several independent blocks back to back (the reset's shuffle and modifier
+// draws): two calls side by side give the scheduler two dependency chains to interleave
+__device__ __forceinline__ uint4 philox4x32_10_inl(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
 
 // noinline on purpose: draws are rare (a few percent of env-steps) and the step kernel has ~20 draw
 // sites; one shared copy keeps the kernel inside the instruction cache.
@@ -133,6 +156,21 @@ struct Draws {
   }
   __device__ double u01();
   __device__ int below(int n);
+  // A step whose round advance is deferred to a second-level tile (bgym_step_part.cuh) continues the SAME draw
+  // sequence there.  16 bits say where it stands: words used of the current block (0..4) | tape positions |
+  // "the prefetched block is still untouched" (see blocks()); the block counter travels in the hot record.
+  __device__ __forceinline__ uint32_t snapshot() const {
+    return (uint32_t)pos | ((uint32_t)iu << 3) | ((uint32_t)ik << 8) | ((pos == 0 && ctr == first + 1) ? 0x4000u : 0u);
+  }
+  __device__ __forceinline__ void restore(uint32_t seed_, uint32_t ctr_, const BgymDraws* tape_, uint32_t snap) {
+    tape = tape_; seed = seed_; ctr = ctr_; pos = (int)(snap & 7u); iu = (int)((snap >> 3) & 31u); ik = (int)((snap >> 8) & 63u);
+    first = (snap & 0x4000u) ? ctr_ - 1 : ctr_;
+    buf0 = buf1 = buf2 = buf3 = 0;
+    if (!tape && pos < 4) {          // a block is open: regenerate it
+      uint4 b = philox4x32_10(ctr_ - 1, 0, 0, 0, seed, BGYM_PHILOX_KEY1);
+      buf0 = b.x; buf1 = b.y; buf2 = b.z; buf3 = b.w;
+    }
+  }
 };
 
 // Out of line (one copy each): the step kernel has ~25 draw sites, all on rare paths.

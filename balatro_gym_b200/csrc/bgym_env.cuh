@@ -608,11 +608,14 @@ __device__ __forceinline__ uint32_t next_episode_seed(uint32_t seed) {
 // specified in include/bgym.h, the reference-side counterpart is the injection recipe of SURVEY Appendix E)
 // ---------------------------------------------------------------------------------------------
 // modifier bits (enhancement << 6 | edition << 10 | seal << 13) of card k = suit * 13 + rank - 2
-__device__ __forceinline__ int gen_card_mods(uint32_t seed, int k) {
-  const uint4 b = philox4x32_10((uint32_t)k, 0, 0, 0, seed, BGYM_GEN_KEY1);
-  const int enh = (b.x >> 30) == 0u ? 1 + (int)((b.x >> 27) & 7u) : 0;
-  const int e = (int)__umulhi(b.y, 30u), sl = (int)__umulhi(b.z, 40u);
+__device__ __forceinline__ int gen_mods_from_words(uint32_t w0, uint32_t w1) {
+  const int enh = (w0 >> 30) == 0u ? 1 + (int)((w0 >> 27) & 7u) : 0;
+  const int e = (int)(((w0 & 0x07FFFFFFu) * 30ull) >> 27), sl = (int)__umulhi(w1, 40u);
   return (enh << 6) | ((e < 3 ? 1 + e : 0) << 10) | ((sl < 4 ? 1 + sl : 0) << 13);
+}
+__device__ __forceinline__ int gen_card_mods(uint32_t seed, int k) {
+  const uint4 b = philox4x32_10((uint32_t)(k >> 1), 0, 0, 0, seed, BGYM_GEN_KEY1);   // two cards per block
+  return (k & 1) ? gen_mods_from_words(b.z, b.w) : gen_mods_from_words(b.x, b.y);
 }
 __device__ __forceinline__ int gen_cons_id(uint32_t w) {
   const int i = (int)__umulhi(w, 52u);
@@ -664,6 +667,18 @@ __device__ __forceinline__ void reset_hot(Hot& h, uint32_t seed) {
   h.rng_seed = seed; h.rng_ctr = 0; h.ep_len = 0; h.episode = 0;
 }
 
+constexpr int OFF_RESET_SCRATCH = 116;  // shop part of the cold record, 52 bytes used
+// apply the 51 parked Fisher-Yates draws in random.shuffle's order, then clear them
+__device__ __forceinline__ void reset_blocks_finish(uint8_t* rec) {
+#pragma unroll 1
+  for (int i = 51; i >= 1; i--) {
+    int j = rec[OFF_RESET_SCRATCH + i];
+    int a = deck16(rec, i), b = deck16(rec, j);
+    set_deck16(rec, i, b); set_deck16(rec, j, a);
+  }
+#pragma unroll 1
+  for (int o = 112; o < BGYM_COLD_BYTES; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
+}
 // deck + shop blocks of a fresh episode, one lane doing all the work (reset kernel: every lane of
 // the warp resets, so per-lane serial work is already converged).
 //   deck52 != nullptr: replay of a supplied permutation (the reference's MT19937 shuffle stream)
@@ -680,16 +695,34 @@ __device__ __noinline__ void reset_blocks_serial(uint8_t* rec, uint32_t seed, co
     }
     return;
   }
+  // ordered deck (+ generated modifiers, two cards per Philox block, two blocks per iteration), then all 51
+  // Fisher-Yates draws (two blocks = four draws per iteration) parked as bytes in the still empty shop part of the
+  // record, then the swaps in random.shuffle's order.  The blocks are independent: generating them in pairs, in line,
+  // lets two dependency chains overlap (this loop is the latency of a level-2 reset tile).
 #pragma unroll 1
-  for (int i = 0; i < 52; i++) set_deck16(rec, i, ((i % 13) * 4 + i / 13) | (gen ? gen_card_mods(seed, i) : 0));
-  uint4 blk = make_uint4(0, 0, 0, 0);
-#pragma unroll 1
-  for (int i = 51; i >= 1; i--) {
-    if ((i & 1) == 0 || i == 51) blk = philox4x32_10((uint32_t)((i - 1) >> 1), 0, 0, 0, seed, BGYM_SHUFFLE_KEY1);
-    int j = shuffle_j_from_block(blk, i);
-    int a = deck16(rec, i), b = deck16(rec, j);
-    set_deck16(rec, i, b); set_deck16(rec, j, a);
+  for (int k = 0; k < 52; k += 4) {
+    int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    if (gen) {
+      const uint4 p = philox4x32_10_inl((uint32_t)(k >> 1), 0, 0, 0, seed, BGYM_GEN_KEY1);
+      const uint4 q = philox4x32_10_inl((uint32_t)(k >> 1) + 1, 0, 0, 0, seed, BGYM_GEN_KEY1);
+      m0 = gen_mods_from_words(p.x, p.y); m1 = gen_mods_from_words(p.z, p.w);
+      m2 = gen_mods_from_words(q.x, q.y); m3 = gen_mods_from_words(q.z, q.w);
+    }
+    set_deck16(rec, k, ((k % 13) * 4 + k / 13) | m0);
+    set_deck16(rec, k + 1, (((k + 1) % 13) * 4 + (k + 1) / 13) | m1);
+    set_deck16(rec, k + 2, (((k + 2) % 13) * 4 + (k + 2) / 13) | m2);
+    set_deck16(rec, k + 3, (((k + 3) % 13) * 4 + (k + 3) / 13) | m3);
   }
+#pragma unroll 1
+  for (int b = 0; b < 26; b += 2) {       // block b -> draws for i = 2b+1, 2b+2
+    const uint4 p = philox4x32_10_inl((uint32_t)b, 0, 0, 0, seed, BGYM_SHUFFLE_KEY1);
+    const uint4 q = philox4x32_10_inl((uint32_t)b + 1, 0, 0, 0, seed, BGYM_SHUFFLE_KEY1);
+    rec[OFF_RESET_SCRATCH + 2 * b + 1] = (uint8_t)shuffle_j_from_block(p, 2 * b + 1);
+    rec[OFF_RESET_SCRATCH + 2 * b + 2] = (uint8_t)shuffle_j_from_block(p, 2 * b + 2);
+    rec[OFF_RESET_SCRATCH + 2 * b + 3] = (uint8_t)shuffle_j_from_block(q, 2 * b + 3);
+    if (2 * b + 4 <= 51) rec[OFF_RESET_SCRATCH + 2 * b + 4] = (uint8_t)shuffle_j_from_block(q, 2 * b + 4);
+  }
+  reset_blocks_finish(rec);
 }
 
 // In-kernel autoreset of the deck/shop blocks, split in two so that several terminated lanes of a
@@ -699,7 +732,6 @@ __device__ __noinline__ void reset_blocks_serial(uint8_t* rec, uint32_t seed, co
 //            are parked as bytes in the (just zeroed) shop block of the record;
 //   finish  (each terminated lane for itself, all of them in parallel): apply the 51 swaps in
 //            random.shuffle's order, then clear the parked draws.
-constexpr int OFF_RESET_SCRATCH = 116;  // shop part of the cold record, 52 bytes used
 __device__ __forceinline__ void reset_blocks_prepare(uint8_t* rec_of_src, uint32_t seed, int lane, bool gen) {
   if (lane < 11) sts128(rec_of_src + 16 * lane, make_uint4(0, 0, 0, 0));
   __syncwarp();
@@ -712,16 +744,6 @@ __device__ __forceinline__ void reset_blocks_prepare(uint8_t* rec_of_src, uint32
     rec_of_src[OFF_RESET_SCRATCH + 2 * lane + 1] = (uint8_t)shuffle_j_from_block(blk, 2 * lane + 1);
     if (2 * lane + 2 <= 51) rec_of_src[OFF_RESET_SCRATCH + 2 * lane + 2] = (uint8_t)shuffle_j_from_block(blk, 2 * lane + 2);
   }
-}
-__device__ __forceinline__ void reset_blocks_finish(uint8_t* rec) {
-#pragma unroll 1
-  for (int i = 51; i >= 1; i--) {
-    int j = rec[OFF_RESET_SCRATCH + i];
-    int a = deck16(rec, i), b = deck16(rec, j);
-    set_deck16(rec, i, b); set_deck16(rec, j, a);
-  }
-#pragma unroll 1
-  for (int o = 112; o < BGYM_COLD_BYTES; o += 16) sts128(rec + o, make_uint4(0, 0, 0, 0));
 }
 // warp-level driver: `want_reset` lanes get fresh deck/shop blocks in their record `my_rec`
 __device__ __forceinline__ void autoreset_warp(bool want_reset, uint32_t new_seed, uint8_t* my_rec, int lane, bool gen) {
@@ -787,10 +809,18 @@ struct StepInfo {
 // ---------------------------------------------------------------------------------------------
 // CATS: which action categories this instantiation compiles in (the partitioned step runs one small
 // kernel per category so that every warp in flight executes the same short code).
-enum { CAT_SELECT = 1, CAT_PLAY = 2, CAT_DISCARD = 4, CAT_OTHER = 8, CAT_ALL = 15 };
-template <int CATS>
+//   CAT_CONS = USE_CONSUMABLE, CAT_SHOP = buy / sell / end shop, CAT_BLIND = select blind, CAT_GEN = reroll / skip blind
+//   (the two actions that generate a shop inventory).
+// DEFER_ADVANCE: a played hand that beats the blind stops before the round advance (advance_round + shop generation):
+//   *defer_snap receives the draw-sequence position (Draws::snapshot) and h.rng_ctr the raw block counter; the caller hands
+//   the env to a second-level tile that runs step_env_advance() — there every lane of the warp advances a round, whereas
+//   inside the PLAY tile a few lanes would walk that long path while the others wait.  -1 = nothing deferred.
+enum { CAT_SELECT = 1, CAT_PLAY = 2, CAT_DISCARD = 4, CAT_CONS = 8, CAT_SHOP = 16, CAT_BLIND = 32, CAT_GEN = 64,
+       CAT_OTHER = CAT_CONS | CAT_SHOP | CAT_BLIND | CAT_GEN, CAT_ALL = 127 };
+template <int CATS, bool DEFER_ADVANCE>
 __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_t mask, const BgymDraws* tape, double& reward_out,
-                         int& terminated_out, StepInfo& info) {
+                         int& terminated_out, StepInfo& info, int* defer_snap) {
+  if (DEFER_ADVANCE) *defer_snap = -1;
   info.final_score = 0; info.x_mult = 1.0; info.chips = 0; info.mult = 0; info.hand_type = -1;
   info.error_code = 0; info.flags = 0; info.cards_played = 0; info.base_score = 0;
   reward_out = 0.0; terminated_out = 0;
@@ -1026,16 +1056,16 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     double progress = (double)h.round_chips / (double)max(h.chips_needed, 1);
     if (progress < 0.5 && h.discards_left > 1) reward += 0.5;
     else if (progress > 0.8 && h.discards_left > 1) reward -= 0.3;
-  } else if ((CATS & CAT_OTHER) && action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) {
+  } else if ((CATS & CAT_CONS) && action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) {
     rare_op = RARE_CONSUMABLE; rare_arg = action - BGYM_A_USE_CONS_BASE;
-  } else if ((CATS & CAT_OTHER) && action == BGYM_A_SHOP_END) {
+  } else if ((CATS & CAT_SHOP) && action == BGYM_A_SHOP_END) {
     h.phase = BGYM_PHASE_PLAY;
     draw_cards(h);
     hand_changed = true;
     info.flags |= BGYM_F_SHOP_DONE;
-  } else if ((CATS & CAT_OTHER) && action == BGYM_A_SHOP_REROLL) {
+  } else if ((CATS & CAT_GEN) && action == BGYM_A_SHOP_REROLL) {
     rare_op = RARE_REROLL;
-  } else if ((CATS & CAT_OTHER) && action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SHOP_BUY_BASE + 10) {
+  } else if ((CATS & CAT_SHOP) && action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SHOP_BUY_BASE + 10) {
     int i = action - BGYM_A_SHOP_BUY_BASE;
     int n_items = rec[OFF_N_ITEMS];
     int type = rec[OFF_ITEM_TYPE + i], id = rec[OFF_ITEM_ID + i];
@@ -1060,7 +1090,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
       if (id == BGYM_VOUCHER_MAGIC_TRICK) h.n_magic = min(h.n_magic + 1, 255); else h.n_minimalist = min(h.n_minimalist + 1, 255);
       reward = 10.0;
     }
-  } else if ((CATS & CAT_OTHER) && action >= BGYM_A_SELL_JOKER_BASE && action < BGYM_A_SELL_JOKER_BASE + 5) {
+  } else if ((CATS & CAT_SHOP) && action >= BGYM_A_SELL_JOKER_BASE && action < BGYM_A_SELL_JOKER_BASE + 5) {
     int j = action - BGYM_A_SELL_JOKER_BASE;
     int id = byte_at(h.jokers, j);
     uint64_t lo = h.jokers & ((1ull << (8 * j)) - 1);
@@ -1069,7 +1099,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     int sell = max(3, (int)c_joker_cost[id] / 2);
     h.money += sell; h.jokers_sold++;
     reward = sell / 5.0;
-  } else if ((CATS & CAT_OTHER) && action >= BGYM_A_SELECT_BLIND_BASE && action < BGYM_A_SELECT_BLIND_BASE + 3) {
+  } else if ((CATS & CAT_BLIND) && action >= BGYM_A_SELECT_BLIND_BASE && action < BGYM_A_SELECT_BLIND_BASE + 3) {
     int bt = action - BGYM_A_SELECT_BLIND_BASE;
     h.round = bt + 1;
     long long needed = (h.ante <= 8) ? (long long)c_blind_chips[max(h.ante, 1) - 1][bt]
@@ -1088,11 +1118,18 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     h.phase = BGYM_PHASE_PLAY;
     draw_cards(h);
     hand_changed = true;
-  } else if ((CATS & CAT_OTHER) && action == BGYM_A_SKIP_BLIND) {
+  } else if ((CATS & CAT_GEN) && action == BGYM_A_SKIP_BLIND) {
     reward = -5.0;
     rare_op = RARE_ADVANCE;
   }
-  if ((CATS & (CAT_PLAY | CAT_OTHER)) && rare_op != RARE_NONE) {   // ONE out-of-line site for every rare path
+  if (DEFER_ADVANCE && (CATS & CAT_PLAY) && rare_op == RARE_ADVANCE && action == BGYM_A_PLAY_HAND) {
+    *defer_snap = (int)rng.snapshot();
+    if (!tape) h.rng_ctr = rng.ctr;          // raw counter: step_env_advance() settles it (Draws::blocks) when it is done
+    reward_out = reward;
+    terminated_out = terminated;
+    return;                                  // a beaten blind changes neither the hand nor the selection any further
+  }
+  if ((CATS & (CAT_PLAY | CAT_CONS | CAT_GEN)) && rare_op != RARE_NONE) {   // ONE out-of-line site for every rare path
     RareOut ro;
     pack_hot(hot, h);
     rare_dispatch(hot, rec, rare_op, rare_arg, &rng, &ro);
@@ -1103,6 +1140,17 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
   if (!tape) h.rng_ctr = rng.blocks();
   reward_out = reward;
   terminated_out = terminated;
+}
+
+// second half of a step whose round advance was deferred (DEFER_ADVANCE above): balatro_env_2.py:914-925 -> :1326-1392
+__device__ __forceinline__ void step_env_advance(Hot& h, uint8_t* hot, uint8_t* rec, const BgymDraws* tape, uint32_t snap) {
+  Draws rng;
+  rng.restore(h.rng_seed, h.rng_ctr, tape, snap);
+  RareOut ro;
+  pack_hot(hot, h);
+  rare_dispatch(hot, rec, RARE_ADVANCE, 0, &rng, &ro);
+  unpack_hot(hot, h);
+  if (!tape) h.rng_ctr = rng.blocks();
 }
 
 // ---------------------------------------------------------------------------------------------

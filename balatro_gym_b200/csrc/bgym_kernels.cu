@@ -1,7 +1,7 @@
 // bgym_kernels.cu — sm_100a kernels and the C-ABI (include/bgym.h) of the batched Balatro env.
 //
 // Kernels
-//   env_step_main_kernel / env_step_gather_kernel / env_step_small_kernel   K2  the fused, category-partitioned BalatroEnv.step
+//   env_step_main_kernel / env_step_list_kernel<LIST> / env_step_small_kernel   K2  the fused, category-partitioned BalatroEnv.step
 //                           (bgym_step_part.cuh): mask check -> phase dispatch -> scoring -> boss ->
 //                           round advance / shop generation -> reward -> observation + mask emission,
 //                           in-place autoreset (K3) and an optional fused random-legal policy
@@ -44,9 +44,10 @@ struct StepArgs {
   const uint8_t* decks52;    // n x 52 (nullable)
   long long n;
   int flags;
-  // partitioned step: three device lists of deferred env indices + their counters
-  int* part_lists;           // [3][part_cap]
-  int* part_counters;        // [4 * PART_CTR_STRIDE] (counter of category c at c * PART_CTR_STRIDE; 0 unused)
+  // partitioned step (bgym_step_part.cuh): device lists of deferred env indices + their counters
+  int* part_lists;           // [N_LISTS][part_cap]
+  int* part_counters;        // [N_LISTS * PART_CTR_STRIDE] (counter of list l at l * PART_CTR_STRIDE)
+  uint16_t* part_aux;        // [part_cap] per env: draw-sequence position of a step continued at level 2
   long long part_cap;
 };
 
@@ -506,10 +507,6 @@ static int ensure_device_setup() {
   BGYM_SET_SMEM(env_reset_kernel, RESET_CTA_SMEM)
   BGYM_SET_SMEM(env_step_main_kernel<1>, MainCfg<1>::cta_smem)
   BGYM_SET_SMEM(env_step_main_kernel<2>, MainCfg<2>::cta_smem)
-  BGYM_SET_SMEM((env_step_gather_kernel<CAT_PLAY, 0, true>), GATHER_CTA_SMEM)
-  BGYM_SET_SMEM((env_step_gather_kernel<CAT_DISCARD, 1, false>), GATHER_CTA_SMEM)
-  BGYM_SET_SMEM((env_step_gather_kernel<CAT_OTHER, 2, true>), GATHER_CTA_SMEM)
-  BGYM_SET_SMEM(env_step_small_kernel, GATHER_CTA_SMEM)
 #undef BGYM_SET_SMEM
   g_dev_sms[dev] = g_sm_count;
   g_dev_ready[dev] = true;
@@ -526,35 +523,38 @@ static long long small_slab_threshold() {
 
 static bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
 
-// scratch of the partitioned step (deferred-env lists + counters) and the side streams of the
-// concurrent gather passes, one set per (device, stream)
-struct PartScratch { int dev; void* stream; long long cap; int* lists; int* counters;
-                     cudaStream_t side[2]; cudaEvent_t ev_main, ev_side[2]; bool streams_ok; };
-static PartScratch g_scratch[64];
-static int g_n_scratch = 0;
+// scratch of the partitioned step (deferred-env lists, their counters, the per-env continuation word), one set per
+// (device, stream) in use; bgym_release_stream() gives a set back
+constexpr int PART_SIDE_STREAMS = 6;   // the seven level-1 list kernels run concurrently: launch stream + six forked ones
+struct PartScratch { bool used; int dev; void* stream; long long cap; int* lists; int* counters; uint16_t* aux;
+                     cudaStream_t side[PART_SIDE_STREAMS]; cudaEvent_t ev_fork, ev_fork2, ev_side[PART_SIDE_STREAMS]; bool streams_ok; };
+constexpr int BGYM_MAX_SCRATCH = 64;
+static PartScratch g_scratch[BGYM_MAX_SCRATCH];
 static int get_part_scratch(long long n, void* stream, PartScratch** out) {
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(g_mu);
   PartScratch* sc = nullptr;
-  for (int i = 0; i < g_n_scratch; i++)
-    if (g_scratch[i].dev == dev && g_scratch[i].stream == stream) sc = &g_scratch[i];
+  for (int i = 0; i < BGYM_MAX_SCRATCH; i++)
+    if (g_scratch[i].used && g_scratch[i].dev == dev && g_scratch[i].stream == stream) sc = &g_scratch[i];
   if (!sc) {
-    if (g_n_scratch == 64) return set_err(BGYM_E_ARG, "bgym_step: too many (device, stream) pairs in use");
-    sc = &g_scratch[g_n_scratch++];
-    sc->dev = dev; sc->stream = stream; sc->cap = 0; sc->lists = nullptr; sc->counters = nullptr;
-    sc->streams_ok = cudaStreamCreateWithFlags(&sc->side[0], cudaStreamNonBlocking) == cudaSuccess &&
-                     cudaStreamCreateWithFlags(&sc->side[1], cudaStreamNonBlocking) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&sc->ev_main, cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&sc->ev_side[0], cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&sc->ev_side[1], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < BGYM_MAX_SCRATCH && !sc; i++) if (!g_scratch[i].used) sc = &g_scratch[i];
+    if (!sc) return set_err(BGYM_E_ARG, "bgym_step: too many (device, stream) pairs in use (bgym_release_stream frees one)");
+    sc->used = true; sc->dev = dev; sc->stream = stream; sc->cap = 0; sc->lists = nullptr; sc->counters = nullptr; sc->aux = nullptr;
+    sc->streams_ok = cudaEventCreateWithFlags(&sc->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&sc->ev_fork2, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < PART_SIDE_STREAMS; i++)
+      sc->streams_ok = sc->streams_ok && cudaStreamCreateWithFlags(&sc->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+                       cudaEventCreateWithFlags(&sc->ev_side[i], cudaEventDisableTiming) == cudaSuccess;
   }
   if (sc->cap < n) {
     if (sc->lists) cudaFree(sc->lists);
-    cudaError_t e = cudaMalloc(&sc->lists, (size_t)(3 * n + 4 * PART_CTR_STRIDE) * sizeof(int));
+    const size_t ints = (size_t)N_LISTS * (size_t)n + (size_t)N_LISTS * PART_CTR_STRIDE;
+    cudaError_t e = cudaMalloc(&sc->lists, ints * sizeof(int) + (size_t)n * sizeof(uint16_t));
     if (e != cudaSuccess) { sc->cap = 0; sc->lists = nullptr; return cuda_rc(e, "cudaMalloc(step scratch)"); }
     sc->cap = n;
-    sc->counters = sc->lists + 3 * n;
+    sc->counters = sc->lists + (size_t)N_LISTS * (size_t)n;
+    sc->aux = reinterpret_cast<uint16_t*>(sc->counters + N_LISTS * PART_CTR_STRIDE);
   }
   *out = sc;
   return 0;
@@ -627,20 +627,22 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
   a.draws = draws; a.obs = reinterpret_cast<uint8_t*>(obs);
   a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.info = info;
   a.n = n; a.flags = flags;
-  a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_cap = sc->cap;
-  // BGYM_STEP_TIMING=1 (diagnostic): synchronising per-phase timing of the launch set, printed every 64 calls
-  static const bool timing = getenv("BGYM_STEP_TIMING") != nullptr;
-  static cudaEvent_t tev[3];
-  static double tsum[2] = {0, 0};
+  a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_aux = sc->aux; a.part_cap = sc->cap;
+  // BGYM_STEP_TIMING (diagnostic, single-threaded use): synchronising timing of the launch set, printed every 64 calls.
+  //   1 = phases (main / level-1 lists concurrently / level-2 lists);  2 = every kernel on its own, launched serially
+  static const int timing = getenv("BGYM_STEP_TIMING") ? atoi(getenv("BGYM_STEP_TIMING")) : 0;
+  constexpr int NEV = N_LISTS + 2;
+  static cudaEvent_t tev[NEV];
+  static double tsum[NEV] = {0};
   static int tcalls = 0;
-  if (timing && tcalls == 0 && tsum[0] == 0) for (int i = 0; i < 3; i++) cudaEventCreate(&tev[i]);
+  if (timing && tcalls == 0 && tsum[0] == 0) for (int i = 0; i < NEV; i++) cudaEventCreate(&tev[i]);
   if (timing) cudaEventRecord(tev[0], s);
   // small slabs: one launch (bgym_step_part.cuh, env_step_small_kernel); BGYM_SMALL_N overrides the threshold
   if (n <= small_slab_threshold() && !timing) {
     env_step_small_kernel<<<tile_grid(n, GATHER_WARPS, GATHER_CTAS_PER_SM), GATHER_WARPS * 32, GATHER_CTA_SMEM, s>>>(a);
     return cuda_rc(cudaGetLastError(), "bgym_step launch");
   }
-  cudaError_t e = cudaMemsetAsync(sc->counters, 0, 4 * PART_CTR_STRIDE * sizeof(int), s);
+  cudaError_t e = cudaMemsetAsync(sc->counters, 0, N_LISTS * PART_CTR_STRIDE * sizeof(int), s);
   if (e != cudaSuccess) return cuda_rc(e, "cudaMemsetAsync(step counters)");
   static const int main_stages = (getenv("BGYM_MAIN_STAGES") && getenv("BGYM_MAIN_STAGES")[0] == '1') ? 1 : 2;
   if (main_stages == 2)
@@ -648,40 +650,75 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
   else
     env_step_main_kernel<1><<<tile_grid(n, MAIN_WARPS, MainCfg<1>::ctas_per_sm), MAIN_WARPS * 32, MainCfg<1>::cta_smem, s>>>(a);
   if (timing) cudaEventRecord(tev[1], s);
-  // the list lengths live on the device: launch resident-size grids, idle warps exit at once
-  int ggrid = tile_grid((n + 3) / 4, GATHER_WARPS, GATHER_CTAS_PER_SM);
-  if (ggrid < 1) ggrid = 1;
-  static const bool serial = getenv("BGYM_SERIAL_GATHER") != nullptr;
+  // The list lengths live on the device: every list kernel is launched with a resident-size grid, idle warps exit at
+  // once.  Level 1 = one kernel per list the main pass filled, run concurrently on forked streams (they touch disjoint
+  // envs); level 2 = the round advances and resets level 1 handed on, again concurrently.  (Chaining ADVANCE behind
+  // PLAY and RESET behind PLAY / CONS / MISC only, so that level 2 overlaps the rest of level 1, measured 4 % slower:
+  // the passes are bound by resident warps, not by idle SMs.)
   const int gt = GATHER_WARPS * 32;
-  if (sc->streams_ok && !serial) {
-    // the three gather passes touch disjoint envs and are latency-bound: run them concurrently
-    cudaEventRecord(sc->ev_main, s);
-    cudaStreamWaitEvent(sc->side[0], sc->ev_main, 0);
-    env_step_gather_kernel<CAT_PLAY, 0, true><<<ggrid, gt, GATHER_CTA_SMEM, sc->side[0]>>>(a);
-    cudaEventRecord(sc->ev_side[0], sc->side[0]);
-    cudaStreamWaitEvent(sc->side[1], sc->ev_main, 0);
-    env_step_gather_kernel<CAT_OTHER, 2, true><<<ggrid, gt, GATHER_CTA_SMEM, sc->side[1]>>>(a);
-    cudaEventRecord(sc->ev_side[1], sc->side[1]);
-    env_step_gather_kernel<CAT_DISCARD, 1, false><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
-    cudaStreamWaitEvent(s, sc->ev_side[0], 0);
-    cudaStreamWaitEvent(s, sc->ev_side[1], 0);
-  } else {
-    env_step_gather_kernel<CAT_PLAY, 0, true><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
-    env_step_gather_kernel<CAT_DISCARD, 1, false><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
-    env_step_gather_kernel<CAT_OTHER, 2, true><<<ggrid, gt, GATHER_CTA_SMEM, s>>>(a);
+  auto lgrid = [&](int list) { int g = tile_grid(n, GATHER_WARPS, list_ctas(list)); return g < 1 ? 1 : g; };
+  static const bool serial = getenv("BGYM_SERIAL_GATHER") != nullptr;
+  const bool fork = sc->streams_ok && !serial && timing != 2;
+  cudaStream_t ls[N_LISTS];
+  for (int l = 0; l < N_LISTS; l++) ls[l] = s;
+  if (fork) {
+    cudaEventRecord(sc->ev_fork, s);
+    for (int i = 0; i < PART_SIDE_STREAMS; i++) { cudaStreamWaitEvent(sc->side[i], sc->ev_fork, 0); ls[1 + i] = sc->side[i]; }
   }
-  if (timing) {
-    cudaEventRecord(tev[2], s);
-    cudaEventSynchronize(tev[2]);
-    float m0 = 0, m1 = 0;
-    cudaEventElapsedTime(&m0, tev[0], tev[1]); cudaEventElapsedTime(&m1, tev[1], tev[2]);
-    tsum[0] += m0; tsum[1] += m1;
+#define BGYM_LAUNCH_LIST(L) env_step_list_kernel<L><<<lgrid(L), gt, list_smem_bytes(L), ls[L]>>>(a); if (timing == 2) cudaEventRecord(tev[2 + L], s);
+  BGYM_LAUNCH_LIST(L_PLAY) BGYM_LAUNCH_LIST(L_CONS) BGYM_LAUNCH_LIST(L_GEN) BGYM_LAUNCH_LIST(L_MISC)
+  BGYM_LAUNCH_LIST(L_DISCARD) BGYM_LAUNCH_LIST(L_SHOP) BGYM_LAUNCH_LIST(L_BLIND)
+  if (fork)
+    for (int i = 0; i < PART_SIDE_STREAMS; i++) { cudaEventRecord(sc->ev_side[i], sc->side[i]); cudaStreamWaitEvent(s, sc->ev_side[i], 0); }
+  if (timing == 1) cudaEventRecord(tev[2], s);
+  if (fork) { cudaEventRecord(sc->ev_fork2, s); cudaStreamWaitEvent(sc->side[0], sc->ev_fork2, 0); ls[L_RESET] = sc->side[0]; }
+  BGYM_LAUNCH_LIST(L_ADVANCE) BGYM_LAUNCH_LIST(L_RESET)
+#undef BGYM_LAUNCH_LIST
+  if (fork) { cudaEventRecord(sc->ev_side[0], sc->side[0]); cudaStreamWaitEvent(s, sc->ev_side[0], 0); }
+  if (timing == 1) cudaEventRecord(tev[3], s);
+  if (timing == 1) {
+    cudaEventSynchronize(tev[3]);
+    for (int i = 0; i < 3; i++) { float m = 0; cudaEventElapsedTime(&m, tev[i], tev[i + 1]); tsum[i] += m; }
     if (++tcalls % 64 == 0) {
-      fprintf(stderr, "[bgym timing] main %.1f us, gathers %.1f us (mean of 64 steps)\n", tsum[0] / 64 * 1e3, tsum[1] / 64 * 1e3);
-      tsum[0] = tsum[1] = 1e-30;
+      fprintf(stderr, "[bgym timing] main %.1f us, level-1 lists %.1f us, level-2 lists %.1f us (mean of 64 steps)\n",
+              tsum[0] / 64 * 1e3, tsum[1] / 64 * 1e3, tsum[2] / 64 * 1e3);
+      for (int i = 0; i < 3; i++) tsum[i] = 1e-30;
+    }
+  } else if (timing == 2) {
+    cudaEventSynchronize(tev[2 + L_RESET]);
+    if (++tcalls % 64 == 0) {
+      static const int order[N_LISTS] = {L_PLAY, L_CONS, L_GEN, L_MISC, L_DISCARD, L_SHOP, L_BLIND, L_ADVANCE, L_RESET};
+      static const char* names[N_LISTS] = {"PLAY", "CONS", "GEN", "MISC", "DISCARD", "SHOP", "BLIND", "ADVANCE", "RESET"};
+      fprintf(stderr, "[bgym timing, serial launches, us]");
+      float m = 0;
+      cudaEventElapsedTime(&m, tev[0], tev[1]);
+      fprintf(stderr, " main %.1f", m * 1e3);
+      int prev = 1;
+      for (int k = 0; k < N_LISTS; k++) {
+        cudaEventElapsedTime(&m, tev[prev], tev[2 + order[k]]);
+        fprintf(stderr, " %s %.1f", names[order[k]], m * 1e3);
+        prev = 2 + order[k];
+      }
+      fprintf(stderr, " (last step of 64)\n");
     }
   }
   return cuda_rc(cudaGetLastError(), "bgym_step launch");
+}
+
+// gives back the step scratch held for `stream` on the current device (the lists are sized for the largest slab the
+// stream has stepped).  Call it after the stream's last step has finished, e.g. before destroying the stream.
+int bgym_release_stream(void* stream) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_err(BGYM_E_NODEV, "bgym_release_stream: no CUDA device");
+  std::lock_guard<std::mutex> lock(g_mu);
+  for (int i = 0; i < BGYM_MAX_SCRATCH; i++)
+    if (g_scratch[i].used && g_scratch[i].dev == dev && g_scratch[i].stream == stream) {
+      if (g_scratch[i].lists) cudaFree(g_scratch[i].lists);
+      cudaEventDestroy(g_scratch[i].ev_fork); cudaEventDestroy(g_scratch[i].ev_fork2);
+      for (int k = 0; k < PART_SIDE_STREAMS; k++) { cudaStreamDestroy(g_scratch[i].side[k]); cudaEventDestroy(g_scratch[i].ev_side[k]); }
+      g_scratch[i] = PartScratch{};
+    }
+  return 0;
 }
 
 int bgym_action_mask(const BgymHot* hot, const BgymCold* cold, uint64_t* mask, int64_t n, void* stream) {
@@ -862,6 +899,7 @@ int bgym_vec_destroy(BgymVec* v) {
   cudaFreeHost(v->h_hot); cudaFreeHost(v->h_cold); cudaFreeHost(v->h_block);
   cudaFreeHost(v->h_decks); cudaFreeHost(v->h_actions);
   cudaFreeHost(v->h_seeds); cudaFreeHost(v->h_draws);
+  bgym_release_stream(v->stream);
   cudaStreamDestroy(v->stream);
   delete v;
   return 0;

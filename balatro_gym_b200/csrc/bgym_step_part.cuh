@@ -1,40 +1,60 @@
 // bgym_step_part.cuh — the category-partitioned step.
 //
-// Why it is split (measured on B200, profiles/r01_ncu_summary_history.md): with every action category
-// compiled into one kernel the step was bound by instruction fetch (84 KB of SASS walked by 12
-// warps at different PCs, ~11 of 32 lanes active, 18 % of HBM peak), while a converged select-only
-// step already ran at ~85 % of the HBM roofline.  So one env-step is split by ACTION CATEGORY into
-// kernels whose code is small and whose warps all execute the same path:
+// Why it is split (measured on B200, profiles/r01_ncu_summary_history.md and r02_ncu_summary.md): with every action
+// category compiled into one kernel and one env per lane, the step was bound by instruction fetch and by divergence
+// (84 KB of SASS walked by warps whose lanes sit on different paths, ~11 of 32 lanes active), while a converged
+// select-only step already ran at ~85 % of the HBM roofline.  Round 1 split it into a main pass and three gather
+// passes (PLAY / DISCARD / everything else); ncu then showed the "everything else" pass running with 7.8 active
+// lanes per instruction and the rare long paths (round advance + shop generation, autoreset, consumables) with 1-5.
+// So the unit of work is now a TILE OF 32 ENVS THAT TAKE THE SAME PATH:
 //
-//   main pass   (every env)    stages ONLY the hot records of each warp's tile (one bulk copy of
-//                              32 x 144 B), fully handles SELECT toggles (~83 % of random-legal
-//                              steps) and never-legal action ids of envs in PLAY phase — writing back only
-//                              the 16-byte chunk of the hot record a toggle changes — and appends the env
-//                              index of everything else to one of three device lists (staged per warp,
-//                              one atomic per run of >= 32).  The cold records are never touched.
-//   gather pass (one per list) each lane pulls ONE listed env's hot + cold record with its own bulk
-//                              copies, runs the category's path converged, pushes hot (+ cold) +
-//                              observation back.  The three passes run concurrently.
+//   main pass      (every env)   stages ONLY the hot records of each warp's tile (one bulk copy of 32 x 144 B), fully
+//                                handles SELECT toggles (~75 % of random-legal steps) and rejected actions of envs in
+//                                PLAY phase — writing back only the 16-byte chunk of the hot record a toggle changes —
+//                                and appends every other env to ONE OF SEVEN lists by the path its action takes
+//                                (staged per warp, one atomic per run of >= 32).  Cold records are never touched.
+//   level-1 pass   (one launch)  walks the tiles of the seven lists: each lane pulls ONE listed env's hot + cold record
+//                                with its own bulk copies, runs that list's path (step_env<CATS> compiles only the list's
+//                                branches), pushes hot (+ cold) + observation back.  Two long paths are NOT run here
+//                                but handed on, again as lists: the round advance of a hand that beat the blind, and
+//                                the in-place reset of a terminated env.
+//   level-2 pass   (one launch)  tiles of envs that advance a round (continuing the step's draw sequence where level 1
+//                                left it) and tiles of envs that are reset (32 fresh decks shuffled side by side).
 //
-//   small slabs (n <= 65536)   one launch of the gather tile code over all envs with every category compiled
-//                              in (env_step_small_kernel): such a step is launch- and latency-bound
+//   small slabs (n <= 65536)     one launch of the gather tile code over all envs with every category compiled in and
+//                                nothing deferred (env_step_small_kernel): such a step is launch- and latency-bound
 //
-// The launches are stream ordered after the main pass and touch disjoint envs, so results do not
-// depend on list order.
+// The launches are stream ordered and every env is owned by exactly one tile per level, so results do not depend on
+// list order.
 #pragma once
 #include "bgym_env.cuh"
 
 namespace bgym {
 
-// 0 = handled by the main pass, 1 = PLAY list, 2 = DISCARD list, 3 = OTHER list
-__device__ __forceinline__ int action_category_part(int action) {
-  if (action == BGYM_A_PLAY_HAND) return 1;
-  if (action == BGYM_A_DISCARD) return 2;
-  if (action >= BGYM_A_SELECT_BASE && action < BGYM_A_SELECT_BASE + 8) return 0;
-  if ((action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) ||
-      (action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SELL_JOKER_BASE + 5) ||
-      (action >= BGYM_A_SELECT_BLIND_BASE && action <= BGYM_A_SKIP_BLIND)) return 3;
-  return 0;  // ids that are never legal: rejected by the mask wherever they are handled
+// lists of deferred env indices.  Level 1 (filled by the main pass): heavy tiles first, so that the persistent
+// warps of the level-1 pass end on the cheap ones.  Level 2 (filled by the level-1 pass).
+enum { L_PLAY = 0, L_CONS, L_GEN, L_MISC, L_DISCARD, L_SHOP, L_BLIND, L_ADVANCE, L_RESET, N_LISTS };
+constexpr int N_LISTS_L1 = 7;
+
+// list of an env the main pass does not serve itself, from what the hot record alone tells (PLAY-phase legality is
+// complete there; in SHOP phase affordability needs the cold record — the tile re-checks the mask), -1 = served here
+__device__ __forceinline__ int route_env(const Hot& h, int action, uint64_t play_mask, bool guard) {
+  if (guard) return L_MISC;
+  if (h.phase == BGYM_PHASE_PLAY) {
+    if (action < 0 || action >= BGYM_NUM_ACTIONS || !((play_mask >> action) & 1)) return -1;   // rejected: no state change
+    if (action == BGYM_A_PLAY_HAND) return L_PLAY;
+    if (action == BGYM_A_DISCARD) return L_DISCARD;
+    return action < BGYM_A_USE_CONS_BASE ? -1 : L_CONS;
+  }
+  if (h.phase == BGYM_PHASE_SHOP) {
+    if (action == BGYM_A_SHOP_REROLL) return L_GEN;
+    return (action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SELL_JOKER_BASE + 5) ? L_SHOP : L_MISC;
+  }
+  if (h.phase == BGYM_PHASE_BLIND_SELECT) {
+    if (action == BGYM_A_SKIP_BLIND) return L_GEN;
+    return (action >= BGYM_A_SELECT_BLIND_BASE && action < BGYM_A_SKIP_BLIND) ? L_BLIND : L_MISC;
+  }
+  return L_MISC;
 }
 
 __device__ __forceinline__ void write_step_outputs(const StepArgs& a, long long e, double reward, int terminated,
@@ -69,7 +89,7 @@ __device__ __forceinline__ int policy_action(const Hot& h, uint64_t mask) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// main pass: per-warp tiles of 32 hot records, one bulk load + two bulk stores per tile
+// main pass: per-warp tiles of 32 hot records, one bulk load + one bulk store per tile
 // ------------------------------------------------------------------------------------------------
 constexpr int MAIN_WARPS = 4;
 constexpr int MAIN_HOT_TILE = 32 * BGYM_HOT_BYTES;   // 4608
@@ -83,8 +103,8 @@ constexpr int PART_CTR_STRIDE = 32;   // ints between list counters
 template <int STAGES>
 struct MainCfg {
   static constexpr int warp_smem = STAGES * MAIN_HOT_TILE + 32 * BGYM_OBS_BYTES;
-  // + per-warp staging of the three deferred lists (PART_STAGE entries each), then the mbarriers
-  static constexpr int cta_smem = MAIN_WARPS * warp_smem + MAIN_WARPS * 3 * PART_STAGE * 4 + 16 * MAIN_WARPS;
+  // + per-warp staging of the level-1 lists (PART_STAGE entries each), then the mbarriers
+  static constexpr int cta_smem = MAIN_WARPS * warp_smem + MAIN_WARPS * N_LISTS_L1 * PART_STAGE * 4 + 16 * MAIN_WARPS;
   static constexpr int ctas_per_sm = (227 * 1024) / cta_smem;
 };
 
@@ -95,20 +115,20 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* hot_base = smem + warp * MAIN_WARP_SMEM;
   uint8_t* obs_buf = hot_base + STAGES * MAIN_HOT_TILE;
-  int* stage_list = reinterpret_cast<int*>(smem + MAIN_WARPS * MAIN_WARP_SMEM) + warp * 3 * PART_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MAIN_WARPS * MAIN_WARP_SMEM + MAIN_WARPS * 3 * PART_STAGE * 4) + warp * 2;
+  int* stage_list = reinterpret_cast<int*>(smem + MAIN_WARPS * MAIN_WARP_SMEM) + warp * N_LISTS_L1 * PART_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MAIN_WARPS * MAIN_WARP_SMEM + MAIN_WARPS * N_LISTS_L1 * PART_STAGE * 4) + warp * 2;
   if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
   __syncwarp();
-  int staged[3] = {0, 0, 0};   // warp-uniform fill of the three staging lists
-  auto flush_list = [&](int c) {   // whole warp; c = 0..2
+  int staged[N_LISTS_L1];   // warp-uniform fill of the staging lists
+#pragma unroll
+  for (int c = 0; c < N_LISTS_L1; c++) staged[c] = 0;
+  auto flush_list = [&](int c, int cnt) {   // whole warp
     __syncwarp();
-    const int cnt = staged[c];
     int basei = 0;
-    if (lane == 0) basei = atomicAdd(a.part_counters + (c + 1) * PART_CTR_STRIDE, cnt);
+    if (lane == 0) basei = atomicAdd(a.part_counters + c * PART_CTR_STRIDE, cnt);
     basei = __shfl_sync(0xffffffffu, basei, 0);
     int* dst = a.part_lists + (long long)c * a.part_cap + basei;
     for (int i = lane; i < cnt; i += 32) dst[i] = stage_list[c * PART_STAGE + i];
-    staged[c] = 0;
     __syncwarp();
   };
   const long long n_tiles = (a.n + 31) >> 5;
@@ -150,33 +170,29 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
     mbar_wait(&bars[stage], (parity_bits >> stage) & 1);
     parity_bits ^= 1u << stage;
 
-    Hot h;
-    double reward = 0.0;
-    int terminated = 0;
-    StepInfo info;
-    bool mine = false;
-    int cat = 4;
+    int cat = -2;   // -2 inactive lane, -1 served here, >= 0 list
     if (active) {
+      Hot h;
       unpack_hot(hot, h);
       // the PLAY-phase mask needs the hot record only; other phases are not served here
       const bool play_phase = h.phase == BGYM_PHASE_PLAY;
-      uint64_t m0 = play_phase ? action_mask(h, nullptr) : 0ull;
+      const uint64_t m0 = play_phase ? action_mask(h, nullptr) : 0ull;
       if (fused_policy) {
         if (play_phase) {
           action = policy_action(h, m0);
           if (a.actions_out) a.actions_out[e] = action;
         } else {
-          action = -1;     // the gather pass has the cold record: it samples there
+          action = -1;     // the MISC tile has the cold record: it samples there
         }
       }
-      cat = action_category_part(action);
-      // guard-terminated envs need a deck rebuild (cold record) -> OTHER list; so does every env
-      // outside PLAY phase (its observation and mask read the shop block)
+      // guard-terminated envs (:619-623) end their episode whatever the action
       const bool guard = h.ante > 100 || h.chips_scored > 1000000000LL;
-      if (!play_phase || guard) cat = 3;
-      mine = cat == 0;
-      if (mine) {
-        step_env<CAT_SELECT>(h, hot, nullptr, action, m0, nullptr, reward, terminated, info);
+      cat = (fused_policy && !play_phase) ? (int)L_MISC : route_env(h, action, m0, guard);
+      if (cat < 0) {
+        double reward = 0.0;
+        int terminated = 0;
+        StepInfo info;
+        step_env<CAT_SELECT, false>(h, hot, nullptr, action, m0, nullptr, reward, terminated, info, nullptr);
         // a card toggle changes bytes 16..31 of the hot record and nothing else (include/bgym.h): that chunk goes
         // straight from registers to its place — one 32-byte sector per env instead of the 144-byte record; a
         // rejected action changes nothing at all
@@ -185,165 +201,277 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
         write_step_outputs(a, e, reward, terminated, info);
       }
     }
-    // defer the other categories: stage the env index in the warp's list, flush runs of >= 32
+    // defer the other envs: stage the env index in the warp's list, flush runs of >= 32
+    if (__ballot_sync(0xffffffffu, cat >= 0)) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      uint32_t bal = __ballot_sync(0xffffffffu, cat == c + 1);
-      if (bal) {
-        if (cat == c + 1) stage_list[c * PART_STAGE + staged[c] + __popc(bal & ((1u << lane) - 1))] = (int)e;
-        staged[c] += __popc(bal);
-        if (staged[c] >= 32) flush_list(c);
+      for (int c = 0; c < N_LISTS_L1; c++) {
+        uint32_t bal = __ballot_sync(0xffffffffu, cat == c);
+        if (bal) {
+          if (cat == c) stage_list[c * PART_STAGE + staged[c] + __popc(bal & ((1u << lane) - 1))] = (int)e;
+          staged[c] += __popc(bal);
+          if (staged[c] >= 32) { flush_list(c, staged[c]); staged[c] = 0; }
+        }
       }
     }
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
       uint32_t cnt = (uint32_t)min(32LL, a.n - tile * 32);
-      // deferred envs' observation slots hold stale bytes; their gather pass rewrites them afterwards
+      // deferred envs' observation slots hold stale bytes; their tile rewrites them afterwards
       if (with_obs) bulk_s2g(a.obs + tile * 32 * BGYM_OBS_BYTES, obs_buf, cnt * BGYM_OBS_BYTES);
       bulk_commit();
     }
   }
 #pragma unroll
-  for (int c = 0; c < 3; c++) if (staged[c]) flush_list(c);
+  for (int c = 0; c < N_LISTS_L1; c++) if (staged[c]) flush_list(c, staged[c]);
   if (lane == 0) bulk_wait0();
 }
 
 // ------------------------------------------------------------------------------------------------
-// gather pass: one listed env per lane, per-lane bulk copies of its hot and cold record
+// list tiles: one listed env per lane
 // ------------------------------------------------------------------------------------------------
-constexpr int GATHER_WARPS = 4;
-// the observation tile (32 x 176 B) is staged OVER the hot + cold tiles once their stores have read
-// them, so a warp needs 10 KB and an SM holds BGYM_GATHER_CTAS x 4 warps (the passes are bound by
-// dependent integer latency: resident warps are what buys throughput)
-constexpr int GATHER_WARP_SMEM = 32 * (BGYM_HOT_BYTES + BGYM_COLD_BYTES);  // 10240 >= 32 * 176
-constexpr int GATHER_CTA_SMEM = GATHER_WARPS * GATHER_WARP_SMEM + 16 * GATHER_WARPS;
+#ifndef BGYM_GATHER_WARPS
+#define BGYM_GATHER_WARPS 4
+#endif
+constexpr int GATHER_WARPS = BGYM_GATHER_WARPS;
+// shared memory of a list kernel: one cold-record slot per lane for the lists that stage it, none for the others
+constexpr int GATHER_CTA_SMEM = GATHER_WARPS * 32 * BGYM_COLD_BYTES;
 #ifndef BGYM_GATHER_CTAS
 #define BGYM_GATHER_CTAS 4
 #endif
 constexpr int GATHER_CTAS_PER_SM = BGYM_GATHER_CTAS;
 
-// One gather tile: lane `lane` serves listed env `e` (active lanes only; n_active of them, lanes 0..n_active-1).
-// hot_buf / cold_buf are the warp's 32-slot staging tiles, the observation tile is staged over them.
-template <int CATS, int LIST, bool STORE_COLD>
-__device__ __forceinline__ void gather_tile(const StepArgs& a, uint8_t* hot_buf, uint8_t* cold_buf, uint64_t* bar,
-                                            uint32_t& parity, long long e, bool active, int n_active, int lane) {
+// append the env of every lane with `push` set to device list `l` (one atomic per call and warp)
+__device__ __forceinline__ void push_list(const StepArgs& a, int l, bool push, long long e, int lane) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, push);
+  if (!bal) return;
+  int basei = 0;
+  if (lane == 0) basei = atomicAdd(a.part_counters + l * PART_CTR_STRIDE, __popc(bal));
+  basei = __shfl_sync(0xffffffffu, basei, 0);
+  if (push) a.part_lists[(long long)l * a.part_cap + basei + __popc(bal & ((1u << lane) - 1))] = (int)e;
+}
+
+#ifdef BGYM_PREFETCH_L1
+#define BGYM_PREFETCH(p) prefetch_l1(p)
+#else
+#define BGYM_PREFETCH(p) prefetch_l2(p)
+#endif
+#ifdef BGYM_LOCKSTEP
+#define BGYM_CTA_SYNC() __syncthreads()
+#else
+#define BGYM_CTA_SYNC()
+#endif
+// tile modes
+enum { TM_SAMPLE = 1,      // fused random policy: envs outside PLAY phase draw their action here (the mask needs the cold record)
+       TM_DEFER = 2,       // level-1 tile: round advances and resets are handed to the level-2 lists
+       TM_STAGE_COLD = 4,
+       TM_COLD_CLEAN = 8 };  // with TM_STAGE_COLD: the path never changes the cold record, the copy is not written back// the path reads AND rewrites the cold record (shop inventory, deck modifiers, shuffles): it works
+                           // on a per-lane copy in shared memory.  In place, every load after a store to the record misses L1
+                           // (global stores do not allocate there): ncu showed those kernels at 30-50 cycles per instruction.
+
+// per-lane copy of a cold record between global and the lane's shared-memory slot (11 x 16 B; the 176-byte slot
+// stride is an odd multiple of 16, so the 128-bit accesses of a warp are bank-conflict free)
+__device__ __forceinline__ void cold_to_smem_async(uint8_t* slot, const uint8_t* g) {   // 11 x cp.async, no registers held
+#pragma unroll
+  for (int k = 0; k < BGYM_COLD_BYTES / 16; k++) cp_async16(slot + 16 * k, g + 16 * k);
+}
+__device__ __forceinline__ void cold_from_smem(uint8_t* g, const uint8_t* slot) {
+#pragma unroll
+  for (int k = 0; k < BGYM_COLD_BYTES / 16; k++) reinterpret_cast<uint4*>(g)[k] = lds128(slot + 16 * k);
+}
+
+// Which lists work on a shared-memory copy of the cold record.  Measured (profiles/r02_step_experiments.md): staging it
+// for the level-1 lists that rewrite it (shop, consumables) left their latency unchanged and cost 13 us of overlap
+// between the seven kernels (22 KB of shared memory per CTA); the level-2 tiles, which are nothing but cold-record
+// rewrites (a shuffle; a shop generation), went from 71 to 34 us with it.
+#if defined(BGYM_STAGE_ALL)
+constexpr int STG_RO = TM_STAGE_COLD, STG_RW = TM_STAGE_COLD;
+#elif defined(BGYM_STAGE_RW)
+constexpr int STG_RO = 0, STG_RW = TM_STAGE_COLD;
+#else
+constexpr int STG_RO = 0, STG_RW = 0;
+#endif
+__host__ __device__ constexpr int list_smem_bytes(int list) { return (list >= 7 /*level 2*/ || STG_RW || STG_RO) ? GATHER_CTA_SMEM : 0; }
+
+// One tile: lane `lane` serves listed env `e`, WORKING ON THE RECORDS WHERE THEY LIE: the hot record is lifted into
+// registers with nine 16-byte loads and written back the same way, the cold record (deck, shop) is read and written in
+// place through L1 — a step touches a handful of its 176 bytes (eight deck entries for a discard, the deck half for a
+// played hand, the shop block in the shop), and the observation goes out as eleven 16-byte stores from registers.
+// What was tried before (profiles/r02_ncu_summary.md): staging hot + cold + observation tiles in shared memory with
+// per-lane bulk copies (round 1: ~50 SM-cycles per bulk copy, 96 per tile, whatever the code between them did), then
+// with cooperative 16-byte cp.async / store sweeps (7 M warp-instructions of address arithmetic per step, 10 KB of
+// shared memory and 128 registers per warp-tile = 16 warps per SM: long-scoreboard and fetch stalls with ~4 warps per
+// scheduler to hide them).  Without the staging a tile needs no shared memory at all and occupancy is set by registers.
+// One KERNEL per list (env_step_list_kernel<LIST>): its own register allocation, arguments in the constant bank, no
+// calls on the common path.  A single kernel walking all lists with out-of-line tile functions was measured first
+// (profiles/r02_ncu_summary.md): 2 KB stack frames per thread, 2.8 M local-memory requests per step missing L1, 200 KB of
+// SASS at 75 % instruction-cache hit rate — slower than round 1's divergent passes in spite of 40 % fewer instructions.
+template <int CATS, int MODE>
+__device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool active, int lane, uint8_t* cold_slot) {
   const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
   const bool fused_policy = (a.flags & BGYM_FLAG_RANDOM_POLICY) != 0;
-  uint8_t* hot = hot_buf + lane * BGYM_HOT_BYTES;
-  uint8_t* cold = cold_buf + lane * BGYM_COLD_BYTES;
-  uint8_t* obs_s = hot_buf + lane * BGYM_OBS_BYTES;     // overlay, see GATHER_WARP_SMEM
-  bulk_wait_read0();    // this lane's bulk stores of the previous tile have read their slots
-  __syncwarp();
-  if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)n_active * (BGYM_HOT_BYTES + BGYM_COLD_BYTES));
-  __syncwarp();
-  if (active) {
-    bulk_g2s(hot, a.hot + e * BGYM_HOT_BYTES, BGYM_HOT_BYTES, bar);
-    bulk_g2s(cold, a.cold + e * BGYM_COLD_BYTES, BGYM_COLD_BYTES, bar);
+  const bool autoreset = (a.flags & BGYM_FLAG_AUTORESET) != 0;
+  constexpr bool DEFER = (MODE & TM_DEFER) != 0;
+  constexpr bool STAGE = (MODE & TM_STAGE_COLD) != 0;
+  uint8_t* hot = a.hot + (active ? e : 0) * BGYM_HOT_BYTES;
+  uint8_t* cold_g = a.cold + (active ? e : 0) * BGYM_COLD_BYTES;
+  uint8_t* cold = STAGE ? cold_slot : cold_g;
+  if (STAGE) {
+    __syncwarp();     // every lane is done with the previous tile's slots
+    if (active) cold_to_smem_async(cold_slot, cold_g);      // in flight together with the hot record's loads below
   }
-  // read once, straight from L2
-  int action = (active && !(fused_policy && LIST >= 2)) ? __ldcg(a.actions + e) : 0;
-  mbar_wait(bar, parity);
-  parity ^= 1;
-
   Hot h;
   double reward = 0.0;
-  int terminated = 0;
+  int terminated = 0, snap = -1;
   StepInfo info;
   bool want_reset = false;
   uint32_t new_seed = 0;
+  int action = 0;
+  uint64_t m0 = 0;
   if (active) {
+    // read once, straight from L2 (with the fused policy the main pass wrote it for PLAY-phase envs)
+    action = __ldcg(a.actions + e);
     unpack_hot(hot, h);
-    uint64_t m0 = action_mask(h, cold);
-    if (fused_policy && LIST >= 2) {
-      // envs outside PLAY phase (and guard-terminated ones) sample here, where the mask is complete;
-      // PLAY-phase envs already carry the action the main pass sampled (LIST 3 = small-slab kernel: no
-      // main pass ran, every env samples here)
-      if (LIST == 2 && h.phase == BGYM_PHASE_PLAY) action = __ldcg(a.actions + e);
-      else { action = policy_action(h, m0); if (a.actions_out) a.actions_out[e] = action; }
+  }
+  if (STAGE) { cp_async_wait_all(); __syncwarp(); }
+  if (active) m0 = action_mask(h, cold);
+  BGYM_CTA_SYNC();
+  if (active) {
+    if ((MODE & TM_SAMPLE) && fused_policy && (h.phase != BGYM_PHASE_PLAY || !DEFER)) {
+      // envs outside PLAY phase sample here, where the mask is complete; PLAY-phase envs of a level-1 tile carry
+      // the action the main pass sampled (the small-slab kernel has no main pass: every env samples here)
+      action = policy_action(h, m0);
+      if (a.actions_out) a.actions_out[e] = action;
     }
-    // the OTHER list also receives SELECT / never-legal ids of envs the main pass does not serve
-    step_env<(LIST == 2) ? (CAT_OTHER | CAT_SELECT) : CATS>(h, hot, cold, action, m0, a.draws ? a.draws + e : nullptr,
-                                                          reward, terminated, info);
-    if (terminated && (a.flags & BGYM_FLAG_AUTORESET)) {
-      uint32_t episode = h.episode + 1;
-      new_seed = next_episode_seed(h.rng_seed);
-      reset_hot(h, new_seed);
-      if (a.flags & BGYM_FLAG_GEN_C3) gen_hot(h, new_seed, a.flags);
-      h.episode = episode;
+    step_env<CATS, DEFER>(h, hot, cold, action, m0, a.draws ? a.draws + e : nullptr, reward, terminated, info, &snap);
+    if (terminated && autoreset) {
       info.flags |= BGYM_F_AUTORESET_DONE;
       want_reset = true;
+      if (!DEFER) {
+        uint32_t episode = h.episode + 1;
+        new_seed = next_episode_seed(h.rng_seed);
+        reset_hot(h, new_seed);
+        if (a.flags & BGYM_FLAG_GEN_C3) gen_hot(h, new_seed, a.flags);
+        h.episode = episode;
+      }
     }
   }
-  if (a.flags & BGYM_FLAG_AUTORESET) autoreset_warp(want_reset, new_seed, cold, lane, (a.flags & BGYM_FLAG_GEN_C3) != 0);
-  ShopObs so;
-  uint64_t m1 = 0;
-  if (active) {
+  BGYM_CTA_SYNC();
+  if (active) write_step_outputs(a, e, reward, terminated, info);
+  bool store_state = active, emit_obs = active && with_obs;
+  if (DEFER) {
+    // hand the long paths on: a reset needs nothing of this tile but the outputs (the level-2 tile reads seed and
+    // episode from the unchanged record), an advancing env continues from the state stored here
+    push_list(a, L_RESET, want_reset, e, lane);
+    push_list(a, L_ADVANCE, snap >= 0, e, lane);
+    if (snap >= 0) a.part_aux[e] = (uint16_t)snap;
+    store_state = active && !want_reset;
+    emit_obs = emit_obs && !want_reset && snap < 0;
+  } else if (autoreset) {
+    autoreset_warp(want_reset, new_seed, cold, lane, (a.flags & BGYM_FLAG_GEN_C3) != 0);
+  }
+  BGYM_CTA_SYNC();
+  if (store_state) {
     pack_hot(hot, h);
-    if (want_reset) hot_clear_extra(hot);
-    if (with_obs) { m1 = action_mask(h, cold); obs_shop_block(h, cold, so); }   // last reads of the cold slot
-    write_step_outputs(a, e, reward, terminated, info);
+    if (!DEFER && want_reset) hot_clear_extra(hot);
   }
-  fence_async_smem();   // every lane: a cooperative reset writes other lanes' slots
-  __syncwarp();
-  if (active) {
-    bulk_s2g(a.hot + e * BGYM_HOT_BYTES, hot, BGYM_HOT_BYTES);
-    if (STORE_COLD || want_reset) bulk_s2g(a.cold + e * BGYM_COLD_BYTES, cold, BGYM_COLD_BYTES);
-    bulk_commit();
-  }
-  if (with_obs) {
-    bulk_wait_read0();  // this lane's record stores have read shared memory ...
-    __syncwarp();       // ... and so have all the others': the tile is free for the observations
-    if (active) write_obs_regs(h, so, m1, obs_s);
-    fence_async_smem();
-    if (active) { bulk_s2g(a.obs + e * BGYM_OBS_BYTES, obs_s, BGYM_OBS_BYTES); bulk_commit(); }
+  BGYM_CTA_SYNC();
+  if (emit_obs) write_obs(h, cold, action_mask(h, cold), a.obs + e * BGYM_OBS_BYTES);
+  if (STAGE) {
+    __syncwarp();     // a cooperative reset (small-slab kernel) writes other lanes' slots
+    if (store_state && !(MODE & TM_COLD_CLEAN)) cold_from_smem(cold_g, cold_slot);
   }
 }
 
-// Small slabs (n <= BGYM_SMALL_N): ONE launch, every env served by the gather tile code with all action
-// categories compiled in (LIST 3 = identity list).  A step of a few thousand envs is bound by launch latency
-// and one tile's dependent chain, not by bandwidth or instruction fetch, so the five-launch split only adds
-// to it: this is what makes the N = 1 Gymnasium facade usable.
-__global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_step_small_kernel(StepArgs a) {
+// level-2 tile: the round advance of a hand that beat the blind (balatro_env_2.py:914-925 -> :1326-1392), every lane
+// on the same path.  The step's outputs were written by the level-1 tile; this one finishes state and observation.
+__device__ __forceinline__ void advance_tile(const StepArgs& a, long long e, bool active, uint8_t* cold_slot) {
+  const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
+  __syncwarp();
+  if (!active) return;
+  uint8_t* hot = a.hot + e * BGYM_HOT_BYTES;
+  uint8_t* cold_g = a.cold + e * BGYM_COLD_BYTES;
+  cold_to_smem_async(cold_slot, cold_g);
+  const uint32_t snap = a.part_aux[e];
+  Hot h;
+  unpack_hot(hot, h);
+  cp_async_wait_all();
+  step_env_advance(h, hot, cold_slot, a.draws ? a.draws + e : nullptr, snap);
+  pack_hot(hot, h);
+  if (with_obs) write_obs(h, cold_slot, action_mask(h, cold_slot), a.obs + e * BGYM_OBS_BYTES);
+  cold_from_smem(cold_g, cold_slot);
+}
+
+// level-2 tile: in-place reset of terminated envs (balatro_env_2.py:505-558), each lane building its own fresh
+// episode; nothing is loaded but the seed and the episode counter of the old record.
+__device__ __forceinline__ void reset_tile(const StepArgs& a, long long e, bool active, uint8_t* cold_slot) {
+  const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
+  __syncwarp();
+  if (!active) return;
+  uint8_t* hot = a.hot + e * BGYM_HOT_BYTES;
+  const uint32_t old_seed = __ldcg(reinterpret_cast<const uint32_t*>(hot + 120));
+  const uint32_t episode = __ldcg(reinterpret_cast<const uint32_t*>(hot + 132)) + 1;
+  const uint32_t new_seed = next_episode_seed(old_seed);
+  const bool gen = (a.flags & BGYM_FLAG_GEN_C3) != 0;
+  Hot h;
+  reset_hot(h, new_seed);
+  if (gen) gen_hot(h, new_seed, a.flags);
+  h.episode = episode;
+  reset_blocks_serial(cold_slot, new_seed, nullptr, gen);      // deck build + shuffle in the lane's shared-memory slot
+  pack_hot(hot, h);
+  hot_clear_extra(hot);
+  if (with_obs) write_obs(h, cold_slot, action_mask(h, cold_slot), a.obs + e * BGYM_OBS_BYTES);
+  cold_from_smem(a.cold + e * BGYM_COLD_BYTES, cold_slot);
+}
+
+// Small slabs (n <= BGYM_SMALL_N): ONE launch, every env served by the tile code with all action categories compiled
+// in and nothing deferred.  A step of a few thousand envs is bound by launch latency and one tile's dependent chain,
+// not by bandwidth or instruction fetch, so the three-launch split only adds to it: this is what makes the N = 1
+// Gymnasium facade usable.
+__global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_step_small_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* hot_buf = smem + warp * GATHER_WARP_SMEM;
-  uint8_t* cold_buf = hot_buf + 32 * BGYM_HOT_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GATHER_WARPS * GATHER_WARP_SMEM) + warp * 2;
-  if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-  __syncwarp();
+  uint8_t* cold_slot = smem + (warp * 32 + lane) * BGYM_COLD_BYTES;
   const long long n_tiles = (a.n + 31) >> 5;
-  uint32_t parity = 0;
-  for (long long tile = (long long)blockIdx.x * GATHER_WARPS + warp; tile < n_tiles; tile += (long long)gridDim.x * GATHER_WARPS) {
-    const long long e = tile * 32 + lane;
+  for (long long tile0 = (long long)blockIdx.x * GATHER_WARPS; tile0 < n_tiles; tile0 += (long long)gridDim.x * GATHER_WARPS) {
+    const long long e = (tile0 + warp) * 32 + lane;     // CTA-uniform trip count
     const bool active = e < a.n;
-    gather_tile<CAT_ALL, 3, true>(a, hot_buf, cold_buf, bar, parity, active ? e : -1, active, (int)min(32LL, a.n - tile * 32), lane);
+    gather_tile<CAT_ALL, TM_SAMPLE | TM_STAGE_COLD>(a, active ? e : -1, active, lane, cold_slot);
   }
-  bulk_wait0();
 }
 
-template <int CATS, int LIST, bool STORE_COLD>
-__global__ void __launch_bounds__(GATHER_WARPS * 32, GATHER_CTAS_PER_SM) env_step_gather_kernel(StepArgs a) {
+// The list passes: one kernel per list, persistent warps walk its tiles.  The level-1 kernels run concurrently (forked
+// streams), the two level-2 kernels after them.
+static_assert(L_PLAY == 0 && L_ADVANCE == 7 && N_LISTS == 9, "list_smem_bytes() / list_ctas() name lists by value");
+// resident CTAs per SM a list kernel is compiled for (register cap).  A list pass is latency-bound — a tile is one long
+// dependent chain of ~20-45 us — so the level's duration is (tiles / resident warps) x tile latency.  More resident
+// warps by a lower register cap cost more in spills than they bring (measured: 5 / 6 / 8 CTAs = +3 / +19 / +42 %).
+#ifndef BGYM_PLAY_CTAS
+#define BGYM_PLAY_CTAS GATHER_CTAS_PER_SM
+#endif
+__host__ __device__ constexpr int list_ctas(int list) { return list == 0 /*L_PLAY*/ ? BGYM_PLAY_CTAS : GATHER_CTAS_PER_SM; }
+template <int LIST>
+__global__ void __launch_bounds__(GATHER_WARPS * 32, list_ctas(LIST)) env_step_list_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* hot_buf = smem + warp * GATHER_WARP_SMEM;
-  uint8_t* cold_buf = hot_buf + 32 * BGYM_HOT_BYTES;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + GATHER_WARPS * GATHER_WARP_SMEM) + warp * 2;
-  if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-  __syncwarp();
-  const int count = a.part_counters[(LIST + 1) * PART_CTR_STRIDE];
+  uint8_t* cold_slot = smem + (warp * 32 + lane) * BGYM_COLD_BYTES;   // only touched by the lists that stage (list_smem_bytes)
+  const int count = a.part_counters[LIST * PART_CTR_STRIDE];
   const int* list = a.part_lists + (long long)LIST * a.part_cap;
   const int n_tiles = (count + 31) >> 5;
-  const int warp_gid = blockIdx.x * GATHER_WARPS + warp;
-  const int warp_cnt = gridDim.x * GATHER_WARPS;
-  uint32_t parity = 0;
-  for (int tile = warp_gid; tile < n_tiles; tile += warp_cnt) {
+  for (int tile = blockIdx.x * GATHER_WARPS + warp; tile < n_tiles; tile += gridDim.x * GATHER_WARPS) {
     const int idx = tile * 32 + lane;
     const bool active = idx < count;
-    const long long e = active ? (long long)list[idx] : -1;
-    gather_tile<CATS, LIST, STORE_COLD>(a, hot_buf, cold_buf, bar, parity, e, active, min(32, count - tile * 32), lane);
+    const long long e = active ? (long long)__ldcg(list + idx) : -1;
+    if (LIST == L_PLAY) gather_tile<CAT_PLAY, TM_DEFER | STG_RO>(a, e, active, lane, cold_slot);
+    else if (LIST == L_CONS) gather_tile<CAT_CONS, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
+    else if (LIST == L_GEN) gather_tile<CAT_GEN, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
+    else if (LIST == L_MISC) gather_tile<CAT_OTHER | CAT_SELECT, TM_DEFER | TM_SAMPLE | STG_RW>(a, e, active, lane, cold_slot);
+    else if (LIST == L_DISCARD) gather_tile<CAT_DISCARD, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
+    else if (LIST == L_SHOP) gather_tile<CAT_SHOP, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
+    else if (LIST == L_BLIND) gather_tile<CAT_BLIND, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
+    else if (LIST == L_ADVANCE) advance_tile(a, e, active, cold_slot);
+    else reset_tile(a, e, active, cold_slot);
   }
-  bulk_wait0();
 }
 
 }  // namespace bgym

@@ -133,6 +133,7 @@ class BalatroVecEnv:
             self._len_acc = torch.zeros(n, dtype=torch.int32, device=dev)
             self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
         self._obs_views: Optional[Dict[str, "torch.Tensor"]] = None
+        self._obs_current = False     # obs_buf describes the current state (False after the state was changed from outside)
         self._step_count = 0
         self._pending_actions = None
         self.observation_keys = list(L.OBS_KEYS)
@@ -197,6 +198,22 @@ class BalatroVecEnv:
                                      seeds32.data_ptr(), self._ptr(decks52), self.num_envs, self._gen_flags, self._stream())
         _lib.check(rc, "bgym_reset")
         self._keep = (seeds32, decks52, reset_mask)  # keep inputs alive until the stream has consumed them
+        self._obs_current = True
+        return self.obs
+
+    def refresh_observations(self):
+        """Re-emit every env's observation from its state records (after the state was changed from outside:
+        load_state, inject_numpy, randomize_c3).  bgym_reset with an all-zero reset mask resets nothing and
+        rewrites the observations."""
+        torch = self.torch
+        zero = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        seeds = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.bgym_reset(self.hot.data_ptr(), self.cold.data_ptr(), self.obs_buf.data_ptr(), zero.data_ptr(),
+                                     seeds.data_ptr(), None, self.num_envs, 0, self._stream())
+        _lib.check(rc, "bgym_reset (observation refresh)")
+        self._keep = (zero, seeds)
+        self._obs_current = True
         return self.obs
 
     # -- step --------------------------------------------------------------------------------------
@@ -226,6 +243,7 @@ class BalatroVecEnv:
                                     self.info_buf.data_ptr() if want_info else None, self.num_envs, flags, self._stream())
         _lib.check(rc, "bgym_step")
         self._keep = (act, draws)
+        self._obs_current = True
         self._step_count += 1
         return self.obs, self.reward, self.terminated, self.truncated, self.info_buf
 
@@ -258,6 +276,8 @@ class BalatroVecEnv:
         if not hasattr(self, "_step_ctr"):
             self._step_ctr = torch.zeros(1, dtype=torch.int64, device=self.device)
         flags = (L.FLAG_AUTORESET if self.autoreset else 0) | (L.FLAG_RANDOM_POLICY if policy == "fused" else 0) | self._gen_flags
+        if not self._obs_current:
+            self.refresh_observations()
 
         def launch():
             st = self._stream()
@@ -299,8 +319,11 @@ class BalatroVecEnv:
 
     # -- checkpoint (save_state / load_state, balatro_env_2.py:1575-1615) ----------------------------
     def save_state(self):
-        return {"hot": self.hot.clone(), "cold": self.cold.clone(), "step_count": self._step_count,
-                "ret_acc": self._ret_acc.clone(), "len_acc": self._len_acc.clone()}
+        ckpt = {"hot": self.hot.clone(), "cold": self.cold.clone(), "obs": self.obs_buf.clone(), "step_count": self._step_count,
+                "ret_acc": self._ret_acc.clone(), "len_acc": self._len_acc.clone(), "stats": self.stats.clone()}
+        if hasattr(self, "_step_ctr"):
+            ckpt["step_ctr"] = self._step_ctr.clone()
+        return ckpt
 
     def load_state(self, ckpt):
         self.hot.copy_(ckpt["hot"])
@@ -308,6 +331,17 @@ class BalatroVecEnv:
         self._step_count = ckpt["step_count"]
         self._ret_acc.copy_(ckpt["ret_acc"])
         self._len_acc.copy_(ckpt["len_acc"])
+        if "stats" in ckpt:
+            self.stats.copy_(ckpt["stats"])
+        if "step_ctr" in ckpt:
+            if not hasattr(self, "_step_ctr"):
+                self._step_ctr = self.torch.zeros(1, dtype=self.torch.int64, device=self.device)
+            self._step_ctr.copy_(ckpt["step_ctr"])
+        if "obs" in ckpt:
+            self.obs_buf.copy_(ckpt["obs"])
+            self._obs_current = True
+        else:
+            self.refresh_observations()
 
     # -- state injection (the C3 state generator of SURVEY §8d; reference: Appendix E) ---------------
     def inject_numpy(self, state_np: np.ndarray):
@@ -316,6 +350,7 @@ class BalatroVecEnv:
         raw = state_np.view(np.uint8).reshape(self.num_envs, L.STATE_BYTES)
         self.hot.copy_(self.torch.from_numpy(np.ascontiguousarray(raw[:, :L.HOT_BYTES])))
         self.cold.copy_(self.torch.from_numpy(np.ascontiguousarray(raw[:, L.HOT_BYTES:])))
+        self.refresh_observations()
 
     def state_numpy(self) -> np.ndarray:
         """Host copy of all envs as combined {hot, cold} records (L.STATE_DTYPE)."""
@@ -351,3 +386,4 @@ class BalatroVecEnv:
         deck = deck_view.to(torch.int64) & 63
         deck = deck | (enh << 6) | (ed << 10) | (seal << 13)
         deck_view.copy_(torch.where(deck >= 2 ** 15, deck - 2 ** 16, deck).to(torch.int16))
+        self.refresh_observations()

@@ -116,11 +116,12 @@ enum {
    * counterpart is the injection recipe of SURVEY Appendix E, oracle/refbaseline.py::_inject_c3).
    * Honoured by bgym_reset AND by the in-kernel autoreset of bgym_step, so every episode of a long
    * rollout starts from a generated state, not only the first.  All draws come from Philox4x32-10
-   * keyed (episode seed, BGYM_GEN_KEY1); integer draws are floor(word * n / 2^32) (|p - 1/n| < n / 2^32).
-   *   card k of the freshly built deck (k = suit * 13 + rank - 2, balatro_env_2.py:519-522), block counter k:
-   *     enhancement: word x, top two bits zero (p = 1/4) -> 1 + next three bits (uniform over the 8)
-   *     edition:     e = floor(y * 30 / 2^32) < 3 (p = 1/10) -> 1 + e (FOIL, HOLO, POLY)
-   *     seal:        s = floor(z * 40 / 2^32) < 4 (p = 1/10) -> 1 + s
+   * keyed (episode seed, BGYM_GEN_KEY1); integer draws are floor(word * n / 2^bits) (|p - 1/n| < n / 2^27).
+   *   card k of the freshly built deck (k = suit * 13 + rank - 2, balatro_env_2.py:519-522): block counter k / 2,
+   *   words (w0, w1) = (x, y) for even k, (z, w) for odd k:
+   *     enhancement: top two bits of w0 zero (p = 1/4) -> 1 + the next three bits (uniform over the 8)
+   *     edition:     e = floor((w0 & 0x7FFFFFF) * 30 / 2^27) < 3 (p = 1/10) -> 1 + e (FOIL, HOLO, POLY)
+   *     seal:        s = floor(w1 * 40 / 2^32) < 4 (p = 1/10) -> 1 + s
    *     the modifiers travel with the card through the shuffle (i.i.d., so position-keyed is the same law)
    *   jokers: blocks 64, 65: five draws without replacement over the BGYM_NUM_SHOP_JOKERS ids with
    *     base_cost > 0 (draw t picks the floor(w_t * (145 - t) / 2^32)-th id not chosen yet), in draw order */
@@ -315,6 +316,11 @@ int bgym_reset(BgymHot* hot, BgymCold* cold, BgymObs* obs, const uint8_t* reset_
 int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* draws, BgymObs* obs,
               double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
               int64_t n, int flags, void* stream);
+
+/* bgym_step keeps a few bytes per env of device scratch (work lists) per (device, stream) it is called on, sized for
+ * the largest slab seen; this gives the scratch of `stream` on the current device back.  Call it once the stream's last
+ * step has completed (bgym_vec_destroy does it for the handle's own stream). */
+int bgym_release_stream(void* stream);
 
 /* action mask as one 64-bit word per env (balatro_env_2.py:1426-1471) */
 int bgym_action_mask(const BgymHot* hot, const BgymCold* cold, uint64_t* mask, int64_t n, void* stream);

@@ -550,13 +550,15 @@ static uint32_t next_episode_seed(uint32_t seed) { /* autoreset: seed of the fol
  * the injection recipe); the law below is the one include/bgym.h specifies, restated with lists. */
 static uint32_t gen_scaled(uint32_t word, uint32_t n) { return (uint32_t)(((uint64_t)word * n) >> 32); }
 
-static uint16_t gen_card_mods(uint32_t seed, int k) { /* card k = suit * 13 + rank - 2 */
+static uint16_t gen_card_mods(uint32_t seed, int k) { /* card k = suit * 13 + rank - 2; two cards share a block */
   uint32_t w[4];
-  philox4x32_10((uint32_t)k, 0, 0, 0, seed, BGYM_GEN_KEY1, w);
+  philox4x32_10((uint32_t)(k / 2), 0, 0, 0, seed, BGYM_GEN_KEY1, w);
+  uint32_t first = w[(k % 2) * 2], second = w[(k % 2) * 2 + 1];
   unsigned enh = 0, ed = 0, seal = 0;
-  if ((w[0] >> 30) == 0) enh = 1 + ((w[0] >> 27) & 7);          /* 1/4, then uniform over the 8 enhancements */
-  uint32_t e = gen_scaled(w[1], 30); if (e < 3) ed = 1 + e;     /* 1/10 over FOIL, HOLO, POLY */
-  uint32_t t = gen_scaled(w[2], 40); if (t < 4) seal = 1 + t;   /* 1/10 over the four seals */
+  if ((first >> 30) == 0) enh = 1 + ((first >> 27) & 7);         /* 1/4, then uniform over the 8 enhancements */
+  uint32_t e = (uint32_t)(((uint64_t)(first & 0x07FFFFFFu) * 30) >> 27);
+  if (e < 3) ed = 1 + e;                                         /* 1/10 over FOIL, HOLO, POLY (low 27 bits) */
+  uint32_t t = gen_scaled(second, 40); if (t < 4) seal = 1 + t;  /* 1/10 over the four seals */
   return (uint16_t)((enh << 6) | (ed << 10) | (seal << 13));
 }
 

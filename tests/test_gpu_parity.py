@@ -232,6 +232,31 @@ def test_step_without_observations(torch, step_path):
                          y.terminated.data_ptr(), y.truncated.data_ptr(), None, n, flags, None) < 0
 
 
+def test_refresh_observations_after_state_injection(torch):
+    """State changed from outside (inject_numpy / load_state): the observation buffer is re-emitted from the state, so
+    the next sampled actions are legal for the injected state."""
+    from balatro_gym_b200 import BalatroVecEnv
+    from oracle import coracle
+    n = 2048
+    v = BalatroVecEnv(n, seed=21, generator="c4")
+    v.reset()
+    for _ in range(40):
+        v.step(random_policy=True)
+    ck = v.save_state()
+    st = v.state_numpy()
+    w = BalatroVecEnv(n, seed=999)
+    w.reset()
+    w.inject_numpy(st)
+    assert torch.equal(w.obs_buf, v.obs_buf)            # observations follow the injected state
+    for _ in range(10):
+        v.step(random_policy=True)
+    v.load_state(ck)
+    assert torch.equal(w.obs_buf, v.obs_buf) and torch.equal(w.hot, v.hot)
+    a = v.sample_actions(seed=5)
+    m = coracle.action_mask(v.state_numpy())
+    assert ((m >> a.cpu().numpy().astype(np.uint64)) & 1).all()
+
+
 def test_empty_slab_calls_are_noops(torch):
     import balatro_gym_b200 as b
     lib = b.load()
