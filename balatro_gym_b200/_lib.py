@@ -44,10 +44,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise BgymError("nvcc not found: cannot build libbgym.so")
     extra = os.environ.get("BGYM_NVCC_EXTRA", "").split()        # experiments only (e.g. -DBGYM_GATHER_CTAS=6)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, SOURCES[0]]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise BgymError("nvcc failed:\n" + res.stdout + res.stderr)
+    # several ranks of one job may get here at once (torchrun): build under a file lock, into a temporary file that
+    # replaces the library atomically, so that nobody ever loads a half-written .so
+    import fcntl
+    with open(SO_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():      # another process built it while we waited
+                return SO_PATH
+            tmp = f"{SO_PATH}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, SOURCES[0]]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise BgymError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, SO_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     if verbose:
         print(res.stderr)
     return SO_PATH

@@ -858,15 +858,16 @@ struct BgymVec {
 
 #define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return cuda_rc(_e, #x); } while (0)
 
-int bgym_vec_create(BgymVec** out, int64_t n, int device) {
-  if (!out || n <= 0) return set_err(BGYM_E_ARG, "bgym_vec_create: bad arguments");
-  int cnt = 0;
-  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) return set_err(BGYM_E_NODEV, "bgym_vec_create: no CUDA device");
-  if (device < 0 || device >= cnt) return set_err(BGYM_E_ARG, "bgym_vec_create: bad device index");
-  CK(cudaSetDevice(device));
-  BgymVec* v = new BgymVec();
-  memset(v, 0, sizeof *v);
-  v->n = n; v->device = device;
+// the handle entry points run on the handle's device and leave the caller's current device as they found it
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) { err = cudaGetDevice(&prev); if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define BGYM_ON_DEVICE(v) DeviceGuard _guard((v)->device); if (_guard.err != cudaSuccess) return cuda_rc(_guard.err, "cudaSetDevice")
+
+static int vec_create_impl(BgymVec* v, int64_t n) {
   CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&v->d_hot, n * BGYM_HOT_BYTES)); CK(cudaMalloc(&v->d_cold, n * BGYM_COLD_BYTES));
   auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
@@ -886,21 +887,43 @@ int bgym_vec_create(BgymVec** out, int64_t n, int device) {
   CK(cudaMallocHost(&v->h_actions, n * 4)); CK(cudaMallocHost(&v->h_seeds, n * 4)); CK(cudaMallocHost(&v->h_draws, n * BGYM_DRAWS_BYTES));
   CK(cudaMemsetAsync(v->d_hot, 0, n * BGYM_HOT_BYTES, v->stream));
   CK(cudaMemsetAsync(v->d_cold, 0, n * BGYM_COLD_BYTES, v->stream));
+  return 0;
+}
+
+int bgym_vec_create(BgymVec** out, int64_t n, int device) {
+  if (!out || n <= 0) return set_err(BGYM_E_ARG, "bgym_vec_create: bad arguments");
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) return set_err(BGYM_E_NODEV, "bgym_vec_create: no CUDA device");
+  if (device < 0 || device >= cnt) return set_err(BGYM_E_ARG, "bgym_vec_create: bad device index");
+  BgymVec* v = new BgymVec();
+  memset(v, 0, sizeof *v);
+  v->n = n; v->device = device;
+  int rc;
+  {
+    DeviceGuard guard(device);
+    rc = guard.err != cudaSuccess ? cuda_rc(guard.err, "cudaSetDevice") : vec_create_impl(v, n);
+  }
+  if (rc) {                 // a failed allocation half way: give everything back (destroy frees what is there)
+    char keep[sizeof g_err];
+    memcpy(keep, g_err, sizeof keep);
+    bgym_vec_destroy(v);
+    memcpy(g_err, keep, sizeof keep);
+    return rc;
+  }
   *out = v;
   return 0;
 }
 
 int bgym_vec_destroy(BgymVec* v) {
   if (!v) return 0;
-  cudaSetDevice(v->device);
-  cudaStreamSynchronize(v->stream);
+  DeviceGuard guard(v->device);
+  if (v->stream) cudaStreamSynchronize(v->stream);
   cudaFree(v->d_hot); cudaFree(v->d_cold); cudaFree(v->d_block); cudaFree(v->d_decks); cudaFree(v->d_mask); cudaFreeHost(v->h_mask);
   cudaFree(v->d_actions); cudaFree(v->d_seeds); cudaFree(v->d_draws);
   cudaFreeHost(v->h_hot); cudaFreeHost(v->h_cold); cudaFreeHost(v->h_block);
   cudaFreeHost(v->h_decks); cudaFreeHost(v->h_actions);
   cudaFreeHost(v->h_seeds); cudaFreeHost(v->h_draws);
-  bgym_release_stream(v->stream);
-  cudaStreamDestroy(v->stream);
+  if (v->stream) { bgym_release_stream(v->stream); cudaStreamDestroy(v->stream); }
   delete v;
   return 0;
 }
@@ -911,7 +934,7 @@ int bgym_vec_reset_host(BgymVec* v, const uint32_t* seeds, const uint8_t* decks5
 
 int bgym_vec_reset_masked_host(BgymVec* v, const uint8_t* reset_mask, const uint32_t* seeds, const uint8_t* decks52, BgymObs* obs_out) {
   if (!v || !seeds) return set_err(BGYM_E_ARG, "bgym_vec_reset_host: bad arguments");
-  CK(cudaSetDevice(v->device));
+  BGYM_ON_DEVICE(v);
   if (reset_mask) {
     memcpy(v->h_mask, reset_mask, v->n);
     CK(cudaMemcpyAsync(v->d_mask, v->h_mask, v->n, cudaMemcpyHostToDevice, v->stream));
@@ -936,7 +959,9 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
                        double* reward_out, uint8_t* terminated_out, uint8_t* truncated_out,
                        BgymInfo* info_out, int flags) {
   if (!v || !actions) return set_err(BGYM_E_ARG, "bgym_vec_step_host: bad arguments");
-  CK(cudaSetDevice(v->device));
+  if (flags & BGYM_FLAG_RANDOM_POLICY)
+    return set_err(BGYM_E_ARG, "bgym_vec_step_host: BGYM_FLAG_RANDOM_POLICY needs the device entry point (the host `actions` array is input only)");
+  BGYM_ON_DEVICE(v);
   memcpy(v->h_actions, actions, v->n * 4);
   CK(cudaMemcpyAsync(v->d_actions, v->h_actions, v->n * 4, cudaMemcpyHostToDevice, v->stream));
   if (draws) {
@@ -975,7 +1000,7 @@ int bgym_vec_pointers(BgymVec* v, void** hot, void** cold, void** obs, void** re
 // host-side BgymState records = {hot, cold} back to back
 int bgym_vec_get_state(BgymVec* v, BgymState* host_out) {
   if (!v || !host_out) return set_err(BGYM_E_ARG, "bgym_vec_get_state: bad arguments");
-  CK(cudaSetDevice(v->device));
+  BGYM_ON_DEVICE(v);
   CK(cudaMemcpyAsync(v->h_hot, v->d_hot, v->n * BGYM_HOT_BYTES, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaMemcpyAsync(v->h_cold, v->d_cold, v->n * BGYM_COLD_BYTES, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaStreamSynchronize(v->stream));
@@ -989,7 +1014,7 @@ int bgym_vec_get_state(BgymVec* v, BgymState* host_out) {
 
 int bgym_vec_set_state(BgymVec* v, const BgymState* host_in) {
   if (!v || !host_in) return set_err(BGYM_E_ARG, "bgym_vec_set_state: bad arguments");
-  CK(cudaSetDevice(v->device));
+  BGYM_ON_DEVICE(v);
   const uint8_t* in = reinterpret_cast<const uint8_t*>(host_in);
   for (int64_t i = 0; i < v->n; i++) {
     memcpy(v->h_hot + i * BGYM_HOT_BYTES, in + i * BGYM_STATE_BYTES, BGYM_HOT_BYTES);

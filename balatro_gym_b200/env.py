@@ -12,10 +12,11 @@ Error convention as in the reference: a masked action returns reward -1.0 and
 info['error'] without raising (:626-627).
 
 Replaying the reference's shuffle: the reference shuffles with CPython's
-`random.Random(seed % 2**32).shuffle` (stream 0 of DeterministicRNG, :84-106, :525); pass
-`options={'shuffle': 'reference'}` (default when a seed is given) to replay that permutation
-stream on reset so episodes start from the same deck as `BalatroEnv(seed=s)` in the reference;
-`options={'shuffle': 'philox'}` uses the native counter-based stream.
+`random.Random(seed % 2**32).shuffle` (stream 0 of DeterministicRNG, :84-106, :525).  With
+`options={'shuffle': 'reference'}` (the default) the facade keeps that MT19937 stream: `reset(seed=s)`
+restarts it, a plain `reset()` takes its NEXT shuffle — the constructor's own reset takes the first —
+exactly as the reference does (:507-509), so `BalatroEnv(seed=s)` followed by any sequence of resets
+sees the reference's decks.  `options={'shuffle': 'philox'}` uses the native counter-based stream.
 """
 from __future__ import annotations
 
@@ -127,7 +128,8 @@ class BalatroEnv(_EnvBase):
         self._p = {k: getattr(self, "_" + k).ctypes.data for k in ("act", "seeds", "obs_rec", "rew", "term", "trunc", "info", "state")}
         self.action_space = _spaces.Discrete(L.NUM_ACTIONS)
         self.observation_space = observation_space()
-        self.reset()
+        self._new_streams(self._seed)
+        self.reset()          # like the reference's constructor: consumes the first shuffle of the seed's stream
 
     # -- conversions ---------------------------------------------------------------------------------
     def _obs(self):
@@ -138,13 +140,30 @@ class BalatroEnv(_EnvBase):
             out[k] = v.copy() if isinstance(v, np.ndarray) else v
         return out
 
+    def _new_streams(self, seed: int):
+        """A seed (re)starts the env's random streams, as `DeterministicRNG(seed)` does in the reference
+        (balatro_env_2.py:507-509): the MT19937 deck-shuffle stream (stream 0: `random.Random(seed % 2**32)`) and the
+        Philox key of the in-game draws."""
+        self._seed = int(seed)
+        self._mt = _pyrandom.Random(self._seed % (2 ** 32))
+        self._philox_seed = np.uint32(self._seed % (2 ** 32) or 1)
+
     def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
-        if seed is not None and seed != 0:
-            self._seed = int(seed)
-        mode = (options or {}).get("shuffle", "reference")
-        self._seeds[0] = self._seed % (2 ** 32)
-        deck = reference_deck(self._seed) if mode == "reference" else None
+        """`reset(seed=s)` restarts the streams; `reset()` CONTINUES them, so every episode gets a new deck, boss and
+        shops — the reference only rebuilds its RNG when a seed is passed (:507-509)."""
         from . import _lib
+        from .sb3_vec_env import next_episode_seed
+        if seed is not None and seed != 0:
+            self._new_streams(seed)
+        else:
+            self._philox_seed = np.uint32(next_episode_seed(np.asarray([self._philox_seed]))[0])
+        mode = (options or {}).get("shuffle", "reference")
+        self._seeds[0] = self._philox_seed
+        deck = None
+        if mode == "reference":      # the next shuffle of the seed's MT19937 stream (:519-525)
+            cards = [(rank - 2) * 4 + suit for suit in range(4) for rank in range(2, 15)]
+            self._mt.shuffle(cards)
+            deck = np.asarray(cards, dtype=np.uint8)
         rc = self.lib.bgym_vec_reset_host(self._h, self._p["seeds"], None if deck is None else deck.ctypes.data, self._p["obs_rec"])
         _lib.check(rc, "bgym_vec_reset_host")
         return self._obs(), {}

@@ -215,8 +215,10 @@ class BalatroSB3VecEnv(_VecEnvBase):
                 if self.monitor:
                     infos[i]['episode'] = {'r': float(round(self._ep_ret[i], 6)), 'l': int(self._ep_len[i]),
                                            't': round(time.time() - self._t0, 6)}
-            if self.shuffle == "philox":
-                self._seeds[idx] = next_episode_seed(self._seeds[idx])
+            # every new episode gets a new key for its in-game draws (boss pick, shop inventories, glass / lucky
+            # rolls), whichever way its deck is shuffled — with 'reference' decks the reference's own streams go on
+            # from where the last episode left them, they do not restart either (balatro_env_2.py:507-509)
+            self._seeds[idx] = next_episode_seed(self._seeds[idx])
             self._device_reset(dones)
             for k in L.OBS_KEYS:
                 obs[k][idx] = L.obs_value(self._rec[idx], k)

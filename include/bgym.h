@@ -270,7 +270,7 @@ typedef struct BgymInfo {
 
 /* ---- replay draws (256 B per env per step) -----------------------------------
  * Replay mode: the random draws the reference made during the same step, recorded
- * on the host (oracle/reftap.py), consumed by the kernel in order instead of Philox.
+ * on the host (oracle/refenv.py::TapRandom), consumed by the kernel in order instead of Philox.
  *   u[]: results of random()/uniform(0,1) calls, in call order
  *   k[]: results of randint/choice/sample calls as 0-based indices into the
  *        population (sample contributes one entry per element drawn) */
@@ -394,6 +394,8 @@ int bgym_vec_reset_host(BgymVec* v, const uint32_t* seeds, const uint8_t* decks5
  * DummyVecEnv.step_wait resets finished envs one by one); untouched envs get their observation re-emitted */
 int bgym_vec_reset_masked_host(BgymVec* v, const uint8_t* reset_mask, const uint32_t* seeds, const uint8_t* decks52,
                                BgymObs* obs_out);
+/* flags: BGYM_FLAG_AUTORESET, BGYM_FLAG_GEN_*; BGYM_FLAG_RANDOM_POLICY is rejected (BGYM_E_ARG): `actions` is input only
+ * here.  Every bgym_vec_* call runs on the handle's device and restores the caller's current device before returning. */
 int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draws, BgymObs* obs_out,
                        double* reward_out, uint8_t* terminated_out, uint8_t* truncated_out,
                        BgymInfo* info_out, int flags);

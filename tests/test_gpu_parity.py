@@ -502,3 +502,107 @@ def test_gym_facade_matches_reference_episode(torch, reference):
             assert ("error" in ri) == ("error" in ei)
             if rt:
                 break
+
+
+def test_gym_facade_unseeded_resets_continue_the_reference_streams(torch, reference):
+    """`BalatroEnv(seed=s)` then plain `reset()` calls: every episode gets the NEXT shuffle of the seed's MT19937 stream
+    (the reference rebuilds its RNG only when a seed is passed, balatro_env_2.py:507-509; the constructor's own reset
+    takes the first shuffle), and a new key for the native in-game draws."""
+    from balatro_gym_b200.env import BalatroEnv
+    from oracle.refenv import card_code
+    for seed in (5, 77):
+        ref = reference.BalatroEnv(seed=seed)
+        env = BalatroEnv(seed=seed)
+        decks, keys = [], []
+        for k in range(4):
+            rd = [card_code(c) for c in ref.state.deck]
+            st = env.state
+            assert (st["deck"] & 63).tolist() == rd, (seed, k)
+            decks.append(tuple(rd)); keys.append(int(st["rng_seed"]))
+            ro, _ = ref.reset()
+            eo, _ = env.reset()
+            for key in L.OBS_KEYS:
+                assert np.array_equal(np.asarray(ro[key]), np.asarray(eo[key])), (seed, k, key)
+        assert len(set(decks)) == 4 and len(set(keys)) == 4          # a new deck and a new draw key every episode
+        ref.reset(seed=seed); env.reset(seed=seed)                     # a seed restarts the streams
+        assert (env.state["deck"] & 63).tolist() == [card_code(c) for c in ref.state.deck]
+        assert tuple((env.state["deck"] & 63).tolist()) == decks[0]   # = the first shuffle of the seed's stream again
+        env.close()
+
+
+def _chi2_ok(counts, expected, dof=None):
+    counts = np.asarray(counts, dtype=np.float64)
+    expected = np.asarray(expected, dtype=np.float64) * np.ones_like(counts)
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    dof = dof if dof is not None else len(counts) - 1
+    return abs(chi2 - dof) < 6 * (2 * dof) ** 0.5 + 6, chi2
+
+
+def test_native_draw_distributions(torch):
+    """Native Philox mode, distribution of the in-game draws (the reference's own draws are matched by
+    replay): boss pick uniform over 28 (boss_blinds.py:522-532); shop inventory — third pack uniform over 3, three
+    distinct jokers uniform over the 145 shop-eligible ids, voucher over 2, two cards over 52 (shop.py:112-139);
+    lucky-card money roll p = 0.0667 per played lucky card (balatro_env_2.py:719-724); The Wheel's face-down roll
+    p = 1/7 per hand card (boss_blinds.py:353)."""
+    from balatro_gym_b200 import BalatroVecEnv
+    n = 1 << 17
+    dev = "cuda"
+    full = lambda a: torch.full((n,), a, dtype=torch.int32, device=dev)
+    # ---- boss pick ----
+    v = BalatroVecEnv(n, seed=4242, autoreset=False)
+    v.reset()
+    v.step(full(47))
+    boss = v.state_field("boss_type").long()
+    assert int(boss.min()) == 1 and int(boss.max()) == 28
+    ok, chi2 = _chi2_ok(torch.bincount(boss, minlength=29)[1:].cpu().numpy(), n / 28.0)
+    assert ok, chi2
+    # ---- shop inventory (skip blind -> round advance -> shop generation) ----
+    v = BalatroVecEnv(n, seed=777, autoreset=False)
+    v.reset()
+    v.step(full(48))
+    st = v.state_numpy()
+    assert (st["phase"] == L.PHASE_SHOP).all() and (st["n_items"] == 9).all()
+    it, iid = st["item_type"], st["item_id"].astype(int)
+    assert (it[:, :3] == 1).all() and (it[:, 3:6] == 3).all() and (it[:, 6] == 4).all() and (it[:, 7:9] == 2).all()
+    assert (iid[:, 0] == 0).all() and (iid[:, 1] == 1).all()
+    ok, chi2 = _chi2_ok(np.bincount(iid[:, 2], minlength=5)[2:], n / 3.0); assert ok, ("third pack", chi2)
+    jk = iid[:, 3:6]
+    assert jk.min() >= 1 and jk.max() <= 145 and (np.diff(np.sort(jk, axis=1), axis=1) > 0).all()
+    ok, chi2 = _chi2_ok(np.bincount(jk.ravel(), minlength=146)[1:], 3 * n / 145.0); assert ok, ("shop jokers", chi2)
+    for pos in range(3):          # every position of the ordered sample is uniform too
+        ok, chi2 = _chi2_ok(np.bincount(jk[:, pos], minlength=146)[1:], n / 145.0); assert ok, ("shop joker pos", pos, chi2)
+    ok, chi2 = _chi2_ok(np.bincount(iid[:, 6], minlength=2), n / 2.0); assert ok, ("voucher", chi2)
+    ok, chi2 = _chi2_ok(np.bincount(iid[:, 7:9].ravel(), minlength=52), 2 * n / 52.0); assert ok, ("shop cards", chi2)
+    # ---- lucky money roll: every card LUCKY, small blind, select five cards, play ----
+    v = BalatroVecEnv(n, seed=99, autoreset=False)
+    v.reset()
+    deck = v.state_field("deck")
+    deck.copy_(((deck.to(torch.int32) & 63) | (L.card16(0, 8) & ~63)).to(torch.int16))
+    v.refresh_observations()
+    v.step(full(45))
+    for s in range(5):
+        v.step(full(2 + s))
+    m0 = v.state_field("money").clone()
+    v.step(full(0))
+    gained = (v.state_field("money") - m0).long()
+    played = (v.info_field("flags").long() & L.F_PLAYED) != 0
+    assert bool(played.all())
+    # a play that beats the blind also pays the round reward; look at hands that did not
+    cont = (v.info_field("flags").long() & L.F_BEAT_BLIND) == 0
+    g = gained[cont]
+    assert bool((g % 20 == 0).all()) and int(g.max()) <= 100
+    hits = float((g // 20).sum()); trials = 5.0 * int(cont.sum())
+    p = 0.0667
+    assert abs(hits / trials - p) < 5 * (p * (1 - p) / trials) ** 0.5, hits / trials
+    # ---- The Wheel: 1 in 7 hand cards face down after a non-final play ----
+    v = BalatroVecEnv(n, seed=31337, autoreset=False)
+    v.reset()
+    v.step(full(47))
+    wheel = v.state_field("boss_type") == 3
+    v.step(full(2)); v.step(full(0))
+    cont = wheel & ((v.info_field("flags").long() & (L.F_PLAYED | L.F_BEAT_BLIND | L.F_FAILED)) == L.F_PLAYED)
+    fd = v.state_field("face_down_mask").long()[cont]
+    hn = v.state_field("hand_n").long()[cont]
+    assert int(cont.sum()) > 2000
+    bits = float(sum(((fd >> i) & 1).sum() for i in range(8))); trials = float(hn.sum())
+    assert abs(bits / trials - 1 / 7) < 5 * ((1 / 7) * (6 / 7) / trials) ** 0.5, bits / trials

@@ -14,7 +14,7 @@ Numbers come from importing the reference, never from hand typing (SURVEY.md §7
       complete_joker_effects.py:121)
 The joker EFFECT table (what each joker does) is code in the reference
 (complete_joker_effects.py:35-183), so it is restated here by hand, keyed by joker NAME, and
-resolved to ids through JOKER_LIBRARY; tests/test_score_parity.py checks every row against the
+resolved to ids through JOKER_LIBRARY; tests/test_oracle_vs_reference.py checks every row against the
 reference one joker at a time.
 """
 import os
