@@ -280,6 +280,60 @@ __device__ __forceinline__ int classify(const HandHist& h) {
   return BGYM_HT_HIGH_CARD;
 }
 
+// RULES evaluator (BGYM_SCORE_RULES): BalatroSimulator.evaluate_hand balatro_sim.py:110-400 on register histograms.
+//   cnt: 13 rank counters of 4 bits (up to 8 equal cards), scnt: 4 suit counters of 8 bits, n: cards
+__device__ __forceinline__ int classify_rules(uint64_t cnt, uint32_t scnt, uint32_t rmask, int n, bool four_fingers, bool shortcut) {
+  const uint64_t ones = 0x1111111111111ull;
+  const uint64_t b0 = cnt & ones, b1 = (cnt >> 1) & ones, b2 = (cnt >> 2) & ones, b3 = (cnt >> 3) & ones;
+  const uint64_t lo = ~b3 & ones;                                   // counts below 8
+  const int n2 = __popcll(lo & ~b2 & b1 & ~b0), n3 = __popcll(lo & ~b2 & b1 & b0);   // exactly 2 / 3 (get_x_same :118)
+  const bool n4 = (lo & b2 & ~b1 & ~b0) != 0, n5 = (lo & b2 & ~b1 & b0) != 0;       // exactly 4 / 5
+  const int required = four_fingers ? 4 : 5;
+  const bool sized = n <= 5 && n >= required;                       // :133, :155
+  bool flush = false;
+#pragma unroll
+  for (int s = 0; s < 4; s++) flush |= (int)((scnt >> (8 * s)) & 0xFF) >= required;
+  flush = flush && sized;
+  bool straight = false;
+  if (sized) {
+    int length = 0;
+    bool skipped = false;
+#pragma unroll 1
+    for (int r = 12; r >= 0 && !straight; r--) {                    // ranks 14 .. 2 (:173-187)
+      if ((rmask >> r) & 1) length++;
+      else if (shortcut && !skipped) skipped = true;
+      else { length = 0; skipped = false; }
+      straight = length >= required;
+    }
+    if (!straight) {                                                // wheel A-2-3-4-5, `skipped` carried over (:190-206)
+      int wheel = 0;
+      bool go = true;
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const int r = k == 0 ? 12 : k - 1;
+        if (go) {
+          if ((rmask >> r) & 1) wheel++;
+          else if (shortcut && !skipped) skipped = true;
+          else go = false;
+        }
+      }
+      straight = wheel >= required;
+    }
+  }
+  if (n5 && flush) return BGYM_HT_FLUSH_FIVE;
+  if (n3 && n2 && flush) return BGYM_HT_FLUSH_HOUSE;
+  if (n5) return BGYM_HT_FIVE_KIND;
+  if (flush && straight) return BGYM_HT_STRAIGHT_FLUSH;
+  if (n4) return BGYM_HT_FOUR_KIND;
+  if (n3 && n2) return BGYM_HT_FULL_HOUSE;
+  if (flush) return BGYM_HT_FLUSH;
+  if (straight) return BGYM_HT_STRAIGHT;
+  if (n3) return BGYM_HT_THREE_KIND;
+  if (n2 == 2 || (n3 == 1 && n2 == 1)) return BGYM_HT_TWO_PAIR;
+  if (n2) return BGYM_HT_ONE_PAIR;
+  return BGYM_HT_HIGH_CARD;
+}
+
 // ScoreEngine.get_hand_chips_mult scoring_engine.py:87-101 (engine level = min(level, 15))
 __device__ __forceinline__ void hand_base(int ht, int level, int& chips, int& mult) {
   int lv = min(max(level, 1), 15) - 1;

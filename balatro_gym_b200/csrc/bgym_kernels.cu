@@ -278,7 +278,20 @@ __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
       if (!(suit == 3 || suit == 0)) all_black = 0;
       kings += rank == 13; queens += rank == 12;
     }
-    int ht = classify(hist);
+    int ht;
+    if (a.flags & BGYM_SCORE_RULES) {      // balatro_sim.py:220-400; Four Fingers / Shortcut are read from the joker slots
+      uint32_t scnt = 0;
+      for (int c = 0; c < nc; c++) scnt += 1u << (8 * (byte_at(cards, c) & 3));
+      bool four_fingers = false, shortcut = false;
+      if (a.jokers8) {
+        const uint2 jw0 = __ldg(reinterpret_cast<const uint2*>(a.jokers8) + i);
+        const uint64_t jr = u64_of(jw0.x, jw0.y);
+        for (int j = 0; j < 8; j++) { const int id = byte_at(jr, j); four_fingers |= id == BGYM_J_FOUR_FINGERS; shortcut |= id == BGYM_J_SHORTCUT; }
+      }
+      ht = classify_rules(hist.cnt, scnt, hist.rmask, nc, four_fingers, shortcut);
+    } else {
+      ht = classify(hist);
+    }
     int lvl = a.levels12 ? a.levels12[i * 12 + ht] : 1;
     int chips, mult;
     hand_base(ht, lvl, chips, mult);
@@ -772,7 +785,7 @@ int bgym_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8_t
   a.money = money; a.seed = seed; a.n = n; a.flags = flags;
   long long blocks = (n + 255) / 256;
   long long cap = (long long)g_sm_count * 16;
-  if (!mods8 && !n_cards && !jokers8 && !levels12 && !ctx)
+  if (!mods8 && !n_cards && !jokers8 && !levels12 && !ctx && !(flags & BGYM_SCORE_RULES))
     score_hands5_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a);
   else
     score_hands_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(a);

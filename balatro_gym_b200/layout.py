@@ -29,7 +29,7 @@ F_BEAT_BLIND, F_FAILED, F_GUARD_TERMINATED, F_PLAYED, F_AUTORESET_DONE, F_SHOP_D
 FLAG_AUTORESET, FLAG_NO_OBS, FLAG_RANDOM_POLICY, FLAG_GEN_C3, FLAG_GEN_CONS = 1, 2, 4, 8, 16
 # state generator of BASELINE configs[2] / configs[3] (include/bgym.h): applied by reset AND by the in-kernel autoreset
 GENERATORS = {None: 0, "c3": FLAG_GEN_C3, "c4": FLAG_GEN_C3 | FLAG_GEN_CONS}
-SCORE_TABLE_NAMES = 1
+SCORE_TABLE_NAMES, SCORE_RULES = 1, 2
 
 
 def _dt(fields, size):

@@ -11,9 +11,12 @@ from . import _lib
 
 
 def score_hands(cards8, mods8=None, n_cards=None, jokers8=None, levels12=None, ctx=None, seed: int = 0,
-                table_names: bool = False, want_x_mult: bool = True, want_money: bool = True, out=None):
+                table_names: bool = False, want_x_mult: bool = True, want_money: bool = True, out=None, rules: bool = False):
     """cards8: uint8 [N,8] card codes; returns dict(hand_type u8, chips i32, mult i32, x_mult f64,
-    score i64, money i32).  `out` may hold preallocated tensors with those keys."""
+    score i64, money i32).  `out` may hold preallocated tensors with those keys.
+    rules=True classifies with the rules evaluator (BalatroSimulator.evaluate_hand, balatro_sim.py:220-400:
+    Five of a Kind / Flush House / Flush Five, Four Fingers and Shortcut read from jokers8) instead of the env's
+    BalatroGame._classify_hand (BGYM_SCORE_RULES)."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     assert cards8.dtype == torch.uint8 and cards8.dim() == 2 and cards8.shape[1] == 8 and cards8.is_contiguous()
@@ -37,6 +40,6 @@ def score_hands(cards8, mods8=None, n_cards=None, jokers8=None, levels12=None, c
         rc = lib.bgym_score_hands(p(cards8), p(mods8), p(n_cards), p(jokers8), p(levels12), p(ctx),
                                   p(out["hand_type"]), p(out["chips"]), p(out["mult"]), p(out.get("x_mult")),
                                   p(out["score"]), p(out.get("money")), seed & 0xFFFFFFFF, n,
-                                  1 if table_names else 0, torch.cuda.current_stream(dev).cuda_stream)
+                                  (1 if table_names else 0) | (2 if rules else 0), torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "bgym_score_hands")
     return out

@@ -133,9 +133,16 @@ enum {
 #define BGYM_GEN_KEY1 0xB200C3C4u
 /* flags argument of bgym_score_hands */
 enum {
-  BGYM_SCORE_TABLE_NAMES = 1 /* hand names as complete_joker_effects.py:64-80 expects ('Pair',
+  BGYM_SCORE_TABLE_NAMES = 1,/* hand names as complete_joker_effects.py:64-80 expects ('Pair',
                                 'Three of a Kind', 'Four of a Kind'); default = the env's own names
                                 ('One Pair', 'Three Kind', 'Four Kind', balatro_env_2.py:674) */
+  BGYM_SCORE_RULES = 2       /* classify with the RULES evaluator, BalatroSimulator.evaluate_hand
+                                (balatro_sim.py:110-400) instead of BalatroGame._classify_hand: FIVE_KIND /
+                                FLUSH_HOUSE / FLUSH_FIVE exist, a rank group counts only at EXACTLY 5/4/3/2 cards,
+                                flushes and straights exist for at most 5 played cards, the Four Fingers joker
+                                (4-card flushes and straights) and the Shortcut joker (one rank gap) are read from
+                                jokers8, and cards8 may repeat a card.  hand_type = the evaluator's 'top' entry;
+                                base chips / mult and the joker pipeline then run on that hand type. */
 };
 
 #define BGYM_E_ARG     (-1)

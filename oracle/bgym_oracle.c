@@ -183,6 +183,66 @@ static int classify_hand(const int* codes, int n) {
   return BGYM_HT_HIGH_CARD;
 }
 
+/* RULES evaluator: BalatroSimulator.evaluate_hand balatro_sim.py:220-400 with get_x_same :110-125,
+ * get_flush :127-148, get_straight :150-214.  Returns the hand type named by results['top']. */
+static int x_same_groups(const int* rank_counts, int num) { /* ranks held by EXACTLY num cards (:118-119) */
+  int groups = 0;
+  for (int r = 2; r <= 14; r++) groups += rank_counts[r] == num;
+  return groups;
+}
+
+static int rules_flush(const int* codes, int n, int four_fingers) {
+  int required = four_fingers ? 4 : 5;
+  if (n > 5 || n < required) return 0;                       /* :133-134 */
+  for (int suit = 0; suit < 4; suit++) {
+    int count = 0;
+    for (int i = 0; i < n; i++) count += code_suit(codes[i]) == suit;
+    if (count >= required) return 1;
+  }
+  return 0;
+}
+
+static int rules_straight(const int* rank_counts, int n, int four_fingers, int shortcut) {
+  int required = four_fingers ? 4 : 5;
+  if (n > 5 || n < required) return 0;                       /* :155-156 */
+  int length = 0, skipped = 0;
+  for (int r = 14; r > 1; r--) {                             /* :173-187 */
+    if (rank_counts[r]) length++;
+    else if (shortcut && !skipped) skipped = 1;
+    else { length = 0; skipped = 0; }
+    if (length >= required) return 1;
+  }
+  static const int WHEEL[5] = {14, 2, 3, 4, 5};              /* :190-206; `skipped` carries over from the scan */
+  int wheel = 0;
+  for (int k = 0; k < 5; k++) {
+    if (rank_counts[WHEEL[k]]) wheel++;
+    else if (shortcut && !skipped) skipped = 1;
+    else break;
+  }
+  return wheel >= required;
+}
+
+static int classify_rules(const int* codes, int n, int four_fingers, int shortcut) {
+  int rank_counts[15] = {0};
+  for (int i = 0; i < n; i++) rank_counts[code_rank(codes[i])]++;
+  int n5 = x_same_groups(rank_counts, 5), n4 = x_same_groups(rank_counts, 4);
+  int n3 = x_same_groups(rank_counts, 3), n2 = x_same_groups(rank_counts, 2);
+  int flush = rules_flush(codes, n, four_fingers);
+  int straight = rules_straight(rank_counts, n, four_fingers, shortcut);
+  if (n5 && flush) return BGYM_HT_FLUSH_FIVE;               /* :255-258, in priority order down to :333 */
+  if (n3 && n2 && flush) return BGYM_HT_FLUSH_HOUSE;
+  if (n5) return BGYM_HT_FIVE_KIND;
+  if (flush && straight) return BGYM_HT_STRAIGHT_FLUSH;
+  if (n4) return BGYM_HT_FOUR_KIND;
+  if (n3 && n2) return BGYM_HT_FULL_HOUSE;
+  if (flush) return BGYM_HT_FLUSH;
+  if (straight) return BGYM_HT_STRAIGHT;
+  if (n3) return BGYM_HT_THREE_KIND;
+  if (n2 == 2 || (n3 == 1 && n2 == 1)) return BGYM_HT_TWO_PAIR;   /* exactly two pairs: three pairs fall through */
+  if (n2) return BGYM_HT_ONE_PAIR;
+  return BGYM_HT_HIGH_CARD;
+}
+
 /* ScoreEngine.get_hand_chips_mult scoring_engine.py:87-101 (engine level is capped at 15,
  * apply_planet :82-85; state.hand_levels is not, balatro_env_2.py:1119) */
 static void hand_chips_mult(const uint8_t* level, int ht, int* chips, int* mult) {
@@ -395,7 +455,13 @@ int oracle_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8
     ScoreIn in;
     memset(&in, 0, sizeof in);
     in.cards = sc; in.n_cards = nc; in.jokers = jk; in.n_jokers = nj;
-    in.hand_type = classify_hand(codes, nc);
+    if (flags & BGYM_SCORE_RULES) {
+      int four_fingers = 0, shortcut = 0;
+      for (int j = 0; j < nj; j++) { four_fingers |= jk[j] == BGYM_J_FOUR_FINGERS; shortcut |= jk[j] == BGYM_J_SHORTCUT; }
+      in.hand_type = classify_rules(codes, nc, four_fingers, shortcut);
+    } else {
+      in.hand_type = classify_hand(codes, nc);
+    }
     in.table_names = (flags & BGYM_SCORE_TABLE_NAMES) != 0;
     in.hands_left = ctx ? ctx[i].hands_left : 4;
     in.discards_left = ctx ? ctx[i].discards_left : 3;

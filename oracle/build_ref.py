@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 DST = os.path.join(HERE, "_ref", "balatro_gym")
 MODULES = ["__init__", "env", "balatro_game", "scoring_engine", "cards", "constants", "shop", "jokers",
            "planets", "consumables", "unified_scoring", "complete_joker_effects", "boss_blinds",
-           "balatro_env_2"]
+           "balatro_env_2", "balatro_sim"]
 
 
 def main():

@@ -96,6 +96,24 @@ def load_reference():
     return ns
 
 
+_rules = None
+
+
+def load_rules_evaluator():
+    """The UNMODIFIED rules evaluator, `balatro_gym/balatro_sim.py::BalatroSimulator` (its `evaluate_hand`,
+    :220-400, pins BGYM_SCORE_RULES).  The module imports `scoring_engine` as a top-level name (:6), so the
+    package directory itself goes on sys.path as well."""
+    global _rules
+    if _rules is None:
+        R = load_reference()
+        pkg = os.path.join(R.root, "balatro_gym")      # a directory, or a path inside the zip archive (zipimport takes both)
+        if pkg not in sys.path:
+            sys.path.append(pkg)
+        import importlib
+        _rules = importlib.import_module("balatro_gym.balatro_sim")
+    return _rules
+
+
 # ---------------------------------------------------------------------------------------------
 # RNG tap
 # ---------------------------------------------------------------------------------------------

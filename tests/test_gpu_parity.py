@@ -606,3 +606,56 @@ def test_native_draw_distributions(torch):
     assert int(cont.sum()) > 2000
     bits = float(sum(((fd >> i) & 1).sum() for i in range(8))); trials = float(hn.sum())
     assert abs(bits / trials - 1 / 7) < 5 * ((1 / 7) * (6 / 7) / trials) ** 0.5, bits / trials
+
+
+class HostHandleStepper:
+    """The golden traces through the HOST-buffer entry points (bgym_vec_* with host pointers, draws included): what a
+    non-torch caller binds."""
+
+    def __init__(self, E):
+        import ctypes as C
+        from balatro_gym_b200 import _lib
+        self.lib, self._lib, self.E = _lib.load(), _lib, E
+        self.h = C.c_void_p()
+        _lib.check(self.lib.bgym_vec_create(C.byref(self.h), E, 0), "create")
+        self.obs = np.zeros(E, L.OBS_DTYPE); self.reward = np.zeros(E); self.term = np.zeros(E, np.uint8)
+        self.trunc = np.zeros(E, np.uint8); self.info = np.zeros(E, L.INFO_DTYPE); self.state = np.zeros(E, L.STATE_DTYPE)
+
+    def reset(self, seeds, decks):
+        s = np.ascontiguousarray(seeds % (2 ** 32), dtype=np.uint32)
+        d = np.ascontiguousarray(decks, dtype=np.uint8)
+        self._lib.check(self.lib.bgym_vec_reset_host(self.h, s.ctypes.data, d.ctypes.data, self.obs.ctypes.data), "reset_host")
+
+    def set_state(self, init_state):
+        self._lib.check(self.lib.bgym_vec_get_state(self.h, self.state.ctypes.data), "get_state")
+        new = init_state.copy()
+        for k in STATE_SKIP:
+            new[k] = self.state[k]
+        self._lib.check(self.lib.bgym_vec_set_state(self.h, new.ctypes.data), "set_state")
+
+    def step(self, actions, draws):
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        d = np.ascontiguousarray(draws)
+        self._lib.check(self.lib.bgym_vec_step_host(self.h, a.ctypes.data, d.ctypes.data, self.obs.ctypes.data, self.reward.ctypes.data,
+                                                    self.term.ctypes.data, self.trunc.ctypes.data, self.info.ctypes.data, 0), "step_host")
+        self._lib.check(self.lib.bgym_vec_get_state(self.h, self.state.ctypes.data), "get_state")
+        return self.state, self.obs, self.reward, self.term, self.info
+
+    def close(self):
+        self.lib.bgym_vec_destroy(self.h)
+
+
+@pytest.mark.parametrize("name", ["c4", "c4x"])
+def test_host_handle_replays_reference_trace_with_draws(torch, name):
+    """Whole reference episodes — boss blinds, shops, rerolls, consumables — through bgym_vec_step_host with the
+    reference's recorded draws passed as HOST BgymDraws records."""
+    from test_oracle_golden import replay
+    tr = load_trace(name)
+    st = HostHandleStepper(tr["action"].shape[1])
+    try:
+        n = replay(tr, st)
+    finally:
+        st.close()
+    assert n == int(tr["length"].sum())
+    # the trace really goes through the shop and boss blinds
+    assert (tr["state"]["phase"] == L.PHASE_SHOP).any() and (tr["state"]["boss_type"] != 0).any()
