@@ -29,6 +29,17 @@ class BgymError(RuntimeError):
     pass
 
 
+def source_hash() -> str:
+    """sha256 over the kernel sources and headers the library is built from: ties measured artefacts (the ncu DRAM
+    traffic bench.py reports, profiles/*_traffic.json) to the code they were measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in SOURCES + HEADERS:
+        h.update(os.path.basename(p).encode())
+        h.update(open(p, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def needs_build() -> bool:
     if not os.path.exists(SO_PATH):
         return True

@@ -34,6 +34,30 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
 
+def measured_traffic(kind):
+    """DRAM bytes per launch set from the committed ncu capture (profiles/r02_traffic.json, written by
+    tools/ncu_summary.py --traffic-json), or (None, why) when the capture was taken on other kernel sources than the
+    ones this run executes: a stale figure is not reported."""
+    path = os.path.join(REPO, "profiles", "r02_traffic.json")
+    try:
+        d = json.load(open(path))
+        from balatro_gym_b200 import _lib
+        prov = {"file": "profiles/r02_traffic.json", "git_head": d["git_head"], "source_hash": d["source_hash"]}
+        if d["source_hash"] != _lib.source_hash():
+            sys.stderr.write(f"bench.py: {path} was captured on other kernel sources (hash {d['source_hash']} != "
+                             f"{_lib.source_hash()}): roofline.traffic is not reported; re-run tools/gpu_prof_part.sh + "
+                             "tools/ncu_summary.py --traffic-json\n")
+            prov["stale"] = True
+            return None, None, prov
+        if kind == "step":
+            prov["kernels"] = d["step"]["kernels"]
+            return d["step"]["traffic_bytes"], d["envs"], prov
+        prov["kernels"] = [d["hands5"]["launch"]["kernel"]]
+        return d["hands5"]["traffic_bytes"], d["hands"], prov
+    except Exception as e:      # no capture committed
+        return None, None, {"file": "profiles/r02_traffic.json", "unavailable": repr(e)}
+
+
 def measured_peak():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -44,6 +68,44 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def bind_host_memory_near_gpu(torch, dev):
+    """Best effort: run this rank and place its future host allocations (the pinned staging buffers) on the NUMA node
+    the GPU hangs off.  With eight ranks on one box, pinned buffers that all land on one socket send half of the result
+    copies across the inter-socket link (SCALE_r01: e2e efficiency 0.24 at 8 GPUs).  Returns what was done."""
+    out = {"gpu_numa_node": None, "cpu_affinity": None, "mempolicy": None}
+    try:
+        bus = torch.cuda.get_device_properties(dev).pci_bus_id if hasattr(torch.cuda.get_device_properties(dev), "pci_bus_id") else None
+        if bus is None:
+            import subprocess as sp
+            q = sp.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(dev.index or 0)],
+                       capture_output=True, text=True).stdout.strip()
+            bus = q[-12:].lower() if q else None            # 00000000:1B:00.0 -> 0000:1b:00.0
+        else:
+            bus = f"0000:{bus:02x}:00.0" if isinstance(bus, int) else str(bus).lower()
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read())
+        out["gpu_numa_node"] = node
+        if node < 0:
+            return out
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            out["cpu_affinity"] = f"{len(allowed)} cpus of node {node}"
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED = 1
+        rc = libc.syscall(238, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))     # set_mempolicy (x86-64)
+        out["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy failed (errno %d)" % ctypes.get_errno()
+    except Exception as e:
+        out["error"] = repr(e)
+    return out
 
 
 class ClockSampler:
@@ -287,33 +349,58 @@ def run_ours(args):
     stats = bdist.allreduce_stats(env.stats.clone())
 
     # ---- e2e: the public API with HOST buffers (pinned), copies inside the timed region ----
+    # Every step: this step's actions come from pinned host memory (H2D), the step's results — observation records,
+    # rewards, terminations — go to pinned host memory (D2H).  The result copies of step t run on a second stream from
+    # a device-side snapshot while step t+1 is launched (double-buffered on both sides); the action path is synchronous.
+    # The timed region ends when the last step's results are in host memory.
     Ke = max(3, min(K, args.e2e_steps))
+    numa = bind_host_memory_near_gpu(torch, dev)
     h_act = torch.empty(n, dtype=torch.int32, pin_memory=True)
-    h_obs = torch.empty((n, L.OBS_BYTES), dtype=torch.uint8, pin_memory=True)
-    h_rew = torch.empty(n, dtype=torch.float64, pin_memory=True)
-    h_term = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     d_act = torch.empty(n, dtype=torch.int32, device=dev)
+    h_res = [{"obs": torch.empty((n, L.OBS_BYTES), dtype=torch.uint8, pin_memory=True),
+              "rew": torch.empty(n, dtype=torch.float64, pin_memory=True),
+              "term": torch.empty(n, dtype=torch.uint8, pin_memory=True)} for _ in range(2)]
+    d_snap = [{"obs": torch.empty_like(env.obs_buf), "rew": torch.empty_like(env.reward), "term": torch.empty_like(env.terminated)}
+              for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    snap_ready = [torch.cuda.Event() for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    main_stream = torch.cuda.current_stream(dev)
 
-    def e2e_step():
+    def e2e_step(t):
+        b2 = t & 1
         env.sample_actions(seed=7)                       # the agent's decision, made on the device
         h_act.copy_(env.actions, non_blocking=True)      # ... and handed to the host, as a host-driven loop has it
-        torch.cuda.current_stream(dev).synchronize()
+        main_stream.synchronize()
         d_act.copy_(h_act, non_blocking=True)            # H2D of this step's inputs from pinned memory
         env.step(d_act, want_info=False)
-        h_obs.copy_(env.obs_buf, non_blocking=True)      # D2H of the step's results
-        h_rew.copy_(env.reward, non_blocking=True)
-        h_term.copy_(env.terminated, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        main_stream.wait_event(copied[b2])               # the snapshot buffer's previous contents have left the device
+        d_snap[b2]["obs"].copy_(env.obs_buf, non_blocking=True)
+        d_snap[b2]["rew"].copy_(env.reward, non_blocking=True)
+        d_snap[b2]["term"].copy_(env.terminated, non_blocking=True)
+        snap_ready[b2].record(main_stream)
+        with torch.cuda.stream(copy_stream):             # D2H of the step's results, overlapping the next step
+            copy_stream.wait_event(snap_ready[b2])
+            for k in ("obs", "rew", "term"):
+                h_res[b2][k].copy_(d_snap[b2][k], non_blocking=True)
+            copied[b2].record(copy_stream)
 
-    for _ in range(2):
-        e2e_step()
+    for t in range(2):
+        e2e_step(t)
+    torch.cuda.synchronize(dev)
     bdist.barrier()
     t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
+    for t in range(Ke):
+        e2e_step(t)
+    copy_stream.synchronize()
+    main_stream.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_rank_gbs = (L.OBS_BYTES + 8 + 1 + 4 + 4) * n * Ke / e2e_s / 1e9     # this rank's PCIe traffic, both directions
     e2e_s = bdist.max_over_ranks(e2e_s, dev)
     e2e_value = ws * n * Ke / e2e_s
+    # the host copy of the last step equals the device buffers
+    last = (Ke - 1) & 1
+    assert torch.equal(h_res[last]["obs"], env.obs_buf.cpu()) and torch.equal(h_res[last]["term"], env.terminated.cpu())
 
     # ---- hands microbench (configs[1]) ----
     hands = None
@@ -327,6 +414,9 @@ def run_ours(args):
 
     if rank != 0:
         return 0
+    tbytes, tenvs, traffic_prov = measured_traffic("step")
+    traffic = None if tbytes is None else tbytes * n / float(tenvs)
+    frac_physical = None if traffic is None else traffic / (step_kernel_ms_max / 1000.0) / 1e9 / peak
     host_facing = None if args.no_facade else bench_host_facing()
     cpu_base = None
     if not args.no_cpu_baseline and ws == 1:
@@ -336,13 +426,13 @@ def run_ours(args):
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64+f64", "data": "synthetic", "config": workload_config(args, n),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of the four launches of one step at
-                     # 2^20 envs, from the committed ncu --set full capture (profiles/r01_ncu_summary_final.md):
-                     # main 160+179 MB, PLAY 54+17, OTHER 38+5, DISCARD 31+1 -> 485 MB = 462 B per env-step
-                     "traffic": 485e6 * n / float(1 << 20), "traffic_unit": "bytes per step launch set (ncu, profiles/)",
-                     "kernel": "one env-step = env_step_main_kernel + 3 concurrent env_step_gather_kernel passes (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
+                     "frac_note": "frac = ALGORITHMIC bytes (872 B per env-step, SURVEY 8d) / kernel_ms / peak; frac_physical = DRAM "
+                                  "bytes the launches really move (ncu) / kernel_ms / peak",
+                     "traffic": traffic, "frac_physical": frac_physical, "traffic_provenance": traffic_prov,
+                     "traffic_unit": "dram__bytes_read.sum + dram__bytes_write.sum over the launches of one env-step (ncu --set full)",
+                     "kernel": "one env-step = env_step_main_kernel + 9 env_step_list_kernel launches (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
                      "units_per_launch": n, "kernel_ms": step_kernel_ms_max, "peak_source": peak_src,
-                     "physical_bytes_per_unit": "main pass 144 (hot read) + 16 (the chunk a toggle changes) + 176 (obs) + 14 = 350 B per env; gather passes add (144+176)*2+176 B for the ~17 % deferred envs"},
+                     "physical_bytes_per_unit": "main pass 144 (hot read) + 16 (the chunk a toggle changes) + 176 (obs) + 14 = 350 B per env; list kernels add the hot / cold / obs records of the ~25 % deferred envs at 64-byte DRAM granularity"},
         "timed_window": {"start": window_start, "end": window_end, "action_mix": action_mix, "phase_mix": phase_mix,
                          "note": "state statistics computed on the device from the env records right before / after the timed "
                                  "steps; action and phase mix are exact over all envs x steps of the timed window (rank 0 slab)"},
@@ -351,7 +441,8 @@ def run_ours(args):
                                       "14 % generator state in its timed window (VERDICT r01 weak #1)"},
         "cpu_baseline": cpu_base,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (L.OBS_BYTES + 8 + 1 + 4) * n,
-                "steps": Ke},
+                "steps": Ke, "pcie_gbs_rank0": e2e_rank_gbs, "host_memory": numa,
+                "note": "bound by the PCIe link: 189 B of results per env-step leave the device; result copies overlap the next step"},
         "gpu_launches": launches,
         "clocks": clk,
         "fused_rollout": {"value": fused_value, "unit": UNIT, "ms_per_step": fused_ms / K,
@@ -440,6 +531,8 @@ def bench_hands(torch, b, dev, peak, args):
     ms = e0.elapsed_time(e1) / reps
     value = n / (ms / 1000.0)
     ach = n * B_HAND / (ms / 1000.0) / 1e9
+    hb, hn, hprov = measured_traffic("hands5")
+    htraffic = None if hb is None else hb * n / float(hn)
     # e2e: host cards in pinned memory -> device -> scores back
     h_cards = torch.empty((n, 8), dtype=torch.uint8, pin_memory=True); h_cards.copy_(cards)
     h_score = torch.empty(n, dtype=torch.int64, pin_memory=True)
@@ -455,8 +548,10 @@ def bench_hands(torch, b, dev, peak, args):
     res = {"metric": "hands_scored_per_sec", "value": value, "unit": "hands/s", "n_hands": n, "ms_per_launch": ms,
            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                         "bytes_per_unit": B_HAND, "kernel": "score_hands5_kernel",
-                        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^24 hands (ncu, profiles/): 134 + 233 MB
-                        "traffic": 367.5e6 * n / float(1 << 24)},
+                        "traffic": htraffic, "frac_physical": None if htraffic is None else htraffic / (ms / 1000.0) / 1e9 / peak,
+                        "traffic_provenance": hprov,
+                        "note": "the kernel reads 8 B and writes 17 B per hand: it is bound by instruction issue (ncu: sm throughput 77 %, "
+                                "issue slots 62 %), not by HBM; frac uses the canonical 32 B per hand"},
            "e2e": {"value": e2e, "unit": "hands/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * n}}
     res["with_jokers"] = bench_hands_jokers(torch, dev, peak)
     if not args.no_cpu_baseline:

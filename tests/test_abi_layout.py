@@ -116,3 +116,17 @@ def test_plain_c_caller_compiles_and_links():
                                "-Wl,-rpath," + os.path.dirname(_lib.SO_PATH)])
         rc = subprocess.call([exe, "16", "2"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         assert rc in (0, 2)     # 2 = "no CUDA device" (this container); 0 on a GPU box
+
+
+def test_committed_ncu_traffic_matches_the_kernel_sources():
+    """profiles/r02_traffic.json (the DRAM traffic bench.py reports in roofline.traffic) must have been captured on the
+    kernel sources in the tree: a kernel edit without a fresh `ncu` capture fails here, loudly, instead of leaving a
+    stale constant in the bench line."""
+    import json
+    import os
+    from balatro_gym_b200 import _lib
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_traffic.json")
+    d = json.load(open(path))
+    assert d["source_hash"] == _lib.source_hash(), \
+        "kernel sources changed since the ncu capture: run tools/gpu_prof_part.sh on the GPU box, then tools/ncu_summary.py --traffic-json"
+    assert d["step"]["traffic_bytes"] > 0 and len(d["step"]["kernels"]) == 10
