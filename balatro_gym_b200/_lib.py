@@ -95,6 +95,7 @@ SYMBOLS = {
     "bgym_score_hands": (_i32, [_vp] * 12 + [_u32, _i64, _i32, _vp]),
     "bgym_episode_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "bgym_featurize": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "bgym_policy_first_layer": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "bgym_masked_sample": (_i32, [_vp, _i32, _vp, _vp, _u32, _u64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "bgym_gae": (_i32, [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _i64, _i64, _vp]),
     "bgym_vec_create": (_i32, [C.POINTER(_vp), _i64, _i32]),

@@ -518,6 +518,7 @@ static int ensure_device_setup() {
   e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);             \
   if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(" #kernel ")");
   BGYM_SET_SMEM(env_reset_kernel, RESET_CTA_SMEM)
+  BGYM_SET_SMEM(policy_first_layer_kernel, FL_SMEM)
   BGYM_SET_SMEM(env_step_main_kernel<1>, MainCfg<1>::cta_smem)
   BGYM_SET_SMEM(env_step_main_kernel<2>, MainCfg<2>::cta_smem)
 #undef BGYM_SET_SMEM
@@ -820,6 +821,22 @@ int bgym_featurize(const BgymObs* obs, void* features, int64_t n, int dtype, voi
   else
     featurize_kernel<__nv_bfloat16><<<grid, ft, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<__nv_bfloat16*>(features), n);
   return cuda_rc(cudaGetLastError(), "bgym_featurize launch");
+}
+
+int bgym_policy_first_layer(const BgymObs* obs, const void* wt_hand, const void* wt_joker, const void* wt_game,
+                            const float* bias, void* out, int64_t n, void* stream) {
+  if (n < 0 || !obs || !wt_hand || !wt_joker || !wt_game || !bias || !out) return set_err(BGYM_E_ARG, "bgym_policy_first_layer: bad arguments");
+  if (misaligned(obs, 16) || misaligned(wt_hand, 16) || misaligned(wt_joker, 16) || misaligned(wt_game, 16) || misaligned(out, 16))
+    return set_err(BGYM_E_ALIGN, "bgym_policy_first_layer: obs / weights / out must be 16-byte aligned");
+  if (n == 0) return 0;
+  int rc = ensure_device_setup();
+  if (rc) return rc;
+  long long ctas = (n + FL_WARPS - 1) / FL_WARPS;
+  if (ctas > g_sm_count) ctas = g_sm_count;                  // persistent: one CTA per SM holds the weights in shared memory
+  policy_first_layer_kernel<<<(int)ctas, FL_WARPS * 32, FL_SMEM, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<const __nv_bfloat16*>(wt_hand), reinterpret_cast<const __nv_bfloat16*>(wt_joker),
+      reinterpret_cast<const __nv_bfloat16*>(wt_game), bias, reinterpret_cast<__nv_bfloat16*>(out), n);
+  return cuda_rc(cudaGetLastError(), "bgym_policy_first_layer launch");
 }
 
 int bgym_masked_sample(const void* logits, int dtype, const BgymObs* obs, const float* uniforms,

@@ -90,6 +90,97 @@ __global__ void __launch_bounds__(FEAT_ENVS_PER_CTA * FEAT_CHUNKS) featurize_ker
 }
 
 // ------------------------------------------------------------------------------------------------
+// policy_first_layer_kernel: the FIRST Linear + ReLU of the extractor's three sub-nets (train_balatro_agent.py:52-69:
+// hand_net[0] 416 -> 256, joker_net[0] 10 -> 128, game_state_net[0] 21 -> 64) computed straight from the observation
+// records.  The hand block of the input is an 8-hot vector (:86-93), so hand_net[0] is a SUM OF EIGHT ROWS of the
+// transposed weight, one per hand slot; featurize_kernel + a 416-wide GEMM wrote and re-read 896 B of mostly zeros
+// per env for it.  One persistent CTA per SM keeps all three transposed weight matrices in shared memory (213 KB of
+// bf16 + 5 KB + biases); a warp serves one env at a time: lane l owns outputs [8l, 8l+8) of the hand block (eight
+// conflict-free LDS.128), [4l, 4l+4) of the joker block, [2l, 2l+2) of the game block; fp32 accumulation, bf16 out
+// (the operands are the bf16 values the GEMM path multiplies: one-hot ones, joker ids, bf16-rounded game scalars).
+// ------------------------------------------------------------------------------------------------
+constexpr int FL_HAND = 256, FL_JOKER = 128, FL_GAME = 64, FL_OUT = FL_HAND + FL_JOKER + FL_GAME;   // 448
+constexpr int FL_WARPS = 8;
+constexpr int FL_SMEM = (416 * FL_HAND + 10 * FL_JOKER + 21 * FL_GAME) * 2 + FL_OUT * 4;           // 220 032 B
+
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ void bf16x2_add(float& a0, float& a1, uint32_t w, float scale) {
+  a0 += scale * __uint_as_float(w << 16);
+  a1 += scale * __uint_as_float(w & 0xFFFF0000u);
+}
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+__global__ void __launch_bounds__(FL_WARPS * 32, 1) policy_first_layer_kernel(const uint8_t* __restrict__ obs,
+    const __nv_bfloat16* __restrict__ wt_hand, const __nv_bfloat16* __restrict__ wt_joker, const __nv_bfloat16* __restrict__ wt_game,
+    const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, long long n) {
+  extern __shared__ __align__(16) uint8_t fl_smem[];
+  uint8_t* s_hand = fl_smem;                                   // [416][256] bf16
+  uint8_t* s_joker = s_hand + 416 * FL_HAND * 2;                // [10][128]
+  uint8_t* s_game = s_joker + 10 * FL_JOKER * 2;                // [21][64]
+  float* s_bias = reinterpret_cast<float*>(s_game + 21 * FL_GAME * 2);   // [448]
+  for (int i = threadIdx.x; i < 416 * FL_HAND * 2 / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_hand)[i] = __ldg(reinterpret_cast<const uint4*>(wt_hand) + i);
+  for (int i = threadIdx.x; i < 10 * FL_JOKER * 2 / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_joker)[i] = __ldg(reinterpret_cast<const uint4*>(wt_joker) + i);
+  for (int i = threadIdx.x; i < 21 * FL_GAME * 2 / 16; i += blockDim.x) reinterpret_cast<uint4*>(s_game)[i] = __ldg(reinterpret_cast<const uint4*>(wt_game) + i);
+  for (int i = threadIdx.x; i < FL_OUT; i += blockDim.x) s_bias[i] = bias[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long env = (long long)blockIdx.x * FL_WARPS + warp; env < n; env += (long long)gridDim.x * FL_WARPS) {
+    const uint8_t* o = obs + env * BGYM_OBS_BYTES;
+    // ---- hand block: bias + one weight row per occupied hand slot ----
+    float h[8];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(s_bias + 8 * lane), b1 = *reinterpret_cast<const float4*>(s_bias + 8 * lane + 4);
+      h[0] = b0.x; h[1] = b0.y; h[2] = b0.z; h[3] = b0.w; h[4] = b1.x; h[5] = b1.y; h[6] = b1.z; h[7] = b1.w;
+    }
+    const unsigned long long hand = __ldg(reinterpret_cast<const unsigned long long*>(o));     // 8 x int8, -1 = empty
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int c = (int)(int8_t)(hand >> (8 * i));
+      if (c >= 0 && c < 52) {            // warp-uniform: every lane looks at the same env
+        const uint4 w = lds128(s_hand + ((i * 52 + c) * FL_HAND + 8 * lane) * 2);
+        bf16x2_add(h[0], h[1], w.x, 1.0f); bf16x2_add(h[2], h[3], w.y, 1.0f);
+        bf16x2_add(h[4], h[5], w.z, 1.0f); bf16x2_add(h[6], h[7], w.w, 1.0f);
+      }
+    }
+    // ---- joker block: joker_ids[k] as a float times row k ----
+    float j[4];
+    {
+      const float4 b = *reinterpret_cast<const float4*>(s_bias + FL_HAND + 4 * lane);
+      j[0] = b.x; j[1] = b.y; j[2] = b.z; j[3] = b.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+      const float id = i16f(o, 64 + 2 * k);
+      if (id != 0.0f) {
+        const uint2 w = *reinterpret_cast<const uint2*>(s_joker + (k * FL_JOKER + 4 * lane) * 2);
+        bf16x2_add(j[0], j[1], w.x, id); bf16x2_add(j[2], j[3], w.y, id);
+      }
+    }
+    // ---- game block: the 21 scaled scalars (feature_scalars) times their rows ----
+    float g0 = s_bias[FL_HAND + FL_JOKER + 2 * lane], g1 = s_bias[FL_HAND + FL_JOKER + 2 * lane + 1];
+    float v1[8], v2[8], v3[8];
+    feature_scalars(o, 1, v1); feature_scalars(o, 2, v2); feature_scalars(o, 3, v3);
+#pragma unroll
+    for (int k = 0; k < 21; k++) {
+      const float f = bf16_round(k < 6 ? v1[2 + k] : (k < 14 ? v2[k - 6] : v3[k - 14]));
+      const uint32_t w = *reinterpret_cast<const uint32_t*>(s_game + (k * FL_GAME + 2 * lane) * 2);
+      bf16x2_add(g0, g1, w, f);
+    }
+    // ---- ReLU, bf16, coalesced stores: [hand 256 | joker 128 | game 64] ----
+    __nv_bfloat16* row = out + env * FL_OUT;
+    uint4 q;
+    q.x = relu_pack_bf16x2(h[0], h[1]); q.y = relu_pack_bf16x2(h[2], h[3]);
+    q.z = relu_pack_bf16x2(h[4], h[5]); q.w = relu_pack_bf16x2(h[6], h[7]);
+    reinterpret_cast<uint4*>(row)[lane] = q;
+    reinterpret_cast<uint2*>(row + FL_HAND)[lane] = make_uint2(relu_pack_bf16x2(j[0], j[1]), relu_pack_bf16x2(j[2], j[3]));
+    reinterpret_cast<uint32_t*>(row + FL_HAND + FL_JOKER)[lane] = relu_pack_bf16x2(g0, g1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // masked categorical: one thread per env, the 60 logits of its row in registers (15 x 16-byte loads; the
 // two halves of every 32-byte sector are consumed by consecutive loads, so L1 absorbs the 240-byte row
 // stride).  Three passes over registers: max, sum of exp (+ entropy numerator), inverse-CDF scan.

@@ -43,6 +43,27 @@ def featurize(obs_records, out=None, dtype=None):
     return out
 
 
+def policy_first_layer(obs_records, wt_hand, wt_joker, wt_game, bias, out=None):
+    """[n, 176] observation records -> [n, 448] bf16 = relu of the first Linear of hand_net / joker_net /
+    game_state_net (bgym_policy_first_layer): the hand block is a sum of eight weight rows, no one-hot is built.
+    wt_* are the TRANSPOSED bf16 weights ([in, out], contiguous), bias the three biases back to back (fp32 [448])."""
+    torch = _torch()
+    lib = _lib.load()
+    n = obs_records.shape[0]
+    assert obs_records.dtype == torch.uint8 and obs_records.shape[1] == L.OBS_BYTES and obs_records.is_contiguous()
+    assert wt_hand.shape == (416, 256) and wt_joker.shape == (10, 128) and wt_game.shape == (21, 64) and bias.shape == (448,)
+    for w in (wt_hand, wt_joker, wt_game):
+        assert w.dtype == torch.bfloat16 and w.is_contiguous()
+    assert bias.dtype == torch.float32 and bias.is_contiguous()
+    if out is None:
+        out = torch.empty((n, 448), dtype=torch.bfloat16, device=obs_records.device)
+    with torch.cuda.device(obs_records.device):
+        rc = lib.bgym_policy_first_layer(obs_records.data_ptr(), wt_hand.data_ptr(), wt_joker.data_ptr(), wt_game.data_ptr(),
+                                         bias.data_ptr(), out.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "bgym_policy_first_layer")
+    return out
+
+
 def masked_sample(logits, obs_records, seed: int = 0, step: int = 0, env_offset: int = 0, uniforms=None,
                   actions=None, logp=None, entropy=None):
     """Sample one legal action per env from softmax(logits | legal) (bgym_masked_sample).
@@ -158,7 +179,12 @@ class RolloutCollector:
         `collect` does it on entry)."""
         torch = self.torch
         with torch.no_grad():
-            self._w16 = {k: v.detach().to(torch.bfloat16).contiguous() for k, v in self.policy.state_dict().items()}
+            sd = self.policy.state_dict()
+            self._w16 = {k: v.detach().to(torch.bfloat16).contiguous() for k, v in sd.items()}
+            # first layer of the three sub-nets: transposed weights for the row-sum kernel
+            self._first = (self._w16["hand_net.0.weight"].t().contiguous(), self._w16["joker_net.0.weight"].t().contiguous(),
+                           self._w16["game_state_net.0.weight"].t().contiguous(),
+                           torch.cat([sd["hand_net.0.bias"], sd["joker_net.0.bias"], sd["game_state_net.0.bias"]]).detach().float().contiguous())
 
     def _mlp(self, x, prefix, n_layers, last_plain=False, act="relu"):
         """Sequential of Linear(+activation) from the cached bf16 weights; ReLU layers use the cuBLASLt
@@ -176,18 +202,26 @@ class RolloutCollector:
                 x = torch.tanh_(torch.addmm(b, x, W.t()))
         return x
 
+    def _mlp_from(self, x, prefix, first, n_layers):
+        """layers first..n_layers-1 of a ReLU Sequential (the first one was done by policy_first_layer)"""
+        torch = self.torch
+        for li in range(first, n_layers):
+            W, b = self._w16[f"{prefix}.{2 * li}.weight"], self._w16[f"{prefix}.{2 * li}.bias"]
+            x = torch._addmm_activation(b, x, W.t(), use_gelu=False)
+        return x
+
     def _forward(self, obs_records):
         torch = self.torch
-        featurize(obs_records, out=self._feats)
         if not self.autocast:
+            featurize(obs_records, out=self._feats)
             logits, value = self.policy(self._feats)
             return logits.float().contiguous(), value.float()
-        f = self._feats
-        # the column slices are strided views: cuBLAS takes them as they are for the hand block (lda = 448);
-        # the two narrow blocks are copied (10 and 21 columns: their row pitch is not 16-byte aligned)
-        h = self._mlp(f[:, :416], "hand_net", 2)
-        j = self._mlp(f[:, 416:426].contiguous(), "joker_net", 2)
-        g = self._mlp(f[:, 426:447].contiguous(), "game_state_net", 2)
+        # first Linear + ReLU of the three sub-nets straight from the records (no one-hot feature matrix), then their
+        # second layers on strided column views of that activation (lda = 448)
+        a = policy_first_layer(obs_records, *self._first, out=self._feats)
+        h = self._mlp_from(a[:, :256], "hand_net", 1, 2)
+        j = self._mlp_from(a[:, 256:384], "joker_net", 1, 2)
+        g = self._mlp_from(a[:, 384:448], "game_state_net", 1, 2)
         z = self._mlp(torch.cat([h, j, g], dim=1), "combined_net", 2)
         logits = self._mlp(z, "pi", 3, last_plain=True, act="tanh")
         value = self._mlp(z, "vf", 3, last_plain=True, act="tanh").squeeze(-1)

@@ -372,6 +372,15 @@ int bgym_sample_actions_ctr(const BgymObs* obs, int32_t* actions, uint32_t seed,
  * features: n x BGYM_FEATURE_DIM of dtype BGYM_DT_F32 or BGYM_DT_BF16, 16-byte aligned. */
 int bgym_featurize(const BgymObs* obs, void* features, int64_t n, int dtype, void* stream);
 
+/* First Linear + ReLU of the reference extractor's three sub-nets (train_balatro_agent.py:52-69: hand_net[0] 416 -> 256,
+ * joker_net[0] 10 -> 128, game_state_net[0] 21 -> 64), computed straight from the observation records: the 8-hot hand
+ * block makes hand_net[0] a sum of eight rows of its weight, so the 448-column feature matrix of bgym_featurize is never
+ * materialised.  Weights are given TRANSPOSED ([in][out], bf16, 16-byte aligned): wt_hand [416][256], wt_joker [10][128],
+ * wt_game [21][64]; bias = the three bias vectors back to back (448 floats).  out: n x 448 bf16 =
+ * relu([hand 256 | joker 128 | game 64]), the inputs of hand_net[2] / joker_net[2] / game_state_net[2]. */
+int bgym_policy_first_layer(const BgymObs* obs, const void* wt_hand, const void* wt_joker, const void* wt_game,
+                            const float* bias, void* out, int64_t n, void* stream);
+
 /* Masked categorical policy head: for each env, softmax over logits[60] restricted to the legal
  * actions of obs[i].action_mask_bits; draws one action by inverse CDF, returns its log-probability
  * and the entropy of the masked distribution (entropy may be NULL).  The uniform comes from

@@ -65,6 +65,28 @@ def test_featurize_matches_the_extractor_preprocessing(torch, mixed_obs):
     assert len(torch.unique(v.obs["phase"])) >= 3                # the slab really is spread over phases
 
 
+def test_policy_first_layer_matches_torch(torch, mixed_obs):
+    """bgym_policy_first_layer (sum of eight weight rows for the 8-hot hand block, no feature matrix) against the plain
+    torch statement: relu(Linear(features)) of the three sub-nets' first layers, fp32 reference on the bf16-rounded
+    operands the kernel uses.  Tolerance: fp32 accumulation in another order + one bf16 rounding of the output."""
+    from balatro_gym_b200.rollout import policy_first_layer, make_policy
+    v = mixed_obs
+    pol = make_policy(seed=3)
+    sd = pol.state_dict()
+    bf = lambda t: t.detach().to(torch.bfloat16)
+    wt = (bf(sd["hand_net.0.weight"]).t().contiguous(), bf(sd["joker_net.0.weight"]).t().contiguous(), bf(sd["game_state_net.0.weight"]).t().contiguous())
+    bias = torch.cat([sd["hand_net.0.bias"], sd["joker_net.0.bias"], sd["game_state_net.0.bias"]]).float().contiguous()
+    out = policy_first_layer(v.obs_buf, *wt, bias)
+    feats = reference_features(torch, v.obs).to(torch.bfloat16).float()            # the operands of the bf16 GEMM path
+    ref = torch.cat([torch.relu(feats[:, :416] @ wt[0].float() + bias[:256]),
+                     torch.relu(feats[:, 416:426] @ wt[1].float() + bias[256:384]),
+                     torch.relu(feats[:, 426:447] @ wt[2].float() + bias[384:448])], dim=1)
+    assert out.shape == (v.num_envs, 448) and out.dtype == torch.bfloat16
+    err = (out.float() - ref).abs()
+    assert float((err - 2 ** -8 * ref.abs()).max()) < 1e-3, float(err.max())       # bf16 output rounding + reordering
+    assert float(ref.abs().max()) > 1.0                                              # the joker block is not tiny: ids up to 150
+
+
 @pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
 def test_masked_sample_matches_torch(torch, mixed_obs, dtype):
     from balatro_gym_b200.rollout import masked_sample, legal_mask
