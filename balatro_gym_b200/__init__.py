@@ -2,6 +2,7 @@
 cassiusfive/balatro-gym).  Public surface:
 
     BalatroVecEnv      vector-env entry point (device-resident state, sm_100a kernels)
+    HostMirror         pinned-host copy of a BalatroVecEnv's step results, kept current by observation deltas
     BalatroEnv         Gymnasium facade over one env; make("BalatroGym-v0")
     score_hands        batched hand scoring microkernel
     BalatroSB3VecEnv   Stable-Baselines3 VecEnv protocol over the device env (sb3_vec_env.py)
@@ -11,14 +12,14 @@ cassiusfive/balatro-gym).  Public surface:
 from . import layout
 from ._lib import build, load, BgymError, SO_PATH
 
-__all__ = ["BalatroVecEnv", "BalatroEnv", "BalatroSB3VecEnv", "make_sb3_vec_env", "make", "make_balatro_env", "score_hands", "build", "load",
+__all__ = ["BalatroVecEnv", "HostMirror", "BalatroEnv", "BalatroSB3VecEnv", "make_sb3_vec_env", "make", "make_balatro_env", "score_hands", "build", "load",
            "BgymError", "layout", "SO_PATH"]
 
 
 def __getattr__(name):  # lazy: importing the package must not need torch/CUDA
-    if name == "BalatroVecEnv":
-        from .vec_env import BalatroVecEnv
-        return BalatroVecEnv
+    if name in ("BalatroVecEnv", "HostMirror"):
+        from . import vec_env
+        return getattr(vec_env, name)
     if name in ("BalatroEnv", "make", "make_balatro_env", "register_envs", "reference_deck"):
         from . import env
         return getattr(env, name)

@@ -86,24 +86,28 @@ SYMBOLS = {
     "bgym_last_error": (C.c_char_p, []),
     "bgym_device_count": (_i32, []),
     "bgym_set_option": (_i32, [_i32, _i64]),
-    "bgym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bgym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bgym_sync_state": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "bgym_sync_obs": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "bgym_pack_dirty_obs": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp]),
+    "bgym_scatter_dirty_obs": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "bgym_release_stream": (_i32, [_vp]),
-    "bgym_action_mask": (_i32, [_vp, _vp, _vp, _i64, _vp]),
-    "bgym_sample_actions": (_i32, [_vp, _vp, _u32, _u64, _i64, _vp]),
-    "bgym_sample_actions_ctr": (_i32, [_vp, _vp, _u32, _vp, _i64, _vp]),
+    "bgym_action_mask": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "bgym_sample_actions": (_i32, [_vp, _i64, _vp, _u32, _u64, _i64, _vp]),
+    "bgym_sample_actions_ctr": (_i32, [_vp, _i64, _vp, _u32, _vp, _i64, _vp]),
     "bgym_score_hands": (_i32, [_vp] * 12 + [_u32, _i64, _i32, _vp]),
     "bgym_episode_stats": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "bgym_featurize": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "bgym_policy_first_layer": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "bgym_masked_sample": (_i32, [_vp, _i32, _vp, _vp, _u32, _u64, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "bgym_masked_sample": (_i32, [_vp, _i32, _vp, _i64, _vp, _u32, _u64, _i64, _vp, _vp, _vp, _i64, _vp]),
     "bgym_gae": (_i32, [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _i64, _i64, _vp]),
     "bgym_vec_create": (_i32, [C.POINTER(_vp), _i64, _i32]),
     "bgym_vec_destroy": (_i32, [_vp]),
     "bgym_vec_reset_host": (_i32, [_vp, _vp, _vp, _vp]),
     "bgym_vec_reset_masked_host": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "bgym_vec_step_host": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
-    "bgym_vec_pointers": (_i32, [_vp] + [C.POINTER(_vp)] * 5),
+    "bgym_vec_pointers": (_i32, [_vp] + [C.POINTER(_vp)] * 7),
     "bgym_vec_get_state": (_i32, [_vp, _vp]),
     "bgym_vec_set_state": (_i32, [_vp, _vp]),
 }
@@ -124,7 +128,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.bgym_abi_version() != 1:
+    if lib.bgym_abi_version() != 2:
         raise BgymError("libbgym.so ABI version mismatch")
     _lib = lib
     return lib

@@ -106,6 +106,42 @@ __device__ __forceinline__ void pack_hot(uint8_t* hot, const Hot& h) {
 }
 __device__ __forceinline__ void hot_clear_extra(uint8_t* hot) { *reinterpret_cast<uint2*>(hot + OFF_HOT_EXTRA) = make_uint2(0u, 0u); }
 
+// ---------------------------------------------------------------------------------------------
+// toggle record (BgymTog, 32 B, include/bgym.h): bytes 0..15 = THE copy of hot bytes 16..31 that card toggles update,
+// bytes 16..31 = the rest of what the select path reads (discards_left, cons_n, guard, Philox key word)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void set_chunk1(Hot& h, const uint4 q1) {
+  h.hand_n = q1.x & 0xFF; h.hand_size = (q1.x >> 8) & 0xFF; h.sel_n = (q1.x >> 16) & 0xFF; h.highlight = q1.x >> 24;
+  h.sel_order = q1.y;
+  h.face_down = q1.z & 0xFF; h.phase = (q1.z >> 8) & 0xFF; h.round = (q1.z >> 16) & 0xFF; h.boss_type = q1.z >> 24;
+  h.ep_len = q1.w;
+}
+__device__ __forceinline__ bool guard_pending(const Hot& h) { return h.ante > 100 || h.chips_scored > 1000000000LL; }   // :619-623
+__device__ __forceinline__ uint4 tog_summary(const Hot& h) {
+  uint4 q;
+  q.x = (h.discards_left & 0xFF) | ((h.cons_n & 0xFF) << 8) | (guard_pending(h) ? 0x10000u : 0u);
+  q.y = h.rng_seed; q.z = 0; q.w = 0;
+  return q;
+}
+// the fields of Hot the select path reads (toggle, PLAY-phase mask, routing, guard, fused policy), from a toggle record
+// alone; every other field of h stays unset.  The guard travels as one flag: it is put back as an ante that trips it.
+__device__ __forceinline__ void unpack_tog(const uint4 t0, const uint4 t1, Hot& h) {
+  set_chunk1(h, t0);
+  h.discards_left = t1.x & 0xFF; h.cons_n = (t1.x >> 8) & 0xFF;
+  h.ante = ((t1.x >> 16) & 0xFF) ? 101 : 1; h.chips_scored = 0;
+  h.rng_seed = t1.y;
+}
+// a whole env for the list / reset tiles: the hot record with its toggle-owned chunk taken from the toggle record
+__device__ __forceinline__ void load_hot(const uint8_t* hot, const uint8_t* tog, Hot& h) {
+  unpack_hot(hot, h);
+  set_chunk1(h, __ldcg(reinterpret_cast<const uint4*>(tog)));
+}
+__device__ __forceinline__ void store_tog(uint8_t* tog, const Hot& h) {
+  reinterpret_cast<uint4*>(tog)[0] = hot_chunk1(h);
+  reinterpret_cast<uint4*>(tog)[1] = tog_summary(h);
+}
+__device__ __forceinline__ void store_hot(uint8_t* hot, uint8_t* tog, const Hot& h) { pack_hot(hot, h); store_tog(tog, h); }
+
 __device__ __forceinline__ int hand_level(const Hot& h, int ht) {
   uint32_t w = ht < 4 ? h.lv0 : (ht < 8 ? h.lv1 : h.lv2);
   return (w >> (8 * (ht & 3))) & 0xFF;
@@ -1235,6 +1271,16 @@ __device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, 
   // 160: action_mask_bits | pad
   q.x = (uint32_t)mask; q.y = (uint32_t)(mask >> 32); q.z = 0; q.w = 0;
   sts128(obs + 160, q);
+}
+
+// selection record (BgymSel, 16 B): selected_cards[8] | action_mask_bits — the two observation fields a toggle changes
+__device__ __forceinline__ uint4 sel_words(const Hot& h, uint64_t mask) {
+  uint32_t selm = 0;
+  #pragma unroll 1
+  for (int k = 0; k < h.sel_n; k++) selm |= 1u << nib_at(h.sel_order, k);
+  uint4 q;
+  q.x = spread4(selm); q.y = spread4(selm >> 4); q.z = (uint32_t)mask; q.w = (uint32_t)(mask >> 32);
+  return q;
 }
 
 __device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs /*smem, 176 B*/) {

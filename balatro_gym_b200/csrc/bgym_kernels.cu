@@ -29,11 +29,13 @@ namespace bgym {
 
 struct StepArgs {
   uint8_t* hot;              // n x 144
+  uint8_t* tog;              // n x 32  toggle records (BgymTog): the select path's working set
   uint8_t* cold;             // n x 176
   const int32_t* actions;    // n (read; written instead with BGYM_FLAG_RANDOM_POLICY)
   int32_t* actions_out;      // n (written with BGYM_FLAG_RANDOM_POLICY, nullable)
   const BgymDraws* draws;    // n (nullable)
   uint8_t* obs;              // n x 176 (nullable)
+  uint8_t* sel;              // n x 16  selection records (BgymSel), nullable together with obs
   double* reward;            // n
   uint8_t* terminated;       // n
   uint8_t* truncated;        // n (nullable)
@@ -102,7 +104,9 @@ __global__ void __launch_bounds__(RESET_WARPS * 32, 3) env_reset_kernel(StepArgs
     if (active) {
       Hot h;
       if (a.reset_mask && !a.reset_mask[e]) {
-        unpack_hot(hot, h);   // untouched env: only re-emit its observation
+        unpack_hot(hot, h);   // untouched env: only re-emit its observation; its toggle record is the current one
+        set_chunk1(h, __ldcg(reinterpret_cast<const uint4*>(a.tog + e * BGYM_TOG_BYTES)));
+        pack_hot(hot, h);
       } else {
         reset_hot(h, a.seeds[e]);
         if (a.flags & BGYM_FLAG_GEN_C3) gen_hot(h, a.seeds[e], a.flags);
@@ -110,7 +114,12 @@ __global__ void __launch_bounds__(RESET_WARPS * 32, 3) env_reset_kernel(StepArgs
         pack_hot(hot, h);
         hot_clear_extra(hot);
       }
-      if (with_obs) write_obs(h, cold, action_mask(h, cold), obs_s);
+      store_tog(a.tog + e * BGYM_TOG_BYTES, h);
+      if (with_obs) {
+        const uint64_t m = action_mask(h, cold);
+        write_obs(h, cold, m, obs_s);
+        *reinterpret_cast<uint4*>(a.sel + e * BGYM_SEL_BYTES) = sel_words(h, m);
+      }
     }
     fence_async_smem();
     __syncwarp();
@@ -399,14 +408,15 @@ __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
 // ---------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void action_mask_kernel(const uint8_t* hot, const uint8_t* cold, uint64_t* mask, long long n) {
+__global__ void action_mask_kernel(const uint8_t* hot, const uint8_t* tog, const uint8_t* cold, uint64_t* mask, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const uint8_t* hr = hot + i * BGYM_HOT_BYTES;
+    const uint8_t* tr = tog + i * BGYM_TOG_BYTES;    // hand_n / sel_n / phase live in the toggle record (BgymTog)
     const uint8_t* cr = cold + i * BGYM_COLD_BYTES;
     uint64_t m = 0;
-    int phase = hr[25];
+    int phase = tr[9];
     if (phase == BGYM_PHASE_PLAY) {
-      int hand_n = hr[16], sel_n = hr[18], discards_left = hr[129], cons_n = hr[131];
+      int hand_n = tr[0], sel_n = tr[2], discards_left = hr[129], cons_n = hr[131];
       m = ((1ull << min(hand_n, 8)) - 1) << BGYM_A_SELECT_BASE;
       if (sel_n > 0) m |= 1ull << BGYM_A_PLAY_HAND;
       if (sel_n > 0 && discards_left > 0) m |= 1ull << BGYM_A_DISCARD;
@@ -432,11 +442,11 @@ __global__ void action_mask_kernel(const uint8_t* hot, const uint8_t* cold, uint
 // step_dev != nullptr: the step number lives on the device (launches replayed from a CUDA graph cannot take it as
 // a kernel argument); bump_counter_kernel advances it after the sampler
 __global__ void bump_counter_kernel(unsigned long long* ctr) { *ctr += 1; }
-__global__ void sample_actions_kernel(const uint8_t* obs, int32_t* actions, uint32_t seed, unsigned long long step,
+__global__ void sample_actions_kernel(const uint8_t* mask_words, long long mask_stride, int32_t* actions, uint32_t seed, unsigned long long step,
                                       const unsigned long long* step_dev, long long n) {
   if (step_dev) step += *step_dev;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    uint64_t m = *reinterpret_cast<const uint64_t*>(obs + i * BGYM_OBS_BYTES + 160);
+    uint64_t m = *reinterpret_cast<const uint64_t*>(mask_words + i * mask_stride);
     int cnt = __popcll(m);
     int act = 0;
     if (cnt) {
@@ -479,6 +489,115 @@ __global__ void episode_stats_kernel(const double* reward, const uint8_t* termin
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// coherence between the record arrays and their side arrays (BgymTog / BgymSel, include/bgym.h)
+// ---------------------------------------------------------------------------------------------
+__global__ void sync_state_kernel(uint8_t* hot, uint8_t* tog, long long n, int from_records) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint8_t* hr = hot + i * BGYM_HOT_BYTES;
+    uint8_t* tr = tog + i * BGYM_TOG_BYTES;
+    if (from_records) {
+      Hot h;
+      unpack_hot(hr, h);
+      store_tog(tr, h);
+    } else {
+      *reinterpret_cast<uint4*>(hr + 16) = *reinterpret_cast<const uint4*>(tr);
+    }
+  }
+}
+__global__ void sync_obs_kernel(uint8_t* obs, uint8_t* sel, long long n, int from_records) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint8_t* o = obs + i * BGYM_OBS_BYTES;
+    uint8_t* s = sel + i * BGYM_SEL_BYTES;
+    if (from_records) {
+      const uint2 sc = *reinterpret_cast<const uint2*>(o + 8), mk = *reinterpret_cast<const uint2*>(o + 160);
+      *reinterpret_cast<uint4*>(s) = make_uint4(sc.x, sc.y, mk.x, mk.y);
+    } else {
+      const uint4 q = *reinterpret_cast<const uint4*>(s);
+      *reinterpret_cast<uint2*>(o + 8) = make_uint2(q.x, q.y);
+      *reinterpret_cast<uint2*>(o + 160) = make_uint2(q.z, q.w);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// observation deltas for a host mirror: the records a step rewrote are exactly those of the envs on its level-1
+// lists.  pack: gather them (index + record) into a dense staging block; scatter: write staged records to their
+// places in another array of BgymObs — pinned host memory included (zero-copy stores over PCIe).
+// staging: int32 count @0 | int32 index[cap] @16 | BgymObs[cap] @(16 + 4 cap, rounded up to 16)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t dirty_rec_offset(long long cap) { return 16 + (((size_t)cap * 4 + 15) & ~(size_t)15); }
+// A staged record is bytes 0..159 of the observation record (BGYM_OBS_DELTA_BYTES): bytes 160..175 are the mask word,
+// which travels in the selection record, and padding.  10 lanes move one record (16 B each), three records per warp.
+// Bit 31 of a staged index says that the record's SHOP CHUNKS (6, 7: shop_items[1..9], shop_costs[0..6]) may differ from
+// what the mirror holds: they are all zero outside SHOP phase, so an env that was and stays in PLAY phase (the PLAY /
+// CONS / DISCARD lists unless the hand advanced the round) does not send them.
+constexpr int DELTA_LANES = BGYM_OBS_DELTA_BYTES / 16, DELTA_PER_WARP = 32 / DELTA_LANES;
+constexpr int OBS_OFF_PHASE = 155;
+__device__ __forceinline__ bool list_is_play_phase(int l) { return l == L_PLAY || l == L_CONS || l == L_DISCARD; }
+__global__ void __launch_bounds__(256) pack_dirty_kernel(const uint8_t* __restrict__ obs, const int* __restrict__ lists,
+                                                         const int* __restrict__ counters, long long part_cap,
+                                                         uint8_t* __restrict__ staging, long long cap) {
+  int base[N_LISTS_L1 + 1];
+  base[0] = 0;
+#pragma unroll
+  for (int l = 0; l < N_LISTS_L1; l++) base[l + 1] = base[l] + counters[l * PART_CTR_STRIDE];
+  const int total = base[N_LISTS_L1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(staging) = total;
+  uint32_t* idx_out = reinterpret_cast<uint32_t*>(staging + 16);
+  uint8_t* rec_out = staging + dirty_rec_offset(cap);
+  const int lane = threadIdx.x & 31, sub = lane / DELTA_LANES, part = lane - sub * DELTA_LANES;
+  const long long warp_gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long warp_cnt = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long k0 = warp_gid * DELTA_PER_WARP; k0 < total; k0 += warp_cnt * DELTA_PER_WARP) {
+    const long long k = k0 + sub;
+    if (sub < DELTA_PER_WARP && k < total && k < cap) {
+      int l = 0;
+#pragma unroll
+      for (int t = 1; t < N_LISTS_L1; t++) l += k >= base[t];
+      const int e = __ldg(lists + (long long)l * part_cap + (k - base[l]));
+      const uint8_t* rec = obs + (long long)e * BGYM_OBS_BYTES;
+      if (part == 0) idx_out[k] = (uint32_t)e | ((!list_is_play_phase(l) || rec[OBS_OFF_PHASE] != BGYM_PHASE_PLAY) ? 0x80000000u : 0u);
+      reinterpret_cast<uint4*>(rec_out + k * BGYM_OBS_DELTA_BYTES)[part] = __ldcs(reinterpret_cast<const uint4*>(rec) + part);
+    }
+  }
+}
+// every record is staged, index = identity, shop chunks included (a one-launch step of a small slab keeps no lists; a
+// mirror is filled for the first time)
+__global__ void __launch_bounds__(256) pack_all_kernel(const uint8_t* __restrict__ obs, uint8_t* __restrict__ staging, long long cap, long long n) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(staging) = (int)n;
+  uint32_t* idx_out = reinterpret_cast<uint32_t*>(staging + 16);
+  uint4* rec_out = reinterpret_cast<uint4*>(staging + dirty_rec_offset(cap));
+  const long long chunks = n * DELTA_LANES;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / DELTA_LANES;
+    rec_out[i] = __ldcs(reinterpret_cast<const uint4*>(obs + k * BGYM_OBS_BYTES) + (i - k * DELTA_LANES));
+    if (i < n) idx_out[i] = (uint32_t)i | 0x80000000u;
+  }
+}
+// staged record k -> the mirror (BGYM_MIRROR_CORE_BYTES = 128: chunks 0..5, 8, 9 of the record at core[e]; BGYM_MIRROR_SHOP_BYTES
+// = 32: chunks 6, 7 at shop[e]).  A core record is one aligned 128-byte line: zero-copy stores into pinned host memory then
+// run at the link's full rate (measured 52 GB/s against 35-42 GB/s for 176-byte records at a 176-byte stride, tools/exp/zc_probe.cu).
+__global__ void __launch_bounds__(256) scatter_dirty_kernel(const uint8_t* __restrict__ staging, long long cap, uint8_t* __restrict__ core,
+                                                            uint8_t* __restrict__ shop) {
+  const int total = *reinterpret_cast<const int*>(staging);
+  const uint32_t* idx = reinterpret_cast<const uint32_t*>(staging + 16);
+  const uint8_t* rec = staging + dirty_rec_offset(cap);
+  const int lane = threadIdx.x & 31, sub = lane / DELTA_LANES, part = lane - sub * DELTA_LANES;
+  const long long warp_gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long warp_cnt = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long k0 = warp_gid * DELTA_PER_WARP; k0 < total; k0 += warp_cnt * DELTA_PER_WARP) {
+    const long long k = k0 + sub;
+    if (sub < DELTA_PER_WARP && k < total && k < cap) {
+      const uint32_t w = __ldg(idx + k);
+      const long long e = w & 0x7FFFFFFFu;
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(rec + k * BGYM_OBS_DELTA_BYTES) + part);
+      if (part < 6) reinterpret_cast<uint4*>(core + e * BGYM_MIRROR_CORE_BYTES)[part] = q;
+      else if (part >= 8) reinterpret_cast<uint4*>(core + e * BGYM_MIRROR_CORE_BYTES)[part - 2] = q;
+      else if (w & 0x80000000u) reinterpret_cast<uint4*>(shop + e * BGYM_MIRROR_SHOP_BYTES)[part - 6] = q;
+    }
+  }
+}
 
 }  // namespace bgym
 
@@ -519,8 +638,6 @@ static int ensure_device_setup() {
   if (e != cudaSuccess) return cuda_rc(e, "cudaFuncSetAttribute(" #kernel ")");
   BGYM_SET_SMEM(env_reset_kernel, RESET_CTA_SMEM)
   BGYM_SET_SMEM(policy_first_layer_kernel, FL_SMEM)
-  BGYM_SET_SMEM(env_step_main_kernel<1>, MainCfg<1>::cta_smem)
-  BGYM_SET_SMEM(env_step_main_kernel<2>, MainCfg<2>::cta_smem)
 #undef BGYM_SET_SMEM
   g_dev_sms[dev] = g_sm_count;
   g_dev_ready[dev] = true;
@@ -541,6 +658,8 @@ static bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintp
 // (device, stream) in use; bgym_release_stream() gives a set back
 constexpr int PART_SIDE_STREAMS = 6;   // the seven level-1 list kernels run concurrently: launch stream + six forked ones
 struct PartScratch { bool used; int dev; void* stream; long long cap; int* lists; int* counters; uint16_t* aux;
+                     long long last_n; bool last_lists;   // the last bgym_step on this stream: slab size, and whether it kept lists
+
                      cudaStream_t side[PART_SIDE_STREAMS]; cudaEvent_t ev_fork, ev_fork2, ev_side[PART_SIDE_STREAMS]; bool streams_ok; };
 constexpr int BGYM_MAX_SCRATCH = 64;
 static PartScratch g_scratch[BGYM_MAX_SCRATCH];
@@ -600,32 +719,35 @@ int bgym_device_count(void) {
   return n;
 }
 
-int bgym_reset(BgymHot* hot, BgymCold* cold, BgymObs* obs, const uint8_t* reset_mask, const uint32_t* seeds,
-               const uint8_t* decks52, int64_t n, int flags, void* stream) {
-  if (n < 0 || !hot || !cold || !seeds) return set_err(BGYM_E_ARG, "bgym_reset: null hot/cold/seeds or negative n");
-  if (!obs && !(flags & BGYM_FLAG_NO_OBS)) return set_err(BGYM_E_ARG, "bgym_reset: obs is NULL without BGYM_FLAG_NO_OBS");
-  if (misaligned(hot, 16) || misaligned(cold, 16) || misaligned(obs, 16))
-    return set_err(BGYM_E_ALIGN, "bgym_reset: hot/cold/obs must be 16-byte aligned");
+int bgym_reset(BgymHot* hot, BgymTog* tog, BgymCold* cold, BgymObs* obs, BgymSel* sel, const uint8_t* reset_mask,
+               const uint32_t* seeds, const uint8_t* decks52, int64_t n, int flags, void* stream) {
+  if (n < 0 || !hot || !tog || !cold || !seeds) return set_err(BGYM_E_ARG, "bgym_reset: null hot/tog/cold/seeds or negative n");
+  if ((!obs || !sel) && !(flags & BGYM_FLAG_NO_OBS)) return set_err(BGYM_E_ARG, "bgym_reset: obs / sel is NULL without BGYM_FLAG_NO_OBS");
+  if (misaligned(hot, 16) || misaligned(tog, 16) || misaligned(cold, 16) || misaligned(obs, 16) || misaligned(sel, 16))
+    return set_err(BGYM_E_ALIGN, "bgym_reset: hot/tog/cold/obs/sel must be 16-byte aligned");
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
   StepArgs a;
   memset(&a, 0, sizeof a);
-  a.hot = reinterpret_cast<uint8_t*>(hot); a.cold = reinterpret_cast<uint8_t*>(cold); a.obs = reinterpret_cast<uint8_t*>(obs);
+  a.hot = reinterpret_cast<uint8_t*>(hot); a.tog = reinterpret_cast<uint8_t*>(tog); a.cold = reinterpret_cast<uint8_t*>(cold);
+  a.obs = reinterpret_cast<uint8_t*>(obs); a.sel = reinterpret_cast<uint8_t*>(sel);
+  if (!obs || !sel) { a.obs = nullptr; a.sel = nullptr; }
   a.reset_mask = reset_mask; a.seeds = seeds; a.decks52 = decks52; a.n = n; a.flags = flags;
   env_reset_kernel<<<tile_grid(n, RESET_WARPS, 3), RESET_WARPS * 32, RESET_CTA_SMEM, (cudaStream_t)stream>>>(a);
   return cuda_rc(cudaGetLastError(), "bgym_reset launch");
 }
 
-int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* draws, BgymObs* obs,
+int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, const BgymDraws* draws, BgymObs* obs, BgymSel* sel,
               double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
               int64_t n, int flags, void* stream) {
-  if (n < 0 || !hot || !cold || !reward || !terminated)
-    return set_err(BGYM_E_ARG, "bgym_step: null hot/cold/reward/terminated or negative n");
+  if (n < 0 || !hot || !tog || !cold || !reward || !terminated)
+    return set_err(BGYM_E_ARG, "bgym_step: null hot/tog/cold/reward/terminated or negative n");
   if (!actions) return set_err(BGYM_E_ARG, "bgym_step: actions is NULL");
-  if (!obs && !(flags & BGYM_FLAG_NO_OBS)) return set_err(BGYM_E_ARG, "bgym_step: obs is NULL without BGYM_FLAG_NO_OBS");
-  if (misaligned(hot, 16) || misaligned(cold, 16) || misaligned(obs, 16) || misaligned(info, 16) || misaligned(draws, 8))
-    return set_err(BGYM_E_ALIGN, "bgym_step: hot/cold/obs/info must be 16-byte aligned");
+  if ((!obs || !sel) && !(flags & BGYM_FLAG_NO_OBS)) return set_err(BGYM_E_ARG, "bgym_step: obs / sel is NULL without BGYM_FLAG_NO_OBS");
+  if (misaligned(hot, 16) || misaligned(tog, 16) || misaligned(cold, 16) || misaligned(obs, 16) || misaligned(sel, 16) ||
+      misaligned(info, 16) || misaligned(draws, 8))
+    return set_err(BGYM_E_ALIGN, "bgym_step: hot/tog/cold/obs/sel/info must be 16-byte aligned");
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
@@ -635,10 +757,12 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
   if (rc) return rc;
   StepArgs a;
   memset(&a, 0, sizeof a);
-  a.hot = reinterpret_cast<uint8_t*>(hot); a.cold = reinterpret_cast<uint8_t*>(cold);
+  a.hot = reinterpret_cast<uint8_t*>(hot); a.tog = reinterpret_cast<uint8_t*>(tog); a.cold = reinterpret_cast<uint8_t*>(cold);
   a.actions = actions;
   a.actions_out = (flags & BGYM_FLAG_RANDOM_POLICY) ? actions : nullptr;
-  a.draws = draws; a.obs = reinterpret_cast<uint8_t*>(obs);
+  a.draws = draws; a.obs = reinterpret_cast<uint8_t*>(obs); a.sel = reinterpret_cast<uint8_t*>(sel);
+  if (!obs || !sel) { a.obs = nullptr; a.sel = nullptr; }
+  sc->last_n = n;
   a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.info = info;
   a.n = n; a.flags = flags;
   a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_aux = sc->aux; a.part_cap = sc->cap;
@@ -652,17 +776,14 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
   if (timing && tcalls == 0 && tsum[0] == 0) for (int i = 0; i < NEV; i++) cudaEventCreate(&tev[i]);
   if (timing) cudaEventRecord(tev[0], s);
   // small slabs: one launch (bgym_step_part.cuh, env_step_small_kernel); BGYM_SMALL_N overrides the threshold
-  if (n <= small_slab_threshold() && !timing) {
+  sc->last_lists = !(n <= small_slab_threshold() && !timing);
+  if (!sc->last_lists) {
     env_step_small_kernel<<<tile_grid(n, GATHER_WARPS, GATHER_CTAS_PER_SM), GATHER_WARPS * 32, GATHER_CTA_SMEM, s>>>(a);
     return cuda_rc(cudaGetLastError(), "bgym_step launch");
   }
   cudaError_t e = cudaMemsetAsync(sc->counters, 0, N_LISTS * PART_CTR_STRIDE * sizeof(int), s);
   if (e != cudaSuccess) return cuda_rc(e, "cudaMemsetAsync(step counters)");
-  static const int main_stages = (getenv("BGYM_MAIN_STAGES") && getenv("BGYM_MAIN_STAGES")[0] == '1') ? 1 : 2;
-  if (main_stages == 2)
-    env_step_main_kernel<2><<<tile_grid(n, MAIN_WARPS, MainCfg<2>::ctas_per_sm), MAIN_WARPS * 32, MainCfg<2>::cta_smem, s>>>(a);
-  else
-    env_step_main_kernel<1><<<tile_grid(n, MAIN_WARPS, MainCfg<1>::ctas_per_sm), MAIN_WARPS * 32, MainCfg<1>::cta_smem, s>>>(a);
+  env_step_main_kernel<<<tile_grid(n, MAIN_WARPS, MAIN_CTAS_PER_SM), MAIN_WARPS * 32, 0, s>>>(a);
   if (timing) cudaEventRecord(tev[1], s);
   // The list lengths live on the device: every list kernel is launched with a resident-size grid, idle warps exit at
   // once.  Level 1 = one kernel per list the main pass filled, run concurrently on forked streams (they touch disjoint
@@ -735,39 +856,110 @@ int bgym_release_stream(void* stream) {
   return 0;
 }
 
-int bgym_action_mask(const BgymHot* hot, const BgymCold* cold, uint64_t* mask, int64_t n, void* stream) {
-  if (n < 0 || !hot || !cold || !mask) return set_err(BGYM_E_ARG, "bgym_action_mask: bad arguments");
+int bgym_action_mask(const BgymHot* hot, const BgymTog* tog, const BgymCold* cold, uint64_t* mask, int64_t n, void* stream) {
+  if (n < 0 || !hot || !tog || !cold || !mask) return set_err(BGYM_E_ARG, "bgym_action_mask: bad arguments");
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
   int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 8 ? (n + 255) / 256 : (long long)g_sm_count * 8);
-  action_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(hot),
+  action_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(hot), reinterpret_cast<const uint8_t*>(tog),
                                                              reinterpret_cast<const uint8_t*>(cold), mask, n);
   return cuda_rc(cudaGetLastError(), "bgym_action_mask launch");
 }
 
-int bgym_sample_actions(const BgymObs* obs, int32_t* actions, uint32_t seed, uint64_t step, int64_t n, void* stream) {
-  if (n < 0 || !obs || !actions) return set_err(BGYM_E_ARG, "bgym_sample_actions: bad arguments");
-  if (n == 0) return 0;
-  int rc = ensure_device_setup();
+static int sample_grid(int64_t n) {
+  // one thread per env up to 64 resident-size waves
+  return (int)((n + 255) / 256 < (long long)g_sm_count * 512 ? (n + 255) / 256 : (long long)g_sm_count * 512);
+}
+static int check_mask_words(const uint64_t* mask_words, int64_t mask_stride, const char* who) {
+  if (!mask_words || mask_stride < 8 || (mask_stride & 7) || misaligned(mask_words, 8)) {
+    snprintf(g_err, sizeof g_err, "%s: mask_words must be 8-byte aligned and mask_stride a multiple of 8 (>= 8)", who);
+    return BGYM_E_ARG;
+  }
+  return 0;
+}
+
+int bgym_sample_actions(const uint64_t* mask_words, int64_t mask_stride, int32_t* actions, uint32_t seed, uint64_t step,
+                        int64_t n, void* stream) {
+  if (n < 0 || !actions) return set_err(BGYM_E_ARG, "bgym_sample_actions: bad arguments");
+  int rc = check_mask_words(mask_words, mask_stride, "bgym_sample_actions");
   if (rc) return rc;
-  // one thread per env up to 64 resident-size waves: the 8-byte mask reads are 176-B strided and
-  // latency-bound, so keep as many in flight as the machine holds
-  int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 512 ? (n + 255) / 256 : (long long)g_sm_count * 512);
-  sample_actions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), actions, seed, step, nullptr, n);
+  if (n == 0) return 0;
+  rc = ensure_device_setup();
+  if (rc) return rc;
+  sample_actions_kernel<<<sample_grid(n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(mask_words), mask_stride, actions, seed, step, nullptr, n);
   return cuda_rc(cudaGetLastError(), "bgym_sample_actions launch");
 }
 
-int bgym_sample_actions_ctr(const BgymObs* obs, int32_t* actions, uint32_t seed, uint64_t* step_counter, int64_t n, void* stream) {
-  if (n < 0 || !obs || !actions || !step_counter) return set_err(BGYM_E_ARG, "bgym_sample_actions_ctr: bad arguments");
+int bgym_sample_actions_ctr(const uint64_t* mask_words, int64_t mask_stride, int32_t* actions, uint32_t seed,
+                            uint64_t* step_counter, int64_t n, void* stream) {
+  if (n < 0 || !actions || !step_counter) return set_err(BGYM_E_ARG, "bgym_sample_actions_ctr: bad arguments");
+  int rc = check_mask_words(mask_words, mask_stride, "bgym_sample_actions_ctr");
+  if (rc) return rc;
+  if (n == 0) return 0;
+  rc = ensure_device_setup();
+  if (rc) return rc;
+  sample_actions_kernel<<<sample_grid(n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(mask_words), mask_stride, actions, seed, 0ull,
+                                                                          reinterpret_cast<const unsigned long long*>(step_counter), n);
+  bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(step_counter));
+  return cuda_rc(cudaGetLastError(), "bgym_sample_actions_ctr launch");
+}
+
+int bgym_sync_state(BgymHot* hot, BgymTog* tog, int64_t n, int direction, void* stream) {
+  if (n < 0 || !hot || !tog || (direction != BGYM_SYNC_TO_RECORDS && direction != BGYM_SYNC_FROM_RECORDS))
+    return set_err(BGYM_E_ARG, "bgym_sync_state: bad arguments");
+  if (misaligned(hot, 16) || misaligned(tog, 16)) return set_err(BGYM_E_ALIGN, "bgym_sync_state: hot/tog must be 16-byte aligned");
   if (n == 0) return 0;
   int rc = ensure_device_setup();
   if (rc) return rc;
-  int grid = (int)((n + 255) / 256 < (long long)g_sm_count * 512 ? (n + 255) / 256 : (long long)g_sm_count * 512);
-  sample_actions_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), actions, seed, 0ull,
-                                                                reinterpret_cast<const unsigned long long*>(step_counter), n);
-  bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(step_counter));
-  return cuda_rc(cudaGetLastError(), "bgym_sample_actions_ctr launch");
+  sync_state_kernel<<<sample_grid(n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint8_t*>(hot), reinterpret_cast<uint8_t*>(tog), n, direction);
+  return cuda_rc(cudaGetLastError(), "bgym_sync_state launch");
+}
+
+int bgym_sync_obs(BgymObs* obs, BgymSel* sel, int64_t n, int direction, void* stream) {
+  if (n < 0 || !obs || !sel || (direction != BGYM_SYNC_TO_RECORDS && direction != BGYM_SYNC_FROM_RECORDS))
+    return set_err(BGYM_E_ARG, "bgym_sync_obs: bad arguments");
+  if (misaligned(obs, 16) || misaligned(sel, 16)) return set_err(BGYM_E_ALIGN, "bgym_sync_obs: obs/sel must be 16-byte aligned");
+  if (n == 0) return 0;
+  int rc = ensure_device_setup();
+  if (rc) return rc;
+  sync_obs_kernel<<<sample_grid(n), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint8_t*>(obs), reinterpret_cast<uint8_t*>(sel), n, direction);
+  return cuda_rc(cudaGetLastError(), "bgym_sync_obs launch");
+}
+
+int bgym_pack_dirty_obs(const BgymObs* obs, void* staging, int64_t cap, int64_t n, int all, void* stream) {
+  if (!obs || !staging || cap <= 0 || n <= 0) return set_err(BGYM_E_ARG, "bgym_pack_dirty_obs: bad arguments");
+  if (misaligned(obs, 16) || misaligned(staging, 16)) return set_err(BGYM_E_ALIGN, "bgym_pack_dirty_obs: obs/staging must be 16-byte aligned");
+  if (cap < n) return set_err(BGYM_E_ARG, "bgym_pack_dirty_obs: cap must be at least n");
+  int rc = ensure_device_setup();
+  if (rc) return rc;
+  PartScratch* sc = nullptr;
+  if (!all) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (int i = 0; i < BGYM_MAX_SCRATCH; i++)
+      if (g_scratch[i].used && g_scratch[i].dev == dev && g_scratch[i].stream == stream) sc = &g_scratch[i];
+    if (!sc || sc->last_n != n) return set_err(BGYM_E_ARG, "bgym_pack_dirty_obs: no bgym_step of n envs has run on this stream");
+  }
+  if (all || !sc->last_lists) {      // (a one-launch step of a small slab keeps no lists: every record may have changed)
+    pack_all_kernel<<<g_sm_count * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<uint8_t*>(staging), cap, n);
+    return cuda_rc(cudaGetLastError(), "bgym_pack_dirty_obs launch");
+  }
+  pack_dirty_kernel<<<g_sm_count * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), sc->lists, sc->counters, sc->cap,
+                                                                     reinterpret_cast<uint8_t*>(staging), cap);
+  return cuda_rc(cudaGetLastError(), "bgym_pack_dirty_obs launch");
+}
+
+int bgym_scatter_dirty_obs(const void* staging, int64_t cap, void* mirror_core, void* mirror_shop, void* stream) {
+  if (!staging || !mirror_core || !mirror_shop || cap <= 0) return set_err(BGYM_E_ARG, "bgym_scatter_dirty_obs: bad arguments");
+  if (misaligned(mirror_core, 128) || misaligned(mirror_shop, 32) || misaligned(staging, 16))
+    return set_err(BGYM_E_ALIGN, "bgym_scatter_dirty_obs: mirror_core needs 128-byte, mirror_shop 32-byte, staging 16-byte alignment");
+  int rc = ensure_device_setup();
+  if (rc) return rc;
+  scatter_dirty_kernel<<<g_sm_count * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(staging), cap,
+                                                                        reinterpret_cast<uint8_t*>(mirror_core), reinterpret_cast<uint8_t*>(mirror_shop));
+  return cuda_rc(cudaGetLastError(), "bgym_scatter_dirty_obs launch");
 }
 
 int bgym_score_hands(const uint8_t* cards8, const uint16_t* mods8, const uint8_t* n_cards,
@@ -839,23 +1031,25 @@ int bgym_policy_first_layer(const BgymObs* obs, const void* wt_hand, const void*
   return cuda_rc(cudaGetLastError(), "bgym_policy_first_layer launch");
 }
 
-int bgym_masked_sample(const void* logits, int dtype, const BgymObs* obs, const float* uniforms,
+int bgym_masked_sample(const void* logits, int dtype, const uint64_t* mask_words, int64_t mask_stride, const float* uniforms,
                        uint32_t seed, uint64_t step, int64_t env_offset,
                        int32_t* actions, float* logp, float* entropy, int64_t n, void* stream) {
-  if (n < 0 || !logits || !obs || !actions || !logp) return set_err(BGYM_E_ARG, "bgym_masked_sample: bad arguments");
+  if (n < 0 || !logits || !actions || !logp) return set_err(BGYM_E_ARG, "bgym_masked_sample: bad arguments");
   if (dtype != BGYM_DT_F32 && dtype != BGYM_DT_BF16) return set_err(BGYM_E_ARG, "bgym_masked_sample: dtype must be BGYM_DT_F32 or BGYM_DT_BF16");
-  if (misaligned(obs, 16) || misaligned(logits, dtype == BGYM_DT_F32 ? 16 : 8))
-    return set_err(BGYM_E_ALIGN, "bgym_masked_sample: obs needs 16-byte, logits 16-byte (f32) / 8-byte (bf16) alignment");
+  int rc = check_mask_words(mask_words, mask_stride, "bgym_masked_sample");
+  if (rc) return rc;
+  if (misaligned(logits, dtype == BGYM_DT_F32 ? 16 : 8))
+    return set_err(BGYM_E_ALIGN, "bgym_masked_sample: logits need 16-byte (f32) / 8-byte (bf16) alignment");
   if (n == 0) return 0;
-  int rc = ensure_device_setup();
+  rc = ensure_device_setup();
   if (rc) return rc;
   long long blocks = (n + 127) / 128;
   if (blocks > 0x7fffffffLL) return set_err(BGYM_E_ARG, "bgym_masked_sample: n too large for one launch");
   if (dtype == BGYM_DT_F32)
-    masked_sample_kernel<float><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(logits), reinterpret_cast<const uint8_t*>(obs),
+    masked_sample_kernel<float><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float*>(logits), reinterpret_cast<const uint8_t*>(mask_words), mask_stride,
         uniforms, seed, step, env_offset, actions, logp, entropy, n);
   else
-    masked_sample_kernel<__nv_bfloat16><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), reinterpret_cast<const uint8_t*>(obs),
+    masked_sample_kernel<__nv_bfloat16><<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(logits), reinterpret_cast<const uint8_t*>(mask_words), mask_stride,
         uniforms, seed, step, env_offset, actions, logp, entropy, n);
   return cuda_rc(cudaGetLastError(), "bgym_masked_sample launch");
 }
@@ -875,7 +1069,7 @@ int bgym_gae(const float* rewards, const float* values, const uint8_t* dones, fl
 // ---- host-buffer handle API ---------------------------------------------------------------------
 struct BgymVec {
   int64_t n; int device; cudaStream_t stream;
-  uint8_t *d_hot, *d_cold, *d_obs, *d_term, *d_trunc, *d_decks; double* d_reward; BgymInfo* d_info; int32_t* d_actions;
+  uint8_t *d_hot, *d_tog, *d_cold, *d_obs, *d_sel, *d_term, *d_trunc, *d_decks; double* d_reward; BgymInfo* d_info; int32_t* d_actions;
   uint32_t* d_seeds; BgymDraws* d_draws;
   // pinned staging
   uint8_t *h_hot, *h_cold, *h_obs, *h_term, *h_trunc, *h_decks; double* h_reward; BgymInfo* h_info; int32_t* h_actions;
@@ -900,6 +1094,8 @@ struct DeviceGuard {
 static int vec_create_impl(BgymVec* v, int64_t n) {
   CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
   CK(cudaMalloc(&v->d_hot, n * BGYM_HOT_BYTES)); CK(cudaMalloc(&v->d_cold, n * BGYM_COLD_BYTES));
+  CK(cudaMalloc(&v->d_tog, n * BGYM_TOG_BYTES)); CK(cudaMalloc(&v->d_sel, n * BGYM_SEL_BYTES));
+  CK(cudaMemsetAsync(v->d_tog, 0, n * BGYM_TOG_BYTES, v->stream)); CK(cudaMemsetAsync(v->d_sel, 0, n * BGYM_SEL_BYTES, v->stream));
   auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const size_t off_rew = up16((size_t)n * BGYM_OBS_BYTES), off_info = up16(off_rew + (size_t)n * 8);
   const size_t off_term = up16(off_info + (size_t)n * BGYM_INFO_BYTES), off_trunc = up16(off_term + (size_t)n);
@@ -948,7 +1144,7 @@ int bgym_vec_destroy(BgymVec* v) {
   if (!v) return 0;
   DeviceGuard guard(v->device);
   if (v->stream) cudaStreamSynchronize(v->stream);
-  cudaFree(v->d_hot); cudaFree(v->d_cold); cudaFree(v->d_block); cudaFree(v->d_decks); cudaFree(v->d_mask); cudaFreeHost(v->h_mask);
+  cudaFree(v->d_hot); cudaFree(v->d_tog); cudaFree(v->d_cold); cudaFree(v->d_sel); cudaFree(v->d_block); cudaFree(v->d_decks); cudaFree(v->d_mask); cudaFreeHost(v->h_mask);
   cudaFree(v->d_actions); cudaFree(v->d_seeds); cudaFree(v->d_draws);
   cudaFreeHost(v->h_hot); cudaFreeHost(v->h_cold); cudaFreeHost(v->h_block);
   cudaFreeHost(v->h_decks); cudaFreeHost(v->h_actions);
@@ -975,10 +1171,11 @@ int bgym_vec_reset_masked_host(BgymVec* v, const uint8_t* reset_mask, const uint
     memcpy(v->h_decks, decks52, v->n * 52);
     CK(cudaMemcpyAsync(v->d_decks, v->h_decks, v->n * 52, cudaMemcpyHostToDevice, v->stream));
   }
-  int rc = bgym_reset(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymCold*>(v->d_cold),
-                      reinterpret_cast<BgymObs*>(v->d_obs), reset_mask ? v->d_mask : nullptr, v->d_seeds, decks52 ? v->d_decks : nullptr,
-                      v->n, 0, v->stream);
+  int rc = bgym_reset(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymTog*>(v->d_tog), reinterpret_cast<BgymCold*>(v->d_cold),
+                      reinterpret_cast<BgymObs*>(v->d_obs), reinterpret_cast<BgymSel*>(v->d_sel), reset_mask ? v->d_mask : nullptr, v->d_seeds,
+                      decks52 ? v->d_decks : nullptr, v->n, 0, v->stream);
   if (rc) return rc;
+  // a reset (masked or not) re-emits every env's observation record whole: no sync needed
   if (obs_out) CK(cudaMemcpyAsync(v->h_obs, v->d_obs, v->n * BGYM_OBS_BYTES, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaStreamSynchronize(v->stream));
   if (obs_out) memcpy(obs_out, v->h_obs, v->n * BGYM_OBS_BYTES);
@@ -998,11 +1195,14 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
     memcpy(v->h_draws, draws, v->n * BGYM_DRAWS_BYTES);
     CK(cudaMemcpyAsync(v->d_draws, v->h_draws, v->n * BGYM_DRAWS_BYTES, cudaMemcpyHostToDevice, v->stream));
   }
-  int rc = bgym_step(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymCold*>(v->d_cold), v->d_actions,
-                     draws ? v->d_draws : nullptr, reinterpret_cast<BgymObs*>(v->d_obs), v->d_reward, v->d_term, v->d_trunc,
-                     v->d_info, v->n, flags & ~BGYM_FLAG_NO_OBS, v->stream);
+  int rc = bgym_step(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymTog*>(v->d_tog), reinterpret_cast<BgymCold*>(v->d_cold), v->d_actions,
+                     draws ? v->d_draws : nullptr, reinterpret_cast<BgymObs*>(v->d_obs), reinterpret_cast<BgymSel*>(v->d_sel),
+                     v->d_reward, v->d_term, v->d_trunc, v->d_info, v->n, flags & ~BGYM_FLAG_NO_OBS, v->stream);
   if (rc) return rc;
   if (obs_out) {
+    // host callers get whole records: fold the selection array (selected_cards, mask word) into them first
+    rc = bgym_sync_obs(reinterpret_cast<BgymObs*>(v->d_obs), reinterpret_cast<BgymSel*>(v->d_sel), v->n, BGYM_SYNC_TO_RECORDS, v->stream);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(v->h_block, v->d_block, v->block_bytes, cudaMemcpyDeviceToHost, v->stream));      // everything, one copy
   } else {   // without observations: skip the 176 B/env part
     const size_t off = reinterpret_cast<uint8_t*>(v->d_reward) - v->d_block;
@@ -1017,11 +1217,13 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
   return 0;
 }
 
-int bgym_vec_pointers(BgymVec* v, void** hot, void** cold, void** obs, void** reward, void** terminated) {
+int bgym_vec_pointers(BgymVec* v, void** hot, void** tog, void** cold, void** obs, void** sel, void** reward, void** terminated) {
   if (!v) return set_err(BGYM_E_ARG, "bgym_vec_pointers: null handle");
   if (hot) *hot = v->d_hot;
+  if (tog) *tog = v->d_tog;
   if (cold) *cold = v->d_cold;
   if (obs) *obs = v->d_obs;
+  if (sel) *sel = v->d_sel;
   if (reward) *reward = v->d_reward;
   if (terminated) *terminated = v->d_term;
   return 0;
@@ -1031,6 +1233,8 @@ int bgym_vec_pointers(BgymVec* v, void** hot, void** cold, void** obs, void** re
 int bgym_vec_get_state(BgymVec* v, BgymState* host_out) {
   if (!v || !host_out) return set_err(BGYM_E_ARG, "bgym_vec_get_state: bad arguments");
   BGYM_ON_DEVICE(v);
+  int rc = bgym_sync_state(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymTog*>(v->d_tog), v->n, BGYM_SYNC_TO_RECORDS, v->stream);
+  if (rc) return rc;
   CK(cudaMemcpyAsync(v->h_hot, v->d_hot, v->n * BGYM_HOT_BYTES, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaMemcpyAsync(v->h_cold, v->d_cold, v->n * BGYM_COLD_BYTES, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaStreamSynchronize(v->stream));
@@ -1052,6 +1256,8 @@ int bgym_vec_set_state(BgymVec* v, const BgymState* host_in) {
   }
   CK(cudaMemcpyAsync(v->d_hot, v->h_hot, v->n * BGYM_HOT_BYTES, cudaMemcpyHostToDevice, v->stream));
   CK(cudaMemcpyAsync(v->d_cold, v->h_cold, v->n * BGYM_COLD_BYTES, cudaMemcpyHostToDevice, v->stream));
+  int rc = bgym_sync_state(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymTog*>(v->d_tog), v->n, BGYM_SYNC_FROM_RECORDS, v->stream);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(v->stream));
   return 0;
 }

@@ -188,14 +188,14 @@ __global__ void __launch_bounds__(FL_WARPS * 32, 1) policy_first_layer_kernel(co
 // two envs instead of one per 32, and reductions instead of serial adds.)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) masked_sample_kernel(const T* __restrict__ logits, const uint8_t* __restrict__ obs,
-                                                            const float* __restrict__ uniforms, uint32_t seed,
+__global__ void __launch_bounds__(128) masked_sample_kernel(const T* __restrict__ logits, const uint8_t* __restrict__ mask_words,
+                                                            long long mask_stride, const float* __restrict__ uniforms, uint32_t seed,
                                                             unsigned long long step, long long env_offset,
                                                             int32_t* __restrict__ actions, float* __restrict__ logp,
                                                             float* __restrict__ entropy, long long n) {
   const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n) return;
-  unsigned long long mask = *reinterpret_cast<const unsigned long long*>(obs + env * BGYM_OBS_BYTES + 160);
+  unsigned long long mask = *reinterpret_cast<const unsigned long long*>(mask_words + env * mask_stride);
   mask &= (1ull << BGYM_NUM_ACTIONS) - 1;
   float x[BGYM_NUM_ACTIONS];
   if constexpr (sizeof(T) == 4) {

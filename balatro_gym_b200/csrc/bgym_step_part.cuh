@@ -89,36 +89,32 @@ __device__ __forceinline__ int policy_action(const Hot& h, uint64_t mask) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// main pass: per-warp tiles of 32 hot records, one bulk load + one bulk store per tile
+// main pass: every env, on the toggle records alone
 // ------------------------------------------------------------------------------------------------
-constexpr int MAIN_WARPS = 4;
-constexpr int MAIN_HOT_TILE = 32 * BGYM_HOT_BYTES;   // 4608
+// A card toggle (and a rejected action) needs nothing but the env's 32-byte toggle record (BgymTog, include/bgym.h): the
+// pass reads tog[e] and actions[e], and for the envs it serves writes tog[e] (the selection), sel[e] (the two
+// observation fields a toggle changes: selected_cards and the legal-action word), reward and flags —
+// 36 B read + 58 B written per env, all of it coalesced (a warp's 32 toggle records are 1 KB contiguous) — where the
+// round-1/2 pass staged 144-byte hot records through shared memory and rewrote whole 176-byte observation records
+// (350 B per env).  The 176-byte observation record of a served env is NOT rewritten: none of its other fields changed.
+// No shared-memory staging of records, no bulk copies: each lane holds its record in eight registers, the next tile's
+// loads are issued before the current tile is served.
 // Deferred env indices are staged per warp in shared memory and appended to the device lists in
 // runs of >= 32 (one atomic per run).  One atomic per tile and list kept a single L2 slice busy for
 // most of the pass (~10^5 same-sector atomics per 2^20 envs); the counters also sit 128 B apart.
+constexpr int MAIN_WARPS = 8;
+#ifndef BGYM_MAIN_CTAS
+#define BGYM_MAIN_CTAS 3
+#endif
+constexpr int MAIN_CTAS_PER_SM = BGYM_MAIN_CTAS;
 constexpr int PART_STAGE = 64;
 constexpr int PART_CTR_STRIDE = 32;   // ints between list counters
-// STAGES = 1: one hot buffer per warp, 4 CTAs/SM (16 warps hide each other's loads)
-// STAGES = 2: the next tile's hot records are prefetched while the current tile is served, 3 CTAs/SM
-template <int STAGES>
-struct MainCfg {
-  static constexpr int warp_smem = STAGES * MAIN_HOT_TILE + 32 * BGYM_OBS_BYTES;
-  // + per-warp staging of the level-1 lists (PART_STAGE entries each), then the mbarriers
-  static constexpr int cta_smem = MAIN_WARPS * warp_smem + MAIN_WARPS * N_LISTS_L1 * PART_STAGE * 4 + 16 * MAIN_WARPS;
-  static constexpr int ctas_per_sm = (227 * 1024) / cta_smem;
-};
+constexpr int MAIN_CTA_SMEM = MAIN_WARPS * N_LISTS_L1 * PART_STAGE * 4;   // static shared memory: the staged lists
 
-template <int STAGES>
-__global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm) env_step_main_kernel(StepArgs a) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int MAIN_WARP_SMEM = MainCfg<STAGES>::warp_smem;
+__global__ void __launch_bounds__(MAIN_WARPS * 32, MAIN_CTAS_PER_SM) env_step_main_kernel(const __grid_constant__ StepArgs a) {
+  __shared__ int stage_all[MAIN_WARPS * N_LISTS_L1 * PART_STAGE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* hot_base = smem + warp * MAIN_WARP_SMEM;
-  uint8_t* obs_buf = hot_base + STAGES * MAIN_HOT_TILE;
-  int* stage_list = reinterpret_cast<int*>(smem + MAIN_WARPS * MAIN_WARP_SMEM) + warp * N_LISTS_L1 * PART_STAGE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MAIN_WARPS * MAIN_WARP_SMEM + MAIN_WARPS * N_LISTS_L1 * PART_STAGE * 4) + warp * 2;
-  if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-  __syncwarp();
+  int* stage_list = stage_all + warp * N_LISTS_L1 * PART_STAGE;
   int staged[N_LISTS_L1];   // warp-uniform fill of the staging lists
 #pragma unroll
   for (int c = 0; c < N_LISTS_L1; c++) staged[c] = 0;
@@ -134,47 +130,32 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
   const long long n_tiles = (a.n + 31) >> 5;
   const long long warp_gid = (long long)blockIdx.x * MAIN_WARPS + warp;
   const long long warp_cnt = (long long)gridDim.x * MAIN_WARPS;
-  const bool with_obs = a.obs != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
+  const bool with_obs = a.sel != nullptr && !(a.flags & BGYM_FLAG_NO_OBS);
   const bool fused_policy = (a.flags & BGYM_FLAG_RANDOM_POLICY) != 0;
-  uint32_t parity_bits = 0;
-  int stage = 0;
-  auto issue_load = [&](long long t, int st) {   // lane 0 only
-    uint32_t bytes = (uint32_t)(min(32LL, a.n - t * 32) * BGYM_HOT_BYTES);
-    mbar_arrive_expect_tx(&bars[st], bytes);
-    bulk_g2s(hot_base + st * MAIN_HOT_TILE, a.hot + t * 32 * BGYM_HOT_BYTES, bytes, &bars[st]);
-  };
-  if (STAGES == 2 && lane == 0 && warp_gid < n_tiles) issue_load(warp_gid, 0);
-  // the action of this lane's env in the NEXT tile is fetched one iteration ahead (its DRAM latency would
-  // otherwise sit between the tile's arrival and the first use)
+  // software pipeline: the toggle record and the action of this lane's env in the NEXT tile are loaded one iteration ahead
+  uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
   int action_next = 0;
-  if (!fused_policy && warp_gid * 32 + lane < a.n) action_next = __ldg(a.actions + warp_gid * 32 + lane);
-  for (long long tile = warp_gid; tile < n_tiles; tile += warp_cnt, stage = (STAGES == 2) ? (stage ^ 1) : 0) {
+  auto fetch = [&](long long tile) {
+    const long long en = tile * 32 + lane;
+    if (tile < n_tiles && en < a.n) {
+      const uint4* t = reinterpret_cast<const uint4*>(a.tog + en * BGYM_TOG_BYTES);
+      n0 = __ldcs(t); n1 = __ldcs(t + 1);                       // read once: streaming
+      if (!fused_policy) action_next = __ldcs(a.actions + en);
+    }
+  };
+  fetch(warp_gid);
+  for (long long tile = warp_gid; tile < n_tiles; tile += warp_cnt) {
     const long long e = tile * 32 + lane;
     const bool active = e < a.n;
-    uint8_t* hot_buf = hot_base + stage * MAIN_HOT_TILE;
-    uint8_t* hot = hot_buf + lane * BGYM_HOT_BYTES;
-    uint8_t* obs_s = obs_buf + lane * BGYM_OBS_BYTES;
-    if (lane == 0) {
-      // the previous tile's bulk stores have finished READING shared memory (its hot buffer is the one
-      // the next load overwrites; the obs buffer is rewritten below)
-      bulk_wait_read0();
-      if (STAGES == 2) { if (tile + warp_cnt < n_tiles) issue_load(tile + warp_cnt, stage ^ 1); }
-      else issue_load(tile, 0);
-    }
+    const uint4 t0 = n0, t1 = n1;
     int action = action_next;
-    {
-      const long long en = (tile + warp_cnt) * 32 + lane;
-      if (!fused_policy && en < a.n) action_next = __ldg(a.actions + en);
-    }
-    __syncwarp();   // lane 0 has passed its wait: the obs buffer is free for every lane
-    mbar_wait(&bars[stage], (parity_bits >> stage) & 1);
-    parity_bits ^= 1u << stage;
+    fetch(tile + warp_cnt);
 
     int cat = -2;   // -2 inactive lane, -1 served here, >= 0 list
     if (active) {
       Hot h;
-      unpack_hot(hot, h);
-      // the PLAY-phase mask needs the hot record only; other phases are not served here
+      unpack_tog(t0, t1, h);
+      // the PLAY-phase mask needs the toggle record only; other phases are not served here
       const bool play_phase = h.phase == BGYM_PHASE_PLAY;
       const uint64_t m0 = play_phase ? action_mask(h, nullptr) : 0ull;
       if (fused_policy) {
@@ -186,18 +167,20 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
         }
       }
       // guard-terminated envs (:619-623) end their episode whatever the action
-      const bool guard = h.ante > 100 || h.chips_scored > 1000000000LL;
+      const bool guard = guard_pending(h);
       cat = (fused_policy && !play_phase) ? (int)L_MISC : route_env(h, action, m0, guard);
       if (cat < 0) {
         double reward = 0.0;
         int terminated = 0;
         StepInfo info;
-        step_env<CAT_SELECT, false>(h, hot, nullptr, action, m0, nullptr, reward, terminated, info, nullptr);
-        // a card toggle changes bytes 16..31 of the hot record and nothing else (include/bgym.h): that chunk goes
-        // straight from registers to its place — one 32-byte sector per env instead of the 144-byte record; a
-        // rejected action changes nothing at all
-        if (info.error_code == 0) *reinterpret_cast<uint4*>(a.hot + e * BGYM_HOT_BYTES + 16) = hot_chunk1(h);
-        if (with_obs) write_obs(h, nullptr, action_mask(h, nullptr), obs_s);
+        step_env<CAT_SELECT, false>(h, nullptr, nullptr, action, m0, nullptr, reward, terminated, info, nullptr);
+        // a rejected action changes nothing at all; a toggle changes the selection: bytes 0..15 of the toggle record
+        // (the summary half is rewritten with it so that the store covers the whole 32-byte sector)
+        if (info.error_code == 0) {
+          uint4* t = reinterpret_cast<uint4*>(a.tog + e * BGYM_TOG_BYTES);
+          t[0] = hot_chunk1(h); t[1] = t1;
+          if (with_obs) *reinterpret_cast<uint4*>(a.sel + e * BGYM_SEL_BYTES) = sel_words(h, action_mask(h, nullptr));
+        }
         write_step_outputs(a, e, reward, terminated, info);
       }
     }
@@ -213,18 +196,9 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MainCfg<STAGES>::ctas_per_sm)
         }
       }
     }
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      uint32_t cnt = (uint32_t)min(32LL, a.n - tile * 32);
-      // deferred envs' observation slots hold stale bytes; their tile rewrites them afterwards
-      if (with_obs) bulk_s2g(a.obs + tile * 32 * BGYM_OBS_BYTES, obs_buf, cnt * BGYM_OBS_BYTES);
-      bulk_commit();
-    }
   }
 #pragma unroll
   for (int c = 0; c < N_LISTS_L1; c++) if (staged[c]) flush_list(c, staged[c]);
-  if (lane == 0) bulk_wait0();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -293,6 +267,13 @@ constexpr int STG_RO = 0, STG_RW = 0;
 #endif
 __host__ __device__ constexpr int list_smem_bytes(int list) { return (list >= 7 /*level 2*/ || STG_RW || STG_RO) ? GATHER_CTA_SMEM : 0; }
 
+// the whole observation of env e: the 176-byte record AND the selection record (both carry selected_cards and the mask)
+__device__ __forceinline__ void emit_observation(const StepArgs& a, long long e, const Hot& h, const uint8_t* cold) {
+  const uint64_t m = action_mask(h, cold);
+  write_obs(h, cold, m, a.obs + e * BGYM_OBS_BYTES);
+  *reinterpret_cast<uint4*>(a.sel + e * BGYM_SEL_BYTES) = sel_words(h, m);
+}
+
 // One tile: lane `lane` serves listed env `e`, WORKING ON THE RECORDS WHERE THEY LIE: the hot record is lifted into
 // registers with nine 16-byte loads and written back the same way, the cold record (deck, shop) is read and written in
 // place through L1 — a step touches a handful of its 176 bytes (eight deck entries for a discard, the deck half for a
@@ -314,6 +295,7 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool
   constexpr bool DEFER = (MODE & TM_DEFER) != 0;
   constexpr bool STAGE = (MODE & TM_STAGE_COLD) != 0;
   uint8_t* hot = a.hot + (active ? e : 0) * BGYM_HOT_BYTES;
+  uint8_t* tog = a.tog + (active ? e : 0) * BGYM_TOG_BYTES;
   uint8_t* cold_g = a.cold + (active ? e : 0) * BGYM_COLD_BYTES;
   uint8_t* cold = STAGE ? cold_slot : cold_g;
   if (STAGE) {
@@ -331,7 +313,7 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool
   if (active) {
     // read once, straight from L2 (with the fused policy the main pass wrote it for PLAY-phase envs)
     action = __ldcg(a.actions + e);
-    unpack_hot(hot, h);
+    load_hot(hot, tog, h);
   }
   if (STAGE) { cp_async_wait_all(); __syncwarp(); }
   if (active) m0 = action_mask(h, cold);
@@ -372,11 +354,11 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool
   }
   BGYM_CTA_SYNC();
   if (store_state) {
-    pack_hot(hot, h);
+    store_hot(hot, tog, h);
     if (!DEFER && want_reset) hot_clear_extra(hot);
   }
   BGYM_CTA_SYNC();
-  if (emit_obs) write_obs(h, cold, action_mask(h, cold), a.obs + e * BGYM_OBS_BYTES);
+  if (emit_obs) emit_observation(a, e, h, cold);
   if (STAGE) {
     __syncwarp();     // a cooperative reset (small-slab kernel) writes other lanes' slots
     if (store_state && !(MODE & TM_COLD_CLEAN)) cold_from_smem(cold_g, cold_slot);
@@ -394,11 +376,11 @@ __device__ __forceinline__ void advance_tile(const StepArgs& a, long long e, boo
   cold_to_smem_async(cold_slot, cold_g);
   const uint32_t snap = a.part_aux[e];
   Hot h;
-  unpack_hot(hot, h);
+  load_hot(hot, a.tog + e * BGYM_TOG_BYTES, h);
   cp_async_wait_all();
   step_env_advance(h, hot, cold_slot, a.draws ? a.draws + e : nullptr, snap);
-  pack_hot(hot, h);
-  if (with_obs) write_obs(h, cold_slot, action_mask(h, cold_slot), a.obs + e * BGYM_OBS_BYTES);
+  store_hot(hot, a.tog + e * BGYM_TOG_BYTES, h);
+  if (with_obs) emit_observation(a, e, h, cold_slot);
   cold_from_smem(cold_g, cold_slot);
 }
 
@@ -418,9 +400,9 @@ __device__ __forceinline__ void reset_tile(const StepArgs& a, long long e, bool 
   if (gen) gen_hot(h, new_seed, a.flags);
   h.episode = episode;
   reset_blocks_serial(cold_slot, new_seed, nullptr, gen);      // deck build + shuffle in the lane's shared-memory slot
-  pack_hot(hot, h);
+  store_hot(hot, a.tog + e * BGYM_TOG_BYTES, h);
   hot_clear_extra(hot);
-  if (with_obs) write_obs(h, cold_slot, action_mask(h, cold_slot), a.obs + e * BGYM_OBS_BYTES);
+  if (with_obs) emit_observation(a, e, h, cold_slot);
   cold_from_smem(a.cold + e * BGYM_COLD_BYTES, cold_slot);
 }
 

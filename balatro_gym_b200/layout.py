@@ -12,6 +12,12 @@ STATE_BYTES = 320
 HOT_BYTES = 144
 COLD_BYTES = 176
 OBS_BYTES = 176
+TOG_BYTES = 32      # BgymTog: device-only toggle record (authoritative copy of hot bytes 16..31 + select-path summary)
+SEL_BYTES = 16      # BgymSel: device-only selection record (authoritative selected_cards + action_mask_bits)
+OBS_DELTA_BYTES = 160   # what an observation delta carries of a record: all but the mask word (selection record) and padding
+MIRROR_CORE_BYTES, MIRROR_SHOP_BYTES = 128, 32   # host mirror of the observations (bgym_scatter_dirty_obs)
+MIRROR_CORE_CHUNKS, MIRROR_SHOP_CHUNKS = (0, 1, 2, 3, 4, 5, 8, 9), (6, 7)   # 16-byte chunks of an obs record
+SYNC_TO_RECORDS, SYNC_FROM_RECORDS = 0, 1
 INFO_BYTES = 32
 DRAWS_BYTES = 256
 NUM_ACTIONS = 60
@@ -82,6 +88,35 @@ OBS_DTYPE = _dt([
     ("boss_blind_active", "i1", 156), ("boss_blind_type", "i1", 157),
     ("action_mask_bits", "<u8", 160),
 ], OBS_BYTES)
+
+
+TOG_DTYPE = _dt([
+    ("hand_n", "u1", 0), ("hand_size", "u1", 1), ("sel_n", "u1", 2), ("highlight_mask", "u1", 3), ("sel_order", "<u4", 4),
+    ("face_down_mask", "u1", 8), ("phase", "u1", 9), ("round", "u1", 10), ("boss_type", "u1", 11), ("ep_len", "<u4", 12),
+    ("discards_left", "u1", 16), ("cons_n", "u1", 17), ("guard", "u1", 18), ("rng_seed", "<u4", 20),
+], TOG_BYTES)
+SEL_DTYPE = _dt([("selected_cards", "(8,)i1", 0), ("action_mask_bits", "<u8", 8)], SEL_BYTES)
+# hot-record fields whose authoritative copy lives in the toggle record on the device
+TOG_OWNED_FIELDS = ["hand_n", "hand_size", "sel_n", "highlight_mask", "sel_order", "face_down_mask", "phase", "round",
+                    "boss_type", "ep_len"]
+
+
+# host mirror core record (HostMirror.core): the observation fields that lie inside chunks 0..5, 8, 9, at their mirror offsets
+
+def _mirror_core_dtype():
+    fields = []
+    for name in OBS_DTYPE.names:
+        dt, off = OBS_DTYPE.fields[name][:2]
+        lo, hi = off // 16, (off + dt.itemsize - 1) // 16
+        if name in ("selected_cards", "action_mask_bits"):
+            continue                                     # the selection record carries them
+        if all(c in MIRROR_CORE_CHUNKS for c in range(lo, hi + 1)) and MIRROR_CORE_CHUNKS.index(hi) - MIRROR_CORE_CHUNKS.index(lo) == hi - lo:
+            fields.append((name, dt, MIRROR_CORE_CHUNKS.index(lo) * 16 + off % 16))
+    return np.dtype({"names": [f[0] for f in fields], "formats": [f[1] for f in fields], "offsets": [f[2] for f in fields],
+                     "itemsize": MIRROR_CORE_BYTES})
+
+
+MIRROR_CORE_DTYPE = _mirror_core_dtype()
 
 
 def mask_from_bits(bits) -> np.ndarray:

@@ -67,7 +67,8 @@ def policy_first_layer(obs_records, wt_hand, wt_joker, wt_game, bias, out=None):
 def masked_sample(logits, obs_records, seed: int = 0, step: int = 0, env_offset: int = 0, uniforms=None,
                   actions=None, logp=None, entropy=None):
     """Sample one legal action per env from softmax(logits | legal) (bgym_masked_sample).
-    Returns (actions int32 [n], logp float32 [n], entropy float32 [n])."""
+    obs_records: [n, 176] WHOLE observation records (the mask word is read at byte 160) or [n, 16] selection records
+    (BgymSel, byte 8) — the array a step keeps current.  Returns (actions int32 [n], logp float32 [n], entropy float32 [n])."""
     torch = _torch()
     lib = _lib.load()
     n = logits.shape[0]
@@ -77,8 +78,10 @@ def masked_sample(logits, obs_records, seed: int = 0, step: int = 0, env_offset:
     actions = torch.empty(n, dtype=torch.int32, device=dev) if actions is None else actions
     logp = torch.empty(n, dtype=torch.float32, device=dev) if logp is None else logp
     entropy = torch.empty(n, dtype=torch.float32, device=dev) if entropy is None else entropy
+    assert obs_records.dtype == torch.uint8 and obs_records.is_contiguous() and obs_records.shape[1] in (L.OBS_BYTES, L.SEL_BYTES)
+    mask_off = 160 if obs_records.shape[1] == L.OBS_BYTES else 8
     with torch.cuda.device(dev):
-        rc = lib.bgym_masked_sample(logits.data_ptr(), code, obs_records.data_ptr(),
+        rc = lib.bgym_masked_sample(logits.data_ptr(), code, obs_records.data_ptr() + mask_off, obs_records.shape[1],
                                     None if uniforms is None else uniforms.data_ptr(), seed & 0xFFFFFFFF, step, env_offset,
                                     actions.data_ptr(), logp.data_ptr(), entropy.data_ptr(), n,
                                     torch.cuda.current_stream().cuda_stream)

@@ -118,10 +118,15 @@ class BalatroVecEnv:
         self._gen_flags = L.GENERATORS[generator]
         n, dev = self.num_envs, self.device
         with torch.cuda.device(dev):
-            # env state = two dense record arrays (include/bgym.h): hot (144 B) and cold (176 B)
-            self.hot = torch.zeros((n, L.HOT_BYTES), dtype=torch.uint8, device=dev)
+            # env state = dense record arrays (include/bgym.h): hot (144 B), cold (176 B) and the toggle records
+            # (32 B: the select path's working set, holding THE copy of hot bytes 16..31); observations = 176-byte
+            # records + selection records (16 B: THE copy of selected_cards and the mask word).  `hot` and `obs_buf`
+            # (properties) give the record arrays with those fields folded back in.
+            self._hot = torch.zeros((n, L.HOT_BYTES), dtype=torch.uint8, device=dev)
+            self.tog = torch.zeros((n, L.TOG_BYTES), dtype=torch.uint8, device=dev)
             self.cold = torch.zeros((n, L.COLD_BYTES), dtype=torch.uint8, device=dev)
-            self.obs_buf = torch.zeros((n, L.OBS_BYTES), dtype=torch.uint8, device=dev)
+            self._obs = torch.zeros((n, L.OBS_BYTES), dtype=torch.uint8, device=dev)
+            self.sel = torch.zeros((n, L.SEL_BYTES), dtype=torch.uint8, device=dev)
             self.info_buf = torch.zeros((n, L.INFO_BYTES), dtype=torch.uint8, device=dev)
             self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
             self.terminated = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -133,6 +138,8 @@ class BalatroVecEnv:
             self._len_acc = torch.zeros(n, dtype=torch.int32, device=dev)
             self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
         self._obs_views: Optional[Dict[str, "torch.Tensor"]] = None
+        self._hot_whole = True        # hot bytes 16..31 equal the toggle records (False after a step)
+        self._obs_whole = True        # obs records' selected_cards / mask word equal the selection records
         self._obs_current = False     # obs_buf describes the current state (False after the state was changed from outside)
         self._step_count = 0
         self._pending_actions = None
@@ -152,14 +159,55 @@ class BalatroVecEnv:
         s = torch.where(s == 0, torch.ones_like(s), s)  # seed 0 is "random" in the reference (SURVEY Q1)
         return s.to(torch.int64)
 
+    # -- record arrays with their device-only side arrays folded in ------------------------------------
+    def _sync(self, what, direction):
+        with self.torch.cuda.device(self.device):
+            if what == "state":
+                rc = self.lib.bgym_sync_state(self._hot.data_ptr(), self.tog.data_ptr(), self.num_envs, direction, self._stream())
+            else:
+                rc = self.lib.bgym_sync_obs(self._obs.data_ptr(), self.sel.data_ptr(), self.num_envs, direction, self._stream())
+        _lib.check(rc, f"bgym_sync_{what}")
+
+    @property
+    def hot(self):
+        """[N, 144] hot records, whole (bgym_sync_state folds the toggle records' chunk back in first).  Code that
+        WRITES into the returned tensor must call state_written() afterwards."""
+        if not self._hot_whole:
+            self._sync("state", L.SYNC_TO_RECORDS)
+            self._hot_whole = True
+        return self._hot
+
+    @property
+    def obs_buf(self):
+        """[N, 176] observation records, whole (bgym_sync_obs folds the selection records back in first)."""
+        if not self._obs_whole:
+            self._sync("obs", L.SYNC_TO_RECORDS)
+            self._obs_whole = True
+        return self._obs
+
+    def state_written(self):
+        """The caller has rewritten hot / cold records from outside (through `hot`, `cold`, state_field views):
+        rebuild the toggle records and re-emit every observation."""
+        self._sync("state", L.SYNC_FROM_RECORDS)
+        self._hot_whole = True
+        return self.refresh_observations()
+
+    @property
+    def mask_words(self):
+        """(pointer to env 0's legal-action word, byte stride): the selection records, which every step keeps current."""
+        return self.sel.data_ptr() + 8, L.SEL_BYTES
+
     @property
     def obs(self) -> Dict[str, "object"]:
-        """The 31-key observation dict of the reference: zero-copy views of the obs records, plus
+        """The 31-key observation dict of the reference: zero-copy views of the obs records — selected_cards and the
+        mask word are views of the selection records, which is where a step keeps them current —, plus
         `action_mask_bits` (the packed legal-action word, int64) and `action_mask` — the reference's int8[N, 60]
         array, expanded from the word on access (it is not stored: 8 B instead of 60 B per record)."""
         if self._obs_views is None:
-            self._obs_views = {k: _field_view(self.torch, self.obs_buf, L.OBS_DTYPE, k) for k in L.OBS_KEYS if k != "action_mask"}
-            self._obs_views["action_mask_bits"] = _field_view(self.torch, self.obs_buf, L.OBS_DTYPE, "action_mask_bits")
+            self._obs_views = {k: _field_view(self.torch, self._obs, L.OBS_DTYPE, k) for k in L.OBS_KEYS
+                               if k not in ("action_mask", "selected_cards")}
+            self._obs_views["selected_cards"] = _field_view(self.torch, self.sel, L.SEL_DTYPE, "selected_cards")
+            self._obs_views["action_mask_bits"] = _field_view(self.torch, self.sel, L.SEL_DTYPE, "action_mask_bits")
             shifts = self.torch.arange(L.NUM_ACTIONS, device=self.device)
             bits = self._obs_views["action_mask_bits"]
             self._obs_views = _ObsViews(self._obs_views, lambda: ((bits.unsqueeze(1) >> shifts) & 1).to(self.torch.int8))
@@ -171,7 +219,7 @@ class BalatroVecEnv:
     def state_field(self, name):
         """Zero-copy typed view of one state field (from the hot or the cold record array)."""
         if name in L.HOT_FIELD_NAMES:
-            return _field_view(self.torch, self.hot, L.HOT_DTYPE, name)
+            return _field_view(self.torch, self.hot, L.HOT_DTYPE, name)      # `hot`: synced first
         return _field_view(self.torch, self.cold, L.COLD_DTYPE, name)
 
     # -- reset -------------------------------------------------------------------------------------
@@ -194,25 +242,28 @@ class BalatroVecEnv:
         if reset_mask is not None:
             reset_mask = torch.as_tensor(reset_mask, device=self.device).to(torch.uint8).contiguous()
         with torch.cuda.device(self.device):
-            rc = self.lib.bgym_reset(self.hot.data_ptr(), self.cold.data_ptr(), self.obs_buf.data_ptr(), self._ptr(reset_mask),
-                                     seeds32.data_ptr(), self._ptr(decks52), self.num_envs, self._gen_flags, self._stream())
+            rc = self.lib.bgym_reset(self._hot.data_ptr(), self.tog.data_ptr(), self.cold.data_ptr(), self._obs.data_ptr(),
+                                     self.sel.data_ptr(), self._ptr(reset_mask), seeds32.data_ptr(), self._ptr(decks52),
+                                     self.num_envs, self._gen_flags, self._stream())
         _lib.check(rc, "bgym_reset")
         self._keep = (seeds32, decks52, reset_mask)  # keep inputs alive until the stream has consumed them
+        self._hot_whole = self._obs_whole = True     # a reset (masked or not) writes whole records for every env
         self._obs_current = True
         return self.obs
 
     def refresh_observations(self):
-        """Re-emit every env's observation from its state records (after the state was changed from outside:
-        load_state, inject_numpy, randomize_c3).  bgym_reset with an all-zero reset mask resets nothing and
-        rewrites the observations."""
+        """Re-emit every env's observation from its state (hot + toggle + cold records).  bgym_reset with an all-zero
+        reset mask resets nothing and rewrites the observations.  After WRITING state records call state_written(),
+        which rebuilds the toggle records first."""
         torch = self.torch
         zero = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
         seeds = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            rc = self.lib.bgym_reset(self.hot.data_ptr(), self.cold.data_ptr(), self.obs_buf.data_ptr(), zero.data_ptr(),
-                                     seeds.data_ptr(), None, self.num_envs, 0, self._stream())
+            rc = self.lib.bgym_reset(self._hot.data_ptr(), self.tog.data_ptr(), self.cold.data_ptr(), self._obs.data_ptr(),
+                                     self.sel.data_ptr(), zero.data_ptr(), seeds.data_ptr(), None, self.num_envs, 0, self._stream())
         _lib.check(rc, "bgym_reset (observation refresh)")
         self._keep = (zero, seeds)
+        self._hot_whole = self._obs_whole = True
         self._obs_current = True
         return self.obs
 
@@ -238,11 +289,13 @@ class BalatroVecEnv:
             draws = torch.as_tensor(draws, device=self.device).contiguous()
             assert draws.dtype == torch.uint8 and draws.shape == (self.num_envs, L.DRAWS_BYTES)
         with torch.cuda.device(self.device):
-            rc = self.lib.bgym_step(self.hot.data_ptr(), self.cold.data_ptr(), act.data_ptr(), self._ptr(draws), self.obs_buf.data_ptr(),
+            rc = self.lib.bgym_step(self._hot.data_ptr(), self.tog.data_ptr(), self.cold.data_ptr(), act.data_ptr(), self._ptr(draws),
+                                    self._obs.data_ptr(), self.sel.data_ptr(),
                                     self.reward.data_ptr(), self.terminated.data_ptr(), self.truncated.data_ptr(),
                                     self.info_buf.data_ptr() if want_info else None, self.num_envs, flags, self._stream())
         _lib.check(rc, "bgym_step")
         self._keep = (act, draws)
+        self._hot_whole = self._obs_whole = False
         self._obs_current = True
         self._step_count += 1
         return self.obs, self.reward, self.terminated, self.truncated, self.info_buf
@@ -260,7 +313,7 @@ class BalatroVecEnv:
         """Uniform random legal action per env from the current observation's mask word."""
         out = self.actions if out is None else out
         with self.torch.cuda.device(self.device):
-            rc = self.lib.bgym_sample_actions(self.obs_buf.data_ptr(), out.data_ptr(), seed & 0xFFFFFFFF,
+            rc = self.lib.bgym_sample_actions(*self.mask_words, out.data_ptr(), seed & 0xFFFFFFFF,
                                               self._step_count, self.num_envs, self._stream())
         _lib.check(rc, "bgym_sample_actions")
         return out
@@ -282,13 +335,15 @@ class BalatroVecEnv:
         def launch():
             st = self._stream()
             if policy == "sampler":
-                rc = self.lib.bgym_sample_actions_ctr(self.obs_buf.data_ptr(), self.actions.data_ptr(), seed & 0xFFFFFFFF,
+                rc = self.lib.bgym_sample_actions_ctr(*self.mask_words, self.actions.data_ptr(), seed & 0xFFFFFFFF,
                                                       self._step_ctr.data_ptr(), self.num_envs, st)
                 _lib.check(rc, "bgym_sample_actions_ctr")
-            rc = self.lib.bgym_step(self.hot.data_ptr(), self.cold.data_ptr(), self.actions.data_ptr(), None, self.obs_buf.data_ptr(),
+            rc = self.lib.bgym_step(self._hot.data_ptr(), self.tog.data_ptr(), self.cold.data_ptr(), self.actions.data_ptr(), None,
+                                    self._obs.data_ptr(), self.sel.data_ptr(),
                                     self.reward.data_ptr(), self.terminated.data_ptr(), self.truncated.data_ptr(), None,
                                     self.num_envs, flags, st)
             _lib.check(rc, "bgym_step")
+            self._hot_whole = self._obs_whole = False
 
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
@@ -300,12 +355,18 @@ class BalatroVecEnv:
         with torch.cuda.graph(graph, stream=side):
             launch()
         self._graphs = getattr(self, "_graphs", []) + [graph]
-        return graph.replay
+
+        def replay():
+            graph.replay()
+            self._hot_whole = self._obs_whole = False
+
+        return replay
 
     def action_masks(self):
         """uint64 mask word per env computed from the state (bit a = action a legal), as int64."""
         with self.torch.cuda.device(self.device):
-            rc = self.lib.bgym_action_mask(self.hot.data_ptr(), self.cold.data_ptr(), self._mask64.data_ptr(), self.num_envs, self._stream())
+            rc = self.lib.bgym_action_mask(self._hot.data_ptr(), self.tog.data_ptr(), self.cold.data_ptr(), self._mask64.data_ptr(),
+                                           self.num_envs, self._stream())
         _lib.check(rc, "bgym_action_mask")
         return self._mask64
 
@@ -326,8 +387,10 @@ class BalatroVecEnv:
         return ckpt
 
     def load_state(self, ckpt):
-        self.hot.copy_(ckpt["hot"])
+        self._hot.copy_(ckpt["hot"])
         self.cold.copy_(ckpt["cold"])
+        self._sync("state", L.SYNC_FROM_RECORDS)
+        self._hot_whole = True
         self._step_count = ckpt["step_count"]
         self._ret_acc.copy_(ckpt["ret_acc"])
         self._len_acc.copy_(ckpt["len_acc"])
@@ -338,7 +401,9 @@ class BalatroVecEnv:
                 self._step_ctr = self.torch.zeros(1, dtype=self.torch.int64, device=self.device)
             self._step_ctr.copy_(ckpt["step_ctr"])
         if "obs" in ckpt:
-            self.obs_buf.copy_(ckpt["obs"])
+            self._obs.copy_(ckpt["obs"])
+            self._sync("obs", L.SYNC_FROM_RECORDS)
+            self._obs_whole = True
             self._obs_current = True
         else:
             self.refresh_observations()
@@ -348,9 +413,9 @@ class BalatroVecEnv:
         """Overwrite all state records from a host array of L.STATE_DTYPE."""
         assert state_np.dtype == L.STATE_DTYPE and state_np.shape == (self.num_envs,)
         raw = state_np.view(np.uint8).reshape(self.num_envs, L.STATE_BYTES)
-        self.hot.copy_(self.torch.from_numpy(np.ascontiguousarray(raw[:, :L.HOT_BYTES])))
+        self._hot.copy_(self.torch.from_numpy(np.ascontiguousarray(raw[:, :L.HOT_BYTES])))
         self.cold.copy_(self.torch.from_numpy(np.ascontiguousarray(raw[:, L.HOT_BYTES:])))
-        self.refresh_observations()
+        self.state_written()
 
     def state_numpy(self) -> np.ndarray:
         """Host copy of all envs as combined {hot, cold} records (L.STATE_DTYPE)."""
@@ -386,4 +451,140 @@ class BalatroVecEnv:
         deck = deck_view.to(torch.int64) & 63
         deck = deck | (enh << 6) | (ed << 10) | (seal << 13)
         deck_view.copy_(torch.where(deck >= 2 ** 15, deck - 2 ** 16, deck).to(torch.int16))
-        self.refresh_observations()
+        self.state_written()
+
+
+class HostMirror:
+    """Pinned-host copy of a slab's step results, kept current by OBSERVATION DELTAS instead of whole-array copies.
+
+    What a host-driven loop over `BalatroVecEnv` needs per step is the reference's step() result on the host:
+    observation, reward, terminated.  A step rewrites the 176-byte observation record only of the envs whose action was
+    not a card toggle (include/bgym.h, BgymSel), so per step this class moves
+        host -> device   actions                                                                4 B / env
+        device -> host   selection records (selected_cards, mask word), reward, terminated      16 + 8 + 1 B / env
+        device -> host   the rewritten observation records, packed on the device (bgym_pack_dirty_obs) and written
+                         into the pinned mirror by the GPU itself (bgym_scatter_dirty_obs, zero-copy stores, one
+                         aligned 128-byte line per record + 32 B for envs in or entering the shop)   128 (+32) B / changed env
+    against 189 B / env for whole arrays.  The device->host traffic of step t runs on a second stream while step t+1
+    is launched (double-buffered snapshots); `wait()` returns when the mirror holds the last step's results.
+
+        mirror = HostMirror(env); env.reset(); mirror.pull_all()
+        mirror.actions[:] = ...                      # host policy writes this step's actions
+        mirror.step()                                # H2D, step, D2H deltas (asynchronous)
+        mirror.wait(); mirror.core / .shop / .sel / .reward / .terminated are current
+
+    Layout of the mirror (include/bgym.h): `core` [n, 128] = chunks 0..5, 8, 9 of the observation record, `shop` [n, 32]
+    = chunks 6, 7, `sel` [n, 16] = selected_cards + mask word.  `obs_records()` reassembles whole L.OBS_DTYPE records
+    (a host-side copy); `field(name)` gives a zero-copy view of one observation field."""
+
+    def __init__(self, env: "BalatroVecEnv"):
+        torch = env.torch
+        self.env, self.torch = env, torch
+        n, dev = env.num_envs, env.device
+        pin = dict(pin_memory=True)
+        self.actions = torch.zeros(n, dtype=torch.int32, **pin)
+        self.core = torch.zeros((n, L.MIRROR_CORE_BYTES), dtype=torch.uint8, **pin)
+        self.shop = torch.zeros((n, L.MIRROR_SHOP_BYTES), dtype=torch.uint8, **pin)
+        self.sel = torch.zeros((n, L.SEL_BYTES), dtype=torch.uint8, **pin)
+        self.reward = torch.zeros(n, dtype=torch.float64, **pin)
+        self.terminated = torch.zeros(n, dtype=torch.uint8, **pin)
+        self._d_act = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.staging_bytes = 16 + ((n * 4 + 15) & ~15) + n * L.OBS_DELTA_BYTES
+        self._snap = [{"staging": torch.zeros(self.staging_bytes, dtype=torch.uint8, device=dev),
+                       "sel": torch.empty_like(env.sel), "rew": torch.empty_like(env.reward),
+                       "term": torch.empty_like(env.terminated)} for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._ready = [torch.cuda.Event() for _ in range(2)]
+        self._copied = [torch.cuda.Event() for _ in range(2)]
+        self._t = 0
+        self.h2d_bytes_per_step = 4 * n
+        self.dense_d2h_bytes_per_step = (L.SEL_BYTES + 8 + 1) * n
+
+    def _pack(self, snap, stream, everything: bool):
+        env = self.env
+        with self.torch.cuda.device(env.device):
+            rc = env.lib.bgym_pack_dirty_obs(env._obs.data_ptr(), snap["staging"].data_ptr(), env.num_envs, env.num_envs,
+                                             1 if everything else 0, stream.cuda_stream)
+        _lib.check(rc, "bgym_pack_dirty_obs")
+
+    def _scatter(self, snap, stream):
+        env = self.env
+        with self.torch.cuda.device(env.device):
+            rc = env.lib.bgym_scatter_dirty_obs(snap["staging"].data_ptr(), env.num_envs, self.core.data_ptr(), self.shop.data_ptr(),
+                                                stream.cuda_stream)
+        _lib.check(rc, "bgym_scatter_dirty_obs")
+
+    def pull_all(self):
+        """Fill the whole mirror from the device arrays (after reset / state injection)."""
+        env, torch = self.env, self.torch
+        main = torch.cuda.current_stream(env.device)
+        self._copy_stream.synchronize()
+        self._pack(self._snap[0], main, True)
+        self._scatter(self._snap[0], main)
+        self.sel.copy_(env.sel, non_blocking=True)
+        self.reward.copy_(env.reward, non_blocking=True)
+        self.terminated.copy_(env.terminated, non_blocking=True)
+        main.synchronize()
+
+    def step(self, want_info: bool = False):
+        env, torch = self.env, self.torch
+        b = self._t & 1
+        self._t += 1
+        snap = self._snap[b]
+        main = torch.cuda.current_stream(env.device)
+        self._d_act.copy_(self.actions, non_blocking=True)
+        env.step(self._d_act, want_info=want_info)
+        main.wait_event(self._copied[b])                       # the snapshot's previous contents have left the device
+        self._pack(snap, main, False)
+        snap["sel"].copy_(env.sel, non_blocking=True)
+        snap["rew"].copy_(env.reward, non_blocking=True)
+        snap["term"].copy_(env.terminated, non_blocking=True)
+        self._ready[b].record(main)
+        cs = self._copy_stream
+        with torch.cuda.stream(cs):
+            cs.wait_event(self._ready[b])
+            self.sel.copy_(snap["sel"], non_blocking=True)
+            self.reward.copy_(snap["rew"], non_blocking=True)
+            self.terminated.copy_(snap["term"], non_blocking=True)
+            self._scatter(snap, cs)
+            self._copied[b].record(cs)
+
+    def wait(self):
+        self._copy_stream.synchronize()
+        self.torch.cuda.current_stream(self.env.device).synchronize()
+
+    def delta_counts(self, which: int = None):
+        """(records, records with their shop chunks) the given (default: last) step's delta carried."""
+        b = ((self._t - 1) & 1) if which is None else which
+        st = self._snap[b]["staging"]
+        cnt = int(st[:4].view(self.torch.int32).item())
+        flagged = int((st[16:16 + 4 * cnt].view(self.torch.int32) < 0).sum().item()) if cnt > 0 else 0
+        return cnt, flagged
+
+    def dirty_count(self, which: int = None):
+        return self.delta_counts(which)[0]
+
+    def obs_records(self) -> np.ndarray:
+        """The mirror as whole observation records (L.OBS_DTYPE), a host-side copy."""
+        n = self.env.num_envs
+        core = self.core.numpy().reshape(n, 8, 16)
+        shop = self.shop.numpy().reshape(n, 2, 16)
+        raw = np.zeros((n, L.OBS_BYTES // 16, 16), dtype=np.uint8)
+        raw[:, list(L.MIRROR_CORE_CHUNKS)] = core
+        raw[:, list(L.MIRROR_SHOP_CHUNKS)] = shop
+        rec = raw.reshape(n, L.OBS_BYTES).reshape(-1).view(L.OBS_DTYPE)
+        s = self.sel.numpy().reshape(-1).view(L.SEL_DTYPE)
+        rec["selected_cards"] = s["selected_cards"]
+        rec["action_mask_bits"] = s["action_mask_bits"]
+        return rec
+
+    def field(self, name):
+        """numpy view of one observation field in the mirror: zero-copy for every field but shop_items / shop_costs (they
+        straddle the core / shop split: assembled copy) and 'action_mask' (expanded from the mask word)."""
+        if name == "action_mask":
+            return L.mask_from_bits(self.field("action_mask_bits"))
+        if name in L.SEL_DTYPE.names:
+            return self.sel.numpy().reshape(-1).view(L.SEL_DTYPE)[name]
+        if name in L.MIRROR_CORE_DTYPE.names:
+            return self.core.numpy().reshape(-1).view(L.MIRROR_CORE_DTYPE)[name]
+        return self.obs_records()[name]

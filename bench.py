@@ -218,6 +218,7 @@ def workload_config(args, n_envs):
 # our arm
 # -------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import numpy as np
     import torch
     import balatro_gym_b200 as b
     from balatro_gym_b200 import dist as bdist
@@ -291,7 +292,7 @@ def run_ours(args):
         ev[1 + 2 * k].record()          # step kernel bracket (same stream as the launches)
         env.step(acts[k], want_info=False)
         ev[2 + 2 * k].record()
-        launches += 5   # sampler + main pass + three gather passes
+        launches += 11  # sampler + main pass + seven level-1 list kernels + two level-2 list kernels
     ev[2 * K + 1].record()
     torch.cuda.synchronize(dev)
     bdist.barrier()
@@ -349,58 +350,47 @@ def run_ours(args):
     stats = bdist.allreduce_stats(env.stats.clone())
 
     # ---- e2e: the public API with HOST buffers (pinned), copies inside the timed region ----
-    # Every step: this step's actions come from pinned host memory (H2D), the step's results — observation records,
-    # rewards, terminations — go to pinned host memory (D2H).  The result copies of step t run on a second stream from
-    # a device-side snapshot while step t+1 is launched (double-buffered on both sides); the action path is synchronous.
-    # The timed region ends when the last step's results are in host memory.
+    # balatro_gym_b200.HostMirror: every step this step's actions come from pinned host memory (H2D) and the step's
+    # results reach pinned host memory (D2H): reward, terminated and the selection records (selected_cards, mask word)
+    # of every env, and the 176-byte observation record of every env whose record the step rewrote (an env whose
+    # action was a card toggle keeps its record) — packed on the device and written into the host mirror by the GPU.
+    # The copies of step t run on a second stream while step t+1 is launched; the action path is synchronous.  The
+    # timed region ends when the last step's results are in host memory; the mirror is then compared with the
+    # device arrays, whole.
     Ke = max(3, min(K, args.e2e_steps))
     numa = bind_host_memory_near_gpu(torch, dev)
-    h_act = torch.empty(n, dtype=torch.int32, pin_memory=True)
-    d_act = torch.empty(n, dtype=torch.int32, device=dev)
-    h_res = [{"obs": torch.empty((n, L.OBS_BYTES), dtype=torch.uint8, pin_memory=True),
-              "rew": torch.empty(n, dtype=torch.float64, pin_memory=True),
-              "term": torch.empty(n, dtype=torch.uint8, pin_memory=True)} for _ in range(2)]
-    d_snap = [{"obs": torch.empty_like(env.obs_buf), "rew": torch.empty_like(env.reward), "term": torch.empty_like(env.terminated)}
-              for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    snap_ready = [torch.cuda.Event() for _ in range(2)]
-    copied = [torch.cuda.Event() for _ in range(2)]
+    mirror = b.HostMirror(env)
     main_stream = torch.cuda.current_stream(dev)
+    mirror.pull_all()
+    dirty = []
 
     def e2e_step(t):
-        b2 = t & 1
-        env.sample_actions(seed=7)                       # the agent's decision, made on the device
-        h_act.copy_(env.actions, non_blocking=True)      # ... and handed to the host, as a host-driven loop has it
+        env.sample_actions(seed=7)                               # the agent's decision, made on the device
+        mirror.actions.copy_(env.actions, non_blocking=True)     # ... and handed to the host, as a host-driven loop has it
         main_stream.synchronize()
-        d_act.copy_(h_act, non_blocking=True)            # H2D of this step's inputs from pinned memory
-        env.step(d_act, want_info=False)
-        main_stream.wait_event(copied[b2])               # the snapshot buffer's previous contents have left the device
-        d_snap[b2]["obs"].copy_(env.obs_buf, non_blocking=True)
-        d_snap[b2]["rew"].copy_(env.reward, non_blocking=True)
-        d_snap[b2]["term"].copy_(env.terminated, non_blocking=True)
-        snap_ready[b2].record(main_stream)
-        with torch.cuda.stream(copy_stream):             # D2H of the step's results, overlapping the next step
-            copy_stream.wait_event(snap_ready[b2])
-            for k in ("obs", "rew", "term"):
-                h_res[b2][k].copy_(d_snap[b2][k], non_blocking=True)
-            copied[b2].record(copy_stream)
+        mirror.step()                                            # H2D actions, step, D2H deltas (second stream)
 
     for t in range(2):
         e2e_step(t)
-    torch.cuda.synchronize(dev)
+    mirror.wait()
     bdist.barrier()
     t0 = time.perf_counter()
     for t in range(Ke):
         e2e_step(t)
-    copy_stream.synchronize()
-    main_stream.synchronize()
+    mirror.wait()
     e2e_s = time.perf_counter() - t0
-    e2e_rank_gbs = (L.OBS_BYTES + 8 + 1 + 4 + 4) * n * Ke / e2e_s / 1e9     # this rank's PCIe traffic, both directions
+    dc = [mirror.delta_counts(k) for k in range(2)]
+    dirty_frac, shop_frac = sum(c[0] for c in dc) / (2.0 * n), sum(c[1] for c in dc) / (2.0 * n)
+    e2e_d2h = (mirror.dense_d2h_bytes_per_step + dirty_frac * n * L.MIRROR_CORE_BYTES + shop_frac * n * L.MIRROR_SHOP_BYTES
+               + 4 * n)    # + the action hand-off
+    e2e_rank_gbs = (e2e_d2h + mirror.h2d_bytes_per_step) * Ke / e2e_s / 1e9     # this rank's PCIe traffic, both directions
     e2e_s = bdist.max_over_ranks(e2e_s, dev)
     e2e_value = ws * n * Ke / e2e_s
-    # the host copy of the last step equals the device buffers
-    last = (Ke - 1) & 1
-    assert torch.equal(h_res[last]["obs"], env.obs_buf.cpu()) and torch.equal(h_res[last]["term"], env.terminated.cpu())
+    # the host mirror equals the device arrays (whole observation records: selection records folded in)
+    host_rec = mirror.obs_records()
+    assert np.array_equal(host_rec.view(np.uint8).reshape(n, L.OBS_BYTES), env.obs_buf.cpu().numpy()), "host mirror differs from the device observations"
+    assert torch.equal(mirror.terminated, env.terminated.cpu()) and torch.equal(mirror.reward, env.reward.cpu())
+    del mirror
 
     # ---- hands microbench (configs[1]) ----
     hands = None
@@ -432,7 +422,7 @@ def run_ours(args):
                      "traffic_unit": "dram__bytes_read.sum + dram__bytes_write.sum over the launches of one env-step (ncu --set full)",
                      "kernel": "one env-step = env_step_main_kernel + 9 env_step_list_kernel launches (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
                      "units_per_launch": n, "kernel_ms": step_kernel_ms_max, "peak_source": peak_src,
-                     "physical_bytes_per_unit": "main pass 144 (hot read) + 16 (the chunk a toggle changes) + 176 (obs) + 14 = 350 B per env; list kernels add the hot / cold / obs records of the ~25 % deferred envs at 64-byte DRAM granularity"},
+                     "physical_bytes_per_unit": "main pass 32 (toggle record) + 4 (action) read, 32 + 16 (selection record) + 10 written = 94 B per env; list kernels add the hot / toggle / cold / obs records of the ~25 % deferred envs at 64-byte DRAM granularity"},
         "timed_window": {"start": window_start, "end": window_end, "action_mix": action_mix, "phase_mix": phase_mix,
                          "note": "state statistics computed on the device from the env records right before / after the timed "
                                  "steps; action and phase mix are exact over all envs x steps of the timed window (rank 0 slab)"},
@@ -440,9 +430,13 @@ def run_ours(args):
                               "note": "round 1 applied the generator once from the host and autoreset built vanilla episodes: "
                                       "14 % generator state in its timed window (VERDICT r01 weak #1)"},
         "cpu_baseline": cpu_base,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (L.OBS_BYTES + 8 + 1 + 4) * n,
-                "steps": Ke, "pcie_gbs_rank0": e2e_rank_gbs, "host_memory": numa,
-                "note": "bound by the PCIe link: 189 B of results per env-step leave the device; result copies overlap the next step"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": e2e_d2h,
+                "steps": Ke, "pcie_gbs_rank0": e2e_rank_gbs, "host_memory": numa, "rewritten_record_frac": dirty_frac, "shop_chunk_frac": shop_frac,
+                "whole_array_d2h_bytes_per_step": (L.OBS_BYTES + 8 + 1 + 4) * n,
+                "note": "HostMirror: reward + terminated + selection record (25 B) of every env and the observation record "
+                        "(one aligned 128-byte line, + 32 B of shop chunks where they can have changed) of every env whose record the step "
+                        "rewrote reach pinned host memory each step, written by the GPU itself (zero-copy stores); the mirror is "
+                        "checked against the device arrays after the timed region; bound by the PCIe link"},
         "gpu_launches": launches,
         "clocks": clk,
         "fused_rollout": {"value": fused_value, "unit": UNIT, "ms_per_step": fused_ms / K,

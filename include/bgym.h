@@ -33,13 +33,16 @@
 extern "C" {
 #endif
 
-#define BGYM_ABI_VERSION 1
+#define BGYM_ABI_VERSION 2
 
 /* ---- sizes ------------------------------------------------------------- */
 #define BGYM_STATE_BYTES 320
 #define BGYM_HOT_BYTES   144
 #define BGYM_COLD_BYTES  176
 #define BGYM_OBS_BYTES   176
+#define BGYM_TOG_BYTES   32    /* BgymTog: the card-select working set of an env (device only) */
+#define BGYM_SEL_BYTES   16    /* BgymSel: the two observation fields a card select changes (device only) */
+#define BGYM_OBS_DELTA_BYTES 160   /* bytes 0..159 of a BgymObs: all of it but the mask word (carried by BgymSel) and padding */
 #define BGYM_INFO_BYTES  32
 #define BGYM_DRAWS_BYTES 256
 #define BGYM_NUM_ACTIONS 60
@@ -217,6 +220,30 @@ typedef struct BgymHot { BGYM_HOT_FIELDS } BgymHot;
 typedef struct BgymCold { BGYM_COLD_FIELDS } BgymCold;
 typedef struct BgymState { BGYM_HOT_FIELDS BGYM_COLD_FIELDS } BgymState;
 
+/* ---- toggle record (32 B, device only) ------------------------------------------
+ * Card-select toggles are ~75 % of the steps of a random-legal rollout, and a toggle reads and writes nothing but
+ * the selection.  tog[n] is the dense array the select path runs on — the main pass of bgym_step reads 32 B and
+ * writes 32 + 16 B per env instead of a 144-byte hot record and a 176-byte observation record:
+ *   bytes  0..15  THE AUTHORITATIVE COPY of bytes 16..31 of the hot record (hand_n .. ep_len, "chunk 1").  A toggle
+ *                 updates it here only: after a step, hot[i] bytes 16..31 may be stale for envs whose last actions were
+ *                 toggles; every other byte of hot[i] is always current.  bgym_sync_state(BGYM_SYNC_TO_RECORDS) copies
+ *                 the chunk back into the hot records (checkpoints, host copies, tests).
+ *   bytes 16..31  a read-only summary of what else the select path needs: discards_left, cons_n (the PLAY-phase
+ *                 action mask, balatro_env_2.py:1426-1445), guard = (ante > 100 || chips_scored > 10^9) (:619-623),
+ *                 the Philox key word (fused random policy).  Rewritten by every pass that rewrites the hot record;
+ *                 bgym_sync_state(BGYM_SYNC_FROM_RECORDS) rebuilds the whole toggle record from a hot record the
+ *                 caller has written. */
+typedef struct BgymTog {
+  uint8_t hand_n; uint8_t hand_size; uint8_t sel_n; uint8_t highlight_mask; uint32_t sel_order;   /*  0 = hot bytes 16..23 */
+  uint8_t face_down_mask; uint8_t phase; uint8_t round; uint8_t boss_type; uint32_t ep_len;       /*  8 = hot bytes 24..31 */
+  uint8_t discards_left;  /* 16 */
+  uint8_t cons_n;         /* 17 */
+  uint8_t guard;          /* 18 ante > 100 || chips_scored > 1 000 000 000 */
+  uint8_t _pad0;          /* 19 */
+  uint32_t rng_seed;      /* 20 */
+  uint8_t _pad1[8];       /* 24 */
+} BgymTog;
+
 /* ---- observation record (176 B) ---------------------------------------------
  * The 31 keys the reference actually emits (balatro_env_2.py:1488-1531), same dtypes
  * except selected_cards / face_down_cards (int8 here, platform int there) and the action
@@ -259,6 +286,19 @@ typedef struct BgymObs {
   uint64_t action_mask_bits;    /* 160 bit a = action a legal (obs['action_mask'][a], :1522) */
   uint8_t  _pad1[8];            /* 168 (record stride 176 = 11 x 16 B)  */
 } BgymObs;
+
+/* ---- selection record (16 B, device only) ------------------------------------------
+ * The two observation fields a card select changes, as a dense array sel[n]: THE AUTHORITATIVE COPY of
+ * BgymObs.selected_cards and BgymObs.action_mask_bits.  Every step writes sel[i] for every env; the 176-byte record
+ * obs[i] is rewritten only when another field changed (every action except a toggle or a rejected action; reset;
+ * autoreset) — with all of its fields, these two included.  After a step, obs[i].selected_cards and
+ * obs[i].action_mask_bits may therefore be stale for envs whose last actions were toggles; device-side consumers
+ * (bgym_sample_actions, bgym_masked_sample) read the mask word from sel, and bgym_sync_obs(BGYM_SYNC_TO_RECORDS)
+ * makes the records whole. */
+typedef struct BgymSel {
+  int8_t   selected_cards[8];   /* 0 = BgymObs.selected_cards   */
+  uint64_t action_mask_bits;    /* 8 = BgymObs.action_mask_bits */
+} BgymSel;
 
 /* ---- per-step info record (32 B) --------------------------------------------
  * Fixed-width restatement of the numeric entries of the reference's info dict
@@ -313,16 +353,55 @@ int bgym_device_count(void);
 /* reset: for every env i with reset_mask == NULL || reset_mask[i] != 0 build a fresh episode
  * (balatro_env_2.py:505-558).  seeds[i] keys the native Philox stream.  decks52 != NULL
  * (n x 52 card codes) replays a supplied permutation (the reference's shuffle stream);
- * NULL = native Fisher-Yates from Philox.  obs may be NULL with BGYM_FLAG_NO_OBS. */
-int bgym_reset(BgymHot* hot, BgymCold* cold, BgymObs* obs, const uint8_t* reset_mask, const uint32_t* seeds,
-               const uint8_t* decks52, int64_t n, int flags, void* stream);
+ * NULL = native Fisher-Yates from Philox.  Writes hot, tog, cold and — unless BGYM_FLAG_NO_OBS — obs and sel of the
+ * envs it resets.  An env the mask leaves alone keeps its state (its toggle record is taken as current) and gets its
+ * observation record and selection record re-emitted whole. */
+int bgym_reset(BgymHot* hot, BgymTog* tog, BgymCold* cold, BgymObs* obs, BgymSel* sel, const uint8_t* reset_mask,
+               const uint32_t* seeds, const uint8_t* decks52, int64_t n, int flags, void* stream);
 
 /* step: one BalatroEnv.step per env (balatro_env_2.py:616-1064, 1174-1392).
  * draws == NULL -> native Philox mode.  info may be NULL. truncated is always 0.
- * `actions` is read (written instead with BGYM_FLAG_RANDOM_POLICY). */
-int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* draws, BgymObs* obs,
+ * `actions` is read (written instead with BGYM_FLAG_RANDOM_POLICY).
+ * State: hot / tog / cold as described at BgymTog (a toggle touches tog only).  Observation: sel[i] is written for
+ * every env, obs[i] for the envs whose other fields changed (see BgymSel); obs and sel must be the arrays the previous
+ * reset / step of these envs wrote.  obs and sel may both be NULL with BGYM_FLAG_NO_OBS. */
+int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, const BgymDraws* draws, BgymObs* obs, BgymSel* sel,
               double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
               int64_t n, int flags, void* stream);
+
+/* Coherence between the record arrays and their device-only side arrays (BgymTog, BgymSel).
+ *   BGYM_SYNC_TO_RECORDS    copy the authoritative fields into the records: hot[i] bytes 16..31 <- tog[i];
+ *                           obs[i].selected_cards / .action_mask_bits <- sel[i].  After it the records are whole
+ *                           (what checkpoints, host copies and the parity tests read).
+ *   BGYM_SYNC_FROM_RECORDS  the caller has (re)written the records: rebuild tog[i] from hot[i] / sel[i] from obs[i]. */
+enum { BGYM_SYNC_TO_RECORDS = 0, BGYM_SYNC_FROM_RECORDS = 1 };
+int bgym_sync_state(BgymHot* hot, BgymTog* tog, int64_t n, int direction, void* stream);
+int bgym_sync_obs(BgymObs* obs, BgymSel* sel, int64_t n, int direction, void* stream);
+
+/* Observation deltas for a HOST mirror (the e2e path: ~65 B per env-step cross PCIe instead of 189 B).
+ * A step rewrites obs[i] only for the envs on its deferred lists; these two calls move exactly those records into a
+ * mirror the GPU writes itself (zero-copy stores into pinned host memory: no host thread touches the records).
+ * Mirror layout — chosen so that a record lands as ONE aligned 128-byte line, which is what makes zero-copy stores run at
+ * the link's full rate (tools/exp/zc_probe.cu: 52 GB/s, against 35-42 GB/s for 176-byte records at a 176-byte stride):
+ *   core[n]  BGYM_MIRROR_CORE_BYTES = 128 per env: the 16-byte chunks 0..5, 8, 9 of BgymObs, in that order
+ *            (bytes 0..95 and 128..159: everything but the middle of the shop block and the mask word)
+ *   shop[n]  BGYM_MIRROR_SHOP_BYTES = 32 per env: chunks 6, 7 (bytes 96..127: shop_items[1..9], shop_costs[0..6]) — all
+ *            zero outside SHOP phase, so an env that was and stays in PLAY phase does not send them
+ *   the mask word and selected_cards come from a copy of the selection array (BgymSel), reward / terminated from theirs.
+ *   bgym_pack_dirty_obs     (on the stream bgym_step ran on, before that stream's next bgym_step) gathers the rewritten
+ *                           records into `staging` (device): int32 count at byte 0, uint32 [cap] from byte 16 (env index,
+ *                           bit 31 = shop chunks included), then from byte 16 + 4 * cap rounded up to 16 the first
+ *                           BGYM_OBS_DELTA_BYTES of each record, [cap].  cap >= n is required (a step that kept no lists —
+ *                           slabs at or below BGYM_OPT_SMALL_SLAB — stages all n records, and so does all != 0, which
+ *                           needs no previous step: the first fill of a mirror); BGYM_DIRTY_STAGING_BYTES(cap) is the size.
+ *   bgym_scatter_dirty_obs  (any stream, once the pack has completed) writes staged record k to mirror_core[index] and,
+ *                           when flagged, mirror_shop[index]; both may be device memory or PINNED HOST memory
+ *                           (128- / 32-byte aligned). */
+#define BGYM_MIRROR_CORE_BYTES 128
+#define BGYM_MIRROR_SHOP_BYTES 32
+#define BGYM_DIRTY_STAGING_BYTES(cap) (16 + (((size_t)(cap) * 4 + 15) & ~(size_t)15) + (size_t)(cap) * BGYM_OBS_DELTA_BYTES)
+int bgym_pack_dirty_obs(const BgymObs* obs, void* staging, int64_t cap, int64_t n, int all, void* stream);
+int bgym_scatter_dirty_obs(const void* staging, int64_t cap, void* mirror_core, void* mirror_shop, void* stream);
 
 /* bgym_step keeps a few bytes per env of device scratch (work lists) per (device, stream) it is called on, sized for
  * the largest slab seen; this gives the scratch of `stream` on the current device back.  Call it once the stream's last
@@ -330,11 +409,13 @@ int bgym_step(BgymHot* hot, BgymCold* cold, int32_t* actions, const BgymDraws* d
 int bgym_release_stream(void* stream);
 
 /* action mask as one 64-bit word per env (balatro_env_2.py:1426-1471) */
-int bgym_action_mask(const BgymHot* hot, const BgymCold* cold, uint64_t* mask, int64_t n, void* stream);
+int bgym_action_mask(const BgymHot* hot, const BgymTog* tog, const BgymCold* cold, uint64_t* mask, int64_t n, void* stream);
 
-/* uniform random legal action per env from BgymObs.action_mask_bits (the policy the
- * reference benchmarks are driven with: random legal actions from obs['action_mask']) */
-int bgym_sample_actions(const BgymObs* obs, int32_t* actions, uint32_t seed, uint64_t step,
+/* uniform random legal action per env from its legal-action word (the policy the reference benchmarks are driven
+ * with: random legal actions from obs['action_mask']).  mask_words points at env 0's word, mask_stride is the
+ * distance in bytes between consecutive envs' words: (&sel->action_mask_bits, sizeof(BgymSel)) for the selection
+ * array a step keeps current, (&obs->action_mask_bits, sizeof(BgymObs)) for whole observation records. */
+int bgym_sample_actions(const uint64_t* mask_words, int64_t mask_stride, int32_t* actions, uint32_t seed, uint64_t step,
                         int64_t n, void* stream);
 
 /* hand scoring: classify cards (balatro_game.py:40-93), per-card chip values
@@ -358,8 +439,8 @@ int bgym_episode_stats(const double* reward, const uint8_t* terminated, double* 
 
 /* bgym_sample_actions with the step number kept on the device (*step_counter is read by the sampler and then
  * incremented): the form a CUDA graph can replay, since a replayed launch cannot take a new kernel argument */
-int bgym_sample_actions_ctr(const BgymObs* obs, int32_t* actions, uint32_t seed, uint64_t* step_counter,
-                            int64_t n, void* stream);
+int bgym_sample_actions_ctr(const uint64_t* mask_words, int64_t mask_stride, int32_t* actions, uint32_t seed,
+                            uint64_t* step_counter, int64_t n, void* stream);
 
 /* ---- on-device PPO rollout collection (config 5) ------------------ */
 /* Observation records -> the dense input of the reference's BalatroFeaturesExtractor.forward
@@ -382,12 +463,12 @@ int bgym_policy_first_layer(const BgymObs* obs, const void* wt_hand, const void*
                             const float* bias, void* out, int64_t n, void* stream);
 
 /* Masked categorical policy head: for each env, softmax over logits[60] restricted to the legal
- * actions of obs[i].action_mask_bits; draws one action by inverse CDF, returns its log-probability
+ * actions of its mask word (mask_words / mask_stride as in bgym_sample_actions); draws one action by inverse CDF, returns its log-probability
  * and the entropy of the masked distribution (entropy may be NULL).  The uniform comes from
  * uniforms[i] when given, else from Philox keyed (seed, sample key) at counter (env_offset + i, step).
  * logits: n x 60, dtype BGYM_DT_F32 (16-byte aligned rows) or BGYM_DT_BF16 (8-byte aligned).
  * An env with no legal action gets action 0, logp 0, entropy 0. */
-int bgym_masked_sample(const void* logits, int dtype, const BgymObs* obs, const float* uniforms,
+int bgym_masked_sample(const void* logits, int dtype, const uint64_t* mask_words, int64_t mask_stride, const float* uniforms,
                        uint32_t seed, uint64_t step, int64_t env_offset,
                        int32_t* actions, float* logp, float* entropy, int64_t n, void* stream);
 
@@ -415,8 +496,9 @@ int bgym_vec_reset_masked_host(BgymVec* v, const uint8_t* reset_mask, const uint
 int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draws, BgymObs* obs_out,
                        double* reward_out, uint8_t* terminated_out, uint8_t* truncated_out,
                        BgymInfo* info_out, int flags);
-/* raw device pointers of the handle (for zero-copy consumers) */
-int bgym_vec_pointers(BgymVec* v, void** hot, void** cold, void** obs, void** reward, void** terminated);
+/* raw device pointers of the handle (for zero-copy consumers; any of the outputs may be NULL).  hot / obs are subject
+ * to the staleness rules of BgymTog / BgymSel: read the toggle and selection arrays next to them. */
+int bgym_vec_pointers(BgymVec* v, void** hot, void** tog, void** cold, void** obs, void** sel, void** reward, void** terminated);
 /* copy state records to / from host (checkpointing: save_state/load_state,
  * balatro_env_2.py:1575-1615) */
 int bgym_vec_get_state(BgymVec* v, BgymState* host_out);

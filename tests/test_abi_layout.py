@@ -19,15 +19,17 @@ def test_library_exports_all_declared_symbols():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.bgym_abi_version() == 1
+    assert lib.bgym_abi_version() == 2
     assert lib.bgym_device_count() >= 0
 
 
 def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
-    assert lib.bgym_step(None, None, None, None, None, None, None, None, None, 4, 0, None) < 0
+    assert lib.bgym_step(None, None, None, None, None, None, None, None, None, None, None, 4, 0, None) < 0
     assert b"bgym_step" in lib.bgym_last_error()
-    assert lib.bgym_reset(None, None, None, None, None, None, 4, 0, None) < 0
+    assert lib.bgym_reset(None, None, None, None, None, None, None, None, 4, 0, None) < 0
+    assert lib.bgym_sync_state(None, None, 4, 0, None) < 0 and lib.bgym_sync_obs(None, None, 4, 0, None) < 0
+    assert lib.bgym_pack_dirty_obs(None, None, 4, 4, 0, None) < 0 and lib.bgym_scatter_dirty_obs(None, 4, None, None, None) < 0
 
 
 def _c_offsets(struct, fields):
@@ -48,7 +50,8 @@ def _c_offsets(struct, fields):
 def test_struct_layouts_match_numpy_dtypes():
     for struct, dt in (("BgymState", L.STATE_DTYPE), ("BgymHot", L.HOT_DTYPE), ("BgymCold", L.COLD_DTYPE),
                        ("BgymObs", L.OBS_DTYPE), ("BgymInfo", L.INFO_DTYPE),
-                       ("BgymDraws", L.DRAWS_DTYPE), ("BgymScoreCtx", L.SCORE_CTX_DTYPE)):
+                       ("BgymDraws", L.DRAWS_DTYPE), ("BgymScoreCtx", L.SCORE_CTX_DTYPE),
+                       ("BgymTog", L.TOG_DTYPE), ("BgymSel", L.SEL_DTYPE)):
         size, offs = _c_offsets(struct, dt.names)
         assert size == dt.itemsize, struct
         assert offs == [dt.fields[n][1] for n in dt.names], struct
@@ -56,6 +59,16 @@ def test_struct_layouts_match_numpy_dtypes():
     for dt, size in ((L.HOT_DTYPE, 144), (L.COLD_DTYPE, 176), (L.OBS_DTYPE, 176)):
         assert dt.itemsize == size and dt.itemsize % 32 == 16
     assert L.STATE_DTYPE.itemsize == 320 == L.HOT_BYTES + L.COLD_BYTES
+    # the toggle record's first half is hot bytes 16..31, field for field; the selection record's fields are the
+    # observation record's
+    for name in L.TOG_OWNED_FIELDS:
+        assert L.TOG_DTYPE.fields[name][1] + 16 == L.HOT_DTYPE.fields[name][1], name
+        assert L.TOG_DTYPE.fields[name][0] == L.HOT_DTYPE.fields[name][0], name
+    assert sorted(L.HOT_DTYPE.fields[n][1] for n in L.TOG_OWNED_FIELDS)[0] == 16
+    assert sum(L.HOT_DTYPE.fields[n][0].itemsize for n in L.TOG_OWNED_FIELDS) == 16
+    for name in L.SEL_DTYPE.names:
+        assert L.SEL_DTYPE.fields[name][0] == L.OBS_DTYPE.fields[name][0], name
+    assert L.TOG_DTYPE.itemsize == 32 and L.SEL_DTYPE.itemsize == 16
 
 
 def test_product_never_imports_the_oracle():

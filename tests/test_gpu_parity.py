@@ -220,16 +220,18 @@ def test_step_without_observations(torch, step_path):
     flags = L.FLAG_AUTORESET | 4
     for t in range(120):
         x.step(random_policy=True)
-        rc = lib.bgym_step(y.hot.data_ptr(), y.cold.data_ptr(), y.actions.data_ptr(), None, None, y.reward.data_ptr(),
-                           y.terminated.data_ptr(), y.truncated.data_ptr(), y.info_buf.data_ptr(), n, flags | L.FLAG_NO_OBS,
-                           torch.cuda.current_stream().cuda_stream)
+        rc = lib.bgym_step(y._hot.data_ptr(), y.tog.data_ptr(), y.cold.data_ptr(), y.actions.data_ptr(), None, None, None,
+                           y.reward.data_ptr(), y.terminated.data_ptr(), y.truncated.data_ptr(), y.info_buf.data_ptr(), n,
+                           flags | L.FLAG_NO_OBS, torch.cuda.current_stream().cuda_stream)
         assert rc == 0
+        y._hot_whole = False
     torch.cuda.synchronize()
+    assert torch.equal(x.tog, y.tog)
     for name in ("hot", "cold", "reward", "terminated", "actions", "info_buf"):
         assert torch.equal(getattr(x, name), getattr(y, name)), name
     # and obs = NULL without the flag is an argument error, not a crash
-    assert lib.bgym_step(y.hot.data_ptr(), y.cold.data_ptr(), y.actions.data_ptr(), None, None, y.reward.data_ptr(),
-                         y.terminated.data_ptr(), y.truncated.data_ptr(), None, n, flags, None) < 0
+    assert lib.bgym_step(y._hot.data_ptr(), y.tog.data_ptr(), y.cold.data_ptr(), y.actions.data_ptr(), None, None, None,
+                         y.reward.data_ptr(), y.terminated.data_ptr(), y.truncated.data_ptr(), None, n, flags, None) < 0
 
 
 def test_refresh_observations_after_state_injection(torch):
@@ -262,13 +264,16 @@ def test_empty_slab_calls_are_noops(torch):
     lib = b.load()
     z = torch.zeros(16, dtype=torch.uint8, device="cuda")
     p = z.data_ptr()
-    assert lib.bgym_reset(p, p, p, None, p, None, 0, 0, None) == 0
-    assert lib.bgym_step(p, p, p, None, p, p, p, p, None, 0, 0, None) == 0
-    assert lib.bgym_action_mask(p, p, p, 0, None) == 0
+    assert lib.bgym_reset(p, p, p, p, p, None, p, None, 0, 0, None) == 0
+    assert lib.bgym_step(p, p, p, p, None, p, p, p, p, p, None, 0, 0, None) == 0
+    assert lib.bgym_action_mask(p, p, p, p, 0, None) == 0
+    assert lib.bgym_sync_state(p, p, 0, 0, None) == 0 and lib.bgym_sync_obs(p, p, 0, 1, None) == 0
+    assert lib.bgym_sample_actions(p, 16, p, 1, 0, 0, None) == 0
     assert lib.bgym_featurize(p, p, 0, 0, None) == 0
     assert lib.bgym_gae(p, p, p, 0.99, 0.95, p, p, 0, 0, None) == 0
     # argument errors come back as negative codes with a message, never a crash
-    assert lib.bgym_step(None, p, p, None, p, p, p, p, None, 4, 0, None) < 0
+    assert lib.bgym_sample_actions(p, 12, p, 1, 0, 4, None) < 0      # stride not a multiple of 8
+    assert lib.bgym_step(None, p, p, p, None, p, p, p, p, p, None, 4, 0, None) < 0
     assert b"bgym_step" in lib.bgym_last_error()
     assert lib.bgym_featurize(p, p, 4, 7, None) < 0
 
@@ -659,3 +664,55 @@ def test_host_handle_replays_reference_trace_with_draws(torch, name):
     assert n == int(tr["length"].sum())
     # the trace really goes through the shop and boss blinds
     assert (tr["state"]["phase"] == L.PHASE_SHOP).any() and (tr["state"]["boss_type"] != 0).any()
+
+
+def test_side_arrays_and_host_mirror_track_the_records(torch, step_path):
+    """The toggle / selection arrays (BgymTog, BgymSel) against the whole records, and HostMirror — the pinned-host copy
+    kept current by observation deltas — against the device arrays, over a rollout with autoresets, masked-out actions
+    and the c4 generator.  The oracle (whole records, no side arrays) steps the same actions: after every step the
+    synced device records equal its records, and the host mirror equals both."""
+    from balatro_gym_b200 import BalatroVecEnv, HostMirror
+    from oracle import coracle
+    n = 6000
+    v = BalatroVecEnv(n, seed=31, generator="c4")
+    v.reset()
+    ov = coracle.OracleVec(n)
+    coracle.reset(ov.state, ov.obs, np.arange(31, 31 + n), flags=L.GENERATORS["c4"])
+    m = HostMirror(v)
+    m.pull_all()
+    rng = np.random.default_rng(5)
+    total_dirty = total_shop = 0
+    for t in range(90):
+        v.sample_actions(seed=17)
+        act = v.actions.cpu().numpy().copy()
+        wild = rng.random(n) < 0.05
+        act[wild] = rng.integers(-2, 64, size=int(wild.sum()))          # rejected / out-of-range actions change nothing
+        m.actions.copy_(torch.from_numpy(act))
+        m.step(want_info=True)
+        oobs, orew, oterm = ov.step(act.astype(np.int32), flags=L.FLAG_AUTORESET | L.GENERATORS["c4"])[:3]
+        m.wait()
+        total_dirty += m.delta_counts()[0]
+        total_shop += m.delta_counts()[1]
+        # side arrays vs whole records (device): the sync folds them in; nothing else changes
+        tog = v.tog.cpu().numpy().reshape(-1).view(L.TOG_DTYPE)
+        st = v.state_numpy()
+        for name in L.TOG_OWNED_FIELDS:
+            assert np.array_equal(tog[name], st[name]), (t, name)
+        assert np.array_equal(tog["discards_left"], st["discards_left"]) and np.array_equal(tog["cons_n"], st["cons_n"])
+        assert np.array_equal(tog["rng_seed"], st["rng_seed"])
+        assert np.array_equal(tog["guard"] != 0, (st["ante"] > 100) | (st["chips_scored"] > 1000000000))
+        assert np.array_equal(st.view(np.uint8), ov.state.view(np.uint8)), t
+        dev_obs = v.obs_numpy()
+        assert np.array_equal(dev_obs.view(np.uint8), oobs.view(np.uint8)), t
+        # host mirror vs device
+        assert np.array_equal(m.obs_records().view(np.uint8), dev_obs.view(np.uint8)), t
+        for name in ("hand", "money", "hand_levels", "phase", "shop_items", "shop_costs", "selected_cards", "action_mask_bits"):
+            assert np.array_equal(m.field(name), dev_obs[name]), (t, name)
+        assert np.array_equal(m.field("action_mask"), L.mask_from_bits(dev_obs["action_mask_bits"]))
+        assert np.array_equal(m.reward.numpy(), v.reward.cpu().numpy()) and np.array_equal(m.terminated.numpy(), v.terminated.cpu().numpy())
+        assert np.array_equal(m.terminated.numpy() != 0, oterm != 0)
+    if step_path == "multi_pass":
+        assert 0 < total_dirty < 0.6 * 90 * n       # deltas, not whole arrays
+        assert 0 < total_shop < 0.5 * total_dirty   # PLAY-phase envs do not resend their (all-zero) shop chunks
+    else:
+        assert total_dirty == 90 * n                # the one-launch step keeps no lists: every record is staged
