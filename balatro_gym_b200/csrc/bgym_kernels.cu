@@ -576,25 +576,27 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const uint8_t* __restrict
   }
 }
 // staged record k -> the mirror (BGYM_MIRROR_CORE_BYTES = 128: chunks 0..5, 8, 9 of the record at core[e]; BGYM_MIRROR_SHOP_BYTES
-// = 32: chunks 6, 7 at shop[e]).  A core record is one aligned 128-byte line: zero-copy stores into pinned host memory then
-// run at the link's full rate (measured 52 GB/s against 35-42 GB/s for 176-byte records at a 176-byte stride, tools/exp/zc_probe.cu).
+// = 32: chunks 6, 7 at shop[e]).  A core record is one aligned 128-byte line WRITTEN BY ONE STORE INSTRUCTION (8 lanes x 16 B,
+// four records per warp): zero-copy stores into pinned host memory then run at the link's full rate (measured 52 GB/s against
+// 35-42 GB/s for 176-byte records at a 176-byte stride, tools/exp/zc_probe.cu; the same line written by two instructions —
+// 96 + 32 bytes — fell to 25 GB/s).
 __global__ void __launch_bounds__(256) scatter_dirty_kernel(const uint8_t* __restrict__ staging, long long cap, uint8_t* __restrict__ core,
                                                             uint8_t* __restrict__ shop) {
   const int total = *reinterpret_cast<const int*>(staging);
   const uint32_t* idx = reinterpret_cast<const uint32_t*>(staging + 16);
   const uint8_t* rec = staging + dirty_rec_offset(cap);
-  const int lane = threadIdx.x & 31, sub = lane / DELTA_LANES, part = lane - sub * DELTA_LANES;
+  const int lane = threadIdx.x & 31, sub = lane >> 3, part = lane & 7;
+  const int chunk = part < 6 ? part : part + 2;
   const long long warp_gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long warp_cnt = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long k0 = warp_gid * DELTA_PER_WARP; k0 < total; k0 += warp_cnt * DELTA_PER_WARP) {
+  for (long long k0 = warp_gid * 4; k0 < total; k0 += warp_cnt * 4) {
     const long long k = k0 + sub;
-    if (sub < DELTA_PER_WARP && k < total && k < cap) {
+    if (k < total && k < cap) {
       const uint32_t w = __ldg(idx + k);
       const long long e = w & 0x7FFFFFFFu;
-      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(rec + k * BGYM_OBS_DELTA_BYTES) + part);
-      if (part < 6) reinterpret_cast<uint4*>(core + e * BGYM_MIRROR_CORE_BYTES)[part] = q;
-      else if (part >= 8) reinterpret_cast<uint4*>(core + e * BGYM_MIRROR_CORE_BYTES)[part - 2] = q;
-      else if (w & 0x80000000u) reinterpret_cast<uint4*>(shop + e * BGYM_MIRROR_SHOP_BYTES)[part - 6] = q;
+      const uint4* src = reinterpret_cast<const uint4*>(rec + k * BGYM_OBS_DELTA_BYTES);
+      reinterpret_cast<uint4*>(core + e * BGYM_MIRROR_CORE_BYTES)[part] = __ldcs(src + chunk);
+      if ((w & 0x80000000u) && part < 2) reinterpret_cast<uint4*>(shop + e * BGYM_MIRROR_SHOP_BYTES)[part] = __ldcs(src + 6 + part);
     }
   }
 }

@@ -387,8 +387,10 @@ def run_ours(args):
     e2e_s = bdist.max_over_ranks(e2e_s, dev)
     e2e_value = ws * n * Ke / e2e_s
     # the host mirror equals the device arrays (whole observation records: selection records folded in)
-    host_rec = mirror.obs_records()
-    assert np.array_equal(host_rec.view(np.uint8).reshape(n, L.OBS_BYTES), env.obs_buf.cpu().numpy()), "host mirror differs from the device observations"
+    host_rec, dev_rec = mirror.obs_records(), env.obs_numpy()
+    for name in L.OBS_DTYPE.names:
+        assert np.array_equal(host_rec[name], dev_rec[name]), f"host mirror differs from the device observations in {name}"
+    del host_rec, dev_rec
     assert torch.equal(mirror.terminated, env.terminated.cpu()) and torch.equal(mirror.reward, env.reward.cpu())
     del mirror
 
