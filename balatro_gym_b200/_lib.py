@@ -87,10 +87,10 @@ SYMBOLS = {
     "bgym_device_count": (_i32, []),
     "bgym_set_option": (_i32, [_i32, _i64]),
     "bgym_reset": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
-    "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bgym_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "bgym_sync_state": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "bgym_sync_obs": (_i32, [_vp, _vp, _i64, _i32, _vp]),
-    "bgym_pack_dirty_obs": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp]),
+    "bgym_pack_dirty_obs": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "bgym_scatter_dirty_obs": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "bgym_release_stream": (_i32, [_vp]),
     "bgym_action_mask": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),

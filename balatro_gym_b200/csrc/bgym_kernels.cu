@@ -36,6 +36,7 @@ struct StepArgs {
   const BgymDraws* draws;    // n (nullable)
   uint8_t* obs;              // n x 176 (nullable)
   uint8_t* sel;              // n x 16  selection records (BgymSel), nullable together with obs
+  uint8_t* obs_dirty;        // n (nullable): |= BGYM_OBS_DIRTY* for every env whose observation record is rewritten
   double* reward;            // n
   uint8_t* terminated;       // n
   uint8_t* truncated;        // n (nullable)
@@ -528,23 +529,90 @@ __global__ void sync_obs_kernel(uint8_t* obs, uint8_t* sel, long long n, int fro
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t dirty_rec_offset(long long cap) { return 16 + (((size_t)cap * 4 + 15) & ~(size_t)15); }
 // A staged record is bytes 0..159 of the observation record (BGYM_OBS_DELTA_BYTES): bytes 160..175 are the mask word,
-// which travels in the selection record, and padding.  10 lanes move one record (16 B each), three records per warp.
-// Bit 31 of a staged index says that the record's SHOP CHUNKS (6, 7: shop_items[1..9], shop_costs[0..6]) may differ from
-// what the mirror holds: they are all zero outside SHOP phase, so an env that was and stays in PLAY phase (the PLAY /
-// CONS / DISCARD lists unless the hand advanced the round) does not send them.
+// which travels in the selection record, and padding.  Bit 31 of a staged index says that the record's SHOP CHUNKS
+// (6, 7: shop_items[1..9], shop_costs[0..6]) may differ from what the mirror holds (BGYM_OBS_DIRTY_SHOP).
+// The records are staged IN ASCENDING ENV ORDER: a stream compaction of the per-env dirty bytes the step wrote
+// (count per block of PACK_ENVS envs -> exclusive prefix -> indices), then a coalesced record move, 10 lanes per record.
+// Ascending order matters to the zero-copy scatter that follows: 128-byte stores into pinned host memory ran at
+// 51.5 GB/s in address order and 42.4 GB/s in random order (tools/exp/zc_probe.cu).
 constexpr int DELTA_LANES = BGYM_OBS_DELTA_BYTES / 16, DELTA_PER_WARP = 32 / DELTA_LANES;
-constexpr int OBS_OFF_PHASE = 155;
-__device__ __forceinline__ bool list_is_play_phase(int l) { return l == L_PLAY || l == L_CONS || l == L_DISCARD; }
-__global__ void __launch_bounds__(256) pack_dirty_kernel(const uint8_t* __restrict__ obs, const int* __restrict__ lists,
-                                                         const int* __restrict__ counters, long long part_cap,
-                                                         uint8_t* __restrict__ staging, long long cap) {
-  int base[N_LISTS_L1 + 1];
-  base[0] = 0;
+constexpr int PACK_THREADS = 256, PACK_PER_THREAD = 16, PACK_ENVS = PACK_THREADS * PACK_PER_THREAD;
+__device__ __forceinline__ int dirty_count16(const uint4 f) {      // number of bytes with BGYM_OBS_DIRTY set
+  return __popc(f.x & 0x01010101u) + __popc(f.y & 0x01010101u) + __popc(f.z & 0x01010101u) + __popc(f.w & 0x01010101u);
+}
+__device__ __forceinline__ uint4 load_flags16(const uint8_t* dirty, long long e0, long long n, bool all) {
+  if (all) {
+    uint32_t w[4];
 #pragma unroll
-  for (int l = 0; l < N_LISTS_L1; l++) base[l + 1] = base[l] + counters[l * PART_CTR_STRIDE];
-  const int total = base[N_LISTS_L1];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(staging) = total;
+    for (int q = 0; q < 4; q++) {
+      w[q] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (e0 + 4 * q + k < n) w[q] |= (uint32_t)(BGYM_OBS_DIRTY | BGYM_OBS_DIRTY_SHOP) << (8 * k);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (e0 + 16 <= n) return *reinterpret_cast<const uint4*>(dirty + e0);
+  uint32_t w[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 16 && e0 + k < n; k++) w[k >> 2] |= (uint32_t)dirty[e0 + k] << (8 * (k & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__global__ void __launch_bounds__(PACK_THREADS) pack_count_kernel(const uint8_t* __restrict__ dirty, int* __restrict__ counts, long long n, int all) {
+  const long long e0 = ((long long)blockIdx.x * PACK_THREADS + threadIdx.x) * PACK_PER_THREAD;
+  int c = e0 < n ? dirty_count16(load_flags16(dirty, e0, n, all != 0)) : 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  __shared__ int part[PACK_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < PACK_THREADS / 32; w++) t += part[w];
+    counts[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(PACK_THREADS) pack_index_kernel(uint8_t* __restrict__ dirty, const int* __restrict__ counts,
+                                                                  uint8_t* __restrict__ staging, long long cap, long long n, int all) {
+  __shared__ int part[PACK_THREADS / 32];
+  __shared__ int s_base;
+  // exclusive prefix of the block counts before this block
+  int b = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += PACK_THREADS) b += counts[i];
+  for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < PACK_THREADS / 32; w++) t += part[w];
+    s_base = t;
+    if (blockIdx.x == gridDim.x - 1) *reinterpret_cast<int*>(staging) = t + counts[blockIdx.x];
+  }
+  __syncthreads();
+  const long long e0 = ((long long)blockIdx.x * PACK_THREADS + threadIdx.x) * PACK_PER_THREAD;
+  const uint4 f = e0 < n ? load_flags16(dirty, e0, n, all != 0) : make_uint4(0, 0, 0, 0);
+  const int c = dirty_count16(f);
+  // block-exclusive prefix of c
+  int incl = c;
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 31) part[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  int off = s_base + incl - c;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); w++) off += part[w];
   uint32_t* idx_out = reinterpret_cast<uint32_t*>(staging + 16);
+  const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const uint32_t fl = (fw[k >> 2] >> (8 * (k & 3))) & 0xFF;
+    if (fl & BGYM_OBS_DIRTY) {
+      if (off < cap) idx_out[off] = (uint32_t)(e0 + k) | ((fl & BGYM_OBS_DIRTY_SHOP) ? 0x80000000u : 0u);
+      off++;
+    }
+  }
+  if (!all && c && e0 + 16 <= n) *reinterpret_cast<uint4*>(dirty + e0) = make_uint4(0, 0, 0, 0);     // consumed
+  else if (!all && c) for (int k = 0; k < 16 && e0 + k < n; k++) dirty[e0 + k] = 0;
+}
+__global__ void __launch_bounds__(256) pack_records_kernel(const uint8_t* __restrict__ obs, uint8_t* __restrict__ staging, long long cap) {
+  const int total = *reinterpret_cast<const int*>(staging);
+  const uint32_t* idx = reinterpret_cast<const uint32_t*>(staging + 16);
   uint8_t* rec_out = staging + dirty_rec_offset(cap);
   const int lane = threadIdx.x & 31, sub = lane / DELTA_LANES, part = lane - sub * DELTA_LANES;
   const long long warp_gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -552,27 +620,9 @@ __global__ void __launch_bounds__(256) pack_dirty_kernel(const uint8_t* __restri
   for (long long k0 = warp_gid * DELTA_PER_WARP; k0 < total; k0 += warp_cnt * DELTA_PER_WARP) {
     const long long k = k0 + sub;
     if (sub < DELTA_PER_WARP && k < total && k < cap) {
-      int l = 0;
-#pragma unroll
-      for (int t = 1; t < N_LISTS_L1; t++) l += k >= base[t];
-      const int e = __ldg(lists + (long long)l * part_cap + (k - base[l]));
-      const uint8_t* rec = obs + (long long)e * BGYM_OBS_BYTES;
-      if (part == 0) idx_out[k] = (uint32_t)e | ((!list_is_play_phase(l) || rec[OBS_OFF_PHASE] != BGYM_PHASE_PLAY) ? 0x80000000u : 0u);
-      reinterpret_cast<uint4*>(rec_out + k * BGYM_OBS_DELTA_BYTES)[part] = __ldcs(reinterpret_cast<const uint4*>(rec) + part);
+      const long long e = idx[k] & 0x7FFFFFFFu;
+      reinterpret_cast<uint4*>(rec_out + k * BGYM_OBS_DELTA_BYTES)[part] = __ldcs(reinterpret_cast<const uint4*>(obs + e * BGYM_OBS_BYTES) + part);
     }
-  }
-}
-// every record is staged, index = identity, shop chunks included (a one-launch step of a small slab keeps no lists; a
-// mirror is filled for the first time)
-__global__ void __launch_bounds__(256) pack_all_kernel(const uint8_t* __restrict__ obs, uint8_t* __restrict__ staging, long long cap, long long n) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(staging) = (int)n;
-  uint32_t* idx_out = reinterpret_cast<uint32_t*>(staging + 16);
-  uint4* rec_out = reinterpret_cast<uint4*>(staging + dirty_rec_offset(cap));
-  const long long chunks = n * DELTA_LANES;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
-    const long long k = i / DELTA_LANES;
-    rec_out[i] = __ldcs(reinterpret_cast<const uint4*>(obs + k * BGYM_OBS_BYTES) + (i - k * DELTA_LANES));
-    if (i < n) idx_out[i] = (uint32_t)i | 0x80000000u;
   }
 }
 // staged record k -> the mirror (BGYM_MIRROR_CORE_BYTES = 128: chunks 0..5, 8, 9 of the record at core[e]; BGYM_MIRROR_SHOP_BYTES
@@ -660,7 +710,6 @@ static bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintp
 // (device, stream) in use; bgym_release_stream() gives a set back
 constexpr int PART_SIDE_STREAMS = 6;   // the seven level-1 list kernels run concurrently: launch stream + six forked ones
 struct PartScratch { bool used; int dev; void* stream; long long cap; int* lists; int* counters; uint16_t* aux;
-                     long long last_n; bool last_lists;   // the last bgym_step on this stream: slab size, and whether it kept lists
 
                      cudaStream_t side[PART_SIDE_STREAMS]; cudaEvent_t ev_fork, ev_fork2, ev_side[PART_SIDE_STREAMS]; bool streams_ok; };
 constexpr int BGYM_MAX_SCRATCH = 64;
@@ -741,7 +790,7 @@ int bgym_reset(BgymHot* hot, BgymTog* tog, BgymCold* cold, BgymObs* obs, BgymSel
 }
 
 int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, const BgymDraws* draws, BgymObs* obs, BgymSel* sel,
-              double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
+              uint8_t* obs_dirty, double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
               int64_t n, int flags, void* stream) {
   if (n < 0 || !hot || !tog || !cold || !reward || !terminated)
     return set_err(BGYM_E_ARG, "bgym_step: null hot/tog/cold/reward/terminated or negative n");
@@ -764,7 +813,8 @@ int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, cons
   a.actions_out = (flags & BGYM_FLAG_RANDOM_POLICY) ? actions : nullptr;
   a.draws = draws; a.obs = reinterpret_cast<uint8_t*>(obs); a.sel = reinterpret_cast<uint8_t*>(sel);
   if (!obs || !sel) { a.obs = nullptr; a.sel = nullptr; }
-  sc->last_n = n;
+  a.obs_dirty = a.obs ? obs_dirty : nullptr;
+
   a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.info = info;
   a.n = n; a.flags = flags;
   a.part_lists = sc->lists; a.part_counters = sc->counters; a.part_aux = sc->aux; a.part_cap = sc->cap;
@@ -778,8 +828,7 @@ int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, cons
   if (timing && tcalls == 0 && tsum[0] == 0) for (int i = 0; i < NEV; i++) cudaEventCreate(&tev[i]);
   if (timing) cudaEventRecord(tev[0], s);
   // small slabs: one launch (bgym_step_part.cuh, env_step_small_kernel); BGYM_SMALL_N overrides the threshold
-  sc->last_lists = !(n <= small_slab_threshold() && !timing);
-  if (!sc->last_lists) {
+  if (n <= small_slab_threshold() && !timing) {
     env_step_small_kernel<<<tile_grid(n, GATHER_WARPS, GATHER_CTAS_PER_SM), GATHER_WARPS * 32, GATHER_CTA_SMEM, s>>>(a);
     return cuda_rc(cudaGetLastError(), "bgym_step launch");
   }
@@ -929,27 +978,20 @@ int bgym_sync_obs(BgymObs* obs, BgymSel* sel, int64_t n, int direction, void* st
   return cuda_rc(cudaGetLastError(), "bgym_sync_obs launch");
 }
 
-int bgym_pack_dirty_obs(const BgymObs* obs, void* staging, int64_t cap, int64_t n, int all, void* stream) {
-  if (!obs || !staging || cap <= 0 || n <= 0) return set_err(BGYM_E_ARG, "bgym_pack_dirty_obs: bad arguments");
-  if (misaligned(obs, 16) || misaligned(staging, 16)) return set_err(BGYM_E_ALIGN, "bgym_pack_dirty_obs: obs/staging must be 16-byte aligned");
+int bgym_pack_dirty_obs(const BgymObs* obs, uint8_t* obs_dirty, void* staging, void* scratch, int64_t cap, int64_t n, void* stream) {
+  if (!obs || !staging || !scratch || cap <= 0 || n <= 0) return set_err(BGYM_E_ARG, "bgym_pack_dirty_obs: bad arguments");
+  if (misaligned(obs, 16) || misaligned(staging, 16) || misaligned(obs_dirty, 16) || misaligned(scratch, 4))
+    return set_err(BGYM_E_ALIGN, "bgym_pack_dirty_obs: obs/staging/obs_dirty must be 16-byte aligned");
   if (cap < n) return set_err(BGYM_E_ARG, "bgym_pack_dirty_obs: cap must be at least n");
   int rc = ensure_device_setup();
   if (rc) return rc;
-  PartScratch* sc = nullptr;
-  if (!all) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(g_mu);
-    for (int i = 0; i < BGYM_MAX_SCRATCH; i++)
-      if (g_scratch[i].used && g_scratch[i].dev == dev && g_scratch[i].stream == stream) sc = &g_scratch[i];
-    if (!sc || sc->last_n != n) return set_err(BGYM_E_ARG, "bgym_pack_dirty_obs: no bgym_step of n envs has run on this stream");
-  }
-  if (all || !sc->last_lists) {      // (a one-launch step of a small slab keeps no lists: every record may have changed)
-    pack_all_kernel<<<g_sm_count * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<uint8_t*>(staging), cap, n);
-    return cuda_rc(cudaGetLastError(), "bgym_pack_dirty_obs launch");
-  }
-  pack_dirty_kernel<<<g_sm_count * 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), sc->lists, sc->counters, sc->cap,
-                                                                     reinterpret_cast<uint8_t*>(staging), cap);
+  const int all = obs_dirty ? 0 : 1;
+  const long long blocks = (n + PACK_ENVS - 1) / PACK_ENVS;
+  if (blocks > 0x7fffffffLL) return set_err(BGYM_E_ARG, "bgym_pack_dirty_obs: n too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  pack_count_kernel<<<(int)blocks, PACK_THREADS, 0, s>>>(obs_dirty, reinterpret_cast<int*>(scratch), n, all);
+  pack_index_kernel<<<(int)blocks, PACK_THREADS, 0, s>>>(obs_dirty, reinterpret_cast<const int*>(scratch), reinterpret_cast<uint8_t*>(staging), cap, n, all);
+  pack_records_kernel<<<g_sm_count * 8, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<uint8_t*>(staging), cap);
   return cuda_rc(cudaGetLastError(), "bgym_pack_dirty_obs launch");
 }
 
@@ -1198,7 +1240,7 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
     CK(cudaMemcpyAsync(v->d_draws, v->h_draws, v->n * BGYM_DRAWS_BYTES, cudaMemcpyHostToDevice, v->stream));
   }
   int rc = bgym_step(reinterpret_cast<BgymHot*>(v->d_hot), reinterpret_cast<BgymTog*>(v->d_tog), reinterpret_cast<BgymCold*>(v->d_cold), v->d_actions,
-                     draws ? v->d_draws : nullptr, reinterpret_cast<BgymObs*>(v->d_obs), reinterpret_cast<BgymSel*>(v->d_sel),
+                     draws ? v->d_draws : nullptr, reinterpret_cast<BgymObs*>(v->d_obs), reinterpret_cast<BgymSel*>(v->d_sel), nullptr,
                      v->d_reward, v->d_term, v->d_trunc, v->d_info, v->n, flags & ~BGYM_FLAG_NO_OBS, v->stream);
   if (rc) return rc;
   if (obs_out) {

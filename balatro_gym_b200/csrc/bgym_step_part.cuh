@@ -268,10 +268,18 @@ constexpr int STG_RO = 0, STG_RW = 0;
 __host__ __device__ constexpr int list_smem_bytes(int list) { return (list >= 7 /*level 2*/ || STG_RW || STG_RO) ? GATHER_CTA_SMEM : 0; }
 
 // the whole observation of env e: the 176-byte record AND the selection record (both carry selected_cards and the mask)
-__device__ __forceinline__ void emit_observation(const StepArgs& a, long long e, const Hot& h, const uint8_t* cold) {
+// shop_changed: the record's shop chunks (shop_items / shop_costs) can differ from what they were before the step
+__device__ __forceinline__ void emit_observation(const StepArgs& a, long long e, const Hot& h, const uint8_t* cold, bool shop_changed) {
   const uint64_t m = action_mask(h, cold);
   write_obs(h, cold, m, a.obs + e * BGYM_OBS_BYTES);
   *reinterpret_cast<uint4*>(a.sel + e * BGYM_SEL_BYTES) = sel_words(h, m);
+  if (a.obs_dirty) a.obs_dirty[e] = (uint8_t)(BGYM_OBS_DIRTY | (shop_changed ? BGYM_OBS_DIRTY_SHOP : 0));
+}
+// the shop block of the observation is all zeros outside SHOP phase and is not touched by a joker sale
+__device__ __forceinline__ bool shop_block_changed(int phase_before, int phase_after, int action) {
+  if (phase_before != BGYM_PHASE_SHOP && phase_after != BGYM_PHASE_SHOP) return false;
+  return !(phase_before == BGYM_PHASE_SHOP && phase_after == BGYM_PHASE_SHOP &&
+           action >= BGYM_A_SELL_JOKER_BASE && action < BGYM_A_SELL_JOKER_BASE + 5);
 }
 
 // One tile: lane `lane` serves listed env `e`, WORKING ON THE RECORDS WHERE THEY LIE: the hot record is lifted into
@@ -315,6 +323,7 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool
     action = __ldcg(a.actions + e);
     load_hot(hot, tog, h);
   }
+  const int phase0 = active ? h.phase : 0;
   if (STAGE) { cp_async_wait_all(); __syncwarp(); }
   if (active) m0 = action_mask(h, cold);
   BGYM_CTA_SYNC();
@@ -358,7 +367,7 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool
     if (!DEFER && want_reset) hot_clear_extra(hot);
   }
   BGYM_CTA_SYNC();
-  if (emit_obs) emit_observation(a, e, h, cold);
+  if (emit_obs) emit_observation(a, e, h, cold, (!DEFER && want_reset) || shop_block_changed(phase0, h.phase, action));
   if (STAGE) {
     __syncwarp();     // a cooperative reset (small-slab kernel) writes other lanes' slots
     if (store_state && !(MODE & TM_COLD_CLEAN)) cold_from_smem(cold_g, cold_slot);
@@ -380,7 +389,7 @@ __device__ __forceinline__ void advance_tile(const StepArgs& a, long long e, boo
   cp_async_wait_all();
   step_env_advance(h, hot, cold_slot, a.draws ? a.draws + e : nullptr, snap);
   store_hot(hot, a.tog + e * BGYM_TOG_BYTES, h);
-  if (with_obs) emit_observation(a, e, h, cold_slot);
+  if (with_obs) emit_observation(a, e, h, cold_slot, true);     // a round advance enters the shop
   cold_from_smem(cold_g, cold_slot);
 }
 
@@ -391,6 +400,7 @@ __device__ __forceinline__ void reset_tile(const StepArgs& a, long long e, bool 
   __syncwarp();
   if (!active) return;
   uint8_t* hot = a.hot + e * BGYM_HOT_BYTES;
+  const int old_phase = a.tog[e * BGYM_TOG_BYTES + 9];        // BgymTog.phase of the episode that just ended
   const uint32_t old_seed = __ldcg(reinterpret_cast<const uint32_t*>(hot + 120));
   const uint32_t episode = __ldcg(reinterpret_cast<const uint32_t*>(hot + 132)) + 1;
   const uint32_t new_seed = next_episode_seed(old_seed);
@@ -402,7 +412,7 @@ __device__ __forceinline__ void reset_tile(const StepArgs& a, long long e, bool 
   reset_blocks_serial(cold_slot, new_seed, nullptr, gen);      // deck build + shuffle in the lane's shared-memory slot
   store_hot(hot, a.tog + e * BGYM_TOG_BYTES, h);
   hot_clear_extra(hot);
-  if (with_obs) emit_observation(a, e, h, cold_slot);
+  if (with_obs) emit_observation(a, e, h, cold_slot, old_phase == BGYM_PHASE_SHOP);
   cold_from_smem(a.cold + e * BGYM_COLD_BYTES, cold_slot);
 }
 

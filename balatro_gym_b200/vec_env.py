@@ -127,6 +127,7 @@ class BalatroVecEnv:
             self.cold = torch.zeros((n, L.COLD_BYTES), dtype=torch.uint8, device=dev)
             self._obs = torch.zeros((n, L.OBS_BYTES), dtype=torch.uint8, device=dev)
             self.sel = torch.zeros((n, L.SEL_BYTES), dtype=torch.uint8, device=dev)
+            self.obs_dirty = None     # [n] uint8, allocated by a HostMirror: which observation records a step rewrote
             self.info_buf = torch.zeros((n, L.INFO_BYTES), dtype=torch.uint8, device=dev)
             self.reward = torch.zeros(n, dtype=torch.float64, device=dev)
             self.terminated = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -290,7 +291,7 @@ class BalatroVecEnv:
             assert draws.dtype == torch.uint8 and draws.shape == (self.num_envs, L.DRAWS_BYTES)
         with torch.cuda.device(self.device):
             rc = self.lib.bgym_step(self._hot.data_ptr(), self.tog.data_ptr(), self.cold.data_ptr(), act.data_ptr(), self._ptr(draws),
-                                    self._obs.data_ptr(), self.sel.data_ptr(),
+                                    self._obs.data_ptr(), self.sel.data_ptr(), self._ptr(self.obs_dirty),
                                     self.reward.data_ptr(), self.terminated.data_ptr(), self.truncated.data_ptr(),
                                     self.info_buf.data_ptr() if want_info else None, self.num_envs, flags, self._stream())
         _lib.check(rc, "bgym_step")
@@ -339,7 +340,7 @@ class BalatroVecEnv:
                                                       self._step_ctr.data_ptr(), self.num_envs, st)
                 _lib.check(rc, "bgym_sample_actions_ctr")
             rc = self.lib.bgym_step(self._hot.data_ptr(), self.tog.data_ptr(), self.cold.data_ptr(), self.actions.data_ptr(), None,
-                                    self._obs.data_ptr(), self.sel.data_ptr(),
+                                    self._obs.data_ptr(), self.sel.data_ptr(), self._ptr(self.obs_dirty),
                                     self.reward.data_ptr(), self.terminated.data_ptr(), self.truncated.data_ptr(), None,
                                     self.num_envs, flags, st)
             _lib.check(rc, "bgym_step")
@@ -489,6 +490,9 @@ class HostMirror:
         self.reward = torch.zeros(n, dtype=torch.float64, **pin)
         self.terminated = torch.zeros(n, dtype=torch.uint8, **pin)
         self._d_act = torch.zeros(n, dtype=torch.int32, device=dev)
+        if env.obs_dirty is None:
+            env.obs_dirty = torch.zeros(n, dtype=torch.uint8, device=dev)     # from now on every step flags the records it rewrites
+        self._scratch = torch.zeros((n + 4095) // 4096 + 4, dtype=torch.int32, device=dev)
         self.staging_bytes = 16 + ((n * 4 + 15) & ~15) + n * L.OBS_DELTA_BYTES
         self._snap = [{"staging": torch.zeros(self.staging_bytes, dtype=torch.uint8, device=dev),
                        "sel": torch.empty_like(env.sel), "rew": torch.empty_like(env.reward),
@@ -503,8 +507,9 @@ class HostMirror:
     def _pack(self, snap, stream, everything: bool):
         env = self.env
         with self.torch.cuda.device(env.device):
-            rc = env.lib.bgym_pack_dirty_obs(env._obs.data_ptr(), snap["staging"].data_ptr(), env.num_envs, env.num_envs,
-                                             1 if everything else 0, stream.cuda_stream)
+            rc = env.lib.bgym_pack_dirty_obs(env._obs.data_ptr(), None if everything else env.obs_dirty.data_ptr(),
+                                             snap["staging"].data_ptr(), self._scratch.data_ptr(), env.num_envs, env.num_envs,
+                                             stream.cuda_stream)
         _lib.check(rc, "bgym_pack_dirty_obs")
 
     def _scatter(self, snap, stream):
@@ -521,6 +526,7 @@ class HostMirror:
         self._copy_stream.synchronize()
         self._pack(self._snap[0], main, True)
         self._scatter(self._snap[0], main)
+        env.obs_dirty.zero_()
         self.sel.copy_(env.sel, non_blocking=True)
         self.reward.copy_(env.reward, non_blocking=True)
         self.terminated.copy_(env.terminated, non_blocking=True)

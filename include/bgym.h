@@ -364,9 +364,13 @@ int bgym_reset(BgymHot* hot, BgymTog* tog, BgymCold* cold, BgymObs* obs, BgymSel
  * `actions` is read (written instead with BGYM_FLAG_RANDOM_POLICY).
  * State: hot / tog / cold as described at BgymTog (a toggle touches tog only).  Observation: sel[i] is written for
  * every env, obs[i] for the envs whose other fields changed (see BgymSel); obs and sel must be the arrays the previous
- * reset / step of these envs wrote.  obs and sel may both be NULL with BGYM_FLAG_NO_OBS. */
+ * reset / step of these envs wrote.  obs and sel may both be NULL with BGYM_FLAG_NO_OBS.
+ * obs_dirty (n bytes, may be NULL): obs_dirty[i] is set to BGYM_OBS_DIRTY (| BGYM_OBS_DIRTY_SHOP when the record's shop block
+ * — shop_items / shop_costs — can have changed) for every env whose observation RECORD this step rewrote; other bytes are
+ * left alone.  The consumer of the deltas (bgym_pack_dirty_obs) clears them. */
+enum { BGYM_OBS_DIRTY = 1, BGYM_OBS_DIRTY_SHOP = 2 };
 int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, const BgymDraws* draws, BgymObs* obs, BgymSel* sel,
-              double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
+              uint8_t* obs_dirty, double* reward, uint8_t* terminated, uint8_t* truncated, BgymInfo* info,
               int64_t n, int flags, void* stream);
 
 /* Coherence between the record arrays and their device-only side arrays (BgymTog, BgymSel).
@@ -379,7 +383,7 @@ int bgym_sync_state(BgymHot* hot, BgymTog* tog, int64_t n, int direction, void* 
 int bgym_sync_obs(BgymObs* obs, BgymSel* sel, int64_t n, int direction, void* stream);
 
 /* Observation deltas for a HOST mirror (the e2e path: ~65 B per env-step cross PCIe instead of 189 B).
- * A step rewrites obs[i] only for the envs on its deferred lists; these two calls move exactly those records into a
+ * A step rewrites obs[i] only for the envs it flags in obs_dirty; these two calls move exactly those records into a
  * mirror the GPU writes itself (zero-copy stores into pinned host memory: no host thread touches the records).
  * Mirror layout — chosen so that a record lands as ONE aligned 128-byte line, which is what makes zero-copy stores run at
  * the link's full rate (tools/exp/zc_probe.cu: 52 GB/s, against 35-42 GB/s for 176-byte records at a 176-byte stride):
@@ -388,19 +392,21 @@ int bgym_sync_obs(BgymObs* obs, BgymSel* sel, int64_t n, int direction, void* st
  *   shop[n]  BGYM_MIRROR_SHOP_BYTES = 32 per env: chunks 6, 7 (bytes 96..127: shop_items[1..9], shop_costs[0..6]) — all
  *            zero outside SHOP phase, so an env that was and stays in PLAY phase does not send them
  *   the mask word and selected_cards come from a copy of the selection array (BgymSel), reward / terminated from theirs.
- *   bgym_pack_dirty_obs     (on the stream bgym_step ran on, before that stream's next bgym_step) gathers the rewritten
- *                           records into `staging` (device): int32 count at byte 0, uint32 [cap] from byte 16 (env index,
- *                           bit 31 = shop chunks included), then from byte 16 + 4 * cap rounded up to 16 the first
- *                           BGYM_OBS_DELTA_BYTES of each record, [cap].  cap >= n is required (a step that kept no lists —
- *                           slabs at or below BGYM_OPT_SMALL_SLAB — stages all n records, and so does all != 0, which
- *                           needs no previous step: the first fill of a mirror); BGYM_DIRTY_STAGING_BYTES(cap) is the size.
+ *   bgym_pack_dirty_obs     (after the step, on its stream) gathers the records flagged in obs_dirty, IN ASCENDING ENV ORDER
+ *                           (zero-copy stores in address order run 20 % faster than in random order), into `staging`
+ *                           (device): int32 count at byte 0, uint32 [cap] from byte 16 (env index, bit 31 = shop chunks
+ *                           included), then from byte 16 + 4 * cap rounded up to 16 the first BGYM_OBS_DELTA_BYTES of each
+ *                           record, [cap]; the flags it consumed are cleared.  obs_dirty == NULL stages every record (the
+ *                           first fill of a mirror).  cap >= n is required; BGYM_DIRTY_STAGING_BYTES(cap) is the size of
+ *                           `staging`, BGYM_DIRTY_SCRATCH_BYTES(n) that of `scratch` (device, block counts).
  *   bgym_scatter_dirty_obs  (any stream, once the pack has completed) writes staged record k to mirror_core[index] and,
  *                           when flagged, mirror_shop[index]; both may be device memory or PINNED HOST memory
  *                           (128- / 32-byte aligned). */
 #define BGYM_MIRROR_CORE_BYTES 128
 #define BGYM_MIRROR_SHOP_BYTES 32
 #define BGYM_DIRTY_STAGING_BYTES(cap) (16 + (((size_t)(cap) * 4 + 15) & ~(size_t)15) + (size_t)(cap) * BGYM_OBS_DELTA_BYTES)
-int bgym_pack_dirty_obs(const BgymObs* obs, void* staging, int64_t cap, int64_t n, int all, void* stream);
+#define BGYM_DIRTY_SCRATCH_BYTES(n) ((((size_t)(n) + 4095) / 4096) * 4)
+int bgym_pack_dirty_obs(const BgymObs* obs, uint8_t* obs_dirty, void* staging, void* scratch, int64_t cap, int64_t n, void* stream);
 int bgym_scatter_dirty_obs(const void* staging, int64_t cap, void* mirror_core, void* mirror_shop, void* stream);
 
 /* bgym_step keeps a few bytes per env of device scratch (work lists) per (device, stream) it is called on, sized for

@@ -25,11 +25,11 @@ def test_library_exports_all_declared_symbols():
 
 def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
-    assert lib.bgym_step(None, None, None, None, None, None, None, None, None, None, None, 4, 0, None) < 0
+    assert lib.bgym_step(None, None, None, None, None, None, None, None, None, None, None, None, 4, 0, None) < 0
     assert b"bgym_step" in lib.bgym_last_error()
     assert lib.bgym_reset(None, None, None, None, None, None, None, None, 4, 0, None) < 0
     assert lib.bgym_sync_state(None, None, 4, 0, None) < 0 and lib.bgym_sync_obs(None, None, 4, 0, None) < 0
-    assert lib.bgym_pack_dirty_obs(None, None, 4, 4, 0, None) < 0 and lib.bgym_scatter_dirty_obs(None, 4, None, None, None) < 0
+    assert lib.bgym_pack_dirty_obs(None, None, None, None, 4, 4, None) < 0 and lib.bgym_scatter_dirty_obs(None, 4, None, None, None) < 0
 
 
 def _c_offsets(struct, fields):

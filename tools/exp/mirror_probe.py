@@ -25,7 +25,10 @@ def timed(fn, reps=10):
 
 snap = m._snap[0]
 env.sample_actions(seed=3); env.step(env.actions, want_info=False)
-def pack(): lib.bgym_pack_dirty_obs(env._obs.data_ptr(), snap["staging"].data_ptr(), n, n, 0, st.cuda_stream)
+keep = env.obs_dirty.clone()
+def pack():
+    env.obs_dirty.copy_(keep)
+    lib.bgym_pack_dirty_obs(env._obs.data_ptr(), env.obs_dirty.data_ptr(), snap["staging"].data_ptr(), m._scratch.data_ptr(), n, n, st.cuda_stream)
 t_pack = timed(pack)
 cnt, flagged = m.delta_counts(0)
 print("dirty records %d (%.3f), with shop chunks %d (%.3f)  pack %.3f ms" % (cnt, cnt / n, flagged, flagged / n, t_pack))

@@ -20,6 +20,16 @@ __global__ void records(const uint4* __restrict__ src, uint8_t* __restrict__ dst
   }
 }
 
+// 128-byte lines at the given record indices (8 lanes per record)
+__global__ void lines_at(const uint4* __restrict__ src, uint8_t* __restrict__ dst, const int* __restrict__ idx, long long nrec) {
+  const int lane = threadIdx.x & 31, sub = lane >> 3, part = lane & 7;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long k0 = warp * 4; k0 < nrec; k0 += warps * 4) {
+    const long long k = k0 + sub;
+    if (k < nrec) reinterpret_cast<uint4*>(dst + (long long)idx[k] * 128)[part] = src[k * 8 + part];
+  }
+}
+
 int main() {
   const long long n = 1 << 20;
   const size_t bytes = (size_t)n * 256;
@@ -57,5 +67,20 @@ int main() {
   report("zero-copy 16-B records contiguous (sel plane)", n * 16.0, reps);
   cudaEventRecord(e0); for (int r = 0; r < reps; r++) records<176, 176><<<148 * 8, 256>>>((const uint4*)d, h, n, 1); cudaEventRecord(e1); CK(cudaDeviceSynchronize());
   report("zero-copy 176-B records, every record", n * 176.0, reps);
+  {
+    // 2^18 of 2^20 line slots, chosen at random; written in ascending order, in random order, and in "interleaved runs"
+    // (the order the step's lists have: runs of ~32 ascending indices from many warps)
+    int* hidx = new int[nrec]; int* didx; CK(cudaMalloc(&didx, nrec * 4));
+    unsigned long long s = 88172645463325252ull;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    for (long long i = 0; i < nrec; i++) hidx[i] = (int)(i * 4 + rnd() % 4);
+    CK(cudaMemcpy(didx, hidx, nrec * 4, cudaMemcpyHostToDevice));
+    cudaEventRecord(e0); for (int r = 0; r < reps; r++) lines_at<<<148 * 8, 256>>>((const uint4*)d, h, didx, nrec); cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+    report("zero-copy 128-B lines, random 1-in-4 slots, ascending order", nrec * 128.0, reps);
+    for (long long i = nrec - 1; i > 0; i--) { long long j = rnd() % (i + 1); int t = hidx[i]; hidx[i] = hidx[j]; hidx[j] = t; }
+    CK(cudaMemcpy(didx, hidx, nrec * 4, cudaMemcpyHostToDevice));
+    cudaEventRecord(e0); for (int r = 0; r < reps; r++) lines_at<<<148 * 8, 256>>>((const uint4*)d, h, didx, nrec); cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+    report("zero-copy 128-B lines, same slots, random order", nrec * 128.0, reps);
+  }
   return 0;
 }
