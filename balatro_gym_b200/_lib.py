@@ -34,7 +34,8 @@ def source_hash() -> str:
     traffic bench.py reports, profiles/*_traffic.json) to the code they were measured on."""
     import hashlib
     h = hashlib.sha256()
-    for p in SOURCES + HEADERS:
+    # (the rollout / policy kernels are not part of what those captures measure: env step and hand scoring)
+    for p in [q for q in SOURCES if not q.endswith(("bgym_rollout.cuh", "bgym_policy.cuh"))] + HEADERS:
         h.update(os.path.basename(p).encode())
         h.update(open(p, "rb").read())
     return h.hexdigest()[:16]

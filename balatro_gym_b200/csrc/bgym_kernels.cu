@@ -1,7 +1,7 @@
 // bgym_kernels.cu — sm_100a kernels and the C-ABI (include/bgym.h) of the batched Balatro env.
 //
 // Kernels
-//   env_step_main_kernel / env_step_list_kernel<LIST> / env_step_small_kernel   K2  the fused, category-partitioned BalatroEnv.step
+//   env_step_main_kernel / env_step_list_kernel<LIST> / env_step_small_kernel   K2  the fused, path-partitioned BalatroEnv.step
 //                           (bgym_step_part.cuh): mask check -> phase dispatch -> scoring -> boss ->
 //                           round advance / shop generation -> reward -> observation + mask emission,
 //                           in-place autoreset (K3) and an optional fused random-legal policy
@@ -10,12 +10,15 @@
 //   action_mask_kernel, sample_actions_kernel, episode_stats_kernel (K6)
 //   featurize_kernel, masked_sample_kernel, gae_kernel (bgym_rollout.cuh)   on-device PPO rollout collection
 //
-// Data movement of K2/K3: env state is two dense arrays, hot[n] (144 B records) and cold[n] (176 B
-// records).  A warp owns a tile of 32 envs; a tile of records is contiguous, so it moves between
-// global and shared memory with ONE 1-D bulk async copy (cp.async.bulk, SASS UBLKCP — the TMA engine
-// without a tensor map) that completes on the warp's mbarrier; each lane then works on its record
-// with 128-bit shared-memory accesses (record strides 144 / 176 / 176 B are odd multiples of 16 B,
-// so a quarter-warp hits 8 distinct bank groups), and results leave with bulk async stores.
+//   sync_state / sync_obs kernels   fold the device-only side arrays (BgymTog, BgymSel) into the records and back
+//   pack_count / pack_index / pack_records / scatter_dirty kernels   observation deltas for a host mirror (HostMirror)
+//
+// Data layout of K2/K3 (include/bgym.h): env state = hot[n] (144 B records), cold[n] (176 B) and tog[n] (32 B toggle
+// records: the card-select working set); observations = obs[n] (176 B) and sel[n] (16 B selection records).  A card
+// toggle — three steps in four — reads and writes tog and sel only, coalesced, from registers (main pass).  Every other
+// action goes through a list tile: one lane per env, records read and written where they lie.  The reset kernel moves
+// tiles of records with 1-D bulk async copies (cp.async.bulk, SASS UBLKCP) completing on a per-warp mbarrier; record
+// strides 144 / 176 B are odd multiples of 16 B, so per-lane 128-bit shared-memory accesses are bank-conflict free.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -862,6 +865,30 @@ int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, cons
 #undef BGYM_LAUNCH_LIST
   if (fork) { cudaEventRecord(sc->ev_side[0], sc->side[0]); cudaStreamWaitEvent(s, sc->ev_side[0], 0); }
   if (timing == 1) cudaEventRecord(tev[3], s);
+#ifdef BGYM_TILE_CLOCK
+  {
+    static int dbg_calls = 0;
+    if (++dbg_calls % 64 == 0) {
+      cudaStreamSynchronize(s);
+      static int hc[N_LISTS * PART_CTR_STRIDE];
+      cudaMemcpy(hc, sc->counters, sizeof hc, cudaMemcpyDeviceToHost);
+      static const char* lnames[N_LISTS] = {"PLAY", "CONS", "GEN", "MISC", "DISCARD", "SHOP", "BLIND", "ADVANCE", "RESET"};
+      unsigned long long t_ref = ~0ull;
+      for (int l = 0; l < N_LISTS; l++) {
+        const unsigned long long* d = reinterpret_cast<const unsigned long long*>(hc + l * PART_CTR_STRIDE + 8);
+        if (d[4] && ~d[0] < t_ref) t_ref = ~d[0];
+      }
+      fprintf(stderr, "[bgym tiles]");
+      for (int l = 0; l < N_LISTS; l++) {
+        const unsigned long long* d = reinterpret_cast<const unsigned long long*>(hc + l * PART_CTR_STRIDE + 8);
+        if (!d[4]) continue;
+        fprintf(stderr, " %s n=%llu start %.1f end %.1f mean %.1f max %.1f |", lnames[l], d[4], (~d[0] - t_ref) * 1e-3, (d[1] - t_ref) * 1e-3,
+                d[2] * 1e-3 / d[4], d[3] * 1e-3);
+      }
+      fprintf(stderr, " (us)\n");
+    }
+  }
+#endif
   if (timing == 1) {
     cudaEventSynchronize(tev[3]);
     for (int i = 0; i < 3; i++) { float m = 0; cudaEventElapsedTime(&m, tev[i], tev[i + 1]); tsum[i] += m; }

@@ -8,17 +8,18 @@
 // lanes per instruction and the rare long paths (round advance + shop generation, autoreset, consumables) with 1-5.
 // So the unit of work is now a TILE OF 32 ENVS THAT TAKE THE SAME PATH:
 //
-//   main pass      (every env)   stages ONLY the hot records of each warp's tile (one bulk copy of 32 x 144 B), fully
-//                                handles SELECT toggles (~75 % of random-legal steps) and rejected actions of envs in
-//                                PLAY phase — writing back only the 16-byte chunk of the hot record a toggle changes —
-//                                and appends every other env to ONE OF SEVEN lists by the path its action takes
-//                                (staged per warp, one atomic per run of >= 32).  Cold records are never touched.
-//   level-1 pass   (one launch)  walks the tiles of the seven lists: each lane pulls ONE listed env's hot + cold record
-//                                with its own bulk copies, runs that list's path (step_env<CATS> compiles only the list's
+//   main pass      (every env)   reads ONLY the 32-byte toggle records (BgymTog: the selection, phase, and what the PLAY-phase
+//                                mask needs), fully handles SELECT toggles (~75 % of random-legal steps) and rejected actions
+//                                of envs in PLAY phase — writing back the toggle record and the 16-byte selection record
+//                                (BgymSel: selected_cards + mask word), 94 B per env in all — and appends every other env to
+//                                ONE OF SEVEN lists by the path its action takes (staged per warp, one atomic per run of
+//                                >= 32).  Hot, cold and observation records are never touched.
+//   level-1 pass   (7 launches)  one kernel per list, concurrent on forked streams: each lane serves ONE listed env — hot +
+//                                toggle record lifted into registers, cold record read in place —, runs that list's path (step_env<CATS> compiles only the list's
 //                                branches), pushes hot (+ cold) + observation back.  Two long paths are NOT run here
 //                                but handed on, again as lists: the round advance of a hand that beat the blind, and
 //                                the in-place reset of a terminated env.
-//   level-2 pass   (one launch)  tiles of envs that advance a round (continuing the step's draw sequence where level 1
+//   level-2 pass   (2 launches)  tiles of envs that advance a round (continuing the step's draw sequence where level 1
 //                                left it) and tiles of envs that are reset (32 fresh decks shuffled side by side).
 //
 //   small slabs (n <= 65536)     one launch of the gather tile code over all envs with every category compiled in and
@@ -204,14 +205,17 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MAIN_CTAS_PER_SM) env_step_ma
 // ------------------------------------------------------------------------------------------------
 // list tiles: one listed env per lane
 // ------------------------------------------------------------------------------------------------
+// One warp per CTA: a CTA's slot (registers) is given back when its tile ends, not when the slowest of four tiles ends
+// (tile latencies within a list spread 2-3x around their mean).  Measured on the bench loop: 4 warps x 4 CTAs 0.2057 /
+// 0.2085 ms per step, 2 x 8: 0.2033, 1 x 16: 0.2021, 1 x 12 (registers capped at 168 instead of 128): 0.1986 / 0.2025.
 #ifndef BGYM_GATHER_WARPS
-#define BGYM_GATHER_WARPS 4
+#define BGYM_GATHER_WARPS 1
 #endif
 constexpr int GATHER_WARPS = BGYM_GATHER_WARPS;
 // shared memory of a list kernel: one cold-record slot per lane for the lists that stage it, none for the others
 constexpr int GATHER_CTA_SMEM = GATHER_WARPS * 32 * BGYM_COLD_BYTES;
 #ifndef BGYM_GATHER_CTAS
-#define BGYM_GATHER_CTAS 4
+#define BGYM_GATHER_CTAS 12
 #endif
 constexpr int GATHER_CTAS_PER_SM = BGYM_GATHER_CTAS;
 
@@ -454,6 +458,10 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, list_ctas(LIST)) env_step_l
     const int idx = tile * 32 + lane;
     const bool active = idx < count;
     const long long e = active ? (long long)__ldcg(list + idx) : -1;
+#ifdef BGYM_TILE_CLOCK
+    unsigned long long tc0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tc0));
+#endif
     if (LIST == L_PLAY) gather_tile<CAT_PLAY, TM_DEFER | STG_RO>(a, e, active, lane, cold_slot);
     else if (LIST == L_CONS) gather_tile<CAT_CONS, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
     else if (LIST == L_GEN) gather_tile<CAT_GEN, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
@@ -463,6 +471,17 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, list_ctas(LIST)) env_step_l
     else if (LIST == L_BLIND) gather_tile<CAT_BLIND, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
     else if (LIST == L_ADVANCE) advance_tile(a, e, active, cold_slot);
     else reset_tile(a, e, active, cold_slot);
+#ifdef BGYM_TILE_CLOCK
+    // diagnostic build (-DBGYM_TILE_CLOCK): per list, when its first tile started, when its last tile ended, and the tile
+    // durations (ns), kept in the spare words behind the list's counter; bgym_step prints them every 64 calls
+    __syncwarp();
+    unsigned long long tc1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tc1));
+    if (lane == 0) {
+      unsigned long long* d = reinterpret_cast<unsigned long long*>(a.part_counters + LIST * PART_CTR_STRIDE + 8);
+      atomicMax(d + 0, ~tc0); atomicMax(d + 1, tc1); atomicAdd(d + 2, tc1 - tc0); atomicMax(d + 3, tc1 - tc0); atomicAdd(d + 4, 1ull);
+    }
+#endif
   }
 }
 

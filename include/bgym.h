@@ -4,7 +4,7 @@
  *   BalatroEnv.reset            balatro_gym/balatro_env_2.py:505-558   -> bgym_reset
  *   BalatroEnv.step             balatro_gym/balatro_env_2.py:616-1064  -> bgym_step
  *   BalatroEnv._get_action_mask balatro_gym/balatro_env_2.py:1426-1471 -> bgym_action_mask
- *   BalatroEnv._get_observation balatro_gym/balatro_env_2.py:1473-1541 -> BgymObs (written by reset/step)
+ *   BalatroEnv._get_observation balatro_gym/balatro_env_2.py:1473-1541 -> BgymObs + BgymSel (written by reset/step)
  *   _classify_hand + CardAdapter.to_scoring_format + UnifiedScorer.score_hand
  *       balatro_gym/balatro_game.py:40-93, balatro_env_2.py:287-325,
  *       balatro_gym/unified_scoring.py:111-299                         -> bgym_score_hands
@@ -158,8 +158,8 @@ enum {
  * (boss_blinds.py:311-319) + Shop inventory (shop.py:96-148).  SURVEY.md Appendix D.
  *
  * ON THE DEVICE the two halves live in two dense arrays, hot[n] (BgymHot, 144 B = 9 x 16) and
- * cold[n] (BgymCold, 176 B = 11 x 16): card-select toggles (~83 % of steps) touch only the hot
- * array, and both strides are odd multiples of 16 B so a tile staged in shared memory is
+ * cold[n] (BgymCold, 176 B = 11 x 16), next to tog[n] (BgymTog, 32 B): card-select toggles (~75 % of steps) touch only
+ * the toggle array, and both record strides are odd multiples of 16 B so a tile staged in shared memory is
  * bank-conflict free for 128-bit per-lane access.  BgymState = {hot, cold} back to back is the
  * HOST-side record (checkpoints, bgym_vec_get_state/set_state, the test oracle). */
 /* hot record, 144 B (offset: field)
@@ -168,8 +168,9 @@ enum {
  *  16 hand_n, 17 hand_size, 18 sel_n, 19 highlight_mask (game.highlighted_indexes as a slot bit set)
  *  20 sel_order           selected_cards, ordered: nibble k = slot of the k-th selection
  *  24 face_down_mask, 25 phase, 26 round (1 small 2 big 3 boss), 27 boss_type (BossBlindType, 0 none)
- *  28 ep_len              valid steps this episode.  Bytes 16..31 are everything a card toggle changes:
- *                         the main pass writes back only this 16-byte chunk for the envs it serves
+ *  28 ep_len              valid steps this episode.  Bytes 16..31 are everything a card toggle changes; ON THE DEVICE
+ *                         their authoritative copy is the env's toggle record (BgymTog below): a toggle updates it
+ *                         there only, and bgym_sync_state folds it back into the hot record
  *  32 joker_slots, 33 cons_slots, 34 n_magic_trick, 35 n_minimalist (voucher counts)
  *  36 ante i16, 38 jokers_sold i16, 40 money i32, 44 chips_needed i32
  *  48 round_chips i64 (round_chips_scored), 56 chips_scored i64
@@ -456,7 +457,8 @@ int bgym_sample_actions_ctr(const uint64_t* mask_words, int64_t mask_stride, int
  *   [426,447) chips_scored/1e6, chips_needed/1e5, progress_ratio, money/100, ante/10, round/3,
  *             hands_left/10, discards_left/5, hand_levels[12]/10, phase/3        :102-113
  *   [447]     0 (pad to a 16-byte multiple)
- * features: n x BGYM_FEATURE_DIM of dtype BGYM_DT_F32 or BGYM_DT_BF16, 16-byte aligned. */
+ * features: n x BGYM_FEATURE_DIM of dtype BGYM_DT_F32 or BGYM_DT_BF16, 16-byte aligned.
+ * Reads none of the fields a BgymSel carries, so obs needs no bgym_sync_obs first (nor does bgym_policy_first_layer). */
 int bgym_featurize(const BgymObs* obs, void* features, int64_t n, int dtype, void* stream);
 
 /* First Linear + ReLU of the reference extractor's three sub-nets (train_balatro_agent.py:52-69: hand_net[0] 416 -> 256,
