@@ -23,6 +23,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-fmad=false", "-shared", "-Xcompiler", "-fPIC"]
 
 _lib = None
+_policy_lib = None
+POLICY_SOURCE = os.path.join(_PKG, "csrc", "bgym_policy.cu")
+POLICY_HEADER = os.path.join(_REPO, "include", "bgym_policy.h")
+POLICY_SO_PATH = os.path.join(_PKG, "libbgym_policy.so")
 
 
 class BgymError(RuntimeError):
@@ -132,6 +136,60 @@ def load():
     if lib.bgym_abi_version() != 2:
         raise BgymError("libbgym.so ABI version mismatch")
     _lib = lib
+    return lib
+
+
+def build_policy(force: bool = False) -> str:
+    """Compile csrc/bgym_policy.cu (the fused tcgen05 policy forward, include/bgym_policy.h) for sm_100a into
+    balatro_gym_b200/libbgym_policy.so.  Its own library: the env path does not depend on it."""
+    if not force and os.path.exists(POLICY_SO_PATH) and all(os.path.getmtime(p) <= os.path.getmtime(POLICY_SO_PATH)
+                                                             for p in (POLICY_SOURCE, POLICY_HEADER)):
+        return POLICY_SO_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise BgymError("nvcc not found: cannot build libbgym_policy.so")
+    import fcntl
+    with open(POLICY_SO_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            tmp = f"{POLICY_SO_PATH}.{os.getpid()}.tmp"
+            cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+                   "-I", os.path.join(_REPO, "include"), "-o", tmp, POLICY_SOURCE]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise BgymError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, POLICY_SO_PATH)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+    return POLICY_SO_PATH
+
+
+POLICY_SYMBOLS = {
+    "bgym_policy_program": (_i32, [_vp, _vp, _vp]),
+    "bgym_policy_forward": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "bgym_policy_last_error": (C.c_char_p, []),
+}
+
+
+def load_policy():
+    """Load libbgym_policy.so (building it first when the source is newer and nvcc is present)."""
+    global _policy_lib
+    if _policy_lib is not None:
+        return _policy_lib
+    stale = not os.path.exists(POLICY_SO_PATH) or any(os.path.getmtime(p) > os.path.getmtime(POLICY_SO_PATH) for p in (POLICY_SOURCE, POLICY_HEADER))
+    if stale:
+        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+            build_policy(force=True)
+        elif not os.path.exists(POLICY_SO_PATH):
+            raise BgymError(f"{POLICY_SO_PATH} is missing and nvcc is not available; run __graft_entry__.build()")
+    lib = C.CDLL(POLICY_SO_PATH)
+    for name, (res, args) in POLICY_SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _policy_lib = lib
     return lib
 
 

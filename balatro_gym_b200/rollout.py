@@ -17,6 +17,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import numpy as np
+
 from . import layout as L
 from . import _lib
 
@@ -62,6 +64,77 @@ def policy_first_layer(obs_records, wt_hand, wt_joker, wt_game, bias, out=None):
                                          bias.data_ptr(), out.data_ptr(), n, torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "bgym_policy_first_layer")
     return out
+
+
+# ---- fused tcgen05 forward of layers 2.. (libbgym_policy.so, include/bgym_policy.h) -------------------------------
+_POLICY_LAYER_KEYS = ["hand_net.2", "joker_net.2", "game_state_net.2", "combined_net.0", "combined_net.2",
+                      "pi.0", "vf.0", "pi.2", "vf.2", "pi.4", "vf.4"]
+
+
+def policy_program():
+    """(steps as a numpy structured array, weight blob bytes, bias blob floats) of bgym_policy_program."""
+    import ctypes as C
+    lib = _lib.load_policy()
+    step_dt = np.dtype([(k, "<i4") for k in ("offset", "bytes", "layer", "n0", "n", "kb", "a_kb", "col", "first", "last", "group", "_pad")])
+    steps = np.zeros(64, dtype=step_dt)
+    wb, bf = C.c_int64(0), C.c_int64(0)
+    n = lib.bgym_policy_program(steps.ctypes.data, C.addressof(wb), C.addressof(bf))
+    return steps[:n], int(wb.value), int(bf.value)
+
+
+def pack_policy_weights(state_dict, device):
+    """Pack the eleven Linear layers after the first ones into the blobs bgym_policy_forward reads: every program step's
+    weight tile (rows [n0, n0 + n) x input columns [64 kb, 64 kb + 64), zero-padded) as n rows of 128 bytes of bf16,
+    16-byte chunk c of row r stored at chunk c ^ (r & 7) (the tensor core's 128-byte swizzle); biases per epilogue group
+    at the accumulator column they are added to."""
+    torch = _torch()
+    steps, wbytes, bfloats = policy_program()
+    blob = np.zeros(wbytes // 2, dtype=np.uint16)
+    mats = []
+    for key in _POLICY_LAYER_KEYS:
+        w = state_dict[key + ".weight"].detach().to(torch.bfloat16).cpu().view(torch.int16).numpy().view(np.uint16)
+        mats.append(w)
+    for st in steps:
+        w = mats[int(st["layer"])]
+        n0, n, kb = int(st["n0"]), int(st["n"]), int(st["kb"])
+        tile = np.zeros((n, 64), dtype=np.uint16)
+        rows = max(0, min(n, w.shape[0] - n0))
+        cols = max(0, min(64, w.shape[1] - 64 * kb))
+        if rows and cols:
+            tile[:rows, :cols] = w[n0:n0 + rows, 64 * kb:64 * kb + cols]
+        chunks = tile.reshape(n, 8, 8)                                   # [row, chunk, 8 bf16]
+        r = np.arange(n)[:, None]
+        pos = np.arange(8)[None, :] ^ (r & 7)                            # chunk c of row r goes to position c ^ (r & 7)
+        sw = np.zeros_like(chunks)
+        sw[r, pos] = chunks
+        off = int(st["offset"]) // 2
+        blob[off:off + n * 64] = sw.reshape(-1)
+    bias = np.zeros(bfloats, dtype=np.float32)
+    goff = lambda g: 0 if g == 0 else 256 + 512 * (g - 1)
+    col_of = {0: (0, 0), 1: (0, 128), 2: (0, 192), 3: (1, 0), 4: (2, 0), 5: (3, 0), 6: (3, 256), 7: (4, 0), 8: (4, 256), 9: (5, 0), 10: (5, 64)}
+    for li, key in enumerate(_POLICY_LAYER_KEYS):
+        b = state_dict[key + ".bias"].detach().float().cpu().numpy()
+        g, col = col_of[li]
+        bias[goff(g) + col:goff(g) + col + b.shape[0]] = b
+    wt = torch.from_numpy(blob.view(np.int16)).to(device).view(torch.bfloat16)
+    return wt, torch.from_numpy(bias).to(device)
+
+
+def policy_forward_fused(act448, weights, bias, logits=None, value=None):
+    """[n, 448] bf16 first-layer activations -> (logits fp32 [n, 60], value fp32 [n]) in one tcgen05 kernel."""
+    torch = _torch()
+    lib = _lib.load_policy()
+    n = act448.shape[0]
+    assert act448.dtype == torch.bfloat16 and act448.shape[1] == 448 and act448.is_contiguous()
+    dev = act448.device
+    logits = torch.empty((n, L.NUM_ACTIONS), dtype=torch.float32, device=dev) if logits is None else logits
+    value = torch.empty(n, dtype=torch.float32, device=dev) if value is None else value
+    with torch.cuda.device(dev):
+        rc = lib.bgym_policy_forward(act448.data_ptr(), weights.data_ptr(), bias.data_ptr(), logits.data_ptr(), value.data_ptr(), n,
+                                     torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise _lib.BgymError(f"bgym_policy_forward failed (rc={rc}): {lib.bgym_policy_last_error().decode()}")
+    return logits, value
 
 
 def masked_sample(logits, obs_records, seed: int = 0, step: int = 0, env_offset: int = 0, uniforms=None,
@@ -157,13 +230,15 @@ class RolloutCollector:
     """
 
     def __init__(self, vec, policy, n_steps: int = 128, gamma: float = 0.99, gae_lambda: float = 0.95,
-                 seed: int = 0, autocast: bool = True):
+                 seed: int = 0, autocast: bool = True, fused: bool = True):
         torch = vec.torch
         self.torch = torch
         self.vec, self.policy = vec, policy
         self.T, self.n = int(n_steps), vec.num_envs
         self.gamma, self.lam, self.seed = gamma, gae_lambda, seed
         self.autocast = autocast
+        # fused = layers 2.. of the rollout forward in one tcgen05 kernel (libbgym_policy.so) instead of eleven library GEMMs
+        self.fused = bool(fused and autocast)
         dev, T, n = vec.device, self.T, self.n
         self.obs = torch.empty((T + 1, n, L.OBS_BYTES), dtype=torch.uint8, device=dev)
         self.actions = torch.empty((T, n), dtype=torch.int32, device=dev)
@@ -175,6 +250,8 @@ class RolloutCollector:
         self.advantages = torch.empty((T, n), dtype=torch.float32, device=dev)
         self.returns = torch.empty((T, n), dtype=torch.float32, device=dev)
         self._feats = torch.empty((n, FEATURE_DIM), dtype=torch.bfloat16 if autocast else torch.float32, device=dev)
+        self._logits = torch.empty((n, L.NUM_ACTIONS), dtype=torch.float32, device=dev)
+        self._value = torch.empty(n, dtype=torch.float32, device=dev)
         self.global_step = 0
 
     def refresh_inference_weights(self):
@@ -188,6 +265,8 @@ class RolloutCollector:
             self._first = (self._w16["hand_net.0.weight"].t().contiguous(), self._w16["joker_net.0.weight"].t().contiguous(),
                            self._w16["game_state_net.0.weight"].t().contiguous(),
                            torch.cat([sd["hand_net.0.bias"], sd["joker_net.0.bias"], sd["game_state_net.0.bias"]]).detach().float().contiguous())
+            if self.fused:
+                self._packed = pack_policy_weights(sd, self.vec.device)
 
     def _mlp(self, x, prefix, n_layers, last_plain=False, act="relu"):
         """Sequential of Linear(+activation) from the cached bf16 weights; ReLU layers use the cuBLASLt
@@ -222,6 +301,8 @@ class RolloutCollector:
         # first Linear + ReLU of the three sub-nets straight from the records (no one-hot feature matrix), then their
         # second layers on strided column views of that activation (lda = 448)
         a = policy_first_layer(obs_records, *self._first, out=self._feats)
+        if self.fused:      # layers 2..: one tcgen05 kernel, activations never leave the SM
+            return policy_forward_fused(a, *self._packed, logits=self._logits, value=self._value)
         h = self._mlp_from(a[:, :256], "hand_net", 1, 2)
         j = self._mlp_from(a[:, 256:384], "joker_net", 1, 2)
         g = self._mlp_from(a[:, 384:448], "game_state_net", 1, 2)
