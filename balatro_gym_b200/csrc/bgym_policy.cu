@@ -1,7 +1,7 @@
 // bgym_policy.cu — fused forward of the rollout policy on the 5th-generation tensor cores (sm_100a), C-ABI in
 // include/bgym_policy.h.  Policy side of on-device PPO rollout collection; its own library.
 //
-// One CTA (128 threads, one per env of a 128-env tile, 1 CTA per SM, persistent over tiles):
+// One CTA (512 threads on a 128-env tile, 1 CTA per SM, persistent over tiles):
 //   X   128 KB of shared memory: the tile's activations, up to 512 columns of bf16, as eight K-blocks of 64 columns;
 //       a K-block is 128 rows x 128 bytes, 128-byte swizzled (16-byte chunk c of row r sits at chunk c ^ (r & 7)) —
 //       the canonical K-major SWIZZLE_128B operand layout of tcgen05.mma, so every layer's output is written exactly
@@ -12,19 +12,24 @@
 //   D   the accumulators: all 512 columns of tensor memory (fp32, lane = env).
 // Thread 0 issues the bulk copies and the MMAs (tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 16..256, K = 16, four per
 // weight tile); tcgen05.commit hands a weight stage back to the copy ring and, after the last tile of a layer group,
-// wakes all four warps, which read their 32 accumulator lanes with tcgen05.ld (32x32b.x32), add the bias, apply ReLU /
-// tanh, round to bf16 and store the next operand into X (or the logits / value to global memory after the last group).
+// wakes all sixteen warps: warp w reads accumulator lanes 32 (w % 4) .. + 31 (the quarter of tensor memory a warp may
+// address), columns of slice w / 4, with tcgen05.ld (32x32b.x32), adds the bias, applies ReLU / tanh, rounds to bf16 and
+// stores the next operand into X (or the logits / value to global memory after the last group).  Four warps per
+// scheduler matter: with one warp per scheduler the epilogues (a dependent chain of ~200 instructions per 32 columns)
+// took 40 of the 86 us a tile needed.
 //
-// Program (63 weight tiles per env tile, six epilogue groups):
-//   g0  hand_net.2 256->128 | joker_net.2 128->64 | game_state_net.2 64->32   (three MMAs chains into columns 0..223)   ReLU
-//   g1  combined_net.0 224(256)->512      g2  combined_net.2 512->512                                                   ReLU
-//   g3  pi.0 512->256 | vf.0 512->256     g4  pi.2 256->256 | vf.2 256->256                                             tanh
-//   g5  pi.4 256->60(64) | vf.4 256->1(16)                                                                              none -> global
+// Program (72 weight tiles per env tile, seven epilogue groups):
+//   g0  hand_net.0 416(448)->256 | joker_net.0 10(64)->128 | game_state_net.0 21(64)->64   from the observation record      ReLU
+//   g1  hand_net.2 256->128 | joker_net.2 128->64 | game_state_net.2 64->32   (three MMA chains into columns 0..223)        ReLU
+//   g2  combined_net.0 224(256)->512      g3  combined_net.2 512->512                                                       ReLU
+//   g4  pi.0 512->256 | vf.0 512->256     g5  pi.2 256->256 | vf.2 256->256                                                 tanh
+//   g6  pi.4 256->60(64) | vf.4 256->1(16)                                                                                  none -> global
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 
 #include "bgym_policy.h"
@@ -32,23 +37,28 @@
 namespace {
 
 constexpr int TILE_M = 128;
+constexpr int N_THREADS = 512;
 constexpr int KB_BYTES = TILE_M * 128;            // one K-block of the activation tile: 16 KB
 constexpr int X_BYTES = 8 * KB_BYTES;             // 128 KB
 constexpr int STAGE_BYTES = 256 * 128;            // 32 KB: the largest weight tile
 constexpr int N_STAGES = 3;
 constexpr int BAR_OFFSET = X_BYTES + N_STAGES * STAGE_BYTES;
 constexpr int SMEM_BYTES = BAR_OFFSET + 128;
-constexpr int IN_CHUNKS = BGYM_POLICY_IN_DIM / 8; // 56 x 16 B per input row
+constexpr int OBS_BYTES = 176;                   // BgymObs (include/bgym.h)
 
 struct LayerDef { int n_real, k_real, n_pad, k_blocks, a_kb, col, group; };
-// n_pad = MMA N (a multiple of 16; 512 is issued as two halves of 256)
+// n_pad = MMA N (a multiple of 16; 512 is issued as two halves of 256).  Layers 0..2 are the FIRST Linear of the three
+// sub-nets, fed from the observation record: the input stage writes the 8-hot hand block (416 columns, K-blocks 0..6) and one
+// more K-block (7) holding joker_ids[10] at columns 0..9 and the 21 scaled game scalars at columns 16..36.
 constexpr LayerDef LAYERS[BGYM_POLICY_LAYERS] = {
-    {128, 256, 128, 4, 0, 0, 0},   {64, 128, 64, 2, 4, 128, 0},   {32, 64, 32, 1, 6, 192, 0},
-    {512, 224, 512, 4, 0, 0, 1},   {512, 512, 512, 8, 0, 0, 2},
-    {256, 512, 256, 8, 0, 0, 3},   {256, 512, 256, 8, 0, 256, 3},
-    {256, 256, 256, 4, 0, 0, 4},   {256, 256, 256, 4, 4, 256, 4},
-    {60, 256, 64, 4, 0, 0, 5},     {1, 256, 16, 4, 4, 64, 5}};
-constexpr int N_GROUPS = 6;
+    {256, 416, 256, 7, 0, 0, 0},   {128, 10, 128, 1, 7, 256, 0},  {64, 21, 64, 1, 7, 384, 0},
+    {128, 256, 128, 4, 0, 0, 1},   {64, 128, 64, 2, 4, 128, 1},   {32, 64, 32, 1, 6, 192, 1},
+    {512, 224, 512, 4, 0, 0, 2},   {512, 512, 512, 8, 0, 0, 3},
+    {256, 512, 256, 8, 0, 0, 4},   {256, 512, 256, 8, 0, 256, 4},
+    {256, 256, 256, 4, 0, 0, 5},   {256, 256, 256, 4, 4, 256, 5},
+    {60, 256, 64, 4, 0, 0, 6},     {1, 256, 16, 4, 4, 64, 6}};
+constexpr int N_GROUPS = 7;
+constexpr int GAME_K_SHIFT = 16;      // column of K-block 7 where the game scalars start
 
 int build_program(BgymPolicyStep* steps, int64_t* weight_bytes) {
   int s = 0;
@@ -69,8 +79,8 @@ int build_program(BgymPolicyStep* steps, int64_t* weight_bytes) {
   if (weight_bytes) *weight_bytes = off;
   return s;
 }
-__host__ __device__ constexpr int bias_offset(int group) { return group == 0 ? 0 : 256 + 512 * (group - 1); }
-constexpr int BIAS_FLOATS = 256 + 512 * (N_GROUPS - 1);
+__host__ __device__ constexpr int bias_offset(int group) { return 512 * group; }
+constexpr int BIAS_FLOATS = 512 * N_GROUPS;
 
 __constant__ BgymPolicyStep c_prog[BGYM_POLICY_MAX_STEPS];
 
@@ -142,30 +152,70 @@ __device__ __forceinline__ uint32_t x_offset(int row, int chunk) {
 }
 
 enum { ACT_RELU = 1, ACT_TANH = 2 };
-// accumulator columns [0, ncols) of this thread's lane -> act(acc + bias) -> bf16 -> X columns [0, ncols)
+// (lo, hi) fp32 -> packed bf16x2 of relu(.) — cvt.rn.relu.bf16x2.f32, one instruction — or of tanh(.): round to bf16, then the
+// packed MUFU tanh (tanh.approx.bf16x2: two results per special-function op; with the fp32 form the two tanh epilogues were
+// bound by the special-function unit, 16 lanes per clock per SM)
 template <int ACT>
-__device__ __forceinline__ void epilogue_to_x(uint32_t taddr, int row, int ncols, const float* __restrict__ bias, uint8_t* X) {
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(taddr + (uint32_t)c0, v);
+__device__ __forceinline__ uint32_t act_pack(float lo, float hi) {
+  uint32_t r;
+  if (ACT == ACT_RELU) {
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    uint32_t p;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(p));
+  }
+  return r;
+}
+// 16 accumulator columns of this thread's lane, asynchronously: the registers are valid after tmem_wait16 on the same array
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+// tcgen05.wait::ld, tied to the registers it makes valid (so that no use of them is scheduled above it)
+__device__ __forceinline__ void tmem_wait16(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]),
+                 "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               : : "memory");
+}
+// 16 columns starting at c0: act(acc + bias) -> bf16 -> two 16-byte chunks of X
+template <int ACT>
+__device__ __forceinline__ void epilogue16(const uint32_t* v, int row, int c0, const float* __restrict__ bias, uint8_t* X) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      float f[8];
+  for (int q = 0; q < 2; q++) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * q)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 8 * q + 4));
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t w[4];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        float x = __uint_as_float(v[8 * q + j]) + __ldg(bias + c0 + 8 * q + j);
-        f[j] = ACT == ACT_RELU ? fmaxf(x, 0.0f) : tanh_fast(x);
-      }
-      uint4 w;
-      w.x = pack_bf16x2(f[0], f[1]); w.y = pack_bf16x2(f[2], f[3]); w.z = pack_bf16x2(f[4], f[5]); w.w = pack_bf16x2(f[6], f[7]);
-      *reinterpret_cast<uint4*>(X + x_offset(row, (c0 >> 3) + q)) = w;
-    }
+    for (int j = 0; j < 4; j++)      // fp32 bias add, then ONE instruction per pair: round to bf16 with ReLU, or round + packed tanh
+      w[j] = act_pack<ACT>(__uint_as_float(v[8 * q + 2 * j]) + bb[2 * j], __uint_as_float(v[8 * q + 2 * j + 1]) + bb[2 * j + 1]);
+    *reinterpret_cast<uint4*>(X + x_offset(row, (c0 >> 3) + q)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+// accumulator columns [c_begin, c_end) (a multiple of 32 wide) of this thread's lane -> act(acc + bias) -> bf16 -> the same columns
+// of X.  Two 16-column register buffers: the tensor-memory load of one is in flight while the other is processed.
+template <int ACT>
+__device__ __forceinline__ void epilogue_to_x(uint32_t taddr, int row, int c_begin, int c_end, const float* __restrict__ bias, uint8_t* X) {
+  uint32_t a[16], b[16];
+  tmem_ld16_async(taddr + (uint32_t)c_begin, a);
+  tmem_wait16(a);
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    tmem_ld16_async(taddr + (uint32_t)(c0 + 16), b);
+    epilogue16<ACT>(a, row, c0, bias, X);
+    tmem_wait16(b);
+    if (c0 + 32 < c_end) tmem_ld16_async(taddr + (uint32_t)(c0 + 32), a);
+    epilogue16<ACT>(b, row, c0 + 16, bias, X);
+    if (c0 + 32 < c_end) tmem_wait16(a);
   }
 }
 
-__global__ void __launch_bounds__(TILE_M, 1) policy_mlp_kernel(const uint4* __restrict__ act, const uint8_t* __restrict__ weights,
+__global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ weights,
                                                                const float* __restrict__ bias, float* __restrict__ logits,
-                                                               float* __restrict__ value, long long n, int n_steps) {
+                                                               float* __restrict__ value, long long n, int n_steps, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* X = smem;
   uint8_t* W = smem + X_BYTES;
@@ -187,82 +237,164 @@ __global__ void __launch_bounds__(TILE_M, 1) policy_mlp_kernel(const uint4* __re
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32 lanes
-  const int row = tid;
+  const int quarter = warp & 3, slice = warp >> 2;                       // accumulator lanes 32 quarter .. + 31, column slice 0..3
+  const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+  const int row = quarter * 32 + (tid & 31);
 
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long total_steps = my_tiles * n_steps;
-  long long produced = 0, consumed = 0;        // thread 0: weight tiles requested / handed to the tensor core
+  const uint32_t x_base = smem_u32(X), w_base = smem_u32(W);
+  // thread 0's pipeline state — small integers only: stage indices and phase bits advance by increment-and-wrap (64-bit
+  // divisions and modulos in this loop cost more than the four MMAs it issues per weight tile)
+  int produced = 0;                            // weight tiles requested (producer thread)
+  const int total = (int)total_steps;
+  int p_stage = 0, p_prog = 0, c_stage = 0;
   uint32_t acc_parity = 0;
+  uint32_t p_phase = 0, c_phase = 0;           // p_phase: parity of the NEXT wait on empty[p_stage] (valid once produced >= N_STAGES)
+  long long t_full = 0, t_empty = 0, t_acc = 0, t_epi = 0, t_in = 0, t_mma = 0, t_copy = 0, t_body = 0, t_all = clock64();   // diagnostic clocks (thread 0, dbg != nullptr)
   // thread 0: request weight tiles up to (but not including) index `upto`
-  auto top_up = [&](long long upto) {
-    while (produced < upto && produced < total_steps) {
-      const int st = (int)(produced % N_STAGES);
-      if (produced >= N_STAGES) mbar_wait(&empty[st], (uint32_t)((produced / N_STAGES - 1) & 1));
-      const BgymPolicyStep& ps = c_prog[produced % n_steps];
-      mbar_expect_tx(&full[st], (uint32_t)ps.bytes);
-      bulk_g2s(W + st * STAGE_BYTES, weights + ps.offset, (uint32_t)ps.bytes, &full[st]);
+  auto top_up = [&](int upto) {
+    while (produced < upto && produced < total) {
+      if (produced >= N_STAGES) {
+        const long long c0 = dbg ? clock64() : 0;
+        mbar_wait(&empty[p_stage], p_phase);
+        if (dbg) t_empty += clock64() - c0;
+      }
+      const long long cc0 = dbg ? clock64() : 0;
+      const BgymPolicyStep& ps = c_prog[p_prog];
+      mbar_expect_tx(&full[p_stage], (uint32_t)ps.bytes);
+      bulk_g2s(W + p_stage * STAGE_BYTES, weights + ps.offset, (uint32_t)ps.bytes, &full[p_stage]);
+      if (dbg) t_copy += clock64() - cc0;
       produced++;
+      if (++p_prog == n_steps) p_prog = 0;
+      if (++p_stage == N_STAGES) { p_stage = 0; if (produced > N_STAGES) p_phase ^= 1; }
     }
   };
-  if (tid == 0) top_up(N_STAGES);
+  constexpr int PRODUCER_TID = 32;            // lane 0 of warp 1 feeds the weight ring; lane 0 of warp 0 issues the MMAs
+  if (tid == PRODUCER_TID) top_up(N_STAGES - 1);
 
   for (long long t = 0; t < my_tiles; t++) {
     const long long tile = blockIdx.x + t * gridDim.x;
-    // ---- the tile's input: 128 rows x 448 bf16 -> K-blocks 0..6 of X (coalesced 16-byte loads, swizzled stores)
-#pragma unroll 4
-    for (int i = tid; i < TILE_M * IN_CHUNKS; i += TILE_M) {
-      const int r = i / IN_CHUNKS, c = i - r * IN_CHUNKS;
+    const long long c_in = dbg ? clock64() : 0;
+    // ---- the tile's input, straight from the observation records (BalatroFeaturesExtractor.forward's preprocessing,
+    // train_balatro_agent.py:84-113): four threads per env; thread (row, part) writes 14 of the 56 chunks of the 8-hot hand
+    // block (K-blocks 0..6: column 52 slot + card = 1 for every occupied hand slot) and two chunks of K-block 7 (joker ids as
+    // numbers at columns 0..9, the 21 scaled game scalars at columns 16..36).  bf16(1.0) = 0x3F80.
+    {
+      const int r = tid >> 2, part = tid & 3;
       const long long g = tile * TILE_M + r;
-      const uint4 v = g < n ? __ldg(act + g * IN_CHUNKS + c) : make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(X + x_offset(r, c)) = v;
+      const uint8_t* o = obs + (g < n ? g : 0) * OBS_BYTES;
+      const unsigned long long hand = g < n ? __ldg(reinterpret_cast<const unsigned long long*>(o)) : ~0ull;   // 8 x int8, -1 = empty
+#pragma unroll
+      for (int c = 0; c < 14; c++) *reinterpret_cast<uint4*>(X + x_offset(r, part * 14 + c)) = make_uint4(0, 0, 0, 0);
+      __syncwarp();      // the four threads of a row are neighbours in one warp: zeros first, then the (at most eight) ones
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int slot = 2 * part + k;
+        const int card = (int)(int8_t)(hand >> (8 * slot));
+        if (card >= 0 && card < 52) {
+          const int col = 52 * slot + card;
+          *reinterpret_cast<uint16_t*>(X + x_offset(r, col >> 3) + 2 * (col & 7)) = (uint16_t)0x3F80;
+        }
+      }
+      // K-block 7: chunks 56..63 of the row; part p writes chunks 56 + 2p, 57 + 2p
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) v[k] = 0.0f;
+      if (g < n) {
+        auto i8f = [&](int off) { return (float)*reinterpret_cast<const int8_t*>(o + off); };
+        auto i16f = [&](int off) { return (float)*reinterpret_cast<const int16_t*>(o + off); };
+        const float r10 = 1.0f / 10.0f;
+        if (part == 0) {            // columns 0..15: joker_ids[0..9]
+#pragma unroll
+          for (int k = 0; k < 10; k++) v[k] = i16f(64 + 2 * k);
+        } else if (part == 1) {     // columns 16..31: chips_scored/1e6, chips_needed/1e5, progress_ratio, money/100, ante/10, round/3,
+                                    //                 hands_left/10, discards_left/5, hand_levels[0..7]/10
+          v[0] = (float)*reinterpret_cast<const long long*>(o + 24) * (1.0f / 1e6f);
+          v[1] = (float)*reinterpret_cast<const int*>(o + 44) * (1.0f / 1e5f);
+          v[2] = *reinterpret_cast<const float*>(o + 36);
+          v[3] = (float)*reinterpret_cast<const int*>(o + 48) * (1.0f / 100.0f);
+          v[4] = i16f(60) * r10;
+          v[5] = i8f(148) * (1.0f / 3.0f);
+          v[6] = i8f(149) * r10;
+          v[7] = i8f(150) * (1.0f / 5.0f);
+#pragma unroll
+          for (int k = 0; k < 8; k++) v[8 + k] = i8f(134 + k) * r10;
+        } else if (part == 2) {     // columns 32..47: hand_levels[8..11]/10, phase/3
+#pragma unroll
+          for (int k = 0; k < 4; k++) v[k] = i8f(142 + k) * r10;
+          v[4] = i8f(155) * (1.0f / 3.0f);
+        }
+      }
+      uint4 q0, q1;
+      q0.x = pack_bf16x2(v[0], v[1]); q0.y = pack_bf16x2(v[2], v[3]); q0.z = pack_bf16x2(v[4], v[5]); q0.w = pack_bf16x2(v[6], v[7]);
+      q1.x = pack_bf16x2(v[8], v[9]); q1.y = pack_bf16x2(v[10], v[11]); q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+      *reinterpret_cast<uint4*>(X + x_offset(r, 56 + 2 * part)) = q0;
+      *reinterpret_cast<uint4*>(X + x_offset(r, 57 + 2 * part)) = q1;
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
+    if (dbg) t_in += clock64() - c_in;
     int s = 0;
     for (int group = 0; group < N_GROUPS; group++) {
-      if (tid == 0) {
+      // the group's steps: [s, s_end)
+      int s_end = s;
+      while (!c_prog[s_end].last) s_end++;
+      s_end++;
+      if (tid == PRODUCER_TID) {
+        // keep the ring N_STAGES - 1 tiles ahead of the LAST step of this group: every stage it waits for is freed by an MMA of
+        // this group or an earlier one, so it never waits on work that needs the coming epilogue (which needs this thread)
+        top_up((int)(t * n_steps) + s_end + N_STAGES - 1);
+      } else if (tid == 0) {
         tc_fence_after();
-        for (;;) {
+        for (; s < s_end; s++) {
           const BgymPolicyStep& ps = c_prog[s];
-          const int st = (int)(consumed % N_STAGES);
-          mbar_wait(&full[st], (uint32_t)((consumed / N_STAGES) & 1));
+          const long long cf = dbg ? clock64() : 0;
+          mbar_wait(&full[c_stage], c_phase);
+          if (dbg) t_full += clock64() - cf;
           tc_fence_after();
-          const uint64_t a_desc = umma_desc(smem_u32(X + ps.a_kb * KB_BYTES));
-          const uint64_t b_desc = umma_desc(smem_u32(W + st * STAGE_BYTES));
+          const uint64_t a_desc = umma_desc(x_base + (uint32_t)ps.a_kb * KB_BYTES);
+          const uint64_t b_desc = umma_desc(w_base + (uint32_t)c_stage * STAGE_BYTES);
           const uint32_t idesc = umma_idesc(ps.n);
-#pragma unroll
-          for (int k = 0; k < 4; k++)      // four K = 16 slices of the 64-column block: +32 bytes = +2 in the address field
-            umma(tmem_base + (uint32_t)ps.col, a_desc + 2 * k, b_desc + 2 * k, idesc, (ps.first && k == 0) ? 0u : 1u);
-          tc_commit(&empty[st]);
-          consumed++;
-          s++;
-          const bool last = ps.last != 0;
-          if (last) tc_commit(acc_bar);
-          top_up(consumed + N_STAGES - 1);      // waits on the stage of the tile BEFORE the one just issued: no bubble
-          if (last) break;
+          const uint32_t d_addr = tmem_base + (uint32_t)ps.col;
+          const long long cm = dbg ? clock64() : 0;
+          umma(d_addr, a_desc, b_desc, idesc, ps.first ? 0u : 1u);      // four K = 16 slices of the 64-column block:
+          umma(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);              // + 32 bytes = + 2 in the descriptor's address field
+          umma(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
+          umma(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+          if (dbg) t_mma += clock64() - cm;
+          tc_commit(&empty[c_stage]);
+          if (++c_stage == N_STAGES) { c_stage = 0; c_phase ^= 1; }
         }
-      } else {
-        // the other threads track the program position only
-        while (!c_prog[s].last) s++;
-        s++;
+        tc_commit(acc_bar);
       }
-      __syncwarp();      // warp 0 reconverges here: its other lanes do not spin on the barrier while thread 0 issues
-      mbar_wait(acc_bar, acc_parity);
+      s = s_end;
+      // Only warp 0 polls the accumulator barrier (its other lanes reconverge with thread 0 first); the other fifteen warps
+      // sleep in the CTA barrier instead of spinning on mbarrier.try_wait next to the two issuing threads.
+      __syncwarp();
+      const long long ca = dbg ? clock64() : 0;
+      if (warp == 0) mbar_wait(acc_bar, acc_parity);
       acc_parity ^= 1;
+      __syncthreads();
       tc_fence_after();
+      const long long ce = dbg ? clock64() : 0;
+      t_acc += ce - ca;
       const float* gb = bias + bias_offset(group);
-      if (group == 0) {
-        epilogue_to_x<ACT_RELU>(taddr, row, 224, gb, X);
+      if (group == 0) {          // first layers: 448 columns (hand 256 | joker 128 | game 64), slices of 128, the last one 64
+        epilogue_to_x<ACT_RELU>(taddr, row, 128 * slice, slice == 3 ? 448 : 128 * slice + 128, gb, X);
+      } else if (group == 1) {   // 224 columns: slices of 64, the last one 32 + the 32 zero columns of combined_net.0's K padding
+        epilogue_to_x<ACT_RELU>(taddr, row, 64 * slice, slice == 3 ? 224 : 64 * slice + 64, gb, X);
+        if (slice == 3) {
 #pragma unroll
-        for (int q = 28; q < 32; q++) *reinterpret_cast<uint4*>(X + x_offset(row, q)) = make_uint4(0, 0, 0, 0);   // columns 224..255: K padding of combined_net.0
-      } else if (group <= 2) {
-        epilogue_to_x<ACT_RELU>(taddr, row, 512, gb, X);
-      } else if (group <= 4) {
-        epilogue_to_x<ACT_TANH>(taddr, row, 512, gb, X);
-      } else {
+          for (int q = 28; q < 32; q++) *reinterpret_cast<uint4*>(X + x_offset(row, q)) = make_uint4(0, 0, 0, 0);
+        }
+      } else if (group <= 3) {
+        epilogue_to_x<ACT_RELU>(taddr, row, 128 * slice, 128 * slice + 128, gb, X);
+      } else if (group <= 5) {
+        epilogue_to_x<ACT_TANH>(taddr, row, 128 * slice, 128 * slice + 128, gb, X);
+      } else if (slice == 0) {
         const long long g = tile * TILE_M + row;
         uint32_t v[32];
         float4* out = reinterpret_cast<float4*>(logits + g * BGYM_POLICY_LOGITS);      // 240-byte rows: 16-byte aligned
@@ -284,10 +416,20 @@ __global__ void __launch_bounds__(TILE_M, 1) policy_mlp_kernel(const uint4* __re
         if (g < n) value[g] = __uint_as_float(v[0]) + __ldg(gb + 64);
       }
       // the next group's MMAs read what this epilogue wrote (generic proxy -> async proxy) and overwrite the accumulators it read
+      if (dbg) t_body += clock64() - ce;       // this warp's epilogue body, without the CTA barrier that follows
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
+      if (dbg) t_epi += clock64() - ce;
     }
+  }
+  if (dbg && tid == 0) {
+    long long* d = dbg + blockIdx.x * 16;
+    d[0] = clock64() - t_all; d[1] = t_in; d[2] = t_full; d[4] = t_acc; d[5] = t_epi; d[6] = my_tiles; d[7] = t_mma; d[9] = t_body;
+  }
+  if (dbg && tid == PRODUCER_TID) {
+    long long* d = dbg + blockIdx.x * 16;
+    d[3] = t_empty; d[8] = t_copy;
   }
   tc_fence_before();
   __syncthreads();
@@ -316,9 +458,9 @@ int bgym_policy_program(BgymPolicyStep* steps, int64_t* weight_bytes, int64_t* b
   return n;
 }
 
-int bgym_policy_forward(const void* act, const void* weights, const float* bias, float* logits, float* value, int64_t n, void* stream) {
-  if (n < 0 || !act || !weights || !bias || !logits || !value) { snprintf(g_perr, sizeof g_perr, "bgym_policy_forward: bad arguments"); return -1; }
-  if (((uintptr_t)act | (uintptr_t)weights) & 15) { snprintf(g_perr, sizeof g_perr, "bgym_policy_forward: act / weights must be 16-byte aligned"); return -1; }
+int bgym_policy_forward(const void* obs, const void* weights, const float* bias, float* logits, float* value, int64_t n, void* stream) {
+  if (n < 0 || !obs || !weights || !bias || !logits || !value) { snprintf(g_perr, sizeof g_perr, "bgym_policy_forward: bad arguments"); return -1; }
+  if (((uintptr_t)obs | (uintptr_t)weights | (uintptr_t)bias | (uintptr_t)logits) & 15) { snprintf(g_perr, sizeof g_perr, "bgym_policy_forward: obs / weights / bias / logits must be 16-byte aligned"); return -1; }
   if (n == 0) return 0;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -338,9 +480,25 @@ int bgym_policy_forward(const void* act, const void* weights, const float* bias,
   }
   const long long tiles = (n + TILE_M - 1) / TILE_M;
   const int grid = (int)(tiles < g_sms[dev] ? tiles : g_sms[dev]);
-  policy_mlp_kernel<<<grid, TILE_M, SMEM_BYTES, (cudaStream_t)stream>>>(reinterpret_cast<const uint4*>(act), reinterpret_cast<const uint8_t*>(weights),
-                                                                        bias, logits, value, n, n_steps);
+  // BGYM_POLICY_CLOCK=1 (diagnostic): per-CTA clocks of thread 0 — input load, waits on weight tiles, on freed stages, on the
+  // accumulators, and the epilogues — averaged over the CTAs and printed after a synchronisation
+  static const bool clocks = getenv("BGYM_POLICY_CLOCK") != nullptr;
+  long long* dbg = nullptr;
+  if (clocks) { cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long)); cudaMemset(dbg, 0, (size_t)grid * 16 * sizeof(long long)); }
+  policy_mlp_kernel<<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<const uint8_t*>(weights),
+                                                                           bias, logits, value, n, n_steps, dbg);
   e = cudaGetLastError();
+  if (clocks && e == cudaSuccess) {
+    cudaStreamSynchronize((cudaStream_t)stream);
+    long long* h = (long long*)malloc((size_t)grid * 16 * sizeof(long long));
+    cudaMemcpy(h, dbg, (size_t)grid * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+    double sum[16] = {0};
+    for (int b = 0; b < grid; b++) for (int k = 0; k < 10; k++) sum[k] += (double)h[b * 16 + k];
+    const double tiles = sum[6] > 0 ? sum[6] : 1;
+    fprintf(stderr, "[bgym policy clocks, cycles per tile] total %.0f | input %.0f | wait weights %.0f | wait stage %.0f | wait accumulators %.0f | epilogue %.0f | in the four MMA issues %.0f | copy issue (producer thread) %.0f | epilogue body of warp 0 %.0f\n",
+            sum[0] / tiles, sum[1] / tiles, sum[2] / tiles, sum[3] / tiles, sum[4] / tiles, sum[5] / tiles, sum[7] / tiles, sum[8] / tiles, sum[9] / tiles);
+    free(h); cudaFree(dbg);
+  }
   if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "bgym_policy_forward launch: %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }

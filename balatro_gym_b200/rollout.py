@@ -67,8 +67,13 @@ def policy_first_layer(obs_records, wt_hand, wt_joker, wt_game, bias, out=None):
 
 
 # ---- fused tcgen05 forward of layers 2.. (libbgym_policy.so, include/bgym_policy.h) -------------------------------
-_POLICY_LAYER_KEYS = ["hand_net.2", "joker_net.2", "game_state_net.2", "combined_net.0", "combined_net.2",
-                      "pi.0", "vf.0", "pi.2", "vf.2", "pi.4", "vf.4"]
+_POLICY_LAYER_KEYS = ["hand_net.0", "joker_net.0", "game_state_net.0", "hand_net.2", "joker_net.2", "game_state_net.2",
+                      "combined_net.0", "combined_net.2", "pi.0", "vf.0", "pi.2", "vf.2", "pi.4", "vf.4"]
+# input-column shift of a layer inside its K-block (the game scalars sit at columns 16..36 of the K-block they share with
+# the joker ids), and (epilogue group, first accumulator column) of every layer: bgym_policy.cu::LAYERS
+_POLICY_K_SHIFT = {2: 16}
+_POLICY_COL_OF = {0: (0, 0), 1: (0, 256), 2: (0, 384), 3: (1, 0), 4: (1, 128), 5: (1, 192), 6: (2, 0), 7: (3, 0),
+                  8: (4, 0), 9: (4, 256), 10: (5, 0), 11: (5, 256), 12: (6, 0), 13: (6, 64)}
 
 
 def policy_program():
@@ -76,61 +81,72 @@ def policy_program():
     import ctypes as C
     lib = _lib.load_policy()
     step_dt = np.dtype([(k, "<i4") for k in ("offset", "bytes", "layer", "n0", "n", "kb", "a_kb", "col", "first", "last", "group", "_pad")])
-    steps = np.zeros(64, dtype=step_dt)
+    steps = np.zeros(80, dtype=step_dt)
     wb, bf = C.c_int64(0), C.c_int64(0)
     n = lib.bgym_policy_program(steps.ctypes.data, C.addressof(wb), C.addressof(bf))
     return steps[:n], int(wb.value), int(bf.value)
 
 
-def pack_policy_weights(state_dict, device):
-    """Pack the eleven Linear layers after the first ones into the blobs bgym_policy_forward reads: every program step's
-    weight tile (rows [n0, n0 + n) x input columns [64 kb, 64 kb + 64), zero-padded) as n rows of 128 bytes of bf16,
-    16-byte chunk c of row r stored at chunk c ^ (r & 7) (the tensor core's 128-byte swizzle); biases per epilogue group
-    at the accumulator column they are added to."""
-    torch = _torch()
+_PACK_INDEX = {}
+
+
+def _pack_index(shapes):
+    """Gather index of the packed weight blob (one int64 per bf16 element): position in the concatenation of the eleven
+    flattened [out, in] weight matrices (+ one trailing zero element that padding points at), built once per set of layer
+    shapes.  Swizzle: 16-byte chunk c of row r is stored at chunk c ^ (r & 7)."""
+    key = tuple(shapes)
+    if key in _PACK_INDEX:
+        return _PACK_INDEX[key]
     steps, wbytes, bfloats = policy_program()
-    blob = np.zeros(wbytes // 2, dtype=np.uint16)
-    mats = []
-    for key in _POLICY_LAYER_KEYS:
-        w = state_dict[key + ".weight"].detach().to(torch.bfloat16).cpu().view(torch.int16).numpy().view(np.uint16)
-        mats.append(w)
+    base = np.concatenate([[0], np.cumsum([a * b for a, b in shapes])]).astype(np.int64)
+    zero_pos = int(base[-1])
+    index = np.full(wbytes // 2, zero_pos, dtype=np.int64)
     for st in steps:
-        w = mats[int(st["layer"])]
-        n0, n, kb = int(st["n0"]), int(st["n"]), int(st["kb"])
-        tile = np.zeros((n, 64), dtype=np.uint16)
-        rows = max(0, min(n, w.shape[0] - n0))
-        cols = max(0, min(64, w.shape[1] - 64 * kb))
-        if rows and cols:
-            tile[:rows, :cols] = w[n0:n0 + rows, 64 * kb:64 * kb + cols]
-        chunks = tile.reshape(n, 8, 8)                                   # [row, chunk, 8 bf16]
-        r = np.arange(n)[:, None]
-        pos = np.arange(8)[None, :] ^ (r & 7)                            # chunk c of row r goes to position c ^ (r & 7)
-        sw = np.zeros_like(chunks)
-        sw[r, pos] = chunks
-        off = int(st["offset"]) // 2
-        blob[off:off + n * 64] = sw.reshape(-1)
-    bias = np.zeros(bfloats, dtype=np.float32)
-    goff = lambda g: 0 if g == 0 else 256 + 512 * (g - 1)
-    col_of = {0: (0, 0), 1: (0, 128), 2: (0, 192), 3: (1, 0), 4: (2, 0), 5: (3, 0), 6: (3, 256), 7: (4, 0), 8: (4, 256), 9: (5, 0), 10: (5, 64)}
+        li, n0, n, kb = int(st["layer"]), int(st["n0"]), int(st["n"]), int(st["kb"])
+        rows_total, cols_total = shapes[li]
+        r = np.arange(n)[:, None, None]                   # tile row
+        c = np.arange(8)[None, :, None]                   # 16-byte chunk of the row (8 bf16)
+        e = np.arange(8)[None, None, :]                   # element of the chunk
+        src_row, src_col = n0 + r, 64 * kb + 8 * c + e - _POLICY_K_SHIFT.get(li, 0)
+        ok = (src_row < rows_total) & (src_col >= 0) & (src_col < cols_total)
+        src = np.where(ok, base[li] + src_row * cols_total + src_col, zero_pos)
+        dst = int(st["offset"]) // 2 + r * 64 + ((c ^ (r & 7)) * 8) + e
+        index[np.broadcast_to(dst, src.shape).reshape(-1)] = src.reshape(-1)
+    bias_at = [512 * _POLICY_COL_OF[li][0] + _POLICY_COL_OF[li][1] for li in range(len(shapes))]
+    _PACK_INDEX[key] = (index, bias_at, bfloats)
+    return _PACK_INDEX[key]
+
+
+def pack_policy_weights(state_dict, device):
+    """Pack the fourteen Linear layers into the blobs bgym_policy_forward reads (on the device: one gather): every program step's weight tile (rows [n0, n0 + n) x input columns [64 kb, 64 kb + 64), zero-padded) as n
+    rows of 128 bytes of bf16, 128-byte swizzled; biases per epilogue group at the accumulator column they are added to."""
+    torch = _torch()
+    ws = [state_dict[k + ".weight"].detach() for k in _POLICY_LAYER_KEYS]
+    index, bias_at, bfloats = _pack_index([tuple(w.shape) for w in ws])
+    cache = _PACK_INDEX.setdefault(("dev", str(device)), {})
+    if "index" not in cache:
+        cache["index"] = torch.from_numpy(index).to(device)
+    flat = torch.cat([w.to(device=device, dtype=torch.bfloat16).reshape(-1) for w in ws] + [torch.zeros(1, dtype=torch.bfloat16, device=device)])
+    blob = flat[cache["index"]].contiguous()
+    bias = torch.zeros(bfloats, dtype=torch.float32, device=device)
     for li, key in enumerate(_POLICY_LAYER_KEYS):
-        b = state_dict[key + ".bias"].detach().float().cpu().numpy()
-        g, col = col_of[li]
-        bias[goff(g) + col:goff(g) + col + b.shape[0]] = b
-    wt = torch.from_numpy(blob.view(np.int16)).to(device).view(torch.bfloat16)
-    return wt, torch.from_numpy(bias).to(device)
+        b = state_dict[key + ".bias"].detach().to(device=device, dtype=torch.float32)
+        bias[bias_at[li]:bias_at[li] + b.shape[0]] = b
+    return blob, bias
 
 
-def policy_forward_fused(act448, weights, bias, logits=None, value=None):
-    """[n, 448] bf16 first-layer activations -> (logits fp32 [n, 60], value fp32 [n]) in one tcgen05 kernel."""
+def policy_forward_fused(obs_records, weights, bias, logits=None, value=None):
+    """[n, 176] observation records -> (logits fp32 [n, 60], value fp32 [n]): the whole policy in one tcgen05 kernel
+    (bgym_policy_forward).  Reads hand, joker_ids and the game scalars of the records: fields a step keeps current."""
     torch = _torch()
     lib = _lib.load_policy()
-    n = act448.shape[0]
-    assert act448.dtype == torch.bfloat16 and act448.shape[1] == 448 and act448.is_contiguous()
-    dev = act448.device
+    n = obs_records.shape[0]
+    assert obs_records.dtype == torch.uint8 and obs_records.shape[1] == L.OBS_BYTES and obs_records.is_contiguous()
+    dev = obs_records.device
     logits = torch.empty((n, L.NUM_ACTIONS), dtype=torch.float32, device=dev) if logits is None else logits
     value = torch.empty(n, dtype=torch.float32, device=dev) if value is None else value
     with torch.cuda.device(dev):
-        rc = lib.bgym_policy_forward(act448.data_ptr(), weights.data_ptr(), bias.data_ptr(), logits.data_ptr(), value.data_ptr(), n,
+        rc = lib.bgym_policy_forward(obs_records.data_ptr(), weights.data_ptr(), bias.data_ptr(), logits.data_ptr(), value.data_ptr(), n,
                                      torch.cuda.current_stream().cuda_stream)
     if rc != 0:
         raise _lib.BgymError(f"bgym_policy_forward failed (rc={rc}): {lib.bgym_policy_last_error().decode()}")
@@ -300,9 +316,9 @@ class RolloutCollector:
             return logits.float().contiguous(), value.float()
         # first Linear + ReLU of the three sub-nets straight from the records (no one-hot feature matrix), then their
         # second layers on strided column views of that activation (lda = 448)
+        if self.fused:      # the whole policy in one tcgen05 kernel, straight from the records: activations never leave the SM
+            return policy_forward_fused(obs_records, *self._packed, logits=self._logits, value=self._value)
         a = policy_first_layer(obs_records, *self._first, out=self._feats)
-        if self.fused:      # layers 2..: one tcgen05 kernel, activations never leave the SM
-            return policy_forward_fused(a, *self._packed, logits=self._logits, value=self._value)
         h = self._mlp_from(a[:, :256], "hand_net", 1, 2)
         j = self._mlp_from(a[:, 256:384], "joker_net", 1, 2)
         g = self._mlp_from(a[:, 384:448], "game_state_net", 1, 2)

@@ -183,32 +183,31 @@ def test_rollout_collector_end_to_end(torch):
 
 
 def test_fused_policy_forward_matches_torch(torch, mixed_obs):
-    """bgym_policy_forward (eleven layers in one tcgen05 kernel, bf16 operands, fp32 accumulation in tensor memory, bf16
-    activations between layers) against the same network in torch: fp32 math on the bf16-rounded weights, with the
-    activations rounded to bf16 between layers as the kernel does.  Tolerance: accumulation order + tanh.approx (2^-11)."""
-    from balatro_gym_b200.rollout import policy_first_layer, make_policy, pack_policy_weights, policy_forward_fused, policy_program
+    """bgym_policy_forward (fourteen layers in one tcgen05 kernel straight from the observation records: bf16 operands, fp32
+    accumulation in tensor memory, bf16 activations between layers) against the same network in torch: fp32 math on the
+    bf16-rounded weights and inputs, with the activations rounded to bf16 between layers as the kernel does.
+    Tolerance: accumulation order + tanh.approx (2^-11) + one bf16 rounding per layer."""
+    from balatro_gym_b200.rollout import make_policy, pack_policy_weights, policy_forward_fused, policy_program
     steps, wbytes, bfloats = policy_program()
-    assert len(steps) == 63 and wbytes == int(steps["bytes"].sum()) and int(steps["last"].sum()) == 6
+    assert len(steps) == 72 and wbytes == int(steps["bytes"].sum()) and int(steps["last"].sum()) == 7
     v = mixed_obs
     pol = make_policy(seed=11)
     with torch.no_grad():       # make the last layers' outputs large enough to be a test
-        for k in ("pi.4", "vf.4"):
-            getattr(pol, k.split(".")[0])[4].weight.mul_(4.0)
+        pol.pi[4].weight.mul_(4.0); pol.vf[4].weight.mul_(4.0)
     sd = pol.state_dict()
     bf = lambda t: t.detach().to(torch.bfloat16)
-    wt = (bf(sd["hand_net.0.weight"]).t().contiguous(), bf(sd["joker_net.0.weight"]).t().contiguous(), bf(sd["game_state_net.0.weight"]).t().contiguous())
-    bias0 = torch.cat([sd["hand_net.0.bias"], sd["joker_net.0.bias"], sd["game_state_net.0.bias"]]).float().contiguous()
-    a = policy_first_layer(v.obs_buf, *wt, bias0)                        # [n, 448] bf16
-    weights, bias = pack_policy_weights(sd, a.device)
-    for n in (a.shape[0], 128, 129, 1):                                  # whole slab, one tile, ragged tiles
-        logits, value = policy_forward_fused(a[:n].contiguous(), weights, bias)
+    weights, bias = pack_policy_weights(sd, v.device)
+    obs = v.obs_buf
+    feats = reference_features(torch, v.obs).to(torch.bfloat16).float()            # the operands of the bf16 path
+    lin = lambda x, key: x @ bf(sd[key + ".weight"]).float().t() + sd[key + ".bias"].float()
+    r16 = lambda t: t.to(torch.bfloat16).float()
+    for n in (obs.shape[0], 128, 129, 1):                                  # whole slab, one tile, ragged tiles
+        logits, value = policy_forward_fused(obs[:n].contiguous(), weights, bias)
         torch.cuda.synchronize()
-        x = a[:n].float()
-        lin = lambda x, key: x @ bf(sd[key + ".weight"]).float().t() + sd[key + ".bias"].float()
-        r16 = lambda t: t.to(torch.bfloat16).float()
-        h = r16(torch.relu(lin(x[:, :256], "hand_net.2")))
-        j = r16(torch.relu(lin(x[:, 256:384], "joker_net.2")))
-        g = r16(torch.relu(lin(x[:, 384:448], "game_state_net.2")))
+        x = feats[:n]
+        h = r16(torch.relu(lin(x[:, :416], "hand_net.0"))); h = r16(torch.relu(lin(h, "hand_net.2")))
+        j = r16(torch.relu(lin(x[:, 416:426], "joker_net.0"))); j = r16(torch.relu(lin(j, "joker_net.2")))
+        g = r16(torch.relu(lin(x[:, 426:447], "game_state_net.0"))); g = r16(torch.relu(lin(g, "game_state_net.2")))
         z = r16(torch.relu(lin(torch.cat([h, j, g], dim=1), "combined_net.0")))
         z = r16(torch.relu(lin(z, "combined_net.2")))
         p = r16(torch.tanh(lin(z, "pi.0"))); p = r16(torch.tanh(lin(p, "pi.2"))); ref_logits = lin(p, "pi.4")
