@@ -485,22 +485,31 @@ def bench_ppo_rollout(torch, bdist, dev, args, rank, ws):
         return a.elapsed_time(b) / reps
     obs0 = roll.obs[0]
     with torch.no_grad():
-        t_feat = timed(lambda: featurize(obs0, out=roll._feats))
         roll.refresh_inference_weights()
-        t_fwd = timed(lambda: roll._forward(obs0)) - t_feat      # _forward = featurize + MLP
+        t_fwd = timed(lambda: roll._forward(obs0))          # the whole policy: one tcgen05 kernel straight from the records
         logits = roll._forward(obs0)[0]
         t_samp = timed(lambda: masked_sample(logits, obs0, seed=1, step=0, actions=roll.actions[0], logp=roll.logp[0], entropy=roll.entropy[0]))
         t_step = timed(lambda: vec.step(roll.actions[0], want_info=False))
         t_copy = timed(lambda: roll.obs[1].copy_(vec.obs_buf))
         t_gae = timed(lambda: gae(roll.rewards, roll.values, roll.dones, 0.99, 0.95, roll.advantages, roll.returns))
+        # the library-GEMM path of the same forward (first-layer kernel + eleven cuBLASLt GEMMs), for comparison
+        roll.fused = False
+        t_lib = timed(lambda: roll._forward(obs0))
+        roll.fused = True
     if rank != 0:
         return None
+    flops = 2 * n * (416 * 256 + 10 * 128 + 21 * 64 + 256 * 128 + 128 * 64 + 64 * 32 + 224 * 512 + 512 * 512 + 2 * (512 * 256 + 256 * 256) + 256 * 61)
     return {"value": ws * n * T / (ms / 1e3), "unit": "env-steps/s", "envs_per_gpu": n, "rollout_steps": T,
             "ms_per_step": ms / T,
-            "breakdown_ms": {"featurize": t_feat, "policy_forward_bf16": t_fwd, "masked_sample": t_samp, "env_step": t_step,
+            "breakdown_ms": {"policy_forward_fused_tcgen05": t_fwd, "masked_sample": t_samp, "env_step": t_step,
                              "obs_copy": t_copy, "gae_whole_rollout": t_gae},
-            "policy": "BalatroFeaturesExtractor topology (416|10|21 -> 224 -> 512 -> 512) + pi/vf [256,256] heads, bf16 weights, cuBLASLt bias+ReLU epilogues",
-            "note": "the MLP forward (policy side, library GEMMs) dominates; the env path's own kernels are featurize + masked_sample + env_step + gae"}
+            "policy_forward_library_gemms_ms": t_lib,
+            "policy_forward_tflops": flops / t_fwd / 1e9,
+            "policy": "BalatroFeaturesExtractor topology (416|10|21 -> 224 -> 512 -> 512) + pi/vf [256,256] heads, bf16 weights: all 14 "
+                      "layers in ONE tcgen05 kernel straight from the observation records (libbgym_policy.so; activations in "
+                      "swizzled shared memory, fp32 accumulators in tensor memory, weights streamed by bulk copies)",
+            "note": "policy_forward_library_gemms_ms = the same forward as first-layer kernel + eleven cuBLASLt GEMMs with bias+ReLU epilogues "
+                    "(what round 1 and the first half of round 2 ran)"}
 
 
 def bench_hands(torch, b, dev, peak, args):

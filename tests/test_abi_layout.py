@@ -23,6 +23,28 @@ def test_library_exports_all_declared_symbols():
     assert lib.bgym_device_count() >= 0
 
 
+def test_policy_library_exports_its_header_and_program():
+    """libbgym_policy.so (include/bgym_policy.h, the fused tcgen05 policy forward): loads, exports every declared symbol,
+    and its weight-tile program is self-consistent (no GPU needed: the program is host code)."""
+    import ctypes as C
+    lib = _lib.load_policy()
+    hdr = open(os.path.join(REPO, "include", "bgym_policy.h")).read()
+    declared = set(re.findall(r"\b(bgym_policy_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.POLICY_SYMBOLS), declared ^ set(_lib.POLICY_SYMBOLS)
+    step_dt = np.dtype([(k, "<i4") for k in ("offset", "bytes", "layer", "n0", "n", "kb", "a_kb", "col", "first", "last", "group", "_pad")])
+    steps = np.zeros(80, dtype=step_dt)
+    wb, bf = C.c_int64(0), C.c_int64(0)
+    n = lib.bgym_policy_program(steps.ctypes.data, C.addressof(wb), C.addressof(bf))
+    steps = steps[:n]
+    assert n == 72 and steps.itemsize == 48
+    assert np.array_equal(steps["offset"], np.concatenate([[0], np.cumsum(steps["bytes"])[:-1]])) and wb.value == int(steps["bytes"].sum())
+    assert (steps["bytes"] == 128 * steps["n"]).all() and (steps["n"] % 16 == 0).all() and steps["n"].max() == 256
+    assert (steps["col"] + steps["n"] <= 512).all() and (steps["a_kb"] < 8).all()          # tensor memory columns, activation K-blocks
+    assert int(steps["last"].sum()) == 7 and steps["last"][-1] == 1 and bf.value == 512 * 7
+    assert (np.diff(steps["group"]) >= 0).all()
+    assert lib.bgym_policy_forward(None, None, None, None, None, 4, None) < 0 and b"bad arguments" in lib.bgym_policy_last_error()
+
+
 def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
     assert lib.bgym_step(None, None, None, None, None, None, None, None, None, None, None, None, 4, 0, None) < 0
