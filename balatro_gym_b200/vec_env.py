@@ -346,7 +346,11 @@ class BalatroVecEnv:
             _lib.check(rc, "bgym_step")
             self._hot_whole = self._obs_whole = False
 
-        side = torch.cuda.Stream(device=self.device)
+        # ONE capture stream per env object: bgym_step keeps its work lists per (device, stream), and a captured graph points
+        # at them — re-capturing on the same stream reuses that scratch instead of taking a new slot every time
+        if not hasattr(self, "_graph_stream"):
+            self._graph_stream = torch.cuda.Stream(device=self.device)
+        side = self._graph_stream
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):          # warm-up on the capture stream: per-stream scratch is allocated here
             for _ in range(2):
