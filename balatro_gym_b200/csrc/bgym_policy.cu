@@ -40,10 +40,10 @@ constexpr int TILE_M = 128;
 constexpr int N_THREADS = 512;
 constexpr int KB_BYTES = TILE_M * 128;            // one K-block of the activation tile: 16 KB
 constexpr int X_BYTES = 8 * KB_BYTES;             // 128 KB
-constexpr int STAGE_BYTES = 256 * 128;            // 32 KB: the largest weight tile
-constexpr int N_STAGES = 3;
-constexpr int BAR_OFFSET = X_BYTES + N_STAGES * STAGE_BYTES;
-constexpr int SMEM_BYTES = BAR_OFFSET + 128;
+constexpr int RING_BYTES = 3 * 256 * 128;         // 96 KB of weight stages: 3 x 32 KB (the largest weight tile), or 6 x 16 KB for CTA pairs
+constexpr int MAX_STAGES = 6;
+constexpr int BAR_OFFSET = X_BYTES + RING_BYTES;
+constexpr int SMEM_BYTES = BAR_OFFSET + 256;
 constexpr int OBS_BYTES = 176;                   // BgymObs (include/bgym.h)
 
 struct LayerDef { int n_real, k_real, n_pad, k_blocks, a_kb, col, group; };
@@ -111,6 +111,26 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- CTA pairs (cta_group::2): one MMA over 256 envs, each CTA holding its 128 rows of A and HALF the rows of every weight tile
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {      // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t rank) {      // arrive on the same barrier of CTA `rank`
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+      "r"(accumulate), "r"(0u) : "memory");
+}
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start address >> 4 | LBO 1 (unused with
 // a swizzle) << 16 | SBO = 1024 B between 8-row groups, >> 4, << 32 | version 1 << 46 | layout type 2 << 61
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -118,7 +138,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (1 << 4), A and B bf16 (1 << 7, 1 << 10), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24
-__device__ __forceinline__ uint32_t umma_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24); }
+__device__ __forceinline__ uint32_t umma_idesc(int n, int m = TILE_M) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -213,36 +233,51 @@ __device__ __forceinline__ void epilogue_to_x(uint32_t taddr, int row, int c_beg
   }
 }
 
+template <int CTAS>      // 1: every CTA on its own; 2: clusters of two CTAs issuing cta_group::2 MMAs (M = 256)
 __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t* __restrict__ obs, const uint8_t* __restrict__ weights,
                                                                const float* __restrict__ bias, float* __restrict__ logits,
                                                                float* __restrict__ value, long long n, int n_steps, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* X = smem;
   uint8_t* W = smem + X_BYTES;
+  // a CTA of a pair holds half of every weight tile: twice the stages at half the size, i.e. a longer prefetch distance for
+  // the same 96 KB (the leader learns of the peer's half through one more barrier hop)
+  constexpr int N_STAGES = 3 * CTAS, STAGE_BYTES = RING_BYTES / N_STAGES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);   // [N_STAGES] weight tile landed
-  uint64_t* empty = full + N_STAGES;                                 // [N_STAGES] the MMAs that read the stage are done
-  uint64_t* acc_bar = empty + N_STAGES;                              // the group's accumulators are complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* empty = full + MAX_STAGES;                               // [N_STAGES] the MMAs that read the stage are done
+  uint64_t* acc_bar = empty + MAX_STAGES;                            // the group's accumulators are complete
+  uint64_t* peer_full = acc_bar + 1;                                 // [N_STAGES] (pairs, leader only) the peer's half of the tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(peer_full + MAX_STAGES);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  auto cta_sync = [&]() { if (CTAS == 2) cluster_sync(); else __syncthreads(); };    // every CTA of the MMA group
   if (tid == 0) {
-    for (int i = 0; i < N_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < N_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&peer_full[i], 1); }
     mbar_init(acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {      // one warp allocates all 512 columns of tensor memory (1 CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 0) {      // one warp (of each CTA of the group) allocates all 512 columns of tensor memory (1 CTA per SM)
+    if (CTAS == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  cta_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int quarter = warp & 3, slice = warp >> 2;                       // accumulator lanes 32 quarter .. + 31, column slice 0..3
   const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
   const int row = quarter * 32 + (tid & 31);
 
-  const long long n_tiles = (n + TILE_M - 1) / TILE_M;
-  const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // a GROUP = CTAS consecutive env tiles; groups are dealt to the clusters round-robin, so both CTAs of a pair run the same
+  // number of iterations (a tile past the end is processed as all-padding: it must still take part in the pair's MMAs)
+  const long long n_groups_total = ((n + TILE_M - 1) / TILE_M + CTAS - 1) / CTAS;
+  const long long cluster_id = blockIdx.x / CTAS, n_clusters = gridDim.x / CTAS;
+  const long long my_tiles = cluster_id < n_groups_total ? (n_groups_total - cluster_id + n_clusters - 1) / n_clusters : 0;
   const long long total_steps = my_tiles * n_steps;
   const uint32_t x_base = smem_u32(X), w_base = smem_u32(W);
   // thread 0's pipeline state — small integers only: stage indices and phase bits advance by increment-and-wrap (64-bit
@@ -263,8 +298,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
       }
       const long long cc0 = dbg ? clock64() : 0;
       const BgymPolicyStep& ps = c_prog[p_prog];
-      mbar_expect_tx(&full[p_stage], (uint32_t)ps.bytes);
-      bulk_g2s(W + p_stage * STAGE_BYTES, weights + ps.offset, (uint32_t)ps.bytes, &full[p_stage]);
+      const uint32_t part = (uint32_t)ps.bytes / CTAS;            // a CTA of a pair holds half the rows of the weight tile
+      mbar_expect_tx(&full[p_stage], part);
+      bulk_g2s(W + p_stage * STAGE_BYTES, weights + ps.offset + rank * part, part, &full[p_stage]);
       if (dbg) t_copy += clock64() - cc0;
       produced++;
       if (++p_prog == n_steps) p_prog = 0;
@@ -275,7 +311,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
   if (tid == PRODUCER_TID) top_up(N_STAGES - 1);
 
   for (long long t = 0; t < my_tiles; t++) {
-    const long long tile = blockIdx.x + t * gridDim.x;
+    const long long tile = (cluster_id + t * n_clusters) * CTAS + rank;
     const long long c_in = dbg ? clock64() : 0;
     // ---- the tile's input, straight from the observation records (BalatroFeaturesExtractor.forward's preprocessing,
     // train_balatro_agent.py:84-113): four threads per env; thread (row, part) writes 14 of the 56 chunks of the 8-hot hand
@@ -335,7 +371,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    cta_sync();
     if (dbg) t_in += clock64() - c_in;
     int s = 0;
     for (int group = 0; group < N_GROUPS; group++) {
@@ -347,28 +383,43 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
         // keep the ring N_STAGES - 1 tiles ahead of the LAST step of this group: every stage it waits for is freed by an MMA of
         // this group or an earlier one, so it never waits on work that needs the coming epilogue (which needs this thread)
         top_up((int)(t * n_steps) + s_end + N_STAGES - 1);
-      } else if (tid == 0) {
+      } else if (tid == 0 && rank == 0) {
         tc_fence_after();
         for (; s < s_end; s++) {
           const BgymPolicyStep& ps = c_prog[s];
           const long long cf = dbg ? clock64() : 0;
           mbar_wait(&full[c_stage], c_phase);
+          if (CTAS == 2) mbar_wait(&peer_full[c_stage], c_phase);
           if (dbg) t_full += clock64() - cf;
           tc_fence_after();
           const uint64_t a_desc = umma_desc(x_base + (uint32_t)ps.a_kb * KB_BYTES);
           const uint64_t b_desc = umma_desc(w_base + (uint32_t)c_stage * STAGE_BYTES);
-          const uint32_t idesc = umma_idesc(ps.n);
+          const uint32_t idesc = umma_idesc(ps.n, TILE_M * CTAS);
           const uint32_t d_addr = tmem_base + (uint32_t)ps.col;
           const long long cm = dbg ? clock64() : 0;
-          umma(d_addr, a_desc, b_desc, idesc, ps.first ? 0u : 1u);      // four K = 16 slices of the 64-column block:
-          umma(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);              // + 32 bytes = + 2 in the descriptor's address field
-          umma(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
-          umma(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+          if (CTAS == 2) {
+            umma_pair(d_addr, a_desc, b_desc, idesc, ps.first ? 0u : 1u);
+            umma_pair(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);
+            umma_pair(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
+            umma_pair(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+          } else {
+            umma(d_addr, a_desc, b_desc, idesc, ps.first ? 0u : 1u);      // four K = 16 slices of the 64-column block:
+            umma(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);              // + 32 bytes = + 2 in the descriptor's address field
+            umma(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
+            umma(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+          }
           if (dbg) t_mma += clock64() - cm;
-          tc_commit(&empty[c_stage]);
+          if (CTAS == 2) tc_commit_pair(&empty[c_stage]); else tc_commit(&empty[c_stage]);
           if (++c_stage == N_STAGES) { c_stage = 0; c_phase ^= 1; }
         }
-        tc_commit(acc_bar);
+        if (CTAS == 2) tc_commit_pair(acc_bar); else tc_commit(acc_bar);
+      } else if (CTAS == 2 && tid == 0) {
+        // the peer's thread 0 tells the leader when this CTA's half of a weight tile has landed
+        for (; s < s_end; s++) {
+          mbar_wait(&full[c_stage], c_phase);
+          mbar_arrive_remote(&peer_full[c_stage], 0);
+          if (++c_stage == N_STAGES) { c_stage = 0; c_phase ^= 1; }
+        }
       }
       s = s_end;
       // Only warp 0 polls the accumulator barrier (its other lanes reconverge with thread 0 first); the other fifteen warps
@@ -419,7 +470,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
       if (dbg) t_body += clock64() - ce;       // this warp's epilogue body, without the CTA barrier that follows
       fence_proxy_async();
       tc_fence_before();
-      __syncthreads();
+      cta_sync();
       if (dbg) t_epi += clock64() - ce;
     }
   }
@@ -432,8 +483,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
     d[3] = t_empty; d[8] = t_copy;
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  cta_sync();
+  if (warp == 0) {
+    if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
 }
 
 thread_local char g_perr[256] = "";
@@ -472,21 +526,39 @@ int bgym_policy_forward(const void* obs, const void* weights, const float* bias,
     std::lock_guard<std::mutex> lock(g_pmu);
     if (!g_ready[dev]) {
       e = cudaMemcpyToSymbol(c_prog, prog, sizeof prog);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_mlp_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
       if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev);
       if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "bgym_policy_forward setup: %s", cudaGetErrorString(e)); return (int)e; }
       g_ready[dev] = true;
     }
   }
+  // BGYM_POLICY_CTAS=2: clusters of two CTAs, one cta_group::2 MMA (M = 256) per weight-tile slice; default: single CTAs
+  static const int ctas = (getenv("BGYM_POLICY_CTAS") && atoi(getenv("BGYM_POLICY_CTAS")) == 2) ? 2 : 1;
   const long long tiles = (n + TILE_M - 1) / TILE_M;
-  const int grid = (int)(tiles < g_sms[dev] ? tiles : g_sms[dev]);
+  const long long groups = (tiles + ctas - 1) / ctas;
+  const long long max_clusters = g_sms[dev] / ctas;
+  const int grid = (int)((groups < max_clusters ? groups : max_clusters) * ctas);
   // BGYM_POLICY_CLOCK=1 (diagnostic): per-CTA clocks of thread 0 — input load, waits on weight tiles, on freed stages, on the
   // accumulators, and the epilogues — averaged over the CTAs and printed after a synchronisation
   static const bool clocks = getenv("BGYM_POLICY_CLOCK") != nullptr;
   long long* dbg = nullptr;
   if (clocks) { cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(long long)); cudaMemset(dbg, 0, (size_t)grid * 16 * sizeof(long long)); }
-  policy_mlp_kernel<<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<const uint8_t*>(weights),
-                                                                           bias, logits, value, n, n_steps, dbg);
+  if (ctas == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(N_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, policy_mlp_kernel<2>, reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<const uint8_t*>(weights), bias,
+                           logits, value, (long long)n, n_steps, dbg);
+    if (e != cudaSuccess) { snprintf(g_perr, sizeof g_perr, "bgym_policy_forward launch (pairs): %s", cudaGetErrorString(e)); return (int)e; }
+  } else {
+    policy_mlp_kernel<1><<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(reinterpret_cast<const uint8_t*>(obs), reinterpret_cast<const uint8_t*>(weights),
+                                                                              bias, logits, value, n, n_steps, dbg);
+  }
   e = cudaGetLastError();
   if (clocks && e == cudaSuccess) {
     cudaStreamSynchronize((cudaStream_t)stream);

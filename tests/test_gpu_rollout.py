@@ -217,3 +217,18 @@ def test_fused_policy_forward_matches_torch(torch, mixed_obs):
         scale = float(ref_logits.abs().max())
         assert err_l < 0.03 * max(1.0, scale) and err_v < 0.03 * max(1.0, float(ref_value.abs().max())), (n, err_l, err_v, scale)
         assert scale > 0.3
+
+
+def test_fused_policy_forward_cta_pairs(torch):
+    """The cta_group::2 variant of the policy kernel (clusters of two CTAs, M = 256 MMAs, each CTA holding half of every weight
+    tile; BGYM_POLICY_CTAS=2, read once per process): the same torch comparison in a child process."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("BGYM_POLICY_CTAS") == "2":
+        pytest.skip("already the child")
+    env = dict(os.environ, BGYM_POLICY_CTAS="2")
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_rollout.py"), "-q", "-x", "-m", "gpu", "-k",
+                          "fused_policy_forward_matches_torch"], env=env, capture_output=True, text=True, timeout=300, cwd=os.path.dirname(here))
+    assert res.returncode == 0 and "1 passed" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
