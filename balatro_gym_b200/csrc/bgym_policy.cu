@@ -10,8 +10,8 @@
 //       same layout) streamed from L2 with 1-D bulk async copies (cp.async.bulk, completion on an mbarrier), two tiles
 //       ahead of the MMA that consumes them, across layer and tile boundaries;
 //   D   the accumulators: all 512 columns of tensor memory (fp32, lane = env).
-// Thread 0 issues the bulk copies and the MMAs (tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 16..256, K = 16, four per
-// weight tile); tcgen05.commit hands a weight stage back to the copy ring and, after the last tile of a layer group,
+// Warp 1 issues the bulk copies, warp 0 the MMAs (tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 16..256, K = 16, four per
+// weight tile; one elected lane each, the loops themselves warp-uniform); tcgen05.commit hands a weight stage back to the copy ring and, after the last tile of a layer group,
 // wakes all sixteen warps: warp w reads accumulator lanes 32 (w % 4) .. + 31 (the quarter of tensor memory a warp may
 // address), columns of slice w / 4, with tcgen05.ld (32x32b.x32), adds the bias, applies ReLU / tanh, rounds to bf16 and
 // stores the next operand into X (or the logits / value to global memory after the last group).  Four warps per
@@ -110,6 +110,17 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one lane of a converged warp (elect.sync): the issuing warps run their loops WARP-UNIFORMLY and predicate only the issue
+// itself, so that descriptors, addresses and barrier operands live in uniform registers — issued from a single divergent
+// thread, every tcgen05.mma was wrapped by the compiler in a lane loop (R2UR + BRA.U.ANY) costing ~70 cycles
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 // ---- CTA pairs (cta_group::2): one MMA over 256 envs, each CTA holding its 128 rows of A and HALF the rows of every weight tile
 __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {      // arrives on the barrier at this offset in BOTH CTAs
@@ -299,16 +310,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
       const long long cc0 = dbg ? clock64() : 0;
       const BgymPolicyStep& ps = c_prog[p_prog];
       const uint32_t part = (uint32_t)ps.bytes / CTAS;            // a CTA of a pair holds half the rows of the weight tile
-      mbar_expect_tx(&full[p_stage], part);
-      bulk_g2s(W + p_stage * STAGE_BYTES, weights + ps.offset + rank * part, part, &full[p_stage]);
+      if (elect_one()) {
+        mbar_expect_tx(&full[p_stage], part);
+        bulk_g2s(W + p_stage * STAGE_BYTES, weights + ps.offset + rank * part, part, &full[p_stage]);
+      }
+      __syncwarp();
       if (dbg) t_copy += clock64() - cc0;
       produced++;
       if (++p_prog == n_steps) p_prog = 0;
       if (++p_stage == N_STAGES) { p_stage = 0; if (produced > N_STAGES) p_phase ^= 1; }
     }
   };
-  constexpr int PRODUCER_TID = 32;            // lane 0 of warp 1 feeds the weight ring; lane 0 of warp 0 issues the MMAs
-  if (tid == PRODUCER_TID) top_up(N_STAGES - 1);
+  constexpr int PRODUCER_WARP = 1;            // warp 1 feeds the weight ring, warp 0 issues the MMAs (one elected lane each)
+  if (warp == PRODUCER_WARP) top_up(N_STAGES - 1);
 
   for (long long t = 0; t < my_tiles; t++) {
     const long long tile = (cluster_id + t * n_clusters) * CTAS + rank;
@@ -379,11 +393,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
       int s_end = s;
       while (!c_prog[s_end].last) s_end++;
       s_end++;
-      if (tid == PRODUCER_TID) {
+      if (warp == PRODUCER_WARP) {
         // keep the ring N_STAGES - 1 tiles ahead of the LAST step of this group: every stage it waits for is freed by an MMA of
         // this group or an earlier one, so it never waits on work that needs the coming epilogue (which needs this thread)
         top_up((int)(t * n_steps) + s_end + N_STAGES - 1);
-      } else if (tid == 0 && rank == 0) {
+      } else if (warp == 0 && rank == 0) {
         tc_fence_after();
         for (; s < s_end; s++) {
           const BgymPolicyStep& ps = c_prog[s];
@@ -397,27 +411,33 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
           const uint32_t idesc = umma_idesc(ps.n, TILE_M * CTAS);
           const uint32_t d_addr = tmem_base + (uint32_t)ps.col;
           const long long cm = dbg ? clock64() : 0;
-          if (CTAS == 2) {
-            umma_pair(d_addr, a_desc, b_desc, idesc, ps.first ? 0u : 1u);
-            umma_pair(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);
-            umma_pair(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
-            umma_pair(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
-          } else {
-            umma(d_addr, a_desc, b_desc, idesc, ps.first ? 0u : 1u);      // four K = 16 slices of the 64-column block:
-            umma(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);              // + 32 bytes = + 2 in the descriptor's address field
-            umma(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
-            umma(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+          if (elect_one()) {
+            if (CTAS == 2) {
+              umma_pair(d_addr, a_desc, b_desc, idesc, ps.first ? 0u : 1u);
+              umma_pair(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);
+              umma_pair(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
+              umma_pair(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+              tc_commit_pair(&empty[c_stage]);
+            } else {
+              umma(d_addr, a_desc, b_desc, idesc, ps.first ? 0u : 1u);      // four K = 16 slices of the 64-column block:
+              umma(d_addr, a_desc + 2, b_desc + 2, idesc, 1u);              // + 32 bytes = + 2 in the descriptor's address field
+              umma(d_addr, a_desc + 4, b_desc + 4, idesc, 1u);
+              umma(d_addr, a_desc + 6, b_desc + 6, idesc, 1u);
+              tc_commit(&empty[c_stage]);
+            }
           }
+          __syncwarp();
           if (dbg) t_mma += clock64() - cm;
-          if (CTAS == 2) tc_commit_pair(&empty[c_stage]); else tc_commit(&empty[c_stage]);
           if (++c_stage == N_STAGES) { c_stage = 0; c_phase ^= 1; }
         }
-        if (CTAS == 2) tc_commit_pair(acc_bar); else tc_commit(acc_bar);
-      } else if (CTAS == 2 && tid == 0) {
+        if (elect_one()) { if (CTAS == 2) tc_commit_pair(acc_bar); else tc_commit(acc_bar); }
+        __syncwarp();
+      } else if (CTAS == 2 && warp == 0) {
         // the peer's thread 0 tells the leader when this CTA's half of a weight tile has landed
         for (; s < s_end; s++) {
           mbar_wait(&full[c_stage], c_phase);
-          mbar_arrive_remote(&peer_full[c_stage], 0);
+          if (elect_one()) mbar_arrive_remote(&peer_full[c_stage], 0);
+          __syncwarp();
           if (++c_stage == N_STAGES) { c_stage = 0; c_phase ^= 1; }
         }
       }
@@ -478,7 +498,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
     long long* d = dbg + blockIdx.x * 16;
     d[0] = clock64() - t_all; d[1] = t_in; d[2] = t_full; d[4] = t_acc; d[5] = t_epi; d[6] = my_tiles; d[7] = t_mma; d[9] = t_body;
   }
-  if (dbg && tid == PRODUCER_TID) {
+  if (dbg && tid == PRODUCER_WARP * 32) {
     long long* d = dbg + blockIdx.x * 16;
     d[3] = t_empty; d[8] = t_copy;
   }
