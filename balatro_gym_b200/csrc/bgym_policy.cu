@@ -37,7 +37,13 @@
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int N_THREADS = 512;
+constexpr int TILE_M_CONST = 128;
+#ifndef BGYM_POLICY_THREADS
+#define BGYM_POLICY_THREADS 512
+#endif
+constexpr int N_THREADS = BGYM_POLICY_THREADS;   // 512, or 1024 (64 registers per thread; measured 1.43 ms against 1.24)
+constexpr int SLICES = N_THREADS / 128;          // column slices of an epilogue (warps per accumulator lane quarter)
+constexpr int PARTS = N_THREADS / TILE_M_CONST;  // threads per env in the input stage
 constexpr int KB_BYTES = TILE_M * 128;            // one K-block of the activation tile: 16 KB
 constexpr int X_BYTES = 8 * KB_BYTES;             // 128 KB
 constexpr int RING_BYTES = 3 * 256 * 128;         // 96 KB of weight stages: 3 x 32 KB (the largest weight tile), or 6 x 16 KB for CTA pairs
@@ -168,11 +174,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
@@ -231,6 +232,7 @@ __device__ __forceinline__ void epilogue16(const uint32_t* v, int row, int c0, c
 // of X.  Two 16-column register buffers: the tensor-memory load of one is in flight while the other is processed.
 template <int ACT>
 __device__ __forceinline__ void epilogue_to_x(uint32_t taddr, int row, int c_begin, int c_end, const float* __restrict__ bias, uint8_t* X) {
+  if (c_begin >= c_end) return;
   uint32_t a[16], b[16];
   tmem_ld16_async(taddr + (uint32_t)c_begin, a);
   tmem_wait16(a);
@@ -280,7 +282,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
   cta_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int quarter = warp & 3, slice = warp >> 2;                       // accumulator lanes 32 quarter .. + 31, column slice 0..3
+  const int quarter = warp & 3, slice = warp >> 2;                       // accumulator lanes 32 quarter .. + 31, column slice 0..SLICES-1
+  // this warp's share [c_lo, c_hi) of an epilogue over ncols columns (multiples of 32)
+  auto slice_lo = [&](int ncols) { const int cps = ((ncols + SLICES * 32 - 1) / (SLICES * 32)) * 32; const int lo = slice * cps; return lo < ncols ? lo : ncols; };
+  auto slice_hi = [&](int ncols) { const int cps = ((ncols + SLICES * 32 - 1) / (SLICES * 32)) * 32; const int hi = slice * cps + cps; return hi < ncols ? hi : ncols; };
   const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
   const int row = quarter * 32 + (tid & 31);
 
@@ -332,16 +337,16 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
     // block (K-blocks 0..6: column 52 slot + card = 1 for every occupied hand slot) and two chunks of K-block 7 (joker ids as
     // numbers at columns 0..9, the 21 scaled game scalars at columns 16..36).  bf16(1.0) = 0x3F80.
     {
-      const int r = tid >> 2, part = tid & 3;
+      const int r = tid / PARTS, part = tid % PARTS;
       const long long g = tile * TILE_M + r;
       const uint8_t* o = obs + (g < n ? g : 0) * OBS_BYTES;
       const unsigned long long hand = g < n ? __ldg(reinterpret_cast<const unsigned long long*>(o)) : ~0ull;   // 8 x int8, -1 = empty
 #pragma unroll
-      for (int c = 0; c < 14; c++) *reinterpret_cast<uint4*>(X + x_offset(r, part * 14 + c)) = make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < 56 / PARTS; c++) *reinterpret_cast<uint4*>(X + x_offset(r, part * (56 / PARTS) + c)) = make_uint4(0, 0, 0, 0);
       __syncwarp();      // the four threads of a row are neighbours in one warp: zeros first, then the (at most eight) ones
 #pragma unroll
-      for (int k = 0; k < 2; k++) {
-        const int slot = 2 * part + k;
+      for (int k = 0; k < 8 / PARTS; k++) {
+        const int slot = (8 / PARTS) * part + k;
         const int card = (int)(int8_t)(hand >> (8 * slot));
         if (card >= 0 && card < 52) {
           const int col = 52 * slot + card;
@@ -356,10 +361,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
         auto i8f = [&](int off) { return (float)*reinterpret_cast<const int8_t*>(o + off); };
         auto i16f = [&](int off) { return (float)*reinterpret_cast<const int16_t*>(o + off); };
         const float r10 = 1.0f / 10.0f;
-        if (part == 0) {            // columns 0..15: joker_ids[0..9]
+        const int pp = part * 4 / PARTS;      // which 16 columns of K-block 7 this thread's values belong to
+        if (pp == 0) {              // columns 0..15: joker_ids[0..9]
 #pragma unroll
           for (int k = 0; k < 10; k++) v[k] = i16f(64 + 2 * k);
-        } else if (part == 1) {     // columns 16..31: chips_scored/1e6, chips_needed/1e5, progress_ratio, money/100, ante/10, round/3,
+        } else if (pp == 1) {       // columns 16..31: chips_scored/1e6, chips_needed/1e5, progress_ratio, money/100, ante/10, round/3,
                                     //                 hands_left/10, discards_left/5, hand_levels[0..7]/10
           v[0] = (float)*reinterpret_cast<const long long*>(o + 24) * (1.0f / 1e6f);
           v[1] = (float)*reinterpret_cast<const int*>(o + 44) * (1.0f / 1e5f);
@@ -371,7 +377,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
           v[7] = i8f(150) * (1.0f / 5.0f);
 #pragma unroll
           for (int k = 0; k < 8; k++) v[8 + k] = i8f(134 + k) * r10;
-        } else if (part == 2) {     // columns 32..47: hand_levels[8..11]/10, phase/3
+        } else if (pp == 2) {       // columns 32..47: hand_levels[8..11]/10, phase/3
 #pragma unroll
           for (int k = 0; k < 4; k++) v[k] = i8f(142 + k) * r10;
           v[4] = i8f(155) * (1.0f / 3.0f);
@@ -380,8 +386,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
       uint4 q0, q1;
       q0.x = pack_bf16x2(v[0], v[1]); q0.y = pack_bf16x2(v[2], v[3]); q0.z = pack_bf16x2(v[4], v[5]); q0.w = pack_bf16x2(v[6], v[7]);
       q1.x = pack_bf16x2(v[8], v[9]); q1.y = pack_bf16x2(v[10], v[11]); q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-      *reinterpret_cast<uint4*>(X + x_offset(r, 56 + 2 * part)) = q0;
-      *reinterpret_cast<uint4*>(X + x_offset(r, 57 + 2 * part)) = q1;
+      if (PARTS == 4) {
+        *reinterpret_cast<uint4*>(X + x_offset(r, 56 + 2 * part)) = q0;
+        *reinterpret_cast<uint4*>(X + x_offset(r, 57 + 2 * part)) = q1;
+      } else {
+        *reinterpret_cast<uint4*>(X + x_offset(r, 56 + part)) = (part & 1) ? q1 : q0;
+      }
     }
     fence_proxy_async();
     tc_fence_before();
@@ -453,18 +463,18 @@ __global__ void __launch_bounds__(N_THREADS, 1) policy_mlp_kernel(const uint8_t*
       const long long ce = dbg ? clock64() : 0;
       t_acc += ce - ca;
       const float* gb = bias + bias_offset(group);
-      if (group == 0) {          // first layers: 448 columns (hand 256 | joker 128 | game 64), slices of 128, the last one 64
-        epilogue_to_x<ACT_RELU>(taddr, row, 128 * slice, slice == 3 ? 448 : 128 * slice + 128, gb, X);
-      } else if (group == 1) {   // 224 columns: slices of 64, the last one 32 + the 32 zero columns of combined_net.0's K padding
-        epilogue_to_x<ACT_RELU>(taddr, row, 64 * slice, slice == 3 ? 224 : 64 * slice + 64, gb, X);
-        if (slice == 3) {
+      if (group == 0) {          // first layers: 448 columns (hand 256 | joker 128 | game 64)
+        epilogue_to_x<ACT_RELU>(taddr, row, slice_lo(448), slice_hi(448), gb, X);
+      } else if (group == 1) {   // 224 columns + the 32 zero columns of combined_net.0's K padding
+        epilogue_to_x<ACT_RELU>(taddr, row, slice_lo(224), slice_hi(224), gb, X);
+        if (slice == SLICES - 1) {
 #pragma unroll
           for (int q = 28; q < 32; q++) *reinterpret_cast<uint4*>(X + x_offset(row, q)) = make_uint4(0, 0, 0, 0);
         }
       } else if (group <= 3) {
-        epilogue_to_x<ACT_RELU>(taddr, row, 128 * slice, 128 * slice + 128, gb, X);
+        epilogue_to_x<ACT_RELU>(taddr, row, slice_lo(512), slice_hi(512), gb, X);
       } else if (group <= 5) {
-        epilogue_to_x<ACT_TANH>(taddr, row, 128 * slice, 128 * slice + 128, gb, X);
+        epilogue_to_x<ACT_TANH>(taddr, row, slice_lo(512), slice_hi(512), gb, X);
       } else if (slice == 0) {
         const long long g = tile * TILE_M + row;
         uint32_t v[32];
