@@ -2,7 +2,7 @@
 # fused tcgen05 policy forward: rollout tests (under a timeout: a wrong barrier phase would hang), kernel timing, PPO bench block
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_rollout.py -x -q -m gpu 2>&1 | grep -v "^E    \+" | tail -6
-tools/gpu_policy2.sh 2>&1 | tail -2
+tools/gpu_policy_time.sh 2>&1 | tail -2
 timeout 300 python - <<'PY'
 import torch, bench, json, argparse
 from balatro_gym_b200 import dist as bdist
