@@ -1271,9 +1271,13 @@ int bgym_vec_step_host(BgymVec* v, const int32_t* actions, const BgymDraws* draw
                      v->d_reward, v->d_term, v->d_trunc, v->d_info, v->n, flags & ~BGYM_FLAG_NO_OBS, v->stream);
   if (rc) return rc;
   if (obs_out) {
-    // host callers get whole records: fold the selection array (selected_cards, mask word) into them first
-    rc = bgym_sync_obs(reinterpret_cast<BgymObs*>(v->d_obs), reinterpret_cast<BgymSel*>(v->d_sel), v->n, BGYM_SYNC_TO_RECORDS, v->stream);
-    if (rc) return rc;
+    // host callers get whole records: fold the selection array (selected_cards, mask word) into them first — unless the slab
+    // took the one-launch step, which rewrites every record whole (the N = 1 Gymnasium facade: one launch less per step)
+    static const bool diag = getenv("BGYM_STEP_TIMING") != nullptr;
+    if (v->n > small_slab_threshold() || diag) {
+      rc = bgym_sync_obs(reinterpret_cast<BgymObs*>(v->d_obs), reinterpret_cast<BgymSel*>(v->d_sel), v->n, BGYM_SYNC_TO_RECORDS, v->stream);
+      if (rc) return rc;
+    }
     CK(cudaMemcpyAsync(v->h_block, v->d_block, v->block_bytes, cudaMemcpyDeviceToHost, v->stream));      // everything, one copy
   } else {   // without observations: skip the 176 B/env part
     const size_t off = reinterpret_cast<uint8_t*>(v->d_reward) - v->d_block;
