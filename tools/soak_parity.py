@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--one-launch", action="store_true", help="exercise the small-slab kernel instead of the multi-pass step")
+    ap.add_argument("--generator", default="c4", choices=["none", "c3", "c4"],
+                    help="device-side state generator applied by reset and by every in-kernel autoreset (mirrored by the oracle)")
     args = ap.parse_args()
     import torch
     from balatro_gym_b200 import BalatroVecEnv, layout as L
@@ -32,12 +34,13 @@ def main():
     n = args.envs
     import balatro_gym_b200
     assert balatro_gym_b200.load().bgym_set_option(1, (1 << 40) if args.one_launch else 0) == 0
-    v = BalatroVecEnv(n, seed=args.seed, autoreset=True)
+    gen = None if args.generator == "none" else args.generator
+    gflags = L.GENERATORS[gen]
+    v = BalatroVecEnv(n, seed=args.seed, autoreset=True, generator=gen)
     v.reset()
-    v.randomize_c3(seed=args.seed)
     ov = coracle.OracleVec(n)
-    ov.reset(np.arange(args.seed, n + args.seed))
-    ov.state[:] = v.state_numpy()
+    coracle.reset(ov.state, ov.obs, np.arange(args.seed, n + args.seed), flags=gflags)
+    assert_records_equal(ov.state, v.state_numpy(), L.STATE_DTYPE, (), "reset state")
     rng = np.random.default_rng(args.seed)
     t0 = time.time()
     episodes = 0
@@ -48,12 +51,12 @@ def main():
         if t % 11 == 5:
             act = rng.integers(-2, 62, size=n).astype(np.int32)
             v.step(torch.from_numpy(act).cuda())
-            ov.step(act, flags=L.FLAG_AUTORESET)
+            ov.step(act, flags=L.FLAG_AUTORESET | gflags)
         else:
             v.step(random_policy=True)
             oact = np.zeros(n, np.int32)
             coracle.step(ov.state, oact, ov.obs, ov.reward, ov.terminated, ov.truncated, ov.info, None,
-                         flags=L.FLAG_AUTORESET | 4)
+                         flags=L.FLAG_AUTORESET | 4 | gflags)
             assert np.array_equal(oact, v.actions.cpu().numpy()), f"policy actions differ at step {t}"
         st = v.state_numpy()
         assert_records_equal(ov.state, st, L.STATE_DTYPE, (), f"step {t} state")
@@ -70,14 +73,14 @@ def main():
         episodes += int(ov.terminated.sum())
         phases += np.bincount(st["phase"] & 3, minlength=4)
         max_ante = max(max_ante, int(st["ante"].max()))
-    msg = (f"soak ({'one-launch small-slab kernel' if args.one_launch else 'multi-pass step: main + gather kernels'}): {n} envs x {args.steps} steps = {n * args.steps} env-steps, 0 mismatches "
+    msg = (f"soak ({'one-launch small-slab kernel' if args.one_launch else 'multi-pass step: main pass on the toggle records + list kernels'}, generator {args.generator}): {n} envs x {args.steps} steps = {n * args.steps} env-steps, 0 mismatches "
            f"(state, obs, terminated, info bit-exact every step; rewards bit-exact except {ulp_cases} last-place log10 cases "
            f"within 1e-12); episodes finished {episodes}; "
            f"env-steps by phase PLAY/SHOP/BLIND_SELECT/PACK_OPEN = {phases.tolist()}; max ante reached {max_ante}; "
            f"wall {time.time() - t0:.1f} s")
     print(msg)
     os.makedirs("gpurun_out", exist_ok=True)
-    open("gpurun_out/soak_parity.txt", "w").write(msg + "\n")
+    open("gpurun_out/soak_parity.txt", "a").write(msg + "\n")
 
 
 if __name__ == "__main__":
