@@ -83,6 +83,24 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 
 __device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void sts128(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+// record accesses with a cache operator.  CG = the address is GLOBAL memory and the data is touched once by this SM
+// (a list tile's hot / toggle / observation records): loads come straight from L2 and stores go there without
+// taking an L1 line each, so that L1 keeps what a tile re-reads (its cold records, its stack frames)
+template <bool CG>
+__device__ __forceinline__ uint4 ldr128(const void* p) {
+  if (CG) return __ldcg(reinterpret_cast<const uint4*>(p));
+  return *reinterpret_cast<const uint4*>(p);
+}
+template <bool CG>
+__device__ __forceinline__ void str128(void* p, uint4 v) {
+  if (CG) __stcg(reinterpret_cast<uint4*>(p), v);
+  else *reinterpret_cast<uint4*>(p) = v;
+}
+template <bool CG>
+__device__ __forceinline__ void str64(void* p, uint2 v) {
+  if (CG) __stcg(reinterpret_cast<uint2*>(p), v);
+  else *reinterpret_cast<uint2*>(p) = v;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (counter-based; Salmon et al. SC'11 constants)

@@ -43,10 +43,12 @@ struct Hot {
   uint32_t rng_seed, rng_ctr, ep_len, episode;
 };
 
+// CG: the record lies in global memory and is read once — straight from L2, no L1 line allocated
+template <bool CG = false>
 __device__ __forceinline__ void unpack_hot(const uint8_t* hot, Hot& h) {
-  uint4 q0 = lds128(hot), q1 = lds128(hot + 16), q2 = lds128(hot + 32), q3 = lds128(hot + 48);
-  uint4 q4 = lds128(hot + 64), q5 = lds128(hot + 80), q6 = lds128(hot + 96), q7 = lds128(hot + 112);
-  uint4 q8 = lds128(hot + 128);
+  uint4 q0 = ldr128<CG>(hot), q1 = ldr128<CG>(hot + 16), q2 = ldr128<CG>(hot + 32), q3 = ldr128<CG>(hot + 48);
+  uint4 q4 = ldr128<CG>(hot + 64), q5 = ldr128<CG>(hot + 80), q6 = ldr128<CG>(hot + 96), q7 = ldr128<CG>(hot + 112);
+  uint4 q8 = ldr128<CG>(hot + 128);
   h.hand = u64_of(q0.x, q0.y); h.hand_code = u64_of(q0.z, q0.w);
   h.hand_n = q1.x & 0xFF; h.hand_size = (q1.x >> 8) & 0xFF; h.sel_n = (q1.x >> 16) & 0xFF; h.highlight = q1.x >> 24;
   h.sel_order = q1.y;
@@ -77,32 +79,33 @@ __device__ __forceinline__ uint4 hot_chunk1(const Hot& h) {
   return q;
 }
 
+template <bool CG = false>
 __device__ __forceinline__ void pack_hot(uint8_t* hot, const Hot& h) {
   uint4 q;
   q.x = (uint32_t)h.hand; q.y = (uint32_t)(h.hand >> 32); q.z = (uint32_t)h.hand_code; q.w = (uint32_t)(h.hand_code >> 32);
-  sts128(hot, q);
-  sts128(hot + 16, hot_chunk1(h));
+  str128<CG>(hot, q);
+  str128<CG>(hot + 16, hot_chunk1(h));
   q.x = (h.joker_slots & 0xFF) | ((h.cons_slots & 0xFF) << 8) | ((h.n_magic & 0xFF) << 16) | ((uint32_t)(h.n_minimalist & 0xFF) << 24);
   q.y = (h.ante & 0xFFFF) | ((uint32_t)(h.jokers_sold & 0xFFFF) << 16);
   q.z = (uint32_t)h.money; q.w = (uint32_t)h.chips_needed;
-  sts128(hot + 32, q);
+  str128<CG>(hot + 32, q);
   q.x = (uint32_t)h.round_chips; q.y = (uint32_t)((uint64_t)h.round_chips >> 32);
   q.z = (uint32_t)h.chips_scored; q.w = (uint32_t)((uint64_t)h.chips_scored >> 32);
-  sts128(hot + 48, q);
+  str128<CG>(hot + 48, q);
   q.x = (uint32_t)h.best_hand; q.y = (uint32_t)h.hands_played_total;
   q.z = (h.hands_played_ante & 0xFFFF) | ((h.boss_flags & 0xFF) << 16) | ((uint32_t)(h.boss_cards_required & 0xFF) << 24);
   q.w = (h.boss_played_types & 0xFFFF) | ((h.boss_hands_played & 0xFF) << 16) | ((uint32_t)(h.deck_n & 0xFF) << 24);
-  sts128(hot + 64, q);
+  str128<CG>(hot + 64, q);
   q.x = (uint32_t)h.boss_played_cards; q.y = (uint32_t)(h.boss_played_cards >> 32);
   q.z = (uint32_t)h.jokers; q.w = (uint32_t)(h.jokers >> 32);
-  sts128(hot + 80, q);
+  str128<CG>(hot + 80, q);
   q.x = (uint32_t)h.cons; q.y = (uint32_t)(h.cons >> 32); q.z = h.lv0; q.w = h.lv1;
-  sts128(hot + 96, q);
+  str128<CG>(hot + 96, q);
   q.x = h.lv2; q.y = (uint32_t)h.shop_reroll_state; q.z = h.rng_seed; q.w = h.rng_ctr;
-  sts128(hot + 112, q);
+  str128<CG>(hot + 112, q);
   q.x = (h.hands_left & 0xFF) | ((h.discards_left & 0xFF) << 8) | ((h.joker_n & 0xFF) << 16) | ((uint32_t)(h.cons_n & 0xFF) << 24);
   q.y = h.episode;
-  *reinterpret_cast<uint2*>(hot + 128) = make_uint2(q.x, q.y);   // bytes 136..143 (deck_extra) stay as they are
+  str64<CG>(hot + 128, make_uint2(q.x, q.y));   // bytes 136..143 (deck_extra) stay as they are
 }
 __device__ __forceinline__ void hot_clear_extra(uint8_t* hot) { *reinterpret_cast<uint2*>(hot + OFF_HOT_EXTRA) = make_uint2(0u, 0u); }
 
@@ -132,15 +135,18 @@ __device__ __forceinline__ void unpack_tog(const uint4 t0, const uint4 t1, Hot& 
   h.rng_seed = t1.y;
 }
 // a whole env for the list / reset tiles: the hot record with its toggle-owned chunk taken from the toggle record
+template <bool CG = false>
 __device__ __forceinline__ void load_hot(const uint8_t* hot, const uint8_t* tog, Hot& h) {
-  unpack_hot(hot, h);
+  unpack_hot<CG>(hot, h);
   set_chunk1(h, __ldcg(reinterpret_cast<const uint4*>(tog)));
 }
+template <bool CG = false>
 __device__ __forceinline__ void store_tog(uint8_t* tog, const Hot& h) {
-  reinterpret_cast<uint4*>(tog)[0] = hot_chunk1(h);
-  reinterpret_cast<uint4*>(tog)[1] = tog_summary(h);
+  str128<CG>(tog, hot_chunk1(h));
+  str128<CG>(tog + 16, tog_summary(h));
 }
-__device__ __forceinline__ void store_hot(uint8_t* hot, uint8_t* tog, const Hot& h) { pack_hot(hot, h); store_tog(tog, h); }
+template <bool CG = false>
+__device__ __forceinline__ void store_hot(uint8_t* hot, uint8_t* tog, const Hot& h) { pack_hot<CG>(hot, h); store_tog<CG>(tog, h); }
 
 __device__ __forceinline__ int hand_level(const Hot& h, int ht) {
   uint32_t w = ht < 4 ? h.lv0 : (ht < 8 ? h.lv1 : h.lv2);
@@ -440,9 +446,19 @@ __device__ __forceinline__ void cons_pop(Hot& h, int idx) {
 // [surviving original cards, in order] ++ [cards appended by Cryptid, in order]; list.remove takes the first EQUAL
 // element: an original card (cards.Card, rank+suit equality, :112-115) is only equal to itself, an appended card
 // (consumables.Card dataclass) is equal to any appended card with the same rank, suit and copy-time modifiers.
-__device__ __noinline__ int immolate(Hot& h, uint8_t* hotrec, uint8_t* rec, Draws& rng) {
+// Two halves.  immolate_sample (the lane that uses the card, inside use_consumable): the draws and which list entries
+// go — a bit set over deck positions.  immolate_compact (the WHOLE WARP, called by the tile at a converged point for every
+// lane that has such a set): the list compaction, lane = deck position.  One lane walking the 52 positions alone was
+// 1 900 dependent warp-instructions that the other 31 lanes of the tile waited for (ncu: 19 % of the consumable list
+// kernel's instructions at 1.1 active lanes); the cooperative form is ~80.
+__device__ __forceinline__ int nth_set_bit64(uint64_t m, int p) {   // position of the p-th (0-based) set bit of m
+  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+  const int c = __popc(lo);
+  return p < c ? (int)__fns(lo, 0u, p + 1) : 32 + (int)__fns(hi, 0u, p - c + 1);
+}
+__device__ __noinline__ int immolate_sample(const Hot& h, const uint8_t* hotrec, const uint8_t* rec, Draws& rng, uint64_t* removed_out) {
   const int n = h.deck_n, n_ex = rec[OFF_EXTRA_N], n_orig = n - n_ex;
-  uint16_t* ex = reinterpret_cast<uint16_t*>(hotrec + OFF_HOT_EXTRA);
+  const uint16_t* ex = reinterpret_cast<const uint16_t*>(hotrec + OFF_HOT_EXTRA);
   const int k = min(5, n);
   uint64_t sampled = 0, removed = 0;
 #pragma unroll 1
@@ -451,10 +467,7 @@ __device__ __noinline__ int immolate(Hot& h, uint8_t* hotrec, uint8_t* rec, Draw
     if (rng.tape) idx = rng.below(n);            // replay: population index recorded from the reference
     else {                                       // native: t-th element of a uniform sample without replacement
       int p = rng.below(n - t);
-      uint64_t fr = ~sampled & ((n >= 64) ? ~0ull : ((1ull << n) - 1));
-#pragma unroll 1
-      for (int i = 0; i < p; i++) fr &= fr - 1;
-      idx = __ffsll((long long)fr) - 1;
+      idx = nth_set_bit64(~sampled & ((n >= 64) ? ~0ull : ((1ull << n) - 1)), p);
     }
     sampled |= 1ull << idx;
     int victim = idx;
@@ -465,30 +478,62 @@ __device__ __noinline__ int immolate(Hot& h, uint8_t* hotrec, uint8_t* rec, Draw
     }
     removed |= 1ull << victim;
   }
-  // compact: codes move down with the cards, modifiers stay with the deck index
-  int w = 0, w_ex = 0;
-  uint64_t pillar = 0;
-#pragma unroll 1
-  for (int i = 0; i < n; i++) {
-    if ((removed >> i) & 1) continue;
-    const int id = i < n_orig ? 0 : ex[i - n_orig];
-    const int code = i < n_orig ? c16_code(deck16(rec, i)) : (id & 63);
-    if (w < 52) set_deck16(rec, w, (deck16(rec, w) & ~63) | code);
-    if (i >= n_orig) ex[w_ex++] = (uint16_t)id;
-    pillar |= ((h.boss_played_cards >> i) & 1ull) << w;
-    w++;
-  }
-#pragma unroll 1
-  for (int i = w; i < 52; i++) set_deck16(rec, i, deck16(rec, i) & ~63);
-#pragma unroll 1
-  for (int j = w_ex; j < MAX_DECK_EXTRA; j++) ex[j] = 0;
-  rec[OFF_EXTRA_N] = (uint8_t)w_ex;
-  h.deck_n = w;
-  h.boss_played_cards = pillar;
+  *removed_out = removed;
   return k;
 }
+// compact: codes move down with the cards, modifiers stay with the deck index.  Whole warp; `removed` != 0 marks the
+// lanes whose env used Immolate this step (h, hotrec, rec are that lane's).  Lane l serves list positions l and l + 32
+// of one env at a time: all reads first, then every surviving card's code goes to its new position.
+__device__ __forceinline__ void immolate_compact(uint64_t removed, Hot& h, uint8_t* hotrec, uint8_t* rec, int lane) {
+  uint32_t need = __ballot_sync(0xffffffffu, removed != 0);
+  if (!need) return;
+  const unsigned long long my_rec = reinterpret_cast<unsigned long long>(rec), my_hot = reinterpret_cast<unsigned long long>(hotrec);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    const uint64_t rm = __shfl_sync(0xffffffffu, removed, src);
+    uint8_t* r = reinterpret_cast<uint8_t*>(__shfl_sync(0xffffffffu, my_rec, src));
+    uint16_t* ex = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(__shfl_sync(0xffffffffu, my_hot, src)) + OFF_HOT_EXTRA);
+    const int n = __shfl_sync(0xffffffffu, h.deck_n, src);
+    const uint64_t bpc = __shfl_sync(0xffffffffu, h.boss_played_cards, src);
+    const int n_ex = r[OFF_EXTRA_N], n_orig = n - n_ex;
+    const uint64_t keep = ~rm & ((1ull << n) - 1);                       // n <= 56
+    const uint64_t keep_ex = keep & ~((1ull << n_orig) - 1);
+    const int w_total = __popcll(keep), w_ex_total = __popcll(keep_ex);
+    int code[2], id[2];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int i = lane + 32 * q;
+      id[q] = (i >= n_orig && i < n) ? ex[i - n_orig] : 0;
+      code[q] = i < n_orig ? c16_code(deck16(r, i)) : (id[q] & 63);
+    }
+    __syncwarp();
+    uint64_t pillar = 0;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int i = lane + 32 * q;
+      if ((keep >> i) & 1) {
+        const uint64_t below = (1ull << i) - 1;
+        const int w = __popcll(keep & below);
+        if (w < 52) set_deck16(r, w, (deck16(r, w) & ~63) | code[q]);
+        if (i >= n_orig) ex[__popcll(keep_ex & below)] = (uint16_t)id[q];
+        pillar |= ((bpc >> i) & 1ull) << w;
+      }
+      if (i >= w_total && i < 52) set_deck16(r, i, deck16(r, i) & ~63);
+    }
+    if (lane >= w_ex_total && lane < MAX_DECK_EXTRA) ex[lane] = 0;
+    if (lane == 0) r[OFF_EXTRA_N] = (uint8_t)w_ex_total;
+    const uint32_t plo = __reduce_or_sync(0xffffffffu, (uint32_t)pillar), phi = __reduce_or_sync(0xffffffffu, (uint32_t)(pillar >> 32));
+    if (lane == src) { h.deck_n = w_total; h.boss_played_cards = u64_of(plo, phi); }
+    __syncwarp();
+  }
+}
 
-__device__ double use_consumable(Hot& h, uint8_t* hotrec, uint8_t* rec, int cidx, Draws& rng, int& err, int& terminated) {
+// *immolate_removed: set by Immolate to the deck positions it destroys (0 otherwise); the caller's tile runs
+// immolate_compact() on it once the warp has converged
+__device__ double use_consumable(Hot& h, uint8_t* hotrec, uint8_t* rec, int cidx, Draws& rng, int& err, int& terminated,
+                                 uint64_t* immolate_removed) {
+  *immolate_removed = 0;
   int cid = byte_at(h.cons, cidx);
   ConsRow row = cons_row(cid);
   // targets: selected cards in selection order (balatro_env_2.py:1074-1083)
@@ -581,7 +626,7 @@ __device__ double use_consumable(Hot& h, uint8_t* hotrec, uint8_t* rec, int cidx
       if (h.joker_n < h.joker_slots) { add_joker = BGYM_J_CANIO + rng.below(5); n_jokers_created = 1; success = true; }
       break;
     case CO_BLACK_HOLE: success = true; break;
-    case CO_IMMOLATE: n_destroyed = immolate(h, hotrec, rec, rng); money_gained = 20; success = true; break;
+    case CO_IMMOLATE: n_destroyed = immolate_sample(h, hotrec, rec, rng, immolate_removed); money_gained = 20; success = true; break;
     case CO_CRYPTID:   // consumables.py:582-592: two copies of the first target are appended to the deck list
       if (nT >= 1) {
         const int n_ex = rec[OFF_EXTRA_N];
@@ -804,12 +849,12 @@ __device__ __forceinline__ void autoreset_warp(bool want_reset, uint32_t new_see
 // stream stays small and register-resident: pack_hot -> rare_dispatch -> unpack_hot at one site.
 // ---------------------------------------------------------------------------------------------
 enum { RARE_NONE = 0, RARE_ADVANCE = 1, RARE_REROLL = 2, RARE_CONSUMABLE = 3 };
-struct RareOut { double reward; int err; int terminated; };
+struct RareOut { double reward; int err; int terminated; uint64_t immolate_removed; };
 
 __device__ __noinline__ void rare_dispatch(uint8_t* hot, uint8_t* rec, int op, int arg, Draws* rng, RareOut* out) {
   Hot h;
   unpack_hot(hot, h);
-  out->reward = 0.0; out->err = 0; out->terminated = 0;
+  out->reward = 0.0; out->err = 0; out->terminated = 0; out->immolate_removed = 0;
   if (op == RARE_ADVANCE) {
     advance_round(h, rec, *rng);
   } else if (op == RARE_REROLL) {
@@ -822,8 +867,8 @@ __device__ __noinline__ void rare_dispatch(uint8_t* hot, uint8_t* rec, int op, i
       shop_generate_inventory(h, rec, *rng);
     }
   } else if (op == RARE_CONSUMABLE) {
-    out->reward = use_consumable(h, hot, rec, arg, *rng, out->err, out->terminated);
-    refresh_hand_codes(h, rec);   // Immolate moves cards under the hand's deck indices
+    // (Immolate moves cards under the hand's deck indices: the tile refreshes the hand codes after immolate_compact)
+    out->reward = use_consumable(h, hot, rec, arg, *rng, out->err, out->terminated, &out->immolate_removed);
   }
   pack_hot(hot, h);
 }
@@ -855,7 +900,7 @@ enum { CAT_SELECT = 1, CAT_PLAY = 2, CAT_DISCARD = 4, CAT_CONS = 8, CAT_SHOP = 1
        CAT_OTHER = CAT_CONS | CAT_SHOP | CAT_BLIND | CAT_GEN, CAT_ALL = 127 };
 template <int CATS, bool DEFER_ADVANCE>
 __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_t mask, const BgymDraws* tape, double& reward_out,
-                         int& terminated_out, StepInfo& info, int* defer_snap) {
+                         int& terminated_out, StepInfo& info, int* defer_snap, uint64_t* immolate_removed = nullptr) {
   if (DEFER_ADVANCE) *defer_snap = -1;
   info.final_score = 0; info.x_mult = 1.0; info.chips = 0; info.mult = 0; info.hand_type = -1;
   info.error_code = 0; info.flags = 0; info.cards_played = 0; info.base_score = 0;
@@ -1171,6 +1216,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     rare_dispatch(hot, rec, rare_op, rare_arg, &rng, &ro);
     unpack_hot(hot, h);
     if (rare_op != RARE_ADVANCE) { reward = ro.reward; info.error_code = ro.err; terminated = ro.terminated; }
+    if (CATS & CAT_CONS) *immolate_removed = ro.immolate_removed;
   }
   if ((CATS & (CAT_PLAY | CAT_DISCARD | CAT_OTHER)) && hand_changed) refresh_hand_codes(h, rec);
   if (!tape) h.rng_ctr = rng.blocks();
@@ -1215,6 +1261,7 @@ __device__ __forceinline__ void obs_shop_block(const Hot& h, const uint8_t* rec,
   so.w[9] = ic[7] | (ic[8] << 16); so.w[10] = ic[9];
 }
 
+template <bool CG = false>
 __device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, uint64_t mask, uint8_t* obs /*smem, 176 B*/) {
   uint4 q;
   uint32_t selm = 0;
@@ -1223,54 +1270,54 @@ __device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, 
   // 0: hand[8] | selected_cards[8]   (hand codes = deck[hand[i]], -1 when empty)
   q.x = (uint32_t)h.hand_code; q.y = (uint32_t)(h.hand_code >> 32);
   q.z = spread4(selm); q.w = spread4(selm >> 4);
-  sts128(obs, q);
+  str128<CG>(obs, q);
   // 16: face_down_cards[8] | chips_scored
   q.x = spread4(h.face_down); q.y = spread4(h.face_down >> 4);
   q.z = (uint32_t)h.chips_scored; q.w = (uint32_t)((uint64_t)h.chips_scored >> 32);
-  sts128(obs + 16, q);
+  str128<CG>(obs + 16, q);
   // 32: round_chips_scored, progress_ratio, mult, chips_needed
   double p = (double)h.round_chips / (double)max(h.chips_needed, 1);
   q.x = (uint32_t)h.round_chips; q.y = __float_as_uint((float)fmin(p, 2.0)); q.z = 1u; q.w = (uint32_t)h.chips_needed;
-  sts128(obs + 32, q);
+  str128<CG>(obs + 32, q);
   // 48: money, hands_played, best_hand_this_ante, ante | shop_rerolls
   q.x = (uint32_t)h.money; q.y = (uint32_t)h.hands_played_total; q.z = (uint32_t)h.best_hand;
   q.w = (h.ante & 0xFFFF) | ((uint32_t)(h.shop_reroll_state & 0xFFFF) << 16);
-  sts128(obs + 48, q);
+  str128<CG>(obs + 48, q);
   // 64..159: int16 arrays and int8 scalars, built as 16-bit lanes
   // joker_ids[10] @64
   uint32_t j[5];
 #pragma unroll
   for (int i = 0; i < 4; i++) j[i] = (uint32_t)byte_at(h.jokers, 2 * i) | ((uint32_t)byte_at(h.jokers, 2 * i + 1) << 16);
   q.x = j[0]; q.y = j[1]; q.z = j[2]; q.w = j[3];
-  sts128(obs + 64, q);
+  str128<CG>(obs + 64, q);
   // 80: joker_ids[8..9] (always 0) | consumables[0..4] (84..93) | shop_items[0] (94)
   int c0 = h.cons_n > 0 ? obs_cons_id(byte_at(h.cons, 0)) : 0, c1 = h.cons_n > 1 ? obs_cons_id(byte_at(h.cons, 1)) : 0;
   int c2 = h.cons_n > 2 ? obs_cons_id(byte_at(h.cons, 2)) : 0, c3 = h.cons_n > 3 ? obs_cons_id(byte_at(h.cons, 3)) : 0;
   int c4 = h.cons_n > 4 ? obs_cons_id(byte_at(h.cons, 4)) : 0;
   q.x = 0; q.y = (uint32_t)c0 | ((uint32_t)c1 << 16); q.z = (uint32_t)c2 | ((uint32_t)c3 << 16); q.w = (uint32_t)c4 | (so.w[0] << 16);
-  sts128(obs + 80, q);
+  str128<CG>(obs + 80, q);
   // 96: shop_items[1..8]
   q.x = so.w[1]; q.y = so.w[2]; q.z = so.w[3]; q.w = so.w[4];
-  sts128(obs + 96, q);
+  str128<CG>(obs + 96, q);
   // 112: shop_items[9] | shop_costs[0..6]
   q.x = so.w[5]; q.y = so.w[6]; q.z = so.w[7]; q.w = so.w[8];
-  sts128(obs + 112, q);
+  str128<CG>(obs + 112, q);
   // 128: shop_costs[7..9] (128..133) | hand_levels[0..9] (134..143)
   q.x = so.w[9];
   q.y = so.w[10] | ((h.lv0 & 0xFFFF) << 16);
   q.z = (h.lv0 >> 16) | ((h.lv1 & 0xFFFF) << 16);
   q.w = (h.lv1 >> 16) | ((h.lv2 & 0xFFFF) << 16);
-  sts128(obs + 128, q);
+  str128<CG>(obs + 128, q);
   // 144: hand_levels[10..11] | hand_size, deck_size | round, hands_left, discards_left, joker_count |
   //      joker_slots, consumable_count, consumable_slots, phase | boss_active, boss_type, pad, pad
   q.x = (h.lv2 >> 16) | ((uint32_t)(h.hand_n & 0xFF) << 16) | ((uint32_t)(h.deck_n & 0xFF) << 24);
   q.y = (h.round & 0xFF) | ((h.hands_left & 0xFF) << 8) | ((h.discards_left & 0xFF) << 16) | ((uint32_t)(h.joker_n & 0xFF) << 24);
   q.z = (h.joker_slots & 0xFF) | ((h.cons_n & 0xFF) << 8) | ((h.cons_slots & 0xFF) << 16) | ((uint32_t)(h.phase & 0xFF) << 24);
   q.w = (h.boss_type != 0 ? 1u : 0u) | ((uint32_t)(h.boss_type & 0xFF) << 8);
-  sts128(obs + 144, q);
+  str128<CG>(obs + 144, q);
   // 160: action_mask_bits | pad
   q.x = (uint32_t)mask; q.y = (uint32_t)(mask >> 32); q.z = 0; q.w = 0;
-  sts128(obs + 160, q);
+  str128<CG>(obs + 160, q);
 }
 
 // selection record (BgymSel, 16 B): selected_cards[8] | action_mask_bits — the two observation fields a toggle changes
@@ -1283,14 +1330,15 @@ __device__ __forceinline__ uint4 sel_words(const Hot& h, uint64_t mask) {
   return q;
 }
 
-__device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs /*smem, 176 B*/) {
+template <bool CG = false>
+__device__ __forceinline__ void write_obs(const Hot& h, const uint8_t* rec, uint64_t mask, uint8_t* obs) {
   ShopObs so;
   if (rec) obs_shop_block(h, rec, so);
   else {
 #pragma unroll
     for (int i = 0; i < 11; i++) so.w[i] = 0;   // PLAY phase (main pass): the shop block is all zeros
   }
-  write_obs_regs(h, so, mask, obs);
+  write_obs_regs<CG>(h, so, mask, obs);
 }
 
 }  // namespace bgym

@@ -229,6 +229,19 @@ __device__ __forceinline__ void push_list(const StepArgs& a, int l, bool push, l
   if (push) a.part_lists[(long long)l * a.part_cap + basei + __popc(bal & ((1u << lane) - 1))] = (int)e;
 }
 
+// two lists at once: both atomics are in flight together (lanes 0 and 1), one round trip instead of two
+__device__ __forceinline__ void push_lists2(const StepArgs& a, int l0, bool push0, int l1, bool push1, long long e, int lane) {
+  const uint32_t bal0 = __ballot_sync(0xffffffffu, push0), bal1 = __ballot_sync(0xffffffffu, push1);
+  if (!(bal0 | bal1)) return;
+  int basei = 0;
+  if (lane == 0 && bal0) basei = atomicAdd(a.part_counters + l0 * PART_CTR_STRIDE, __popc(bal0));
+  if (lane == 1 && bal1) basei = atomicAdd(a.part_counters + l1 * PART_CTR_STRIDE, __popc(bal1));
+  const int base0 = __shfl_sync(0xffffffffu, basei, 0), base1 = __shfl_sync(0xffffffffu, basei, 1);
+  const uint32_t below = (1u << lane) - 1;
+  if (push0) a.part_lists[(long long)l0 * a.part_cap + base0 + __popc(bal0 & below)] = (int)e;
+  if (push1) a.part_lists[(long long)l1 * a.part_cap + base1 + __popc(bal1 & below)] = (int)e;
+}
+
 #ifdef BGYM_PREFETCH_L1
 #define BGYM_PREFETCH(p) prefetch_l1(p)
 #else
@@ -271,12 +284,24 @@ constexpr int STG_RO = 0, STG_RW = 0;
 #endif
 __host__ __device__ constexpr int list_smem_bytes(int list) { return (list >= 7 /*level 2*/ || STG_RW || STG_RO) ? GATHER_CTA_SMEM : 0; }
 
+// cache operators of the list tiles' record traffic (ldr128 / str128, bgym_device.cuh)
+#ifdef BGYM_LD_CG
+constexpr bool LIST_LD_CG = true;
+#else
+constexpr bool LIST_LD_CG = false;
+#endif
+#ifdef BGYM_ST_CG
+constexpr bool LIST_ST_CG = true;
+#else
+constexpr bool LIST_ST_CG = false;
+#endif
+
 // the whole observation of env e: the 176-byte record AND the selection record (both carry selected_cards and the mask)
 // shop_changed: the record's shop chunks (shop_items / shop_costs) can differ from what they were before the step
 __device__ __forceinline__ void emit_observation(const StepArgs& a, long long e, const Hot& h, const uint8_t* cold, bool shop_changed) {
   const uint64_t m = action_mask(h, cold);
-  write_obs(h, cold, m, a.obs + e * BGYM_OBS_BYTES);
-  *reinterpret_cast<uint4*>(a.sel + e * BGYM_SEL_BYTES) = sel_words(h, m);
+  write_obs<LIST_ST_CG>(h, cold, m, a.obs + e * BGYM_OBS_BYTES);
+  str128<LIST_ST_CG>(a.sel + e * BGYM_SEL_BYTES, sel_words(h, m));
   if (a.obs_dirty) a.obs_dirty[e] = (uint8_t)(BGYM_OBS_DIRTY | (shop_changed ? BGYM_OBS_DIRTY_SHOP : 0));
 }
 // the shop block of the observation is all zeros outside SHOP phase and is not touched by a joker sale
@@ -321,11 +346,16 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool
   bool want_reset = false;
   uint32_t new_seed = 0;
   int action = 0;
-  uint64_t m0 = 0;
+  uint64_t m0 = 0, imm_removed = 0;
   if (active) {
+#ifdef BGYM_PF_COLD
+    // the cold record's lines on their way into L1 while the hot record arrives: its first touches (deck[hand[i]], the
+    // hand-play count, the shop block) are otherwise dependent DRAM round trips in the middle of the tile's chain
+    if (!STAGE) { prefetch_l1(cold_g); prefetch_l1(cold_g + 128); prefetch_l1(cold_g + BGYM_COLD_BYTES - 1); }
+#endif
     // read once, straight from L2 (with the fused policy the main pass wrote it for PLAY-phase envs)
     action = __ldcg(a.actions + e);
-    load_hot(hot, tog, h);
+    load_hot<LIST_LD_CG>(hot, tog, h);
   }
   const int phase0 = active ? h.phase : 0;
   if (STAGE) { cp_async_wait_all(); __syncwarp(); }
@@ -338,7 +368,13 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool
       action = policy_action(h, m0);
       if (a.actions_out) a.actions_out[e] = action;
     }
-    step_env<CATS, DEFER>(h, hot, cold, action, m0, a.draws ? a.draws + e : nullptr, reward, terminated, info, &snap);
+    step_env<CATS, DEFER>(h, hot, cold, action, m0, a.draws ? a.draws + e : nullptr, reward, terminated, info, &snap, &imm_removed);
+  }
+  if (CATS & CAT_CONS) {     // Immolate's deck compaction, by the whole warp (bgym_env.cuh)
+    immolate_compact(imm_removed, h, hot, cold, lane);
+    if (imm_removed) refresh_hand_codes(h, cold);
+  }
+  if (active) {
     if (terminated && autoreset) {
       info.flags |= BGYM_F_AUTORESET_DONE;
       want_reset = true;
@@ -357,8 +393,12 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool
   if (DEFER) {
     // hand the long paths on: a reset needs nothing of this tile but the outputs (the level-2 tile reads seed and
     // episode from the unchanged record), an advancing env continues from the state stored here
+#ifdef BGYM_PUSH2
+    push_lists2(a, L_RESET, want_reset, L_ADVANCE, snap >= 0, e, lane);
+#else
     push_list(a, L_RESET, want_reset, e, lane);
     push_list(a, L_ADVANCE, snap >= 0, e, lane);
+#endif
     if (snap >= 0) a.part_aux[e] = (uint16_t)snap;
     store_state = active && !want_reset;
     emit_obs = emit_obs && !want_reset && snap < 0;
@@ -367,7 +407,7 @@ __device__ __forceinline__ void gather_tile(const StepArgs& a, long long e, bool
   }
   BGYM_CTA_SYNC();
   if (store_state) {
-    store_hot(hot, tog, h);
+    store_hot<LIST_ST_CG>(hot, tog, h);
     if (!DEFER && want_reset) hot_clear_extra(hot);
   }
   BGYM_CTA_SYNC();
@@ -389,10 +429,10 @@ __device__ __forceinline__ void advance_tile(const StepArgs& a, long long e, boo
   cold_to_smem_async(cold_slot, cold_g);
   const uint32_t snap = a.part_aux[e];
   Hot h;
-  load_hot(hot, a.tog + e * BGYM_TOG_BYTES, h);
+  load_hot<LIST_LD_CG>(hot, a.tog + e * BGYM_TOG_BYTES, h);
   cp_async_wait_all();
   step_env_advance(h, hot, cold_slot, a.draws ? a.draws + e : nullptr, snap);
-  store_hot(hot, a.tog + e * BGYM_TOG_BYTES, h);
+  store_hot<LIST_ST_CG>(hot, a.tog + e * BGYM_TOG_BYTES, h);
   if (with_obs) emit_observation(a, e, h, cold_slot, true);     // a round advance enters the shop
   cold_from_smem(cold_g, cold_slot);
 }
@@ -414,7 +454,7 @@ __device__ __forceinline__ void reset_tile(const StepArgs& a, long long e, bool 
   if (gen) gen_hot(h, new_seed, a.flags);
   h.episode = episode;
   reset_blocks_serial(cold_slot, new_seed, nullptr, gen);      // deck build + shuffle in the lane's shared-memory slot
-  store_hot(hot, a.tog + e * BGYM_TOG_BYTES, h);
+  store_hot<LIST_ST_CG>(hot, a.tog + e * BGYM_TOG_BYTES, h);
   hot_clear_extra(hot);
   if (with_obs) emit_observation(a, e, h, cold_slot, old_phase == BGYM_PHASE_SHOP);
   cold_from_smem(a.cold + e * BGYM_COLD_BYTES, cold_slot);
