@@ -174,6 +174,7 @@ struct Draws {
   }
   __device__ double u01();
   __device__ int below(int n);
+  __device__ int count_u01_below(int n, uint32_t tested, double threshold);
   // A step whose round advance is deferred to a second-level tile (bgym_step_part.cuh) continues the SAME draw
   // sequence there.  16 bits say where it stands: words used of the current block (0..4) | tape positions |
   // "the prefetched block is still untouched" (see blocks()); the block counter travels in the hot record.
@@ -198,6 +199,23 @@ __device__ __noinline__ double Draws::u01() {
   uint32_t a = word() >> 5;
   uint32_t b = word() >> 6;
   return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+}
+// the next n u01() draws in one call: how many of those marked in `tested` (bit j = draw j) fall below `threshold`.
+// Same stream positions as n calls of u01(); the lanes of a tile that have draws to make run this loop together.
+__device__ __noinline__ int Draws::count_u01_below(int n, uint32_t tested, double threshold) {
+  int cnt = 0;
+  if (tape) {
+#pragma unroll 1
+    for (int j = 0; j < n; j++) cnt += ((tested >> j) & 1u) && tape->u[iu + j] < threshold;
+    iu += n;
+    return cnt;
+  }
+#pragma unroll 1
+  for (int j = 0; j < n; j++) {
+    const uint32_t a = word() >> 5, b = word() >> 6;
+    if ((tested >> j) & 1u) cnt += (a * 67108864.0 + b) * (1.0 / 9007199254740992.0) < threshold;
+  }
+  return cnt;
 }
 // unbiased integer in [0, n): Lemire multiply-shift with rejection
 __device__ __noinline__ int Draws::below(int n) {
@@ -227,6 +245,15 @@ __device__ __forceinline__ int shuffle_j_from_block(uint4 b, int i) {
     if (l < (0u - un) % un) m = (uint64_t)w1 * un;
   }
   return (int)(m >> 32);
+}
+
+// x / y for y > 0 and x >= 0 where x is often exactly zero (progress of a round that has just begun, a score of 0):
+// the fp64 division's fast path does not take a zero numerator — every such lane went through the ~60-instruction
+// out-of-line path, one small group of lanes at a time (ncu: 5.6 % of the PLAY list kernel's instructions)
+__device__ __forceinline__ double div_nz(double x, double y) {
+  double r = 0.0;
+  if (x != 0.0) r = x / y;
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -383,7 +383,7 @@ enum ConsOp : uint8_t {
 };
 struct ConsRow { uint8_t op, arg; };
 
-__device__ __forceinline__ ConsRow cons_row(int cid) {
+constexpr ConsRow cons_row_of(int cid) {
   int t = (cid >= 101 && cid <= 122) ? cid - 100 : cid;  // enum-style tarot names resolve the same way
   switch (t) {
     case 1: return {CO_FOOL, 0};
@@ -429,6 +429,19 @@ __device__ __forceinline__ ConsRow cons_row(int cid) {
     case 65: return {CO_CRYPTID, 0};
   }
   return {CO_NONE, 0};
+}
+// the same as a 128-entry table in global memory (built at compile time): the lanes of a consumable tile hold ~20 different
+// ids, and the switch above ran once per distinct id (ncu: 3 % of the list kernel's instructions at 3.8 active lanes)
+struct ConsTable { uint16_t v[128]; };
+constexpr ConsTable make_cons_table() {
+  ConsTable t{};
+  for (int i = 0; i < 128; i++) { const ConsRow r = cons_row_of(i); t.v[i] = (uint16_t)(r.op | (r.arg << 8)); }
+  return t;
+}
+__device__ const ConsTable g_cons_table = make_cons_table();
+__device__ __forceinline__ ConsRow cons_row(int cid) {
+  const uint32_t v = (cid >= 0 && cid < 128) ? g_cons_table.v[cid] : 0u;
+  return {(uint8_t)(v & 0xFF), (uint8_t)(v >> 8)};
 }
 
 __device__ __forceinline__ void cons_append(Hot& h, int cid) {
@@ -533,6 +546,7 @@ __device__ __forceinline__ void immolate_compact(uint64_t removed, Hot& h, uint8
 // immolate_compact() on it once the warp has converged
 __device__ double use_consumable(Hot& h, uint8_t* hotrec, uint8_t* rec, int cidx, Draws& rng, int& err, int& terminated,
                                  uint64_t* immolate_removed) {
+  const unsigned entered = __activemask();   // the lanes that walk this call together
   *immolate_removed = 0;
   int cid = byte_at(h.cons, cidx);
   ConsRow row = cons_row(cid);
@@ -645,6 +659,9 @@ __device__ double use_consumable(Hot& h, uint8_t* hotrec, uint8_t* rec, int cidx
       break;
     default: break;
   }
+  // every lane took its own case: meet again here, so that the bookkeeping below runs once for the tile and not once
+  // per case (ncu: lines :609-:625 at 2 active lanes, 10 % of the list kernel's instructions)
+  __syncwarp(entered);
   if (raise) {  // SafeBalatroEnv convention, train_balatro_fixed.py:262-269
     err = BGYM_ERR_REF_EXCEPTION; terminated = 1;
     return -100.0;
@@ -916,7 +933,9 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
   h.ep_len++;
   Draws rng;
   rng.init(h.rng_seed, h.rng_ctr, tape);
-  if (CATS & CAT_PLAY) rng.prefetch();   // glass / lucky rolls of the card loop: one converged Philox call
+  // glass / lucky rolls of a played hand's card loop, the draws of a consumable: ONE converged Philox call here instead
+  // of one per lane inside whichever branch draws first (an unused block is not counted, Draws::blocks)
+  if (CATS & (CAT_PLAY | CAT_CONS)) rng.prefetch();
   double reward = 0.0;
   int terminated = 0;
   int rare_op = RARE_NONE, rare_arg = 0;
@@ -941,6 +960,8 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     uint64_t played_bits = 0;          // bit set over deck indices of the played cards
     int n_played = 0, card_chip_sum = 0, faces_ge11 = 0, extra_money = 0, n_red = 0, n_blue = 0;
     int boss = h.boss_type, debuffed = 0;
+    int n_rolls = 0;            // u01 draws of the card loop, in order; bit j of lucky_rolls: draw j decides a Lucky card's money
+    uint32_t lucky_rolls = 0;
     #pragma unroll 1
     for (int k = 0; k < h.sel_n; k++) {
       int sl = nib_at(h.sel_order, k);
@@ -959,13 +980,16 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
       // boss debuffs (boss_blinds.py:447-478): Plant = face ranks, Violet = all, Pillar = played before
       debuffed += (boss == B_PLANT && jqk) || boss == B_VIOLET || (boss == B_PILLAR && ((h.boss_played_cards >> idx) & 1));
       // per-card enhancement / seal loop (:703-734), draws in selection order
-      if (enh == BGYM_ENH_GLASS) { (void)rng.u01(); }
-      else if (enh == BGYM_ENH_LUCKY) { (void)rng.u01(); if (rng.u01() < 0.0667) extra_money += 20; }
+      // (:703-734 draws one uniform for a Glass card and two for a Lucky card, of which only the second decides
+      // anything; the draws themselves are made after the loop, by all lanes that have some at once)
+      if (enh == BGYM_ENH_GLASS) n_rolls++;
+      else if (enh == BGYM_ENH_LUCKY) { lucky_rolls |= 2u << n_rolls; n_rolls += 2; }
       extra_money += (seal == BGYM_SEAL_GOLD) ? 3 : 0;
       n_red += seal == BGYM_SEAL_RED;
       // blue seal: room is tested against the list as it is now, creation re-tests (:733, :765-767)
       n_blue += (seal == BGYM_SEAL_BLUE) && (h.cons_n < h.cons_slots);
     }
+    if (n_rolls) extra_money += 20 * rng.count_u01_below(n_rolls, lucky_rolls, 0.0667);
     // ---- highlight + classification on deck[slot] of every highlighted slot (:663-671) ----
     h.highlight |= sel_slots;
     HandHist hist;
@@ -1004,7 +1028,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
       else if (boss == B_OXIDE) { mc = 0; }
       else if (boss == B_ARM) { mc = (int)(mc * 0.75); mm = (int)(mm * 0.75); }
       if (debuffed > 0) { double p = c_pow_0_8[debuffed]; mc = (int)(mc * p); mm = (int)(mm * p); }
-      double cr = (double)mc / (double)bc, mr = (double)mm / (double)bm;
+      double cr = div_nz((double)mc, (double)bc), mr = div_nz((double)mm, (double)bm);
       fs = (long long)((double)fs * cr * mr);
     }
     fs = (long long)((double)fs * (1 + n_red * 0.5));  // retriggers :757-759
@@ -1015,7 +1039,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
       for (int i = 0; i < n_blue; i++) if (h.cons_n < h.cons_slots) cons_append(h, planet);
     }
     double needed = (double)max(h.chips_needed, 1);
-    double old_progress = fmin(1.0, (double)h.round_chips / needed);
+    double old_progress = fmin(1.0, div_nz((double)h.round_chips, needed));
     h.round_chips += fs; h.chips_scored += fs;
     h.hands_played_total++; h.hands_played_ante++;
     if (fs > (long long)h.best_hand) h.best_hand = (int)min(fs, 2147483647LL);
@@ -1029,13 +1053,13 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     }
     h.sel_n = 0; h.sel_order = 0;
     // ---- reward shaping (:799-892) ----
-    double new_progress = fmin(1.0, (double)h.round_chips / needed);
+    double new_progress = fmin(1.0, div_nz((double)h.round_chips, needed));
     double milestone = 0.0;
     if (old_progress < 0.25 && 0.25 <= new_progress) milestone = 5.0;
     else if (old_progress < 0.5 && 0.5 <= new_progress) milestone = 10.0;
     else if (old_progress < 0.75 && 0.75 <= new_progress) milestone = 15.0;
     else if (old_progress < 1.0 && 1.0 <= new_progress) milestone = 25.0;
-    double score_reward = (h.ante <= 3) ? fmin(10.0, (double)fs / 100.0)
+    double score_reward = (h.ante <= 3) ? fmin(10.0, div_nz((double)fs, 100.0))
                                         : fmin(10.0, 3.0 * log10_out_of_line((double)max(fs, 1LL)));
     double hq = ht == 0 ? 0.1 : ht == 1 ? 0.5 : ht == 2 ? 1.0 : ht == 3 ? 2.0 : (ht == 4 || ht == 5) ? 2.5
               : ht == 6 ? 3.5 : ht == 7 ? 5.0 : ht == 8 ? 7.0 : ht == 9 ? 10.0 : 0.0;
@@ -1134,7 +1158,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     reward = 0.2;
     if (n_discard_jokers) reward += 0.5 * n_discard_jokers;
     if (money_from_discards > 0) reward += money_from_discards / 5.0;
-    double progress = (double)h.round_chips / (double)max(h.chips_needed, 1);
+    double progress = div_nz((double)h.round_chips, (double)max(h.chips_needed, 1));
     if (progress < 0.5 && h.discards_left > 1) reward += 0.5;
     else if (progress > 0.8 && h.discards_left > 1) reward -= 0.3;
   } else if ((CATS & CAT_CONS) && action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) {
@@ -1276,7 +1300,7 @@ __device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, 
   q.z = (uint32_t)h.chips_scored; q.w = (uint32_t)((uint64_t)h.chips_scored >> 32);
   str128<CG>(obs + 16, q);
   // 32: round_chips_scored, progress_ratio, mult, chips_needed
-  double p = (double)h.round_chips / (double)max(h.chips_needed, 1);
+  double p = div_nz((double)h.round_chips, (double)max(h.chips_needed, 1));
   q.x = (uint32_t)h.round_chips; q.y = __float_as_uint((float)fmin(p, 2.0)); q.z = 1u; q.w = (uint32_t)h.chips_needed;
   str128<CG>(obs + 32, q);
   // 48: money, hands_played, best_hand_this_ante, ante | shop_rerolls
