@@ -264,6 +264,24 @@ __device__ __forceinline__ uint64_t with_byte(uint64_t v, int i, int b) {
   return (v & ~(0xFFull << (8 * i))) | ((uint64_t)(b & 0xFF) << (8 * i));
 }
 __device__ __forceinline__ int nib_at(uint32_t v, int i) { return (int)((v >> (4 * i)) & 15); }
+// the ordered selection list: n hand slots (0..7, each at most once) as the low n nibbles of a word.  Both helpers are
+// branch-free: as loops over the list they ran to the longest list of the warp and were a quarter of the main pass's
+// instructions (ncu).
+// bit set of the listed slots
+__device__ __forceinline__ uint32_t sel_slot_mask(uint32_t order, int n) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) m |= (k < n ? 1u : 0u) << ((order >> (4 * k)) & 15u);
+  return m;
+}
+// position of `slot` in the list, -1 when it is not there (zero-nibble test on order ^ slot-in-every-nibble; the
+// lowest flagged nibble is always a true match, borrows can only flag nibbles above it)
+__device__ __forceinline__ int sel_find(uint32_t order, int n, int slot) {
+  const uint32_t x = order ^ (0x11111111u * (uint32_t)slot);
+  uint32_t t = (x - 0x11111111u) & ~x & 0x88888888u;
+  t &= n >= 8 ? 0xFFFFFFFFu : ((1u << (4 * n)) - 1u);
+  return t ? (__ffs((int)t) - 1) >> 2 : -1;
+}
 // 4 mask bits -> 4 bytes of 0/1
 __device__ __forceinline__ uint32_t spread4(uint32_t bits) { return ((bits & 0xF) * 0x00204081u) & 0x01010101u; }
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }

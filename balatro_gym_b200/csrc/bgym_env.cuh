@@ -944,9 +944,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
   if ((CATS & CAT_SELECT) && action >= BGYM_A_SELECT_BASE && action < BGYM_A_SELECT_BASE + 8) {
     // toggle in the ordered selection list (:1052-1058); legal only in PLAY phase by the mask
     int slot = action - BGYM_A_SELECT_BASE;
-    int found = -1;
-    #pragma unroll 1
-    for (int k = 0; k < h.sel_n; k++) if (nib_at(h.sel_order, k) == slot) found = k;
+    const int found = sel_find(h.sel_order, h.sel_n, slot);
     if (found >= 0) {
       uint32_t lo = h.sel_order & ((1u << (4 * found)) - 1);
       uint32_t hi = (found == 7) ? 0u : ((h.sel_order >> (4 * (found + 1))) << (4 * found));
@@ -1288,9 +1286,7 @@ __device__ __forceinline__ void obs_shop_block(const Hot& h, const uint8_t* rec,
 template <bool CG = false>
 __device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, uint64_t mask, uint8_t* obs /*smem, 176 B*/) {
   uint4 q;
-  uint32_t selm = 0;
-  #pragma unroll 1
-  for (int k = 0; k < h.sel_n; k++) selm |= 1u << nib_at(h.sel_order, k);
+  const uint32_t selm = sel_slot_mask(h.sel_order, h.sel_n);
   // 0: hand[8] | selected_cards[8]   (hand codes = deck[hand[i]], -1 when empty)
   q.x = (uint32_t)h.hand_code; q.y = (uint32_t)(h.hand_code >> 32);
   q.z = spread4(selm); q.w = spread4(selm >> 4);
@@ -1346,9 +1342,7 @@ __device__ __forceinline__ void write_obs_regs(const Hot& h, const ShopObs& so, 
 
 // selection record (BgymSel, 16 B): selected_cards[8] | action_mask_bits — the two observation fields a toggle changes
 __device__ __forceinline__ uint4 sel_words(const Hot& h, uint64_t mask) {
-  uint32_t selm = 0;
-  #pragma unroll 1
-  for (int k = 0; k < h.sel_n; k++) selm |= 1u << nib_at(h.sel_order, k);
+  const uint32_t selm = sel_slot_mask(h.sel_order, h.sel_n);
   uint4 q;
   q.x = spread4(selm); q.y = spread4(selm >> 4); q.z = (uint32_t)mask; q.w = (uint32_t)(mask >> 32);
   return q;

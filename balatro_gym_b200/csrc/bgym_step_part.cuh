@@ -101,14 +101,17 @@ __device__ __forceinline__ int policy_action(const Hot& h, uint64_t mask) {
 // No shared-memory staging of records, no bulk copies: each lane holds its record in eight registers, the next tile's
 // loads are issued before the current tile is served.
 // Deferred env indices are staged per warp in shared memory and appended to the device lists in
-// runs of >= 32 (one atomic per run).  One atomic per tile and list kept a single L2 slice busy for
+// runs of ~100 (one atomic per run, PART_STAGE).  One atomic per tile and list kept a single L2 slice busy for
 // most of the pass (~10^5 same-sector atomics per 2^20 envs); the counters also sit 128 B apart.
 constexpr int MAIN_WARPS = 8;
 #ifndef BGYM_MAIN_CTAS
 #define BGYM_MAIN_CTAS 3
 #endif
 constexpr int MAIN_CTAS_PER_SM = BGYM_MAIN_CTAS;
-constexpr int PART_STAGE = 64;
+#ifndef BGYM_PART_STAGE
+#define BGYM_PART_STAGE 128
+#endif
+constexpr int PART_STAGE = BGYM_PART_STAGE;   // entries per staged list; a list is flushed when a tile could overflow it
 constexpr int PART_CTR_STRIDE = 32;   // ints between list counters
 constexpr int MAIN_CTA_SMEM = MAIN_WARPS * N_LISTS_L1 * PART_STAGE * 4;   // static shared memory: the staged lists
 
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MAIN_CTAS_PER_SM) env_step_ma
         write_step_outputs(a, e, reward, terminated, info);
       }
     }
-    // defer the other envs: stage the env index in the warp's list, flush runs of >= 32
+    // defer the other envs: stage the env index in the warp's list, flush a list before a tile could overflow it
     if (__ballot_sync(0xffffffffu, cat >= 0)) {
 #pragma unroll
       for (int c = 0; c < N_LISTS_L1; c++) {
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(MAIN_WARPS * 32, MAIN_CTAS_PER_SM) env_step_ma
         if (bal) {
           if (cat == c) stage_list[c * PART_STAGE + staged[c] + __popc(bal & ((1u << lane) - 1))] = (int)e;
           staged[c] += __popc(bal);
-          if (staged[c] >= 32) { flush_list(c, staged[c]); staged[c] = 0; }
+          if (staged[c] > PART_STAGE - 32) { flush_list(c, staged[c]); staged[c] = 0; }
         }
       }
     }
