@@ -162,9 +162,9 @@ __device__ __forceinline__ bool name_matches(int ht, bool table_names, int hn) {
 }
 
 struct ScoreRng {  // native draws of the scoring path: Philox keyed by (seed), counter (blk, hand index, 1)
-  uint32_t seed, ctr; unsigned long long index; uint4 buf; int pos;
+  uint32_t seed, ctr; unsigned long long index; uint4 buf; int pos, skip;   // skip: words of the next block already consumed
   __device__ __forceinline__ uint32_t word() {
-    if (pos == 4) { buf = philox4x32_10(ctr++, (uint32_t)index, (uint32_t)(index >> 32), 1, seed, BGYM_PHILOX_KEY1); pos = 0; }
+    if (pos == 4) { buf = philox4x32_10(ctr++, (uint32_t)index, (uint32_t)(index >> 32), 1, seed, BGYM_PHILOX_KEY1); pos = skip; skip = 0; }
     uint32_t w = pos == 0 ? buf.x : pos == 1 ? buf.y : pos == 2 ? buf.z : buf.w;
     pos++;
     return w;
@@ -245,12 +245,58 @@ struct FxRow {
   __device__ __forceinline__ int money() const { return (int)(short)(q.w & 0xFFFF); }
 };
 
-// The effect table is staged in SHARED memory and each hand's (up to 8) rows are lifted into
-// registers once: per-lane joker ids index the table divergently, which the constant cache serialises
-// (one replay per distinct address in the warp) — in the (card x joker) loop that was ~99 % of the
-// kernel's time.
+// The interpreter's tables are staged in SHARED memory per CTA: per-lane joker ids index them divergently, which the
+// constant cache serialises (one replay per distinct address in the warp) — in the (card x joker) loop that was ~99 %
+// of the first version's time.  Three words per joker id:
+//   s_fx   the 16-byte effect row (chips, mult, xmult, money)
+//   s_jm   individual phase: the joker as a mask over card bits {rank 0..14} u {16 + suit 0..4}, bit 31 = Bloodstone
+//   s_uop  main phase as ONE branch-free micro-op: which hand predicate gates the joker, which of its three effects
+//          apply, and what scales them — every lane of a warp executes the same ~25 instructions per joker slot whatever
+//          its joker is (the switch over effect kinds ran once per distinct kind in the warp: 14 % of the kernel's
+//          instructions at 1-3 active lanes, ncu)
+// hand predicates (bit index in the per-hand word P)
+enum { HP_ALWAYS = 0, HP_SUIT0 = 1 /* ..4 */, HP_HALF = 5, HP_LAST_HAND = 6, HP_NO_DISCARDS = 7, HP_ALL_BLACK = 8, HP_SEEING_DOUBLE = 9,
+       HP_FLOWER_POT = 10, HP_KINGS = 11, HP_QUEENS = 12, HP_NAME0 = 13 /* + BGYM_HN_* (6 names) */, HP_NEVER = 31 };
+// micro-op fields
+enum { UOP_PRED_BITS = 5, UOP_CSCALE_SHIFT = 5, UOP_MSCALE_SHIFT = 7, UOP_CHIPS = 1 << 9, UOP_MULT = 1 << 10, UOP_XMULT = 1 << 11,
+       UOP_BARON = 1 << 12, UOP_MISPRINT = 1 << 13 };
+enum { SC_ONE = 0, SC_DISCARDS = 1, SC_DECK = 2, SM_ONE = 0, SM_NJ = 1, SM_QUEENS = 2 };
+__device__ __forceinline__ uint32_t main_uop(int kind, int arg) {
+  switch (kind) {
+    case BGYM_FX_MAIN_ALWAYS: return HP_ALWAYS | UOP_CHIPS | UOP_MULT | UOP_XMULT;
+    case BGYM_FX_MAIN_HANDNAME: return (arg >= 0 && arg < 6 ? HP_NAME0 + arg : HP_NEVER) | UOP_CHIPS | UOP_MULT | UOP_XMULT;
+    case BGYM_FX_MAIN_SUIT_ANY: return (HP_SUIT0 + (arg & 3)) | UOP_MULT;
+    case BGYM_FX_MAIN_STATE:
+      switch (arg) {
+        case BGYM_FXS_HALF: return HP_HALF | UOP_MULT;
+        case BGYM_FXS_ABSTRACT: return HP_ALWAYS | UOP_MULT | (SM_NJ << UOP_MSCALE_SHIFT);
+        case BGYM_FXS_ACROBAT: return HP_LAST_HAND | UOP_XMULT;
+        case BGYM_FXS_MYSTIC: return HP_NO_DISCARDS | UOP_MULT;
+        case BGYM_FXS_BANNER: return HP_ALWAYS | UOP_CHIPS | (SC_DISCARDS << UOP_CSCALE_SHIFT);
+        case BGYM_FXS_BLUE: return HP_ALWAYS | UOP_CHIPS | (SC_DECK << UOP_CSCALE_SHIFT);
+        case BGYM_FXS_MISPRINT: return HP_NEVER | UOP_MISPRINT;
+      }
+      return HP_NEVER;
+    case BGYM_FX_MAIN_SPECIAL:
+      switch (arg) {
+        case BGYM_FXSP_BLACKBOARD: return HP_ALL_BLACK | UOP_XMULT;
+        case BGYM_FXSP_SEEING_DOUBLE: return HP_SEEING_DOUBLE | UOP_XMULT;
+        case BGYM_FXSP_FLOWER_POT: return HP_FLOWER_POT | UOP_XMULT;
+        case BGYM_FXSP_BARON: return HP_KINGS | UOP_XMULT | UOP_BARON;
+        case BGYM_FXSP_SHOOT_MOON: return HP_QUEENS | UOP_MULT | (SM_QUEENS << UOP_MSCALE_SHIFT);
+      }
+      return HP_NEVER;
+  }
+  return HP_NEVER;    // individual-phase jokers and empty rows do nothing in the main phase
+}
+__device__ __forceinline__ uint32_t ind_mask(int kind, int arg) {
+  return (kind == BGYM_FX_IND_RANKSET || kind == BGYM_FX_IND_FACE) ? (uint32_t)arg
+       : (kind == BGYM_FX_IND_SUIT) ? ((1u << (16 + (arg & 3))) | ((arg & 0x80) ? 0x80000000u : 0u)) : 0u;
+}
+
 __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
   __shared__ uint4 s_fx[BGYM_NUM_JOKERS + 1];
+  __shared__ uint32_t s_jm[BGYM_NUM_JOKERS + 1], s_uop[BGYM_NUM_JOKERS + 1];
   for (int t = threadIdx.x; t < BGYM_NUM_JOKERS + 1; t += blockDim.x) {
     const BgymJokerFx f = c_joker_fx[t];
     uint4 q;
@@ -259,14 +305,22 @@ __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
     q.z = __float_as_uint(f.xmult);
     q.w = (uint32_t)(uint16_t)f.money;
     s_fx[t] = q;
+    s_jm[t] = t ? ind_mask(f.kind, f.arg) : 0u;
+    s_uop[t] = t ? main_uop(f.kind, f.arg) : (uint32_t)HP_NEVER;
   }
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
-    uint2 cw = __ldg(reinterpret_cast<const uint2*>(a.cards8) + i);
+  const int lane = threadIdx.x & 31;
+  const bool table_names = (a.flags & BGYM_SCORE_TABLE_NAMES) != 0;
+  // warp-uniform trip count: the Bloodstone rolls below are made by the whole warp
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < a.n; i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + lane;
+    const bool valid = i < a.n;
+    uint2 cw = make_uint2(0, 0);
+    if (valid) cw = __ldg(reinterpret_cast<const uint2*>(a.cards8) + i);
     uint64_t cards = u64_of(cw.x, cw.y);
-    int nc = a.n_cards ? a.n_cards[i] : 5;
+    int nc = !valid ? 0 : (a.n_cards ? a.n_cards[i] : 5);
     uint4 mw = make_uint4(0, 0, 0, 0);
-    if (a.mods8) mw = __ldg(reinterpret_cast<const uint4*>(a.mods8) + i);
+    if (a.mods8 && valid) mw = __ldg(reinterpret_cast<const uint4*>(a.mods8) + i);
     // classification + card chips
     HandHist hist;
     hist.clear();
@@ -291,53 +345,66 @@ __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
       if (!(suit == 3 || suit == 0)) all_black = 0;
       kings += rank == 13; queens += rank == 12;
     }
+    const bool with_jokers = a.jokers8 != nullptr;
+    uint64_t jraw = 0;
+    if (with_jokers && valid) {
+      const uint2 jw = __ldg(reinterpret_cast<const uint2*>(a.jokers8) + i);
+      jraw = u64_of(jw.x, jw.y);
+    }
     int ht;
     if (a.flags & BGYM_SCORE_RULES) {      // balatro_sim.py:220-400; Four Fingers / Shortcut are read from the joker slots
       uint32_t scnt = 0;
       for (int c = 0; c < nc; c++) scnt += 1u << (8 * (byte_at(cards, c) & 3));
       bool four_fingers = false, shortcut = false;
-      if (a.jokers8) {
-        const uint2 jw0 = __ldg(reinterpret_cast<const uint2*>(a.jokers8) + i);
-        const uint64_t jr = u64_of(jw0.x, jw0.y);
-        for (int j = 0; j < 8; j++) { const int id = byte_at(jr, j); four_fingers |= id == BGYM_J_FOUR_FINGERS; shortcut |= id == BGYM_J_SHORTCUT; }
-      }
+      for (int j = 0; j < 8; j++) { const int id = byte_at(jraw, j); four_fingers |= id == BGYM_J_FOUR_FINGERS; shortcut |= id == BGYM_J_SHORTCUT; }
       ht = classify_rules(hist.cnt, scnt, hist.rmask, nc, four_fingers, shortcut);
     } else {
       ht = classify(hist);
     }
-    int lvl = a.levels12 ? a.levels12[i * 12 + ht] : 1;
+    int lvl = (a.levels12 && valid) ? a.levels12[i * 12 + ht] : 1;
     int chips, mult;
     hand_base(ht, lvl, chips, mult);
     chips += chip_sum;
     double x_mult = 1.0;
     int money = 0;
-    if (a.jokers8) {
+    if (with_jokers) {      // (kernel argument: the whole warp takes this branch)
       // K4: table-driven joker interpreter (unified_scoring.py:156-244), joker order preserved
-      uint2 jw = __ldg(reinterpret_cast<const uint2*>(a.jokers8) + i);
-      uint64_t jraw = u64_of(jw.x, jw.y), jk = 0;
+      uint64_t jk = 0;
       int nj = 0;
-      for (int j = 0; j < 8; j++) { int id = byte_at(jraw, j); if (id) { jk |= (uint64_t)id << (8 * nj); nj++; } }
+      for (int j = 0; j < 8; j++) { int id = byte_at(jraw, j); if (id) { jk |= (uint64_t)min(id, BGYM_NUM_JOKERS) << (8 * nj); nj++; } }
       BgymScoreCtx cx;
       cx.hands_left = 4; cx.discards_left = 3; cx.deck_len = 52; cx.use_replay = 0; cx.bloodstone_bits = 0;
       cx.misprint[0] = 0;
-      if (a.ctx) cx = a.ctx[i];
-      bool table_names = (a.flags & BGYM_SCORE_TABLE_NAMES) != 0;
-      ScoreRng rng; rng.seed = a.seed; rng.ctr = 0; rng.index = (unsigned long long)i; rng.pos = 4;
-      // individual phase: card-major, joker-minor (:173-209).  A card is a bit set {rank 0..14} u
-      // {16 + suit 0..4}; a rank-set / face / suit joker is a mask over the same bits, so "fires" is one
-      // AND.  The loops are not unrolled (one small body instead of 64 copies) and everything but the
-      // Bloodstone roll is branch-free.
-      int ind_chips = 0, ind_mult = 0; double ind_x = 1.0;
-      // per-joker match masks, once per hand (individual-phase jokers are ~8 % of the ids: most are 0);
-      // bit 31 marks Bloodstone, which rolls for every card whether the suit matches or not
+      if (a.ctx && valid) cx = a.ctx[i];
+      ScoreRng rng; rng.seed = a.seed; rng.ctr = 0; rng.index = (unsigned long long)i; rng.pos = 4; rng.skip = 0;
+      // individual phase: card-major, joker-minor (:173-209).  A card is a bit set {rank 0..14} u {16 + suit 0..4};
+      // a rank-set / face / suit joker is a mask over the same bits (s_jm), so "fires" is one AND.  Bit 31 marks
+      // Bloodstone, which rolls for every card whether the suit matches or not.
       uint32_t jm[8];
+      int n_blood = 0;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
-        const uint32_t w0 = j < nj ? s_fx[min(byte_at(jk, j), BGYM_NUM_JOKERS)].x : 0u;
-        const int kind = (int)(w0 & 0xFF), arg = (int)(w0 >> 16);
-        jm[j] = (kind == BGYM_FX_IND_RANKSET || kind == BGYM_FX_IND_FACE) ? (uint32_t)arg
-              : (kind == BGYM_FX_IND_SUIT) ? ((1u << (16 + (arg & 3))) | ((arg & 0x80) ? 0x80000000u : 0u)) : 0u;
+        jm[j] = j < nj ? s_jm[byte_at(jk, j)] : 0u;
+        n_blood += jm[j] >> 31;
       }
+      // Bloodstone rolls (:161, `random() < 0.5` per (card, joker) pair in loop order): roll k reads stream words 2k and
+      // 2k + 1, and u01 < 0.5 is "bit 31 of word 2k is clear" (u01 = ((w0 >> 5) * 2^26 + (w1 >> 6)) / 2^53).  Philox blocks
+      // are independent, so the WARP makes them: lane b computes block b of the hand that needs rolls — one converged
+      // Philox pass per such hand instead of a chain of up to 32 on one lane (16 % of the kernel's instructions, ncu).
+      const int n_rolls = cx.use_replay ? 0 : nc * n_blood;
+      uint32_t roll_even = 0, roll_odd = 0;      // bit b: roll 2b / roll 2b + 1 hit
+      {
+        uint32_t need = __ballot_sync(0xffffffffu, n_rolls > 0);
+        while (need) {
+          const int src = __ffs((int)need) - 1;
+          need &= need - 1;
+          const unsigned long long idx = __shfl_sync(0xffffffffu, rng.index, src);
+          const uint4 blk = philox4x32_10_inl((uint32_t)lane, (uint32_t)idx, (uint32_t)(idx >> 32), 1, a.seed, BGYM_PHILOX_KEY1);
+          const uint32_t e = __ballot_sync(0xffffffffu, !(blk.x >> 31)), o = __ballot_sync(0xffffffffu, !(blk.z >> 31));
+          if (lane == src) { roll_even = e; roll_odd = o; }
+        }
+      }
+      int ind_chips = 0, ind_mult = 0, roll = 0; double ind_x = 1.0;
 #pragma unroll 1
       for (int c = 0; c < nc; c++) {
         const uint32_t cardbits = (1u << byte_at(rank8, c)) | (1u << (16 + nib_at(suit8, c))) | 0x80000000u;
@@ -345,66 +412,64 @@ __global__ void __launch_bounds__(256) score_hands_kernel(ScoreArgs a) {
         for (int j = 0; j < 8; j++) {
           if (cardbits & jm[j]) {          // rare: the card matches, or the joker is Bloodstone
             bool fire = (cardbits & jm[j] & 0x7FFFFFFFu) != 0u;
-            if (jm[j] & 0x80000000u) {     // Bloodstone: one roll per (card, joker) pair (:161)
-              const bool hit = cx.use_replay ? ((cx.bloodstone_bits >> c) & 1) : (rng.u01() < 0.5);
+            if (jm[j] & 0x80000000u) {
+              const bool hit = cx.use_replay ? ((cx.bloodstone_bits >> c) & 1) : ((((roll & 1) ? roll_odd : roll_even) >> (roll >> 1)) & 1u);
+              roll++;
               fire = fire && hit;
             }
             if (fire) {
-              const FxRow fx = {s_fx[min(byte_at(jk, j), BGYM_NUM_JOKERS)]};
+              const FxRow fx = {s_fx[byte_at(jk, j)]};
               ind_chips += fx.chips(); ind_mult += fx.mult(); money += fx.money(); ind_x *= (double)fx.xmult();
             }
           }
         }
       }
+      rng.ctr = (uint32_t)(n_rolls >> 1); rng.skip = (n_rolls & 1) * 2;     // the stream stands behind word 2 * n_rolls
       chips += ind_chips; mult += ind_mult; x_mult *= ind_x;
-      // main phase, joker order (:211-244)
+      // main phase, joker order (:211-244): one micro-op per joker slot (s_uop)
+      const int n_suit_names = __popc(suit_present) + (int)stone_present;
+      uint32_t P = 1u | (suit_present & 15u) << HP_SUIT0;
+      P |= (nc <= 3 ? 1u : 0u) << HP_HALF | (cx.hands_left == 1 ? 1u : 0u) << HP_LAST_HAND | (cx.discards_left == 0 ? 1u : 0u) << HP_NO_DISCARDS;
+      P |= (all_black ? 1u : 0u) << HP_ALL_BLACK | (((suit_present & 1) && n_suit_names > 1) ? 1u : 0u) << HP_SEEING_DOUBLE;
+      P |= (n_suit_names == 4 ? 1u : 0u) << HP_FLOWER_POT | (kings > 0 ? 1u : 0u) << HP_KINGS | (queens > 0 ? 1u : 0u) << HP_QUEENS;
+      {  // hand-name jokers (complete_joker_effects.py:64-80 vs balatro_env_2.py:674)
+        const uint32_t tn = table_names ? 1u : 0u;
+        P |= (tn & (ht == BGYM_HT_ONE_PAIR)) << (HP_NAME0 + BGYM_HN_PAIR) | (tn & (ht == BGYM_HT_THREE_KIND)) << (HP_NAME0 + BGYM_HN_THREE_OAK);
+        P |= (tn & (ht == BGYM_HT_FOUR_KIND)) << (HP_NAME0 + BGYM_HN_FOUR_OAK) | (uint32_t)(ht == BGYM_HT_TWO_PAIR) << (HP_NAME0 + BGYM_HN_TWO_PAIR);
+        P |= (uint32_t)(ht == BGYM_HT_STRAIGHT) << (HP_NAME0 + BGYM_HN_STRAIGHT) | (uint32_t)(ht == BGYM_HT_FLUSH) << (HP_NAME0 + BGYM_HN_FLUSH);
+      }
+      const uint64_t cscale = 1ull | (uint64_t)cx.discards_left << 16 | (uint64_t)cx.deck_len << 32;
+      const uint64_t mscale = 1ull | (uint64_t)nj << 16 | (uint64_t)queens << 32;
+      const double baron = c_pow_1_5[min(kings, 100)];
       int misprint_seen = 0;
-      int n_suit_names = __popc(suit_present) + (int)stone_present;
 #pragma unroll 1
       for (int j = 0; j < nj; j++) {
-        const FxRow row = {s_fx[min(byte_at(jk, j), BGYM_NUM_JOKERS)]};
-        struct { int kind, arg, chips, mult; float xmult; } fx = {row.kind(), row.arg(), row.chips(), row.mult(), row.xmult()};
-        int ec = 0, em = 0; double ex = 1.0;
-        switch (fx.kind) {
-          case BGYM_FX_MAIN_ALWAYS: ec = fx.chips; em = fx.mult; ex = fx.xmult; break;
-          case BGYM_FX_MAIN_HANDNAME: if (name_matches(ht, table_names, fx.arg)) { ec = fx.chips; em = fx.mult; ex = fx.xmult; } break;
-          case BGYM_FX_MAIN_SUIT_ANY: if ((suit_present >> fx.arg) & 1) { em = fx.mult; } break;
-          case BGYM_FX_MAIN_STATE:
-            switch (fx.arg) {
-              case BGYM_FXS_HALF: if (nc <= 3) em = fx.mult; break;
-              case BGYM_FXS_ABSTRACT: em = fx.mult * nj; break;
-              case BGYM_FXS_ACROBAT: if (cx.hands_left == 1) ex = fx.xmult; break;
-              case BGYM_FXS_MYSTIC: if (cx.discards_left == 0) em = fx.mult; break;
-              case BGYM_FXS_BANNER: ec = fx.chips * cx.discards_left; break;
-              case BGYM_FXS_BLUE: ec = fx.chips * cx.deck_len; break;
-              case BGYM_FXS_MISPRINT:
-                em = cx.use_replay ? cx.misprint[min(misprint_seen, 4)] : rng.below(24);
-                misprint_seen++;
-                break;
-            }
-            break;
-          case BGYM_FX_MAIN_SPECIAL:
-            switch (fx.arg) {
-              case BGYM_FXSP_BLACKBOARD: if (all_black) ex = fx.xmult; break;
-              case BGYM_FXSP_SEEING_DOUBLE: if ((suit_present & 1) && n_suit_names > 1) ex = fx.xmult; break;
-              case BGYM_FXSP_FLOWER_POT: if (n_suit_names == 4) ex = fx.xmult; break;
-              case BGYM_FXSP_BARON: if (kings > 0) ex = c_pow_1_5[kings]; break;
-              case BGYM_FXSP_SHOOT_MOON: if (queens > 0) em = fx.mult * queens; break;
-            }
-            break;
-          default: break;
+        const int id = byte_at(jk, j);
+        const uint32_t u = s_uop[id];
+        const FxRow row = {s_fx[id]};
+        const bool on = (P >> (u & ((1u << UOP_PRED_BITS) - 1))) & 1u;
+        const int cs = (int)((cscale >> (16 * ((u >> UOP_CSCALE_SHIFT) & 3u))) & 0xFFFFu);
+        const int ms = (int)((mscale >> (16 * ((u >> UOP_MSCALE_SHIFT) & 3u))) & 0xFFFFu);
+        int ec = (on && (u & UOP_CHIPS)) ? row.chips() * cs : 0;
+        int em = (on && (u & UOP_MULT)) ? row.mult() * ms : 0;
+        double ex = (on && (u & UOP_XMULT)) ? ((u & UOP_BARON) ? baron : (double)row.xmult()) : 1.0;
+        if (u & UOP_MISPRINT) {      // the one main-phase effect that draws (rare)
+          em = cx.use_replay ? cx.misprint[min(misprint_seen, 4)] : rng.below(24);
+          misprint_seen++;
         }
         chips += ec; mult += em; x_mult *= ex;
       }
     }
     // final_score = int(chips * mult * x_mult), unified_scoring.py:286
     long long score = (long long)((double)((long long)chips * (long long)mult) * x_mult);
-    a.hand_type[i] = (uint8_t)ht;
-    a.chips[i] = chips;
-    a.mult[i] = mult;
-    if (a.x_mult) a.x_mult[i] = x_mult;
-    a.score[i] = score;
-    if (a.money) a.money[i] = money;
+    if (valid) {
+      a.hand_type[i] = (uint8_t)ht;
+      a.chips[i] = chips;
+      a.mult[i] = mult;
+      if (a.x_mult) a.x_mult[i] = x_mult;
+      a.score[i] = score;
+      if (a.money) a.money[i] = money;
+    }
   }
 }
 
