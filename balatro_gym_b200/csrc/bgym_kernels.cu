@@ -911,6 +911,17 @@ int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, cons
   // the passes are bound by resident warps, not by idle SMs.)
   const int gt = GATHER_WARPS * 32;
   auto lgrid = [&](int list) { int g = tile_grid(n, GATHER_WARPS, list_ctas(list)); return g < 1 ? 1 : g; };
+  // BGYM_LEVEL_KERNELS (bit 0: level 2, bit 1: level 1): one kernel per level on the launch stream
+  // (env_step_level_kernel) instead of one per list on forked streams
+  // Measured (tools/exp/level_kernels.sh): level 2 as one kernel 0.1841 -> 0.1830 ms per step (one launch instead of a
+  // fork, two launches and a join) — the default; level 1 as one kernel 0.218 ms (255 registers and 2 KB of spills: the
+  // compiler keeps state of all seven bodies alive across the switch).
+  static const int level_kernels = getenv("BGYM_LEVEL_KERNELS") ? atoi(getenv("BGYM_LEVEL_KERNELS")) : 1;
+  if ((level_kernels & 2) && !timing) {
+    env_step_level_kernel<1><<<g_sm_count * level_ctas(1), 32, 0, s>>>(a);
+    env_step_level_kernel<2><<<g_sm_count * level_ctas(2), 32, 32 * BGYM_COLD_BYTES, s>>>(a);
+    return cuda_rc(cudaGetLastError(), "bgym_step launch");
+  }
   static const bool serial = getenv("BGYM_SERIAL_GATHER") != nullptr;
   const bool fork = sc->streams_ok && !serial && timing != 2;
   cudaStream_t ls[N_LISTS];
@@ -925,10 +936,14 @@ int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, cons
   if (fork)
     for (int i = 0; i < PART_SIDE_STREAMS; i++) { cudaEventRecord(sc->ev_side[i], sc->side[i]); cudaStreamWaitEvent(s, sc->ev_side[i], 0); }
   if (timing == 1) cudaEventRecord(tev[2], s);
-  if (fork) { cudaEventRecord(sc->ev_fork2, s); cudaStreamWaitEvent(sc->side[0], sc->ev_fork2, 0); ls[L_RESET] = sc->side[0]; }
-  BGYM_LAUNCH_LIST(L_ADVANCE) BGYM_LAUNCH_LIST(L_RESET)
+  if ((level_kernels & 1) && timing != 2) {
+    env_step_level_kernel<2><<<g_sm_count * level_ctas(2), 32, 32 * BGYM_COLD_BYTES, s>>>(a);
+  } else {
+    if (fork) { cudaEventRecord(sc->ev_fork2, s); cudaStreamWaitEvent(sc->side[0], sc->ev_fork2, 0); ls[L_RESET] = sc->side[0]; }
+    BGYM_LAUNCH_LIST(L_ADVANCE) BGYM_LAUNCH_LIST(L_RESET)
+    if (fork) { cudaEventRecord(sc->ev_side[0], sc->side[0]); cudaStreamWaitEvent(s, sc->ev_side[0], 0); }
+  }
 #undef BGYM_LAUNCH_LIST
-  if (fork) { cudaEventRecord(sc->ev_side[0], sc->side[0]); cudaStreamWaitEvent(s, sc->ev_side[0], 0); }
   if (timing == 1) cudaEventRecord(tev[3], s);
 #ifdef BGYM_TILE_CLOCK
   {

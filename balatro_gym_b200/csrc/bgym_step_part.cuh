@@ -489,6 +489,71 @@ static_assert(L_PLAY == 0 && L_ADVANCE == 7 && N_LISTS == 9, "list_smem_bytes() 
 #define BGYM_PLAY_CTAS GATHER_CTAS_PER_SM
 #endif
 __host__ __device__ constexpr int list_ctas(int list) { return list == 0 /*L_PLAY*/ ? BGYM_PLAY_CTAS : GATHER_CTAS_PER_SM; }
+// one tile of list LIST: lane `lane` serves env e (bgym_step_part.cuh head: which path each list is)
+template <int LIST>
+__device__ __forceinline__ void list_tile(const StepArgs& a, long long e, bool active, int lane, uint8_t* cold_slot) {
+  if (LIST == L_PLAY) gather_tile<CAT_PLAY, TM_DEFER | STG_RO>(a, e, active, lane, cold_slot);
+  else if (LIST == L_CONS) gather_tile<CAT_CONS, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
+  else if (LIST == L_GEN) gather_tile<CAT_GEN, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
+  else if (LIST == L_MISC) gather_tile<CAT_OTHER | CAT_SELECT, TM_DEFER | TM_SAMPLE | STG_RW>(a, e, active, lane, cold_slot);
+  else if (LIST == L_DISCARD) gather_tile<CAT_DISCARD, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
+  else if (LIST == L_SHOP) gather_tile<CAT_SHOP, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
+  else if (LIST == L_BLIND) gather_tile<CAT_BLIND, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
+  else if (LIST == L_ADVANCE) advance_tile(a, e, active, cold_slot);
+  else reset_tile(a, e, active, cold_slot);
+}
+
+// ONE KERNEL PER LEVEL (BGYM_LEVEL_KERNELS=1): every tile body of the level inlined into one kernel, the warps walk the
+// level's lists as one concatenated tile space, heaviest list first.  A step is then three launches on one stream — no
+// forked streams, no events between the levels.  (The first single-kernel version of this round called out-of-line
+// tile functions: 2 KB stack frames, see profiles/r02_step_experiments.md #1; here the bodies are inlined and the kernel
+// takes the largest body's registers.)
+#ifndef BGYM_L1K_CTAS
+#define BGYM_L1K_CTAS 8        // the level-1 kernel needs ~200 registers to hold every list's body without spills
+#endif
+__host__ __device__ constexpr int level_ctas(int level) { return level == 1 ? BGYM_L1K_CTAS : GATHER_CTAS_PER_SM; }
+template <int LEVEL>
+__global__ void __launch_bounds__(32, level_ctas(LEVEL)) env_step_level_kernel(const __grid_constant__ StepArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  uint8_t* cold_slot = smem + lane * BGYM_COLD_BYTES;
+  constexpr int NL = LEVEL == 1 ? N_LISTS_L1 : 2;
+  // walk order: long tiles first, so that the level ends on short ones
+  const int order[7] = {LEVEL == 1 ? (int)L_CONS : (int)L_RESET, LEVEL == 1 ? (int)L_GEN : (int)L_ADVANCE, L_PLAY, L_SHOP, L_DISCARD, L_BLIND, L_MISC};
+  int cnt[NL], first[NL + 1];
+  first[0] = 0;
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    cnt[k] = a.part_counters[order[k] * PART_CTR_STRIDE];
+    first[k + 1] = first[k] + ((cnt[k] + 31) >> 5);
+  }
+  for (int t = blockIdx.x; t < first[NL]; t += gridDim.x) {
+    int k = 0;
+#pragma unroll
+    for (int q = 1; q < NL; q++) k += t >= first[q];
+    int list_id = 0, tile0 = 0, count = 0;
+#pragma unroll
+    for (int q = 0; q < NL; q++) if (k == q) { list_id = order[q]; tile0 = first[q]; count = cnt[q]; }
+    const int idx = (t - tile0) * 32 + lane;
+    const bool active = idx < count;
+    const long long e = active ? (long long)__ldcg(a.part_lists + (long long)list_id * a.part_cap + idx) : -1;
+    if (LEVEL == 1) {
+      switch (list_id) {
+        case L_PLAY: list_tile<L_PLAY>(a, e, active, lane, cold_slot); break;
+        case L_CONS: list_tile<L_CONS>(a, e, active, lane, cold_slot); break;
+        case L_GEN: list_tile<L_GEN>(a, e, active, lane, cold_slot); break;
+        case L_MISC: list_tile<L_MISC>(a, e, active, lane, cold_slot); break;
+        case L_DISCARD: list_tile<L_DISCARD>(a, e, active, lane, cold_slot); break;
+        case L_SHOP: list_tile<L_SHOP>(a, e, active, lane, cold_slot); break;
+        default: list_tile<L_BLIND>(a, e, active, lane, cold_slot); break;
+      }
+    } else {
+      if (list_id == L_ADVANCE) list_tile<L_ADVANCE>(a, e, active, lane, cold_slot);
+      else list_tile<L_RESET>(a, e, active, lane, cold_slot);
+    }
+  }
+}
+
 template <int LIST>
 __global__ void __launch_bounds__(GATHER_WARPS * 32, list_ctas(LIST)) env_step_list_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -505,15 +570,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32, list_ctas(LIST)) env_step_l
     unsigned long long tc0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tc0));
 #endif
-    if (LIST == L_PLAY) gather_tile<CAT_PLAY, TM_DEFER | STG_RO>(a, e, active, lane, cold_slot);
-    else if (LIST == L_CONS) gather_tile<CAT_CONS, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
-    else if (LIST == L_GEN) gather_tile<CAT_GEN, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
-    else if (LIST == L_MISC) gather_tile<CAT_OTHER | CAT_SELECT, TM_DEFER | TM_SAMPLE | STG_RW>(a, e, active, lane, cold_slot);
-    else if (LIST == L_DISCARD) gather_tile<CAT_DISCARD, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
-    else if (LIST == L_SHOP) gather_tile<CAT_SHOP, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
-    else if (LIST == L_BLIND) gather_tile<CAT_BLIND, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
-    else if (LIST == L_ADVANCE) advance_tile(a, e, active, cold_slot);
-    else reset_tile(a, e, active, cold_slot);
+    list_tile<LIST>(a, e, active, lane, cold_slot);
 #ifdef BGYM_TILE_CLOCK
     // diagnostic build (-DBGYM_TILE_CLOCK): per list, when its first tile started, when its last tile ended, and the tile
     // durations (ns), kept in the spare words behind the list's counter; bgym_step prints them every 64 calls
