@@ -182,12 +182,15 @@ __device__ __forceinline__ uint64_t action_mask(const Hot& h, const uint8_t* rec
     if (h.sel_n > 0 && h.discards_left > 0) m |= 1ull << BGYM_A_DISCARD;
     m |= ((1ull << h.cons_n) - 1) << BGYM_A_USE_CONS_BASE;
   } else if (h.phase == BGYM_PHASE_SHOP) {
-    int n_items = rec[OFF_N_ITEMS];
-    #pragma unroll 1
-    for (int i = 0; i < n_items; i++) {
-      int cost = *reinterpret_cast<const int*>(rec + OFF_ITEM_COST + 4 * i);
-      if (h.money >= cost) m |= 1ull << (BGYM_A_SHOP_BUY_BASE + i);
-    }
+    // the nine cost words with three loads in flight together, the compares unrolled (as a loop over n_items — one
+    // dependent load per item, run twice per tile — this was a fifth of the shop list kernel's stall samples)
+    const int n_items = rec[OFF_N_ITEMS];
+    const uint2 c01 = *reinterpret_cast<const uint2*>(rec + OFF_ITEM_COST);
+    const uint4 c25 = *reinterpret_cast<const uint4*>(rec + OFF_ITEM_COST + 8), c69 = *reinterpret_cast<const uint4*>(rec + OFF_ITEM_COST + 24);
+    const int cost[9] = {(int)c01.x, (int)c01.y, (int)c25.x, (int)c25.y, (int)c25.z, (int)c25.w, (int)c69.x, (int)c69.y, (int)c69.z};
+    #pragma unroll
+    for (int i = 0; i < 9; i++)
+      if (i < n_items && h.money >= cost[i]) m |= 1ull << (BGYM_A_SHOP_BUY_BASE + i);
     if (h.money >= h.shop_reroll_state) m |= 1ull << BGYM_A_SHOP_REROLL;
     m |= 1ull << BGYM_A_SHOP_END;
     m |= ((1ull << h.joker_n) - 1) << BGYM_A_SELL_JOKER_BASE;
@@ -913,8 +916,9 @@ struct StepInfo {
 //   *defer_snap receives the draw-sequence position (Draws::snapshot) and h.rng_ctr the raw block counter; the caller hands
 //   the env to a second-level tile that runs step_env_advance() — there every lane of the warp advances a round, whereas
 //   inside the PLAY tile a few lanes would walk that long path while the others wait.  -1 = nothing deferred.
-enum { CAT_SELECT = 1, CAT_PLAY = 2, CAT_DISCARD = 4, CAT_CONS = 8, CAT_SHOP = 16, CAT_BLIND = 32, CAT_GEN = 64,
-       CAT_OTHER = CAT_CONS | CAT_SHOP | CAT_BLIND | CAT_GEN, CAT_ALL = 127 };
+//   CAT_SHOP_END = leaving the shop: like a blind selection it deals a hand (draw + hand codes), so it rides with CAT_BLIND
+enum { CAT_SELECT = 1, CAT_PLAY = 2, CAT_DISCARD = 4, CAT_CONS = 8, CAT_SHOP = 16, CAT_BLIND = 32, CAT_GEN = 64, CAT_SHOP_END = 128,
+       CAT_OTHER = CAT_CONS | CAT_SHOP | CAT_BLIND | CAT_GEN | CAT_SHOP_END, CAT_ALL = 255 };
 template <int CATS, bool DEFER_ADVANCE>
 __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_t mask, const BgymDraws* tape, double& reward_out,
                          int& terminated_out, StepInfo& info, int* defer_snap, uint64_t* immolate_removed = nullptr) {
@@ -1161,7 +1165,7 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     else if (progress > 0.8 && h.discards_left > 1) reward -= 0.3;
   } else if ((CATS & CAT_CONS) && action >= BGYM_A_USE_CONS_BASE && action < BGYM_A_USE_CONS_BASE + 5) {
     rare_op = RARE_CONSUMABLE; rare_arg = action - BGYM_A_USE_CONS_BASE;
-  } else if ((CATS & CAT_SHOP) && action == BGYM_A_SHOP_END) {
+  } else if ((CATS & CAT_SHOP_END) && action == BGYM_A_SHOP_END) {
     h.phase = BGYM_PHASE_PLAY;
     draw_cards(h);
     hand_changed = true;
@@ -1267,8 +1271,12 @@ __device__ __forceinline__ int obs_cons_id(int cid) { return cid >= BGYM_CONS_EN
 struct ShopObs { uint32_t w[11]; };   // it0 | it1,2 | it3,4 | it5,6 | it7,8 | it9,ic0 | ic1,2 | ic3,4 | ic5,6 | ic7,8 | ic9
 
 __device__ __forceinline__ void obs_shop_block(const Hot& h, const uint8_t* rec, ShopObs& so) {
-  bool shop = h.phase == BGYM_PHASE_SHOP;
-  int n_items = shop ? rec[OFF_N_ITEMS] : 0;
+  if (h.phase != BGYM_PHASE_SHOP) {       // nothing to read: a whole tile of the PLAY-phase lists takes this branch
+#pragma unroll
+    for (int i = 0; i < 11; i++) so.w[i] = 0;
+    return;
+  }
+  int n_items = rec[OFF_N_ITEMS];
   int it[10], ic[10];
 #pragma unroll
   for (int i = 0; i < 10; i++) {

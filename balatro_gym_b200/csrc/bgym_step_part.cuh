@@ -49,6 +49,7 @@ __device__ __forceinline__ int route_env(const Hot& h, int action, uint64_t play
   }
   if (h.phase == BGYM_PHASE_SHOP) {
     if (action == BGYM_A_SHOP_REROLL) return L_GEN;
+    if (action == BGYM_A_SHOP_END) return L_BLIND;      // deals a hand, like a blind selection
     return (action >= BGYM_A_SHOP_BUY_BASE && action < BGYM_A_SELL_JOKER_BASE + 5) ? L_SHOP : L_MISC;
   }
   if (h.phase == BGYM_PHASE_BLIND_SELECT) {
@@ -498,7 +499,7 @@ __device__ __forceinline__ void list_tile(const StepArgs& a, long long e, bool a
   else if (LIST == L_MISC) gather_tile<CAT_OTHER | CAT_SELECT, TM_DEFER | TM_SAMPLE | STG_RW>(a, e, active, lane, cold_slot);
   else if (LIST == L_DISCARD) gather_tile<CAT_DISCARD, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
   else if (LIST == L_SHOP) gather_tile<CAT_SHOP, TM_DEFER | STG_RW>(a, e, active, lane, cold_slot);
-  else if (LIST == L_BLIND) gather_tile<CAT_BLIND, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
+  else if (LIST == L_BLIND) gather_tile<CAT_BLIND | CAT_SHOP_END, TM_DEFER | STG_RO | TM_COLD_CLEAN>(a, e, active, lane, cold_slot);
   else if (LIST == L_ADVANCE) advance_tile(a, e, active, cold_slot);
   else reset_tile(a, e, active, cold_slot);
 }
