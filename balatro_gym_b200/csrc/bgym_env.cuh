@@ -203,44 +203,52 @@ __device__ __forceinline__ uint64_t action_mask(const Hot& h, const uint8_t* rec
 // ---------------------------------------------------------------------------------------------
 // hand list operations
 // ---------------------------------------------------------------------------------------------
+// The three hand-list helpers below run over the eight hand slots with STATIC slot indices (fully unrolled, predicated):
+// as loops over hand_n with a run-time byte position they were ~25 instructions per slot (64-bit variable shifts to
+// extract and insert a byte) with one dependent deck load per trip; unrolled, a slot is ~8 instructions and the eight
+// deck loads are in flight together.
 // BalatroGame._draw_cards balatro_game.py:95-109: top up with the lowest deck indices not in hand
 __device__ __forceinline__ void draw_cards(Hot& h) {
   int want = h.hand_size - h.hand_n;
   if (want <= 0) return;
   uint64_t in_hand = 0;
-  #pragma unroll 1
-  for (int i = 0; i < h.hand_n; i++) in_hand |= 1ull << byte_at(h.hand, i);
+#pragma unroll
+  for (int i = 0; i < 8; i++) if (i < h.hand_n) in_hand |= 1ull << ((h.hand >> (8 * i)) & 0xFF);
   uint64_t avail = ~in_hand & ((h.deck_n >= 64) ? ~0ull : ((1ull << h.deck_n) - 1));
-  #pragma unroll 1
-  while (want > 0 && avail && h.hand_n < 8) {
-    int idx = __ffsll((long long)avail) - 1;
-    avail &= avail - 1;
-    h.hand = with_byte(h.hand, h.hand_n, idx);
-    h.hand_n++;
-    want--;
+  const int n0 = h.hand_n;
+#pragma unroll
+  for (int sl = 0; sl < 8; sl++) {
+    if (sl >= n0 && sl < n0 + want && avail) {      // (avail runs dry for good: the filled slots stay a prefix)
+      const uint64_t idx = (uint64_t)(__ffsll((long long)avail) - 1);
+      avail &= avail - 1;
+      h.hand = (h.hand & ~(0xFFull << (8 * sl))) | (idx << (8 * sl));
+      h.hand_n++;
+    }
   }
 }
 // remove the hand slots in `slots` (bit set), keeping order
 __device__ __forceinline__ void remove_slots(Hot& h, int slots) {
-  uint64_t out = ~0ull;
+  uint64_t out = 0;
   int n = 0;
-  #pragma unroll 1
-  for (int i = 0; i < h.hand_n; i++) {
-    if ((slots >> i) & 1) continue;
-    out = with_byte(out, n, byte_at(h.hand, i));
-    n++;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    if (i < h.hand_n && !((slots >> i) & 1)) {
+      out |= ((h.hand >> (8 * i)) & 0xFF) << (8 * n);
+      n++;
+    }
   }
-  h.hand = out;
+  h.hand = out | (n >= 8 ? 0ull : (~0ull << (8 * n)));     // empty slots read 0xFF
   h.hand_n = n;
 }
 // hand_code cache: card code of every hand slot (what obs['hand'] shows), refreshed whenever the
 // hand list changes so that passes that only have the hot record can emit the observation
 __device__ __forceinline__ void refresh_hand_codes(Hot& h, const uint8_t* rec) {
   uint64_t codes = ~0ull;
-#pragma unroll 1
-  for (int i = 0; i < h.hand_n; i++) {
-    int idx = byte_at(h.hand, i);
-    if (idx < h.deck_n) codes = with_byte(codes, i, c16_code(deck16(rec, idx)));
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int idx = (int)((h.hand >> (8 * i)) & 0xFF);
+    if (i < h.hand_n && idx < h.deck_n)
+      codes = (codes & ~(0xFFull << (8 * i))) | ((uint64_t)c16_code(deck16(rec, idx)) << (8 * i));
   }
   h.hand_code = codes;
 }
@@ -996,8 +1004,13 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     h.highlight |= sel_slots;
     HandHist hist;
     hist.clear();
-    #pragma unroll 1
-    for (int sl = 0; sl < 8; sl++) if ((h.highlight >> sl) & 1) hist.add(c16_code(deck16(rec, sl)));
+    {
+      const uint4 d8 = *reinterpret_cast<const uint4*>(rec + OFF_DECK);      // deck[0..7], one load
+      const uint32_t dw[4] = {d8.x, d8.y, d8.z, d8.w};
+      #pragma unroll
+      for (int sl = 0; sl < 8; sl++)
+        if ((h.highlight >> sl) & 1) hist.add(c16_code((int)((dw[sl >> 1] >> (16 * (sl & 1))) & 0xFFFFu)));
+    }
     int ht = classify(hist);
     // ---- boss gate (boss_blinds.py:380-407) ----
     bool allowed = true;
@@ -1017,10 +1030,10 @@ __device__ void step_env(Hot& h, uint8_t* hot, uint8_t* rec, int action, uint64_
     long long fs = base_score;
     // steel cards left in hand (:560-570)
     int n_steel = 0;
-    #pragma unroll 1
-    for (int i = 0; i < h.hand_n; i++) {
-      int idx = byte_at(h.hand, i);
-      if (!((sel_slots >> i) & 1) && idx < 52 && c16_enh(deck16(rec, idx)) == BGYM_ENH_STEEL) n_steel++;
+    #pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int idx = (int)((h.hand >> (8 * i)) & 0xFF);
+      if (i < h.hand_n && !((sel_slots >> i) & 1) && idx < 52 && c16_enh(deck16(rec, idx)) == BGYM_ENH_STEEL) n_steel++;
     }
     fs = (long long)((double)fs * c_pow_1_5[n_steel]);
     // boss modification ratio (:745-755, boss_blinds.py:409-445)

@@ -776,6 +776,10 @@ static bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintp
 
 // scratch of the partitioned step (deferred-env lists, their counters, the per-env continuation word), one set per
 // (device, stream) in use; bgym_release_stream() gives a set back
+// default launch plan of level 1 (see bgym_step): streams by list, launch order
+#define BGYM_L1_PLAN_STREAMS "0121230"
+#define BGYM_L1_PLAN_STREAMS_FUSED "0123456"
+#define BGYM_L1_PLAN_ORDER "2105463"
 constexpr int PART_SIDE_STREAMS = 6;   // the seven level-1 list kernels run concurrently: launch stream + six forked ones
 struct PartScratch { bool used; int dev; void* stream; long long cap; int* lists; int* counters; uint16_t* aux;
 
@@ -926,24 +930,51 @@ int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, cons
   const bool fork = sc->streams_ok && !serial && timing != 2;
   cudaStream_t ls[N_LISTS];
   for (int l = 0; l < N_LISTS; l++) ls[l] = s;
+  // Level-1 launch plan: which stream each list kernel goes to (0 = the launch stream, k = forked stream k - 1) and the
+  // launch order.  Kernels on one stream run one after the other, kernels on different streams concurrently — in an order
+  // the block scheduler picks, and the level's duration moves by +-5 % with it (profiles/r02_step_experiments.md).  The plan
+  // puts the lists with long tiles at the head of the streams and chains the lists with short tiles behind them, so that
+  // the level ends on short tiles.  BGYM_L1_STREAMS / BGYM_L1_ORDER (7 digits each, indexed / listing PLAY CONS GEN MISC
+  // DISCARD SHOP BLIND = 0..6) override it; with the fused policy every env outside PLAY phase is in MISC.
+  static const char* plan_streams_env = getenv("BGYM_L1_STREAMS");
+  static const char* plan_order_env = getenv("BGYM_L1_ORDER");
+  static const char* plan_streams_f_env = getenv("BGYM_L1_STREAMS_FUSED");
+  const bool fusedp = (flags & BGYM_FLAG_RANDOM_POLICY) != 0;
+  const char* plan_streams = fusedp ? (plan_streams_f_env ? plan_streams_f_env : BGYM_L1_PLAN_STREAMS_FUSED)
+                                    : (plan_streams_env ? plan_streams_env : BGYM_L1_PLAN_STREAMS);
+  const char* plan_order = plan_order_env ? plan_order_env : BGYM_L1_PLAN_ORDER;
+  int n_side = 0;
   if (fork) {
+    for (int l = 0; l < N_LISTS_L1; l++) {
+      int k = plan_streams[l] - '0';
+      if (k < 0 || k > PART_SIDE_STREAMS) k = 0;
+      ls[l] = k == 0 ? s : sc->side[k - 1];
+      if (k > n_side) n_side = k;
+    }
     cudaEventRecord(sc->ev_fork, s);
-    for (int i = 0; i < PART_SIDE_STREAMS; i++) { cudaStreamWaitEvent(sc->side[i], sc->ev_fork, 0); ls[1 + i] = sc->side[i]; }
+    for (int i = 0; i < n_side; i++) cudaStreamWaitEvent(sc->side[i], sc->ev_fork, 0);
   }
-#define BGYM_LAUNCH_LIST(L) env_step_list_kernel<L><<<lgrid(L), gt, list_smem_bytes(L), ls[L]>>>(a); if (timing == 2) cudaEventRecord(tev[2 + L], s);
-  BGYM_LAUNCH_LIST(L_PLAY) BGYM_LAUNCH_LIST(L_CONS) BGYM_LAUNCH_LIST(L_GEN) BGYM_LAUNCH_LIST(L_MISC)
-  BGYM_LAUNCH_LIST(L_DISCARD) BGYM_LAUNCH_LIST(L_SHOP) BGYM_LAUNCH_LIST(L_BLIND)
+  for (int q = 0; q < N_LISTS_L1; q++) {
+    const int l = fork ? plan_order[q] - '0' : q;
+    switch (l) {
+#define BGYM_LAUNCH_LIST(L) case L: env_step_list_kernel<L><<<lgrid(L), gt, list_smem_bytes(L), ls[L]>>>(a); if (timing == 2) cudaEventRecord(tev[2 + L], s); break;
+      BGYM_LAUNCH_LIST(L_PLAY) BGYM_LAUNCH_LIST(L_CONS) BGYM_LAUNCH_LIST(L_GEN) BGYM_LAUNCH_LIST(L_MISC)
+      BGYM_LAUNCH_LIST(L_DISCARD) BGYM_LAUNCH_LIST(L_SHOP) BGYM_LAUNCH_LIST(L_BLIND)
+#undef BGYM_LAUNCH_LIST
+      default: break;
+    }
+  }
   if (fork)
-    for (int i = 0; i < PART_SIDE_STREAMS; i++) { cudaEventRecord(sc->ev_side[i], sc->side[i]); cudaStreamWaitEvent(s, sc->ev_side[i], 0); }
+    for (int i = 0; i < n_side; i++) { cudaEventRecord(sc->ev_side[i], sc->side[i]); cudaStreamWaitEvent(s, sc->ev_side[i], 0); }
   if (timing == 1) cudaEventRecord(tev[2], s);
   if ((level_kernels & 1) && timing != 2) {
     env_step_level_kernel<2><<<g_sm_count * level_ctas(2), 32, 32 * BGYM_COLD_BYTES, s>>>(a);
   } else {
     if (fork) { cudaEventRecord(sc->ev_fork2, s); cudaStreamWaitEvent(sc->side[0], sc->ev_fork2, 0); ls[L_RESET] = sc->side[0]; }
-    BGYM_LAUNCH_LIST(L_ADVANCE) BGYM_LAUNCH_LIST(L_RESET)
+    env_step_list_kernel<L_ADVANCE><<<lgrid(L_ADVANCE), gt, list_smem_bytes(L_ADVANCE), s>>>(a); if (timing == 2) cudaEventRecord(tev[2 + L_ADVANCE], s);
+    env_step_list_kernel<L_RESET><<<lgrid(L_RESET), gt, list_smem_bytes(L_RESET), ls[L_RESET]>>>(a); if (timing == 2) cudaEventRecord(tev[2 + L_RESET], s);
     if (fork) { cudaEventRecord(sc->ev_side[0], sc->side[0]); cudaStreamWaitEvent(s, sc->ev_side[0], 0); }
   }
-#undef BGYM_LAUNCH_LIST
   if (timing == 1) cudaEventRecord(tev[3], s);
 #ifdef BGYM_TILE_CLOCK
   {
