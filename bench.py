@@ -292,7 +292,7 @@ def run_ours(args):
         ev[1 + 2 * k].record()          # step kernel bracket (same stream as the launches)
         env.step(acts[k], want_info=False)
         ev[2 + 2 * k].record()
-        launches += 11  # sampler + main pass + seven level-1 list kernels + two level-2 list kernels
+        launches += 10  # sampler + main pass + seven level-1 list kernels + the level-2 kernel (round advances and resets)
     ev[2 * K + 1].record()
     torch.cuda.synchronize(dev)
     bdist.barrier()
@@ -422,7 +422,7 @@ def run_ours(args):
                                   "bytes the launches really move (ncu) / kernel_ms / peak",
                      "traffic": traffic, "frac_physical": frac_physical, "traffic_provenance": traffic_prov,
                      "traffic_unit": "dram__bytes_read.sum + dram__bytes_write.sum over the launches of one env-step (ncu --set full)",
-                     "kernel": "one env-step = env_step_main_kernel + 9 env_step_list_kernel launches (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
+                     "kernel": "one env-step = env_step_main_kernel + 7 env_step_list_kernel launches + env_step_level_kernel<2> (all launches of the step are inside the timed bracket)", "bytes_per_unit": B_STEP,
                      "units_per_launch": n, "kernel_ms": step_kernel_ms_max, "peak_source": peak_src,
                      "physical_bytes_per_unit": "main pass 32 (toggle record) + 4 (action) read, 32 + 16 (selection record) + 10 written = 94 B per env; list kernels add the hot / toggle / cold / obs records of the ~25 % deferred envs at 64-byte DRAM granularity"},
         "timed_window": {"start": window_start, "end": window_end, "action_mix": action_mix, "phase_mix": phase_mix,
@@ -647,7 +647,7 @@ def bench_hands_jokers(torch, dev, peak):
     return {"value": n / (ms / 1e3), "unit": "hands/s", "n_hands": n, "ms_per_launch": ms,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_unit": 64,
                          "kernel": "score_hands_kernel (joker interpreter)",
-                         "note": "bound by divergent interpretation (12 of 32 lanes active), not by HBM"}}
+                         "note": "bound by instruction issue of a divergent interpreter (per-lane card counts; see profiles/r02_ncu_summary.md for active lanes per instruction), not by HBM"}}
 
 
 def main():
