@@ -8,5 +8,5 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; 
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 python bench.py --steps 200 --warmup 20 > gpurun_out/bench.json 2> gpurun_out/bench.err; python -c "
 import json; d=json.load(open('gpurun_out/bench.json')); r=json.load(open('gpurun_out/bench_reference.json')); print('value %.3e frac %.3f kernel_ms %.3f fused %.3e e2e %.3e hands %.3e ppo %.3e (policy %.3f ms, library %.3f ms) | reference arm %.3e on %s cores' % (d['value'], d['roofline']['frac'], d['roofline']['kernel_ms'], d['fused_rollout']['value'], d['e2e']['value'], d['hands']['value'], d['ppo_rollout']['value'], d['ppo_rollout']['breakdown_ms']['policy_forward_fused_tcgen05'], d['ppo_rollout']['policy_forward_library_gemms_ms'], r['value'], r['cpu_baseline']['cores']))" || tail -5 gpurun_out/bench.err
-tools/gpu_prof_small.sh
+# tools/gpu_prof_small.sh   (run separately)
 ls gpurun_out | wc -l
