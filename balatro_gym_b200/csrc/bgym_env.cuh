@@ -511,6 +511,7 @@ __device__ __noinline__ int immolate_sample(const Hot& h, const uint8_t* hotrec,
 __device__ __forceinline__ void immolate_compact(uint64_t removed, Hot& h, uint8_t* hotrec, uint8_t* rec, int lane) {
   uint32_t need = __ballot_sync(0xffffffffu, removed != 0);
   if (!need) return;
+  __syncwarp();     // the lane's own accesses to its records are ordered before the warp reads and rewrites them
   const unsigned long long my_rec = reinterpret_cast<unsigned long long>(rec), my_hot = reinterpret_cast<unsigned long long>(hotrec);
   while (need) {
     const int src = __ffs(need) - 1;
@@ -858,6 +859,7 @@ __device__ __forceinline__ void reset_blocks_prepare(uint8_t* rec_of_src, uint32
 __device__ __forceinline__ void autoreset_warp(bool want_reset, uint32_t new_seed, uint8_t* my_rec, int lane, bool gen) {
   uint32_t rmask = __ballot_sync(0xffffffffu, want_reset);
   if (!rmask) return;
+  __syncwarp();     // a lane's own writes to its record (the step it just ran) are ordered before the warp rewrites that record
   unsigned long long my_ptr = reinterpret_cast<unsigned long long>(my_rec);
   uint32_t m = rmask;
   while (m) {

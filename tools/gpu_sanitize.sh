@@ -9,3 +9,13 @@ done
 timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_parity.py tests/test_gpu_rollout.py -x -q -m gpu \
   -k "ragged or empty or sampler or known or host_buffer or replayed or featurize or gae or masked or side_arrays or fused_policy_forward_matches or first_layer" > gpurun_out/sanitize_memcheck_tests.log 2>&1
 echo "== memcheck tests rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitize_memcheck_tests.log | tail -3
+# the warp-cooperative paths (Immolate's compaction, the consumable tile's re-convergence, the joker interpreter's warp-made
+# rolls) need consumables in play: the c4 generator soak on both launch structures, and the hands-vs-oracle test
+for tool in memcheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/soak_parity.py --envs 2048 --steps 48 > gpurun_out/sanitize_${tool}_soak.log 2>&1
+  echo "== $tool soak (multi-pass) rc=$?"; grep -E "ERROR SUMMARY|mismatches" gpurun_out/sanitize_${tool}_soak.log | cut -c1-160 | tail -2
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/soak_parity.py --envs 1024 --steps 48 --one-launch > gpurun_out/sanitize_${tool}_soak1.log 2>&1
+  echo "== $tool soak (one launch) rc=$?"; grep -E "ERROR SUMMARY|mismatches" gpurun_out/sanitize_${tool}_soak1.log | cut -c1-160 | tail -2
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "score_hands_cuda_vs_oracle or score_hands_replayed" > gpurun_out/sanitize_${tool}_hands.log 2>&1
+  echo "== $tool hands rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitize_${tool}_hands.log | tail -2
+done
