@@ -780,6 +780,7 @@ static bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintp
 #define BGYM_L1_PLAN_STREAMS "0121230"
 #define BGYM_L1_PLAN_STREAMS_FUSED "0123456"
 #define BGYM_L1_PLAN_ORDER "2105463"
+#define BGYM_L1_PLAN_ORDER_FUSED "2105463"
 constexpr int PART_SIDE_STREAMS = 6;   // the seven level-1 list kernels run concurrently: launch stream + six forked ones
 struct PartScratch { bool used; int dev; void* stream; long long cap; int* lists; int* counters; uint16_t* aux;
 
@@ -939,10 +940,12 @@ int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, cons
   static const char* plan_streams_env = getenv("BGYM_L1_STREAMS");
   static const char* plan_order_env = getenv("BGYM_L1_ORDER");
   static const char* plan_streams_f_env = getenv("BGYM_L1_STREAMS_FUSED");
+  static const char* plan_order_f_env = getenv("BGYM_L1_ORDER_FUSED");
   const bool fusedp = (flags & BGYM_FLAG_RANDOM_POLICY) != 0;
   const char* plan_streams = fusedp ? (plan_streams_f_env ? plan_streams_f_env : BGYM_L1_PLAN_STREAMS_FUSED)
                                     : (plan_streams_env ? plan_streams_env : BGYM_L1_PLAN_STREAMS);
-  const char* plan_order = plan_order_env ? plan_order_env : BGYM_L1_PLAN_ORDER;
+  const char* plan_order = fusedp ? (plan_order_f_env ? plan_order_f_env : BGYM_L1_PLAN_ORDER_FUSED)
+                                  : (plan_order_env ? plan_order_env : BGYM_L1_PLAN_ORDER);
   int n_side = 0;
   if (fork) {
     for (int l = 0; l < N_LISTS_L1; l++) {
