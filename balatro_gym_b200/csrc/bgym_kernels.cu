@@ -919,8 +919,8 @@ int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, cons
   // BGYM_LEVEL_KERNELS (bit 0: level 2, bit 1: level 1): one kernel per level on the launch stream
   // (env_step_level_kernel) instead of one per list on forked streams
   // Measured (tools/exp/level_kernels.sh): level 2 as one kernel 0.1841 -> 0.1830 ms per step (one launch instead of a
-  // fork, two launches and a join) — the default; level 1 as one kernel 0.218 ms (255 registers and 2 KB of spills: the
-  // compiler keeps state of all seven bodies alive across the switch).
+  // fork, two launches and a join) — the default; level 1 as one kernel with out-of-line bodies and claimed tiles 0.197 ms
+  // against 0.177 (inlined bodies: 0.218 ms, 255 registers and 2 KB of spills).
   static const int level_kernels = getenv("BGYM_LEVEL_KERNELS") ? atoi(getenv("BGYM_LEVEL_KERNELS")) : 1;
   if ((level_kernels & 2) && !timing) {
     env_step_level_kernel<1><<<g_sm_count * level_ctas(1), 32, 0, s>>>(a);

@@ -510,17 +510,28 @@ __device__ __forceinline__ void list_tile(const StepArgs& a, long long e, bool a
 // tile functions: 2 KB stack frames, see profiles/r02_step_experiments.md #1; here the bodies are inlined and the kernel
 // takes the largest body's registers.)
 #ifndef BGYM_L1K_CTAS
-#define BGYM_L1K_CTAS 8        // the level-1 kernel needs ~200 registers to hold every list's body without spills
+#define BGYM_L1K_CTAS GATHER_CTAS_PER_SM
 #endif
 __host__ __device__ constexpr int level_ctas(int level) { return level == 1 ? BGYM_L1K_CTAS : GATHER_CTAS_PER_SM; }
+// out-of-line tile bodies for the level-1 kernel: each keeps its own register allocation (inlined into one kernel the seven
+// bodies needed 255 registers and 2 KB of spills); the arguments stay where they are — `a` is a __grid_constant__ parameter,
+// a reference to it is a pointer into the constant bank, not a copy on the stack
+template <int LIST>
+__device__ __noinline__ void list_tile_ool(const StepArgs& a, long long e, bool active, int lane, uint8_t* cold_slot) {
+  list_tile<LIST>(a, e, active, lane, cold_slot);
+}
+constexpr int PART_CLAIM_CTR = L_MISC * PART_CTR_STRIDE + 24;    // spare word of the counter block: next unclaimed tile of the level
 template <int LEVEL>
 __global__ void __launch_bounds__(32, level_ctas(LEVEL)) env_step_level_kernel(const __grid_constant__ StepArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   uint8_t* cold_slot = smem + lane * BGYM_COLD_BYTES;
   constexpr int NL = LEVEL == 1 ? N_LISTS_L1 : 2;
-  // walk order: long tiles first, so that the level ends on short ones
-  const int order[7] = {LEVEL == 1 ? (int)L_CONS : (int)L_RESET, LEVEL == 1 ? (int)L_GEN : (int)L_ADVANCE, L_PLAY, L_SHOP, L_DISCARD, L_BLIND, L_MISC};
+  // walk order: long tiles first, so that the level ends on short ones (with the fused policy MISC holds every env outside
+  // PLAY phase and goes first)
+  const bool fused = LEVEL == 1 && (a.flags & BGYM_FLAG_RANDOM_POLICY) != 0;
+  const int order[7] = {LEVEL == 1 ? (fused ? (int)L_MISC : (int)L_GEN) : (int)L_RESET, LEVEL == 1 ? (int)L_CONS : (int)L_ADVANCE, L_PLAY, L_SHOP, L_DISCARD,
+                        L_BLIND, fused ? (int)L_GEN : (int)L_MISC};
   int cnt[NL], first[NL + 1];
   first[0] = 0;
 #pragma unroll
@@ -528,7 +539,12 @@ __global__ void __launch_bounds__(32, level_ctas(LEVEL)) env_step_level_kernel(c
     cnt[k] = a.part_counters[order[k] * PART_CTR_STRIDE];
     first[k + 1] = first[k] + ((cnt[k] + 31) >> 5);
   }
-  for (int t = blockIdx.x; t < first[NL]; t += gridDim.x) {
+  // level 1: tiles are CLAIMED (first one = blockIdx.x, the next ones from a counter; the claim for the tile after this one is
+  // in flight while this one is served), so that a warp that drew short tiles takes more of them; level 2: static walk
+  int t = blockIdx.x, t_next = 0;
+  auto claim = [&]() { if (LEVEL == 1 && lane == 0) t_next = (int)gridDim.x + atomicAdd(a.part_counters + PART_CLAIM_CTR, 1); };
+  claim();
+  while (t < first[NL]) {
     int k = 0;
 #pragma unroll
     for (int q = 1; q < NL; q++) k += t >= first[q];
@@ -540,17 +556,20 @@ __global__ void __launch_bounds__(32, level_ctas(LEVEL)) env_step_level_kernel(c
     const long long e = active ? (long long)__ldcg(a.part_lists + (long long)list_id * a.part_cap + idx) : -1;
     if (LEVEL == 1) {
       switch (list_id) {
-        case L_PLAY: list_tile<L_PLAY>(a, e, active, lane, cold_slot); break;
-        case L_CONS: list_tile<L_CONS>(a, e, active, lane, cold_slot); break;
-        case L_GEN: list_tile<L_GEN>(a, e, active, lane, cold_slot); break;
-        case L_MISC: list_tile<L_MISC>(a, e, active, lane, cold_slot); break;
-        case L_DISCARD: list_tile<L_DISCARD>(a, e, active, lane, cold_slot); break;
-        case L_SHOP: list_tile<L_SHOP>(a, e, active, lane, cold_slot); break;
-        default: list_tile<L_BLIND>(a, e, active, lane, cold_slot); break;
+        case L_PLAY: list_tile_ool<L_PLAY>(a, e, active, lane, cold_slot); break;
+        case L_CONS: list_tile_ool<L_CONS>(a, e, active, lane, cold_slot); break;
+        case L_GEN: list_tile_ool<L_GEN>(a, e, active, lane, cold_slot); break;
+        case L_MISC: list_tile_ool<L_MISC>(a, e, active, lane, cold_slot); break;
+        case L_DISCARD: list_tile_ool<L_DISCARD>(a, e, active, lane, cold_slot); break;
+        case L_SHOP: list_tile_ool<L_SHOP>(a, e, active, lane, cold_slot); break;
+        default: list_tile_ool<L_BLIND>(a, e, active, lane, cold_slot); break;
       }
+      t = __shfl_sync(0xffffffffu, t_next, 0);
+      claim();
     } else {
       if (list_id == L_ADVANCE) list_tile<L_ADVANCE>(a, e, active, lane, cold_slot);
       else list_tile<L_RESET>(a, e, active, lane, cold_slot);
+      t += gridDim.x;
     }
   }
 }
