@@ -250,11 +250,14 @@ __device__ __forceinline__ int shuffle_j_from_block(uint4 b, int i) {
 // x / y for y > 0 and x >= 0 where x is often exactly zero (progress of a round that has just begun, a score of 0):
 // the fp64 division's fast path does not take a zero numerator — every such lane went through the ~60-instruction
 // out-of-line path, one small group of lanes at a time (ncu: 5.6 % of the PLAY list kernel's instructions)
-// (a branch around the division is folded back into an unconditional one by the compiler, slow path included: the
-// zero numerator is replaced by the denominator instead — y / y takes the fast path — and the quotient by zero)
+// (a branch around the division is folded back into an unconditional one by the compiler, slow path included, and so is
+// a plain select: the zero numerator is replaced by the denominator behind an empty asm — y / y takes the fast path —
+// and the quotient by zero)
 __device__ __forceinline__ double div_nz(double x, double y) {
   const bool nz = x != 0.0;
-  const double q = (nz ? x : y) / y;
+  double xs = nz ? x : y;
+  asm volatile("" : "+d"(xs));      // opaque to the optimiser, which otherwise proves the select away and divides x again
+  const double q = xs / y;
   return nz ? q : 0.0;
 }
 
