@@ -466,7 +466,7 @@ class HostMirror:
     observation, reward, terminated.  A step rewrites the 176-byte observation record only of the envs whose action was
     not a card toggle (include/bgym.h, BgymSel), so per step this class moves
         host -> device   actions                                                                4 B / env
-        device -> host   selection records (selected_cards, mask word), reward, terminated      16 + 8 + 1 B / env
+        device -> host   selection (8 selected_cards flags as ONE byte, mask word), reward, terminated  1 + 8 + 8 + 1 B / env
         device -> host   the rewritten observation records, packed on the device (bgym_pack_dirty_obs) and written
                          into the pinned mirror by the GPU itself (bgym_scatter_dirty_obs, zero-copy stores, one
                          aligned 128-byte line per record + 32 B for envs in or entering the shop)   128 (+32) B / changed env
@@ -476,11 +476,13 @@ class HostMirror:
         mirror = HostMirror(env); env.reset(); mirror.pull_all()
         mirror.actions[:] = ...                      # host policy writes this step's actions
         mirror.step()                                # H2D, step, D2H deltas (asynchronous)
-        mirror.wait(); mirror.core / .shop / .sel / .reward / .terminated are current
+        mirror.wait(); mirror.core / .shop / .sel_bits / .mask_words / .reward / .terminated are current
 
     Layout of the mirror (include/bgym.h): `core` [n, 128] = chunks 0..5, 8, 9 of the observation record, `shop` [n, 32]
-    = chunks 6, 7, `sel` [n, 16] = selected_cards + mask word.  `obs_records()` reassembles whole L.OBS_DTYPE records
-    (a host-side copy); `field(name)` gives a zero-copy view of one observation field."""
+    = chunks 6, 7; the selection record travels packed — `sel_bits` [n] uint8 (bit i = selected_cards[i]) and `mask_words`
+    [n] int64 (the legal-action word) — 9 B instead of 16 B per env and step: like `action_mask`, `selected_cards` is
+    expanded on access (`field('selected_cards')`, `sel`).  `obs_records()` reassembles whole L.OBS_DTYPE records (a
+    host-side copy); `field(name)` gives a zero-copy view of one observation field where the mirror stores it as such."""
 
     def __init__(self, env: "BalatroVecEnv"):
         torch = env.torch
@@ -490,7 +492,8 @@ class HostMirror:
         self.actions = torch.zeros(n, dtype=torch.int32, **pin)
         self.core = torch.zeros((n, L.MIRROR_CORE_BYTES), dtype=torch.uint8, **pin)
         self.shop = torch.zeros((n, L.MIRROR_SHOP_BYTES), dtype=torch.uint8, **pin)
-        self.sel = torch.zeros((n, L.SEL_BYTES), dtype=torch.uint8, **pin)
+        self.sel_bits = torch.zeros(n, dtype=torch.uint8, **pin)
+        self.mask_words = torch.zeros(n, dtype=torch.int64, **pin)
         self.reward = torch.zeros(n, dtype=torch.float64, **pin)
         self.terminated = torch.zeros(n, dtype=torch.uint8, **pin)
         self._d_act = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -499,14 +502,35 @@ class HostMirror:
         self._scratch = torch.zeros((n + 4095) // 4096 + 4, dtype=torch.int32, device=dev)
         self.staging_bytes = 16 + ((n * 4 + 15) & ~15) + n * L.OBS_DELTA_BYTES
         self._snap = [{"staging": torch.zeros(self.staging_bytes, dtype=torch.uint8, device=dev),
-                       "sel": torch.empty_like(env.sel), "rew": torch.empty_like(env.reward),
-                       "term": torch.empty_like(env.terminated)} for _ in range(2)]
+                       "selbits": torch.empty(n, dtype=torch.uint8, device=dev), "maskw": torch.empty(n, dtype=torch.int64, device=dev),
+                       "rew": torch.empty_like(env.reward), "term": torch.empty_like(env.terminated)} for _ in range(2)]
+        self._prod = torch.empty(n, dtype=torch.int64, device=dev)
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._ready = [torch.cuda.Event() for _ in range(2)]
         self._copied = [torch.cuda.Event() for _ in range(2)]
         self._t = 0
         self.h2d_bytes_per_step = 4 * n
-        self.dense_d2h_bytes_per_step = (L.SEL_BYTES + 8 + 1) * n
+        self.dense_d2h_bytes_per_step = (1 + 8 + 8 + 1) * n
+
+    # eight 0/1 bytes b0..b7 of a little-endian int64 -> the byte sum(b_i << i): the product with this constant puts b_i at
+    # bit 56 + i (no two partial products share a bit, so nothing carries), i.e. the answer is the product's top byte
+    _GATHER_BITS = 0x0102040810204080
+
+    def _pack_sel(self, snap):
+        """Selection records (16 B: selected_cards[8] | mask word) -> one byte of flags + the word, on the current stream."""
+        n = self.env.num_envs
+        selv = self.env.sel.view(self.torch.int64)              # [n, 2]
+        self.torch.mul(selv[:, 0], self._GATHER_BITS, out=self._prod)
+        snap["selbits"].copy_(self._prod.view(self.torch.uint8).view(n, 8)[:, 7], non_blocking=True)
+        snap["maskw"].copy_(selv[:, 1], non_blocking=True)
+
+    @property
+    def sel(self) -> np.ndarray:
+        """The selection records as the device keeps them (L.SEL_DTYPE), expanded from the packed mirror: a host-side copy."""
+        out = np.zeros(self.env.num_envs, dtype=L.SEL_DTYPE)
+        out["selected_cards"] = np.unpackbits(self.sel_bits.numpy()[:, None], axis=1, bitorder="little")
+        out["action_mask_bits"] = self.mask_words.numpy().view(out["action_mask_bits"].dtype)
+        return out
 
     def _pack(self, snap, stream, everything: bool):
         env = self.env
@@ -531,7 +555,9 @@ class HostMirror:
         self._pack(self._snap[0], main, True)
         self._scatter(self._snap[0], main)
         env.obs_dirty.zero_()
-        self.sel.copy_(env.sel, non_blocking=True)
+        self._pack_sel(self._snap[0])
+        self.sel_bits.copy_(self._snap[0]["selbits"], non_blocking=True)
+        self.mask_words.copy_(self._snap[0]["maskw"], non_blocking=True)
         self.reward.copy_(env.reward, non_blocking=True)
         self.terminated.copy_(env.terminated, non_blocking=True)
         main.synchronize()
@@ -546,14 +572,15 @@ class HostMirror:
         env.step(self._d_act, want_info=want_info)
         main.wait_event(self._copied[b])                       # the snapshot's previous contents have left the device
         self._pack(snap, main, False)
-        snap["sel"].copy_(env.sel, non_blocking=True)
+        self._pack_sel(snap)
         snap["rew"].copy_(env.reward, non_blocking=True)
         snap["term"].copy_(env.terminated, non_blocking=True)
         self._ready[b].record(main)
         cs = self._copy_stream
         with torch.cuda.stream(cs):
             cs.wait_event(self._ready[b])
-            self.sel.copy_(snap["sel"], non_blocking=True)
+            self.sel_bits.copy_(snap["selbits"], non_blocking=True)
+            self.mask_words.copy_(snap["maskw"], non_blocking=True)
             self.reward.copy_(snap["rew"], non_blocking=True)
             self.terminated.copy_(snap["term"], non_blocking=True)
             self._scatter(snap, cs)
@@ -583,18 +610,21 @@ class HostMirror:
         raw[:, list(L.MIRROR_CORE_CHUNKS)] = core
         raw[:, list(L.MIRROR_SHOP_CHUNKS)] = shop
         rec = raw.reshape(n, L.OBS_BYTES).reshape(-1).view(L.OBS_DTYPE)
-        s = self.sel.numpy().reshape(-1).view(L.SEL_DTYPE)
+        s = self.sel
         rec["selected_cards"] = s["selected_cards"]
         rec["action_mask_bits"] = s["action_mask_bits"]
         return rec
 
     def field(self, name):
         """numpy view of one observation field in the mirror: zero-copy for every field but shop_items / shop_costs (they
-        straddle the core / shop split: assembled copy) and 'action_mask' (expanded from the mask word)."""
+        straddle the core / shop split: assembled copy), 'action_mask' (expanded from the mask word) and 'selected_cards'
+        (expanded from the flag byte)."""
         if name == "action_mask":
             return L.mask_from_bits(self.field("action_mask_bits"))
-        if name in L.SEL_DTYPE.names:
-            return self.sel.numpy().reshape(-1).view(L.SEL_DTYPE)[name]
+        if name == "action_mask_bits":
+            return self.mask_words.numpy().view(L.SEL_DTYPE.fields["action_mask_bits"][0])
+        if name == "selected_cards":
+            return np.unpackbits(self.sel_bits.numpy()[:, None], axis=1, bitorder="little").view(L.SEL_DTYPE.fields["selected_cards"][0].base)
         if name in L.MIRROR_CORE_DTYPE.names:
             return self.core.numpy().reshape(-1).view(L.MIRROR_CORE_DTYPE)[name]
         return self.obs_records()[name]

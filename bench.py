@@ -351,7 +351,7 @@ def run_ours(args):
 
     # ---- e2e: the public API with HOST buffers (pinned), copies inside the timed region ----
     # balatro_gym_b200.HostMirror: every step this step's actions come from pinned host memory (H2D) and the step's
-    # results reach pinned host memory (D2H): reward, terminated and the selection records (selected_cards, mask word)
+    # results reach pinned host memory (D2H): reward, terminated and the selection records (selected_cards as one flag byte, mask word)
     # of every env, and the 176-byte observation record of every env whose record the step rewrote (an env whose
     # action was a card toggle keeps its record) — packed on the device and written into the host mirror by the GPU.
     # The copies of step t run on a second stream while step t+1 is launched; the action path is synchronous.  The
@@ -435,7 +435,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": e2e_d2h,
                 "steps": Ke, "pcie_gbs_rank0": e2e_rank_gbs, "host_memory": numa, "rewritten_record_frac": dirty_frac, "shop_chunk_frac": shop_frac,
                 "whole_array_d2h_bytes_per_step": (L.OBS_BYTES + 8 + 1 + 4) * n,
-                "note": "HostMirror: reward + terminated + selection record (25 B) of every env and the observation record "
+                "note": "HostMirror: reward + terminated + packed selection (flag byte + mask word: 18 B) of every env and the observation record "
                         "(one aligned 128-byte line, + 32 B of shop chunks where they can have changed) of every env whose record the step "
                         "rewrote reach pinned host memory each step, written by the GPU itself (zero-copy stores); the mirror is "
                         "checked against the device arrays after the timed region; bound by the PCIe link"},
