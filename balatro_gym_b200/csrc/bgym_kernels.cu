@@ -817,6 +817,19 @@ static int get_part_scratch(long long n, void* stream, PartScratch** out) {
   return 0;
 }
 
+// a launch-plan override (bgym_step): seven digits 0..6, as an order each exactly once; anything else -> nullptr (ignored)
+static const char* valid_plan(const char* v, bool permutation) {
+  if (!v || strlen(v) != (size_t)N_LISTS_L1) return nullptr;
+  int seen = 0;
+  for (int i = 0; i < N_LISTS_L1; i++) {
+    const int k = v[i] - '0';
+    if (k < 0 || k > PART_SIDE_STREAMS) return nullptr;
+    seen |= 1 << k;
+  }
+  if (permutation && seen != (1 << N_LISTS_L1) - 1) return nullptr;
+  return v;
+}
+
 static int tile_grid(long long n, int warps, int ctas_per_sm) {
   long long tiles = (n + 31) / 32;
   long long ctas = (tiles + warps - 1) / warps;
@@ -937,10 +950,12 @@ int bgym_step(BgymHot* hot, BgymTog* tog, BgymCold* cold, int32_t* actions, cons
   // puts the lists with long tiles at the head of the streams and chains the lists with short tiles behind them, so that
   // the level ends on short tiles.  BGYM_L1_STREAMS / BGYM_L1_ORDER (7 digits each, indexed / listing PLAY CONS GEN MISC
   // DISCARD SHOP BLIND = 0..6) override it; with the fused policy every env outside PLAY phase is in MISC.
-  static const char* plan_streams_env = getenv("BGYM_L1_STREAMS");
-  static const char* plan_order_env = getenv("BGYM_L1_ORDER");
-  static const char* plan_streams_f_env = getenv("BGYM_L1_STREAMS_FUSED");
-  static const char* plan_order_f_env = getenv("BGYM_L1_ORDER_FUSED");
+  // (an override that is not seven digits — streams 0..6, order a permutation of 0..6 — is ignored: a list that is never
+  // launched would leave its envs unstepped)
+  static const char* plan_streams_env = valid_plan(getenv("BGYM_L1_STREAMS"), false);
+  static const char* plan_order_env = valid_plan(getenv("BGYM_L1_ORDER"), true);
+  static const char* plan_streams_f_env = valid_plan(getenv("BGYM_L1_STREAMS_FUSED"), false);
+  static const char* plan_order_f_env = valid_plan(getenv("BGYM_L1_ORDER_FUSED"), true);
   const bool fusedp = (flags & BGYM_FLAG_RANDOM_POLICY) != 0;
   const char* plan_streams = fusedp ? (plan_streams_f_env ? plan_streams_f_env : BGYM_L1_PLAN_STREAMS_FUSED)
                                     : (plan_streams_env ? plan_streams_env : BGYM_L1_PLAN_STREAMS);
