@@ -13,14 +13,18 @@
 //                                of envs in PLAY phase — writing back the toggle record and the 16-byte selection record
 //                                (BgymSel: selected_cards + mask word), 94 B per env in all — and appends every other env to
 //                                ONE OF SEVEN lists by the path its action takes (staged per warp, one atomic per run of
-//                                >= 32).  Hot, cold and observation records are never touched.
-//   level-1 pass   (7 launches)  one kernel per list, concurrent on forked streams: each lane serves ONE listed env — hot +
+//                                ~100).  Hot, cold and observation records are never touched.
+//   level-1 pass   (7 launches)  one kernel per list, on forked streams by a launch plan (bgym_step: long-tile lists head the
+//                                streams, short-tile lists are chained behind them): each lane serves ONE listed env — hot +
 //                                toggle record lifted into registers, cold record read in place —, runs that list's path (step_env<CATS> compiles only the list's
 //                                branches), pushes hot (+ cold) + observation back.  Two long paths are NOT run here
 //                                but handed on, again as lists: the round advance of a hand that beat the blind, and
 //                                the in-place reset of a terminated env.
-//   level-2 pass   (2 launches)  tiles of envs that advance a round (continuing the step's draw sequence where level 1
-//                                left it) and tiles of envs that are reset (32 fresh decks shuffled side by side).
+//   level-2 pass   (1 launch)    env_step_level_kernel<2>: tiles of envs that are reset (32 fresh decks shuffled side by side)
+//                                and tiles of envs that advance a round (continuing the step's draw sequence where level 1
+//                                left it).
+//   Inside a tile, work that one lane would do alone is done by the warp (Immolate's deck compaction, the in-tile
+//   autoreset) or by all lanes that need it at one converged point (a played hand's rolls, the consumables' bookkeeping).
 //
 //   small slabs (n <= 65536)     one launch of the gather tile code over all envs with every category compiled in and
 //                                nothing deferred (env_step_small_kernel): such a step is launch- and latency-bound
