@@ -287,6 +287,19 @@ __device__ __forceinline__ int sel_find(uint32_t order, int n, int slot) {
   t &= n >= 8 ? 0xFFFFFFFFu : ((1u << (4 * n)) - 1u);
   return t ? (__ffs((int)t) - 1) >> 2 : -1;
 }
+// position of the k-th (0-based) set bit of m, k < popc(m): a branch-free binary search on popcounts (as a loop that
+// clears k low bits it ran to the largest k of the warp: the random policy's choice among ~10 legal actions)
+__device__ __forceinline__ int select_bit64(uint64_t m, int k) {
+  uint32_t w = (uint32_t)m;
+  int pos = 0, c = __popc(w);
+  if (k >= c) { k -= c; w = (uint32_t)(m >> 32); pos = 32; }
+#pragma unroll
+  for (int sh = 16; sh >= 1; sh >>= 1) {
+    c = __popc(w & ((1u << sh) - 1u));
+    if (k >= c) { k -= c; w >>= sh; pos += sh; }
+  }
+  return pos;
+}
 // 4 mask bits -> 4 bytes of 0/1
 __device__ __forceinline__ uint32_t spread4(uint32_t bits) { return ((bits & 0xF) * 0x00204081u) & 0x01010101u; }
 __device__ __forceinline__ uint64_t u64_of(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }

@@ -475,11 +475,6 @@ __device__ __forceinline__ void cons_pop(Hot& h, int idx) {
 // lane that has such a set): the list compaction, lane = deck position.  One lane walking the 52 positions alone was
 // 1 900 dependent warp-instructions that the other 31 lanes of the tile waited for (ncu: 19 % of the consumable list
 // kernel's instructions at 1.1 active lanes); the cooperative form is ~80.
-__device__ __forceinline__ int nth_set_bit64(uint64_t m, int p) {   // position of the p-th (0-based) set bit of m
-  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-  const int c = __popc(lo);
-  return p < c ? (int)__fns(lo, 0u, p + 1) : 32 + (int)__fns(hi, 0u, p - c + 1);
-}
 __device__ __noinline__ int immolate_sample(const Hot& h, const uint8_t* hotrec, const uint8_t* rec, Draws& rng, uint64_t* removed_out) {
   const int n = h.deck_n, n_ex = rec[OFF_EXTRA_N], n_orig = n - n_ex;
   const uint16_t* ex = reinterpret_cast<const uint16_t*>(hotrec + OFF_HOT_EXTRA);
@@ -491,7 +486,7 @@ __device__ __noinline__ int immolate_sample(const Hot& h, const uint8_t* hotrec,
     if (rng.tape) idx = rng.below(n);            // replay: population index recorded from the reference
     else {                                       // native: t-th element of a uniform sample without replacement
       int p = rng.below(n - t);
-      idx = nth_set_bit64(~sampled & ((n >= 64) ? ~0ull : ((1ull << n) - 1)), p);
+      idx = select_bit64(~sampled & ((n >= 64) ? ~0ull : ((1ull << n) - 1)), p);
     }
     sampled |= 1ull << idx;
     int victim = idx;

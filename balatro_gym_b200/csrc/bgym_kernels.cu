@@ -521,8 +521,7 @@ __global__ void sample_actions_kernel(const uint8_t* mask_words, long long mask_
     if (cnt) {
       uint4 w = philox4x32_10((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), (uint32_t)step, (uint32_t)(step >> 32), seed, BGYM_POLICY_KEY1);
       int k = (int)__umulhi(w.x, (uint32_t)cnt);
-      for (int t = 0; t < k; t++) m &= m - 1;
-      act = __ffsll((long long)m) - 1;
+      act = select_bit64(m, k);
     }
     actions[i] = act;
   }

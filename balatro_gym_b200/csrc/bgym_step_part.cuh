@@ -89,9 +89,7 @@ __device__ __forceinline__ int policy_action(const Hot& h, uint64_t mask) {
   if (!cnt) return 0;
   uint4 w = philox4x32_10(h.ep_len, 0, 0, 0, h.rng_seed, BGYM_POLICY_KEY1);
   int k = (int)__umulhi(w.x, (uint32_t)cnt);
-#pragma unroll 1
-  for (int i = 0; i < k; i++) mask &= mask - 1;
-  return __ffsll((long long)mask) - 1;
+  return select_bit64(mask, k);
 }
 
 // ------------------------------------------------------------------------------------------------
