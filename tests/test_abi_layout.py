@@ -165,3 +165,16 @@ def test_committed_ncu_traffic_matches_the_kernel_sources():
     assert d["source_hash"] == _lib.source_hash(), \
         "kernel sources changed since the ncu capture: run tools/gpu_prof_part.sh on the GPU box, then tools/ncu_summary.py --traffic-json"
     assert d["step"]["traffic_bytes"] > 0 and len(d["step"]["kernels"]) == 9      # main pass + seven list kernels + the level-2 kernel
+
+
+def test_host_mirror_flag_gather_constant():
+    """HostMirror packs the eight selected_cards flags of a selection record into one byte with a 64-bit multiply: the
+    product's top byte must be sum(flag_i << i) for every flag pattern (no carries between partial products)."""
+    import numpy as np
+    from balatro_gym_b200.vec_env import HostMirror
+    flags = ((np.arange(256)[:, None] >> np.arange(8)) & 1).astype(np.uint8)          # all 256 patterns, little-endian bytes
+    words = flags.view(np.uint64)[:, 0]
+    with np.errstate(over="ignore"):
+        top = ((words * np.uint64(HostMirror._GATHER_BITS)) >> np.uint64(56)).astype(np.uint8)
+    assert np.array_equal(top, np.arange(256, dtype=np.uint8))
+    assert np.array_equal(np.unpackbits(top[:, None], axis=1, bitorder="little"), flags)   # and the host-side expansion inverts it
