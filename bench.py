@@ -457,13 +457,14 @@ def run_ours(args):
 
 def bench_ppo_rollout(torch, bdist, dev, args, rank, ws):
     """configs[4]: PPO rollout collection with the policy on the device — 2^19 envs per GPU
-    (2^22 over 8), observations -> features -> MLP (bf16 autocast) -> masked categorical -> env step,
-    GAE at the end; nothing leaves the device.  Reported as whole-job env-steps/s, max over ranks."""
+    (2^22 over 8), every episode from the c4 state generator, observation records -> policy (one tcgen05 kernel) -> masked
+    categorical -> env step, GAE at the end; nothing leaves the device.  Reported as whole-job env-steps/s, max over ranks."""
     from balatro_gym_b200 import BalatroVecEnv
     from balatro_gym_b200.rollout import RolloutCollector, make_policy, featurize, masked_sample, gae
     n, T = args.ppo_envs, args.ppo_steps
-    vec = BalatroVecEnv(n, device=dev, seed=1, env_offset=rank * n)
-    vec.reset(); vec.randomize_c3(0)
+    # the same per-episode state generator as the headline loop (reset AND every in-kernel autoreset)
+    vec = BalatroVecEnv(n, device=dev, seed=1, env_offset=rank * n, generator="c4")
+    vec.reset()
     for _ in range(32):
         vec.step(random_policy=True)
     policy = make_policy(device=dev, seed=0)
